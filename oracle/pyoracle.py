@@ -52,15 +52,21 @@ def build_oracle():
 _libs = {}
 
 
-def oracle(depth=8):
-    """Load liboracle<depth>.so (building it if needed)."""
-    key = ("o", depth)
+def oracle(depth=8, emul=False):
+    """Load liboracle<depth>.so (building it if needed).  emul=True loads libcoreemul<depth>.so
+    instead: the same oracle plus emul_estimate(), the CPU emulation of the product's la_core.h
+    state machine (tests/core_emul.cpp)."""
+    key = ("e" if emul else "o", depth)
     if key in _libs:
         return _libs[key]
-    path = os.path.join(BUILD, "liboracle%d.so" % depth)
+    path = os.path.join(BUILD, ("libcoreemul%d.so" if emul else "liboracle%d.so") % depth)
     if not os.path.exists(path):
         build_oracle()
     L = C.CDLL(path)
+    if emul:
+        L.emul_estimate.restype = C.c_int64
+        L.emul_estimate.argtypes = [C.c_void_p, C.POINTER(Frame), C.POINTER(Frame), C.POINTER(Frame)] + [C.c_int] * 6 + \
+                                   [C.POINTER(Weight), C.POINTER(Weight)]
     L.ola_frame_create.restype = C.POINTER(Frame)
     L.ola_frame_create.argtypes = [C.c_int] * 6
     L.ola_frame_destroy.argtypes = [C.POINTER(Frame)]
@@ -317,11 +323,12 @@ class OracleReplay:
     checksums in it) with its own compiled C code; the oracle must reproduce all of them from the
     same synthetic input."""
 
-    def __init__(self, trace, use_trace_weights=False, keep=None):
+    def __init__(self, trace, use_trace_weights=False, keep=None, emul=False):
         self.t = trace
         cfg = trace.cfg
         self.depth = cfg["depth"]
-        self.lib = oracle(self.depth)
+        self.lib = oracle(self.depth, emul=emul)
+        self.estimate = self.lib.emul_estimate if emul else self.lib.ola_estimate
         self.ctx = self.lib.ola_ctx_create(cfg["bFrameBias"], cfg["numCoopSlices"], cfg["numRowsPerSlice"])
         self.frames = {}
         self.use_trace_weights = use_trace_weights
@@ -374,7 +381,7 @@ class OracleReplay:
         used = Weight()
         if self.use_trace_weights:
             wt = C.pointer(Weight(1 if j["wflag"] == 1 else 0, j["wscale"], j["wdenom"], j["woffset"]))
-        score = self.lib.ola_estimate(self.ctx, fenc.p, r0.p, r1.p, d0, d1, -1, -1, 0 if j["batch"] else 1,
+        score = self.estimate(self.ctx, fenc.p, r0.p, r1.p, d0, d1, -1, -1, 0 if j["batch"] else 1,
                                       cfg["weightp"], wt, C.byref(used))
         tag = "J%d/%d/%d." % (j["p0"], j["b"], j["p1"])
         want = j["costEst"] * 100 // (130 + cfg["bFrameBias"]) if d1 > 0 else j["costEst"]

@@ -755,6 +755,14 @@ void ola_intra_estimate(ola_frame* f, int lambda)
  * ---------------------------------------------------------------------------------------- */
 typedef struct ref_planes { pixel* plane[4]; intptr_t stride; } ref_planes;
 
+/* public wrapper used by tests/core_emul.cpp */
+static void lowres_mc(const ref_planes* r, intptr_t blockOffset, int qx, int qy, pixel* blk);
+void ola_lowres_mc(pixel* const planes[4], intptr_t stride, intptr_t blockOffset, int qx, int qy, pixel* blk)
+{
+    ref_planes r = { { planes[0], planes[1], planes[2], planes[3] }, stride };
+    lowres_mc(&r, blockOffset, qx, qy, blk);
+}
+
 /* fills blk[64] (stride 8) with the reference block for quarter-pel MV (qx,qy) */
 static void lowres_mc(const ref_planes* r, intptr_t blockOffset, int qx, int qy, pixel* blk)
 {

@@ -140,6 +140,7 @@ int64_t ola_estimate(ola_ctx* c, ola_frame* fenc, ola_frame* ref0, ola_frame* re
                      int search0, int search1, int sliced, int weightp, const ola_weight* weight, ola_weight* usedWeight);
 
 /* helpers for tests */
+void ola_lowres_mc(pixel* const planes[4], intptr_t stride, intptr_t blockOffset, int qx, int qy, pixel* blk);
 uint32_t ola_crc32(const void* p, size_t n);
 void ola_synth_frame(int w, int h, int t, int nframes, uint32_t seed, void* y, int ystride, void* u, void* v, int cstride);
 void ola_copy_picture(const pixel* src, int w, int h, pixel* dst, intptr_t dstStride);
