@@ -116,7 +116,7 @@ def build_depth(depth, jobs, cli):
     shim = os.path.join(OUT, "libx265ref%d.so" % depth)
     deps = [shim_src, lib, os.path.join(HERE, "ref_hooks.h"), os.path.join(HERE, "synth.h")]
     if os.path.exists(shim_src) and not newer(shim, *deps):
-        run(["g++"] + F + ["-shared", "-Wl,-Bsymbolic", shim_src, "-o", shim, "-Wl,--whole-archive", lib, "-Wl,--no-whole-archive",
+        run(["g++"] + F + ["-shared", shim_src, "-o", shim, "-Wl,--whole-archive", lib, "-Wl,--no-whole-archive",
                             "-lpthread", "-ldl", "-lm"])
 
     if cli:

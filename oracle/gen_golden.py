@@ -15,7 +15,7 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import pyoracle as po  # noqa: E402
 
-GOLD = os.path.join(os.path.dirname(po.HERE), "tests", "golden")
+GOLD = os.environ.get("X265LA_GOLDEN_DIR") or os.path.join(os.path.dirname(po.HERE), "tests", "golden")
 
 # name -> (depth, w, h, nframes, seed, pool threads, options, dump?)
 CASES = {
@@ -61,6 +61,9 @@ def main():
         print("%-10s %dx%d %d-bit %d frames: lookahead %.2fs (%.1f fps) wall %.1fs  %s  types=%s" %
               (name, w, h, depth, n, secs, n / secs, time.time() - t0, stats, "".join(" IiPbB"[t] if 0 <= t < 6 else "?" for t in types)))
         sys.stdout.flush()
+    # the reference's thread pool / static destructors do not survive interpreter teardown
+    # reliably; results are on disk, leave without running them
+    os._exit(0)
 
 
 if __name__ == "__main__":

@@ -269,6 +269,9 @@ class Trace:
                     self.cfg["aqStrength"] = float(t[1])
                     self.cfg["scenecut"] = int(t[2])
                     self.cfg["keyint"] = int(t[3])
+                elif k == "L":
+                    self.cfg["lutCrc"] = int(t[1], 16)
+                    self.cfg["lambda"] = int(t[2])
                 elif k == "P":
                     self.events.append(("P", dict(poc=int(t[1]), planes=int(t[2], 16), intraCost=int(t[3], 16),
                                                    intraMode=int(t[4], 16), lowresCosts=int(t[5], 16), rowSatds=int(t[6], 16),

@@ -103,7 +103,8 @@ extern "C" void x265ref_hook_pre(Frame* frame)
         fprintf(g_ts.trace, "P %d %08x %08x %08x %08x %08x %lld %lld %08x %llu %llu\n", l.frameNum, cPlanes, cIC, cIM, cLC, cRS,
                 (long long)l.costEst[0][0], (long long)l.costEstAq[0][0], cIQ,
                 (unsigned long long)l.wp_ssd[0], (unsigned long long)l.wp_sum[0]);
-        dumpArray("PLAN", l.frameNum, 0, 0, 0, l.buffer[0], 4 * planeBytes);
+        if (l.frameNum == 0)
+            dumpArray("PLAN", l.frameNum, 0, 0, 0, l.buffer[0], 4 * planeBytes);
         dumpArray("ICST", l.frameNum, 0, 0, 0, l.intraCost, n * sizeof(int32_t));
         dumpArray("IMOD", l.frameNum, 0, 0, 0, l.intraMode, n);
         dumpArray("LCST", l.frameNum, l.frameNum, l.frameNum, 0, l.lowresCosts[0][0], n * sizeof(uint16_t));
@@ -238,6 +239,8 @@ uint64_t x265ref_var8(const pixel* p, intptr_t s) { return primitives.cu[BLOCK_8
 void x265ref_propagate_cost(int* dst, const uint16_t* pin, const int32_t* intra, const uint16_t* inter, const int32_t* invq, const double* fps, int len)
 { primitives.propagateCost(dst, pin, intra, inter, invq, fps, len); }
 
+void x265ref_mvcost_table(uint16_t* out);
+int x265ref_lambda_int(void);
 int x265ref_lookahead_qp(void) { return X265_LOOKAHEAD_QP; }
 int x265ref_lambda_int(void) { return (int)x265_lambda_tab[X265_LOOKAHEAD_QP]; }
 /* copies LUT[-65536 .. 65536] (131073 entries) of BitCost::setQP(X265_LOOKAHEAD_QP), bitcost.cpp:31-59 */
@@ -321,6 +324,11 @@ double x265ref_run_lookahead(int width, int height, int nframes, uint32_t seed,
                 p->bframes, p->lookaheadDepth, p->bFrameAdaptive, p->bEnableWeightedPred, p->rc.aqMode, p->rc.cuTree,
                 la->m_numCoopSlices, la->m_numRowsPerSlice, p->bFrameBias, poolThreads);
         fprintf(g_ts.trace, "Q %.17g %d %d\n", p->rc.aqStrength, p->scenecutThreshold, p->keyframeMax);
+        {
+            std::vector<uint16_t> lut(4 * 32768 + 1);
+            x265ref_mvcost_table(&lut[0]);
+            fprintf(g_ts.trace, "L %08x %d\n", crc32(&lut[0], lut.size() * sizeof(uint16_t)), x265ref_lambda_int());
+        }
     }
 
     /* generate all input frames up front */

@@ -1,0 +1,784 @@
+/* x265cu.cu -- host side of libx265cu.so: context, device mirrors of `Lowres`, batching and the
+ * extern "C" entry points declared in include/x265cu.h.  No CPU fallback anywhere: every entry
+ * either runs its CUDA kernels or fails with an error code.
+ *
+ * HBM layout (one allocation per array family, sized at x265cu_open for numFrameSlots mirrors):
+ *   planes      [slot][4][planeSize]                padded lowres planes, layout of Lowres::buffer[0]
+ *   intraCost   [slot][nCU] i32      intraMode [slot][nCU] u8      invQ [slot][nCU] i32
+ *   lowresCosts [slot][bf+2][bf+2][nCU] u16         rowSatds [slot][bf+2][bf+2][hCU] i32
+ *   mvs         [slot][2][bf+1][nCU] (int16 x, int16 y)      mvCosts [slot][2][bf+1][nCU] i32
+ *   wplanes     pool of weighted 4-plane copies (one per weighted job of a batch)
+ * Results of a batch are also written to one packed device record per job and reach the host in a
+ * single device->host copy into pinned staging, from where they are scattered to the caller's
+ * Lowres arrays.
+ */
+#include "../../../include/x265cu.h"
+#include "x265cu_kernels.cuh"
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <mutex>
+#include <vector>
+
+namespace {
+
+char g_openError[512] = "";
+
+struct PendingEvent { int kind; cudaEvent_t a, b; };
+
+} // namespace
+
+struct x265cu_ctx
+{
+    x265cu_config cfg;
+    GeomDev g;
+    int pb;            /* bytes per sample */
+    int pixelMax;
+    int correction;    /* IF_INTERNAL_PREC - X265_DEPTH */
+    int bf;
+    cudaStream_t stream;
+    bool ownStream;
+    std::mutex mtx;
+    char err[512];
+
+    uint8_t* dPlanes;
+    int* dIntraCost;
+    uint8_t* dIntraMode;
+    int* dInvQ;
+    std::vector<char> hasInvQ;
+    uint16_t* dLowresCosts;
+    int* dRowSatds;
+    int* dMvs;
+    int* dMvCosts;
+    uint16_t* dLut;        /* base; centre at +65536 */
+    uint8_t* dSrc;         /* full-resolution luma staging */
+    int64_t srcPitch;      /* samples */
+    unsigned long long* dSmall;   /* small scratch for sums */
+
+    /* growable staging */
+    uint8_t* dStage; size_t dStageCap;
+    uint8_t* hStage; size_t hStageCap;
+    uint8_t* dArgs; size_t dArgsCap;       /* JobDev[], SearchItem[], int[] */
+    uint8_t* hArgs; size_t hArgsCap;
+    std::vector<void*> wPool;              /* weighted plane sets */
+    uint8_t* dGeneric; size_t dGenericCap; /* pixelcmp / var scratch */
+
+    bool timing;
+    std::vector<PendingEvent> pending;
+    std::vector<cudaEvent_t> freeEvents;
+    x265cu_stats stats;
+
+    int searchWarps;
+};
+
+namespace {
+
+#define CU_TRY(ctx, call)                                                                           \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+        {                                                                                           \
+            snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return X265CU_ECUDA;                                                                    \
+        }                                                                                           \
+    } while (0)
+
+int fail(x265cu_ctx* c, int code, const char* msg)
+{
+    snprintf(c->err, sizeof(c->err), "%s", msg);
+    return code;
+}
+
+inline size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int growDevice(x265cu_ctx* c, uint8_t** p, size_t* cap, size_t need)
+{
+    if (*cap >= need) return 0;
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (*p) cudaFree(*p);
+    *p = NULL; *cap = 0;
+    size_t n = alignUp(need + need / 2, 1 << 20);
+    CU_TRY(c, cudaMalloc((void**)p, n));
+    *cap = n;
+    return 0;
+}
+
+int growHost(x265cu_ctx* c, uint8_t** p, size_t* cap, size_t need)
+{
+    if (*cap >= need) return 0;
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (*p) cudaFreeHost(*p);
+    *p = NULL; *cap = 0;
+    size_t n = alignUp(need + need / 2, 1 << 20);
+    CU_TRY(c, cudaMallocHost((void**)p, n));
+    *cap = n;
+    return 0;
+}
+
+/* ---- timing helpers ---- */
+cudaEvent_t getEvent(x265cu_ctx* c)
+{
+    if (!c->freeEvents.empty()) { cudaEvent_t e = c->freeEvents.back(); c->freeEvents.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct KernelScope
+{
+    x265cu_ctx* c; int kind; cudaEvent_t a, b; bool on;
+    KernelScope(x265cu_ctx* ctx, int k, int launches = 1) : c(ctx), kind(k), on(ctx->timing)
+    {
+        c->stats.launches[kind] += launches;
+        if (on) { a = getEvent(c); b = getEvent(c); cudaEventRecord(a, c->stream); }
+    }
+    ~KernelScope()
+    {
+        if (on) { cudaEventRecord(b, c->stream); PendingEvent p = { kind, a, b }; c->pending.push_back(p); }
+    }
+};
+
+void resolveEvents(x265cu_ctx* c)
+{
+    for (size_t i = 0; i < c->pending.size(); i++)
+    {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->pending[i].a, c->pending[i].b) == cudaSuccess)
+            c->stats.ms[c->pending[i].kind] += ms;
+        c->freeEvents.push_back(c->pending[i].a);
+        c->freeEvents.push_back(c->pending[i].b);
+    }
+    c->pending.clear();
+}
+
+int syncStream(x265cu_ctx* c)
+{
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    resolveEvents(c);
+    return 0;
+}
+
+/* ---- mirrors ---- */
+inline uint8_t* slotBuffer(x265cu_ctx* c, int slot) { return c->dPlanes + (size_t)slot * 4 * c->g.planeSize * c->pb; }
+inline uint8_t* slotPlane0(x265cu_ctx* c, int slot) { return slotBuffer(c, slot) + (size_t)c->g.padOffset * c->pb; }
+inline int* slotIntraCost(x265cu_ctx* c, int slot) { return c->dIntraCost + (size_t)slot * c->g.nCU; }
+inline uint8_t* slotIntraMode(x265cu_ctx* c, int slot) { return c->dIntraMode + (size_t)slot * c->g.nCU; }
+inline int* slotInvQ(x265cu_ctx* c, int slot) { return c->dInvQ + (size_t)slot * c->g.nCU; }
+inline uint16_t* slotLowresCosts(x265cu_ctx* c, int slot, int d0, int d1)
+{
+    return c->dLowresCosts + (((size_t)slot * (c->bf + 2) + d0) * (c->bf + 2) + d1) * c->g.nCU;
+}
+inline int* slotRowSatds(x265cu_ctx* c, int slot, int d0, int d1)
+{
+    return c->dRowSatds + (((size_t)slot * (c->bf + 2) + d0) * (c->bf + 2) + d1) * c->g.hCU;
+}
+inline int* slotMvs(x265cu_ctx* c, int slot, int list, int d) { return c->dMvs + (((size_t)slot * 2 + list) * (c->bf + 1) + (d - 1)) * c->g.nCU; }
+inline int* slotMvCosts(x265cu_ctx* c, int slot, int list, int d) { return c->dMvCosts + (((size_t)slot * 2 + list) * (c->bf + 1) + (d - 1)) * c->g.nCU; }
+
+bool badSlot(const x265cu_ctx* c, int s) { return s < 0 || s >= c->cfg.numFrameSlots; }
+
+void freeAll(x265cu_ctx* c)
+{
+    cudaFree(c->dPlanes); cudaFree(c->dIntraCost); cudaFree(c->dIntraMode); cudaFree(c->dInvQ);
+    cudaFree(c->dLowresCosts); cudaFree(c->dRowSatds); cudaFree(c->dMvs); cudaFree(c->dMvCosts);
+    cudaFree(c->dLut); cudaFree(c->dSrc); cudaFree(c->dSmall); cudaFree(c->dStage); cudaFree(c->dArgs); cudaFree(c->dGeneric);
+    if (c->hStage) cudaFreeHost(c->hStage);
+    if (c->hArgs) cudaFreeHost(c->hArgs);
+    for (size_t i = 0; i < c->wPool.size(); i++) cudaFree(c->wPool[i]);
+    for (size_t i = 0; i < c->freeEvents.size(); i++) cudaEventDestroy(c->freeEvents[i]);
+    if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
+}
+
+} // namespace
+
+/* ============================================================================================ */
+extern "C" {
+
+int x265cu_abi_version(void) { return X265CU_ABI_VERSION; }
+
+int x265cu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* x265cu_last_error(const x265cu_ctx* ctx) { return ctx ? ctx->err : g_openError; }
+
+int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
+{
+    if (!cfg || !out) { snprintf(g_openError, sizeof(g_openError), "x265cu_open: NULL argument"); return X265CU_EINVAL; }
+    *out = NULL;
+    if (cfg->srcWidth < 16 || cfg->srcHeight < 16 || cfg->bframes < 0 || cfg->bframes > X265CU_BFRAME_MAX ||
+        cfg->numFrameSlots < 1 || !cfg->mvcost || (cfg->bitDepth != 8 && cfg->bitDepth != 10 && cfg->bitDepth != 12) ||
+        cfg->marginX < 32 || (cfg->marginX & 3) || cfg->marginY < 16 || cfg->numCoopSlices < 1 || cfg->numRowsPerSlice < 1)
+    {
+        snprintf(g_openError, sizeof(g_openError), "x265cu_open: unsupported configuration");
+        return X265CU_EINVAL;
+    }
+    int ndev = x265cu_device_count();
+    if (ndev <= 0 || cfg->device < 0 || cfg->device >= ndev)
+    {
+        snprintf(g_openError, sizeof(g_openError), "x265cu_open: no usable CUDA device (count=%d, requested %d); there is no CPU fallback", ndev, cfg->device);
+        return X265CU_ENODEV;
+    }
+    x265cu_ctx* c = new x265cu_ctx();
+    c->cfg = *cfg;
+    c->err[0] = 0;
+    c->dPlanes = NULL; c->dIntraCost = NULL; c->dIntraMode = NULL; c->dInvQ = NULL; c->dLowresCosts = NULL; c->dRowSatds = NULL;
+    c->dMvs = NULL; c->dMvCosts = NULL; c->dLut = NULL; c->dSrc = NULL; c->dSmall = NULL;
+    c->dStage = NULL; c->dStageCap = 0; c->hStage = NULL; c->hStageCap = 0; c->dArgs = NULL; c->dArgsCap = 0; c->hArgs = NULL; c->hArgsCap = 0;
+    c->dGeneric = NULL; c->dGenericCap = 0;
+    c->timing = false;
+    memset(&c->stats, 0, sizeof(c->stats));
+    c->stream = NULL; c->ownStream = false;
+    c->pb = cfg->bitDepth > 8 ? 2 : 1;
+    c->pixelMax = (1 << cfg->bitDepth) - 1;
+    c->correction = 14 - cfg->bitDepth;
+    c->bf = cfg->bframes;
+    c->searchWarps = cfg->searchWarps > 0 ? cfg->searchWarps : 16;
+    if (c->searchWarps > 16) c->searchWarps = 16;   /* search_kernel is compiled for <= 512 threads */
+
+    /* geometry: Lowres::create, common/lowres.cpp:34-48 */
+    GeomDev& g = c->g;
+    int w = cfg->srcWidth / 2, l = cfg->srcHeight / 2;
+    g.stride = w + 2 * cfg->marginX;
+    if (g.stride & 31) g.stride += 32 - (g.stride & 31);
+    g.wCU = (w + 7) >> 3; g.hCU = (l + 7) >> 3; g.nCU = g.wCU * g.hCU;
+    g.width = g.wCU * 8; g.lines = g.hCU * 8;
+    g.marginX = cfg->marginX; g.marginY = cfg->marginY;
+    g.paddedLines = g.lines + 2 * cfg->marginY;
+    g.planeSize = (int64_t)g.stride * g.paddedLines;
+    g.padOffset = (int64_t)g.stride * cfg->marginY + cfg->marginX;
+    if (g.hCU > SEARCH_MAX_ROWS) { delete c; snprintf(g_openError, sizeof(g_openError), "x265cu_open: picture too tall"); return X265CU_EINVAL; }
+
+#define OPEN_TRY(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+        {                                                                                           \
+            snprintf(g_openError, sizeof(g_openError), "x265cu_open: %s: %s", #call, cudaGetErrorString(e_)); \
+            freeAll(c); delete c;                                                                   \
+            return e_ == cudaErrorMemoryAllocation ? X265CU_ENOMEM : X265CU_ECUDA;                  \
+        }                                                                                           \
+    } while (0)
+
+    OPEN_TRY(cudaSetDevice(cfg->device));
+    if (cfg->stream) c->stream = (cudaStream_t)cfg->stream;
+    else { OPEN_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->ownStream = true; }
+
+    const size_t S = (size_t)cfg->numFrameSlots, n = (size_t)g.nCU, t2 = (size_t)(c->bf + 2) * (c->bf + 2), t1 = (size_t)2 * (c->bf + 1);
+    size_t planeBytes = S * 4 * (size_t)g.planeSize * c->pb + 256;
+    OPEN_TRY(cudaMalloc((void**)&c->dPlanes, planeBytes));
+    OPEN_TRY(cudaMemsetAsync(c->dPlanes, 0, planeBytes, c->stream));   /* CHECKED_MALLOC_ZERO, lowres.cpp:62 */
+    OPEN_TRY(cudaMalloc((void**)&c->dIntraCost, S * n * sizeof(int)));
+    OPEN_TRY(cudaMalloc((void**)&c->dIntraMode, S * n));
+    OPEN_TRY(cudaMalloc((void**)&c->dInvQ, S * n * sizeof(int)));
+    OPEN_TRY(cudaMalloc((void**)&c->dLowresCosts, S * t2 * n * sizeof(uint16_t)));
+    OPEN_TRY(cudaMalloc((void**)&c->dRowSatds, S * t2 * g.hCU * sizeof(int)));
+    OPEN_TRY(cudaMalloc((void**)&c->dMvs, S * t1 * n * sizeof(int)));
+    OPEN_TRY(cudaMalloc((void**)&c->dMvCosts, S * t1 * n * sizeof(int)));
+    OPEN_TRY(cudaMemsetAsync(c->dMvs, 0, S * t1 * n * sizeof(int), c->stream));
+    OPEN_TRY(cudaMemsetAsync(c->dMvCosts, 0, S * t1 * n * sizeof(int), c->stream));
+    OPEN_TRY(cudaMalloc((void**)&c->dLut, (4 * 32768 + 1) * sizeof(uint16_t)));
+    OPEN_TRY(cudaMemcpyAsync(c->dLut, cfg->mvcost - 2 * 32768, (4 * 32768 + 1) * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+    c->srcPitch = (int64_t)alignUp((size_t)(2 * g.width + 1), 64);
+    OPEN_TRY(cudaMalloc((void**)&c->dSrc, (size_t)c->srcPitch * (2 * g.lines + 1) * c->pb + 256));
+    OPEN_TRY(cudaMalloc((void**)&c->dSmall, 64 * sizeof(unsigned long long)));
+    c->hasInvQ.assign(S, 0);
+    OPEN_TRY(cudaStreamSynchronize(c->stream));
+    c->cfg.mvcost = NULL;   /* caller's table was copied */
+    *out = c;
+    return X265CU_OK;
+}
+
+void x265cu_close(x265cu_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    cudaStreamSynchronize(c->stream);
+    resolveEvents(c);
+    freeAll(c);
+    delete c;
+}
+
+int x265cu_get_geometry(const x265cu_ctx* c, x265cu_geometry* o)
+{
+    if (!c || !o) return X265CU_EINVAL;
+    o->width = c->g.width; o->lines = c->g.lines; o->stride = c->g.stride; o->paddedLines = c->g.paddedLines;
+    o->widthInCU = c->g.wCU; o->heightInCU = c->g.hCU; o->cuCount = c->g.nCU;
+    o->planeSize = c->g.planeSize; o->padOffset = c->g.padOffset; o->pixelBytes = c->pb;
+    return X265CU_OK;
+}
+
+int x265cu_sync(x265cu_ctx* c)
+{
+    if (!c) return X265CU_EINVAL;
+    std::lock_guard<std::mutex> lk(c->mtx);
+    return syncStream(c);
+}
+
+int x265cu_host_register(void* ptr, size_t bytes)
+{
+    if (!ptr || !bytes) return X265CU_EINVAL;
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return X265CU_ECUDA; }
+    return X265CU_OK;
+}
+
+int x265cu_host_unregister(void* ptr)
+{
+    if (!ptr) return X265CU_EINVAL;
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return X265CU_ECUDA; }
+    return X265CU_OK;
+}
+
+int x265cu_stats_enable(x265cu_ctx* c, int timing)
+{
+    if (!c) return X265CU_EINVAL;
+    std::lock_guard<std::mutex> lk(c->mtx);
+    syncStream(c);
+    c->timing = timing != 0;
+    return X265CU_OK;
+}
+
+int x265cu_stats_get(x265cu_ctx* c, x265cu_stats* o, int reset)
+{
+    if (!c || !o) return X265CU_EINVAL;
+    std::lock_guard<std::mutex> lk(c->mtx);
+    int r = syncStream(c);
+    *o = c->stats;
+    if (reset) memset(&c->stats, 0, sizeof(c->stats));
+    return r;
+}
+
+/* -------------------------------------------------------------------------------------------- */
+int x265cu_frame_init(x265cu_ctx* c, int slot, const void* luma, intptr_t srcStride, int lumaIsDevice, void* planesOut)
+{
+    if (!c || !luma || badSlot(c, slot) || srcStride < 2 * c->g.width + 1) return c ? fail(c, X265CU_EINVAL, "x265cu_frame_init: bad argument") : X265CU_EINVAL;
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CU_TRY(c, cudaSetDevice(c->cfg.device));
+    const GeomDev& g = c->g;
+    const void* src = luma;
+    int64_t pitch = srcStride;
+    if (!lumaIsDevice)
+    {
+        size_t wbytes = (size_t)(2 * g.width + 1) * c->pb;
+        CU_TRY(c, cudaMemcpy2DAsync(c->dSrc, (size_t)c->srcPitch * c->pb, luma, (size_t)srcStride * c->pb, wbytes, 2 * g.lines + 1,
+                                    cudaMemcpyHostToDevice, c->stream));
+        c->stats.h2dBytes += (int64_t)wbytes * (2 * g.lines + 1);
+        src = c->dSrc;
+        pitch = c->srcPitch;
+    }
+    else if (((uintptr_t)luma & 7) || (((size_t)srcStride * c->pb) & 7))
+        return fail(c, X265CU_EINVAL, "x265cu_frame_init: device luma must be 8-byte aligned with an 8-byte multiple pitch");
+    {
+        KernelScope ks(c, X265CU_K_LOWRES);
+        const int padW = g.width + 2 * g.marginX;
+        dim3 grid((padW / 4 + 255) / 256, g.paddedLines);
+        if (c->pb == 1)
+            lowres_init_kernel<uint8_t><<<grid, 256, 0, c->stream>>>((const uint8_t*)src, pitch, (uint8_t*)slotBuffer(c, slot), g);
+        else
+            lowres_init_kernel<uint16_t><<<grid, 256, 0, c->stream>>>((const uint16_t*)src, pitch, (uint16_t*)slotBuffer(c, slot), g);
+    }
+    CU_TRY(c, cudaGetLastError());
+    if (planesOut)
+    {
+        size_t bytes = (size_t)4 * g.planeSize * c->pb;
+        CU_TRY(c, cudaMemcpyAsync(planesOut, slotBuffer(c, slot), bytes, cudaMemcpyDeviceToHost, c->stream));
+        c->stats.d2hBytes += (int64_t)bytes;
+    }
+    /* the caller may reuse its luma buffer as soon as we return */
+    return syncStream(c);
+}
+
+int x265cu_frame_set_invqscale(x265cu_ctx* c, int slot, const int32_t* invQ)
+{
+    if (!c || badSlot(c, slot)) return c ? fail(c, X265CU_EINVAL, "x265cu_frame_set_invqscale: bad slot") : X265CU_EINVAL;
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CU_TRY(c, cudaSetDevice(c->cfg.device));
+    c->hasInvQ[slot] = invQ != NULL;
+    if (invQ)
+    {
+        CU_TRY(c, cudaMemcpyAsync(slotInvQ(c, slot), invQ, (size_t)c->g.nCU * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        c->stats.h2dBytes += (int64_t)c->g.nCU * sizeof(int);
+        return syncStream(c);
+    }
+    return X265CU_OK;
+}
+
+int x265cu_intra(x265cu_ctx* c, int slot, x265cu_intra_out* out)
+{
+    if (!c || badSlot(c, slot)) return c ? fail(c, X265CU_EINVAL, "x265cu_intra: bad slot") : X265CU_EINVAL;
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CU_TRY(c, cudaSetDevice(c->cfg.device));
+    const GeomDev& g = c->g;
+    IntraOutDev o;
+    o.intraCost = slotIntraCost(c, slot);
+    o.intraMode = slotIntraMode(c, slot);
+    o.lowresCosts = slotLowresCosts(c, slot, 0, 0);
+    o.rowSatds = slotRowSatds(c, slot, 0, 0);
+    o.sums = c->dSmall;
+    o.invQ = c->hasInvQ[slot] ? slotInvQ(c, slot) : NULL;
+    CU_TRY(c, cudaMemsetAsync(o.rowSatds, 0, (size_t)g.hCU * sizeof(int), c->stream));
+    CU_TRY(c, cudaMemsetAsync(c->dSmall, 0, 2 * sizeof(unsigned long long), c->stream));
+    {
+        KernelScope ks(c, X265CU_K_INTRA);
+        int blocks = (g.nCU + 7) / 8;
+        if (c->pb == 1)
+            intra_kernel<uint8_t><<<blocks, 256, 0, c->stream>>>((const uint8_t*)slotPlane0(c, slot), g, c->cfg.lookaheadLambda, c->pixelMax, o);
+        else
+            intra_kernel<uint16_t><<<blocks, 256, 0, c->stream>>>((const uint16_t*)slotPlane0(c, slot), g, c->cfg.lookaheadLambda, c->pixelMax, o);
+    }
+    CU_TRY(c, cudaGetLastError());
+    if (out)
+    {
+        unsigned long long sums[2] = { 0, 0 };
+        if (out->intraCost) { CU_TRY(c, cudaMemcpyAsync(out->intraCost, o.intraCost, (size_t)g.nCU * 4, cudaMemcpyDeviceToHost, c->stream)); c->stats.d2hBytes += g.nCU * 4; }
+        if (out->intraMode) { CU_TRY(c, cudaMemcpyAsync(out->intraMode, o.intraMode, (size_t)g.nCU, cudaMemcpyDeviceToHost, c->stream)); c->stats.d2hBytes += g.nCU; }
+        if (out->lowresCosts) { CU_TRY(c, cudaMemcpyAsync(out->lowresCosts, o.lowresCosts, (size_t)g.nCU * 2, cudaMemcpyDeviceToHost, c->stream)); c->stats.d2hBytes += g.nCU * 2; }
+        if (out->rowSatds) { CU_TRY(c, cudaMemcpyAsync(out->rowSatds, o.rowSatds, (size_t)g.hCU * 4, cudaMemcpyDeviceToHost, c->stream)); c->stats.d2hBytes += g.hCU * 4; }
+        CU_TRY(c, cudaMemcpyAsync(sums, c->dSmall, sizeof(sums), cudaMemcpyDeviceToHost, c->stream));
+        int r = syncStream(c);
+        out->sums[0] = (int64_t)sums[0];
+        out->sums[1] = (int64_t)sums[1];
+        return r;
+    }
+    return syncStream(c);
+}
+
+/* -------------------------------------------------------------------------------------------- */
+static void weightArgs(const x265cu_ctx* c, int scale, int denom, int offset, int* round, int* shift, int* off)
+{
+    /* weightCostLuma / weightsAnalyse call sites, slicetype.cpp:345-352,476-484 */
+    int r = denom ? 1 << (denom - 1) : 0;
+    *round = r << c->correction;
+    *shift = denom + c->correction;
+    *off = offset << (c->cfg.bitDepth - 8);
+    (void)scale;
+}
+
+int x265cu_weight_cost_batch(x265cu_ctx* c, int n, const x265cu_weight_item* items, uint32_t* costs)
+{
+    if (!c || n < 0 || (n && (!items || !costs))) return c ? fail(c, X265CU_EINVAL, "x265cu_weight_cost_batch: bad argument") : X265CU_EINVAL;
+    if (!n) return X265CU_OK;
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CU_TRY(c, cudaSetDevice(c->cfg.device));
+    const GeomDev& g = c->g;
+    size_t argBytes = alignUp((size_t)n * sizeof(WeightCostDev), 256) + (size_t)n * sizeof(unsigned int);
+    if (growHost(c, &c->hArgs, &c->hArgsCap, argBytes) || growDevice(c, &c->dArgs, &c->dArgsCap, argBytes)) return X265CU_ECUDA;
+    WeightCostDev* h = (WeightCostDev*)c->hArgs;
+    for (int i = 0; i < n; i++)
+    {
+        if (badSlot(c, items[i].fenc) || badSlot(c, items[i].ref)) return fail(c, X265CU_EINVAL, "x265cu_weight_cost_batch: bad slot");
+        h[i].fenc = slotPlane0(c, items[i].fenc);
+        h[i].ref = slotPlane0(c, items[i].ref);
+        h[i].intraCost = slotIntraCost(c, items[i].fenc);
+        h[i].weighted = items[i].weighted;
+        h[i].scale = items[i].scale;
+        weightArgs(c, items[i].scale, items[i].denom, items[i].offset, &h[i].round, &h[i].shift, &h[i].offset);
+    }
+    unsigned int* dCosts = (unsigned int*)(c->dArgs + alignUp((size_t)n * sizeof(WeightCostDev), 256));
+    CU_TRY(c, cudaMemcpyAsync(c->dArgs, h, (size_t)n * sizeof(WeightCostDev), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemsetAsync(dCosts, 0, (size_t)n * sizeof(unsigned int), c->stream));
+    {
+        KernelScope ks(c, X265CU_K_WEIGHT);
+        int bx = (g.nCU / 8 + 7) / 8;
+        if (bx > 148 * 2) bx = 148 * 2;
+        if (bx < 1) bx = 1;
+        dim3 grid(bx, n);
+        if (c->pb == 1)
+            weight_cost_kernel<uint8_t><<<grid, 256, 0, c->stream>>>((const WeightCostDev*)c->dArgs, dCosts, g, c->correction, c->pixelMax);
+        else
+            weight_cost_kernel<uint16_t><<<grid, 256, 0, c->stream>>>((const WeightCostDev*)c->dArgs, dCosts, g, c->correction, c->pixelMax);
+    }
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaMemcpyAsync(costs, dCosts, (size_t)n * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    c->stats.d2hBytes += (int64_t)n * 4;
+    return syncStream(c);
+}
+
+/* -------------------------------------------------------------------------------------------- */
+int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_job_result* results)
+{
+    if (!c || n < 0 || (n && (!jobs || !results))) return c ? fail(c, X265CU_EINVAL, "x265cu_estimate_batch: bad argument") : X265CU_EINVAL;
+    if (!n) return X265CU_OK;
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CU_TRY(c, cudaSetDevice(c->cfg.device));
+    const GeomDev& g = c->g;
+    const size_t nCU = (size_t)g.nCU, hCU = (size_t)g.hCU;
+
+    /* ---- plan: per-job packed record + work items ---- */
+    std::vector<size_t> recOff(n);
+    std::vector<SearchItem> items;
+    std::vector<int> costIdx;
+    std::vector<int> weightedJobs;
+    size_t total = 0;
+    for (int i = 0; i < n; i++)
+    {
+        const x265cu_job& j = jobs[i];
+        if (badSlot(c, j.fenc) || badSlot(c, j.ref0) || (j.d1 > 0 && badSlot(c, j.ref1)) || j.d0 < 1 || j.d0 > c->bf + 1 || j.d1 < 0 || j.d1 > c->bf + 1)
+            return fail(c, X265CU_EINVAL, "x265cu_estimate_batch: bad job");
+        if (j.doSearch[1] && j.d1 == 0) return fail(c, X265CU_EINVAL, "x265cu_estimate_batch: L1 search without p1");
+        recOff[i] = total;
+        size_t rec = 32 + alignUp(hCU * 4, 16) + alignUp(nCU * 2, 16);
+        if (j.doSearch[0]) rec += 2 * alignUp(nCU * 4, 16);
+        if (j.doSearch[1]) rec += 2 * alignUp(nCU * 4, 16);
+        total += rec;
+        const bool search = j.doSearch[0] || j.doSearch[1];
+        if (search)
+        {
+            bool useSlices = j.sliced && c->cfg.numCoopSlices > 1;   /* (p1 > b || search) holds here */
+            int ns = useSlices ? c->cfg.numCoopSlices : 1;
+            for (int s = 0; s < ns; s++)
+            {
+                SearchItem it;
+                it.job = i;
+                it.firstY = useSlices ? c->cfg.numRowsPerSlice * s : 0;
+                it.lastY = (!useSlices || s == ns - 1) ? g.hCU - 1 : c->cfg.numRowsPerSlice * (s + 1) - 1;
+                items.push_back(it);
+            }
+        }
+        else
+            costIdx.push_back(i);
+        if (j.weighted && j.doSearch[0]) weightedJobs.push_back(i);
+    }
+    /* weighted reference pool */
+    while (c->wPool.size() < weightedJobs.size())
+    {
+        void* p = NULL;
+        CU_TRY(c, cudaMalloc(&p, (size_t)4 * g.planeSize * c->pb + 256));
+        c->wPool.push_back(p);
+    }
+
+    size_t offJobs = 0;
+    size_t offItems = alignUp(offJobs + (size_t)n * sizeof(JobDev), 256);
+    size_t offCost = alignUp(offItems + items.size() * sizeof(SearchItem), 256);
+    size_t offW = alignUp(offCost + costIdx.size() * sizeof(int), 256);
+    size_t argBytes = alignUp(offW + weightedJobs.size() * sizeof(WeightDev), 256);
+    if (growHost(c, &c->hArgs, &c->hArgsCap, argBytes) || growDevice(c, &c->dArgs, &c->dArgsCap, argBytes)) return X265CU_ECUDA;
+    if (growDevice(c, &c->dStage, &c->dStageCap, total) || growHost(c, &c->hStage, &c->hStageCap, total)) return X265CU_ECUDA;
+
+    JobDev* hj = (JobDev*)(c->hArgs + offJobs);
+    std::vector<int> wSlotOfJob(n, -1);
+    for (size_t k = 0; k < weightedJobs.size(); k++) wSlotOfJob[weightedJobs[k]] = (int)k;
+    for (int i = 0; i < n; i++)
+    {
+        const x265cu_job& j = jobs[i];
+        JobDev& d = hj[i];
+        memset(&d, 0, sizeof(d));
+        const int ref1 = j.d1 > 0 ? j.ref1 : j.fenc;
+        d.fenc = slotPlane0(c, j.fenc);
+        d.ref0 = slotPlane0(c, j.ref0);
+        d.ref0w = wSlotOfJob[i] >= 0 ? (const void*)((uint8_t*)c->wPool[wSlotOfJob[i]] + (size_t)g.padOffset * c->pb) : d.ref0;
+        d.ref1 = slotPlane0(c, ref1);
+        d.mvs[0] = slotMvs(c, j.fenc, 0, j.d0);
+        d.mvCosts[0] = slotMvCosts(c, j.fenc, 0, j.d0);
+        d.mvs[1] = j.d1 > 0 ? slotMvs(c, j.fenc, 1, j.d1) : NULL;
+        d.mvCosts[1] = j.d1 > 0 ? slotMvCosts(c, j.fenc, 1, j.d1) : NULL;
+        d.lowresCosts = slotLowresCosts(c, j.fenc, j.d0, j.d1);
+        d.rowSatds = slotRowSatds(c, j.fenc, j.d0, j.d1);
+        d.intraCost = slotIntraCost(c, j.fenc);
+        d.invQ = c->hasInvQ[j.fenc] ? slotInvQ(c, j.fenc) : NULL;
+        uint8_t* rec = c->dStage + recOff[i];
+        d.outSums = (unsigned long long*)rec; rec += 32;
+        d.outRows = (int*)rec; rec += alignUp(hCU * 4, 16);
+        d.outLowresCosts = (uint16_t*)rec; rec += alignUp(nCU * 2, 16);
+        for (int l = 0; l < 2; l++)
+            if (j.doSearch[l])
+            {
+                d.outMvs[l] = (int*)rec; rec += alignUp(nCU * 4, 16);
+                d.outMvCosts[l] = (int*)rec; rec += alignUp(nCU * 4, 16);
+            }
+        d.d0 = j.d0; d.d1 = j.d1;
+        d.doSearch[0] = j.doSearch[0] != 0; d.doSearch[1] = j.doSearch[1] != 0;
+        d.bidir = j.d1 > 0;
+    }
+    if (!items.empty()) memcpy(c->hArgs + offItems, &items[0], items.size() * sizeof(SearchItem));
+    if (!costIdx.empty()) memcpy(c->hArgs + offCost, &costIdx[0], costIdx.size() * sizeof(int));
+    WeightDev* hw = (WeightDev*)(c->hArgs + offW);
+    for (size_t k = 0; k < weightedJobs.size(); k++)
+    {
+        const x265cu_job& j = jobs[weightedJobs[k]];
+        hw[k].src = slotBuffer(c, j.ref0);
+        hw[k].dst = c->wPool[k];
+        hw[k].scale = j.wScale;
+        weightArgs(c, j.wScale, j.wDenom, j.wOffset, &hw[k].round, &hw[k].shift, &hw[k].offset);
+    }
+    CU_TRY(c, cudaMemcpyAsync(c->dArgs, c->hArgs, argBytes, cudaMemcpyHostToDevice, c->stream));
+    c->stats.h2dBytes += (int64_t)argBytes;
+    /* zero the sums of every record (32 bytes at the head of each) -- one memset over the staging
+     * area is simpler than n small ones and the area is written anyway */
+    CU_TRY(c, cudaMemsetAsync(c->dStage, 0, total, c->stream));
+
+    if (!weightedJobs.empty())
+    {
+        KernelScope ks(c, X265CU_K_WEIGHT);
+        dim3 grid(148, (unsigned)weightedJobs.size());
+        if (c->pb == 1)
+            weight_planes_kernel<uint8_t><<<grid, 256, 0, c->stream>>>((const WeightDev*)(c->dArgs + offW), 4 * g.planeSize, c->correction, c->pixelMax);
+        else
+            weight_planes_kernel<uint16_t><<<grid, 256, 0, c->stream>>>((const WeightDev*)(c->dArgs + offW), 4 * g.planeSize, c->correction, c->pixelMax);
+        CU_TRY(c, cudaGetLastError());
+    }
+    if (!items.empty())
+    {
+        KernelScope ks(c, X265CU_K_SEARCH);
+        int warps = c->searchWarps;
+        if (c->pb == 1)
+            search_kernel<uint8_t><<<(unsigned)items.size(), warps * 32, 0, c->stream>>>((const JobDev*)(c->dArgs + offJobs), (const SearchItem*)(c->dArgs + offItems), g, c->dLut + 2 * 32768);
+        else
+            search_kernel<uint16_t><<<(unsigned)items.size(), warps * 32, 0, c->stream>>>((const JobDev*)(c->dArgs + offJobs), (const SearchItem*)(c->dArgs + offItems), g, c->dLut + 2 * 32768);
+        CU_TRY(c, cudaGetLastError());
+    }
+    if (!costIdx.empty())
+    {
+        KernelScope ks(c, X265CU_K_COST);
+        dim3 grid(g.hCU, (unsigned)costIdx.size());
+        if (c->pb == 1)
+            cost_kernel<uint8_t><<<grid, 128, 0, c->stream>>>((const JobDev*)(c->dArgs + offJobs), (const int*)(c->dArgs + offCost), g);
+        else
+            cost_kernel<uint16_t><<<grid, 128, 0, c->stream>>>((const JobDev*)(c->dArgs + offJobs), (const int*)(c->dArgs + offCost), g);
+        CU_TRY(c, cudaGetLastError());
+    }
+    CU_TRY(c, cudaMemcpyAsync(c->hStage, c->dStage, total, cudaMemcpyDeviceToHost, c->stream));
+    c->stats.d2hBytes += (int64_t)total;
+    int r = syncStream(c);
+    if (r) return r;
+
+    /* scatter to the caller's Lowres arrays */
+    for (int i = 0; i < n; i++)
+    {
+        const x265cu_job& j = jobs[i];
+        const uint8_t* rec = c->hStage + recOff[i];
+        const unsigned long long* sums = (const unsigned long long*)rec; rec += 32;
+        x265cu_job_result& res = results[i];
+        res.costEstRaw = (int64_t)sums[0];
+        res.costEstAq = (int64_t)sums[1];
+        res.intraMbs = (int32_t)sums[2];
+        res.reserved = 0;
+        res.costEst = j.d1 > 0 ? res.costEstRaw * 100 / (130 + c->cfg.bFrameBias) : res.costEstRaw;   /* slicetype.cpp:2053-2057 */
+        if (j.rowSatds) memcpy(j.rowSatds, rec, hCU * 4);
+        rec += alignUp(hCU * 4, 16);
+        if (j.lowresCosts) memcpy(j.lowresCosts, rec, nCU * 2);
+        rec += alignUp(nCU * 2, 16);
+        for (int l = 0; l < 2; l++)
+            if (j.doSearch[l])
+            {
+                if (j.mvs[l]) memcpy(j.mvs[l], rec, nCU * 4);
+                rec += alignUp(nCU * 4, 16);
+                if (j.mvCosts[l]) memcpy(j.mvCosts[l], rec, nCU * 4);
+                rec += alignUp(nCU * 4, 16);
+            }
+    }
+    return X265CU_OK;
+}
+
+/* -------------------------------------------------------------------------------------------- */
+int x265cu_pixelcmp_batch(x265cu_ctx* c, int kind, const void* bufA, size_t samplesA, intptr_t strideA,
+                          const void* bufB, size_t samplesB, intptr_t strideB,
+                          int n, const int64_t* offA, const int64_t* offB, int32_t* out)
+{
+    if (!c || kind < 0 || kind > 3 || !bufA || !bufB || n < 0 || (n && (!offA || !offB || !out)))
+        return c ? fail(c, X265CU_EINVAL, "x265cu_pixelcmp_batch: bad argument") : X265CU_EINVAL;
+    if (!n) return X265CU_OK;
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CU_TRY(c, cudaSetDevice(c->cfg.device));
+    size_t bytesA = alignUp(samplesA * c->pb + 16, 256), bytesB = alignUp(samplesB * c->pb + 16, 256);
+    size_t offs = alignUp((size_t)n * 8, 256);
+    size_t need = bytesA + bytesB + 2 * offs + alignUp((size_t)n * 4, 256);
+    if (growDevice(c, &c->dGeneric, &c->dGenericCap, need)) return X265CU_ECUDA;
+    uint8_t* dA = c->dGeneric; uint8_t* dB = dA + bytesA;
+    int64_t* dOffA = (int64_t*)(dB + bytesB); int64_t* dOffB = (int64_t*)((uint8_t*)dOffA + offs);
+    int* dOut = (int*)((uint8_t*)dOffB + offs);
+    CU_TRY(c, cudaMemsetAsync(dA, 0, bytesA + bytesB, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(dA, bufA, samplesA * c->pb, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(dB, bufB, samplesB * c->pb, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(dOffA, offA, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(dOffB, offB, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    {
+        KernelScope ks(c, X265CU_K_PIXEL);
+        int blocks = (n * 4 + 255) / 256;
+        if (c->pb == 1)
+            pixelcmp_batch_kernel<uint8_t><<<blocks, 256, 0, c->stream>>>(kind, (const uint8_t*)dA, strideA, (const uint8_t*)dB, strideB, n, dOffA, dOffB, dOut);
+        else
+            pixelcmp_batch_kernel<uint16_t><<<blocks, 256, 0, c->stream>>>(kind, (const uint16_t*)dA, strideA, (const uint16_t*)dB, strideB, n, dOffA, dOffB, dOut);
+    }
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaMemcpyAsync(out, dOut, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    return syncStream(c);
+}
+
+int x265cu_pixelcmp_frames(x265cu_ctx* c, int kind, int slotA, int slotB, int32_t* out, float* ms)
+{
+    if (!c || kind < 0 || kind > 2 || badSlot(c, slotA) || badSlot(c, slotB))
+        return c ? fail(c, X265CU_EINVAL, "x265cu_pixelcmp_frames: bad argument") : X265CU_EINVAL;
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CU_TRY(c, cudaSetDevice(c->cfg.device));
+    const GeomDev& g = c->g;
+    if (growDevice(c, &c->dGeneric, &c->dGenericCap, (size_t)g.nCU * 4)) return X265CU_ECUDA;
+    cudaEvent_t e0 = getEvent(c), e1 = getEvent(c);
+    c->stats.launches[X265CU_K_PIXEL]++;
+    CU_TRY(c, cudaEventRecord(e0, c->stream));
+    int blocks = (g.nCU / 8 + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    if (c->pb == 1)
+        pixelcmp_frames_kernel<uint8_t><<<blocks, 256, 0, c->stream>>>(kind, (const uint8_t*)slotPlane0(c, slotA), (const uint8_t*)slotPlane0(c, slotB), g, (int*)c->dGeneric);
+    else
+        pixelcmp_frames_kernel<uint16_t><<<blocks, 256, 0, c->stream>>>(kind, (const uint16_t*)slotPlane0(c, slotA), (const uint16_t*)slotPlane0(c, slotB), g, (int*)c->dGeneric);
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaEventRecord(e1, c->stream));
+    if (out) CU_TRY(c, cudaMemcpyAsync(out, c->dGeneric, (size_t)g.nCU * 4, cudaMemcpyDeviceToHost, c->stream));
+    int r = syncStream(c);
+    float t = 0;
+    cudaEventElapsedTime(&t, e0, e1);
+    c->stats.ms[X265CU_K_PIXEL] += t;
+    if (ms) *ms = t;
+    c->freeEvents.push_back(e0); c->freeEvents.push_back(e1);
+    return r;
+}
+
+int x265cu_frame_var(x265cu_ctx* c, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride,
+                     uint32_t* energy, uint64_t sums[6])
+{
+    if (!c || !y || !energy || !sums || ((u == NULL) != (v == NULL)))
+        return c ? fail(c, X265CU_EINVAL, "x265cu_frame_var: bad argument") : X265CU_EINVAL;
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CU_TRY(c, cudaSetDevice(c->cfg.device));
+    const int W = c->cfg.srcWidth, H = c->cfg.srcHeight;
+    const int bxN = (W + 15) / 16, byN = (H + 15) / 16;
+    const size_t yp = alignUp((size_t)bxN * 16, 64), cp = alignUp((size_t)bxN * 8, 64);
+    const size_t yBytes = yp * byN * 16 * c->pb, cBytes = cp * byN * 8 * c->pb;
+    const size_t eBytes = alignUp((size_t)bxN * byN * 4, 256);
+    if (growDevice(c, &c->dGeneric, &c->dGenericCap, yBytes + 2 * cBytes + eBytes + 256)) return X265CU_ECUDA;
+    uint8_t* dY = c->dGeneric; uint8_t* dU = dY + yBytes; uint8_t* dV = dU + cBytes; unsigned int* dE = (unsigned int*)(dV + cBytes);
+    CU_TRY(c, cudaMemcpy2DAsync(dY, yp * c->pb, y, (size_t)yStride * c->pb, (size_t)bxN * 16 * c->pb, byN * 16, cudaMemcpyHostToDevice, c->stream));
+    if (u)
+    {
+        CU_TRY(c, cudaMemcpy2DAsync(dU, cp * c->pb, u, (size_t)cStride * c->pb, (size_t)bxN * 8 * c->pb, byN * 8, cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(c, cudaMemcpy2DAsync(dV, cp * c->pb, v, (size_t)cStride * c->pb, (size_t)bxN * 8 * c->pb, byN * 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    c->stats.h2dBytes += (int64_t)(yBytes + (u ? 2 * cBytes : 0));
+    CU_TRY(c, cudaMemsetAsync(c->dSmall, 0, 6 * sizeof(unsigned long long), c->stream));
+    {
+        KernelScope ks(c, X265CU_K_VAR);
+        int blocks = (bxN * byN + 7) / 8;
+        if (c->pb == 1)
+            frame_var_kernel<uint8_t><<<blocks, 256, 0, c->stream>>>((const uint8_t*)dY, (int64_t)yp, u ? (const uint8_t*)dU : NULL, u ? (const uint8_t*)dV : NULL, (int64_t)cp, bxN, byN, dE, c->dSmall);
+        else
+            frame_var_kernel<uint16_t><<<blocks, 256, 0, c->stream>>>((const uint16_t*)dY, (int64_t)yp, u ? (const uint16_t*)dU : NULL, u ? (const uint16_t*)dV : NULL, (int64_t)cp, bxN, byN, dE, c->dSmall);
+    }
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaMemcpyAsync(energy, dE, (size_t)bxN * byN * 4, cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long hs[6];
+    CU_TRY(c, cudaMemcpyAsync(hs, c->dSmall, sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
+    int r = syncStream(c);
+    for (int i = 0; i < 6; i++) sums[i] = hs[i];
+    return r;
+}
+
+} // extern "C"

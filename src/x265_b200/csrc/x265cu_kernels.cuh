@@ -1,0 +1,873 @@
+/* x265cu_kernels.cuh -- the CUDA kernels of libx265cu.so (hand-written for sm_100a).
+ *
+ * Kernel            replaces (x265_1.9/source)                                  bound
+ * ----------------  ----------------------------------------------------------  ----------------
+ * lowres_init       frame_init_lowres_core pixel.cpp:549 + extendPicBorder :908   HBM (8*Np*P bytes)
+ * intra_estimate    lowresIntraEstimate slicetype.cpp:230-336, intrapred.cpp      int ALU
+ * search            estimateCUCost slicetype.cpp:2068 + motionEstimate (lowres)   dependency latency
+ *                   motion.cpp:571; wavefront over CUs, one CTA per (job, slice)  / int ALU
+ * cost              estimateCUCost without searches (cost-only estimates)         L2/int ALU
+ * weight_planes     weight_pp_c pixel.cpp:463 over the 4 padded planes            HBM
+ * weight_cost       weightCostLuma slicetype.cpp:338-371                          HBM
+ * pixelcmp_*        sad/satd/sa8d primitives pixel.cpp:39-322                     HBM
+ * frame_var         pixel_var<16>/<8> pixel.cpp:649 (acEnergyCu)                  HBM
+ *
+ * Tensor cores are not used anywhere: this is byte/integer work (SAD, Hadamard, compares).
+ */
+#ifndef X265CU_KERNELS_CUH
+#define X265CU_KERNELS_CUH
+
+#include "x265cu_dev.cuh"
+
+#define X265CU_SA8D_16x16_K 3
+
+struct GeomDev
+{
+    int width, lines, stride, marginX, marginY, paddedLines;
+    int wCU, hCU, nCU;
+    int64_t planeSize, padOffset;
+};
+
+/* ===========================================================================================
+ * lowres_init: one thread = 4 consecutive samples of one padded output row, all four planes.
+ * Rows/columns in the margins recompute the clamped source position, so the border replication
+ * of extendPicBorder is fused into the same pass: no second kernel, no inter-block dependency.
+ * FILTER(a,b,c,d) = avg(avg(a,b), avg(c,d)) with round-up at both levels == chained __vavgu4.
+ * =========================================================================================== */
+template <typename P>
+__device__ __forceinline__ int lowres_px(const P* r0, const P* r1, int c0, int c1)
+{
+    int a = ((int)r0[c0] + (int)r1[c0] + 1) >> 1;
+    int b = ((int)r0[c1] + (int)r1[c1] + 1) >> 1;
+    return (a + b + 1) >> 1;
+}
+
+template <typename P>
+__global__ void __launch_bounds__(256) lowres_init_kernel(const P* __restrict__ src, int64_t srcPitch, P* __restrict__ planes, GeomDev g)
+{
+    const int oy = blockIdx.y;                                  /* padded row */
+    const int ox0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4; /* padded column of the first of 4 samples */
+    const int padW = g.width + 2 * g.marginX;
+    if (ox0 >= padW) return;
+    int yy = oy - g.marginY;
+    yy = yy < 0 ? 0 : (yy > g.lines - 1 ? g.lines - 1 : yy);
+    const P* r0 = src + (int64_t)(2 * yy) * srcPitch;
+    const P* r1 = r0 + srcPitch;
+    const P* r2 = r1 + srcPitch;
+    P* d0 = planes + (int64_t)oy * g.stride + ox0;
+    P* dh = d0 + g.planeSize;
+    P* dv = dh + g.planeSize;
+    P* dc = dv + g.planeSize;
+    const int x0 = ox0 - g.marginX;
+    int o0[4], oh[4], ov[4], oc[4];
+    if (sizeof(P) == 1 && x0 >= 0 && x0 + 3 < g.width && ox0 + 3 < padW)
+    {
+        /* interior fast path, 8-bit: 8 source bytes + 1 per row, packed rounded averages */
+        const uint8_t* s0 = (const uint8_t*)r0 + 2 * x0;
+        const uint8_t* s1 = (const uint8_t*)r1 + 2 * x0;
+        const uint8_t* s2 = (const uint8_t*)r2 + 2 * x0;
+        uint2 a = __ldg((const uint2*)s0), b = __ldg((const uint2*)s1), c = __ldg((const uint2*)s2);
+        uint32_t a8 = __ldg(s0 + 8), b8 = __ldg(s1 + 8), c8 = __ldg(s2 + 8);
+        uint32_t v01lo = __vavgu4(a.x, b.x), v01hi = __vavgu4(a.y, b.y), v01x = (a8 + b8 + 1) >> 1;
+        uint32_t v12lo = __vavgu4(b.x, c.x), v12hi = __vavgu4(b.y, c.y), v12x = (b8 + c8 + 1) >> 1;
+        /* even columns 0,2,4,6 / odd 1,3,5,7 / even shifted 2,4,6,8 */
+        uint32_t e01 = __byte_perm(v01lo, v01hi, 0x6420), o01 = __byte_perm(v01lo, v01hi, 0x7531);
+        uint32_t e12 = __byte_perm(v12lo, v12hi, 0x6420), o12 = __byte_perm(v12lo, v12hi, 0x7531);
+        uint32_t f01 = (e01 >> 8) | (v01x << 24), f12 = (e12 >> 8) | (v12x << 24);
+        *(uint32_t*)d0 = __vavgu4(e01, o01);
+        *(uint32_t*)dh = __vavgu4(o01, f01);
+        *(uint32_t*)dv = __vavgu4(e12, o12);
+        *(uint32_t*)dc = __vavgu4(o12, f12);
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        int xx = x0 + i;
+        xx = xx < 0 ? 0 : (xx > g.width - 1 ? g.width - 1 : xx);
+        int c0 = 2 * xx, c1 = c0 + 1, c2 = c0 + 2;
+        o0[i] = lowres_px(r0, r1, c0, c1);
+        oh[i] = lowres_px(r0, r1, c1, c2);
+        ov[i] = lowres_px(r1, r2, c0, c1);
+        oc[i] = lowres_px(r1, r2, c1, c2);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        if (ox0 + i < padW)
+        {
+            d0[i] = (P)o0[i]; dh[i] = (P)oh[i]; dv[i] = (P)ov[i]; dc[i] = (P)oc[i];
+        }
+}
+
+/* ===========================================================================================
+ * intra_estimate: one warp per CU.  The 33 neighbour samples and their [1 2 1] filtered copy
+ * live in shared memory; quad q predicts one mode, lane sub-block (bx,by) of it, straight from
+ * the neighbour arrays (no predicted block is ever stored), then SATD against fenc.
+ * Pass 1: DC, planar, angular 5..30 (8 modes = 8 quads); pass 2: best-2/+2; pass 3: best-1/+1.
+ * =========================================================================================== */
+template <typename P>
+__device__ __forceinline__ int intra_pred_px(int mode, int x, int y, const P* s, const P* f, int dcVal, int pixelMax)
+{
+    if (mode == 1)
+    {
+        /* intra_pred_dc_c<8> + dcPredFilter, intrapred.cpp:53-85 */
+        const P* above = s + 1;
+        const P* left = s + 17;
+        if (x == 0 && y == 0) return (above[0] + left[0] + 2 * dcVal + 2) >> 2;
+        if (y == 0) return (above[x] + 3 * dcVal + 2) >> 2;
+        if (x == 0) return (left[y] + 3 * dcVal + 2) >> 2;
+        return dcVal;
+    }
+    if (mode == 0)
+    {
+        /* planar_pred_c<3> on the filtered neighbours, intrapred.cpp:87-100 */
+        const P* above = f + 1;
+        const P* left = f + 17;
+        return ((7 - x) * left[y] + (7 - y) * above[x] + (x + 1) * above[8] + (y + 1) * left[8] + 8) >> 4;
+    }
+    /* intra_pred_ang_c<8>, intrapred.cpp:102-204; filtered neighbours only for modes 2, 18, 34 */
+    const P* n = (mode == 2 || mode == 18 || mode == 34) ? f : s;
+    const int hor = mode < 18;
+    /* S(k): neighbour k after the horizontal-mode swap of top and left */
+#define S_(k) ((int)n[(hor && (k) > 0) ? ((k) <= 16 ? (k) + 16 : (k) - 16) : (k)])
+    const int xx = hor ? y : x, yy = hor ? x : y;
+    const int angleOffset = hor ? 10 - mode : mode - 26;
+    /* angleTable[8 + angleOffset] = sign * {0,2,5,9,13,17,21,26,32}[|angleOffset|] */
+    const int mag = angleOffset < 0 ? -angleOffset : angleOffset;
+    const int absAng = (int)((0x201A15110D090502ull >> (8 * ((mag - 1) & 7))) & 0xff);
+    const int angle = mag == 0 ? 0 : (angleOffset < 0 ? -absAng : absAng);
+    if (angle == 0)
+    {
+        int v = S_(1 + xx);
+        if (xx == 0)
+        {
+            v = S_(1) + ((S_(17 + yy) - S_(0)) >> 1);
+            v = v < 0 ? 0 : (v > pixelMax ? pixelMax : v);
+        }
+        return v;
+    }
+    const int pos = (yy + 1) * angle;
+    const int off = pos >> 5, frac = pos & 31;
+    int invAngle = 0;
+    if (angle < 0)
+    {
+        /* invAngleTable = {4096,1638,910,630,482,390,315,256}[-angleOffset - 1] */
+        switch (mag)
+        {
+        case 1: invAngle = 4096; break; case 2: invAngle = 1638; break; case 3: invAngle = 910; break;
+        case 4: invAngle = 630; break;  case 5: invAngle = 482; break;  case 6: invAngle = 390; break;
+        case 7: invAngle = 315; break;  default: invAngle = 256; break;
+        }
+    }
+    /* ref(k): k >= -1 -> S(k+1) (top-left and top); k < -1 -> projected left neighbour */
+#define REF_(k) (((k) >= -1) ? S_((k) + 1) : S_(16 + ((128 + (-1 - (k)) * invAngle) >> 8)))
+    const int k0 = off + xx;
+    int v;
+    if (frac)
+        v = ((32 - frac) * REF_(k0) + frac * REF_(k0 + 1) + 16) >> 5;
+    else
+        v = REF_(k0);
+#undef REF_
+#undef S_
+    return v;
+}
+
+struct IntraOutDev
+{
+    int32_t* intraCost;
+    uint8_t* intraMode;
+    uint16_t* lowresCosts;    /* [0][0] */
+    int32_t* rowSatds;        /* [0][0], zeroed before launch */
+    unsigned long long* sums; /* costEst, costEstAq; zeroed before launch */
+    const int32_t* invQ;      /* or NULL */
+};
+
+template <typename P>
+__global__ void __launch_bounds__(256) intra_kernel(const P* __restrict__ plane0, GeomDev g, int lambda, int pixelMax, IntraOutDev o)
+{
+    __shared__ P sNb[8][2][36];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cuXY = blockIdx.x * 8 + warp;
+    if (cuXY >= g.nCU) return;
+    const int cuX = cuXY % g.wCU, cuY = cuXY / g.wCU;
+    const int q = lane >> 2, sub = lane & 3, bx = (sub & 1) * 4, by = (sub >> 1) * 4;
+    const P* pix = plane0 + (int64_t)(8 * cuY) * g.stride + 8 * cuX;
+    P* s = sNb[warp][0];
+    P* f = sNb[warp][1];
+    /* neighbours: 17 samples of the row above from the top-left, 16 of the left column (slicetype.cpp:264-267) */
+    {
+        const P* tl = pix - g.stride - 1;
+        if (lane < 17) s[lane] = tl[lane];
+        if (lane < 16) s[17 + lane] = tl[(int64_t)(lane + 1) * g.stride];
+        __syncwarp();
+        /* intraFilter<8>, intrapred.cpp:31-51 */
+        for (int i = lane; i < 33; i += 32)
+        {
+            int v;
+            if (i == 0) v = (2 * s[0] + s[1] + s[17] + 2) >> 2;
+            else if (i == 16 || i == 32) v = s[i];
+            else if (i == 17) v = (2 * s[17] + s[0] + s[18] + 2) >> 2;
+            else v = (2 * s[i] + s[i - 1] + s[i + 1] + 2) >> 2;
+            f[i] = (P)v;
+        }
+        __syncwarp();
+    }
+    int dcVal = 8;
+#pragma unroll
+    for (int i = 0; i < 8; i++) dcVal += s[1 + i] + s[17 + i];
+    dcVal >>= 4;   /* dcVal / 16, dcVal >= 0 */
+
+    /* fenc sub-block */
+    int fe[4][4];
+#pragma unroll
+    for (int y = 0; y < 4; y++)
+    {
+        typename Px<P>::Row4 r = Px<P>::load_aligned(pix + (int64_t)(by + y) * g.stride + bx);
+        Px<P>::unpack(r, fe[y]);
+    }
+
+    int icost = LA_COST_MAX, ilow = 0, acost = LA_COST_MAX, alow = 4;
+#pragma unroll 1
+    for (int pass = 0; pass < 3; pass++)
+    {
+        int mode, valid = 1;
+        if (pass == 0)
+            mode = q == 0 ? 1 : (q == 1 ? 0 : 5 * (q - 1));          /* DC, planar, 5,10,...,30 */
+        else
+        {
+            int dist = pass == 1 ? 2 : 1;
+            mode = q == 0 ? alow - dist : alow + dist;
+            valid = q < 2;
+            if (!valid) mode = 10;
+        }
+        int d[4][4];
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+#pragma unroll
+            for (int x = 0; x < 4; x++)
+                d[y][x] = fe[y][x] - intra_pred_px<P>(mode, bx + x, by + y, s, f, dcVal, pixelMax);
+        int cost = quad_sum(hadamard4x4_abs(d)) >> 1;
+        if (!valid) cost = LA_COST_MAX;
+        int c[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) c[k] = __shfl_sync(FULL_MASK, cost, 4 * k);
+        if (pass == 0)
+        {
+            if (c[0] < icost) { icost = c[0]; ilow = 1; }
+            if (c[1] < icost) { icost = c[1]; ilow = 0; }
+#pragma unroll
+            for (int k = 2; k < 8; k++)
+                if (c[k] < acost) { acost = c[k]; alow = 5 * (k - 1); }
+        }
+        else
+        {
+            int dist = pass == 1 ? 2 : 1;
+            int minusmode = alow - dist, plusmode = alow + dist;
+            if (c[0] < acost) { acost = c[0]; alow = minusmode; }
+            if (c[1] < acost) { acost = c[1]; alow = plusmode; }
+        }
+    }
+    if (acost < icost) { icost = acost; ilow = alow; }
+    icost += 5 * lambda + 4;
+    if (lane == 0)
+    {
+        int capped = icost < LA_LOWRES_COST_MASK ? icost : LA_LOWRES_COST_MASK;
+        o.lowresCosts[cuXY] = (uint16_t)capped;
+        o.intraCost[cuXY] = icost;
+        o.intraMode[cuXY] = (uint8_t)ilow;
+        int scored = (cuX > 0 && cuX < g.wCU - 1 && cuY > 0 && cuY < g.hCU - 1) || g.wCU <= 2 || g.hCU <= 2;
+        int icostAq = (scored && o.invQ) ? ((icost * o.invQ[cuXY] + 128) >> 8) : icost;
+        if (scored)
+        {
+            atomicAdd(&o.sums[0], (unsigned long long)icost);
+            atomicAdd(&o.sums[1], (unsigned long long)icostAq);
+        }
+        atomicAdd(&o.rowSatds[cuY], icostAq);
+    }
+}
+
+/* ===========================================================================================
+ * search / cost kernels
+ * =========================================================================================== */
+struct JobDev
+{
+    const void* fenc;          /* sample (0,0) of plane 0 of frames[b] */
+    const void* ref0w;         /* L0 reference for the SEARCH (weighted copy when isWeighted) */
+    const void* ref0;          /* un-weighted L0 reference (bidir MC, co-located) */
+    const void* ref1;
+    int* mvs[2];               /* device mirrors of lowresMvs[l][d-1] (packed int16 x | y << 16) */
+    int* mvCosts[2];
+    uint16_t* lowresCosts;     /* mirror of lowresCosts[d0][d1] */
+    int* rowSatds;             /* mirror of rowSatds[d0][d1] */
+    const int* intraCost;
+    const int* invQ;           /* or NULL */
+    /* packed output record of this job (device staging, copied to the host in one transfer) */
+    unsigned long long* outSums;   /* costEst, costEstAq, intraMbs */
+    int* outRows;
+    uint16_t* outLowresCosts;
+    int* outMvs[2];
+    int* outMvCosts[2];
+    int d0, d1;
+    int doSearch[2];
+    int bidir;
+};
+
+struct SearchItem { int job, firstY, lastY; };
+
+/* cost of one candidate for this lane's quad: partial over the lane's 4x4, quad-reduced */
+template <typename P>
+__device__ __forceinline__ int eval_cand(const LaCand& c, const LaSearch& s, const uint16_t* __restrict__ lut,
+                                         const RefPlanes<P>& ref, int px, int py, const typename Px<P>::Row4 fe[4])
+{
+    typename Px<P>::Row4 r[4];
+    int part = 0;
+    if (c.valid)
+    {
+        mc_fetch4x4<P>(ref, px, py, c.qx, c.qy, r);
+        part = c.satd ? satd4x4_abs<P>(fe, r) : sad4x4<P>(fe, r);
+    }
+    int cost = quad_sum(part);
+    if (c.satd) cost >>= 1;
+    if (c.addMv && c.valid) cost += la_mvcost(lut, s, c.qx, c.qy);
+    return c.valid ? cost : LA_COST_MAX;
+}
+
+#define SEARCH_MAX_ROWS 512
+
+template <typename P>
+__global__ void __launch_bounds__(512, 1) search_kernel(const JobDev* __restrict__ jobs, const SearchItem* __restrict__ items,
+                                                          GeomDev g, const uint16_t* __restrict__ lut)
+{
+    __shared__ int sProg[SEARCH_MAX_ROWS];
+    __shared__ unsigned long long sSums[3];
+    __shared__ JobDev sJob;
+    volatile int* prog = sProg;
+    const SearchItem it = items[blockIdx.x];
+    const int nRows = it.lastY - it.firstY + 1;
+    for (int i = threadIdx.x; i < nRows; i += blockDim.x) sProg[i] = g.wCU;
+    if (threadIdx.x < 3) sSums[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < (int)(sizeof(JobDev) / sizeof(int)); i += blockDim.x)
+        ((int*)&sJob)[i] = ((const int*)&jobs[it.job])[i];
+    __syncthreads();
+    const JobDev& job = sJob;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nWarps = blockDim.x >> 5;
+    const int q = lane >> 2, sub = lane & 3, bx = (sub & 1) * 4, by = (sub >> 1) * 4;
+    const int W = g.wCU, H = g.hCU;
+    const P* fencPlane = (const P*)job.fenc;
+    RefPlanes<P> r0w = { (const P*)job.ref0w, g.planeSize, g.stride };
+    RefPlanes<P> r0 = { (const P*)job.ref0, g.planeSize, g.stride };
+    RefPlanes<P> r1 = { (const P*)job.ref1, g.planeSize, g.stride };
+    const int bidir = job.bidir;
+
+    long long accCost = 0, accAq = 0;
+    int accIntra = 0;
+
+    for (int rowIdx = warp; rowIdx < nRows; rowIdx += nWarps)
+    {
+        const int cuY = it.lastY - rowIdx;
+        const int lastRow = rowIdx == 0;
+        int rowSum = 0;
+        int prevMv[2] = { 0, 0 };   /* MV of (cuX+1, cuY): our own previous result */
+        for (int cuX = W - 1; cuX >= 0; cuX--)
+        {
+            if (!lastRow)
+            {
+                const int need = cuX > 0 ? cuX - 1 : 0;
+                while (prog[rowIdx - 1] > need) { }
+                __syncwarp();
+                __threadfence_block();
+            }
+            const int cuXY = cuX + cuY * W;
+            const int px = 8 * cuX + bx, py = 8 * cuY + by;
+            typename Px<P>::Row4 fe[4];
+#pragma unroll
+            for (int y = 0; y < 4; y++)
+                fe[y] = Px<P>::load_aligned(fencPlane + (int64_t)(py + y) * g.stride + px);
+
+            int listCost[2] = { LA_COST_MAX, LA_COST_MAX };
+            int mvOut[2] = { 0, 0 };
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+            {
+                if (i == 1 && !bidir) break;
+                if (!job.doSearch[i])
+                {
+                    listCost[i] = job.mvCosts[i][cuXY];
+                    mvOut[i] = job.mvs[i][cuXY];
+                    continue;
+                }
+                volatile const int* mv = job.mvs[i];
+                int nb0 = 0, nb1 = 0, nb2 = 0, nb3 = 0, numc = 0;
+                if (cuX < W - 1) { nb0 = prevMv[i]; numc = 1; }
+                if (!lastRow)
+                {
+                    int below = mv[cuXY + W];
+                    if (numc == 0) nb0 = below; else nb1 = below;
+                    numc++;
+                    if (cuX > 0)
+                    {
+                        int bl = mv[cuXY + W - 1];
+                        if (numc == 1) nb1 = bl; else nb2 = bl;
+                        numc++;
+                    }
+                    if (cuX < W - 1)
+                    {
+                        int br = mv[cuXY + W + 1];
+                        if (numc == 2) nb2 = br; else nb3 = br;
+                        numc++;
+                    }
+                }
+                const RefPlanes<P>& ref = i ? r1 : r0w;
+                LaSearch s;
+                la_search_begin(s, cuX, cuY, W, H, bidir, numc, nb0, nb1, nb2, nb3);
+#pragma unroll 1
+                while (s.phase != LA_PH_DONE)
+                {
+                    LaCand c = la_candidate(s, q);
+                    int cost = eval_cand<P>(c, s, lut, ref, px, py, fe);
+                    int cs[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) cs[k] = __shfl_sync(FULL_MASK, cost, 4 * k);
+                    la_update(s, cs, lut);
+                }
+                listCost[i] = s.outcost;
+                mvOut[i] = la_pack_mv(s.outx, s.outy);
+                prevMv[i] = mvOut[i];
+                if (lane == 0)
+                {
+                    ((volatile int*)job.mvs[i])[cuXY] = mvOut[i];
+                    job.mvCosts[i][cuXY] = s.outcost;
+                    job.outMvs[i][cuXY] = mvOut[i];
+                    job.outMvCosts[i][cuXY] = s.outcost;
+                }
+            }
+
+            int bi0 = LA_COST_MAX, bi1 = LA_COST_MAX;
+            if (bidir)
+            {
+                /* quad 0: avg(L0-MC, L1-MC) on the UN-weighted references; quad 1: co-located average */
+                typename Px<P>::Row4 a[4], b[4];
+                int part = 0;
+                if (q < 2)
+                {
+                    int m0 = q == 0 ? mvOut[0] : 0, m1 = q == 0 ? mvOut[1] : 0;
+                    mc_fetch4x4<P>(r0, px, py, la_mv_x(m0), la_mv_y(m0), a);
+                    mc_fetch4x4<P>(r1, px, py, la_mv_x(m1), la_mv_y(m1), b);
+#pragma unroll
+                    for (int y = 0; y < 4; y++) a[y] = Px<P>::avg(a[y], b[y]);
+                    part = satd4x4_abs<P>(fe, a);
+                }
+                int cost = quad_sum(part) >> 1;
+                bi0 = __shfl_sync(FULL_MASK, cost, 0);
+                bi1 = __shfl_sync(FULL_MASK, cost, 4);
+            }
+            const int hasQ = job.invQ != NULL;
+            LaCuResult res = la_cu_finish(cuX, cuY, W, H, bidir, listCost[0], listCost[1], bi0, bi1, job.intraCost[cuXY],
+                                          hasQ, hasQ ? job.invQ[cuXY] : 256);
+            if (res.scored)
+            {
+                accCost += res.bcost;
+                accAq += res.bcostAq;
+                accIntra += res.intraMb;
+            }
+            rowSum += res.bcostAq;
+            if (lane == 0)
+            {
+                job.lowresCosts[cuXY] = res.lowresCost;
+                job.outLowresCosts[cuXY] = res.lowresCost;
+            }
+            __syncwarp();
+            if (lane == 0)
+            {
+                __threadfence_block();
+                prog[rowIdx] = cuX;
+            }
+        }
+        if (lane == 0)
+        {
+            job.rowSatds[cuY] = rowSum;
+            job.outRows[cuY] = rowSum;
+        }
+    }
+    if (lane == 0)
+    {
+        atomicAdd(&sSums[0], (unsigned long long)accCost);
+        atomicAdd(&sSums[1], (unsigned long long)accAq);
+        atomicAdd(&sSums[2], (unsigned long long)accIntra);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3)
+        atomicAdd(&job.outSums[threadIdx.x], sSums[threadIdx.x]);
+}
+
+/* cost-only estimates (both bDoSearch false): every CU is independent.  grid = (hCU, jobs);
+ * a block owns one CU row of one job, so rowSatds needs no atomics. */
+template <typename P>
+__global__ void __launch_bounds__(128) cost_kernel(const JobDev* __restrict__ jobs, const int* __restrict__ jobIdx, GeomDev g)
+{
+    __shared__ int sRow;
+    __shared__ unsigned long long sSums[3];
+    const JobDev& job = jobs[jobIdx[blockIdx.y]];
+    const int cuY = blockIdx.x;
+    const int W = g.wCU, H = g.hCU;
+    if (threadIdx.x == 0) sRow = 0;
+    if (threadIdx.x < 3) sSums[threadIdx.x] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bidir = job.bidir;
+    const int hasQ = job.invQ != NULL;
+    int rowSum = 0, accIntra = 0;
+    long long accCost = 0, accAq = 0;
+    if (!bidir)
+    {
+        for (int cuX = threadIdx.x; cuX < W; cuX += blockDim.x)
+        {
+            const int cuXY = cuX + cuY * W;
+            LaCuResult res = la_cu_finish(cuX, cuY, W, H, 0, job.mvCosts[0][cuXY], LA_COST_MAX, LA_COST_MAX, LA_COST_MAX,
+                                          job.intraCost[cuXY], hasQ, hasQ ? job.invQ[cuXY] : 256);
+            if (res.scored) { accCost += res.bcost; accAq += res.bcostAq; accIntra += res.intraMb; }
+            rowSum += res.bcostAq;
+            job.lowresCosts[cuXY] = res.lowresCost;
+            job.outLowresCosts[cuXY] = res.lowresCost;
+        }
+    }
+    else
+    {
+        const P* fencPlane = (const P*)job.fenc;
+        RefPlanes<P> r0 = { (const P*)job.ref0, g.planeSize, g.stride };
+        RefPlanes<P> r1 = { (const P*)job.ref1, g.planeSize, g.stride };
+        const int q = lane >> 2, sub = lane & 3, bx = (sub & 1) * 4, by = (sub >> 1) * 4;
+        const int nWarps = blockDim.x >> 5;
+        for (int base = warp * 4; base < W; base += nWarps * 4)
+        {
+            const int cuX = base + (q >> 1);
+            const int cand = q & 1;
+            const int valid = cuX < W;
+            const int cuXY = (valid ? cuX : 0) + cuY * W;
+            int part = 0;
+            int mv0 = 0, mv1 = 0;
+            if (valid)
+            {
+                mv0 = job.mvs[0][cuXY]; mv1 = job.mvs[1][cuXY];
+                const int px = 8 * cuX + bx, py = 8 * cuY + by;
+                typename Px<P>::Row4 fe[4], a[4], b[4];
+#pragma unroll
+                for (int y = 0; y < 4; y++)
+                    fe[y] = Px<P>::load_aligned(fencPlane + (int64_t)(py + y) * g.stride + px);
+                int m0 = cand == 0 ? mv0 : 0, m1 = cand == 0 ? mv1 : 0;
+                mc_fetch4x4<P>(r0, px, py, la_mv_x(m0), la_mv_y(m0), a);
+                mc_fetch4x4<P>(r1, px, py, la_mv_x(m1), la_mv_y(m1), b);
+#pragma unroll
+                for (int y = 0; y < 4; y++) a[y] = Px<P>::avg(a[y], b[y]);
+                part = satd4x4_abs<P>(fe, a);
+            }
+            int cost = quad_sum(part) >> 1;
+            int other = __shfl_down_sync(FULL_MASK, cost, 4);   /* co-located candidate of the same CU */
+            if (valid && cand == 0 && sub == 0)
+            {
+                LaCuResult res = la_cu_finish(cuX, cuY, W, H, 1, job.mvCosts[0][cuXY], job.mvCosts[1][cuXY], cost, other,
+                                              job.intraCost[cuXY], hasQ, hasQ ? job.invQ[cuXY] : 256);
+                if (res.scored) { accCost += res.bcost; accAq += res.bcostAq; }
+                rowSum += res.bcostAq;
+                job.lowresCosts[cuXY] = res.lowresCost;
+                job.outLowresCosts[cuXY] = res.lowresCost;
+            }
+        }
+    }
+    rowSum = warp_sum(rowSum);
+    accIntra = warp_sum(accIntra);
+    /* 64-bit sums: reduce as two 32-bit halves is unnecessary -- per-row totals fit 32 bits */
+    int c32 = warp_sum((int)accCost), a32 = warp_sum((int)accAq);
+    if (lane == 0)
+    {
+        atomicAdd(&sRow, rowSum);
+        atomicAdd(&sSums[0], (unsigned long long)(unsigned int)c32);
+        atomicAdd(&sSums[1], (unsigned long long)(unsigned int)a32);
+        atomicAdd(&sSums[2], (unsigned long long)(unsigned int)accIntra);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        job.rowSatds[cuY] = sRow;
+        job.outRows[cuY] = sRow;
+    }
+    if (threadIdx.x < 3)
+        atomicAdd(&job.outSums[threadIdx.x], sSums[threadIdx.x]);
+}
+
+/* ===========================================================================================
+ * weighted prediction helpers
+ * =========================================================================================== */
+struct WeightDev
+{
+    const void* src;     /* buffer[0] of the reference (start of the padded plane 0) */
+    void* dst;           /* weighted copy, same layout (4 padded planes) */
+    int scale, round, shift, offset;   /* weight_pp arguments (round/shift already include the 14-depth correction) */
+};
+
+/* weight_pp_c (pixel.cpp:463-488) over all four padded planes: dst = clip(((w0 * (src << corr) + round) >> shift) + offset) */
+template <typename P>
+__global__ void __launch_bounds__(256) weight_planes_kernel(const WeightDev* __restrict__ items, int64_t totalSamples, int correction, int pixelMax)
+{
+    const WeightDev w = items[blockIdx.y];
+    const P* src = (const P*)w.src;
+    P* dst = (P*)w.dst;
+    const int64_t per = 16 / sizeof(P);
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * per; i < totalSamples; i += (int64_t)gridDim.x * blockDim.x * per)
+    {
+        uint4 v = __ldg((const uint4*)(src + i));
+        P* pv = (P*)&v;
+#pragma unroll
+        for (int k = 0; k < (int)per; k++)
+        {
+            int val = (int)(int16_t)((int)pv[k] << correction);
+            int r = ((w.scale * val + w.round) >> w.shift) + w.offset;
+            pv[k] = (P)(r < 0 ? 0 : (r > pixelMax ? pixelMax : r));
+        }
+        *(uint4*)(dst + i) = v;
+    }
+}
+
+struct WeightCostDev
+{
+    const void* fenc;    /* sample (0,0) of plane 0 */
+    const void* ref;     /* sample (0,0) of plane 0 of the reference */
+    const int* intraCost;
+    int weighted, scale, round, shift, offset;
+};
+
+/* weightCostLuma (slicetype.cpp:338-371): the weighted reference is never materialised, the weight
+ * is applied to the reference samples on the fly.  grid = (ceil(nCU / 8 / warpsPerBlock), items). */
+template <typename P>
+__global__ void __launch_bounds__(256) weight_cost_kernel(const WeightCostDev* __restrict__ items, unsigned int* __restrict__ costs,
+                                                           GeomDev g, int correction, int pixelMax)
+{
+    const WeightCostDev w = items[blockIdx.y];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
+    const int q = lane >> 2, sub = lane & 3, bx = (sub & 1) * 4, by = (sub >> 1) * 4;
+    const P* fenc = (const P*)w.fenc;
+    const P* ref = (const P*)w.ref;
+    unsigned int acc = 0;
+    for (int base = (blockIdx.x * nWarps + warp) * 8; base < g.nCU; base += gridDim.x * nWarps * 8)
+    {
+        const int mb = base + q;
+        const int valid = mb < g.nCU;
+        int part = 0;
+        if (valid)
+        {
+            const int cuX = mb % g.wCU, cuY = mb / g.wCU;
+            const int64_t off = (int64_t)(8 * cuY + by) * g.stride + 8 * cuX + bx;
+            int d[4][4];
+#pragma unroll
+            for (int y = 0; y < 4; y++)
+            {
+                int a[4], b[4];
+                Px<P>::unpack(Px<P>::load_aligned(ref + off + (int64_t)y * g.stride), a);
+                Px<P>::unpack(Px<P>::load_aligned(fenc + off + (int64_t)y * g.stride), b);
+#pragma unroll
+                for (int x = 0; x < 4; x++)
+                {
+                    int v = a[x];
+                    if (w.weighted)
+                    {
+                        int val = (int)(int16_t)(v << correction);
+                        v = ((w.scale * val + w.round) >> w.shift) + w.offset;
+                        v = v < 0 ? 0 : (v > pixelMax ? pixelMax : v);
+                    }
+                    d[y][x] = v - b[x];
+                }
+            }
+            part = hadamard4x4_abs(d);
+        }
+        int satd = quad_sum(part) >> 1;
+        if (valid && sub == 0)
+        {
+            int ic = w.intraCost[mb];
+            acc += (unsigned int)(satd < ic ? satd : ic);
+        }
+    }
+    acc = (unsigned int)warp_sum((int)acc);
+    if (lane == 0 && acc)
+        atomicAdd(&costs[blockIdx.y], acc);
+}
+
+/* ===========================================================================================
+ * pixel primitives as batch kernels (common/pixel.cpp:39-322)
+ * =========================================================================================== */
+/* 8-point Hadamard abs-sum pieces for sa8d: lane owns a 4x4 quadrant of the 8x8 difference block;
+ * the 8x8 transform = 4x4 transform inside each quadrant, then a 2x2 butterfly across quadrants. */
+__device__ __forceinline__ int sa8d_quad_abs(int d[4][4], int sub)
+{
+    /* in-quadrant 4x4 Hadamard (no abs) */
+#pragma unroll
+    for (int y = 0; y < 4; y++)
+    {
+        int s01 = d[y][0] + d[y][1], d01 = d[y][0] - d[y][1];
+        int s23 = d[y][2] + d[y][3], d23 = d[y][2] - d[y][3];
+        d[y][0] = s01 + s23; d[y][1] = d01 + d23; d[y][2] = s01 - s23; d[y][3] = d01 - d23;
+    }
+#pragma unroll
+    for (int x = 0; x < 4; x++)
+    {
+        int s01 = d[0][x] + d[1][x], d01 = d[0][x] - d[1][x];
+        int s23 = d[2][x] + d[3][x], d23 = d[2][x] - d[3][x];
+        d[0][x] = s01 + s23; d[1][x] = d01 + d23; d[2][x] = s01 - s23; d[3][x] = d01 - d23;
+    }
+    int sum = 0;
+#pragma unroll
+    for (int y = 0; y < 4; y++)
+#pragma unroll
+        for (int x = 0; x < 4; x++)
+        {
+            int v = d[y][x];
+            int h = __shfl_xor_sync(FULL_MASK, v, 1);          /* horizontal neighbour quadrant */
+            v = (sub & 1) ? h - v : v + h;
+            int w = __shfl_xor_sync(FULL_MASK, v, 2);          /* vertical neighbour quadrant */
+            v = (sub & 2) ? w - v : v + w;
+            sum += abs(v);
+        }
+    return sum;
+}
+
+/* n block pairs at arbitrary sample offsets; one quad per pair (kind 3 = sa8d 16x16: four passes) */
+template <typename P>
+__global__ void __launch_bounds__(256) pixelcmp_batch_kernel(int kind, const P* __restrict__ A, int64_t strideA, const P* __restrict__ B, int64_t strideB,
+                                                              int n, const int64_t* __restrict__ offA, const int64_t* __restrict__ offB, int* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int sub = lane & 3, bx = (sub & 1) * 4, by = (sub >> 1) * 4;
+    const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const int valid = idx < n;
+    const P* a = A + (valid ? offA[idx] : 0);
+    const P* b = B + (valid ? offB[idx] : 0);
+    int result = 0;
+    const int nSub = kind == X265CU_SA8D_16x16_K ? 4 : 1;
+    for (int s8 = 0; s8 < nSub; s8++)
+    {
+        const int ox = (s8 & 1) * 8, oy = (s8 >> 1) * 8;
+        typename Px<P>::Row4 fa[4], fb[4];
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+        {
+            if (valid)
+            {
+                fa[y] = Px<P>::load(a + (int64_t)(oy + by + y) * strideA + ox + bx);
+                fb[y] = Px<P>::load(b + (int64_t)(oy + by + y) * strideB + ox + bx);
+            }
+            else { fa[y] = fb[y] = typename Px<P>::Row4(); }
+        }
+        if (kind == 0)
+            result += quad_sum(sad4x4<P>(fa, fb));
+        else if (kind == 1)
+            result += quad_sum(satd4x4_abs<P>(fa, fb)) >> 1;
+        else
+        {
+            int d[4][4];
+#pragma unroll
+            for (int y = 0; y < 4; y++)
+            {
+                int u[4], v[4];
+                Px<P>::unpack(fa[y], u); Px<P>::unpack(fb[y], v);
+#pragma unroll
+                for (int x = 0; x < 4; x++) d[y][x] = u[x] - v[x];
+            }
+            result += quad_sum(sa8d_quad_abs(d, sub));
+        }
+    }
+    if (kind >= 2) result = (result + 2) >> 2;
+    if (valid && sub == 0) out[idx] = result;
+}
+
+/* every aligned 8x8 block of plane 0 of two frames (the HBM-bound "SATD Gpix/s" kernel):
+ * a warp covers 8 horizontally adjacent CUs, so each load instruction touches full 32-byte sectors. */
+template <typename P>
+__global__ void __launch_bounds__(256) pixelcmp_frames_kernel(int kind, const P* __restrict__ A, const P* __restrict__ B, GeomDev g, int* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
+    const int q = lane >> 2, sub = lane & 3, bx = (sub & 1) * 4, by = (sub >> 1) * 4;
+    for (int base = (blockIdx.x * nWarps + warp) * 8; base < g.nCU; base += gridDim.x * nWarps * 8)
+    {
+        const int mb = base + q;
+        const int valid = mb < g.nCU;
+        const int cuX = valid ? mb % g.wCU : 0, cuY = valid ? mb / g.wCU : 0;
+        const int64_t off = (int64_t)(8 * cuY + by) * g.stride + 8 * cuX + bx;
+        typename Px<P>::Row4 fa[4], fb[4];
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+        {
+            fa[y] = Px<P>::load_aligned(A + off + (int64_t)y * g.stride);
+            fb[y] = Px<P>::load_aligned(B + off + (int64_t)y * g.stride);
+        }
+        int result;
+        if (kind == 0)
+            result = quad_sum(sad4x4<P>(fa, fb));
+        else if (kind == 1)
+            result = quad_sum(satd4x4_abs<P>(fa, fb)) >> 1;
+        else
+        {
+            int d[4][4];
+#pragma unroll
+            for (int y = 0; y < 4; y++)
+            {
+                int u[4], v[4];
+                Px<P>::unpack(fa[y], u); Px<P>::unpack(fb[y], v);
+#pragma unroll
+                for (int x = 0; x < 4; x++) d[y][x] = u[x] - v[x];
+            }
+            result = (quad_sum(sa8d_quad_abs(d, sub)) + 2) >> 2;
+        }
+        if (valid && sub == 0) out[mb] = result;
+    }
+}
+
+/* ===========================================================================================
+ * frame_var: pixel_var<16> (luma) + pixel_var<8> (Cb, Cr) per 16x16 block, acEnergyCu
+ * (slicetype.cpp:48-93).  One warp per 16x16 block.  sums6: wp_sum[0..2], wp_ssd[0..2].
+ * =========================================================================================== */
+template <typename P>
+__global__ void __launch_bounds__(256) frame_var_kernel(const P* __restrict__ y, int64_t ys, const P* __restrict__ u, const P* __restrict__ v, int64_t cs,
+                                                         int blocksX, int blocksY, unsigned int* __restrict__ energy, unsigned long long* __restrict__ sums6)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int blk = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (blk >= blocksX * blocksY) return;
+    const int bxi = blk % blocksX, byi = blk / blocksX;
+    /* luma: 256 samples, 8 per lane */
+    unsigned int sum = 0, sqr = 0;
+    {
+        const P* p = y + (int64_t)(16 * byi + (lane >> 1)) * ys + 16 * bxi + (lane & 1) * 8;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { unsigned int t = p[i]; sum += t; sqr += t * t; }
+    }
+    sum = (unsigned int)warp_sum((int)sum); sqr = (unsigned int)warp_sum((int)sqr);
+    unsigned int var = sqr - (unsigned int)(((unsigned long long)sum * sum) >> 8);
+    unsigned int s1 = 0, q1 = 0, s2 = 0, q2 = 0;
+    if (u && v)
+    {
+        const int64_t co = (int64_t)(8 * byi + (lane >> 2)) * cs + 8 * bxi + (lane & 3) * 2;
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+        {
+            unsigned int a = u[co + i], b = v[co + i];
+            s1 += a; q1 += a * a; s2 += b; q2 += b * b;
+        }
+        s1 = (unsigned int)warp_sum((int)s1); q1 = (unsigned int)warp_sum((int)q1);
+        s2 = (unsigned int)warp_sum((int)s2); q2 = (unsigned int)warp_sum((int)q2);
+        var += q1 - (unsigned int)(((unsigned long long)s1 * s1) >> 6);
+        var += q2 - (unsigned int)(((unsigned long long)s2 * s2) >> 6);
+    }
+    if (lane == 0)
+    {
+        energy[blk] = var;
+        atomicAdd(&sums6[0], (unsigned long long)sum);
+        atomicAdd(&sums6[3], (unsigned long long)sqr);
+        if (u && v)
+        {
+            atomicAdd(&sums6[1], (unsigned long long)s1); atomicAdd(&sums6[4], (unsigned long long)q1);
+            atomicAdd(&sums6[2], (unsigned long long)s2); atomicAdd(&sums6[5], (unsigned long long)q2);
+        }
+    }
+}
+
+#endif /* X265CU_KERNELS_CUH */

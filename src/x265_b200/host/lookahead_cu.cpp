@@ -1,0 +1,615 @@
+/* lookahead_cu.cpp -- see lookahead_cu.h.  Host layer above the C ABI; float decisions only. */
+#include "lookahead_cu.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+namespace x265cu {
+
+namespace {
+inline int imin(int a, int b) { return a < b ? a : b; }
+inline int imax(int a, int b) { return a > b ? a : b; }
+inline int iclip(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
+inline size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+/* x265_exp2fix8, common/common.cpp:94-101; LUT entries are round(256 * (2^(i/64) - 1)) */
+int exp2fix8(double x)
+{
+    static uint8_t lut[64];
+    static bool init = false;
+    if (!init)
+    {
+        for (int i = 0; i < 64; i++)
+            lut[i] = (uint8_t)floor(256.0 * (pow(2.0, i / 64.0) - 1.0) + 0.5);
+        init = true;
+    }
+    int i = (int)(x * (-64.f / 6.f) + 512.5f);
+    if (i < 0) return 0;
+    if (i > 1023) return 0xffff;
+    return (lut[i & 63] + 256) << (i >> 6) >> 8;
+}
+
+uint32_t crc32(const void* p, size_t n)
+{
+    static uint32_t tab[256];
+    if (!tab[1])
+        for (uint32_t i = 0; i < 256; i++)
+        {
+            uint32_t c = i;
+            for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+            tab[i] = c;
+        }
+    const uint8_t* b = (const uint8_t*)p;
+    uint32_t crc = 0xFFFFFFFFu;
+    while (n--) crc = tab[(crc ^ *b++) & 255] ^ (crc >> 8);
+    return ~crc;
+}
+} // namespace
+
+/* BitCost::CalculateLogs + BitCost::setQP(X265_LOOKAHEAD_QP), encoder/bitcost.cpp:30-59,73-90.
+ * lambda = x265_lambda_tab[12 + 6 * (depth - 8)] = 2^(depth - 8) exactly (constants.cpp:74-125). */
+void Lookahead::mvcostTable(int bitDepth, uint16_t* out, int* lambdaInt)
+{
+    const int M = 2 * 32768;
+    double lambda = (double)(1 << (2 * (bitDepth - 8)));
+    if (lambdaInt) *lambdaInt = (int)lambda;
+    float log2_2 = 2.0f / logf(2.0f);
+    for (int i = 0; i <= M; i++)
+    {
+        float bits = i ? logf((float)(i + 1)) * log2_2 + 1.718f : 0.718f;
+        double v = bits * lambda + 0.5f;
+        if (v > 32767.0) v = 32767.0;
+        out[M + i] = out[M - i] = (uint16_t)v;
+    }
+}
+
+Lookahead::Lookahead() : m_ctx(NULL), m_mvcost(NULL), m_lambda(1) { m_error[0] = 0; memset(&m_param, 0, sizeof(m_param)); }
+Lookahead::~Lookahead() { destroy(); }
+
+/* Lookahead::Lookahead + Lookahead::create, encoder/slicetype.cpp:490-591 */
+bool Lookahead::create(const Param& p)
+{
+    m_param = p;
+    if (!m_param.maxCUSize) m_param.maxCUSize = 64;
+    m_8x8Height = ((p.sourceHeight / 2) + 7) >> 3;
+    m_8x8Width = ((p.sourceWidth / 2) + 7) >> 3;
+    m_cuCount = m_8x8Width * m_8x8Height;
+    m_8x8Blocks = m_8x8Width > 2 && m_8x8Height > 2 ? (m_cuCount + 4 - 2 * (m_8x8Width + m_8x8Height)) : m_cuCount;
+    m_bAdaptiveQuant = p.aqMode || p.bEnableWeightedPred;
+    int slices = p.lookaheadSlices;
+    if (slices && !p.poolWorkers) slices = 0;
+    if (slices && p.sourceHeight < 720) slices = 0;
+    if (slices > 1)
+    {
+        m_numRowsPerSlice = m_8x8Height / slices;
+        m_numRowsPerSlice = imax(m_numRowsPerSlice, 10);
+        m_numRowsPerSlice = imin(m_numRowsPerSlice, m_8x8Height);
+        m_numCoopSlices = m_8x8Height / m_numRowsPerSlice;
+    }
+    else
+    {
+        m_numRowsPerSlice = m_8x8Height;
+        m_numCoopSlices = 1;
+    }
+    m_mvcost = (uint16_t*)malloc((4 * 32768 + 1) * sizeof(uint16_t));
+    if (!m_mvcost) return false;
+    mvcostTable(p.bitDepth, m_mvcost, &m_lambda);
+
+    x265cu_config cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.srcWidth = p.sourceWidth; cfg.srcHeight = p.sourceHeight; cfg.bitDepth = p.bitDepth;
+    cfg.marginX = m_param.maxCUSize + 32; cfg.marginY = m_param.maxCUSize + 16;   /* picyuv.cpp:62-63 */
+    cfg.bframes = p.bframes;
+    cfg.numFrameSlots = p.frameSlots > 0 ? p.frameSlots : p.lookaheadDepth + p.bframes + 8;
+    cfg.numCoopSlices = m_numCoopSlices; cfg.numRowsPerSlice = m_numRowsPerSlice;
+    cfg.bFrameBias = p.bFrameBias;
+    cfg.lookaheadLambda = m_lambda;
+    cfg.mvcost = m_mvcost + 2 * 32768;
+    cfg.device = p.device;
+    int r = x265cu_open(&cfg, &m_ctx);
+    if (r != X265CU_OK)
+    {
+        snprintf(m_error, sizeof(m_error), "x265cu_open failed (%d): %s", r, x265cu_last_error(NULL));
+        m_ctx = NULL;
+        return false;
+    }
+    x265cu_get_geometry(m_ctx, &m_geom);
+    m_freeSlots.clear();
+    for (int i = cfg.numFrameSlots - 1; i >= 0; i--) m_freeSlots.push_back(i);
+    return true;
+}
+
+void Lookahead::destroy()
+{
+    if (m_ctx) { x265cu_close(m_ctx); m_ctx = NULL; }
+    free(m_mvcost); m_mvcost = NULL;
+}
+
+/* Lowres::create, common/lowres.cpp:30-95: every output array, carved out of one pinned arena */
+Lowres* Lookahead::allocLowres()
+{
+    if (m_freeSlots.empty()) { snprintf(m_error, sizeof(m_error), "allocLowres: no free frame slot"); return NULL; }
+    Lowres* l = (Lowres*)calloc(1, sizeof(Lowres));
+    const int bf = m_param.bframes, n = m_cuCount, rows = m_8x8Height;
+    const size_t pb = m_geom.pixelBytes;
+    size_t bytes = alignUp((size_t)4 * m_geom.planeSize * pb, 64);
+    bytes += alignUp((size_t)n * 4, 64) + alignUp((size_t)n, 64);                         /* intraCost, intraMode */
+    bytes += 2 * alignUp((size_t)n * 8, 64) + 2 * alignUp((size_t)n * 4, 64);             /* qpAq, qpCuTree, invQ, blockVariance */
+    bytes += (size_t)(bf + 2) * (bf + 2) * (alignUp((size_t)rows * 4, 64) + alignUp((size_t)n * 2, 64));
+    bytes += (size_t)2 * (bf + 1) * 2 * alignUp((size_t)n * 4, 64);
+    l->arenaBytes = bytes;
+    if (posix_memalign((void**)&l->arena, 4096, bytes)) { free(l); return NULL; }
+    memset(l->arena, 0, bytes);
+    x265cu_host_register(l->arena, bytes);   /* pinned: async copies, no staging; failure only costs speed */
+    uint8_t* p = l->arena;
+    for (int i = 0; i < 4; i++)
+    {
+        l->buffer[i] = p + (size_t)i * m_geom.planeSize * pb;
+        l->lowresPlane[i] = (uint8_t*)l->buffer[i] + (size_t)m_geom.padOffset * pb;
+    }
+    p += alignUp((size_t)4 * m_geom.planeSize * pb, 64);
+    l->intraCost = (int32_t*)p; p += alignUp((size_t)n * 4, 64);
+    l->intraMode = p; p += alignUp((size_t)n, 64);
+    l->qpAqOffset = (double*)p; p += alignUp((size_t)n * 8, 64);
+    l->qpCuTreeOffset = (double*)p; p += alignUp((size_t)n * 8, 64);
+    l->invQscaleFactor = (int*)p; p += alignUp((size_t)n * 4, 64);
+    l->blockVariance = (uint32_t*)p; p += alignUp((size_t)n * 4, 64);
+    if (!m_param.aqMode)
+        l->qpAqOffset = l->qpCuTreeOffset = NULL, l->invQscaleFactor = NULL, l->blockVariance = NULL;   /* lowres.cpp:53-59 */
+    for (int i = 0; i < bf + 2; i++)
+        for (int j = 0; j < bf + 2; j++)
+        {
+            l->rowSatds[i][j] = (int32_t*)p; p += alignUp((size_t)rows * 4, 64);
+            l->lowresCosts[i][j] = (uint16_t*)p; p += alignUp((size_t)n * 2, 64);
+        }
+    for (int i = 0; i < bf + 1; i++)
+        for (int k = 0; k < 2; k++)
+        {
+            l->lowresMvs[k][i] = (MV*)p; p += alignUp((size_t)n * 4, 64);
+            l->lowresMvCosts[k][i] = (int32_t*)p; p += alignUp((size_t)n * 4, 64);
+        }
+    l->width = m_geom.width; l->lines = m_geom.lines; l->lumaStride = m_geom.stride; l->bframes = bf;
+    l->slot = m_freeSlots.back();
+    m_freeSlots.pop_back();
+    return l;
+}
+
+void Lookahead::freeLowres(Lowres* l)
+{
+    if (!l) return;
+    m_freeSlots.push_back(l->slot);
+    x265cu_host_unregister(l->arena);
+    free(l->arena);
+    free(l);
+}
+
+/* Lowres::init, common/lowres.cpp:128-165 */
+bool Lookahead::lowresInit(Lowres& l, const void* luma, intptr_t stride, int poc, bool copyPlanesBack)
+{
+    l.frameNum = poc;
+    memset(l.costEst, -1, sizeof(l.costEst));
+    memset(l.weightedCostDelta, 0, sizeof(l.weightedCostDelta));
+    memset(l.weightedRef, 0, sizeof(l.weightedRef));
+    if (l.qpAqOffset && l.invQscaleFactor)
+        memset(l.costEstAq, -1, sizeof(l.costEstAq));
+    for (int y = 0; y < l.bframes + 2; y++)
+        for (int x = 0; x < l.bframes + 2; x++)
+            l.rowSatds[y][x][0] = -1;
+    for (int i = 0; i < l.bframes + 1; i++)
+    {
+        l.lowresMvs[0][i][0].x = 0x7FFF;
+        l.lowresMvs[1][i][0].x = 0x7FFF;
+    }
+    for (int i = 0; i < l.bframes + 2; i++)
+        l.intraMbs[i] = 0;
+    int r = x265cu_frame_init(m_ctx, l.slot, luma, stride, 0, copyPlanesBack ? l.buffer[0] : NULL);
+    if (r) { snprintf(m_error, sizeof(m_error), "x265cu_frame_init: %s", x265cu_last_error(m_ctx)); return false; }
+    return true;
+}
+
+/* LookaheadTLD::calcAdaptiveQuantFrame, encoder/slicetype.cpp:95-228 (no quantOffsets).
+ * The per-block AC energy and the wp sums come from the GPU; the mapping below is the host float. */
+bool Lookahead::calcAdaptiveQuantFrame(Lowres& l, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride)
+{
+    const Param& param = m_param;
+    int maxCol = param.sourceWidth, maxRow = param.sourceHeight;
+    const int blocksX = (maxCol + 15) / 16, blocksY = (maxRow + 15) / 16;
+    const int blockCount = m_cuCount;
+    const bool needVar = !(param.aqMode == 0 || param.aqStrength == 0) || param.bEnableWeightedPred;
+    std::vector<uint32_t> energy((size_t)blocksX * blocksY);
+    uint64_t sums[6] = { 0, 0, 0, 0, 0, 0 };
+    if (needVar)
+    {
+        int r = x265cu_frame_var(m_ctx, y, yStride, u, v, cStride, &energy[0], sums);
+        if (r) { snprintf(m_error, sizeof(m_error), "x265cu_frame_var: %s", x265cu_last_error(m_ctx)); return false; }
+    }
+    for (int i = 0; i < 3; i++) { l.wp_sum[i] = sums[i]; l.wp_ssd[i] = sums[3 + i]; }
+
+    double strength = 0.f;
+    if (param.aqMode == 0 || param.aqStrength == 0)
+    {
+        if (param.aqMode && param.aqStrength == 0)
+        {
+            memset(l.qpCuTreeOffset, 0, blockCount * sizeof(double));
+            memset(l.qpAqOffset, 0, blockCount * sizeof(double));
+            for (int i = 0; i < blockCount; i++) l.invQscaleFactor[i] = 256;
+        }
+    }
+    else
+    {
+        int blockXY = 0;
+        double avg_adj_pow2 = 0, avg_adj = 0, qp_adj = 0;
+        double bias_strength = 0.f;
+        if (param.aqMode == 2 || param.aqMode == 3)
+        {
+            double bit_depth_correction = 1.f / (1 << (2 * (param.bitDepth - 8)));
+            l.frameVariance = 0;
+            for (int by = 0; by < blocksY; by++)
+            {
+                uint64_t rowVariance = 0;
+                for (int bx = 0; bx < blocksX; bx++)
+                {
+                    uint32_t e = energy[blockXY];
+                    l.blockVariance[blockXY] = e;
+                    rowVariance += e;
+                    qp_adj = pow(e * bit_depth_correction + 1, 0.1);
+                    l.qpCuTreeOffset[blockXY] = qp_adj;
+                    avg_adj += qp_adj;
+                    avg_adj_pow2 += qp_adj * qp_adj;
+                    blockXY++;
+                }
+                l.frameVariance += (rowVariance / maxCol);
+            }
+            l.frameVariance /= maxRow;
+            avg_adj /= blockCount;
+            avg_adj_pow2 /= blockCount;
+            strength = param.aqStrength * avg_adj;
+            avg_adj = avg_adj - 0.5f * (avg_adj_pow2 - (11.f)) / avg_adj;
+            bias_strength = param.aqStrength;
+        }
+        else
+            strength = param.aqStrength * 1.0397f;
+
+        blockXY = 0;
+        for (int by = 0; by < blocksY; by++)
+            for (int bx = 0; bx < blocksX; bx++)
+            {
+                if (param.aqMode == 3)
+                {
+                    qp_adj = l.qpCuTreeOffset[blockXY];
+                    qp_adj = strength * (qp_adj - avg_adj) + bias_strength * (1.f - 11.f / (qp_adj * qp_adj));
+                }
+                else if (param.aqMode == 2)
+                {
+                    qp_adj = l.qpCuTreeOffset[blockXY];
+                    qp_adj = strength * (qp_adj - avg_adj);
+                }
+                else
+                {
+                    uint32_t e = energy[blockXY];
+                    qp_adj = strength * (log2((double)(e > 1 ? e : 1)) - (14.427f + 2 * (param.bitDepth - 8)));
+                }
+                l.qpAqOffset[blockXY] = qp_adj;
+                l.qpCuTreeOffset[blockXY] = qp_adj;
+                l.invQscaleFactor[blockXY] = exp2fix8(qp_adj);
+                blockXY++;
+            }
+    }
+    if (param.bEnableWeightedPred)
+    {
+        maxCol = ((maxCol + 8) >> 4) << 4;
+        maxRow = ((maxRow + 8) >> 4) << 4;
+        int width[3] = { maxCol, maxCol >> 1, maxCol >> 1 };
+        int height[3] = { maxRow, maxRow >> 1, maxRow >> 1 };
+        for (int i = 0; i < 3; i++)
+        {
+            uint64_t sum = l.wp_sum[i], ssd = l.wp_ssd[i];
+            l.wp_ssd[i] = ssd - (sum * sum + (width[i] * height[i]) / 2) / (width[i] * height[i]);
+        }
+    }
+    int r = x265cu_frame_set_invqscale(m_ctx, l.slot, l.invQscaleFactor);
+    if (r) { snprintf(m_error, sizeof(m_error), "x265cu_frame_set_invqscale: %s", x265cu_last_error(m_ctx)); return false; }
+    return true;
+}
+
+/* LookaheadTLD::lowresIntraEstimate, encoder/slicetype.cpp:230-336 */
+bool Lookahead::lowresIntraEstimate(Lowres& l)
+{
+    x265cu_intra_out o;
+    o.intraCost = l.intraCost; o.intraMode = l.intraMode;
+    o.lowresCosts = l.lowresCosts[0][0]; o.rowSatds = l.rowSatds[0][0];
+    int r = x265cu_intra(m_ctx, l.slot, &o);
+    if (r) { snprintf(m_error, sizeof(m_error), "x265cu_intra: %s", x265cu_last_error(m_ctx)); return false; }
+    l.costEst[0][0] = o.sums[0];
+    l.costEstAq[0][0] = o.sums[1];
+    return true;
+}
+
+/* PreLookaheadGroup::processTasks for one frame, encoder/slicetype.cpp:831-856 */
+bool Lookahead::preLookahead(Lowres& l, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride, int poc, bool copyPlanesBack)
+{
+    if (!lowresInit(l, y, yStride, poc, copyPlanesBack)) return false;
+    if (m_bAdaptiveQuant)
+    {
+        if (!calcAdaptiveQuantFrame(l, y, yStride, u, v, cStride)) return false;
+    }
+    else
+        x265cu_frame_set_invqscale(m_ctx, l.slot, NULL);
+    return lowresIntraEstimate(l);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * CostEstimateGroup, encoder/slicetype.cpp:1899-2066
+ * ---------------------------------------------------------------------------------------- */
+void CostEstimateGroup::add(int p0, int p1, int b)
+{
+    m_batchMode = true;
+    Estimate& e = m_estimates[m_jobTotal++];
+    e.p0 = p0; e.p1 = p1; e.b = b;
+    if (m_jobTotal == MAX_BATCH_SIZE)
+        finishBatch();
+}
+
+bool CostEstimateGroup::finishBatch()
+{
+    bool ok = runEstimates(m_estimates, m_jobTotal, true);
+    m_jobTotal = 0;
+    return ok;
+}
+
+int64_t CostEstimateGroup::singleCost(int p0, int p1, int b, bool intraPenalty)
+{
+    Lowres* fenc = m_frames[b];
+    int64_t score;
+    if (fenc->costEst[b - p0][p1 - b] >= 0 && fenc->rowSatds[b - p0][p1 - b][0] != -1)
+        score = fenc->costEst[b - p0][p1 - b];
+    else
+    {
+        Estimate e = { p0, b, p1 };
+        if (!runEstimates(&e, 1, false)) return -1;
+        score = fenc->costEst[b - p0][p1 - b];
+    }
+    if (intraPenalty)
+        score += score * fenc->intraMbs[b - p0] / (m_lookahead.ncu() * 8);
+    return score;
+}
+
+namespace {
+/* first half of LookaheadTLD::weightsAnalyse (slicetype.cpp:416-455): the float guesses */
+struct WeightGuess { bool skip; int minscale, mindenom, curScale, curOffset; };
+
+WeightGuess weightGuess(const Lowres& fenc, const Lowres& ref, int depth)
+{
+    static const float epsilon = 1.f / 128.f;
+    WeightGuess g;
+    g.skip = true; g.minscale = g.mindenom = g.curScale = g.curOffset = 0;
+    float guessScale, fencMean, refMean;
+    if (fenc.wp_ssd[0] && ref.wp_ssd[0])
+        guessScale = sqrtf((float)fenc.wp_ssd[0] / ref.wp_ssd[0]);
+    else
+        guessScale = 1.0f;
+    fencMean = (float)fenc.wp_sum[0] / (fenc.lines * fenc.width) / (1 << (depth - 8));
+    refMean = (float)ref.wp_sum[0] / (fenc.lines * fenc.width) / (1 << (depth - 8));
+    if (fabsf(refMean - fencMean) < 0.5f && fabsf(1.f - guessScale) < epsilon)
+        return g;
+    /* WeightParam::setFromWeightAndOffset((int)(guessScale * 128 + 0.5f), 0, 7, true), slice.h:292-305 */
+    int denom = 7, w = (int)(guessScale * 128 + 0.5f);
+    while (denom > 0 && w > 127) { denom--; w >>= 1; }
+    w = imin(w, 127);
+    g.mindenom = denom; g.minscale = w;
+    int curScale = w;
+    int curOffset = (int)(fencMean - refMean * curScale / (1 << denom) + 0.5f);
+    if (curOffset < -128 || curOffset > 127)
+    {
+        curOffset = iclip(-128, 127, curOffset);
+        curScale = (int)((1 << denom) * (fencMean - curOffset) / refMean + 0.5f);
+        curScale = iclip(0, 127, curScale);
+    }
+    g.curScale = curScale; g.curOffset = curOffset;
+    g.skip = false;
+    return g;
+}
+} // namespace
+
+bool CostEstimateGroup::runEstimates(const Estimate* est, int n, bool batchMode)
+{
+    Lookahead& la = m_lookahead;
+    const Param& param = la.m_param;
+    std::vector<x265cu_job> jobs;
+    std::vector<int> jobOf;                 /* index into est[] */
+    std::vector<WeightGuess> guesses;
+    std::vector<x265cu_weight_item> witems;
+    std::vector<int> wjob;                  /* job index of each pair of weight items */
+
+    for (int i = 0; i < n; i++)
+    {
+        const int p0 = est[i].p0, p1 = est[i].p1, b = est[i].b;
+        Lowres* fenc = m_frames[b];
+        const int d0 = b - p0, d1 = p1 - b;
+        if (fenc->costEst[d0][d1] >= 0 && fenc->rowSatds[d0][d1][0] != -1)
+            continue;                       /* cached (estimateFrameCost :1982) */
+        x265cu_job j;
+        memset(&j, 0, sizeof(j));
+        j.fenc = fenc->slot; j.ref0 = m_frames[p0]->slot; j.ref1 = m_frames[p1]->slot;
+        j.d0 = d0; j.d1 = d1;
+        j.doSearch[0] = p0 < b && fenc->lowresMvs[0][d0 - 1][0].x == 0x7FFF;
+        j.doSearch[1] = p1 > b && fenc->lowresMvs[1][d1 - 1][0].x == 0x7FFF;
+        j.sliced = !batchMode;
+        fenc->weightedRef[d0].present = 0;
+        if (param.bEnableWeightedPred && j.doSearch[0])
+        {
+            WeightGuess g = weightGuess(*fenc, *m_frames[p0], param.bitDepth);
+            if (!g.skip)
+            {
+                x265cu_weight_item w0 = { fenc->slot, m_frames[p0]->slot, 0, 0, 0, 0 };
+                x265cu_weight_item w1 = { fenc->slot, m_frames[p0]->slot, 1, g.curScale, g.mindenom, g.curOffset };
+                witems.push_back(w0); witems.push_back(w1);
+                wjob.push_back((int)jobs.size());
+                guesses.push_back(g);
+            }
+        }
+        for (int l = 0; l < 2; l++)
+        {
+            int d = l ? d1 : d0;
+            if (j.doSearch[l])
+            {
+                j.mvs[l] = fenc->lowresMvs[l][d - 1];
+                j.mvCosts[l] = fenc->lowresMvCosts[l][d - 1];
+            }
+        }
+        j.lowresCosts = fenc->lowresCosts[d0][d1];
+        j.rowSatds = fenc->rowSatds[d0][d1];
+        jobs.push_back(j);
+        jobOf.push_back(i);
+    }
+    if (jobs.empty()) return true;
+
+    /* second half of weightsAnalyse (slicetype.cpp:432-487): the two SATD sweeps run on the GPU */
+    if (!witems.empty())
+    {
+        std::vector<uint32_t> costs(witems.size());
+        int r = x265cu_weight_cost_batch(la.m_ctx, (int)witems.size(), &witems[0], &costs[0]);
+        if (r) { snprintf(la.m_error, sizeof(la.m_error), "x265cu_weight_cost_batch: %s", x265cu_last_error(la.m_ctx)); return false; }
+        for (size_t k = 0; k < wjob.size(); k++)
+        {
+            x265cu_job& j = jobs[wjob[k]];
+            const WeightGuess& g = guesses[k];
+            Lowres* fenc = m_frames[est[jobOf[wjob[k]]].b];
+            unsigned int origscore = costs[2 * k], minscore = origscore;
+            if (!minscore) continue;
+            int minscale = g.minscale, mindenom = g.mindenom, minoff = 0, found = 0;
+            unsigned int s = costs[2 * k + 1];
+            if (s < minscore) { minscore = s; minscale = g.curScale; minoff = g.curOffset; found = 1; }
+            while (mindenom > 0 && !(minscale & 1)) { mindenom--; minscale >>= 1; }
+            if (!found || (minscale == 1 << mindenom && minoff == 0) || (float)minscore / origscore > 0.998f)
+                continue;
+            fenc->weightedCostDelta[j.d0] = minscore / origscore;     /* unsigned integer division, as in the reference */
+            fenc->weightedRef[j.d0].present = 1;
+            fenc->weightedRef[j.d0].scale = minscale;
+            fenc->weightedRef[j.d0].denom = mindenom;
+            fenc->weightedRef[j.d0].offset = minoff;
+            j.weighted = 1; j.wScale = minscale; j.wDenom = mindenom; j.wOffset = minoff;
+        }
+    }
+
+    std::vector<x265cu_job_result> res(jobs.size());
+    int r = x265cu_estimate_batch(la.m_ctx, (int)jobs.size(), &jobs[0], &res[0]);
+    if (r) { snprintf(la.m_error, sizeof(la.m_error), "x265cu_estimate_batch: %s", x265cu_last_error(la.m_ctx)); return false; }
+    for (size_t k = 0; k < jobs.size(); k++)
+    {
+        Lowres* fenc = m_frames[est[jobOf[k]].b];
+        const int d0 = jobs[k].d0, d1 = jobs[k].d1;
+        fenc->costEst[d0][d1] = res[k].costEst;
+        fenc->costEstAq[d0][d1] = res[k].costEstAq;
+        if (d1 == 0)
+            fenc->intraMbs[d0] += res[k].intraMbs;
+    }
+    return true;
+}
+
+} // namespace x265cu
+
+/* ================================================================================================
+ * flat C view
+ * ============================================================================================== */
+using namespace x265cu;
+
+extern "C" {
+
+void* x265cuh_open(const x265cuh_params* p, char* err, int errLen)
+{
+    Param q;
+    memset(&q, 0, sizeof(q));
+    q.sourceWidth = p->sourceWidth; q.sourceHeight = p->sourceHeight; q.bitDepth = p->bitDepth; q.maxCUSize = p->maxCUSize;
+    q.bframes = p->bframes; q.lookaheadDepth = p->lookaheadDepth; q.lookaheadSlices = p->lookaheadSlices; q.poolWorkers = p->poolWorkers;
+    q.bEnableWeightedPred = p->bEnableWeightedPred; q.aqMode = p->aqMode; q.aqStrength = p->aqStrength;
+    q.bFrameBias = p->bFrameBias; q.device = p->device; q.frameSlots = p->frameSlots;
+    Lookahead* la = new Lookahead();
+    if (!la->create(q))
+    {
+        if (err && errLen > 0) snprintf(err, errLen, "%s", la->m_error);
+        delete la;
+        return NULL;
+    }
+    return la;
+}
+
+void x265cuh_close(void* la) { delete (Lookahead*)la; }
+void* x265cuh_ctx(void* la) { return ((Lookahead*)la)->m_ctx; }
+const char* x265cuh_error(void* la) { return ((Lookahead*)la)->m_error; }
+
+void x265cuh_info(void* h, int* o)
+{
+    Lookahead* la = (Lookahead*)h;
+    o[0] = la->m_8x8Width; o[1] = la->m_8x8Height; o[2] = la->m_cuCount; o[3] = la->m_geom.stride;
+    o[4] = (int)la->m_geom.planeSize; o[5] = la->m_numCoopSlices; o[6] = la->m_numRowsPerSlice; o[7] = la->m_lambda;
+    o[8] = la->m_geom.pixelBytes; o[9] = la->m_geom.paddedLines; o[10] = (int)la->m_geom.padOffset; o[11] = la->m_8x8Blocks;
+}
+
+uint32_t x265cuh_mvcost_crc(void* h) { return crc32(((Lookahead*)h)->m_mvcost, (4 * 32768 + 1) * sizeof(uint16_t)); }
+uint32_t x265cuh_crc32(const void* p, size_t n) { return crc32(p, n); }
+
+void* x265cuh_frame_alloc(void* la) { return ((Lookahead*)la)->allocLowres(); }
+void x265cuh_frame_free(void* la, void* f) { ((Lookahead*)la)->freeLowres((Lowres*)f); }
+
+int x265cuh_pre_lookahead(void* la, void* frame, const void* y, intptr_t ys, const void* u, const void* v, intptr_t cs, int poc, int planesBack)
+{
+    return ((Lookahead*)la)->preLookahead(*(Lowres*)frame, y, ys, u, v, cs, poc, planesBack != 0) ? 0 : -1;
+}
+
+int x265cuh_estimate(void* h, void** frames, int nframes, const int* triples, int n, int batch, int64_t* scores)
+{
+    Lookahead* la = (Lookahead*)h;
+    (void)nframes;
+    CostEstimateGroup grp(*la, (Lowres**)frames);
+    if (batch)
+    {
+        for (int i = 0; i < n; i++)
+            grp.add(triples[3 * i], triples[3 * i + 1], triples[3 * i + 2]);
+        if (!grp.finishBatch()) return -1;
+        for (int i = 0; i < n; i++)
+        {
+            Lowres* f = (Lowres*)frames[triples[3 * i + 2]];
+            scores[i] = f->costEst[triples[3 * i + 2] - triples[3 * i]][triples[3 * i + 1] - triples[3 * i + 2]];
+        }
+    }
+    else
+        for (int i = 0; i < n; i++)
+        {
+            scores[i] = grp.singleCost(triples[3 * i], triples[3 * i + 1], triples[3 * i + 2], false);
+            if (scores[i] < 0) return -1;
+        }
+    return 0;
+}
+
+const void* x265cuh_array(void* h, void* frame, int which, int d0, int d1, size_t* bytes)
+{
+    Lookahead* la = (Lookahead*)h;
+    Lowres* l = (Lowres*)frame;
+    const size_t n = la->m_cuCount;
+    switch (which)
+    {
+    case 0: *bytes = (size_t)4 * la->m_geom.planeSize * la->m_geom.pixelBytes; return l->buffer[0];
+    case 1: *bytes = n * 4; return l->intraCost;
+    case 2: *bytes = n; return l->intraMode;
+    case 3: *bytes = l->invQscaleFactor ? n * 4 : 0; return l->invQscaleFactor;
+    case 4: *bytes = n * 2; return l->lowresCosts[d0][d1];
+    case 5: *bytes = (size_t)la->m_8x8Height * 4; return l->rowSatds[d0][d1];
+    case 6: *bytes = n * 4; return l->lowresMvs[d0][d1 - 1];
+    case 7: *bytes = n * 4; return l->lowresMvCosts[d0][d1 - 1];
+    default: *bytes = 0; return NULL;
+    }
+}
+
+void x265cuh_frame_scalars(void* frame, int d0, int d1, int64_t* o)
+{
+    Lowres* l = (Lowres*)frame;
+    o[0] = l->costEst[d0][d1]; o[1] = l->costEstAq[d0][d1]; o[2] = l->intraMbs[d0];
+    o[3] = (int64_t)l->wp_ssd[0]; o[4] = (int64_t)l->wp_sum[0];
+    o[5] = l->weightedRef[d0].present; o[6] = l->weightedRef[d0].scale; o[7] = l->weightedRef[d0].denom;
+    o[8] = l->weightedRef[d0].offset;
+}
+
+} // extern "C"

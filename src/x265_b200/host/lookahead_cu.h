@@ -1,0 +1,167 @@
+/* lookahead_cu.h -- host-side lookahead layer above the C ABI (libx265cu.so), in x265's own
+ * language (C++), mirroring the reference's interface for this path so that callers and tests
+ * read like x265 (names, argument meaning and error behaviour):
+ *
+ *   x265cu::Lowres              <-> struct Lowres                  common/lowres.h:107-159
+ *   x265cu::Lookahead           <-> class Lookahead (cost side)    encoder/slicetype.h:98-176
+ *   ::preLookahead()            <-> PreLookaheadGroup::processTasks encoder/slicetype.cpp:831-856
+ *   ::calcAdaptiveQuantFrame()  <-> LookaheadTLD::calcAdaptiveQuantFrame  slicetype.cpp:95-228
+ *   ::weightsAnalyse()          <-> LookaheadTLD::weightsAnalyse   slicetype.cpp:391-488
+ *   x265cu::CostEstimateGroup   <-> class CostEstimateGroup        encoder/slicetype.h:199-240
+ *
+ * Everything integer and data-parallel runs on the GPU through the C ABI; the small float decisions
+ * (AQ strength mapping, weight guesses, mvcost table) stay here on the host, compiled with the
+ * reference's flags (-ffast-math) because the bitstream depends on them.
+ * The slice-type decision, scenecut, cuTree and VBV logic of x265 are consumers of this layer and
+ * are NOT re-implemented (out of scope: they stay x265's own code).
+ */
+#ifndef X265CU_LOOKAHEAD_CU_H
+#define X265CU_LOOKAHEAD_CU_H
+
+#include <stdint.h>
+#include <stddef.h>
+#include <vector>
+
+#include "../../../include/x265cu.h"
+
+namespace x265cu {
+
+enum { BFRAME_MAX = 16, MAX_BATCH_SIZE = 512 };
+
+struct MV { int16_t x, y; };
+
+/* the subset of x265_param the lookahead cost path reads */
+struct Param
+{
+    int sourceWidth, sourceHeight;
+    int bitDepth;            /* X265_DEPTH of the build being replaced */
+    int maxCUSize;           /* g_maxCUSize (margins) */
+    int bframes;
+    int lookaheadDepth;
+    int lookaheadSlices;     /* as given by the user; normalised like Lookahead::Lookahead */
+    int poolWorkers;         /* size of the worker pool the host encoder would have had (slices need a pool) */
+    int bEnableWeightedPred;
+    int aqMode;              /* 0 none, 1 variance, 2 auto-variance, 3 auto-variance biased */
+    double aqStrength;
+    int bFrameBias;
+    int device;
+    int frameSlots;          /* 0 = lookaheadDepth + bframes + 8 */
+};
+
+struct WeightParam { int present, scale, denom, offset; };
+
+/* lookahead outputs of one frame: same members, meaning and layout as the reference's Lowres */
+struct Lowres
+{
+    int frameNum;
+    int slot;                /* device mirror index */
+    int width, lines;
+    intptr_t lumaStride;
+    int bframes;
+    void* buffer[4];         /* padded planes (pixel = uint8_t / uint16_t) */
+    void* lowresPlane[4];
+    int64_t costEst[BFRAME_MAX + 2][BFRAME_MAX + 2];
+    int64_t costEstAq[BFRAME_MAX + 2][BFRAME_MAX + 2];
+    int32_t* rowSatds[BFRAME_MAX + 2][BFRAME_MAX + 2];
+    int intraMbs[BFRAME_MAX + 2];
+    int32_t* intraCost;
+    uint8_t* intraMode;
+    uint16_t* lowresCosts[BFRAME_MAX + 2][BFRAME_MAX + 2];
+    int32_t* lowresMvCosts[2][BFRAME_MAX + 1];
+    MV* lowresMvs[2][BFRAME_MAX + 1];
+    double* qpAqOffset;
+    double* qpCuTreeOffset;
+    int* invQscaleFactor;
+    uint32_t* blockVariance;
+    uint64_t wp_ssd[3];
+    uint64_t wp_sum[3];
+    uint64_t frameVariance;
+    double weightedCostDelta[BFRAME_MAX + 2];
+    WeightParam weightedRef[BFRAME_MAX + 2];   /* reference keeps ReferencePlanes here; we keep the weight */
+    uint8_t* arena;          /* one pinned allocation holding every array above */
+    size_t arenaBytes;
+};
+
+class Lookahead
+{
+public:
+    Param m_param;
+    x265cu_ctx* m_ctx;
+    x265cu_geometry m_geom;
+    int m_8x8Width, m_8x8Height, m_8x8Blocks, m_cuCount;
+    int m_numCoopSlices, m_numRowsPerSlice;
+    bool m_bAdaptiveQuant;
+    uint16_t* m_mvcost;      /* BitCost::s_costs[X265_LOOKAHEAD_QP] (base pointer) */
+    int m_lambda;
+    char m_error[512];
+    std::vector<int> m_freeSlots;   /* device mirror slots not bound to a Lowres */
+
+    Lookahead();
+    ~Lookahead();
+    bool create(const Param& p);
+    void destroy();
+
+    Lowres* allocLowres();                 /* Lowres::create */
+    void freeLowres(Lowres* l);
+    /* Lowres::init (lowres.cpp:128-165); luma = PicYuv::m_picOrg[0] padded as copyFromPicture does */
+    bool lowresInit(Lowres& l, const void* luma, intptr_t stride, int poc, bool copyPlanesBack);
+    /* LookaheadTLD::calcAdaptiveQuantFrame; planes padded like PicYuv */
+    bool calcAdaptiveQuantFrame(Lowres& l, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride);
+    bool lowresIntraEstimate(Lowres& l);
+    /* PreLookaheadGroup::processTasks for one frame */
+    bool preLookahead(Lowres& l, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride, int poc, bool copyPlanesBack);
+
+    int64_t ncu() const { return m_8x8Blocks; }
+    static void mvcostTable(int bitDepth, uint16_t* out131073, int* lambdaInt);
+};
+
+/* same call protocol as the reference's CostEstimateGroup: add()/finishBatch() for batches,
+ * singleCost() for one estimate (cached results are returned without touching the GPU) */
+class CostEstimateGroup
+{
+public:
+    Lookahead& m_lookahead;
+    Lowres** m_frames;
+    bool m_batchMode;
+    struct Estimate { int p0, b, p1; } m_estimates[MAX_BATCH_SIZE];
+    int m_jobTotal;
+
+    CostEstimateGroup(Lookahead& l, Lowres** f) : m_lookahead(l), m_frames(f), m_batchMode(false), m_jobTotal(0) {}
+    void add(int p0, int p1, int b);
+    bool finishBatch();
+    int64_t singleCost(int p0, int p1, int b, bool intraPenalty = false);
+
+protected:
+    bool runEstimates(const Estimate* e, int n, bool batchMode);
+};
+
+} // namespace x265cu
+
+/* ---- flat C view of the layer for ctypes (tests, bench.py): handles are opaque pointers ---- */
+extern "C" {
+typedef struct x265cuh_params
+{
+    int sourceWidth, sourceHeight, bitDepth, maxCUSize, bframes, lookaheadDepth, lookaheadSlices, poolWorkers;
+    int bEnableWeightedPred, aqMode;
+    double aqStrength;
+    int bFrameBias, device, frameSlots;
+} x265cuh_params;
+void* x265cuh_open(const x265cuh_params* p, char* err, int errLen);
+void  x265cuh_close(void* la);
+void* x265cuh_ctx(void* la);                                  /* the underlying x265cu_ctx* */
+void  x265cuh_info(void* la, int* out16);                     /* wCU, hCU, nCU, stride, planeSize(lo32), numCoopSlices, numRowsPerSlice, lambda, pixelBytes */
+uint32_t x265cuh_mvcost_crc(void* la);
+void* x265cuh_frame_alloc(void* la);
+void  x265cuh_frame_free(void* la, void* frame);
+int   x265cuh_pre_lookahead(void* la, void* frame, const void* y, intptr_t ys, const void* u, const void* v, intptr_t cs, int poc, int planesBack);
+/* jobs: n triples (p0, p1, b) as indices into frames[]; batch != 0 -> add()+finishBatch(), else singleCost() each */
+int   x265cuh_estimate(void* la, void** frames, int nframes, const int* triples, int n, int batch, int64_t* scores);
+/* array accessors for checks: which = 0 planes, 1 intraCost, 2 intraMode, 3 invQscale, 4 lowresCosts[d0][d1],
+ * 5 rowSatds[d0][d1], 6 lowresMvs[list=d0][d1-1], 7 lowresMvCosts[list=d0][d1-1]; returns pointer and byte size */
+const void* x265cuh_array(void* la, void* frame, int which, int d0, int d1, size_t* bytes);
+void  x265cuh_frame_scalars(void* frame, int d0, int d1, int64_t* out9);  /* costEst, costEstAq, intraMbs[d0], wp_ssd0, wp_sum0, weighted, scale, denom, offset */
+uint32_t x265cuh_crc32(const void* p, size_t n);
+const char* x265cuh_error(void* la);
+}
+
+#endif

@@ -1,0 +1,21 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "slow: long-running oracle replays")
+
+
+@pytest.fixture(scope="session")
+def built():
+    """Everything native is built in-tree (idempotent)."""
+    import __graft_entry__ as ge
+    ge.build()
+    return True

@@ -1,0 +1,110 @@
+"""GPU parity tests proper: the CUDA path, called through the host layer and the C ABI, must
+reproduce bit-for-bit what the UNMODIFIED reference produced (CRC32 of every output array of every
+pre-lookahead frame and every frame-cost estimate in the golden traces) and what the oracle
+computes for the pixel primitives on the reference TestBench's own input recipes."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods(built):
+    from harness import replay
+    from oracle import pyoracle as po
+    from src.x265_b200 import abi
+    if abi.lib_cu().x265cu_device_count() < 1:
+        pytest.fail("no CUDA device visible: the GPU tests must run on the B200 box (there is no CPU fallback)")
+    return replay, po, abi
+
+
+def _replay(mods, name, max_events=None):
+    replay, po, abi = mods
+    res = replay.replay_trace(name, max_events=max_events)
+    assert res["jobs"] > 0 and res["frames"] > 0
+    assert not res["mismatches"], "%s: %d mismatches, first: %r" % (name, len(res["mismatches"]), res["mismatches"][:5])
+    return res
+
+
+@pytest.mark.parametrize("name", ["tiny8", "odd8", "tiny10"])
+def test_replay_small(mods, name):
+    _replay(mods, name)
+
+
+@pytest.mark.parametrize("name", ["c0_720p", "pool3_720p", "c0_720p10"])
+def test_replay_720p(mods, name):
+    """720p: cooperative slices (sliced searches), weighted prediction, AQ, 8- and 10-bit"""
+    _replay(mods, name)
+
+
+def test_replay_config1_1080p(mods):
+    """BASELINE.json configs[1]: 1080p, b-adapt 2, rc-lookahead 40, cuTree on (the bench workload)"""
+    _replay(mods, "c1_1080p")
+
+
+def test_replay_config0_1080p(mods):
+    _replay(mods, "c0_1080p")
+
+
+def test_replay_config2_4k(mods):
+    """configs[2]: 4K, rc-lookahead 40, bframes 8"""
+    _replay(mods, "c2_4k")
+
+
+def test_replay_config3_4k_10bit(mods):
+    """configs[3]: 10-bit 4K, --preset slow"""
+    _replay(mods, "c3_4k10")
+
+
+def _pixel_buffers(po, depth, seed):
+    """the three TestBench buffers: random, all-min, all-max (test/pixelharness.cpp:30-62)"""
+    dt = po.pixel_dtype(depth)
+    rng = np.random.default_rng(seed)
+    n = 64 * 64 * 4
+    mx = (1 << depth) - 1
+    return [rng.integers(0, mx + 1, n).astype(dt), np.zeros(n, dt), np.full(n, mx, dt)]
+
+
+@pytest.mark.parametrize("depth", [8, 10])
+@pytest.mark.parametrize("kind,fn", [(0, "ola_sad8x8"), (1, "ola_satd8x8"), (2, "ola_sa8d8x8"), (3, "ola_sa8d16x16")])
+def test_pixelcmp_batch(mods, depth, kind, fn):
+    """check_pixelcmp recipe (pixelharness.cpp:80-99): stride 64 vs FENC_STRIDE-5-like odd stride,
+    offsets stepping through the buffers, all combinations of random/min/max buffers"""
+    replay, po, abi = mods
+    lib = po.oracle(depth)
+    bufs = _pixel_buffers(po, depth, 1234 + kind)
+    la = abi.Lookahead(64, 64, depth, 1, 4, 0, 0, 0, 0, 0.0)
+    try:
+        for ia, a in enumerate(bufs):
+            for ib, b in enumerate(bufs):
+                sa, sb = 64, 59
+                n = 100
+                offA = (np.arange(n, dtype=np.int64) * 37) % 1500
+                offB = (np.arange(n, dtype=np.int64) * 53 + 3) % 1500
+                out = np.zeros(n, np.int32)
+                r = abi.lib_cu().x265cu_pixelcmp_batch(la.ctx, kind, a.ctypes.data, a.size, sa, b.ctypes.data, b.size, sb, n,
+                                                       offA.ctypes.data, offB.ctypes.data, out.ctypes.data)
+                assert r == 0, abi.lib_cu().x265cu_last_error(la.ctx)
+                isz = a.itemsize
+                want = np.array([getattr(lib, fn)(a.ctypes.data + int(oa) * isz, sa, b.ctypes.data + int(ob) * isz, sb)
+                                 for oa, ob in zip(offA, offB)], np.int32)
+                assert np.array_equal(out, want), (ia, ib, out[:8], want[:8])
+    finally:
+        la.close()
+
+
+def test_bad_arguments_fail_loudly(mods):
+    replay, po, abi = mods
+    L = abi.lib_cu()
+    la = abi.Lookahead(320, 192, 8, 3, 10, 0, 0, 1, 1, 1.0)
+    try:
+        assert L.x265cu_frame_init(la.ctx, 9999, None, 0, 0, None) == -1
+        res = (abi.JobResult * 1)()
+        job = (abi.Job * 1)()
+        job[0].fenc = 0; job[0].ref0 = 0; job[0].d0 = 0
+        assert L.x265cu_estimate_batch(la.ctx, 1, job, res) == -1
+        assert b"bad job" in L.x265cu_last_error(la.ctx)
+    finally:
+        la.close()
