@@ -103,10 +103,10 @@ int x265cu_frame_set_invqscale(x265cu_ctx* ctx, int slot, const int32_t* invQsca
  * pixel_var<16> on luma + pixel_var<8> on Cb/Cr (pixel.cpp:649-666) per 16x16 block of a 4:2:0
  * picture.  energy[block] = summed AC energy of the three planes (u/v may be NULL: luma only),
  * sums[6] = wp_sum[0..2], wp_ssd[0..2] raw accumulations (before the final normalisation at
- * slicetype.cpp:222-227).  Planes are host pointers padded like PicYuv.  Float mapping to QP
- * offsets stays on the host. */
+ * slicetype.cpp:222-227).  Planes are host (or, planesAreDevice != 0, device) pointers padded like
+ * PicYuv to a multiple of 16.  Float mapping to QP offsets stays on the host. */
 int x265cu_frame_var(x265cu_ctx* ctx, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride,
-                     uint32_t* energy, uint64_t sums[6]);
+                     int planesAreDevice, uint32_t* energy, uint64_t sums[6]);
 
 /* ---- LookaheadTLD::lowresIntraEstimate (slicetype.cpp:230-336).  Outputs (any may be NULL):
  * Lowres::intraCost, intraMode, lowresCosts[0][0], rowSatds[0][0]; sums[0] = costEst[0][0],
@@ -170,10 +170,13 @@ enum { X265CU_SAD_8x8 = 0, X265CU_SATD_8x8 = 1, X265CU_SA8D_8x8 = 2, X265CU_SA8D
 int x265cu_pixelcmp_batch(x265cu_ctx* ctx, int kind, const void* bufA, size_t samplesA, intptr_t strideA,
                           const void* bufB, size_t samplesB, intptr_t strideB,
                           int n, const int64_t* offA, const int64_t* offB, int32_t* out);
-/* same metric over every aligned 8x8 (16x16) block of plane 0 of two frame slots, device
- * resident; out (host, may be NULL) gets cuCount results.  Returns the kernel's device time in
- * milliseconds through *ms when ms != NULL (CUDA events on the ctx stream). */
-int x265cu_pixelcmp_frames(x265cu_ctx* ctx, int kind, int slotA, int slotB, int32_t* out, float* ms);
+/* same metric over every aligned 8x8 block of plane 0 of nPairs pairs of frame slots, device
+ * resident, ONE launch; out (host, may be NULL) gets nPairs * cuCount results.  Returns the
+ * kernel's device time in milliseconds through *ms when ms != NULL (CUDA events on the ctx stream). */
+int x265cu_pixelcmp_frames(x265cu_ctx* ctx, int kind, int nPairs, const int* slotsA, const int* slotsB, int32_t* out, float* ms);
+/* measured integer-issue peaks of this GPU in Gop/s (packed |a-b| accumulate = the SAD inner op;
+ * plain 32-bit adds): the roofline the search/cost kernels are judged against */
+int x265cu_int_peak(x265cu_ctx* ctx, double* gopsVabsdiff4, double* gopsIadd);
 
 /* ---- instrumentation: device time (ms, CUDA events on the ctx stream) and launch counts
  * accumulated since the last reset, per kernel family. */

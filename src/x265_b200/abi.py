@@ -58,7 +58,7 @@ class HostParams(C.Structure):
     _fields_ = [("sourceWidth", C.c_int), ("sourceHeight", C.c_int), ("bitDepth", C.c_int), ("maxCUSize", C.c_int),
                 ("bframes", C.c_int), ("lookaheadDepth", C.c_int), ("lookaheadSlices", C.c_int), ("poolWorkers", C.c_int),
                 ("bEnableWeightedPred", C.c_int), ("aqMode", C.c_int), ("aqStrength", C.c_double),
-                ("bFrameBias", C.c_int), ("device", C.c_int), ("frameSlots", C.c_int)]
+                ("bFrameBias", C.c_int), ("device", C.c_int), ("frameSlots", C.c_int), ("stream", C.c_void_p), ("searchWarps", C.c_int)]
 
 
 # every symbol include/x265cu.h declares (tests check that the library exports all of them)
@@ -66,7 +66,7 @@ ABI_SYMBOLS = (
     "x265cu_abi_version", "x265cu_device_count", "x265cu_open", "x265cu_close", "x265cu_last_error",
     "x265cu_get_geometry", "x265cu_sync", "x265cu_host_register", "x265cu_host_unregister",
     "x265cu_frame_init", "x265cu_frame_set_invqscale", "x265cu_frame_var", "x265cu_intra",
-    "x265cu_weight_cost_batch", "x265cu_estimate_batch", "x265cu_pixelcmp_batch", "x265cu_pixelcmp_frames",
+    "x265cu_weight_cost_batch", "x265cu_estimate_batch", "x265cu_pixelcmp_batch", "x265cu_pixelcmp_frames", "x265cu_int_peak",
     "x265cu_stats_enable", "x265cu_stats_get",
 )
 
@@ -89,13 +89,14 @@ def lib_cu():
         L.x265cu_host_unregister.argtypes = [C.c_void_p]
         L.x265cu_frame_init.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_ssize_t, C.c_int, C.c_void_p]
         L.x265cu_frame_set_invqscale.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
-        L.x265cu_frame_var.argtypes = [C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_void_p]
+        L.x265cu_frame_var.argtypes = [C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_int, C.c_void_p, C.c_void_p]
         L.x265cu_intra.argtypes = [C.c_void_p, C.c_int, C.POINTER(IntraOut)]
         L.x265cu_weight_cost_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(WeightItem), C.c_void_p]
         L.x265cu_estimate_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(Job), C.POINTER(JobResult)]
         L.x265cu_pixelcmp_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_ssize_t, C.c_void_p, C.c_size_t, C.c_ssize_t,
                                             C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
-        L.x265cu_pixelcmp_frames.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_float)]
+        L.x265cu_pixelcmp_frames.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+        L.x265cu_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.x265cu_stats_enable.argtypes = [C.c_void_p, C.c_int]
         L.x265cu_stats_get.argtypes = [C.c_void_p, C.POINTER(Stats), C.c_int]
         _cu = L
@@ -135,9 +136,10 @@ class Lookahead:
     """Python handle on x265cu::Lookahead (host/lookahead_cu.h)."""
 
     def __init__(self, width, height, depth=8, bframes=4, lookahead=20, slices=8, pool=16, weightp=1, aq_mode=1,
-                 aq_strength=1.0, bframe_bias=0, device=0, slots=0, ctu=64):
+                 aq_strength=1.0, bframe_bias=0, device=0, slots=0, ctu=64, stream=None, search_warps=0):
         self.L = lib_host()
-        p = HostParams(width, height, depth, ctu, bframes, lookahead, slices, pool, weightp, aq_mode, aq_strength, bframe_bias, device, slots)
+        p = HostParams(width, height, depth, ctu, bframes, lookahead, slices, pool, weightp, aq_mode, aq_strength, bframe_bias, device, slots,
+                       stream, search_warps)
         err = C.create_string_buffer(512)
         self.h = self.L.x265cuh_open(C.byref(p), err, 512)
         if not self.h:

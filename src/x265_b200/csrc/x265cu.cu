@@ -516,7 +516,11 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     std::vector<SearchItem> items;
     std::vector<int> costIdx;
     std::vector<int> weightedJobs;
-    size_t total = 0;
+    /* staging layout: [n x 32-byte sums][record 0][record 1]...; when the caller wants no arrays
+     * back (all destination pointers NULL) only the sums cross PCIe */
+    const size_t sumsBytes = alignUp((size_t)n * 32, 256);
+    size_t total = sumsBytes;
+    bool wantArrays = false;
     for (int i = 0; i < n; i++)
     {
         const x265cu_job& j = jobs[i];
@@ -524,7 +528,8 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
             return fail(c, X265CU_EINVAL, "x265cu_estimate_batch: bad job");
         if (j.doSearch[1] && j.d1 == 0) return fail(c, X265CU_EINVAL, "x265cu_estimate_batch: L1 search without p1");
         recOff[i] = total;
-        size_t rec = 32 + alignUp(hCU * 4, 16) + alignUp(nCU * 2, 16);
+        if (j.mvs[0] || j.mvs[1] || j.mvCosts[0] || j.mvCosts[1] || j.lowresCosts || j.rowSatds) wantArrays = true;
+        size_t rec = alignUp(hCU * 4, 16) + alignUp(nCU * 2, 16);
         if (j.doSearch[0]) rec += 2 * alignUp(nCU * 4, 16);
         if (j.doSearch[1]) rec += 2 * alignUp(nCU * 4, 16);
         total += rec;
@@ -584,7 +589,7 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
         d.intraCost = slotIntraCost(c, j.fenc);
         d.invQ = c->hasInvQ[j.fenc] ? slotInvQ(c, j.fenc) : NULL;
         uint8_t* rec = c->dStage + recOff[i];
-        d.outSums = (unsigned long long*)rec; rec += 32;
+        d.outSums = (unsigned long long*)(c->dStage + (size_t)i * 32);
         d.outRows = (int*)rec; rec += alignUp(hCU * 4, 16);
         d.outLowresCosts = (uint16_t*)rec; rec += alignUp(nCU * 2, 16);
         for (int l = 0; l < 2; l++)
@@ -610,9 +615,7 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     }
     CU_TRY(c, cudaMemcpyAsync(c->dArgs, c->hArgs, argBytes, cudaMemcpyHostToDevice, c->stream));
     c->stats.h2dBytes += (int64_t)argBytes;
-    /* zero the sums of every record (32 bytes at the head of each) -- one memset over the staging
-     * area is simpler than n small ones and the area is written anyway */
-    CU_TRY(c, cudaMemsetAsync(c->dStage, 0, total, c->stream));
+    CU_TRY(c, cudaMemsetAsync(c->dStage, 0, sumsBytes, c->stream));
 
     if (!weightedJobs.empty())
     {
@@ -644,8 +647,9 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
             cost_kernel<uint16_t><<<grid, 128, 0, c->stream>>>((const JobDev*)(c->dArgs + offJobs), (const int*)(c->dArgs + offCost), g);
         CU_TRY(c, cudaGetLastError());
     }
-    CU_TRY(c, cudaMemcpyAsync(c->hStage, c->dStage, total, cudaMemcpyDeviceToHost, c->stream));
-    c->stats.d2hBytes += (int64_t)total;
+    const size_t back = wantArrays ? total : (size_t)n * 32;
+    CU_TRY(c, cudaMemcpyAsync(c->hStage, c->dStage, back, cudaMemcpyDeviceToHost, c->stream));
+    c->stats.d2hBytes += (int64_t)back;
     int r = syncStream(c);
     if (r) return r;
 
@@ -654,13 +658,14 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     {
         const x265cu_job& j = jobs[i];
         const uint8_t* rec = c->hStage + recOff[i];
-        const unsigned long long* sums = (const unsigned long long*)rec; rec += 32;
+        const unsigned long long* sums = (const unsigned long long*)(c->hStage + (size_t)i * 32);
         x265cu_job_result& res = results[i];
         res.costEstRaw = (int64_t)sums[0];
         res.costEstAq = (int64_t)sums[1];
         res.intraMbs = (int32_t)sums[2];
         res.reserved = 0;
         res.costEst = j.d1 > 0 ? res.costEstRaw * 100 / (130 + c->cfg.bFrameBias) : res.costEstRaw;   /* slicetype.cpp:2053-2057 */
+        if (!wantArrays) continue;
         if (j.rowSatds) memcpy(j.rowSatds, rec, hCU * 4);
         rec += alignUp(hCU * 4, 16);
         if (j.lowresCosts) memcpy(j.lowresCosts, rec, nCU * 2);
@@ -712,27 +717,37 @@ int x265cu_pixelcmp_batch(x265cu_ctx* c, int kind, const void* bufA, size_t samp
     return syncStream(c);
 }
 
-int x265cu_pixelcmp_frames(x265cu_ctx* c, int kind, int slotA, int slotB, int32_t* out, float* ms)
+int x265cu_pixelcmp_frames(x265cu_ctx* c, int kind, int nPairs, const int* slotsA, const int* slotsB, int32_t* out, float* ms)
 {
-    if (!c || kind < 0 || kind > 2 || badSlot(c, slotA) || badSlot(c, slotB))
+    if (!c || kind < 0 || kind > 2 || nPairs < 1 || nPairs > 4096 || !slotsA || !slotsB)
         return c ? fail(c, X265CU_EINVAL, "x265cu_pixelcmp_frames: bad argument") : X265CU_EINVAL;
+    for (int i = 0; i < nPairs; i++)
+        if (badSlot(c, slotsA[i]) || badSlot(c, slotsB[i])) return fail(c, X265CU_EINVAL, "x265cu_pixelcmp_frames: bad slot");
     std::lock_guard<std::mutex> lk(c->mtx);
     CU_TRY(c, cudaSetDevice(c->cfg.device));
     const GeomDev& g = c->g;
-    if (growDevice(c, &c->dGeneric, &c->dGenericCap, (size_t)g.nCU * 4)) return X265CU_ECUDA;
+    const size_t outBytes = alignUp((size_t)nPairs * g.nCU * 4, 256);
+    if (growDevice(c, &c->dGeneric, &c->dGenericCap, outBytes + (size_t)nPairs * 16)) return X265CU_ECUDA;
+    const void** hp = (const void**)malloc((size_t)nPairs * 16);
+    for (int i = 0; i < nPairs; i++) { hp[2 * i] = slotPlane0(c, slotsA[i]); hp[2 * i + 1] = slotPlane0(c, slotsB[i]); }
+    cudaError_t ce = cudaMemcpyAsync(c->dGeneric + outBytes, hp, (size_t)nPairs * 16, cudaMemcpyHostToDevice, c->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
+    free(hp);
+    CU_TRY(c, ce);
     cudaEvent_t e0 = getEvent(c), e1 = getEvent(c);
     c->stats.launches[X265CU_K_PIXEL]++;
     CU_TRY(c, cudaEventRecord(e0, c->stream));
-    int blocks = (g.nCU / 8 + 7) / 8;
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    if (blocks < 1) blocks = 1;
+    int bx = (g.nCU / 8 + 7) / 8;
+    if (bx > 148 * 4) bx = 148 * 4;
+    if (bx < 1) bx = 1;
+    dim3 grid(bx, nPairs);
     if (c->pb == 1)
-        pixelcmp_frames_kernel<uint8_t><<<blocks, 256, 0, c->stream>>>(kind, (const uint8_t*)slotPlane0(c, slotA), (const uint8_t*)slotPlane0(c, slotB), g, (int*)c->dGeneric);
+        pixelcmp_frames_kernel<uint8_t><<<grid, 256, 0, c->stream>>>(kind, (const void* const*)(c->dGeneric + outBytes), g, (int*)c->dGeneric);
     else
-        pixelcmp_frames_kernel<uint16_t><<<blocks, 256, 0, c->stream>>>(kind, (const uint16_t*)slotPlane0(c, slotA), (const uint16_t*)slotPlane0(c, slotB), g, (int*)c->dGeneric);
+        pixelcmp_frames_kernel<uint16_t><<<grid, 256, 0, c->stream>>>(kind, (const void* const*)(c->dGeneric + outBytes), g, (int*)c->dGeneric);
     CU_TRY(c, cudaGetLastError());
     CU_TRY(c, cudaEventRecord(e1, c->stream));
-    if (out) CU_TRY(c, cudaMemcpyAsync(out, c->dGeneric, (size_t)g.nCU * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (out) CU_TRY(c, cudaMemcpyAsync(out, c->dGeneric, (size_t)nPairs * g.nCU * 4, cudaMemcpyDeviceToHost, c->stream));
     int r = syncStream(c);
     float t = 0;
     cudaEventElapsedTime(&t, e0, e1);
@@ -742,8 +757,43 @@ int x265cu_pixelcmp_frames(x265cu_ctx* c, int kind, int slotA, int slotB, int32_
     return r;
 }
 
+/* integer-pipe micro-benchmark: the roofline of the search/cost kernels is integer issue rate, not
+ * HBM, and MEASURED_PEAKS.json has no integer peak.  Times a dependent-free stream of packed
+ * absolute-difference-accumulate (the SAD inner op) and of IADD3-class adds on every SM. */
+int x265cu_int_peak(x265cu_ctx* c, double* gopsVabsdiff4, double* gopsIadd)
+{
+    if (!c) return X265CU_EINVAL;
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CU_TRY(c, cudaSetDevice(c->cfg.device));
+    if (growDevice(c, &c->dGeneric, &c->dGenericCap, 1 << 20)) return X265CU_ECUDA;
+    const int iters = 4096, blocks = 148 * 8, threads = 256;
+    double res[2] = { 0, 0 };
+    for (int mode = 0; mode < 2; mode++)
+    {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; rep++)
+        {
+            cudaEvent_t e0 = getEvent(c), e1 = getEvent(c);
+            CU_TRY(c, cudaEventRecord(e0, c->stream));
+            int_peak_kernel<<<blocks, threads, 0, c->stream>>>(mode, iters, (unsigned int*)c->dGeneric);
+            CU_TRY(c, cudaEventRecord(e1, c->stream));
+            CU_TRY(c, cudaStreamSynchronize(c->stream));
+            float t = 0;
+            cudaEventElapsedTime(&t, e0, e1);
+            if (rep && t < best) best = t;
+            c->freeEvents.push_back(e0); c->freeEvents.push_back(e1);
+        }
+        /* 16 independent ops per iteration per thread */
+        res[mode] = (double)blocks * threads * iters * 16 / (best * 1e-3) / 1e9;
+    }
+    CU_TRY(c, cudaGetLastError());
+    if (gopsVabsdiff4) *gopsVabsdiff4 = res[0];
+    if (gopsIadd) *gopsIadd = res[1];
+    return X265CU_OK;
+}
+
 int x265cu_frame_var(x265cu_ctx* c, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride,
-                     uint32_t* energy, uint64_t sums[6])
+                     int planesAreDevice, uint32_t* energy, uint64_t sums[6])
 {
     if (!c || !y || !energy || !sums || ((u == NULL) != (v == NULL)))
         return c ? fail(c, X265CU_EINVAL, "x265cu_frame_var: bad argument") : X265CU_EINVAL;
@@ -756,21 +806,30 @@ int x265cu_frame_var(x265cu_ctx* c, const void* y, intptr_t yStride, const void*
     const size_t eBytes = alignUp((size_t)bxN * byN * 4, 256);
     if (growDevice(c, &c->dGeneric, &c->dGenericCap, yBytes + 2 * cBytes + eBytes + 256)) return X265CU_ECUDA;
     uint8_t* dY = c->dGeneric; uint8_t* dU = dY + yBytes; uint8_t* dV = dU + cBytes; unsigned int* dE = (unsigned int*)(dV + cBytes);
-    CU_TRY(c, cudaMemcpy2DAsync(dY, yp * c->pb, y, (size_t)yStride * c->pb, (size_t)bxN * 16 * c->pb, byN * 16, cudaMemcpyHostToDevice, c->stream));
-    if (u)
+    int64_t ypitch = (int64_t)yp, cpitch = (int64_t)cp;
+    if (planesAreDevice)
     {
-        CU_TRY(c, cudaMemcpy2DAsync(dU, cp * c->pb, u, (size_t)cStride * c->pb, (size_t)bxN * 8 * c->pb, byN * 8, cudaMemcpyHostToDevice, c->stream));
-        CU_TRY(c, cudaMemcpy2DAsync(dV, cp * c->pb, v, (size_t)cStride * c->pb, (size_t)bxN * 8 * c->pb, byN * 8, cudaMemcpyHostToDevice, c->stream));
+        dY = (uint8_t*)y; dU = (uint8_t*)u; dV = (uint8_t*)v;
+        ypitch = yStride; cpitch = cStride;
     }
-    c->stats.h2dBytes += (int64_t)(yBytes + (u ? 2 * cBytes : 0));
+    else
+    {
+        CU_TRY(c, cudaMemcpy2DAsync(dY, yp * c->pb, y, (size_t)yStride * c->pb, (size_t)bxN * 16 * c->pb, byN * 16, cudaMemcpyHostToDevice, c->stream));
+        if (u)
+        {
+            CU_TRY(c, cudaMemcpy2DAsync(dU, cp * c->pb, u, (size_t)cStride * c->pb, (size_t)bxN * 8 * c->pb, byN * 8, cudaMemcpyHostToDevice, c->stream));
+            CU_TRY(c, cudaMemcpy2DAsync(dV, cp * c->pb, v, (size_t)cStride * c->pb, (size_t)bxN * 8 * c->pb, byN * 8, cudaMemcpyHostToDevice, c->stream));
+        }
+        c->stats.h2dBytes += (int64_t)(yBytes + (u ? 2 * cBytes : 0));
+    }
     CU_TRY(c, cudaMemsetAsync(c->dSmall, 0, 6 * sizeof(unsigned long long), c->stream));
     {
         KernelScope ks(c, X265CU_K_VAR);
         int blocks = (bxN * byN + 7) / 8;
         if (c->pb == 1)
-            frame_var_kernel<uint8_t><<<blocks, 256, 0, c->stream>>>((const uint8_t*)dY, (int64_t)yp, u ? (const uint8_t*)dU : NULL, u ? (const uint8_t*)dV : NULL, (int64_t)cp, bxN, byN, dE, c->dSmall);
+            frame_var_kernel<uint8_t><<<blocks, 256, 0, c->stream>>>((const uint8_t*)dY, ypitch, u ? (const uint8_t*)dU : NULL, u ? (const uint8_t*)dV : NULL, cpitch, bxN, byN, dE, c->dSmall);
         else
-            frame_var_kernel<uint16_t><<<blocks, 256, 0, c->stream>>>((const uint16_t*)dY, (int64_t)yp, u ? (const uint16_t*)dU : NULL, u ? (const uint16_t*)dV : NULL, (int64_t)cp, bxN, byN, dE, c->dSmall);
+            frame_var_kernel<uint16_t><<<blocks, 256, 0, c->stream>>>((const uint16_t*)dY, ypitch, u ? (const uint16_t*)dU : NULL, u ? (const uint16_t*)dV : NULL, cpitch, bxN, byN, dE, c->dSmall);
     }
     CU_TRY(c, cudaGetLastError());
     CU_TRY(c, cudaMemcpyAsync(energy, dE, (size_t)bxN * byN * 4, cudaMemcpyDeviceToHost, c->stream));

@@ -779,11 +779,15 @@ __global__ void __launch_bounds__(256) pixelcmp_batch_kernel(int kind, const P* 
     if (valid && sub == 0) out[idx] = result;
 }
 
-/* every aligned 8x8 block of plane 0 of two frames (the HBM-bound "SATD Gpix/s" kernel):
- * a warp covers 8 horizontally adjacent CUs, so each load instruction touches full 32-byte sectors. */
+/* every aligned 8x8 block of plane 0 of pairs of frames (the HBM-bound "SATD Gpix/s" kernel):
+ * a warp covers 8 horizontally adjacent CUs, so each load instruction touches full 32-byte sectors.
+ * grid = (blocks, pairs); planes[2 * pair], planes[2 * pair + 1] = sample (0,0) of the two planes. */
 template <typename P>
-__global__ void __launch_bounds__(256) pixelcmp_frames_kernel(int kind, const P* __restrict__ A, const P* __restrict__ B, GeomDev g, int* __restrict__ out)
+__global__ void __launch_bounds__(256) pixelcmp_frames_kernel(int kind, const void* const* __restrict__ planes, GeomDev g, int* __restrict__ out)
 {
+    const P* A = (const P*)planes[2 * blockIdx.y];
+    const P* B = (const P*)planes[2 * blockIdx.y + 1];
+    out += (int64_t)blockIdx.y * g.nCU;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
     const int q = lane >> 2, sub = lane & 3, bx = (sub & 1) * 4, by = (sub >> 1) * 4;
     for (int base = (blockIdx.x * nWarps + warp) * 8; base < g.nCU; base += gridDim.x * nWarps * 8)
@@ -819,6 +823,37 @@ __global__ void __launch_bounds__(256) pixelcmp_frames_kernel(int kind, const P*
         }
         if (valid && sub == 0) out[mb] = result;
     }
+}
+
+/* integer-pipe micro-benchmark (see x265cu_int_peak): 16 independent accumulator chains per thread */
+__global__ void __launch_bounds__(256) int_peak_kernel(int mode, int iters, unsigned int* __restrict__ sink)
+{
+    unsigned int a[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) a[k] = threadIdx.x * 16 + k;
+    unsigned int x = blockIdx.x * 0x9E3779B1u + threadIdx.x;
+    if (mode == 0)
+    {
+        for (int i = 0; i < iters; i++)
+        {
+#pragma unroll
+            for (int k = 0; k < 16; k++) a[k] = __vsadu4(a[k], x) + a[k];
+            x += 0x01010101u;
+        }
+    }
+    else
+    {
+        for (int i = 0; i < iters; i++)
+        {
+#pragma unroll
+            for (int k = 0; k < 16; k++) a[k] = a[k] + x + (unsigned int)k;
+            x ^= a[0];
+        }
+    }
+    unsigned int r = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) r ^= a[k];
+    if (r == 0xDEADBEEFu) sink[0] = r;
 }
 
 /* ===========================================================================================

@@ -108,6 +108,8 @@ bool Lookahead::create(const Param& p)
     cfg.lookaheadLambda = m_lambda;
     cfg.mvcost = m_mvcost + 2 * 32768;
     cfg.device = p.device;
+    cfg.stream = p.stream;
+    cfg.searchWarps = p.searchWarps;
     int r = x265cu_open(&cfg, &m_ctx);
     if (r != X265CU_OK)
     {
@@ -222,7 +224,7 @@ bool Lookahead::calcAdaptiveQuantFrame(Lowres& l, const void* y, intptr_t yStrid
     uint64_t sums[6] = { 0, 0, 0, 0, 0, 0 };
     if (needVar)
     {
-        int r = x265cu_frame_var(m_ctx, y, yStride, u, v, cStride, &energy[0], sums);
+        int r = x265cu_frame_var(m_ctx, y, yStride, u, v, cStride, 0, &energy[0], sums);
         if (r) { snprintf(m_error, sizeof(m_error), "x265cu_frame_var: %s", x265cu_last_error(m_ctx)); return false; }
     }
     for (int i = 0; i < 3; i++) { l.wp_sum[i] = sums[i]; l.wp_ssd[i] = sums[3 + i]; }
@@ -526,6 +528,7 @@ void* x265cuh_open(const x265cuh_params* p, char* err, int errLen)
     q.bframes = p->bframes; q.lookaheadDepth = p->lookaheadDepth; q.lookaheadSlices = p->lookaheadSlices; q.poolWorkers = p->poolWorkers;
     q.bEnableWeightedPred = p->bEnableWeightedPred; q.aqMode = p->aqMode; q.aqStrength = p->aqStrength;
     q.bFrameBias = p->bFrameBias; q.device = p->device; q.frameSlots = p->frameSlots;
+    q.stream = p->stream; q.searchWarps = p->searchWarps;
     Lookahead* la = new Lookahead();
     if (!la->create(q))
     {

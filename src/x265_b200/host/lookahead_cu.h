@@ -46,6 +46,8 @@ struct Param
     int bFrameBias;
     int device;
     int frameSlots;          /* 0 = lookaheadDepth + bframes + 8 */
+    void* stream;            /* cudaStream_t to run on (NULL: own stream) */
+    int searchWarps;         /* 0 = default */
 };
 
 struct WeightParam { int present, scale, denom, offset; };
@@ -145,6 +147,8 @@ typedef struct x265cuh_params
     int bEnableWeightedPred, aqMode;
     double aqStrength;
     int bFrameBias, device, frameSlots;
+    void* stream;
+    int searchWarps;
 } x265cuh_params;
 void* x265cuh_open(const x265cuh_params* p, char* err, int errLen);
 void  x265cuh_close(void* la);

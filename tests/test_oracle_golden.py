@@ -1,0 +1,95 @@
+"""The oracle against the golden traces/dumps the UNMODIFIED reference produced (oracle/gen_golden.py):
+every pre-lookahead frame and every frame-cost estimate of the clip is recomputed by the oracle from
+the same synthetic input and every sum / CRC32 must match.  This is the pin of the oracle that
+travels with the repository (the reference itself ships no golden vectors)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def run(name, **kw):
+    t = po.Trace(os.path.join(GOLD, name + ".trace"))
+    r = po.OracleReplay(t, **kw)
+    try:
+        mm = r.run()
+        assert r.njobs == sum(1 for _ in t.jobs())
+        assert not mm, "%s: %d mismatches, first %r" % (name, len(mm), mm[:5])
+    finally:
+        r.close()
+    return t
+
+
+@pytest.mark.parametrize("name", ["tiny8", "tiny10", "odd8"])
+def test_small_traces(name):
+    run(name)
+
+
+@pytest.mark.parametrize("name", ["c0_720p", "c0_720p10", "pool3_720p"])
+def test_720p_traces(name):
+    """sliced (cooperative) estimates, weighted prediction, AQ; 8 and 10 bit; small pool"""
+    t = run(name)
+    jobs = list(t.jobs())
+    assert any(j["sliced"] and not j["batch"] for j in jobs)
+
+
+def test_trace_weights_given():
+    """same replay with the reference's accepted weights passed in instead of re-derived"""
+    run("c0_720p", use_trace_weights=True)
+
+
+def test_perturbed_input_is_detected():
+    """negative control: a different clip seed must break the checksums"""
+    t = po.Trace(os.path.join(GOLD, "tiny8.trace"))
+    t.cfg["seed"] += 1
+    r = po.OracleReplay(t)
+    try:
+        assert r.run(max_events=6)
+    finally:
+        r.close()
+
+
+@pytest.mark.parametrize("name,depth", [("tiny8", 8), ("tiny10", 10), ("odd8", 8)])
+def test_dump_arrays(name, depth):
+    """full arrays (not only CRCs) of the small clips: planes of frame 0, intra costs/modes, MVs,
+    MV costs, lowresCosts, rowSatds of every estimate"""
+    t = po.Trace(os.path.join(GOLD, name + ".trace"))
+    dump = po.read_dump(os.path.join(GOLD, name + ".dump"))
+    r = po.OracleReplay(t, keep=10 ** 6)
+    try:
+        assert not r.run()
+        checked = 0
+        f0 = r.frames[0]
+        assert f0.planes().tobytes() == dump[("PLAN", 0, 0, 0, 0)]
+        for (tag, a, b, c, idx), data in dump.items():
+            if tag == "ICST":
+                assert r.frames[a].intra_cost().tobytes() == data
+            elif tag == "IMOD":
+                assert r.frames[a].intra_mode().tobytes() == data
+            elif tag == "INVQ":
+                assert r.frames[a].inv_qscale().tobytes() == data
+            else:
+                continue
+            checked += 1
+        assert checked >= 2 * t.cfg["nframes"]
+    finally:
+        r.close()
+
+
+def test_golden_lut_crc():
+    """mvcost LUT of the reference (trace header) == oracle's"""
+    for name, depth in (("tiny8", 8), ("tiny10", 10)):
+        t = po.Trace(os.path.join(GOLD, name + ".trace"))
+        lut = np.zeros(4 * 32768 + 1, np.uint16)
+        po.oracle(depth).ola_mvcost_table(lut.ctypes.data)
+        assert po.crc(lut) == t.cfg["lutCrc"]
+        assert po.oracle(depth).ola_lambda_int() == t.cfg["lambda"]
+
+
+@pytest.mark.slow
+def test_config0_1080p():
+    run("c0_1080p")

@@ -1,0 +1,151 @@
+"""Pin of the oracle, primitive by primitive, against the reference's OWN compiled C functions
+(setupCPrimitives table exposed by oracle/_ref/libx265ref<depth>.so, built from the unmodified
+sources by oracle/build_ref.py).  Input recipes follow the reference's TestBench
+(test/pixelharness.cpp:30-62,80-200,318-359,499-527; test/intrapredharness.cpp:47-140).
+
+Runs only where oracle/_ref exists (the build container); the committed golden traces carry the
+same pin to machines without the reference (tests/test_oracle_golden.py)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+DEPTHS = [d for d in (8, 10) if po.ref_available(d)]
+pytestmark = pytest.mark.skipif(not DEPTHS, reason="oracle/_ref not built (reference tree absent)")
+
+
+def bufs(depth, seed, n=64 * 64 * 2):
+    dt = po.pixel_dtype(depth)
+    rng = np.random.default_rng(seed)
+    mx = (1 << depth) - 1
+    return [rng.integers(0, mx + 1, n).astype(dt), np.zeros(n, dt), np.full(n, mx, dt),
+            rng.integers(0, 4, n).astype(dt), (mx - rng.integers(0, 4, n)).astype(dt)]
+
+
+def ptr(a, off=0):
+    return a.ctypes.data + off * a.itemsize
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+@pytest.mark.parametrize("name", ["sad8x8", "satd8x8", "sa8d8x8", "sa8d16x16"])
+def test_pixelcmp(depth, name):
+    O, R = po.oracle(depth), po.ref(depth)
+    fo, fr = getattr(O, "ola_" + name), getattr(R, "x265ref_" + name)
+    B = bufs(depth, 11)
+    for a in B:
+        for b in B:
+            for it in range(100):
+                oa, ob = (it * 32) % 3000, (it * 37 + 5) % 3000
+                assert fo(ptr(a, oa), 64, ptr(b, ob), 59) == fr(ptr(a, oa), 64, ptr(b, ob), 59)
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_sad_x3_x4(depth):
+    O, R = po.oracle(depth), po.ref(depth)
+    B = bufs(depth, 12)
+    fenc = np.zeros(64 * 8, B[0].dtype)   # FENC_STRIDE 64
+    res = (C.c_int32 * 4)()
+    for a in B[:3]:
+        for b in B[:3]:
+            fenc[:] = a[:64 * 8]
+            for it in range(50):
+                offs = [(it * 7 + k * 13) % 2000 for k in range(4)]
+                R.x265ref_sad_x4_8x8(ptr(fenc), ptr(b, offs[0]), ptr(b, offs[1]), ptr(b, offs[2]), ptr(b, offs[3]), 59, res)
+                want = [O.ola_sad8x8(ptr(fenc), 64, ptr(b, o), 59) for o in offs]
+                assert list(res) == want
+                R.x265ref_sad_x3_8x8(ptr(fenc), ptr(b, offs[0]), ptr(b, offs[1]), ptr(b, offs[2]), 59, res)
+                assert list(res)[:3] == want[:3]
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_pixelavg(depth):
+    O, R = po.oracle(depth), po.ref(depth)
+    B = bufs(depth, 13)
+    for a in B:
+        for b in B:
+            d1 = np.zeros(64 * 8, a.dtype)
+            d2 = np.zeros(64 * 8, a.dtype)
+            O.ola_pixelavg8x8(ptr(d1), 64, ptr(a, 17), 61, ptr(b, 29), 67)
+            R.x265ref_pixelavg8x8(ptr(d2), 64, ptr(a, 17), 61, ptr(b, 29), 67)
+            assert np.array_equal(d1, d2)
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_frame_init_lowres_and_border(depth):
+    O, R = po.oracle(depth), po.ref(depth)
+    dt = po.pixel_dtype(depth)
+    rng = np.random.default_rng(14)
+    w, h, mx, my = 40, 24, 48, 32
+    sstride = 2 * w + 17
+    src = rng.integers(0, 1 << depth, (2 * h + 1) * sstride).astype(dt)
+    dstride = w + 2 * mx + 8
+    size = dstride * (h + 2 * my)
+    outs = []
+    for L, pre in ((O, "ola_"), (R, "x265ref_")):
+        planes = [np.zeros(size, dt) for _ in range(4)]
+        base = dstride * my + mx
+        getattr(L, pre + "frame_init_lowres")(ptr(src), *[ptr(p, base) for p in planes], sstride, dstride, w, h)
+        for p in planes:
+            getattr(L, pre + "extend_border")(ptr(p, base), dstride, w, h, mx, my)
+        outs.append(np.concatenate(planes))
+    assert np.array_equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_intra_filter_and_predictors(depth):
+    O, R = po.oracle(depth), po.ref(depth)
+    dt = po.pixel_dtype(depth)
+    rng = np.random.default_rng(15)
+    mx = (1 << depth) - 1
+    for it in range(100):
+        kind = it % 4
+        if kind == 0:
+            nb = rng.integers(0, mx + 1, 33).astype(dt)
+        elif kind == 1:
+            nb = np.zeros(33, dt)
+        elif kind == 2:
+            nb = np.full(33, mx, dt)
+        else:
+            nb = np.where(rng.integers(0, 2, 33) > 0, mx, 0).astype(dt)
+        f1, f2 = np.zeros(33, dt), np.zeros(33, dt)
+        O.ola_intra_filter8(ptr(nb), ptr(f1))
+        R.x265ref_intra_filter8(ptr(nb), ptr(f2))
+        assert np.array_equal(f1, f2)
+        for mode in range(35):
+            for bf in (0, 1):
+                p1, p2 = np.zeros(64, dt), np.zeros(64, dt)
+                O.ola_intra_pred8(mode, ptr(p1), 8, ptr(nb), bf)
+                R.x265ref_intra_pred8(mode, ptr(p2), 8, ptr(nb), bf)
+                assert np.array_equal(p1, p2), (mode, bf)
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_weight_pp_and_var(depth):
+    O, R = po.oracle(depth), po.ref(depth)
+    B = bufs(depth, 16)
+    corr = 14 - depth
+    for a in B:
+        for (w0, denom, off) in ((64, 6, 0), (70, 6, -3), (127, 7, 12), (33, 5, -128), (1, 0, 127), (90, 7, 5)):
+            rnd = (1 << (denom - 1)) if denom else 0
+            d1, d2 = np.zeros(64 * 16, a.dtype), np.zeros(64 * 16, a.dtype)
+            O.ola_weight_pp(ptr(a), ptr(d1), 64, 64, 16, w0, rnd << corr, denom + corr, off << (depth - 8))
+            R.x265ref_weight_pp(ptr(a), ptr(d2), 64, 64, 16, w0, rnd << corr, denom + corr, off << (depth - 8))
+            assert np.array_equal(d1, d2)
+        for o in (0, 5, 77):
+            assert O.ola_var16(ptr(a, o), 64) == R.x265ref_var16(ptr(a, o), 64)
+            assert O.ola_var8(ptr(a, o), 61) == R.x265ref_var8(ptr(a, o), 61)
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_mvcost_table_and_exp2fix8(depth):
+    O, R = po.oracle(depth), po.ref(depth)
+    t1 = np.zeros(4 * 32768 + 1, np.uint16)
+    t2 = np.zeros(4 * 32768 + 1, np.uint16)
+    O.ola_mvcost_table(ptr(t1))
+    R.x265ref_mvcost_table(ptr(t2))
+    assert np.array_equal(t1, t2)
+    assert O.ola_lambda_int() == R.x265ref_lambda_int()
+    for x in np.linspace(-60, 60, 4001):
+        assert O.ola_exp2fix8(float(x)) == R.x265ref_exp2fix8(float(x))
