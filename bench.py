@@ -1,0 +1,426 @@
+#!/usr/bin/env python3
+"""bench.py -- lookahead frames/s of the B200 lookahead cost-estimation path (BASELINE.json metric).
+
+A "step" = one pass of the hot path over one synthetic clip: every pre-lookahead frame (lowres
+init + AQ variance + intra estimate) and every frame-cost estimate (motion searches, bidir/intra
+costs, weighted-prediction analysis) that x265 1.9's own lookahead issues for that clip, replayed in
+the reference's order and batching from the golden trace (tests/golden/<workload>.trace), through
+the host layer (x265cu::Lookahead / CostEstimateGroup) and the C ABI.
+
+  value   device-resident: source pictures already in HBM, result arrays stay in HBM mirrors
+          (only the per-estimate sums return); the host float decisions still run.
+  e2e     the reference-facing call path with HOST buffers: pictures are uploaded from pinned host
+          memory and every Lowres output array (planes, MVs, costs...) is copied back, inside the
+          timed region.
+  --impl reference   the UNMODIFIED x265 1.9 lookahead (oracle/_ref, C primitives) on the host
+          cores, same clip and options, all threads.
+
+One process per GPU (torchrun for N > 1): every rank runs its own independent stream (weak
+scaling, no collective on the cost path); timing is barrier + synchronize on both sides, CUDA
+events on the launching stream, MAX over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def reference_arm(args, rank, world):
+    """`--impl reference`: the reference's own CPU lookahead on the host cores (rank 0 only)."""
+    if rank != 0:
+        return 0
+    from harness.workloads import WORKLOADS, DESCRIPTIONS
+    depth, w, h, nframes, seed, _pool, opts, _ = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    pool = min(64, cores)          # one x265 thread pool holds at most 64 workers (threadpool.h:44)
+    times = []
+    kind = "reference"
+    for it in range(args.warmup + args.steps):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "harness", "refrun.py"), args.workload, str(pool)],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        if r.returncode != 0 or not r.stdout.strip():
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref lookahead driver failed: " + r.stderr.strip()[-200:]}))
+            return 0
+        out = json.loads(r.stdout.strip().splitlines()[-1])
+        kind = out["kind"]
+        if it >= args.warmup:
+            times.append(out["seconds"])
+    total = sum(times)
+    value = nframes * len(times) / total
+    line = {
+        "impl": "reference", "metric": "lookahead_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8" if depth == 8 else "u16", "data": "synthetic",
+        "config": {"workload": DESCRIPTIONS.get(args.workload, args.workload), "trace": args.workload, "frames_per_step": nframes,
+                   "resolution": "%dx%d" % (w, h), "bit_depth": depth},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": pool, "kind": kind,
+                         "sample": "whole workload (%d frames) per step, x265 1.9 Lookahead only (no frame encoders), C primitives (no asm: no yasm/nasm in the image), pool of %d threads" % (nframes, pool)},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+class Runner:
+    """pre-marshalled replay of a trace through the host layer (resident or host-buffer mode)."""
+
+    def __init__(self, trace, clip, stream, device, resident, torch):
+        from src.x265_b200 import abi
+        self.abi, self.torch, self.resident = abi, torch, resident
+        cfg = trace.cfg
+        self.cfg = cfg
+        slices = cfg["numCoopSlices"] if cfg["numCoopSlices"] > 1 else 0
+        n = cfg["nframes"]
+        la = None
+        for s in ([slices] + list(range(2, 17)) if slices else [0]):
+            la = abi.Lookahead(cfg["width"], cfg["height"], cfg["depth"], cfg["bframes"], cfg["lookahead"], s, cfg["pool"], cfg["weightp"],
+                               cfg["aqmode"], cfg["aqStrength"], cfg["bFrameBias"], device, n + 2, stream=stream)
+            if not slices or (la.numCoopSlices, la.numRowsPerSlice) == (cfg["numCoopSlices"], cfg["numRowsPerSlice"]):
+                break
+            la.close()
+        self.la = la
+        la.set_resident(resident)
+        self.frames = {t: la.frame_alloc() for t in range(n)}
+        self.inputs = {}
+        self.keepalive = []
+        dt = torch.uint8 if cfg["depth"] == 8 else torch.int16
+        for t in range(n):
+            y, u, v = clip.frames[t]
+            if resident:
+                # device copies with 8-byte aligned pitches (x265cu_frame_init device-pointer contract)
+                def dev(a):
+                    pitch = (a.shape[1] * a.itemsize + 63) // 64 * 64 // a.itemsize
+                    d = torch.zeros((a.shape[0], pitch), dtype=dt, device="cuda")
+                    d[:, :a.shape[1]] = torch.from_numpy(a.view("int16") if cfg["depth"] > 8 else a).to("cuda")
+                    return d, pitch
+                dy, py = dev(y)
+                du, pu = dev(u)
+                dv, _ = dev(v)
+                self.keepalive += [dy, du, dv]
+                self.inputs[t] = (dy.data_ptr(), py, du.data_ptr(), dv.data_ptr(), pu)
+            else:
+                # pinned host pictures (the encoder's PicYuv, registered once)
+                for a in (y, u, v):
+                    abi.lib_cu().x265cu_host_register(a.ctypes.data, a.nbytes)
+                self.keepalive += [y, u, v]
+                self.inputs[t] = (y.ctypes.data, y.strides[0] // y.itemsize, u.ctypes.data, v.ctypes.data, u.strides[0] // u.itemsize)
+        # pre-marshal the call sequence
+        self.calls = []
+        for e in trace.events:
+            if e[0] == "P":
+                self.calls.append(("P", e[1]["poc"]))
+            elif e[0] in ("J", "B"):
+                jobs = [e[1]] if e[0] == "J" else e[1]
+                if not jobs:
+                    continue
+                lo = min(j["p0"] for j in jobs)
+                hi = max(j["p1"] for j in jobs)
+                fr = [self.frames.get(p) for p in range(lo, hi + 1)]
+                tr = [(j["p0"] - lo, j["p1"] - lo, j["b"] - lo) for j in jobs]
+                self.calls.append(("E", la.prepare_estimate(fr, tr), e[0] == "B"))
+        self.units = sum(j["s0"] + j["s1"] for j in trace.jobs())
+        self.njobs = sum(1 for _ in trace.jobs())
+
+    def step(self):
+        la = self.la
+        for c in self.calls:
+            if c[0] == "P":
+                t = c[1]
+                y, ys, u, v, cs = self.inputs[t]
+                la.pre_lookahead_ptr(self.frames[t], y, ys, u, v, cs, t, True)
+            else:
+                la.estimate_prepared(c[1], c[2])
+
+    def close(self):
+        for f in self.frames.values():
+            self.la.frame_free(f)
+        if not self.resident:
+            for a in self.keepalive:
+                self.abi.lib_cu().x265cu_host_unregister(a.ctypes.data)
+        self.la.close()
+
+
+def timed(torch, dist, world, fn, steps):
+    """barrier + synchronize on both sides; CUDA events on the current (launching) stream; max over ranks"""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c1_1080p")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--profile-mode", action="store_true",
+                    help="short run for ncu: device-resident runner only, 1 warm-up + 1 timed step, no parity/e2e/baseline")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if (args.impl == "ours" and not args.profile_mode) else args.warmup
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+
+    if args.impl == "reference":
+        return reference_arm(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    if rank == 0 or not os.path.exists(os.path.join(ROOT, "src", "x265_b200", "libx265cu.so")):
+        ge.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+
+    from harness import replay
+    from harness.workloads import DESCRIPTIONS
+    from oracle import pyoracle as po
+    from src.x265_b200 import abi
+
+    trace = po.Trace(replay.trace_path(args.workload))
+    cfg = trace.cfg
+    nframes = cfg["nframes"]
+    clip = replay.Clip(cfg)
+
+    # ---- parity gate on this very workload, through the same call path ----
+    parity = "skipped"
+    if not args.no_parity and not args.profile_mode:
+        r = replay.CuReplay(trace, device=local, check=True, clip=clip)
+        mm = r.run()
+        nchk = r.njobs
+        r.close()
+        if mm:
+            raise SystemExit("bench.py: parity FAILED on %s: %d mismatches, first %r" % (args.workload, len(mm), mm[0]))
+        parity = "bit-exact vs x265 1.9 reference trace: %d frames, %d estimates, every output array CRC" % (nframes, nchk)
+
+    stream = torch.cuda.current_stream().cuda_stream
+    sampler = ClockSampler(local)
+
+    if args.profile_mode:
+        res = Runner(trace, clip, stream, local, True, torch)
+        res.step()
+        ms = timed(torch, dist, world, res.step, 1)
+        st = res.la.stats()
+        res.close()
+        print(json.dumps({"profile_mode": True, "ms_per_step": ms, "launches": st["launches"]}))
+        return 0
+
+    # ---- value: device-resident ----
+    res = Runner(trace, clip, stream, local, True, torch)
+    for _ in range(args.warmup):
+        res.step()
+    res.la.stats_enable(True)
+    res.la.stats(reset=True)
+    sampler.start()
+    ms_value = timed(torch, dist, world, res.step, args.steps)
+    st = res.la.stats(reset=True)
+    res.la.stats_enable(False)
+    int_peak = (abi.C.c_double(), abi.C.c_double())
+    abi.lib_cu().x265cu_int_peak(res.la.ctx, abi.C.byref(int_peak[0]), abi.C.byref(int_peak[1]))
+    # SATD primitive throughput (HBM-bound kernel): all frame pairs (t, t+1) in one launch
+    satd = None
+    try:
+        import numpy as np
+        slots = np.array([abi.lib_host().x265cuh_frame_slot(res.frames[t]) for t in range(nframes)], np.int32)
+        a, b = np.ascontiguousarray(np.tile(slots[:-1], 8)), np.ascontiguousarray(np.tile(slots[1:], 8))
+        msf = abi.C.c_float()
+        best = None
+        for _ in range(4):
+            abi.lib_cu().x265cu_pixelcmp_frames(res.la.ctx, 1, len(a), a.ctypes.data, b.ctypes.data, None, abi.C.byref(msf))
+            best = msf.value if best is None else min(best, msf.value)
+        pix = len(a) * res.la.nCU * 64
+        satd = {"gpix_per_s": pix / (best * 1e-3) / 1e9, "pairs": len(a), "ms": best}
+    except Exception as ex:  # pragma: no cover - reported, not fatal
+        satd = {"error": str(ex)}
+    res.close()
+
+    # ---- e2e: host buffers in, all arrays back ----
+    e2e = Runner(trace, clip, stream, local, False, torch)
+    for _ in range(args.warmup):
+        e2e.step()
+    e2e.la.stats(reset=True)
+    ms_e2e = timed(torch, dist, world, e2e.step, args.steps)
+    st_e2e = e2e.la.stats(reset=True)
+    units, njobs = e2e.units, e2e.njobs
+    e2e.close()
+    clocks = sampler.stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    P = 1 if cfg["depth"] == 8 else 2
+    nCU = ((cfg["width"] // 2 + 7) // 8) * ((cfg["height"] // 2 + 7) // 8)
+    Np = nCU * 64
+    # SURVEY.md §8(d) algorithmic bytes per unit
+    alg = {
+        "lowres": 8 * Np * P * nframes,                         # A: per frame
+        "intra": (Np * P + 7 * nCU) * nframes,                  # B: per frame
+        "search": (5 * Np * P + 8 * nCU) * units,               # C: per (frame, list, distance) searched
+    }
+    kms = {k: v / args.steps for k, v in st["ms"].items()}
+    klaunch = {k: v / args.steps for k, v in st["launches"].items()}
+    dom = max(("lowres", "intra", "search", "cost", "weight", "var"), key=lambda k: kms[k])
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+    except (OSError, ValueError):
+        pass
+    if dom in alg and kms[dom] > 0:
+        per_launch_bytes = alg[dom] / max(klaunch[dom], 1)
+        avg_ms = kms[dom] / max(klaunch[dom], 1)
+        achieved = per_launch_bytes / (avg_ms * 1e-3) / 1e9
+    else:
+        achieved = 0.0
+    roofline = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": traffic, "peak_source": peak_src,
+                "note": "the dominant kernel (wavefront motion search) is bound by dependent integer work, not HBM: see int_roofline"}
+    # integer roofline of the search kernel: SAD/SATD pixel-ops actually performed per searched CU-list
+    # (~20 SAD + ~9 SATD 8x8 per search -> (20*2 + 9*7) * 64 int ops before packing)
+    ops_per_search_cu = (20 * 2 + 9 * 7) * 64
+    int_ops = ops_per_search_cu * nCU * units
+    int_roofline = {"achieved_gops": int_ops / (kms["search"] * 1e-3) / 1e9 if kms["search"] > 0 else 0.0,
+                    "peak_gops_vabsdiff4": int_peak[0].value, "peak_gops_iadd": int_peak[1].value,
+                    "ops_model": "(20 SAD*2 + 9 SATD*7 ops/px)*64 px per searched CU-list, un-packed (SURVEY.md 8d)"}
+    if int_peak[1].value > 0:
+        int_roofline["frac_of_iadd_peak"] = int_roofline["achieved_gops"] / int_peak[1].value
+    if satd and "gpix_per_s" in satd:
+        roof_pix = hbm_peak / (2 * P + 4.0 / 64)     # GB/s / (bytes per pixel pair) = Gpix/s
+        satd["roofline_gpix_per_s"] = roof_pix
+        satd["frac"] = satd["gpix_per_s"] / roof_pix
+
+    # ---- CPU baseline (reported, not the target): the reference's own lookahead on the host cores ----
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        pool = min(64, cores)
+        rr = subprocess.run([sys.executable, os.path.join(ROOT, "harness", "refrun.py"), args.workload, str(pool)],
+                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        try:
+            o = json.loads(rr.stdout.strip().splitlines()[-1])
+            cpu_baseline = {"value": nframes / o["seconds"], "unit": "frames/s", "cores": o["threads"], "kind": o["kind"],
+                            "sample": "the whole workload once (%d frames, %.1f s): x265 1.9 Lookahead only, C primitives "
+                                      "(asm build impossible: no yasm/nasm)" % (nframes, o["seconds"])}
+        except (ValueError, IndexError, KeyError):
+            cpu_baseline = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "failed: " + rr.stderr.strip()[-160:]}
+
+    launches = int(sum(st["launches"].values()))
+    value = world * nframes * args.steps / (ms_value * 1e-3)
+    e2e_value = world * nframes * args.steps / (ms_e2e * 1e-3)
+    line = {
+        "metric": "lookahead_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8" if cfg["depth"] == 8 else "u16", "data": "synthetic",
+        "config": {"workload": DESCRIPTIONS.get(args.workload, args.workload), "trace": args.workload, "frames_per_step": nframes,
+                   "estimates_per_step": njobs, "searches_per_step": units, "resolution": "%dx%d" % (cfg["width"], cfg["height"]),
+                   "streams": world, "parallelism": "%d independent stream(s), one per GPU, no collective on the cost path" % world,
+                   "l2": "working set per step (%d frames x 4 padded planes + sources, > 300 MB) exceeds the 126 MB L2; no explicit flush" % nframes,
+                   "parity": parity},
+        "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": st_e2e["h2d"] // args.steps, "d2h_bytes_per_step": st_e2e["d2h"] // args.steps},
+        "gpu_launches": launches,
+        "kernel_ms_per_step": kms, "kernel_launches_per_step": klaunch,
+        "roofline": roofline, "int_roofline": int_roofline, "satd_8x8": satd,
+        "cpu_baseline": cpu_baseline, "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

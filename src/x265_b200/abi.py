@@ -111,6 +111,8 @@ def lib_host():
         L.x265cuh_open.restype = C.c_void_p
         L.x265cuh_open.argtypes = [C.POINTER(HostParams), C.c_char_p, C.c_int]
         L.x265cuh_close.argtypes = [C.c_void_p]
+        L.x265cuh_set_resident.argtypes = [C.c_void_p, C.c_int]
+        L.x265cuh_frame_slot.argtypes = [C.c_void_p]
         L.x265cuh_ctx.restype = C.c_void_p
         L.x265cuh_ctx.argtypes = [C.c_void_p]
         L.x265cuh_info.argtypes = [C.c_void_p, C.c_void_p]
@@ -177,6 +179,30 @@ class Lookahead:
                                          (u.strides[0] // u.itemsize) if u is not None else 0, poc, 1 if planes_back else 0)
         if r:
             raise RuntimeError("preLookahead failed: " + self.error())
+
+    def set_resident(self, on):
+        """inputs become device pointers, result arrays stay in HBM (only sums return)"""
+        self.L.x265cuh_set_resident(self.h, 1 if on else 0)
+
+    def pre_lookahead_ptr(self, frame, y, ys, u, v, cs, poc, planes_back):
+        """raw-pointer form (host or, in resident mode, device addresses)"""
+        r = self.L.x265cuh_pre_lookahead(self.h, frame, y, ys, u, v, cs, poc, 1 if planes_back else 0)
+        if r:
+            raise RuntimeError("preLookahead failed: " + self.error())
+
+    def prepare_estimate(self, frames, triples):
+        """pre-marshal an estimate call (bench inner loop): returns an opaque tuple for estimate_prepared"""
+        n = len(triples)
+        fr = (C.c_void_p * len(frames))(*frames)
+        tr = (C.c_int * (3 * n))(*[x for t in triples for x in t])
+        sc = (C.c_int64 * n)()
+        return (fr, len(frames), tr, n, sc)
+
+    def estimate_prepared(self, prep, batch):
+        fr, nf, tr, n, sc = prep
+        if self.L.x265cuh_estimate(self.h, fr, nf, tr, n, 1 if batch else 0, sc):
+            raise RuntimeError("estimate failed: " + self.error())
+        return sc
 
     def estimate(self, frames, triples, batch):
         """frames: list of frame handles; triples: list of (p0, p1, b) indices into frames."""

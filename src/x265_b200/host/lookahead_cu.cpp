@@ -65,7 +65,7 @@ void Lookahead::mvcostTable(int bitDepth, uint16_t* out, int* lambdaInt)
     }
 }
 
-Lookahead::Lookahead() : m_ctx(NULL), m_mvcost(NULL), m_lambda(1) { m_error[0] = 0; memset(&m_param, 0, sizeof(m_param)); }
+Lookahead::Lookahead() : m_ctx(NULL), m_mvcost(NULL), m_lambda(1), m_resident(false) { m_error[0] = 0; memset(&m_param, 0, sizeof(m_param)); }
 Lookahead::~Lookahead() { destroy(); }
 
 /* Lookahead::Lookahead + Lookahead::create, encoder/slicetype.cpp:490-591 */
@@ -206,7 +206,7 @@ bool Lookahead::lowresInit(Lowres& l, const void* luma, intptr_t stride, int poc
     }
     for (int i = 0; i < l.bframes + 2; i++)
         l.intraMbs[i] = 0;
-    int r = x265cu_frame_init(m_ctx, l.slot, luma, stride, 0, copyPlanesBack ? l.buffer[0] : NULL);
+    int r = x265cu_frame_init(m_ctx, l.slot, luma, stride, m_resident ? 1 : 0, (copyPlanesBack && !m_resident) ? l.buffer[0] : NULL);
     if (r) { snprintf(m_error, sizeof(m_error), "x265cu_frame_init: %s", x265cu_last_error(m_ctx)); return false; }
     return true;
 }
@@ -224,7 +224,7 @@ bool Lookahead::calcAdaptiveQuantFrame(Lowres& l, const void* y, intptr_t yStrid
     uint64_t sums[6] = { 0, 0, 0, 0, 0, 0 };
     if (needVar)
     {
-        int r = x265cu_frame_var(m_ctx, y, yStride, u, v, cStride, 0, &energy[0], sums);
+        int r = x265cu_frame_var(m_ctx, y, yStride, u, v, cStride, m_resident ? 1 : 0, &energy[0], sums);
         if (r) { snprintf(m_error, sizeof(m_error), "x265cu_frame_var: %s", x265cu_last_error(m_ctx)); return false; }
     }
     for (int i = 0; i < 3; i++) { l.wp_sum[i] = sums[i]; l.wp_ssd[i] = sums[3 + i]; }
@@ -322,6 +322,12 @@ bool Lookahead::lowresIntraEstimate(Lowres& l)
     x265cu_intra_out o;
     o.intraCost = l.intraCost; o.intraMode = l.intraMode;
     o.lowresCosts = l.lowresCosts[0][0]; o.rowSatds = l.rowSatds[0][0];
+    if (m_resident)
+    {
+        /* device-resident mode: arrays stay in the HBM mirrors, only the two sums come back */
+        o.intraCost = NULL; o.intraMode = NULL; o.lowresCosts = NULL; o.rowSatds = NULL;
+        l.rowSatds[0][0][0] = 0;
+    }
     int r = x265cu_intra(m_ctx, l.slot, &o);
     if (r) { snprintf(m_error, sizeof(m_error), "x265cu_intra: %s", x265cu_last_error(m_ctx)); return false; }
     l.costEst[0][0] = o.sums[0];
@@ -455,14 +461,17 @@ bool CostEstimateGroup::runEstimates(const Estimate* est, int n, bool batchMode)
         for (int l = 0; l < 2; l++)
         {
             int d = l ? d1 : d0;
-            if (j.doSearch[l])
+            if (j.doSearch[l] && !la.m_resident)
             {
                 j.mvs[l] = fenc->lowresMvs[l][d - 1];
                 j.mvCosts[l] = fenc->lowresMvCosts[l][d - 1];
             }
         }
-        j.lowresCosts = fenc->lowresCosts[d0][d1];
-        j.rowSatds = fenc->rowSatds[d0][d1];
+        if (!la.m_resident)
+        {
+            j.lowresCosts = fenc->lowresCosts[d0][d1];
+            j.rowSatds = fenc->rowSatds[d0][d1];
+        }
         jobs.push_back(j);
         jobOf.push_back(i);
     }
@@ -507,6 +516,13 @@ bool CostEstimateGroup::runEstimates(const Estimate* est, int n, bool batchMode)
         fenc->costEstAq[d0][d1] = res[k].costEstAq;
         if (d1 == 0)
             fenc->intraMbs[d0] += res[k].intraMbs;
+        if (la.m_resident)
+        {
+            /* nothing was copied back: clear the host-side "not searched / not computed" markers */
+            if (jobs[k].doSearch[0]) fenc->lowresMvs[0][d0 - 1][0].x = 0;
+            if (jobs[k].doSearch[1]) fenc->lowresMvs[1][d1 - 1][0].x = 0;
+            fenc->rowSatds[d0][d1][0] = 0;
+        }
     }
     return true;
 }
@@ -540,6 +556,8 @@ void* x265cuh_open(const x265cuh_params* p, char* err, int errLen)
 }
 
 void x265cuh_close(void* la) { delete (Lookahead*)la; }
+void x265cuh_set_resident(void* la, int on) { ((Lookahead*)la)->m_resident = on != 0; }
+int x265cuh_frame_slot(void* frame) { return ((Lowres*)frame)->slot; }
 void* x265cuh_ctx(void* la) { return ((Lookahead*)la)->m_ctx; }
 const char* x265cuh_error(void* la) { return ((Lookahead*)la)->m_error; }
 

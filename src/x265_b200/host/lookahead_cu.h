@@ -97,6 +97,7 @@ public:
     int m_lambda;
     char m_error[512];
     std::vector<int> m_freeSlots;   /* device mirror slots not bound to a Lowres */
+    bool m_resident;         /* inputs are device pointers and result arrays stay in HBM (only sums return) */
 
     Lookahead();
     ~Lookahead();
@@ -152,6 +153,8 @@ typedef struct x265cuh_params
 } x265cuh_params;
 void* x265cuh_open(const x265cuh_params* p, char* err, int errLen);
 void  x265cuh_close(void* la);
+void  x265cuh_set_resident(void* la, int on);                /* device-resident inputs/outputs (see Lookahead::m_resident) */
+int   x265cuh_frame_slot(void* frame);
 void* x265cuh_ctx(void* la);                                  /* the underlying x265cu_ctx* */
 void  x265cuh_info(void* la, int* out16);                     /* wCU, hCU, nCU, stride, planeSize(lo32), numCoopSlices, numRowsPerSlice, lambda, pixelBytes */
 uint32_t x265cuh_mvcost_crc(void* la);
