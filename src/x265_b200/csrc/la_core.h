@@ -1,17 +1,29 @@
-/* la_core.h -- warp-uniform control logic of the lookahead CU estimate, as a small state machine.
+/* la_core.h -- warp-uniform control logic of the lookahead CU estimate, phase by phase.
  *
  * Product code (part of libx265cu.so).  Plain scalar C++ usable from host and device: the CUDA
- * kernels (x265cu_estimate.cuh) run it redundantly in every lane of the warp that owns a CU (so
- * control flow stays warp-uniform) while the pixel work of each pass -- up to 8 candidate blocks
- * -- is spread over the 32 lanes (one 4x4 sub-block per lane, one candidate per quad).
+ * search kernel (x265cu_kernels.cuh) runs it redundantly in every lane of the warp that owns a CU
+ * row (so control flow stays warp-uniform) while the pixel work of each pass -- up to 8 candidate
+ * blocks -- is spread over the 32 lanes (one 4x4 sub-block per lane, one candidate per quad).
  * tests/core_emul.cpp compiles the very same header on the CPU with scalar evaluators to prove
- * the state machine against the oracle before any GPU time is spent.
+ * the logic against the reference's golden traces before any GPU time is spent.
  *
  * What it restates (file:line in /root/reference/x265_1.9/source):
  *   MV candidates / MVP selection / skip shortcut   encoder/slicetype.cpp:2117-2159
  *   MotionEstimate::motionEstimate, lowres HEX path  encoder/motion.cpp:587-624,670-742,1081-1119
  *   list / bidir / intra decision and accumulation   encoder/slicetype.cpp:2161-2224
- * Every comparison is a strict '<' taken in the reference's candidate order ("first minimum wins").
+ *
+ * Passes of one list search (each pass = candidates measured in parallel, then one update):
+ *   CAND  <=4 neighbour MVs, SATD, no mvcost          -> MVP (+ skipCost)
+ *   START qpel MVP (SAD, no mvcost), rounded MVP, zero  -> search start
+ *   HEX6  6-point hexagon radius 2                      -> move or stay
+ *   HEX3  half hexagon, up to merange/2-1 = 7 times     -> move or stop
+ *   SQ8   8-point unit square                           -> full-pel winner (or the qpel MVP)
+ *   HPEL  4 half-pel SADs                               -> half-pel winner
+ *   QPEL  SATD re-measure + 4 quarter-pel SATDs         -> result
+ * A pass whose winner is decided by "first strict minimum in candidate order" is fed with the
+ * minimum of the packed keys (cost << 3 | k) over its valid candidates, which is exactly how the
+ * reference packs direction bits into the cost (motion.cpp:693-725): one warp min-reduction
+ * replaces the sequential COPYn_IF_LT chain bit-exactly.
  */
 #ifndef X265CU_LA_CORE_H
 #define X265CU_LA_CORE_H
@@ -25,24 +37,13 @@
 #endif
 
 #define LA_COST_MAX (1 << 28)
+#define LA_KEY_NONE 0xFFFFFFFFu
 #define LA_LOWRES_COST_MASK ((1 << 14) - 1)
 #define LA_LOWRES_COST_SHIFT 14
 #define LA_MERANGE 16
 
-/* one candidate block of a pass */
-struct LaCand
-{
-    int valid;
-    int qx, qy;     /* quarter-pel MV relative to the CU position */
-    int satd;       /* 1: SATD, 0: SAD */
-    int addMv;      /* add mvcost(qx,qy) to the measured distortion */
-};
-
-enum LaPhase { LA_PH_CAND = 0, LA_PH_START, LA_PH_HEX6, LA_PH_HEX3, LA_PH_SQ8, LA_PH_HPEL, LA_PH_QPEL, LA_PH_DONE };
-
 struct LaSearch
 {
-    int phase;
     int minx, miny, maxx, maxy;   /* full-pel search bounds (mvmin/mvmax) */
     int numc;
     int c0, c1, c2, c3;           /* packed candidate MVs: (uint16)x | y << 16 */
@@ -57,11 +58,12 @@ struct LaSearch
 
 LA_HD int la_pack_mv(int x, int y) { return (int)(((uint32_t)x & 0xffffu) | ((uint32_t)y << 16)); }
 LA_HD int la_mv_x(int p) { return (int)(int16_t)(p & 0xffff); }
-LA_HD int la_mv_y(int p) { return (int)(int16_t)((uint32_t)p >> 16); }
+LA_HD int la_mv_y(int p) { return p >> 16; }
 LA_HD int la_clip(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
+LA_HD uint32_t la_key(int cost, int k) { return ((uint32_t)cost << 3) | (uint32_t)k; }
 
 /* radius-2 hexagon with wrap-around copies, (x-1)%6 table and the unit square (motion.cpp:64-66),
- * packed as 4-bit fields (value + 2) so that lane-dependent lookups need no memory */
+ * packed as 4-bit fields so that lane-dependent lookups need no memory */
 LA_HD int la_hex2x(int i) { return (int)((0x01343101u >> (4 * i)) & 15) - 2; }   /* -1,-2,-1,1,2,1,-1,-2 */
 LA_HD int la_hex2y(int i) { return (int)((0x20024420u >> (4 * i)) & 15) - 2; }   /* -2,0,2,2,0,-2,-2,0   */
 LA_HD int la_mod6m1(int i) { return (int)((0x05432105u >> (4 * i)) & 15); }       /* 5,0,1,2,3,4,5,0      */
@@ -77,15 +79,7 @@ LA_HD int la_mvcost(const uint16_t* lut, const LaSearch& s, int qx, int qy)
 
 LA_HD bool la_in_range(const LaSearch& s) { return s.bmx >= s.minx && s.bmx <= s.maxx && s.bmy >= s.miny && s.bmy <= s.maxy; }
 
-/* clip the MVP to the qpel search bounds (motion.cpp:600-601) and enter the START pass */
-LA_HD void la_enter_start(LaSearch& s)
-{
-    s.pmx = la_clip(s.minx * 4, s.maxx * 4, s.mvpx);
-    s.pmy = la_clip(s.miny * 4, s.maxy * 4, s.mvpy);
-    s.phase = LA_PH_START;
-}
-
-/* begin the search of one list for CU (cuX, cuY).  nb[] = packed MVs of the right, below,
+/* begin the search of one list for CU (cuX, cuY).  n0..n3 = packed MVs of the right, below,
  * below-left, below-right neighbours in that order, already filtered by availability
  * (slicetype.cpp:2117-2128). */
 LA_HD void la_search_begin(LaSearch& s, int cuX, int cuY, int wCU, int hCU, int bidir, int numc, int n0, int n1, int n2, int n3)
@@ -99,165 +93,129 @@ LA_HD void la_search_begin(LaSearch& s, int cuX, int cuY, int wCU, int hCU, int 
     s.c0 = n0; s.c1 = n1; s.c2 = n2; s.c3 = n3;
     s.mvpx = s.mvpy = 0;
     s.skipCost = 0x7fffffff;
+    s.pmx = s.pmy = 0;
     s.bprecost = s.bcost = LA_COST_MAX;
     s.bmx = s.bmy = s.dir = s.iter = 0;
     s.outx = s.outy = 0;
     s.outcost = LA_COST_MAX;
-    if (numc)
-        s.phase = LA_PH_CAND;
-    else
-        la_enter_start(s);
 }
 
-/* q-th candidate (0..7) of the current pass */
-LA_HD LaCand la_candidate(const LaSearch& s, int q)
+/* ---- CAND: the q-th neighbour MV (q < numc), measured with SATD, no mvcost ---- */
+LA_HD int la_cand_mv(const LaSearch& s, int q) { return q == 0 ? s.c0 : (q == 1 ? s.c1 : (q == 2 ? s.c2 : s.c3)); }
+
+LA_HD void la_upd_cand(LaSearch& s, int c0, int c1, int c2, int c3)
 {
-    LaCand c;
-    c.valid = 0; c.qx = c.qy = 0; c.satd = 0; c.addMv = 1;
-    switch (s.phase)
+    int mvpcost = LA_COST_MAX;
+    for (int k = 0; k < 4; k++)
     {
-    case LA_PH_CAND:
-    {
-        int p = q == 0 ? s.c0 : (q == 1 ? s.c1 : (q == 2 ? s.c2 : s.c3));
-        c.valid = q < s.numc;
-        c.qx = la_mv_x(p); c.qy = la_mv_y(p);
-        c.satd = 1; c.addMv = 0;
-        break;
+        if (k >= s.numc) break;
+        int cost = k == 0 ? c0 : (k == 1 ? c1 : (k == 2 ? c2 : c3));
+        int p = la_cand_mv(s, k);
+        if (cost < mvpcost) { mvpcost = cost; s.mvpx = la_mv_x(p); s.mvpy = la_mv_y(p); }
+        /* holds the cost of the last candidate measured while the best MVP is still zero */
+        if (!(s.mvpx | s.mvpy) && s.bidir)
+            s.skipCost = cost;
     }
-    case LA_PH_START:
-        if (q == 0) { c.valid = 1; c.qx = s.pmx; c.qy = s.pmy; c.addMv = 0; }
-        else if (q == 1) { c.valid = ((s.pmx | s.pmy) & 3) != 0; c.qx = ((s.pmx + 2) >> 2) * 4; c.qy = ((s.pmy + 2) >> 2) * 4; }
-        else if (q == 2) { c.valid = (s.pmx | s.pmy) != 0; }
-        break;
-    case LA_PH_HEX6:
-        c.valid = q < 6;
-        c.qx = (s.bmx + la_hex2x((q + 1) & 7)) * 4; c.qy = (s.bmy + la_hex2y((q + 1) & 7)) * 4;
-        break;
-    case LA_PH_HEX3:
-        c.valid = q < 3;
-        c.qx = (s.bmx + la_hex2x((s.dir + q) & 7)) * 4; c.qy = (s.bmy + la_hex2y((s.dir + q) & 7)) * 4;
-        break;
-    case LA_PH_SQ8:
-        c.valid = 1;
-        c.qx = (s.bmx + la_sq1x(q + 1)) * 4; c.qy = (s.bmy + la_sq1y(q + 1)) * 4;
-        break;
-    case LA_PH_HPEL:
-        c.valid = q < 4;
-        c.qx = s.bmx + la_sq1x((q + 1) & 7) * 2; c.qy = s.bmy + la_sq1y((q + 1) & 7) * 2;
-        break;
-    case LA_PH_QPEL:
-        c.valid = q < 5;
-        c.qx = s.bmx + la_sq1x(q & 7); c.qy = s.bmy + la_sq1y(q & 7);
-        c.satd = 1;
-        break;
-    default:
-        break;
-    }
-    return c;
 }
 
-/* consume the costs of the current pass (cost[k] already includes mvcost where addMv was set;
- * entries of invalid candidates are ignored) and move to the next phase */
-LA_HD void la_update(LaSearch& s, const int cost[8], const uint16_t* lut)
+/* ---- START (motion.cpp:600-624): q0 = clipped qpel MVP (no mvcost), q1 = rounded MVP (only when
+ * the MVP is sub-pel), q2 = zero MV (only when the MVP is non-zero) ---- */
+LA_HD void la_enter_start(LaSearch& s)
 {
-    switch (s.phase)
+    s.pmx = la_clip(s.minx * 4, s.maxx * 4, s.mvpx);
+    s.pmy = la_clip(s.miny * 4, s.maxy * 4, s.mvpy);
+}
+LA_HD bool la_start_subpel(const LaSearch& s) { return ((s.pmx | s.pmy) & 3) != 0; }
+LA_HD bool la_start_nonzero(const LaSearch& s) { return (s.pmx | s.pmy) != 0; }
+
+LA_HD void la_upd_start(LaSearch& s, int c0, int c1, int c2)
+{
+    s.bprecost = c0;
+    s.bmx = (s.pmx + 2) >> 2; s.bmy = (s.pmy + 2) >> 2;
+    s.bcost = la_start_subpel(s) ? c1 : c0;
+    if (la_start_nonzero(s) && c2 < s.bcost) { s.bcost = c2; s.bmx = s.bmy = 0; }
+}
+
+/* ---- HEX6: candidate q < 6 at bm + hex2[q + 1]; returns true when the half-hexagon loop runs ---- */
+LA_HD bool la_upd_hex6(LaSearch& s, uint32_t key)
+{
+    if (key != LA_KEY_NONE && (int)(key >> 3) < s.bcost)
     {
-    case LA_PH_CAND:
-    {
-        int mvpcost = LA_COST_MAX;
-        for (int k = 0; k < 4; k++)
-        {
-            if (k >= s.numc) break;
-            int p = k == 0 ? s.c0 : (k == 1 ? s.c1 : (k == 2 ? s.c2 : s.c3));
-            if (cost[k] < mvpcost) { mvpcost = cost[k]; s.mvpx = la_mv_x(p); s.mvpy = la_mv_y(p); }
-            /* holds the cost of the last candidate measured while the best MVP is still zero */
-            if (!(s.mvpx | s.mvpy) && s.bidir)
-                s.skipCost = cost[k];
-        }
-        la_enter_start(s);
-        break;
+        int best = (int)(key & 7);
+        s.bcost = (int)(key >> 3);
+        s.dir = best;
+        s.bmx += la_hex2x(best + 1); s.bmy += la_hex2y(best + 1);
+        s.iter = (LA_MERANGE >> 1) - 1;
+        return la_in_range(s);
     }
-    case LA_PH_START:
-        s.bprecost = cost[0];
-        s.bmx = (s.pmx + 2) >> 2; s.bmy = (s.pmy + 2) >> 2;
-        s.bcost = ((s.pmx | s.pmy) & 3) ? cost[1] : cost[0];
-        if ((s.pmx | s.pmy) && cost[2] < s.bcost) { s.bcost = cost[2]; s.bmx = s.bmy = 0; }
-        s.phase = LA_PH_HEX6;
-        break;
-    case LA_PH_HEX6:
+    return false;
+}
+
+/* ---- HEX3: candidate q < 3 at bm + hex2[dir + q]; returns true to run another round ---- */
+LA_HD bool la_upd_hex3(LaSearch& s, uint32_t key)
+{
+    if (key != LA_KEY_NONE && (int)(key >> 3) < s.bcost)
     {
-        int best = -1;
-        for (int k = 0; k < 6; k++)
-            if (cost[k] < s.bcost) { s.bcost = cost[k]; best = k; }
-        s.phase = LA_PH_SQ8;
-        if (best >= 0)
-        {
-            s.dir = best;
-            s.bmx += la_hex2x(best + 1); s.bmy += la_hex2y(best + 1);
-            s.iter = (LA_MERANGE >> 1) - 1;
-            if (la_in_range(s)) s.phase = LA_PH_HEX3;
-        }
-        break;
+        int step = (int)(key & 7);
+        s.bcost = (int)(key >> 3);
+        s.dir = la_mod6m1(s.dir + step);      /* mod6m1[dir + (step + 1) - 2 + 1] */
+        s.bmx += la_hex2x(s.dir + 1); s.bmy += la_hex2y(s.dir + 1);
+        s.iter--;
+        return s.iter > 0 && la_in_range(s);
     }
-    case LA_PH_HEX3:
+    return false;
+}
+
+/* ---- SQ8: candidate q < 8 at bm + square1[q + 1]; afterwards the winner becomes quarter-pel.
+ * Returns true when the sub-pel refine runs, false when the search ends here (zero residual) ---- */
+LA_HD bool la_upd_sq8(LaSearch& s, uint32_t key, const uint16_t* lut)
+{
+    if (key != LA_KEY_NONE && (int)(key >> 3) < s.bcost)
     {
-        int step = -1;
-        for (int k = 0; k < 3; k++)
-            if (cost[k] < s.bcost) { s.bcost = cost[k]; step = k; }
-        s.phase = LA_PH_SQ8;
-        if (step >= 0)
-        {
-            s.dir = la_mod6m1(s.dir + step);      /* mod6m1[dir + (step + 1) - 2 + 1] */
-            s.bmx += la_hex2x(s.dir + 1); s.bmy += la_hex2y(s.dir + 1);
-            s.iter--;
-            if (s.iter > 0 && la_in_range(s)) s.phase = LA_PH_HEX3;
-        }
-        break;
-    }
-    case LA_PH_SQ8:
-    {
-        int best = 0;
-        for (int k = 0; k < 8; k++)
-            if (cost[k] < s.bcost) { s.bcost = cost[k]; best = k + 1; }
+        int best = (int)(key & 7) + 1;
+        s.bcost = (int)(key >> 3);
         s.bmx += la_sq1x(best); s.bmy += la_sq1y(best);
-        if (s.bprecost < s.bcost) { s.bmx = s.pmx; s.bmy = s.pmy; s.bcost = s.bprecost; }
-        else { s.bmx *= 4; s.bmy *= 4; }
-        if (!s.bcost)
-        {
-            s.outcost = la_mvcost(lut, s, s.bmx, s.bmy);
-            s.outx = s.bmx; s.outy = s.bmy;
-            s.phase = LA_PH_DONE;
-        }
-        else
-            s.phase = LA_PH_HPEL;
-        break;
     }
-    case LA_PH_HPEL:
+    if (s.bprecost < s.bcost) { s.bmx = s.pmx; s.bmy = s.pmy; s.bcost = s.bprecost; }
+    else { s.bmx *= 4; s.bmy *= 4; }
+    if (!s.bcost)
     {
-        int bdir = 0;
-        for (int k = 0; k < 4; k++)
-            if (cost[k] < s.bcost) { s.bcost = cost[k]; bdir = k + 1; }
+        s.outcost = la_mvcost(lut, s, s.bmx, s.bmy);
+        s.outx = s.bmx; s.outy = s.bmy;
+        return false;
+    }
+    return true;
+}
+
+/* ---- HPEL: candidate q < 4 at bm + square1[q + 1] * 2 (quarter-pel units), SAD + mvcost ---- */
+LA_HD void la_upd_hpel(LaSearch& s, uint32_t key)
+{
+    if (key != LA_KEY_NONE && (int)(key >> 3) < s.bcost)
+    {
+        int bdir = (int)(key & 7) + 1;
+        s.bcost = (int)(key >> 3);
         s.bmx += la_sq1x(bdir) * 2; s.bmy += la_sq1y(bdir) * 2;
-        s.phase = LA_PH_QPEL;
-        break;
     }
-    case LA_PH_QPEL:
+}
+
+/* ---- QPEL: q0 = SATD re-measure at bm (may go up), q1..q4 at bm + square1[q]; key covers q >= 1 ---- */
+LA_HD void la_upd_qpel(LaSearch& s, int c0, uint32_t key)
+{
+    s.bcost = c0;
+    if (key != LA_KEY_NONE && (int)(key >> 3) < s.bcost)
     {
-        int bdir = 0;
-        s.bcost = cost[0];       /* SATD re-measure at the half-pel winner (may go up) */
-        for (int k = 1; k < 5; k++)
-            if (cost[k] < s.bcost) { s.bcost = cost[k]; bdir = k; }
+        int bdir = (int)(key & 7);
+        s.bcost = (int)(key >> 3);
         s.bmx += la_sq1x(bdir); s.bmy += la_sq1y(bdir);
-        s.outcost = s.bcost; s.outx = s.bmx; s.outy = s.bmy;
-        s.phase = LA_PH_DONE;
-        break;
     }
-    default:
-        break;
-    }
-    if (s.phase == LA_PH_DONE && s.skipCost < 64 && s.skipCost < s.outcost && s.bidir)
+    s.outcost = s.bcost; s.outx = s.bmx; s.outy = s.bmy;
+}
+
+/* bidir-only zero-MV skip shortcut (slicetype.cpp:2155-2159), applied once the search is done */
+LA_HD void la_finish_skip(LaSearch& s)
+{
+    if (s.skipCost < 64 && s.skipCost < s.outcost && s.bidir)
     {
-        /* bidir-only zero-MV skip shortcut (slicetype.cpp:2155-2159) */
         s.outcost = s.skipCost;
         s.outx = s.outy = 0;
     }
@@ -270,8 +228,7 @@ struct LaCuResult
     uint16_t lowresCost;
 };
 
-/* listCost[i] < 0 means list i is not part of this estimate.  bicost0/bicost1: SATD of the
- * avg(L0-MC, L1-MC) and co-located average candidates (B only). */
+/* bicost0/bicost1: SATD of the avg(L0-MC, L1-MC) and co-located average candidates (B only). */
 LA_HD LaCuResult la_cu_finish(int cuX, int cuY, int wCU, int hCU, int bidir, int cost0, int cost1,
                               int bicost0, int bicost1, int intraCost, int hasInvQ, int invQ)
 {

@@ -238,8 +238,14 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     c->pixelMax = (1 << cfg->bitDepth) - 1;
     c->correction = 14 - cfg->bitDepth;
     c->bf = cfg->bframes;
-    c->searchWarps = cfg->searchWarps > 0 ? cfg->searchWarps : 16;
-    if (c->searchWarps > 16) c->searchWarps = 16;   /* search_kernel is compiled for <= 512 threads */
+    c->searchWarps = cfg->searchWarps > 0 ? cfg->searchWarps : 32;
+    if (c->searchWarps > 32) c->searchWarps = 32;
+    if ((size_t)(c->searchWarps + 1) * (((size_t)cfg->srcWidth / 2 + 7) / 8) * sizeof(int) > 48 * 1024)
+    {
+        delete c;
+        snprintf(g_openError, sizeof(g_openError), "x265cu_open: picture too wide for the search kernel's MV ring");
+        return X265CU_EINVAL;
+    }
 
     /* geometry: Lowres::create, common/lowres.cpp:34-48 */
     GeomDev& g = c->g;
@@ -521,6 +527,7 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     const size_t sumsBytes = alignUp((size_t)n * 32, 256);
     size_t total = sumsBytes;
     bool wantArrays = false;
+    int maxItemRows = 1;
     for (int i = 0; i < n; i++)
     {
         const x265cu_job& j = jobs[i];
@@ -538,17 +545,20 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
         {
             bool useSlices = j.sliced && c->cfg.numCoopSlices > 1;   /* (p1 > b || search) holds here */
             int ns = useSlices ? c->cfg.numCoopSlices : 1;
-            for (int s = 0; s < ns; s++)
-            {
-                SearchItem it;
-                it.job = i;
-                it.firstY = useSlices ? c->cfg.numRowsPerSlice * s : 0;
-                it.lastY = (!useSlices || s == ns - 1) ? g.hCU - 1 : c->cfg.numRowsPerSlice * (s + 1) - 1;
-                items.push_back(it);
-            }
+            /* one work item per (list searched, slice): the two lists are independent searches */
+            for (int l = 0; l < 2; l++)
+                for (int s = 0; s < ns && j.doSearch[l]; s++)
+                {
+                    SearchItem it;
+                    it.job = i;
+                    it.list = l;
+                    it.firstY = useSlices ? c->cfg.numRowsPerSlice * s : 0;
+                    it.lastY = (!useSlices || s == ns - 1) ? g.hCU - 1 : c->cfg.numRowsPerSlice * (s + 1) - 1;
+                    if (it.lastY - it.firstY + 1 > maxItemRows) maxItemRows = it.lastY - it.firstY + 1;
+                    items.push_back(it);
+                }
         }
-        else
-            costIdx.push_back(i);
+        costIdx.push_back(i);     /* bidir / intra decision + sums of every estimate: cost_kernel */
         if (j.weighted && j.doSearch[0]) weightedJobs.push_back(i);
     }
     /* weighted reference pool */
@@ -630,11 +640,13 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     if (!items.empty())
     {
         KernelScope ks(c, X265CU_K_SEARCH);
-        int warps = c->searchWarps;
+        /* one warp per CU row of the tallest item, capped by the CTA size */
+        int warps = maxItemRows < c->searchWarps ? maxItemRows : c->searchWarps;
+        size_t smem = (size_t)(warps + 1) * g.wCU * sizeof(int);
         if (c->pb == 1)
-            search_kernel<uint8_t><<<(unsigned)items.size(), warps * 32, 0, c->stream>>>((const JobDev*)(c->dArgs + offJobs), (const SearchItem*)(c->dArgs + offItems), g, c->dLut + 2 * 32768);
+            search_kernel<uint8_t><<<(unsigned)items.size(), warps * 32, smem, c->stream>>>((const JobDev*)(c->dArgs + offJobs), (const SearchItem*)(c->dArgs + offItems), g, c->dLut + 2 * 32768);
         else
-            search_kernel<uint16_t><<<(unsigned)items.size(), warps * 32, 0, c->stream>>>((const JobDev*)(c->dArgs + offJobs), (const SearchItem*)(c->dArgs + offItems), g, c->dLut + 2 * 32768);
+            search_kernel<uint16_t><<<(unsigned)items.size(), warps * 32, smem, c->stream>>>((const JobDev*)(c->dArgs + offJobs), (const SearchItem*)(c->dArgs + offItems), g, c->dLut + 2 * 32768);
         CU_TRY(c, cudaGetLastError());
     }
     if (!costIdx.empty())

@@ -312,194 +312,7 @@ struct JobDev
     int bidir;
 };
 
-struct SearchItem { int job, firstY, lastY; };
-
-/* cost of one candidate for this lane's quad: partial over the lane's 4x4, quad-reduced */
-template <typename P>
-__device__ __forceinline__ int eval_cand(const LaCand& c, const LaSearch& s, const uint16_t* __restrict__ lut,
-                                         const RefPlanes<P>& ref, int px, int py, const typename Px<P>::Row4 fe[4])
-{
-    typename Px<P>::Row4 r[4];
-    int part = 0;
-    if (c.valid)
-    {
-        mc_fetch4x4<P>(ref, px, py, c.qx, c.qy, r);
-        part = c.satd ? satd4x4_abs<P>(fe, r) : sad4x4<P>(fe, r);
-    }
-    int cost = quad_sum(part);
-    if (c.satd) cost >>= 1;
-    if (c.addMv && c.valid) cost += la_mvcost(lut, s, c.qx, c.qy);
-    return c.valid ? cost : LA_COST_MAX;
-}
-
-#define SEARCH_MAX_ROWS 512
-
-template <typename P>
-__global__ void __launch_bounds__(512, 1) search_kernel(const JobDev* __restrict__ jobs, const SearchItem* __restrict__ items,
-                                                          GeomDev g, const uint16_t* __restrict__ lut)
-{
-    __shared__ int sProg[SEARCH_MAX_ROWS];
-    __shared__ unsigned long long sSums[3];
-    __shared__ JobDev sJob;
-    volatile int* prog = sProg;
-    const SearchItem it = items[blockIdx.x];
-    const int nRows = it.lastY - it.firstY + 1;
-    for (int i = threadIdx.x; i < nRows; i += blockDim.x) sProg[i] = g.wCU;
-    if (threadIdx.x < 3) sSums[threadIdx.x] = 0;
-    for (int i = threadIdx.x; i < (int)(sizeof(JobDev) / sizeof(int)); i += blockDim.x)
-        ((int*)&sJob)[i] = ((const int*)&jobs[it.job])[i];
-    __syncthreads();
-    const JobDev& job = sJob;
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nWarps = blockDim.x >> 5;
-    const int q = lane >> 2, sub = lane & 3, bx = (sub & 1) * 4, by = (sub >> 1) * 4;
-    const int W = g.wCU, H = g.hCU;
-    const P* fencPlane = (const P*)job.fenc;
-    RefPlanes<P> r0w = { (const P*)job.ref0w, g.planeSize, g.stride };
-    RefPlanes<P> r0 = { (const P*)job.ref0, g.planeSize, g.stride };
-    RefPlanes<P> r1 = { (const P*)job.ref1, g.planeSize, g.stride };
-    const int bidir = job.bidir;
-
-    long long accCost = 0, accAq = 0;
-    int accIntra = 0;
-
-    for (int rowIdx = warp; rowIdx < nRows; rowIdx += nWarps)
-    {
-        const int cuY = it.lastY - rowIdx;
-        const int lastRow = rowIdx == 0;
-        int rowSum = 0;
-        int prevMv[2] = { 0, 0 };   /* MV of (cuX+1, cuY): our own previous result */
-        for (int cuX = W - 1; cuX >= 0; cuX--)
-        {
-            if (!lastRow)
-            {
-                const int need = cuX > 0 ? cuX - 1 : 0;
-                while (prog[rowIdx - 1] > need) { }
-                __syncwarp();
-                __threadfence_block();
-            }
-            const int cuXY = cuX + cuY * W;
-            const int px = 8 * cuX + bx, py = 8 * cuY + by;
-            typename Px<P>::Row4 fe[4];
-#pragma unroll
-            for (int y = 0; y < 4; y++)
-                fe[y] = Px<P>::load_aligned(fencPlane + (int64_t)(py + y) * g.stride + px);
-
-            int listCost[2] = { LA_COST_MAX, LA_COST_MAX };
-            int mvOut[2] = { 0, 0 };
-#pragma unroll
-            for (int i = 0; i < 2; i++)
-            {
-                if (i == 1 && !bidir) break;
-                if (!job.doSearch[i])
-                {
-                    listCost[i] = job.mvCosts[i][cuXY];
-                    mvOut[i] = job.mvs[i][cuXY];
-                    continue;
-                }
-                volatile const int* mv = job.mvs[i];
-                int nb0 = 0, nb1 = 0, nb2 = 0, nb3 = 0, numc = 0;
-                if (cuX < W - 1) { nb0 = prevMv[i]; numc = 1; }
-                if (!lastRow)
-                {
-                    int below = mv[cuXY + W];
-                    if (numc == 0) nb0 = below; else nb1 = below;
-                    numc++;
-                    if (cuX > 0)
-                    {
-                        int bl = mv[cuXY + W - 1];
-                        if (numc == 1) nb1 = bl; else nb2 = bl;
-                        numc++;
-                    }
-                    if (cuX < W - 1)
-                    {
-                        int br = mv[cuXY + W + 1];
-                        if (numc == 2) nb2 = br; else nb3 = br;
-                        numc++;
-                    }
-                }
-                const RefPlanes<P>& ref = i ? r1 : r0w;
-                LaSearch s;
-                la_search_begin(s, cuX, cuY, W, H, bidir, numc, nb0, nb1, nb2, nb3);
-#pragma unroll 1
-                while (s.phase != LA_PH_DONE)
-                {
-                    LaCand c = la_candidate(s, q);
-                    int cost = eval_cand<P>(c, s, lut, ref, px, py, fe);
-                    int cs[8];
-#pragma unroll
-                    for (int k = 0; k < 8; k++) cs[k] = __shfl_sync(FULL_MASK, cost, 4 * k);
-                    la_update(s, cs, lut);
-                }
-                listCost[i] = s.outcost;
-                mvOut[i] = la_pack_mv(s.outx, s.outy);
-                prevMv[i] = mvOut[i];
-                if (lane == 0)
-                {
-                    ((volatile int*)job.mvs[i])[cuXY] = mvOut[i];
-                    job.mvCosts[i][cuXY] = s.outcost;
-                    job.outMvs[i][cuXY] = mvOut[i];
-                    job.outMvCosts[i][cuXY] = s.outcost;
-                }
-            }
-
-            int bi0 = LA_COST_MAX, bi1 = LA_COST_MAX;
-            if (bidir)
-            {
-                /* quad 0: avg(L0-MC, L1-MC) on the UN-weighted references; quad 1: co-located average */
-                typename Px<P>::Row4 a[4], b[4];
-                int part = 0;
-                if (q < 2)
-                {
-                    int m0 = q == 0 ? mvOut[0] : 0, m1 = q == 0 ? mvOut[1] : 0;
-                    mc_fetch4x4<P>(r0, px, py, la_mv_x(m0), la_mv_y(m0), a);
-                    mc_fetch4x4<P>(r1, px, py, la_mv_x(m1), la_mv_y(m1), b);
-#pragma unroll
-                    for (int y = 0; y < 4; y++) a[y] = Px<P>::avg(a[y], b[y]);
-                    part = satd4x4_abs<P>(fe, a);
-                }
-                int cost = quad_sum(part) >> 1;
-                bi0 = __shfl_sync(FULL_MASK, cost, 0);
-                bi1 = __shfl_sync(FULL_MASK, cost, 4);
-            }
-            const int hasQ = job.invQ != NULL;
-            LaCuResult res = la_cu_finish(cuX, cuY, W, H, bidir, listCost[0], listCost[1], bi0, bi1, job.intraCost[cuXY],
-                                          hasQ, hasQ ? job.invQ[cuXY] : 256);
-            if (res.scored)
-            {
-                accCost += res.bcost;
-                accAq += res.bcostAq;
-                accIntra += res.intraMb;
-            }
-            rowSum += res.bcostAq;
-            if (lane == 0)
-            {
-                job.lowresCosts[cuXY] = res.lowresCost;
-                job.outLowresCosts[cuXY] = res.lowresCost;
-            }
-            __syncwarp();
-            if (lane == 0)
-            {
-                __threadfence_block();
-                prog[rowIdx] = cuX;
-            }
-        }
-        if (lane == 0)
-        {
-            job.rowSatds[cuY] = rowSum;
-            job.outRows[cuY] = rowSum;
-        }
-    }
-    if (lane == 0)
-    {
-        atomicAdd(&sSums[0], (unsigned long long)accCost);
-        atomicAdd(&sSums[1], (unsigned long long)accAq);
-        atomicAdd(&sSums[2], (unsigned long long)accIntra);
-    }
-    __syncthreads();
-    if (threadIdx.x < 3)
-        atomicAdd(&job.outSums[threadIdx.x], sSums[threadIdx.x]);
-}
+#include "x265cu_search.cuh"
 
 /* cost-only estimates (both bDoSearch false): every CU is independent.  grid = (hCU, jobs);
  * a block owns one CU row of one job, so rowSatds needs no atomics. */

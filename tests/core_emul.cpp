@@ -20,17 +20,17 @@ struct Refs
     intptr_t stride;
 };
 
-int evalCand(const pixel* fenc, const Refs& r, intptr_t off, const LaCand& c)
+int evalQ(const pixel* fenc, const Refs& r, intptr_t off, int qx, int qy, int satd)
 {
     pixel blk[64];
     /* exercise la_mc_src (the kernel's address computation) instead of the oracle's own MC */
-    LaMcSrc m = la_mc_src(c.qx, c.qy);
+    LaMcSrc m = la_mc_src(qx, qy);
     const pixel* a = r.plane[m.planeA] + off + m.ax + (intptr_t)m.ay * r.stride;
     const pixel* b = r.plane[m.planeB] + off + m.bx + (intptr_t)m.by * r.stride;
     for (int y = 0; y < 8; y++)
         for (int x = 0; x < 8; x++)
             blk[8 * y + x] = m.avg ? (pixel)((a[y * r.stride + x] + b[y * r.stride + x] + 1) >> 1) : a[y * r.stride + x];
-    return c.satd ? ola_satd8x8(fenc, 8, blk, 8) : ola_sad8x8(fenc, 8, blk, 8);
+    return satd ? ola_satd8x8(fenc, 8, blk, 8) : ola_sad8x8(fenc, 8, blk, 8);
 }
 
 struct Acc { int64_t costEst, costEstAq; int intraMbs; };
@@ -70,23 +70,98 @@ void emulCU(ola_ctx* c, ola_frame* fenc, ola_frame* fref0, ola_frame* fref1, con
         const Refs& ref = i ? r1 : wref0;
         LaSearch s;
         la_search_begin(s, cuX, cuY, W, H, bidir, numc, nb[0], nb[1], nb[2], nb[3]);
-        int guard = 0;
-        while (s.phase != LA_PH_DONE)
+        /* one pass = up to 8 candidates measured "in parallel", then one uniform update,
+         * exactly the sequence of the CUDA search kernel */
+        int cost[8];
+        struct Pass
         {
-            int cost[8];
-            for (int q = 0; q < 8; q++)
+            static uint32_t minKey(const int* c, const bool* valid, int from, int n)
             {
-                LaCand cd = la_candidate(s, q);
+                uint32_t key = LA_KEY_NONE;
+                for (int k = from; k < n; k++)
+                    if (valid[k]) { uint32_t kk = la_key(c[k], k - (from ? 0 : 0)); if (kk < key) key = kk; }
+                return key;
+            }
+        };
+        bool valid[8];
+        if (numc)
+        {
+            for (int q = 0; q < 4; q++)
+            {
                 cost[q] = LA_COST_MAX;
-                if (cd.valid)
+                if (q < numc)
                 {
-                    cost[q] = evalCand(fb, ref, off, cd);
-                    if (cd.addMv) cost[q] += la_mvcost(c->mvcost, s, cd.qx, cd.qy);
+                    int p = la_cand_mv(s, q);
+                    cost[q] = evalQ(fb, ref, off, la_mv_x(p), la_mv_y(p), 1);
                 }
             }
-            la_update(s, cost, c->mvcost);
-            if (++guard > 64) break;
+            la_upd_cand(s, cost[0], cost[1], cost[2], cost[3]);
         }
+        la_enter_start(s);
+        {
+            int c0 = evalQ(fb, ref, off, s.pmx, s.pmy, 0);
+            int c1 = LA_COST_MAX, c2 = LA_COST_MAX;
+            if (la_start_subpel(s))
+            {
+                int rx = ((s.pmx + 2) >> 2) * 4, ry = ((s.pmy + 2) >> 2) * 4;
+                c1 = evalQ(fb, ref, off, rx, ry, 0) + la_mvcost(c->mvcost, s, rx, ry);
+            }
+            if (la_start_nonzero(s))
+                c2 = evalQ(fb, ref, off, 0, 0, 0) + la_mvcost(c->mvcost, s, 0, 0);
+            la_upd_start(s, c0, c1, c2);
+        }
+        {
+            for (int q = 0; q < 8; q++)
+            {
+                valid[q] = q < 6;
+                if (!valid[q]) continue;
+                int qx = (s.bmx + la_hex2x(q + 1)) * 4, qy = (s.bmy + la_hex2y(q + 1)) * 4;
+                cost[q] = evalQ(fb, ref, off, qx, qy, 0) + la_mvcost(c->mvcost, s, qx, qy);
+            }
+            bool more = la_upd_hex6(s, Pass::minKey(cost, valid, 0, 8));
+            int guard = 0;
+            while (more && guard++ < 16)
+            {
+                for (int q = 0; q < 8; q++)
+                {
+                    valid[q] = q < 3;
+                    if (!valid[q]) continue;
+                    int qx = (s.bmx + la_hex2x(s.dir + q)) * 4, qy = (s.bmy + la_hex2y(s.dir + q)) * 4;
+                    cost[q] = evalQ(fb, ref, off, qx, qy, 0) + la_mvcost(c->mvcost, s, qx, qy);
+                }
+                more = la_upd_hex3(s, Pass::minKey(cost, valid, 0, 8));
+            }
+        }
+        bool subpel;
+        {
+            for (int q = 0; q < 8; q++)
+            {
+                valid[q] = true;
+                int qx = (s.bmx + la_sq1x(q + 1)) * 4, qy = (s.bmy + la_sq1y(q + 1)) * 4;
+                cost[q] = evalQ(fb, ref, off, qx, qy, 0) + la_mvcost(c->mvcost, s, qx, qy);
+            }
+            subpel = la_upd_sq8(s, Pass::minKey(cost, valid, 0, 8), c->mvcost);
+        }
+        if (subpel)
+        {
+            for (int q = 0; q < 8; q++)
+            {
+                valid[q] = q < 4;
+                if (!valid[q]) continue;
+                int qx = s.bmx + la_sq1x(q + 1) * 2, qy = s.bmy + la_sq1y(q + 1) * 2;
+                cost[q] = evalQ(fb, ref, off, qx, qy, 0) + la_mvcost(c->mvcost, s, qx, qy);
+            }
+            la_upd_hpel(s, Pass::minKey(cost, valid, 0, 8));
+            for (int q = 0; q < 8; q++)
+            {
+                valid[q] = q >= 1 && q < 5;
+                if (q >= 5) continue;
+                int qx = s.bmx + la_sq1x(q), qy = s.bmy + la_sq1y(q);
+                cost[q] = evalQ(fb, ref, off, qx, qy, 1) + la_mvcost(c->mvcost, s, qx, qy);
+            }
+            la_upd_qpel(s, cost[0], Pass::minKey(cost, valid, 0, 8));
+        }
+        la_finish_skip(s);
         listCost[i] = s.outcost;
         fenc->mvCosts[i][dist][cuXY] = s.outcost;
         mv[cuXY].x = (int16_t)s.outx; mv[cuXY].y = (int16_t)s.outy;
