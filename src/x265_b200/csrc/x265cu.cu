@@ -238,9 +238,9 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     c->pixelMax = (1 << cfg->bitDepth) - 1;
     c->correction = 14 - cfg->bitDepth;
     c->bf = cfg->bframes;
-    c->searchWarps = cfg->searchWarps > 0 ? cfg->searchWarps : 32;
-    if (c->searchWarps > 32) c->searchWarps = 32;
-    if ((size_t)(c->searchWarps + 1) * (((size_t)cfg->srcWidth / 2 + 7) / 8) * sizeof(int) > 48 * 1024)
+    c->searchWarps = cfg->searchWarps > 0 ? cfg->searchWarps : 4;    /* CU rows (= warps) per search CTA */
+    if (c->searchWarps > SEARCH_MAX_GROUP_ROWS) c->searchWarps = SEARCH_MAX_GROUP_ROWS;
+    if ((size_t)c->searchWarps * (((size_t)cfg->srcWidth / 2 + 7) / 8) * sizeof(int) > 48 * 1024)
     {
         delete c;
         snprintf(g_openError, sizeof(g_openError), "x265cu_open: picture too wide for the search kernel's MV ring");
@@ -258,7 +258,6 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     g.paddedLines = g.lines + 2 * cfg->marginY;
     g.planeSize = (int64_t)g.stride * g.paddedLines;
     g.padOffset = (int64_t)g.stride * cfg->marginY + cfg->marginX;
-    if (g.hCU > SEARCH_MAX_ROWS) { delete c; snprintf(g_openError, sizeof(g_openError), "x265cu_open: picture too tall"); return X265CU_EINVAL; }
 
 #define OPEN_TRY(call)                                                                              \
     do {                                                                                            \
@@ -549,13 +548,23 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
             for (int l = 0; l < 2; l++)
                 for (int s = 0; s < ns && j.doSearch[l]; s++)
                 {
-                    SearchItem it;
-                    it.job = i;
-                    it.list = l;
-                    it.firstY = useSlices ? c->cfg.numRowsPerSlice * s : 0;
-                    it.lastY = (!useSlices || s == ns - 1) ? g.hCU - 1 : c->cfg.numRowsPerSlice * (s + 1) - 1;
-                    if (it.lastY - it.firstY + 1 > maxItemRows) maxItemRows = it.lastY - it.firstY + 1;
-                    items.push_back(it);
+                    const int sFirst = useSlices ? c->cfg.numRowsPerSlice * s : 0;
+                    const int sLast = (!useSlices || s == ns - 1) ? g.hCU - 1 : c->cfg.numRowsPerSlice * (s + 1) - 1;
+                    /* row groups, bottom first: a group only waits for a group with a lower block index */
+                    for (int bottom = sLast; bottom >= sFirst; bottom -= c->searchWarps)
+                    {
+                        SearchItem it;
+                        it.job = i;
+                        it.list = l;
+                        it.sliceFirstY = sFirst;
+                        it.sliceLastY = sLast;
+                        it.lastY = bottom;
+                        it.firstY = bottom - c->searchWarps + 1 > sFirst ? bottom - c->searchWarps + 1 : sFirst;
+                        it.progBase = (i * 2 + l) * g.hCU;
+                        it.pad = 0;
+                        if (it.lastY - it.firstY + 1 > maxItemRows) maxItemRows = it.lastY - it.firstY + 1;
+                        items.push_back(it);
+                    }
                 }
         }
         costIdx.push_back(i);     /* bidir / intra decision + sums of every estimate: cost_kernel */
@@ -573,7 +582,8 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     size_t offItems = alignUp(offJobs + (size_t)n * sizeof(JobDev), 256);
     size_t offCost = alignUp(offItems + items.size() * sizeof(SearchItem), 256);
     size_t offW = alignUp(offCost + costIdx.size() * sizeof(int), 256);
-    size_t argBytes = alignUp(offW + weightedJobs.size() * sizeof(WeightDev), 256);
+    size_t offProg = alignUp(offW + weightedJobs.size() * sizeof(WeightDev), 256);   /* device only: wavefront progress */
+    size_t argBytes = alignUp(offProg + (size_t)n * 2 * g.hCU * sizeof(int), 256);
     if (growHost(c, &c->hArgs, &c->hArgsCap, argBytes) || growDevice(c, &c->dArgs, &c->dArgsCap, argBytes)) return X265CU_ECUDA;
     if (growDevice(c, &c->dStage, &c->dStageCap, total) || growHost(c, &c->hStage, &c->hStageCap, total)) return X265CU_ECUDA;
 
@@ -623,9 +633,11 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
         hw[k].scale = j.wScale;
         weightArgs(c, j.wScale, j.wDenom, j.wOffset, &hw[k].round, &hw[k].shift, &hw[k].offset);
     }
-    CU_TRY(c, cudaMemcpyAsync(c->dArgs, c->hArgs, argBytes, cudaMemcpyHostToDevice, c->stream));
-    c->stats.h2dBytes += (int64_t)argBytes;
+    CU_TRY(c, cudaMemcpyAsync(c->dArgs, c->hArgs, offProg, cudaMemcpyHostToDevice, c->stream));
+    c->stats.h2dBytes += (int64_t)offProg;
     CU_TRY(c, cudaMemsetAsync(c->dStage, 0, sumsBytes, c->stream));
+    if (!items.empty())
+        CU_TRY(c, cudaMemsetAsync(c->dArgs + offProg, 0, (size_t)n * 2 * g.hCU * sizeof(int), c->stream));
 
     if (!weightedJobs.empty())
     {
@@ -640,13 +652,14 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     if (!items.empty())
     {
         KernelScope ks(c, X265CU_K_SEARCH);
-        /* one warp per CU row of the tallest item, capped by the CTA size */
-        int warps = maxItemRows < c->searchWarps ? maxItemRows : c->searchWarps;
-        size_t smem = (size_t)(warps + 1) * g.wCU * sizeof(int);
+        /* one CTA per row group, one warp per CU row of the group */
+        int warps = maxItemRows;
+        size_t smem = (size_t)warps * g.wCU * sizeof(int);
+        int* dProg = (int*)(c->dArgs + offProg);
         if (c->pb == 1)
-            search_kernel<uint8_t><<<(unsigned)items.size(), warps * 32, smem, c->stream>>>((const JobDev*)(c->dArgs + offJobs), (const SearchItem*)(c->dArgs + offItems), g, c->dLut + 2 * 32768);
+            search_kernel<uint8_t><<<(unsigned)items.size(), warps * 32, smem, c->stream>>>((const JobDev*)(c->dArgs + offJobs), (const SearchItem*)(c->dArgs + offItems), g, c->dLut + 2 * 32768, dProg);
         else
-            search_kernel<uint16_t><<<(unsigned)items.size(), warps * 32, smem, c->stream>>>((const JobDev*)(c->dArgs + offJobs), (const SearchItem*)(c->dArgs + offItems), g, c->dLut + 2 * 32768);
+            search_kernel<uint16_t><<<(unsigned)items.size(), warps * 32, smem, c->stream>>>((const JobDev*)(c->dArgs + offJobs), (const SearchItem*)(c->dArgs + offItems), g, c->dLut + 2 * 32768, dProg);
         CU_TRY(c, cudaGetLastError());
     }
     if (!costIdx.empty())

@@ -142,20 +142,77 @@ __device__ __forceinline__ int hadamard4x4_abs(int d[4][4])
     return sum;
 }
 
+/* Row stage of the 4x4 Hadamard straight from packed samples with the integer dot-product
+ * instructions: coefficient k of row y of H*(f - r) = dp(f_y, h_k) + dp(r_y, -h_k), h_k in {+1,-1}^4.
+ * dp4a (8-bit samples) / dp2a (16-bit samples) are exact integer ops, so this is bit-equal to
+ * unpack + subtract + butterflies while using a quarter of the instructions. */
+__device__ __forceinline__ int dp4a_us(uint32_t a_u8x4, uint32_t b_s8x4, int c)
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_s8x4), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_lo_us(uint32_t a_u16x2, uint32_t b_s8x4, int c)
+{
+    int d;
+    asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u16x2), "r"(b_s8x4), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_us(uint32_t a_u16x2, uint32_t b_s8x4, int c)
+{
+    int d;
+    asm("dp2a.hi.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u16x2), "r"(b_s8x4), "r"(c));
+    return d;
+}
+
+/* +-1 patterns (byte i = sample i): h0 = ++++, h1 = +-+-, h2 = ++--, h3 = +--+ and their negations */
+#define HAD_P0 0x01010101u
+#define HAD_P1 0xFF01FF01u
+#define HAD_P2 0xFFFF0101u
+#define HAD_P3 0x01FFFF01u
+#define HAD_N0 0xFFFFFFFFu
+#define HAD_N1 0x01FF01FFu
+#define HAD_N2 0x0101FFFFu
+#define HAD_N3 0xFF0101FFu
+
+__device__ __forceinline__ void had_row(Px<uint8_t>::Row4 f, Px<uint8_t>::Row4 r, int t[4])
+{
+    t[0] = dp4a_us(f.v, HAD_P0, dp4a_us(r.v, HAD_N0, 0));
+    t[1] = dp4a_us(f.v, HAD_P1, dp4a_us(r.v, HAD_N1, 0));
+    t[2] = dp4a_us(f.v, HAD_P2, dp4a_us(r.v, HAD_N2, 0));
+    t[3] = dp4a_us(f.v, HAD_P3, dp4a_us(r.v, HAD_N3, 0));
+}
+
+__device__ __forceinline__ int dp2a4(Px<uint16_t>::Row4 a, uint32_t h, int c)
+{
+    return dp2a_hi_us(a.hi, h, dp2a_lo_us(a.lo, h, c));
+}
+
+__device__ __forceinline__ void had_row(Px<uint16_t>::Row4 f, Px<uint16_t>::Row4 r, int t[4])
+{
+    t[0] = dp2a4(f, HAD_P0, dp2a4(r, HAD_N0, 0));
+    t[1] = dp2a4(f, HAD_P1, dp2a4(r, HAD_N1, 0));
+    t[2] = dp2a4(f, HAD_P2, dp2a4(r, HAD_N2, 0));
+    t[3] = dp2a4(f, HAD_P3, dp2a4(r, HAD_N3, 0));
+}
+
+/* sum |H4 * (F - R) * H4| of this lane's 4x4 block (not halved) */
 template <typename P>
 __device__ __forceinline__ int satd4x4_abs(const typename Px<P>::Row4 f[4], const typename Px<P>::Row4 r[4])
 {
-    int d[4][4];
+    int t[4][4];
 #pragma unroll
     for (int y = 0; y < 4; y++)
-    {
-        int a[4], b[4];
-        Px<P>::unpack(f[y], a);
-        Px<P>::unpack(r[y], b);
+        had_row(f[y], r[y], t[y]);
+    int sum = 0;
 #pragma unroll
-        for (int x = 0; x < 4; x++) d[y][x] = a[x] - b[x];
+    for (int x = 0; x < 4; x++)
+    {
+        int s01 = t[0][x] + t[1][x], d01 = t[0][x] - t[1][x];
+        int s23 = t[2][x] + t[3][x], d23 = t[2][x] - t[3][x];
+        sum += abs(s01 + s23) + abs(d01 + d23) + abs(s01 - s23) + abs(d01 - d23);
     }
-    return hadamard4x4_abs(d);
+    return sum;
 }
 
 __device__ __forceinline__ int quad_sum(int v)
