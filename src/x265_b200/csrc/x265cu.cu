@@ -240,7 +240,7 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     c->bf = cfg->bframes;
     c->searchWarps = cfg->searchWarps > 0 ? cfg->searchWarps : 4;    /* CU rows (= warps) per search CTA */
     if (c->searchWarps > SEARCH_MAX_GROUP_ROWS) c->searchWarps = SEARCH_MAX_GROUP_ROWS;
-    if ((size_t)c->searchWarps * (((size_t)cfg->srcWidth / 2 + 7) / 8) * sizeof(int) > 48 * 1024)
+    if ((size_t)c->searchWarps * (((size_t)cfg->srcWidth / 2 + 7) / 8) * sizeof(unsigned long long) > 48 * 1024)
     {
         delete c;
         snprintf(g_openError, sizeof(g_openError), "x265cu_open: picture too wide for the search kernel's MV ring");
@@ -527,6 +527,7 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     size_t total = sumsBytes;
     bool wantArrays = false;
     int maxItemRows = 1;
+    int handRows = 0;            /* global hand-off rows (one per row group that has a group above it) */
     for (int i = 0; i < n; i++)
     {
         const x265cu_job& j = jobs[i];
@@ -551,6 +552,7 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
                     const int sFirst = useSlices ? c->cfg.numRowsPerSlice * s : 0;
                     const int sLast = (!useSlices || s == ns - 1) ? g.hCU - 1 : c->cfg.numRowsPerSlice * (s + 1) - 1;
                     /* row groups, bottom first: a group only waits for a group with a lower block index */
+                    int prevPub = -1;
                     for (int bottom = sLast; bottom >= sFirst; bottom -= c->searchWarps)
                     {
                         SearchItem it;
@@ -560,8 +562,9 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
                         it.sliceLastY = sLast;
                         it.lastY = bottom;
                         it.firstY = bottom - c->searchWarps + 1 > sFirst ? bottom - c->searchWarps + 1 : sFirst;
-                        it.progBase = (i * 2 + l) * g.hCU;
-                        it.pad = 0;
+                        it.subBase = prevPub;                                   /* hand-off row of the group below */
+                        it.pubBase = it.firstY > sFirst ? handRows++ * g.wCU : -1; /* the top group has nobody above */
+                        prevPub = it.pubBase;
                         if (it.lastY - it.firstY + 1 > maxItemRows) maxItemRows = it.lastY - it.firstY + 1;
                         items.push_back(it);
                     }
@@ -583,7 +586,7 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     size_t offCost = alignUp(offItems + items.size() * sizeof(SearchItem), 256);
     size_t offW = alignUp(offCost + costIdx.size() * sizeof(int), 256);
     size_t offProg = alignUp(offW + weightedJobs.size() * sizeof(WeightDev), 256);   /* device only: wavefront progress */
-    size_t argBytes = alignUp(offProg + (size_t)n * 2 * g.hCU * sizeof(int), 256);
+    size_t argBytes = 8 + alignUp(offProg + (size_t)handRows * g.wCU * sizeof(unsigned long long), 256);
     if (growHost(c, &c->hArgs, &c->hArgsCap, argBytes) || growDevice(c, &c->dArgs, &c->dArgsCap, argBytes)) return X265CU_ECUDA;
     if (growDevice(c, &c->dStage, &c->dStageCap, total) || growHost(c, &c->hStage, &c->hStageCap, total)) return X265CU_ECUDA;
 
@@ -637,7 +640,7 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     c->stats.h2dBytes += (int64_t)offProg;
     CU_TRY(c, cudaMemsetAsync(c->dStage, 0, sumsBytes, c->stream));
     if (!items.empty())
-        CU_TRY(c, cudaMemsetAsync(c->dArgs + offProg, 0, (size_t)n * 2 * g.hCU * sizeof(int), c->stream));
+        CU_TRY(c, cudaMemsetAsync(c->dArgs + offProg, 0, (size_t)handRows * g.wCU * sizeof(unsigned long long) + 8, c->stream));
 
     if (!weightedJobs.empty())
     {
@@ -654,8 +657,8 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
         KernelScope ks(c, X265CU_K_SEARCH);
         /* one CTA per row group, one warp per CU row of the group */
         int warps = maxItemRows;
-        size_t smem = (size_t)warps * g.wCU * sizeof(int);
-        int* dProg = (int*)(c->dArgs + offProg);
+        size_t smem = (size_t)warps * g.wCU * sizeof(unsigned long long);
+        unsigned long long* dProg = (unsigned long long*)(c->dArgs + offProg);
         if (c->pb == 1)
             search_kernel<uint8_t><<<(unsigned)items.size(), warps * 32, smem, c->stream>>>((const JobDev*)(c->dArgs + offJobs), (const SearchItem*)(c->dArgs + offItems), g, c->dLut + 2 * 32768, dProg);
         else
