@@ -197,6 +197,7 @@ class Runner:
                 la.pre_lookahead_ptr(self.frames[t], y, ys, u, v, cs, t, True)
             else:
                 la.estimate_prepared(c[1], c[2])
+        la.sync()          # every output, including the asynchronous plane copy-backs, is on the host
 
     def close(self):
         for f in self.frames.values():

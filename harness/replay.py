@@ -101,6 +101,7 @@ class CuReplay:
             return
         la, tag = self.la, "P%d." % poc
         if self.planes_back:
+            la.sync()      # the padded planes come back behind the compute stream
             self._chk(tag + "planes", la.crc(f, 0), e["planes"])
         if cfg["aqmode"]:
             self._chk(tag + "invQ", la.crc(f, 3), e["invQ"])

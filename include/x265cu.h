@@ -91,7 +91,9 @@ int  x265cu_host_unregister(void* ptr);
  * plane must be valid for (2*width+1) x (2*lines+1) samples as PicYuv::copyFromPicture guarantees
  * (picyuv.cpp:168-178,287-298).  srcStride in samples.  If planesOut != NULL the four padded
  * planes (4 * planeSize samples, layout of Lowres::buffer[0]) are copied back for the host-side
- * consumers (weightPrediction.cpp).  The per-frame resets of Lowres::init
+ * consumers (weightPrediction.cpp); that copy runs behind the compute stream and is
+ * complete once x265cu_sync() has returned (none of the lookahead's own decisions read the planes;
+ * the encoder reads them after slicetypeDecide).  The per-frame resets of Lowres::init
  * (costEst = -1, MV sentinels ...) stay on the host.  lumaIsDevice: `luma` is a device pointer. */
 int x265cu_frame_init(x265cu_ctx* ctx, int slot, const void* luma, intptr_t srcStride, int lumaIsDevice, void* planesOut);
 
@@ -107,6 +109,11 @@ int x265cu_frame_set_invqscale(x265cu_ctx* ctx, int slot, const int32_t* invQsca
  * PicYuv to a multiple of 16.  Float mapping to QP offsets stays on the host. */
 int x265cu_frame_var(x265cu_ctx* ctx, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride,
                      int planesAreDevice, uint32_t* energy, uint64_t sums[6]);
+
+/* ---- x265cu_frame_init + x265cu_frame_var in one call, as PreLookaheadGroup::processTasks runs them
+ * back to back (slicetype.cpp:845-849): the luma is uploaded once and both kernels read it. */
+int x265cu_frame_init_var(x265cu_ctx* ctx, int slot, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride,
+                          int planesAreDevice, void* planesOut, uint32_t* energy, uint64_t sums[6]);
 
 /* ---- LookaheadTLD::lowresIntraEstimate (slicetype.cpp:230-336).  Outputs (any may be NULL):
  * Lowres::intraCost, intraMode, lowresCosts[0][0], rowSatds[0][0]; sums[0] = costEst[0][0],

@@ -65,7 +65,7 @@ class HostParams(C.Structure):
 ABI_SYMBOLS = (
     "x265cu_abi_version", "x265cu_device_count", "x265cu_open", "x265cu_close", "x265cu_last_error",
     "x265cu_get_geometry", "x265cu_sync", "x265cu_host_register", "x265cu_host_unregister",
-    "x265cu_frame_init", "x265cu_frame_set_invqscale", "x265cu_frame_var", "x265cu_intra",
+    "x265cu_frame_init", "x265cu_frame_set_invqscale", "x265cu_frame_var", "x265cu_frame_init_var", "x265cu_intra",
     "x265cu_weight_cost_batch", "x265cu_estimate_batch", "x265cu_pixelcmp_batch", "x265cu_pixelcmp_frames", "x265cu_int_peak",
     "x265cu_stats_enable", "x265cu_stats_get",
 )
@@ -112,6 +112,7 @@ def lib_host():
         L.x265cuh_open.argtypes = [C.POINTER(HostParams), C.c_char_p, C.c_int]
         L.x265cuh_close.argtypes = [C.c_void_p]
         L.x265cuh_set_resident.argtypes = [C.c_void_p, C.c_int]
+        L.x265cuh_sync.argtypes = [C.c_void_p]
         L.x265cuh_frame_slot.argtypes = [C.c_void_p]
         L.x265cuh_ctx.restype = C.c_void_p
         L.x265cuh_ctx.argtypes = [C.c_void_p]
@@ -179,6 +180,11 @@ class Lookahead:
                                          (u.strides[0] // u.itemsize) if u is not None else 0, poc, 1 if planes_back else 0)
         if r:
             raise RuntimeError("preLookahead failed: " + self.error())
+
+    def sync(self):
+        """wait for everything in flight, including the asynchronous plane copy-backs"""
+        if self.L.x265cuh_sync(self.h):
+            raise RuntimeError("sync failed: " + self.error())
 
     def set_resident(self, on):
         """inputs become device pointers, result arrays stay in HBM (only sums return)"""

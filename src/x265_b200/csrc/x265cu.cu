@@ -40,6 +40,10 @@ struct x265cu_ctx
     int bf;
     cudaStream_t stream;
     bool ownStream;
+    cudaStream_t copyStream;               /* device->host copies of the padded planes run behind the compute stream */
+    std::vector<cudaEvent_t> planesCopied; /* per slot: last planes copy-back finished */
+    std::vector<char> planesPending;
+    cudaEvent_t evKernel;
     std::mutex mtx;
     char err[512];
 
@@ -189,6 +193,9 @@ void freeAll(x265cu_ctx* c)
     for (size_t i = 0; i < c->wPool.size(); i++) cudaFree(c->wPool[i]);
     for (size_t i = 0; i < c->freeEvents.size(); i++) cudaEventDestroy(c->freeEvents[i]);
     if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
+    if (c->copyStream) cudaStreamDestroy(c->copyStream);
+    if (c->evKernel) cudaEventDestroy(c->evKernel);
+    for (size_t i = 0; i < c->planesCopied.size(); i++) if (c->planesCopied[i]) cudaEventDestroy(c->planesCopied[i]);
 }
 
 } // namespace
@@ -233,7 +240,7 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     c->dGeneric = NULL; c->dGenericCap = 0;
     c->timing = false;
     memset(&c->stats, 0, sizeof(c->stats));
-    c->stream = NULL; c->ownStream = false;
+    c->stream = NULL; c->ownStream = false; c->copyStream = NULL; c->evKernel = NULL;
     c->pb = cfg->bitDepth > 8 ? 2 : 1;
     c->pixelMax = (1 << cfg->bitDepth) - 1;
     c->correction = 14 - cfg->bitDepth;
@@ -273,6 +280,12 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     OPEN_TRY(cudaSetDevice(cfg->device));
     if (cfg->stream) c->stream = (cudaStream_t)cfg->stream;
     else { OPEN_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->ownStream = true; }
+    OPEN_TRY(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+    OPEN_TRY(cudaEventCreateWithFlags(&c->evKernel, cudaEventDisableTiming));
+    c->planesCopied.assign(cfg->numFrameSlots, (cudaEvent_t)NULL);
+    c->planesPending.assign(cfg->numFrameSlots, 0);
+    for (int i = 0; i < cfg->numFrameSlots; i++)
+        OPEN_TRY(cudaEventCreateWithFlags(&c->planesCopied[i], cudaEventDisableTiming));
 
     const size_t S = (size_t)cfg->numFrameSlots, n = (size_t)g.nCU, t2 = (size_t)(c->bf + 2) * (c->bf + 2), t1 = (size_t)2 * (c->bf + 1);
     size_t planeBytes = S * 4 * (size_t)g.planeSize * c->pb + 256;
@@ -304,6 +317,7 @@ void x265cu_close(x265cu_ctx* c)
     if (!c) return;
     cudaSetDevice(c->cfg.device);
     cudaStreamSynchronize(c->stream);
+    if (c->copyStream) cudaStreamSynchronize(c->copyStream);
     resolveEvents(c);
     freeAll(c);
     delete c;
@@ -322,7 +336,10 @@ int x265cu_sync(x265cu_ctx* c)
 {
     if (!c) return X265CU_EINVAL;
     std::lock_guard<std::mutex> lk(c->mtx);
-    return syncStream(c);
+    int r = syncStream(c);
+    CU_TRY(c, cudaStreamSynchronize(c->copyStream));     /* pending plane copy-backs have landed */
+    for (size_t i = 0; i < c->planesPending.size(); i++) c->planesPending[i] = 0;
+    return r;
 }
 
 int x265cu_host_register(void* ptr, size_t bytes)
@@ -361,7 +378,23 @@ int x265cu_stats_get(x265cu_ctx* c, x265cu_stats* o, int reset)
 }
 
 /* -------------------------------------------------------------------------------------------- */
+static int frameInitImpl(x265cu_ctx* c, int slot, const void* luma, intptr_t srcStride, int lumaIsDevice, void* planesOut,
+                         const void* u, const void* v, intptr_t cStride, uint32_t* varEnergy, uint64_t* varSums);
+
 int x265cu_frame_init(x265cu_ctx* c, int slot, const void* luma, intptr_t srcStride, int lumaIsDevice, void* planesOut)
+{
+    return frameInitImpl(c, slot, luma, srcStride, lumaIsDevice, planesOut, NULL, NULL, 0, NULL, NULL);
+}
+
+int x265cu_frame_init_var(x265cu_ctx* c, int slot, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride,
+                          int planesAreDevice, void* planesOut, uint32_t* energy, uint64_t sums[6])
+{
+    if (!energy || !sums || ((u == NULL) != (v == NULL))) return c ? fail(c, X265CU_EINVAL, "x265cu_frame_init_var: bad argument") : X265CU_EINVAL;
+    return frameInitImpl(c, slot, y, yStride, planesAreDevice, planesOut, u, v, cStride, energy, sums);
+}
+
+static int frameInitImpl(x265cu_ctx* c, int slot, const void* luma, intptr_t srcStride, int lumaIsDevice, void* planesOut,
+                         const void* u, const void* v, intptr_t cStride, uint32_t* varEnergy, uint64_t* varSums)
 {
     if (!c || !luma || badSlot(c, slot) || srcStride < 2 * c->g.width + 1) return c ? fail(c, X265CU_EINVAL, "x265cu_frame_init: bad argument") : X265CU_EINVAL;
     std::lock_guard<std::mutex> lk(c->mtx);
@@ -371,6 +404,7 @@ int x265cu_frame_init(x265cu_ctx* c, int slot, const void* luma, intptr_t srcStr
     int64_t pitch = srcStride;
     if (!lumaIsDevice)
     {
+        /* (2W+1) x (2H+1) samples for the downscale; that also covers the 16-aligned picture pixel_var reads */
         size_t wbytes = (size_t)(2 * g.width + 1) * c->pb;
         CU_TRY(c, cudaMemcpy2DAsync(c->dSrc, (size_t)c->srcPitch * c->pb, luma, (size_t)srcStride * c->pb, wbytes, 2 * g.lines + 1,
                                     cudaMemcpyHostToDevice, c->stream));
@@ -380,6 +414,8 @@ int x265cu_frame_init(x265cu_ctx* c, int slot, const void* luma, intptr_t srcStr
     }
     else if (((uintptr_t)luma & 7) || (((size_t)srcStride * c->pb) & 7))
         return fail(c, X265CU_EINVAL, "x265cu_frame_init: device luma must be 8-byte aligned with an 8-byte multiple pitch");
+    if (c->planesPending[slot])
+        CU_TRY(c, cudaStreamWaitEvent(c->stream, c->planesCopied[slot], 0));   /* do not overwrite planes still being copied out */
     {
         KernelScope ks(c, X265CU_K_LOWRES);
         const int padW = g.width + 2 * g.marginX;
@@ -392,9 +428,49 @@ int x265cu_frame_init(x265cu_ctx* c, int slot, const void* luma, intptr_t srcStr
     CU_TRY(c, cudaGetLastError());
     if (planesOut)
     {
+        /* the planes travel back on the copy stream, behind the compute stream: complete after x265cu_sync() */
         size_t bytes = (size_t)4 * g.planeSize * c->pb;
-        CU_TRY(c, cudaMemcpyAsync(planesOut, slotBuffer(c, slot), bytes, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(c, cudaEventRecord(c->evKernel, c->stream));
+        CU_TRY(c, cudaStreamWaitEvent(c->copyStream, c->evKernel, 0));
+        CU_TRY(c, cudaMemcpyAsync(planesOut, slotBuffer(c, slot), bytes, cudaMemcpyDeviceToHost, c->copyStream));
+        CU_TRY(c, cudaEventRecord(c->planesCopied[slot], c->copyStream));
+        c->planesPending[slot] = 1;
         c->stats.d2hBytes += (int64_t)bytes;
+    }
+    if (varEnergy)
+    {
+        /* acEnergyCu's integer work on the luma that is already on the device + the two chroma planes */
+        const int W = c->cfg.srcWidth, H = c->cfg.srcHeight;
+        const int bxN = (W + 15) / 16, byN = (H + 15) / 16;
+        const size_t cp = alignUp((size_t)bxN * 8, 64);
+        const size_t cBytes = cp * byN * 8 * c->pb;
+        const size_t eBytes = alignUp((size_t)bxN * byN * 4, 256);
+        if (growDevice(c, &c->dGeneric, &c->dGenericCap, 2 * cBytes + eBytes + 256)) return X265CU_ECUDA;
+        uint8_t* dU = c->dGeneric; uint8_t* dV = dU + cBytes; unsigned int* dE = (unsigned int*)(dV + cBytes);
+        int64_t cpitch = (int64_t)cp;
+        if (u && !lumaIsDevice)
+        {
+            CU_TRY(c, cudaMemcpy2DAsync(dU, cp * c->pb, u, (size_t)cStride * c->pb, (size_t)bxN * 8 * c->pb, byN * 8, cudaMemcpyHostToDevice, c->stream));
+            CU_TRY(c, cudaMemcpy2DAsync(dV, cp * c->pb, v, (size_t)cStride * c->pb, (size_t)bxN * 8 * c->pb, byN * 8, cudaMemcpyHostToDevice, c->stream));
+            c->stats.h2dBytes += (int64_t)(2 * (size_t)bxN * 8 * c->pb * byN * 8);
+        }
+        else if (u) { dU = (uint8_t*)u; dV = (uint8_t*)v; cpitch = cStride; }
+        CU_TRY(c, cudaMemsetAsync(c->dSmall, 0, 6 * sizeof(unsigned long long), c->stream));
+        {
+            KernelScope ks(c, X265CU_K_VAR);
+            int blocks = (bxN * byN + 7) / 8;
+            if (c->pb == 1)
+                frame_var_kernel<uint8_t><<<blocks, 256, 0, c->stream>>>((const uint8_t*)src, pitch, u ? (const uint8_t*)dU : NULL, u ? (const uint8_t*)dV : NULL, cpitch, bxN, byN, dE, c->dSmall);
+            else
+                frame_var_kernel<uint16_t><<<blocks, 256, 0, c->stream>>>((const uint16_t*)src, pitch, u ? (const uint16_t*)dU : NULL, u ? (const uint16_t*)dV : NULL, cpitch, bxN, byN, dE, c->dSmall);
+        }
+        CU_TRY(c, cudaGetLastError());
+        CU_TRY(c, cudaMemcpyAsync(varEnergy, dE, (size_t)bxN * byN * 4, cudaMemcpyDeviceToHost, c->stream));
+        unsigned long long hs[6];
+        CU_TRY(c, cudaMemcpyAsync(hs, c->dSmall, sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
+        int r = syncStream(c);
+        for (int i = 0; i < 6; i++) varSums[i] = hs[i];
+        return r;
     }
     /* the caller may reuse its luma buffer as soon as we return */
     return syncStream(c);
@@ -408,9 +484,10 @@ int x265cu_frame_set_invqscale(x265cu_ctx* c, int slot, const int32_t* invQ)
     c->hasInvQ[slot] = invQ != NULL;
     if (invQ)
     {
+        /* stream-ordered before any kernel that reads it; Lowres::invQscaleFactor lives as long as the frame */
         CU_TRY(c, cudaMemcpyAsync(slotInvQ(c, slot), invQ, (size_t)c->g.nCU * sizeof(int), cudaMemcpyHostToDevice, c->stream));
         c->stats.h2dBytes += (int64_t)c->g.nCU * sizeof(int);
-        return syncStream(c);
+        return X265CU_OK;
     }
     return X265CU_OK;
 }

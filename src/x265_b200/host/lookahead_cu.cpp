@@ -188,7 +188,7 @@ void Lookahead::freeLowres(Lowres* l)
 }
 
 /* Lowres::init, common/lowres.cpp:128-165 */
-bool Lookahead::lowresInit(Lowres& l, const void* luma, intptr_t stride, int poc, bool copyPlanesBack)
+void Lookahead::lowresReset(Lowres& l, int poc)
 {
     l.frameNum = poc;
     memset(l.costEst, -1, sizeof(l.costEst));
@@ -206,6 +206,11 @@ bool Lookahead::lowresInit(Lowres& l, const void* luma, intptr_t stride, int poc
     }
     for (int i = 0; i < l.bframes + 2; i++)
         l.intraMbs[i] = 0;
+}
+
+bool Lookahead::lowresInit(Lowres& l, const void* luma, intptr_t stride, int poc, bool copyPlanesBack)
+{
+    lowresReset(l, poc);
     int r = x265cu_frame_init(m_ctx, l.slot, luma, stride, m_resident ? 1 : 0, (copyPlanesBack && !m_resident) ? l.buffer[0] : NULL);
     if (r) { snprintf(m_error, sizeof(m_error), "x265cu_frame_init: %s", x265cu_last_error(m_ctx)); return false; }
     return true;
@@ -213,7 +218,8 @@ bool Lookahead::lowresInit(Lowres& l, const void* luma, intptr_t stride, int poc
 
 /* LookaheadTLD::calcAdaptiveQuantFrame, encoder/slicetype.cpp:95-228 (no quantOffsets).
  * The per-block AC energy and the wp sums come from the GPU; the mapping below is the host float. */
-bool Lookahead::calcAdaptiveQuantFrame(Lowres& l, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride)
+bool Lookahead::calcAdaptiveQuantFrame(Lowres& l, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride,
+                                       const uint32_t* preEnergy, const uint64_t* preSums)
 {
     const Param& param = m_param;
     int maxCol = param.sourceWidth, maxRow = param.sourceHeight;
@@ -222,7 +228,13 @@ bool Lookahead::calcAdaptiveQuantFrame(Lowres& l, const void* y, intptr_t yStrid
     const bool needVar = !(param.aqMode == 0 || param.aqStrength == 0) || param.bEnableWeightedPred;
     std::vector<uint32_t> energy((size_t)blocksX * blocksY);
     uint64_t sums[6] = { 0, 0, 0, 0, 0, 0 };
-    if (needVar)
+    if (needVar && preEnergy)
+    {
+        /* already measured by the fused x265cu_frame_init_var call of preLookahead() */
+        memcpy(&energy[0], preEnergy, energy.size() * sizeof(uint32_t));
+        memcpy(sums, preSums, sizeof(sums));
+    }
+    else if (needVar)
     {
         int r = x265cu_frame_var(m_ctx, y, yStride, u, v, cStride, m_resident ? 1 : 0, &energy[0], sums);
         if (r) { snprintf(m_error, sizeof(m_error), "x265cu_frame_var: %s", x265cu_last_error(m_ctx)); return false; }
@@ -338,13 +350,29 @@ bool Lookahead::lowresIntraEstimate(Lowres& l)
 /* PreLookaheadGroup::processTasks for one frame, encoder/slicetype.cpp:831-856 */
 bool Lookahead::preLookahead(Lowres& l, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride, int poc, bool copyPlanesBack)
 {
-    if (!lowresInit(l, y, yStride, poc, copyPlanesBack)) return false;
-    if (m_bAdaptiveQuant)
+    const bool needVar = m_bAdaptiveQuant && (!(m_param.aqMode == 0 || m_param.aqStrength == 0) || m_param.bEnableWeightedPred);
+    if (needVar)
     {
-        if (!calcAdaptiveQuantFrame(l, y, yStride, u, v, cStride)) return false;
+        /* Lowres::init and acEnergyCu share one upload of the picture */
+        lowresReset(l, poc);
+        const int blocks = ((m_param.sourceWidth + 15) / 16) * ((m_param.sourceHeight + 15) / 16);
+        std::vector<uint32_t> energy((size_t)blocks);
+        uint64_t sums[6];
+        int r = x265cu_frame_init_var(m_ctx, l.slot, y, yStride, u, v, cStride, m_resident ? 1 : 0,
+                                      (copyPlanesBack && !m_resident) ? l.buffer[0] : NULL, &energy[0], sums);
+        if (r) { snprintf(m_error, sizeof(m_error), "x265cu_frame_init_var: %s", x265cu_last_error(m_ctx)); return false; }
+        if (!calcAdaptiveQuantFrame(l, y, yStride, u, v, cStride, &energy[0], sums)) return false;
     }
     else
-        x265cu_frame_set_invqscale(m_ctx, l.slot, NULL);
+    {
+        if (!lowresInit(l, y, yStride, poc, copyPlanesBack)) return false;
+        if (m_bAdaptiveQuant)
+        {
+            if (!calcAdaptiveQuantFrame(l, y, yStride, u, v, cStride, NULL, NULL)) return false;
+        }
+        else
+            x265cu_frame_set_invqscale(m_ctx, l.slot, NULL);
+    }
     return lowresIntraEstimate(l);
 }
 
@@ -556,6 +584,7 @@ void* x265cuh_open(const x265cuh_params* p, char* err, int errLen)
 }
 
 void x265cuh_close(void* la) { delete (Lookahead*)la; }
+int x265cuh_sync(void* la) { return x265cu_sync(((Lookahead*)la)->m_ctx); }
 void x265cuh_set_resident(void* la, int on) { ((Lookahead*)la)->m_resident = on != 0; }
 int x265cuh_frame_slot(void* frame) { return ((Lowres*)frame)->slot; }
 void* x265cuh_ctx(void* la) { return ((Lookahead*)la)->m_ctx; }

@@ -109,7 +109,11 @@ public:
     /* Lowres::init (lowres.cpp:128-165); luma = PicYuv::m_picOrg[0] padded as copyFromPicture does */
     bool lowresInit(Lowres& l, const void* luma, intptr_t stride, int poc, bool copyPlanesBack);
     /* LookaheadTLD::calcAdaptiveQuantFrame; planes padded like PicYuv */
-    bool calcAdaptiveQuantFrame(Lowres& l, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride);
+    bool calcAdaptiveQuantFrame(Lowres& l, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride,
+                                const uint32_t* preEnergy = NULL, const uint64_t* preSums = NULL);
+    void lowresReset(Lowres& l, int poc);   /* the host-side resets of Lowres::init */
+    /* the padded planes of preLookahead(copyPlanesBack) are complete on the host after sync() */
+    bool sync() { return x265cu_sync(m_ctx) == 0; }
     bool lowresIntraEstimate(Lowres& l);
     /* PreLookaheadGroup::processTasks for one frame */
     bool preLookahead(Lowres& l, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride, int poc, bool copyPlanesBack);
@@ -153,6 +157,7 @@ typedef struct x265cuh_params
 } x265cuh_params;
 void* x265cuh_open(const x265cuh_params* p, char* err, int errLen);
 void  x265cuh_close(void* la);
+int   x265cuh_sync(void* la);                                 /* x265cu_sync: pending plane copy-backs have landed */
 void  x265cuh_set_resident(void* la, int on);                /* device-resident inputs/outputs (see Lookahead::m_resident) */
 int   x265cuh_frame_slot(void* frame);
 void* x265cuh_ctx(void* la);                                  /* the underlying x265cu_ctx* */
