@@ -141,7 +141,8 @@ class Runner:
         la = None
         for s in ([slices] + list(range(2, 17)) if slices else [0]):
             la = abi.Lookahead(cfg["width"], cfg["height"], cfg["depth"], cfg["bframes"], cfg["lookahead"], s, cfg["pool"], cfg["weightp"],
-                               cfg["aqmode"], cfg["aqStrength"], cfg["bFrameBias"], device, n + 2, stream=stream)
+                               cfg["aqmode"], cfg["aqStrength"], cfg["bFrameBias"], device, n + 2, stream=stream,
+                               search_warps=env_int("X265CU_SEARCH_ROWS", 0))
             if not slices or (la.numCoopSlices, la.numRowsPerSlice) == (cfg["numCoopSlices"], cfg["numRowsPerSlice"]):
                 break
             la.close()

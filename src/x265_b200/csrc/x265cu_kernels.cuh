@@ -99,192 +99,7 @@ __global__ void __launch_bounds__(256) lowres_init_kernel(const P* __restrict__ 
         }
 }
 
-/* ===========================================================================================
- * intra_estimate: one warp per CU.  The 33 neighbour samples and their [1 2 1] filtered copy
- * live in shared memory; quad q predicts one mode, lane sub-block (bx,by) of it, straight from
- * the neighbour arrays (no predicted block is ever stored), then SATD against fenc.
- * Pass 1: DC, planar, angular 5..30 (8 modes = 8 quads); pass 2: best-2/+2; pass 3: best-1/+1.
- * =========================================================================================== */
-template <typename P>
-__device__ __forceinline__ int intra_pred_px(int mode, int x, int y, const P* s, const P* f, int dcVal, int pixelMax)
-{
-    if (mode == 1)
-    {
-        /* intra_pred_dc_c<8> + dcPredFilter, intrapred.cpp:53-85 */
-        const P* above = s + 1;
-        const P* left = s + 17;
-        if (x == 0 && y == 0) return (above[0] + left[0] + 2 * dcVal + 2) >> 2;
-        if (y == 0) return (above[x] + 3 * dcVal + 2) >> 2;
-        if (x == 0) return (left[y] + 3 * dcVal + 2) >> 2;
-        return dcVal;
-    }
-    if (mode == 0)
-    {
-        /* planar_pred_c<3> on the filtered neighbours, intrapred.cpp:87-100 */
-        const P* above = f + 1;
-        const P* left = f + 17;
-        return ((7 - x) * left[y] + (7 - y) * above[x] + (x + 1) * above[8] + (y + 1) * left[8] + 8) >> 4;
-    }
-    /* intra_pred_ang_c<8>, intrapred.cpp:102-204; filtered neighbours only for modes 2, 18, 34 */
-    const P* n = (mode == 2 || mode == 18 || mode == 34) ? f : s;
-    const int hor = mode < 18;
-    /* S(k): neighbour k after the horizontal-mode swap of top and left */
-#define S_(k) ((int)n[(hor && (k) > 0) ? ((k) <= 16 ? (k) + 16 : (k) - 16) : (k)])
-    const int xx = hor ? y : x, yy = hor ? x : y;
-    const int angleOffset = hor ? 10 - mode : mode - 26;
-    /* angleTable[8 + angleOffset] = sign * {0,2,5,9,13,17,21,26,32}[|angleOffset|] */
-    const int mag = angleOffset < 0 ? -angleOffset : angleOffset;
-    const int absAng = (int)((0x201A15110D090502ull >> (8 * ((mag - 1) & 7))) & 0xff);
-    const int angle = mag == 0 ? 0 : (angleOffset < 0 ? -absAng : absAng);
-    if (angle == 0)
-    {
-        int v = S_(1 + xx);
-        if (xx == 0)
-        {
-            v = S_(1) + ((S_(17 + yy) - S_(0)) >> 1);
-            v = v < 0 ? 0 : (v > pixelMax ? pixelMax : v);
-        }
-        return v;
-    }
-    const int pos = (yy + 1) * angle;
-    const int off = pos >> 5, frac = pos & 31;
-    int invAngle = 0;
-    if (angle < 0)
-    {
-        /* invAngleTable = {4096,1638,910,630,482,390,315,256}[-angleOffset - 1] */
-        switch (mag)
-        {
-        case 1: invAngle = 4096; break; case 2: invAngle = 1638; break; case 3: invAngle = 910; break;
-        case 4: invAngle = 630; break;  case 5: invAngle = 482; break;  case 6: invAngle = 390; break;
-        case 7: invAngle = 315; break;  default: invAngle = 256; break;
-        }
-    }
-    /* ref(k): k >= -1 -> S(k+1) (top-left and top); k < -1 -> projected left neighbour */
-#define REF_(k) (((k) >= -1) ? S_((k) + 1) : S_(16 + ((128 + (-1 - (k)) * invAngle) >> 8)))
-    const int k0 = off + xx;
-    int v;
-    if (frac)
-        v = ((32 - frac) * REF_(k0) + frac * REF_(k0 + 1) + 16) >> 5;
-    else
-        v = REF_(k0);
-#undef REF_
-#undef S_
-    return v;
-}
-
-struct IntraOutDev
-{
-    int32_t* intraCost;
-    uint8_t* intraMode;
-    uint16_t* lowresCosts;    /* [0][0] */
-    int32_t* rowSatds;        /* [0][0], zeroed before launch */
-    unsigned long long* sums; /* costEst, costEstAq; zeroed before launch */
-    const int32_t* invQ;      /* or NULL */
-};
-
-template <typename P>
-__global__ void __launch_bounds__(256) intra_kernel(const P* __restrict__ plane0, GeomDev g, int lambda, int pixelMax, IntraOutDev o)
-{
-    __shared__ P sNb[8][2][36];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cuXY = blockIdx.x * 8 + warp;
-    if (cuXY >= g.nCU) return;
-    const int cuX = cuXY % g.wCU, cuY = cuXY / g.wCU;
-    const int q = lane >> 2, sub = lane & 3, bx = (sub & 1) * 4, by = (sub >> 1) * 4;
-    const P* pix = plane0 + (int64_t)(8 * cuY) * g.stride + 8 * cuX;
-    P* s = sNb[warp][0];
-    P* f = sNb[warp][1];
-    /* neighbours: 17 samples of the row above from the top-left, 16 of the left column (slicetype.cpp:264-267) */
-    {
-        const P* tl = pix - g.stride - 1;
-        if (lane < 17) s[lane] = tl[lane];
-        if (lane < 16) s[17 + lane] = tl[(int64_t)(lane + 1) * g.stride];
-        __syncwarp();
-        /* intraFilter<8>, intrapred.cpp:31-51 */
-        for (int i = lane; i < 33; i += 32)
-        {
-            int v;
-            if (i == 0) v = (2 * s[0] + s[1] + s[17] + 2) >> 2;
-            else if (i == 16 || i == 32) v = s[i];
-            else if (i == 17) v = (2 * s[17] + s[0] + s[18] + 2) >> 2;
-            else v = (2 * s[i] + s[i - 1] + s[i + 1] + 2) >> 2;
-            f[i] = (P)v;
-        }
-        __syncwarp();
-    }
-    int dcVal = 8;
-#pragma unroll
-    for (int i = 0; i < 8; i++) dcVal += s[1 + i] + s[17 + i];
-    dcVal >>= 4;   /* dcVal / 16, dcVal >= 0 */
-
-    /* fenc sub-block */
-    int fe[4][4];
-#pragma unroll
-    for (int y = 0; y < 4; y++)
-    {
-        typename Px<P>::Row4 r = Px<P>::load_aligned(pix + (int64_t)(by + y) * g.stride + bx);
-        Px<P>::unpack(r, fe[y]);
-    }
-
-    int icost = LA_COST_MAX, ilow = 0, acost = LA_COST_MAX, alow = 4;
-#pragma unroll 1
-    for (int pass = 0; pass < 3; pass++)
-    {
-        int mode, valid = 1;
-        if (pass == 0)
-            mode = q == 0 ? 1 : (q == 1 ? 0 : 5 * (q - 1));          /* DC, planar, 5,10,...,30 */
-        else
-        {
-            int dist = pass == 1 ? 2 : 1;
-            mode = q == 0 ? alow - dist : alow + dist;
-            valid = q < 2;
-            if (!valid) mode = 10;
-        }
-        int d[4][4];
-#pragma unroll
-        for (int y = 0; y < 4; y++)
-#pragma unroll
-            for (int x = 0; x < 4; x++)
-                d[y][x] = fe[y][x] - intra_pred_px<P>(mode, bx + x, by + y, s, f, dcVal, pixelMax);
-        int cost = quad_sum(hadamard4x4_abs(d)) >> 1;
-        if (!valid) cost = LA_COST_MAX;
-        int c[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) c[k] = __shfl_sync(FULL_MASK, cost, 4 * k);
-        if (pass == 0)
-        {
-            if (c[0] < icost) { icost = c[0]; ilow = 1; }
-            if (c[1] < icost) { icost = c[1]; ilow = 0; }
-#pragma unroll
-            for (int k = 2; k < 8; k++)
-                if (c[k] < acost) { acost = c[k]; alow = 5 * (k - 1); }
-        }
-        else
-        {
-            int dist = pass == 1 ? 2 : 1;
-            int minusmode = alow - dist, plusmode = alow + dist;
-            if (c[0] < acost) { acost = c[0]; alow = minusmode; }
-            if (c[1] < acost) { acost = c[1]; alow = plusmode; }
-        }
-    }
-    if (acost < icost) { icost = acost; ilow = alow; }
-    icost += 5 * lambda + 4;
-    if (lane == 0)
-    {
-        int capped = icost < LA_LOWRES_COST_MASK ? icost : LA_LOWRES_COST_MASK;
-        o.lowresCosts[cuXY] = (uint16_t)capped;
-        o.intraCost[cuXY] = icost;
-        o.intraMode[cuXY] = (uint8_t)ilow;
-        int scored = (cuX > 0 && cuX < g.wCU - 1 && cuY > 0 && cuY < g.hCU - 1) || g.wCU <= 2 || g.hCU <= 2;
-        int icostAq = (scored && o.invQ) ? ((icost * o.invQ[cuXY] + 128) >> 8) : icost;
-        if (scored)
-        {
-            atomicAdd(&o.sums[0], (unsigned long long)icost);
-            atomicAdd(&o.sums[1], (unsigned long long)icostAq);
-        }
-        atomicAdd(&o.rowSatds[cuY], icostAq);
-    }
-}
+#include "x265cu_intra.cuh"
 
 /* ===========================================================================================
  * search / cost kernels
