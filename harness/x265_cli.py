@@ -1,0 +1,73 @@
+"""Run an x265 CLI binary of oracle/_ref (stock `x265_ref<d>` or GPU-lookahead `x265_cu<d>`) on the
+synthetic clip and return the md5 of the bitstream (test harness)."""
+import hashlib
+import os
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import pyoracle as po  # noqa: E402
+
+REF = os.path.join(ROOT, "oracle", "_ref")
+
+# name -> (depth, width, height, frames, seed, extra CLI options)
+CLI_CASES = {
+    "cli_720p": (8, 1280, 720, 24, 1234, ["--preset", "medium", "--bframes", "4", "--rc-lookahead", "20"]),
+    "cli_360p_b2": (8, 640, 368, 30, 77, ["--preset", "fast", "--bframes", "2", "--rc-lookahead", "12", "--b-adapt", "1"]),
+}
+# results depend on the pool size: pin it to values every machine can provide
+PIN = ["--pools", "4", "--frame-threads", "2"]
+
+
+def write_clip(path, depth, w, h, n, seed):
+    lib = po.oracle(depth)
+    import numpy as np
+    dt = po.pixel_dtype(depth)
+    y = np.zeros((h, w), dt)
+    u = np.zeros((h // 2, w // 2), dt)
+    v = np.zeros((h // 2, w // 2), dt)
+    with open(path, "wb") as f:
+        for t in range(n):
+            lib.ola_synth_frame(w, h, t, n, seed, y.ctypes.data, w, u.ctypes.data, v.ctypes.data, w // 2)
+            f.write(y.tobytes()); f.write(u.tobytes()); f.write(v.tobytes())
+
+
+def binary(kind, depth):
+    return os.path.join(REF, "x265_%s%d" % (kind, depth))
+
+
+def run_case(kind, name, workdir=None, keep=False):
+    depth, w, h, n, seed, opts = CLI_CASES[name]
+    exe = binary(kind, depth)
+    if not os.path.exists(exe):
+        raise FileNotFoundError(exe)
+    d = workdir or tempfile.mkdtemp(prefix="x265cli_")
+    yuv = os.path.join(d, "%s.yuv" % name)
+    if not os.path.exists(yuv):
+        write_clip(yuv, depth, w, h, n, seed)
+    out = os.path.join(d, "%s_%s.hevc" % (name, kind))
+    cmd = [exe, "--input", yuv, "--input-res", "%dx%d" % (w, h), "--fps", "30", "--input-depth", str(depth), "--frames", str(n),
+           "--log-level", "error", "--no-progress"] + opts + PIN + ["-o", out]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1200)
+    if r.returncode != 0:
+        raise RuntimeError("%s failed: %s" % (" ".join(cmd), r.stdout[-800:]))
+    md5 = hashlib.md5(open(out, "rb").read()).hexdigest()
+    size = os.path.getsize(out)
+    if not keep:
+        os.remove(out)
+    return md5, size, d
+
+
+if __name__ == "__main__":
+    import json
+    kind = sys.argv[1] if len(sys.argv) > 1 else "ref"
+    res = {}
+    for nm in CLI_CASES:
+        md5, size, _ = run_case(kind, nm)
+        res[nm] = {"md5": md5, "bytes": size}
+        print(nm, md5, size, flush=True)
+    if kind == "ref" and "--write-golden" in sys.argv:
+        json.dump(res, open(os.path.join(ROOT, "tests", "golden", "cli_md5.json"), "w"), indent=1)

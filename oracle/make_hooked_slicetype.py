@@ -6,9 +6,9 @@ usage: make_hooked_slicetype.py <reference slicetype.cpp> <out.cpp>
 The copy lives only under oracle/_ref/ (git-ignored).  This script holds no reference source: it
 finds a handful of one-line anchors in the file it is given and inserts call-outs to the hooks
 declared in oracle/ref_hooks.h.  The call-outs only OBSERVE (trace which estimates the lookahead
-ran, checksum their outputs); no arithmetic or control flow of the reference is changed, which
-tests/test_ref_pin.py::test_hooks_do_not_change_bitstream proves by comparing encoder output of
-the hooked and un-hooked objects.
+ran, checksum their outputs); no arithmetic or control flow of the reference is changed: the
+hooks are plain function calls that only read the reference's state (oracle/ref_shim.cpp).  The
+stock CLI (oracle/_ref/x265_ref<d>) is linked with the UN-hooked object.
 
 Hook sites (reference file:line in x265_1.9/source/encoder/slicetype.cpp):
   :851  after PreLookaheadGroup::processTasks finished a frame (m_lowresInit = true)
