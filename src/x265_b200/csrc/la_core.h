@@ -211,6 +211,40 @@ LA_HD void la_upd_qpel(LaSearch& s, int c0, uint32_t key)
     s.outcost = s.bcost; s.outx = s.bmx; s.outy = s.bmy;
 }
 
+/* ---- speculative fast path ------------------------------------------------------------------
+ * When nothing moves, the search visits positions that are all known once the MVP is known:
+ *   START   qpel MVP pm, rounded MVP bm0 = (pm + 2) >> 2, zero
+ *   HEX6    bm0 + hex2[1..6]          SQ8   bm0 + square1[1..8]
+ *   HPEL    pm + 2 * square1[1..4]    QPEL  pm, pm + square1[1..4]
+ * (the sub-pel refine is centred on pm both when the qpel MVP beats the full-pel winner and when pm
+ * is full-pel and nothing moved).  The kernel measures all of them at once and feeds the costs to
+ * la_fast_path(), which replays the reference's decisions in order and stops at the first step
+ * whose speculative inputs do not apply (the search moved); it returns the stage at which the
+ * one-pass-at-a-time evaluation has to resume, with `s` exactly as that stage expects it.  A cost
+ * is a function of the position alone, so consuming it early is bit-exact. */
+enum { LA_RESUME_DONE = 0, LA_RESUME_HEX6, LA_RESUME_HEX3, LA_RESUME_SQ8, LA_RESUME_HPEL, LA_RESUME_QPEL };
+
+LA_HD int la_fast_path(LaSearch& s, int c0, int c1, int c2, uint32_t hexKey, uint32_t sqKey, uint32_t hpelKey,
+                       int qc0, uint32_t qpelKey, const uint16_t* lut)
+{
+    la_upd_start(s, c0, c1, c2);
+    if (s.bmx != ((s.pmx + 2) >> 2) || s.bmy != ((s.pmy + 2) >> 2))
+        return LA_RESUME_HEX6;                          /* the zero MV won the start: hexagon is elsewhere */
+    if (hexKey != LA_KEY_NONE && (int)(hexKey >> 3) < s.bcost)
+        return la_upd_hex6(s, hexKey) ? LA_RESUME_HEX3 : LA_RESUME_SQ8;
+    if (!la_upd_sq8(s, sqKey, lut))
+        return LA_RESUME_DONE;                          /* zero residual: result is final */
+    if (s.bmx != s.pmx || s.bmy != s.pmy)
+        return LA_RESUME_HPEL;                          /* the square moved and the qpel MVP lost */
+    if (hpelKey != LA_KEY_NONE && (int)(hpelKey >> 3) < s.bcost)
+    {
+        la_upd_hpel(s, hpelKey);
+        return LA_RESUME_QPEL;
+    }
+    la_upd_qpel(s, qc0, qpelKey);
+    return LA_RESUME_DONE;
+}
+
 /* bidir-only zero-MV skip shortcut (slicetype.cpp:2155-2159), applied once the search is done */
 LA_HD void la_finish_skip(LaSearch& s)
 {

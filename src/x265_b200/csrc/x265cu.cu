@@ -19,6 +19,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <mutex>
 #include <vector>
 
@@ -68,13 +69,23 @@ struct x265cu_ctx
     uint8_t* hArgs; size_t hArgsCap;
     std::vector<void*> wPool;              /* weighted plane sets */
     uint8_t* dGeneric; size_t dGenericCap; /* pixelcmp / var scratch */
+    uint8_t* dMemo; size_t dMemoCap;       /* search memo of a batch: [search][nCU][MEMO_N] int4 */
+    /* hint bookkeeping for the speculation kernel (affects speed only, never a result): relative
+     * picture order of the frame slots inferred from the jobs (poc(fenc) - poc(ref0) = d0, ...) and
+     * which MV mirrors hold a finished search */
+    std::vector<long long> slotPoc;
+    long long pocBase;
+    std::vector<char> slotPocKnown;
+    std::vector<char> mvValid;             /* [slot][list][d - 1] */
 
     bool timing;
     std::vector<PendingEvent> pending;
     std::vector<cudaEvent_t> freeEvents;
     x265cu_stats stats;
 
-    int searchWarps;
+    int searchWarps;       /* CU rows (= warps) per commit CTA */
+    int searchSpec;        /* 0: commit kernel alone (no speculation kernel); experiments only */
+    long long dbgPlans[4];
 };
 
 namespace {
@@ -187,7 +198,7 @@ void freeAll(x265cu_ctx* c)
 {
     cudaFree(c->dPlanes); cudaFree(c->dIntraCost); cudaFree(c->dIntraMode); cudaFree(c->dInvQ);
     cudaFree(c->dLowresCosts); cudaFree(c->dRowSatds); cudaFree(c->dMvs); cudaFree(c->dMvCosts);
-    cudaFree(c->dLut); cudaFree(c->dSrc); cudaFree(c->dSmall); cudaFree(c->dStage); cudaFree(c->dArgs); cudaFree(c->dGeneric);
+    cudaFree(c->dLut); cudaFree(c->dSrc); cudaFree(c->dSmall); cudaFree(c->dStage); cudaFree(c->dArgs); cudaFree(c->dGeneric); cudaFree(c->dMemo);
     if (c->hStage) cudaFreeHost(c->hStage);
     if (c->hArgs) cudaFreeHost(c->hArgs);
     for (size_t i = 0; i < c->wPool.size(); i++) cudaFree(c->wPool[i]);
@@ -237,7 +248,7 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     c->dPlanes = NULL; c->dIntraCost = NULL; c->dIntraMode = NULL; c->dInvQ = NULL; c->dLowresCosts = NULL; c->dRowSatds = NULL;
     c->dMvs = NULL; c->dMvCosts = NULL; c->dLut = NULL; c->dSrc = NULL; c->dSmall = NULL;
     c->dStage = NULL; c->dStageCap = 0; c->hStage = NULL; c->hStageCap = 0; c->dArgs = NULL; c->dArgsCap = 0; c->hArgs = NULL; c->hArgsCap = 0;
-    c->dGeneric = NULL; c->dGenericCap = 0;
+    c->dGeneric = NULL; c->dGenericCap = 0; c->dMemo = NULL; c->dMemoCap = 0;
     c->timing = false;
     memset(&c->stats, 0, sizeof(c->stats));
     c->stream = NULL; c->ownStream = false; c->copyStream = NULL; c->evKernel = NULL;
@@ -245,9 +256,12 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     c->pixelMax = (1 << cfg->bitDepth) - 1;
     c->correction = 14 - cfg->bitDepth;
     c->bf = cfg->bframes;
-    c->searchWarps = cfg->searchWarps > 0 ? cfg->searchWarps : 4;    /* CU rows (= warps) per search CTA */
+    c->searchWarps = cfg->searchWarps > 0 ? cfg->searchWarps : 4;    /* CU rows (= warps) per commit CTA */
     if (c->searchWarps > SEARCH_MAX_GROUP_ROWS) c->searchWarps = SEARCH_MAX_GROUP_ROWS;
-    if ((size_t)c->searchWarps * (((size_t)cfg->srcWidth / 2 + 7) / 8) * sizeof(unsigned long long) > 48 * 1024)
+    c->searchSpec = 1;
+    memset(c->dbgPlans, 0, sizeof(c->dbgPlans));
+    if (const char* e = getenv("X265CU_SEARCH_SPEC")) c->searchSpec = atoi(e);   /* tuning experiments only */
+    if (search_smem_bytes<uint16_t>(c->searchWarps, (cfg->srcWidth / 2 + 7) / 8) > 48 * 1024)
     {
         delete c;
         snprintf(g_openError, sizeof(g_openError), "x265cu_open: picture too wide for the search kernel's MV ring");
@@ -306,6 +320,10 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     OPEN_TRY(cudaMalloc((void**)&c->dSrc, (size_t)c->srcPitch * (2 * g.lines + 1) * c->pb + 256));
     OPEN_TRY(cudaMalloc((void**)&c->dSmall, 64 * sizeof(unsigned long long)));
     c->hasInvQ.assign(S, 0);
+    c->slotPoc.assign(S, 0);
+    c->pocBase = 0;
+    c->slotPocKnown.assign(S, 0);
+    c->mvValid.assign(S * t1, 0);
     OPEN_TRY(cudaStreamSynchronize(c->stream));
     c->cfg.mvcost = NULL;   /* caller's table was copied */
     *out = c;
@@ -318,6 +336,18 @@ void x265cu_close(x265cu_ctx* c)
     cudaSetDevice(c->cfg.device);
     cudaStreamSynchronize(c->stream);
     if (c->copyStream) cudaStreamSynchronize(c->copyStream);
+#ifdef X265CU_SEARCH_STATS
+    {
+        unsigned long long h[32];
+        cudaMemcpyFromSymbol(h, g_searchStats, sizeof(h));
+        fprintf(stderr, "plans %lld hinted(earlier batch) %lld hinted(in-batch seed) %lld\n", c->dbgPlans[0], c->dbgPlans[1], c->dbgPlans[2]);
+        fprintf(stderr, "search stats: cus %llu chain searches %llu (%llu, %llu) resume[done,hex6,hex3,sq8,hpel,qpel] %llu %llu %llu %llu %llu %llu\n"
+                        "  cycles per CU: total %.0f search %.0f (%.0f per search) wait-below %.0f wait-right %.0f; cand passes %llu fast path %llu\n",
+                h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9],
+                (double)h[13] / (h[0] ? h[0] : 1), (double)h[10] / (h[0] ? h[0] : 1), (double)h[10] / (h[1] ? h[1] : 1),
+                (double)h[11] / (h[0] ? h[0] : 1), (double)h[12] / (h[0] ? h[0] : 1), h[14], h[15]);
+    }
+#endif
     resolveEvents(c);
     freeAll(c);
     delete c;
@@ -416,6 +446,9 @@ static int frameInitImpl(x265cu_ctx* c, int slot, const void* luma, intptr_t src
         return fail(c, X265CU_EINVAL, "x265cu_frame_init: device luma must be 8-byte aligned with an 8-byte multiple pitch");
     if (c->planesPending[slot])
         CU_TRY(c, cudaStreamWaitEvent(c->stream, c->planesCopied[slot], 0));   /* do not overwrite planes still being copied out */
+    /* a new picture in this slot: its order and its MV fields are unknown again */
+    c->slotPocKnown[slot] = 0;
+    std::fill(c->mvValid.begin() + (size_t)slot * 2 * (c->bf + 1), c->mvValid.begin() + (size_t)(slot + 1) * 2 * (c->bf + 1), 0);
     {
         KernelScope ks(c, X265CU_K_LOWRES);
         const int padW = g.width + 2 * g.marginX;
@@ -593,9 +626,10 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     const GeomDev& g = c->g;
     const size_t nCU = (size_t)g.nCU, hCU = (size_t)g.hCU;
 
-    /* ---- plan: per-job packed record + work items ---- */
+    /* ---- plan: per-job packed record + one SearchPlan per (job, list) searched ---- */
     std::vector<size_t> recOff(n);
     std::vector<SearchItem> items;
+    std::vector<SearchPlan> plans;
     std::vector<int> costIdx;
     std::vector<int> weightedJobs;
     /* staging layout: [n x 32-byte sums][record 0][record 1]...; when the caller wants no arrays
@@ -603,8 +637,6 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     const size_t sumsBytes = alignUp((size_t)n * 32, 256);
     size_t total = sumsBytes;
     bool wantArrays = false;
-    int maxItemRows = 1;
-    int handRows = 0;            /* global hand-off rows (one per row group that has a group above it) */
     for (int i = 0; i < n; i++)
     {
         const x265cu_job& j = jobs[i];
@@ -617,35 +649,18 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
         if (j.doSearch[0]) rec += 2 * alignUp(nCU * 4, 16);
         if (j.doSearch[1]) rec += 2 * alignUp(nCU * 4, 16);
         total += rec;
-        const bool search = j.doSearch[0] || j.doSearch[1];
-        if (search)
+        const bool useSlices = j.sliced && c->cfg.numCoopSlices > 1;   /* (p1 > b || search) holds for a searching job */
+        for (int l = 0; l < 2; l++)
         {
-            bool useSlices = j.sliced && c->cfg.numCoopSlices > 1;   /* (p1 > b || search) holds here */
-            int ns = useSlices ? c->cfg.numCoopSlices : 1;
-            /* one work item per (list searched, slice): the two lists are independent searches */
-            for (int l = 0; l < 2; l++)
-                for (int s = 0; s < ns && j.doSearch[l]; s++)
-                {
-                    const int sFirst = useSlices ? c->cfg.numRowsPerSlice * s : 0;
-                    const int sLast = (!useSlices || s == ns - 1) ? g.hCU - 1 : c->cfg.numRowsPerSlice * (s + 1) - 1;
-                    /* row groups, bottom first: a group only waits for a group with a lower block index */
-                    int prevPub = -1;
-                    for (int bottom = sLast; bottom >= sFirst; bottom -= c->searchWarps)
-                    {
-                        SearchItem it;
-                        it.job = i;
-                        it.list = l;
-                        it.sliceFirstY = sFirst;
-                        it.sliceLastY = sLast;
-                        it.lastY = bottom;
-                        it.firstY = bottom - c->searchWarps + 1 > sFirst ? bottom - c->searchWarps + 1 : sFirst;
-                        it.subBase = prevPub;                                   /* hand-off row of the group below */
-                        it.pubBase = it.firstY > sFirst ? handRows++ * g.wCU : -1; /* the top group has nobody above */
-                        prevPub = it.pubBase;
-                        if (it.lastY - it.firstY + 1 > maxItemRows) maxItemRows = it.lastY - it.firstY + 1;
-                        items.push_back(it);
-                    }
-                }
+            if (!j.doSearch[l]) continue;
+            /* the two lists of an estimate are independent searches */
+            SearchPlan pl;
+            memset(&pl, 0, sizeof(pl));
+            pl.job = i;
+            pl.list = l;
+            pl.rowsPerSlice = useSlices ? c->cfg.numRowsPerSlice : g.hCU;
+            pl.numSlices = useSlices ? c->cfg.numCoopSlices : 1;
+            plans.push_back(pl);
         }
         costIdx.push_back(i);     /* bidir / intra decision + sums of every estimate: cost_kernel */
         if (j.weighted && j.doSearch[0]) weightedJobs.push_back(i);
@@ -658,9 +673,142 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
         c->wPool.push_back(p);
     }
 
+    /* ---- hints for the speculation kernel (speed only, never a result): a finished MV field of the
+     * temporally nearest frame for the same list and distance.  Searches of a batch that have no such
+     * field yet are run in two WAVES: one seed per (list, distance) first, the others after it with the
+     * seed's field as their hint. ---- */
+    std::vector<int> waveOf(plans.size(), 0);
+    int numWaves = plans.empty() ? 0 : 1;
+    if (!plans.empty())
+    {
+        for (;;)
+        {
+            /* relative picture order of the slots, propagated through the jobs' (fenc, ref0, ref1, d0, d1) relations */
+            for (int pass = 0; pass < n + 1; pass++)
+            {
+                bool changed = false;
+                for (int i = 0; i < n; i++)
+                {
+                    const x265cu_job& j = jobs[i];
+                    const int F = j.fenc, R0 = j.ref0, R1 = j.d1 > 0 ? j.ref1 : -1;
+                    if (!c->slotPocKnown[F])
+                    {
+                        if (c->slotPocKnown[R0]) { c->slotPoc[F] = c->slotPoc[R0] + j.d0; c->slotPocKnown[F] = 1; changed = true; }
+                        else if (R1 >= 0 && c->slotPocKnown[R1]) { c->slotPoc[F] = c->slotPoc[R1] - j.d1; c->slotPocKnown[F] = 1; changed = true; }
+                    }
+                    if (c->slotPocKnown[F])
+                    {
+                        if (!c->slotPocKnown[R0]) { c->slotPoc[R0] = c->slotPoc[F] - j.d0; c->slotPocKnown[R0] = 1; changed = true; }
+                        if (R1 >= 0 && !c->slotPocKnown[R1]) { c->slotPoc[R1] = c->slotPoc[F] + j.d1; c->slotPocKnown[R1] = 1; changed = true; }
+                    }
+                }
+                if (!changed) break;
+            }
+            /* a job none of whose frames is placed yet (a new stream of slots): give it an origin of its own */
+            int orphan = -1;
+            for (int i = 0; i < n && orphan < 0; i++)
+                if (!c->slotPocKnown[jobs[i].fenc]) orphan = i;
+            if (orphan < 0) break;
+            c->pocBase += 1 << 20;
+            c->slotPoc[jobs[orphan].fenc] = c->pocBase;
+            c->slotPocKnown[jobs[orphan].fenc] = 1;
+        }
+        const size_t perSlot = (size_t)2 * (c->bf + 1);
+        const int maxStep = 8;
+        for (size_t k = 0; k < plans.size(); k++)
+        {
+            SearchPlan& pl = plans[k];
+            const x265cu_job& j = jobs[pl.job];
+            const int F = j.fenc, d = pl.list ? j.d1 : j.d0;
+            long long best = maxStep + 1;
+            for (size_t sl = 0; sl < c->slotPocKnown.size(); sl++)
+            {
+                if ((int)sl == F || !c->slotPocKnown[sl] || !c->mvValid[sl * perSlot + (size_t)pl.list * (c->bf + 1) + (d - 1)]) continue;
+                long long dist = c->slotPoc[sl] - c->slotPoc[F];
+                if (dist < 0) dist = -dist;
+                if (dist < best) { best = dist; pl.hint = slotMvs(c, (int)sl, pl.list, d); }
+            }
+        }
+        /* in-batch seeds: per (list, distance) class still without a hint, the plan in the middle of the
+         * class's picture-order range goes first (wave 0, unhinted), the rest follow in wave 1 */
+        for (int l = 0; l < 2; l++)
+            for (int d = 1; d <= c->bf + 1; d++)
+            {
+                std::vector<size_t> cls;
+                for (size_t k = 0; k < plans.size(); k++)
+                {
+                    const x265cu_job& j = jobs[plans[k].job];
+                    if (!plans[k].hint && plans[k].list == l && (l ? j.d1 : j.d0) == d) cls.push_back(k);
+                }
+                if (cls.size() < 2) continue;
+                std::sort(cls.begin(), cls.end(), [&](size_t a, size_t b) { return c->slotPoc[jobs[plans[a].job].fenc] < c->slotPoc[jobs[plans[b].job].fenc]; });
+                const size_t seed = cls[cls.size() / 2];
+                const int* seedField = slotMvs(c, jobs[plans[seed].job].fenc, l, d);
+                for (size_t i = 0; i < cls.size(); i++)
+                    if (cls[i] != seed) { plans[cls[i]].hint = seedField; waveOf[cls[i]] = 1; numWaves = 2; }
+            }
+#ifdef X265CU_SEARCH_STATS
+        for (size_t k = 0; k < plans.size(); k++) { c->dbgPlans[0]++; if (plans[k].hint) c->dbgPlans[waveOf[k] ? 2 : 1]++; }
+#endif
+        /* fields this batch produces become hints for later batches */
+        for (size_t k = 0; k < plans.size(); k++)
+        {
+            const x265cu_job& j = jobs[plans[k].job];
+            c->mvValid[(size_t)j.fenc * perSlot + (size_t)plans[k].list * (c->bf + 1) + ((plans[k].list ? j.d1 : j.d0) - 1)] = 1;
+        }
+        /* wave 0 first */
+        if (numWaves > 1)
+        {
+            std::vector<SearchPlan> sorted;
+            for (int w = 0; w < 2; w++)
+                for (size_t k = 0; k < plans.size(); k++)
+                    if (waveOf[k] == w) sorted.push_back(plans[k]);
+            plans.swap(sorted);
+        }
+    }
+    size_t wavePlans[3] = { 0, 0, plans.size() };
+    for (size_t k = 0; k < waveOf.size(); k++) if (waveOf[k] == 0) wavePlans[1]++;
+    const size_t memoPerSearch = nCU * MEMO_N * sizeof(int4);
+    if (!plans.empty() && growDevice(c, &c->dMemo, &c->dMemoCap, plans.size() * memoPerSearch)) return X265CU_ECUDA;
+
+    /* ---- commit work items: one per row group of every (search, cooperative slice) ---- */
+    int maxItemRows = 1;
+    int handRows = 0;            /* global hand-off rows (one per row group that has a group above it) */
+    size_t waveItems[3] = { 0, 0, 0 };
+    for (size_t k = 0; k < plans.size(); k++)
+    {
+        SearchPlan& pl = plans[k];
+        pl.memo = (int4*)(c->dMemo + k * memoPerSearch);
+        if (k == wavePlans[1]) waveItems[1] = items.size();
+        for (int s = 0; s < pl.numSlices; s++)
+        {
+            const int sFirst = pl.numSlices > 1 ? pl.rowsPerSlice * s : 0;
+            const int sLast = s == pl.numSlices - 1 ? g.hCU - 1 : pl.rowsPerSlice * (s + 1) - 1;
+            /* row groups, bottom first: a group only waits for a group with a lower block index */
+            int prevPub = -1;
+            for (int bottom = sLast; bottom >= sFirst; bottom -= c->searchWarps)
+            {
+                SearchItem it;
+                it.search = (int)k;
+                it.sliceFirstY = sFirst;
+                it.sliceLastY = sLast;
+                it.lastY = bottom;
+                it.firstY = bottom - c->searchWarps + 1 > sFirst ? bottom - c->searchWarps + 1 : sFirst;
+                it.subBase = prevPub;                                   /* hand-off row of the group below */
+                it.pubBase = it.firstY > sFirst ? handRows++ * g.wCU : -1; /* the top group has nobody above */
+                prevPub = it.pubBase;
+                if (it.lastY - it.firstY + 1 > maxItemRows) maxItemRows = it.lastY - it.firstY + 1;
+                items.push_back(it);
+            }
+        }
+    }
+    if (wavePlans[1] == plans.size()) waveItems[1] = items.size();
+    waveItems[2] = items.size();
+
     size_t offJobs = 0;
     size_t offItems = alignUp(offJobs + (size_t)n * sizeof(JobDev), 256);
-    size_t offCost = alignUp(offItems + items.size() * sizeof(SearchItem), 256);
+    size_t offPlans = alignUp(offItems + items.size() * sizeof(SearchItem), 256);
+    size_t offCost = alignUp(offPlans + plans.size() * sizeof(SearchPlan), 256);
     size_t offW = alignUp(offCost + costIdx.size() * sizeof(int), 256);
     size_t offProg = alignUp(offW + weightedJobs.size() * sizeof(WeightDev), 256);   /* device only: wavefront progress */
     size_t argBytes = 8 + alignUp(offProg + (size_t)handRows * g.wCU * sizeof(unsigned long long), 256);
@@ -703,6 +851,7 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
         d.bidir = j.d1 > 0;
     }
     if (!items.empty()) memcpy(c->hArgs + offItems, &items[0], items.size() * sizeof(SearchItem));
+    if (!plans.empty()) memcpy(c->hArgs + offPlans, &plans[0], plans.size() * sizeof(SearchPlan));
     if (!costIdx.empty()) memcpy(c->hArgs + offCost, &costIdx[0], costIdx.size() * sizeof(int));
     WeightDev* hw = (WeightDev*)(c->hArgs + offW);
     for (size_t k = 0; k < weightedJobs.size(); k++)
@@ -732,14 +881,31 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     if (!items.empty())
     {
         KernelScope ks(c, X265CU_K_SEARCH);
-        /* one CTA per row group, one warp per CU row of the group */
+        const JobDev* dJobs = (const JobDev*)(c->dArgs + offJobs);
+        const SearchPlan* dPlans = (const SearchPlan*)(c->dArgs + offPlans);
+        const SearchItem* dItems = (const SearchItem*)(c->dArgs + offItems);
+        const uint16_t* dLutC = c->dLut + 2 * 32768;
+        /* per wave -- speculation: every CU of every search in parallel (memo); then the commit wavefront:
+         * one CTA per row group, one warp per CU row of the group */
         int warps = maxItemRows;
-        size_t smem = (size_t)warps * g.wCU * sizeof(unsigned long long);
         unsigned long long* dProg = (unsigned long long*)(c->dArgs + offProg);
-        if (c->pb == 1)
-            search_kernel<uint8_t><<<(unsigned)items.size(), warps * 32, smem, c->stream>>>((const JobDev*)(c->dArgs + offJobs), (const SearchItem*)(c->dArgs + offItems), g, c->dLut + 2 * 32768, dProg);
-        else
-            search_kernel<uint16_t><<<(unsigned)items.size(), warps * 32, smem, c->stream>>>((const JobDev*)(c->dArgs + offJobs), (const SearchItem*)(c->dArgs + offItems), g, c->dLut + 2 * 32768, dProg);
+        for (int w = 0; w < numWaves; w++)
+        {
+            const unsigned np = (unsigned)(wavePlans[w + 1] - wavePlans[w]), ni = (unsigned)(waveItems[w + 1] - waveItems[w]);
+            if (!np) continue;
+            dim3 sgrid((unsigned)((g.nCU + SPEC_WARPS - 1) / SPEC_WARPS), np);
+            if (!c->searchSpec) CU_TRY(c, cudaMemsetAsync(c->dMemo + wavePlans[w] * memoPerSearch, 0xff, np * memoPerSearch, c->stream));
+            if (c->pb == 1)
+            {
+                if (c->searchSpec) spec_kernel<uint8_t><<<sgrid, SPEC_WARPS * 32, 0, c->stream>>>(dJobs, dPlans + wavePlans[w], g, dLutC);
+                search_kernel<uint8_t><<<ni, warps * 32, search_smem_bytes<uint8_t>(warps, g.wCU), c->stream>>>(dJobs, dPlans, dItems + waveItems[w], g, dLutC, dProg, warps);
+            }
+            else
+            {
+                if (c->searchSpec) spec_kernel<uint16_t><<<sgrid, SPEC_WARPS * 32, 0, c->stream>>>(dJobs, dPlans + wavePlans[w], g, dLutC);
+                search_kernel<uint16_t><<<ni, warps * 32, search_smem_bytes<uint16_t>(warps, g.wCU), c->stream>>>(dJobs, dPlans, dItems + waveItems[w], g, dLutC, dProg, warps);
+            }
+        }
         CU_TRY(c, cudaGetLastError());
     }
     if (!costIdx.empty())
@@ -757,6 +923,16 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     c->stats.d2hBytes += (int64_t)back;
     int r = syncStream(c);
     if (r) return r;
+#ifdef X265CU_SEARCH_STATS
+    if (!plans.empty() && getenv("X265CU_STATS_PER_BATCH"))
+    {
+        unsigned long long h[32], z[32] = { 0 };
+        cudaMemcpyFromSymbol(h, g_searchStats, sizeof(h));
+        cudaMemcpyToSymbol(g_searchStats, z, sizeof(z));
+        fprintf(stderr, "batch: jobs %d searches %zu waves %d | cus %llu fast %llu cand-pass %llu chain-search %llu | cyc/CU total %.0f wait-below %.0f search %.0f\n",
+                n, plans.size(), numWaves, h[0], h[15], h[14], h[1], (double)h[13] / (h[0] ? h[0] : 1), (double)h[11] / (h[0] ? h[0] : 1), (double)h[10] / (h[0] ? h[0] : 1));
+    }
+#endif
 
     /* scatter to the caller's Lowres arrays */
     for (int i = 0; i < n; i++)

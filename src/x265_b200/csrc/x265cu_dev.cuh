@@ -38,6 +38,8 @@ template <> struct Px<uint8_t>
     {
         Row4 r; r.v = __ldg((const uint32_t*)p); return r;
     }
+    /* 4 samples starting k (0..3) samples into the 8 samples u0:u1 */
+    static __device__ __forceinline__ Row4 combine(Row4 u0, Row4 u1, int k) { Row4 r; r.v = __funnelshift_r(u0.v, u1.v, k * 8); return r; }
     static __device__ __forceinline__ Row4 avg(Row4 a, Row4 b) { Row4 r; r.v = __vavgu4(a.v, b.v); return r; }
     static __device__ __forceinline__ int sad(Row4 a, Row4 b) { return (int)__vsadu4(a.v, b.v); }
     static __device__ __forceinline__ void unpack(Row4 a, int v[4])
@@ -68,6 +70,12 @@ template <> struct Px<uint16_t>
     {
         uint2 w = __ldg((const uint2*)p);
         Row4 r; r.lo = w.x; r.hi = w.y; return r;
+    }
+    static __device__ __forceinline__ Row4 combine(Row4 u0, Row4 u1, int k)
+    {
+        const uint32_t sh = (uint32_t)(k & 1) * 16;
+        const uint32_t m0 = (k & 2) ? u0.hi : u0.lo, m1 = (k & 2) ? u1.lo : u0.hi, m2 = (k & 2) ? u1.hi : u1.lo;
+        Row4 r; r.lo = __funnelshift_r(m0, m1, sh); r.hi = __funnelshift_r(m1, m2, sh); return r;
     }
     static __device__ __forceinline__ Row4 avg(Row4 a, Row4 b)
     {

@@ -1,43 +1,83 @@
-/* x265cu_search.cuh -- the wavefront motion-search kernel (sm_100a).
+/* x265cu_search.cuh -- the motion-search kernels of a frame-cost estimate (sm_100a).
  *
- * Replaces, for ONE reference list of one frame-cost estimate, the search half of
+ * Replace, for ONE reference list of one estimate, the search half of
  * CostEstimateGroup::estimateCUCost (encoder/slicetype.cpp:2106-2160) and the lowres branch of
  * MotionEstimate::motionEstimate (encoder/motion.cpp:571-1172).  The L0 and L1 searches of an
  * estimate are independent of each other (they only meet in the bidir/intra decision, which
- * cost_kernel does afterwards for the whole frame in parallel), so the unit of work is
- * (job, list, cooperative slice), further cut into ROW GROUPS of a few CU rows: one small CTA per
- * group, one warp per CU row, so that the rows of one slice spread over many SMs and every warp
- * gets (close to) a scheduler of its own -- the search is a long dependent chain per CU, so
- * per-warp issue rate, not occupancy, is what sets the latency of an estimate.
+ * cost_kernel does afterwards for the whole frame in parallel), so the unit of work is a SEARCH =
+ * (job, list).
  *
- * Rows form a wavefront because a CU's MVP candidates are its right, below, below-left and
- * below-right neighbours (slicetype.cpp:2117-2128).  A finished CU publishes ONE 64-bit word
- * {tag = 1, packed MV}; the row above polls exactly the words it needs.  Because tag and data
- * travel in the same naturally aligned 8-byte store there is no separate progress counter and no
- * memory fence anywhere on the chain.  Inside a group the words live in shared memory, between
- * groups in a global hand-off row (L2).  A group only ever waits for a group with a LOWER block
- * index (launched earlier), so the scheme cannot deadlock even when a launch does not fit the GPU.
+ * The reference's dependency: a CU's MVP candidates are the MVs of its right, below, below-left and
+ * below-right neighbours (slicetype.cpp:2117-2128), which makes a frame (or cooperative slice) a
+ * wavefront and every CU row a serial chain of ~10 dependent measuring passes per CU.  Here the
+ * chain only carries DECISIONS; the measuring is taken off it, bit-exactly, in three steps:
  *
- * Inside a CU the search is a chain of dependent passes (la_core.h).  Each pass measures up to 8
- * candidate blocks at once: quad q = lane >> 2 owns candidate q, each lane its 4x4 sub-block; the
- * winner is one warp min-reduction over packed (cost << 3 | q) keys.  Passes are branch-free:
- * every quad always measures a (valid-address) block and invalid candidates are masked out of the
- * key reduction; the per-lane candidate offsets of every pass are computed once per kernel.
+ * 1. ONE-SHOT SEARCH (search_mv).  Everything the search does once the MVP is chosen is a function
+ *    of the MVP alone, and in the common case (the search confirms its predictor) it only visits
+ *    positions that are known up front.  All 26 of them are measured in one straight-line burst
+ *    from a window staged in shared memory, and la_fast_path() (la_core.h) replays the reference's
+ *    decisions on the costs; only when the search really moves does it fall back to
+ *    one-pass-at-a-time evaluation, from the stage where the speculation stopped applying.
+ *
+ * 2. SPECULATION KERNEL (spec_kernel): every CU of every search in parallel, no dependencies.  A
+ *    HINT field (the MVs an earlier, temporally adjacent search produced; zero when there is none)
+ *    predicts the neighbours' MVs; for each distinct predicted vector the CU's full search is run
+ *    and memoised per CU as {MVP, SATD at the MVP, resulting MV, resulting cost}.  Hints only ever
+ *    select WHICH vectors get measured early, never a result.
+ *
+ * 3. COMMIT KERNEL (search_kernel): the wavefront.  One warp per CU row; per CU it takes the real
+ *    neighbour MVs, looks their SATDs up in the memo (same MV => same pixels => same cost), picks
+ *    the MVP exactly as the reference does (strict <, reference order, skipCost rule) and takes the
+ *    memoised search result.  Pixels are only touched on the chain when a vector was not
+ *    predicted (then: the reference's CAND pass and/or a one-shot search, inline).
+ *
+ * A finished CU publishes ONE 64-bit word {tag = 1, packed MV}; tag and data travel in the same
+ * naturally aligned 8-byte store, so there is no separate progress counter and no fence on the
+ * chain.  Inside a row group the words live in shared memory, between groups in a global hand-off
+ * row (L2).  A group only ever waits for a group with a LOWER block index (launched earlier), so
+ * the scheme cannot deadlock even when a launch does not fit the GPU.
+ *
+ * Lane mapping of every measure: quad q = lane >> 2 owns one candidate block, each lane its 4x4
+ * sub-block; winners are warp min-reductions over packed (cost << 3 | k) keys (la_core.h).
  */
 #ifndef X265CU_SEARCH_CUH
 #define X265CU_SEARCH_CUH
 
-struct SearchItem
+/* one (job, list) search of a batch */
+struct SearchPlan
 {
     int job, list;
+    int rowsPerSlice, numSlices;   /* cooperative slices (numSlices == 1: whole frame) */
+    const int* hint;               /* packed MV field predicting this search's result, or NULL (zero field) */
+    int hintNeg;                   /* the hint is the opposite list's field: negate it */
+    int4* memo;                    /* [nCU][MEMO_N] {mvp, SATD at mvp or -1, result MV, result cost or -1 (empty)} */
+};
+
+/* one row group of a search: a CTA of the commit kernel */
+struct SearchItem
+{
+    int search;                    /* index into SearchPlan[] */
     int sliceFirstY, sliceLastY;   /* cooperative slice (or whole frame) this group belongs to */
     int firstY, lastY;             /* CU rows of this group (lastY = bottom row, processed first) */
     int pubBase;                   /* hand-off row this group's TOP row publishes to (index of entry 0), -1: none */
     int subBase;                   /* hand-off row the group's BOTTOM row reads (the group below), -1: none */
 };
 
-#define SEARCH_MAX_GROUP_ROWS 8
+#define MEMO_N 4
+#define SEARCH_MAX_GROUP_ROWS 16
+#define SEARCH_MAX_THREADS 256
+#define SPEC_WARPS 8
 #define HAND_TAG (1ull << 32)
+
+/* optional instrumentation for kernel tuning (compile with -DX265CU_SEARCH_STATS; never in the shipped library) */
+#ifdef X265CU_SEARCH_STATS
+__device__ unsigned long long g_searchStats[32];
+#define SSTAT_ADD(i, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_searchStats[i], (unsigned long long)(v)); } while (0)
+#define SSTAT_CLOCK() clock64()
+#else
+#define SSTAT_ADD(i, v) do { } while (0)
+#define SSTAT_CLOCK() 0ll
+#endif
 
 /* two-source fetch at quarter-pel MV (qx, qy); when the MV is not odd both sources coincide and the
  * rounded average returns the sample itself, so the code is the same for every candidate
@@ -79,45 +119,337 @@ __device__ __forceinline__ int hand_wait(volatile const unsigned long long* e)
     return (int)(uint32_t)v;
 }
 
-template <typename P>
-__global__ void __launch_bounds__(SEARCH_MAX_GROUP_ROWS * 32, 3)
-search_kernel(const JobDev* __restrict__ jobs, const SearchItem* __restrict__ items, GeomDev g,
-              const uint16_t* __restrict__ lut, unsigned long long* gHand)
+/* per-lane candidate geometry of the fixed-shape rounds/passes (motion.cpp:64-66 tables), computed once */
+struct LaneGeom
 {
-    extern __shared__ unsigned long long sHand[];  /* [rows of the group][W] hand-off words */
+    int q;
+    /* one-shot rounds */
+    int r1dx, r1dy;          /* round 1: quads 3..6 = half-pel square around pm (quarter-pel units) */
+    int r2off, r2dx, r2dy;   /* round 2: quads 0..5 = hexagon, 6..7 = square1[1..2] */
+    int r3off, r3dx, r3dy;   /* round 3: quads 0..5 = square1[3..8] */
+    int r4dx, r4dy;          /* round 4: quads 0..4 = pm + square1[0..4] (quarter-pel units) */
+    /* one-pass-at-a-time fallback */
+    int hex6off, hex6dx, hex6dy, sq8off, sq8dx, sq8dy, hpdx, hpdy, qpdx, qpdy;
+};
+
+__device__ __forceinline__ LaneGeom lane_geom(int lane, int stride)
+{
+    LaneGeom L;
+    const int q = lane >> 2;
+    L.q = q;
+    L.r1dx = (q >= 3 && q < 7) ? la_sq1x(q - 2) * 2 : 0;
+    L.r1dy = (q >= 3 && q < 7) ? la_sq1y(q - 2) * 2 : 0;
+    L.r2dx = q < 6 ? la_hex2x(q + 1) : la_sq1x(q - 5);
+    L.r2dy = q < 6 ? la_hex2y(q + 1) : la_sq1y(q - 5);
+    L.r2off = L.r2dy * stride + L.r2dx;
+    L.r3dx = q < 6 ? la_sq1x(q + 3) : 0;
+    L.r3dy = q < 6 ? la_sq1y(q + 3) : 0;
+    L.r3off = L.r3dy * stride + L.r3dx;
+    L.r4dx = q < 5 ? la_sq1x(q) : 0;
+    L.r4dy = q < 5 ? la_sq1y(q) : 0;
+    L.hex6dx = la_hex2x((q + 1) & 7); L.hex6dy = la_hex2y((q + 1) & 7);
+    L.hex6off = L.hex6dy * stride + L.hex6dx;
+    L.sq8dx = la_sq1x(q + 1); L.sq8dy = la_sq1y(q + 1);
+    L.sq8off = L.sq8dy * stride + L.sq8dx;
+    L.hpdx = la_sq1x((q + 1) & 7) * 2; L.hpdy = la_sq1y((q + 1) & 7) * 2;
+    L.qpdx = la_sq1x(q); L.qpdy = la_sq1y(q);
+    return L;
+}
+
+/* The window a one-shot search reads: WIN_H rows x WIN_W samples of each of the four hpel planes
+ * around the clipped MVP pm, staged in shared memory (one private buffer per warp) with coalesced
+ * row loads.  Origin (full-pel, relative to the CU): wx0 = ((pm.x >> 2) - 2) & ~3, wy0 = (pm.y >> 2) - 2.
+ * Covers the hexagon (+-2) and the square (+-1) around round(pm) and every half-/quarter-pel point
+ * within +-2 quarter samples of pm, i.e. all 26 positions of the no-move path. */
+#define WIN_W 16
+#define WIN_H 13
+#define WIN_ROW_UNITS (WIN_W / 4)
+#define WIN_PLANE_UNITS (WIN_H * WIN_ROW_UNITS)
+#define WIN_UNITS (4 * WIN_PLANE_UNITS)
+#define WIN_PITCH (WIN_UNITS + 8)           /* + slack: an aligned read's second unit may lie one past the end */
+
+/* 4 samples at window position (dx, dy) of plane `plane` */
+template <typename P>
+__device__ __forceinline__ typename Px<P>::Row4 win_read(const typename Px<P>::Row4* win, int plane, int dx, int dy)
+{
+    const typename Px<P>::Row4* u = win + plane * WIN_PLANE_UNITS + dy * WIN_ROW_UNITS + (dx >> 2);
+    return Px<P>::combine(u[0], u[1], dx & 3);
+}
+
+/* this lane's 4x4 of the reference block at quarter-pel MV (qx, qy), from the window (lx, ly = the
+ * lane's sub-block offset minus the window origin) */
+template <typename P>
+__device__ __forceinline__ void win_qpel(const typename Px<P>::Row4* win, int lx, int ly, int qx, int qy, typename Px<P>::Row4 out[4])
+{
+    const int hpelA = (qy & 2) | ((qx & 2) >> 1);
+    const int qx2 = qx + (qx & 1), qy2 = qy + (qy & 1);
+    const int hpelB = (qy2 & 2) | ((qx2 & 2) >> 1);
+    const int ax = lx + (qx >> 2), ay = ly + (qy >> 2), bx = lx + (qx2 >> 2), by = ly + (qy2 >> 2);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        out[i] = Px<P>::avg(win_read<P>(win, hpelA, ax, ay + i), win_read<P>(win, hpelB, bx, by + i));
+}
+
+template <typename P>
+__device__ __forceinline__ void win_fpel(const typename Px<P>::Row4* win, int lx, int ly, int fx, int fy, typename Px<P>::Row4 out[4])
+{
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        out[i] = win_read<P>(win, 0, lx + fx, ly + fy + i);
+}
+
+/* The whole search of one CU for a given MVP `m` (packed quarter-pel), result before the skip
+ * shortcut: motion.cpp:587-624,670-742,1081-1119.  Also returns the SATD at pm without mvcost
+ * (centerSatd): when pm == m (candOk) that is exactly the candidate cost of the neighbour MV m in
+ * the MVP selection (slicetype.cpp:2130-2150), so the CAND pass costs nothing extra. */
+template <typename P>
+__device__ __forceinline__ void search_mv(const P* __restrict__ refCU, const P* __restrict__ refLane, typename Px<P>::Row4* win,
+                                          int planeSize, int stride, const typename Px<P>::Row4 fe[4],
+                                          const uint16_t* __restrict__ lut, const LaneGeom& L, int lane, int bx, int by,
+                                          int cuX, int cuY, int W, int H, int m,
+                                          int& outMv, int& outCost, int& centerSatd, bool& candOk)
+{
+    typedef typename Px<P>::Row4 Row4;
+    const int q = L.q;
+    LaSearch s;
+    la_search_begin(s, cuX, cuY, W, H, 0, 0, 0, 0, 0, 0);
+    s.mvpx = la_mv_x(m); s.mvpy = la_mv_y(m);
+    la_enter_start(s);
+    candOk = s.pmx == s.mvpx && s.pmy == s.mvpy;
+    const uint16_t* __restrict__ lutx = lut - s.mvpx;
+    const uint16_t* __restrict__ luty = lut - s.mvpy;
+    const int bm0x = (s.pmx + 2) >> 2, bm0y = (s.pmy + 2) >> 2;
+    const int wx0 = ((s.pmx >> 2) - 2) & ~3, wy0 = (s.pmy >> 2) - 2;
+
+    /* ---- stage the window: unit i = (plane, row, 4-sample column), consecutive lanes walk a row ---- */
+    __syncwarp();
+    {
+        const P* __restrict__ wbase = refCU + wy0 * stride + wx0;
+#pragma unroll
+        for (int k = 0; k < (WIN_UNITS + 31) / 32; k++)
+        {
+            const int i = lane + 32 * k;
+            if (i < WIN_UNITS)
+            {
+                const int plane = i / WIN_PLANE_UNITS, rem = i - plane * WIN_PLANE_UNITS;
+                win[i] = Px<P>::load_aligned(wbase + plane * planeSize + (rem / WIN_ROW_UNITS) * stride + (rem % WIN_ROW_UNITS) * 4);
+            }
+        }
+    }
+    __syncwarp();
+    const int lx = bx - wx0, ly = by - wy0;
+
+    /* ---- round 1: q0 qpel MVP (no mvcost), q1 rounded MVP, q3..6 the 4 half-pel points around pm ---- */
+    int cost1;
+    {
+        const int qx = (q == 1 ? bm0x * 4 : s.pmx) + L.r1dx;
+        const int qy = (q == 1 ? bm0y * 4 : s.pmy) + L.r1dy;
+        Row4 r[4];
+        win_qpel<P>(win, lx, ly, qx, qy, r);
+        const int mvc = q == 0 ? 0 : lutx[qx] + luty[qy];
+        cost1 = quad_sum(sad4x4<P>(fe, r)) + mvc;
+    }
+    /* ---- rounds 2, 3: hexagon (6) and unit square (8) around the rounded MVP, full-pel SAD;
+     *      the two spare quads of round 3 measure the zero MV straight from global memory ---- */
+    int cost2, cost3;
+    {
+        Row4 r2[4], r3[4];
+        win_fpel<P>(win, lx, ly, bm0x + L.r2dx, bm0y + L.r2dy, r2);
+        if (q < 6) win_fpel<P>(win, lx, ly, bm0x + L.r3dx, bm0y + L.r3dy, r3);
+        else fetch_off<P>(refLane, stride, 0, r3);
+        const int f3x = q < 6 ? bm0x + L.r3dx : 0, f3y = q < 6 ? bm0y + L.r3dy : 0;
+        cost2 = quad_sum(sad4x4<P>(fe, r2)) + lutx[(bm0x + L.r2dx) * 4] + luty[(bm0y + L.r2dy) * 4];
+        cost3 = quad_sum(sad4x4<P>(fe, r3)) + lutx[f3x * 4] + luty[f3y * 4];
+    }
+    /* ---- round 4: SATD at pm and the 4 quarter-pel points around it ---- */
+    int cost4, raw4;
+    {
+        const int qx = s.pmx + L.r4dx, qy = s.pmy + L.r4dy;
+        Row4 r[4];
+        win_qpel<P>(win, lx, ly, qx, qy, r);
+        raw4 = quad_sum(satd4x4_abs<P>(fe, r)) >> 1;
+        cost4 = raw4 + lutx[qx] + luty[qy];
+    }
+    int resume;
+    {
+        const int c0 = __shfl_sync(FULL_MASK, cost1, 0), c1 = __shfl_sync(FULL_MASK, cost1, 4), c2 = __shfl_sync(FULL_MASK, cost3, 24);
+        const uint32_t hpelKey = warp_min_key(q >= 3 && q < 7, cost1, q - 3);
+        const uint32_t hexKey = warp_min_key(q < 6, cost2, q);
+        const uint32_t sqKey = __reduce_min_sync(FULL_MASK, q < 6 ? la_key(cost3, q + 2) : la_key(cost2, q - 6));
+        const int qc0 = __shfl_sync(FULL_MASK, cost4, 0);
+        centerSatd = __shfl_sync(FULL_MASK, raw4, 0);
+        const uint32_t qpelKey = warp_min_key(q >= 1 && q < 5, cost4, q);
+        resume = la_fast_path(s, c0, c1, c2, hexKey, sqKey, hpelKey, qc0, qpelKey, lut);
+        SSTAT_ADD(4 + resume, 1);
+    }
+
+    /* ---- the search moved: continue one pass at a time from the stage the speculation stopped at ---- */
+    if (resume != LA_RESUME_DONE)
+    {
+        bool more = resume == LA_RESUME_HEX3;
+        if (resume == LA_RESUME_HEX6)
+        {
+            const int fx = s.bmx + L.hex6dx, fy = s.bmy + L.hex6dy;
+            Row4 r[4];
+            fetch_off<P>(refLane, stride, s.bmy * stride + s.bmx + L.hex6off, r);
+            const int cost = quad_sum(sad4x4<P>(fe, r)) + lutx[fx * 4] + luty[fy * 4];
+            more = la_upd_hex6(s, warp_min_key(q < 6, cost, q));
+        }
+        while (more)
+        {
+            const int hdx = la_hex2x((s.dir + q) & 7), hdy = la_hex2y((s.dir + q) & 7);
+            const int hx = s.bmx + hdx, hy = s.bmy + hdy;
+            Row4 r3[4];
+            fetch_off<P>(refLane, stride, hy * stride + hx, r3);
+            const int c3 = quad_sum(sad4x4<P>(fe, r3)) + lutx[hx * 4] + luty[hy * 4];
+            more = la_upd_hex3(s, warp_min_key(q < 3, c3, q));
+        }
+        bool subpel = true;
+        if (resume <= LA_RESUME_SQ8)
+        {
+            const int fx = s.bmx + L.sq8dx, fy = s.bmy + L.sq8dy;
+            Row4 r[4];
+            fetch_off<P>(refLane, stride, s.bmy * stride + s.bmx + L.sq8off, r);
+            const int cost = quad_sum(sad4x4<P>(fe, r)) + lutx[fx * 4] + luty[fy * 4];
+            subpel = la_upd_sq8(s, warp_min_key(true, cost, q), lut);
+        }
+        if (subpel)
+        {
+            if (resume <= LA_RESUME_HPEL)
+            {
+                const int qx = s.bmx + L.hpdx, qy = s.bmy + L.hpdy;
+                Row4 r[4];
+                fetch_qpel<P>(refLane, planeSize, stride, qx, qy, r);
+                const int cost = quad_sum(sad4x4<P>(fe, r)) + lutx[qx] + luty[qy];
+                la_upd_hpel(s, warp_min_key(q < 4, cost, q));
+            }
+            {
+                const int qx = s.bmx + L.qpdx, qy = s.bmy + L.qpdy;
+                Row4 r[4];
+                fetch_qpel<P>(refLane, planeSize, stride, qx, qy, r);
+                const int cost = (quad_sum(satd4x4_abs<P>(fe, r)) >> 1) + lutx[qx] + luty[qy];
+                const int c0 = __shfl_sync(FULL_MASK, cost, 0);
+                la_upd_qpel(s, c0, warp_min_key(q >= 1 && q < 5, cost, q));
+            }
+        }
+    }
+    outMv = la_pack_mv(s.outx, s.outy);
+    outCost = s.outcost;
+}
+
+/* ===========================================================================================
+ * spec_kernel: grid (ceil(nCU / SPEC_WARPS), searches), one warp per CU, no dependencies.
+ * =========================================================================================== */
+__device__ __forceinline__ int hint_at(const int* __restrict__ hint, int neg, int idx)
+{
+    if (!hint) return 0;
+    const int h = __ldg(hint + idx);
+    return neg ? la_pack_mv(-la_mv_x(h), -la_mv_y(h)) : h;
+}
+
+template <typename P>
+__global__ void __launch_bounds__(SPEC_WARPS * 32, 3)
+spec_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restrict__ plans, GeomDev g, const uint16_t* __restrict__ lut)
+{
+    __shared__ typename Px<P>::Row4 sWin[SPEC_WARPS][WIN_PITCH];
+    const SearchPlan pl = plans[blockIdx.y];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int W = g.wCU, H = g.hCU;
+    const int cuXY = blockIdx.x * SPEC_WARPS + warp;
+    if (cuXY >= g.nCU) return;
+    const int cuY = cuXY / W, cuX = cuXY - cuY * W;
+    const JobDev* __restrict__ jp = jobs + pl.job;
+    const P* __restrict__ fencPlane = (const P*)jp->fenc;
+    const P* __restrict__ refPlane = (const P*)(pl.list ? jp->ref1 : jp->ref0w);
+    const int sub = lane & 3, bx = (sub & 1) * 4, by = (sub >> 1) * 4;
+    const int stride = g.stride, planeSize = (int)g.planeSize;
+    const LaneGeom L = lane_geom(lane, stride);
+
+    /* bottom row of a cooperative slice (or of the frame): no candidates from below (slicetype.cpp:1957-1968) */
+    const bool lastRow = cuY == H - 1 || (pl.numSlices > 1 && (cuY + 1) % pl.rowsPerSlice == 0 && (cuY + 1) / pl.rowsPerSlice < pl.numSlices);
+    const bool hasR = cuX < W - 1, hasB = !lastRow, hasBL = hasB && cuX > 0, hasBR = hasB && hasR;
+    /* predicted neighbour MVs, most likely MVP first: below, right, below-left, below-right; the CU's own hint fills in */
+    int v0 = hasB ? hint_at(pl.hint, pl.hintNeg, cuXY + W) : (hasR ? hint_at(pl.hint, pl.hintNeg, cuXY + 1) : 0);
+    int v1 = hasR ? hint_at(pl.hint, pl.hintNeg, cuXY + 1) : v0;
+    int v2 = hasBL ? hint_at(pl.hint, pl.hintNeg, cuXY + W - 1) : v0;
+    int v3 = hasBR ? hint_at(pl.hint, pl.hintNeg, cuXY + W + 1) : v0;
+    int v4 = (hasB || hasR) ? hint_at(pl.hint, pl.hintNeg, cuXY) : 0;
+    /* keep the first MEMO_N distinct ones */
+    int mv[MEMO_N];
+    int n = 0;
+    {
+        const int cand[5] = { v0, v1, v2, v3, v4 };
+#pragma unroll
+        for (int i = 0; i < 5; i++)
+        {
+            bool dup = false;
+#pragma unroll
+            for (int k = 0; k < MEMO_N; k++) dup = dup || (k < n && mv[k] == cand[i]);
+            if (!dup && n < MEMO_N)
+            {
+#pragma unroll
+                for (int k = 0; k < MEMO_N; k++) if (k == n) mv[k] = cand[i];
+                n++;
+            }
+        }
+    }
+    const int rowBase = (8 * cuY + by) * stride + bx;
+    typename Px<P>::Row4 fe[4];
+#pragma unroll
+    for (int y = 0; y < 4; y++)
+        fe[y] = Px<P>::load_aligned(fencPlane + rowBase + 8 * cuX + y * stride);
+    const P* __restrict__ refCU = refPlane + 8 * cuY * stride + 8 * cuX;
+    const P* __restrict__ refLane = refPlane + rowBase + 8 * cuX;
+    int4* __restrict__ memo = pl.memo + (size_t)cuXY * MEMO_N;
+#pragma unroll 1
+    for (int k = 0; k < MEMO_N; k++)
+    {
+        int4 e = make_int4(0, -1, 0, -1);
+        if (k < n)
+        {
+            int m = mv[0];
+#pragma unroll
+            for (int i = 1; i < MEMO_N; i++) if (i == k) m = mv[i];
+            int oMv, oCost, cs;
+            bool cok;
+            search_mv<P>(refCU, refLane, sWin[warp], planeSize, stride, fe, lut, L, lane, bx, by, cuX, cuY, W, H, m, oMv, oCost, cs, cok);
+            e = make_int4(m, cok ? cs : -1, oMv, oCost);
+        }
+        if (lane == 0) memo[k] = e;
+    }
+}
+
+/* ===========================================================================================
+ * search_kernel (commit): one CTA per row group, one warp per CU row, wavefront over the rows.
+ * =========================================================================================== */
+template <typename P>
+__host__ __device__ inline size_t search_smem_bytes(int rows, int wCU)
+{
+    return (size_t)rows * wCU * sizeof(unsigned long long) + (size_t)rows * WIN_PITCH * sizeof(typename Px<P>::Row4);
+}
+
+template <typename P>
+__global__ void __launch_bounds__(SEARCH_MAX_GROUP_ROWS * 32)
+search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restrict__ plans, const SearchItem* __restrict__ items, GeomDev g,
+              const uint16_t* __restrict__ lut, unsigned long long* gHand, int rowsMax)
+{
+    extern __shared__ unsigned long long sHand[];  /* [rowsMax][W] hand-off words, then one window per warp */
     const SearchItem it = items[blockIdx.x];
+    const SearchPlan pl = plans[it.search];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nRows = it.lastY - it.firstY + 1;
     const int W = g.wCU, H = g.hCU;
+    typename Px<P>::Row4* win = (typename Px<P>::Row4*)(sHand + rowsMax * W) + warp * WIN_PITCH;
     for (int i = threadIdx.x; i < nRows * W; i += blockDim.x) sHand[i] = 0;
-    const JobDev* __restrict__ jp = jobs + it.job;
-    const int list = it.list;
-    {
-        /* Stream this group's band of the source plane and of the four reference planes into L2
-         * before the dependent chain starts: a single estimate reads frames that left L2 long
-         * ago, and a DRAM miss inside a pass stalls the whole chain for ~1 us.  Fire and forget. */
-        const int bandRows = (it.lastY - it.firstY + 1) * 8 + 64;           /* +-32 rows of search range */
-        const int bandTop = it.firstY * 8 - 32;
-        const int linesPerRow = (g.width + 64) * (int)sizeof(P) / 128 + 1;
-        const char* fencB = (const char*)jp->fenc;
-        const char* refB = (const char*)(list ? jp->ref1 : jp->ref0w);
-        const int total = bandRows * linesPerRow * 5;
-        for (int i = threadIdx.x; i < total; i += blockDim.x)
-        {
-            const int plane = i / (bandRows * linesPerRow);                  /* 0..3 reference planes, 4 = source */
-            const int rem = i - plane * bandRows * linesPerRow;
-            const int row = bandTop + rem / linesPerRow, line = rem % linesPerRow;
-            if (plane == 4 && (row < it.firstY * 8 || row >= (it.lastY + 1) * 8)) continue;
-            const char* base = plane == 4 ? fencB : refB + (int64_t)plane * g.planeSize * (int)sizeof(P);
-            const char* ptr = base + ((int64_t)row * g.stride - 32) * (int)sizeof(P) + line * 128;
-            asm volatile("prefetch.global.L2 [%0];" :: "l"(ptr));
-        }
-    }
+    const JobDev* __restrict__ jp = jobs + pl.job;
+    const int list = pl.list;
     __syncthreads();
     if (warp >= nRows) return;
 
-    const int q = lane >> 2, sub = lane & 3, bx = (sub & 1) * 4, by = (sub >> 1) * 4;
+    const int sub = lane & 3, bx = (sub & 1) * 4, by = (sub >> 1) * 4;
     const int stride = g.stride, planeSize = (int)g.planeSize;
+    const LaneGeom L = lane_geom(lane, stride);
+    const int q = L.q;
     const int bidir = jp->bidir;
     const P* __restrict__ fencPlane = (const P*)jp->fenc;
     const P* __restrict__ refPlane = (const P*)(list ? jp->ref1 : jp->ref0w);
@@ -134,139 +466,120 @@ search_kernel(const JobDev* __restrict__ jobs, const SearchItem* __restrict__ it
     volatile unsigned long long* myHandG = gHand + (it.pubBase >= 0 ? it.pubBase : 0);
     volatile const unsigned long long* below = (warp == 0) ? (volatile const unsigned long long*)(gHand + (it.subBase >= 0 ? it.subBase : 0))
                                                            : (volatile const unsigned long long*)(sHand + (warp - 1) * W);
-
-    /* per-lane candidate geometry of the fixed-shape passes (motion.cpp:64-66 tables) */
-    const int hex6dx = la_hex2x((q + 1) & 7), hex6dy = la_hex2y((q + 1) & 7);
-    const int hex6off = hex6dy * stride + hex6dx;
-    const int sq8dx = la_sq1x(q + 1), sq8dy = la_sq1y(q + 1);
-    const int sq8off = sq8dy * stride + sq8dx;
-    const int hpdx = la_sq1x((q + 1) & 7) * 2, hpdy = la_sq1y((q + 1) & 7) * 2;   /* quarter-pel units */
-    const int qpdx = la_sq1x(q), qpdy = la_sq1y(q);
-
+    const int4* __restrict__ memoRow = pl.memo + (size_t)cuY * W * MEMO_N;
     const int rowBase = (8 * cuY + by) * stride + bx;
     int prevMv = 0;                                /* MV of (cuX + 1, cuY): our own previous result */
-    typename Px<P>::Row4 fe[4], feNext[4];
-#pragma unroll
-    for (int y = 0; y < 4; y++)
-        feNext[y] = Px<P>::load_aligned(fencPlane + rowBase + 8 * (W - 1) + y * stride);
+    int belowX = 0, belowX1 = 0;                   /* MVs of (cuX, cuY + 1) and (cuX + 1, cuY + 1): read while working on the CUs to the right */
+    if (!lastRow) belowX = hand_wait(below + W - 1);
+    /* memo of the CU being worked on / of the next one, in registers; lines further ahead are pulled into L1 */
+    int4 e0, e1, e2, e3, n0, n1, n2, n3;
+    n0 = memoRow[(W - 1) * MEMO_N + 0]; n1 = memoRow[(W - 1) * MEMO_N + 1];
+    n2 = memoRow[(W - 1) * MEMO_N + 2]; n3 = memoRow[(W - 1) * MEMO_N + 3];
+    if (lane < 16 && W - 2 - (lane >> 1) >= 0)
+        asm volatile("prefetch.global.L1 [%0];" :: "l"((const char*)(memoRow + (W - 2 - (lane >> 1)) * MEMO_N) + (lane & 1) * 32));
 
     for (int cuX = W - 1; cuX >= 0; cuX--)
     {
-#pragma unroll
-        for (int y = 0; y < 4; y++) fe[y] = feNext[y];
+        e0 = n0; e1 = n1; e2 = n2; e3 = n3;
         if (cuX > 0)
         {
-#pragma unroll
-            for (int y = 0; y < 4; y++)
-                feNext[y] = Px<P>::load_aligned(fencPlane + rowBase + 8 * (cuX - 1) + y * stride);
+            const int4* __restrict__ mp = memoRow + (cuX - 1) * MEMO_N;
+            n0 = mp[0]; n1 = mp[1]; n2 = mp[2]; n3 = mp[3];
         }
-        const P* __restrict__ refLane = refPlane + rowBase + 8 * cuX;
-        if (cuX > 0)
-        {
-            /* pull the likely window of the NEXT CU (same MV as our right neighbour, 8 samples to the
-             * left) into L1 while this CU is being searched: 16 rows x 4 planes, two sectors per row */
-            const int prow = (lane & 15) - 4, pplane = lane >> 4;
-            const P* w = refPlane + (8 * cuY + (la_mv_y(prevMv) >> 2) + prow) * stride + 8 * (cuX - 1) + (la_mv_x(prevMv) >> 2) - 4;
-            asm volatile("prefetch.global.L1 [%0];" :: "l"(w + pplane * planeSize));
-            asm volatile("prefetch.global.L1 [%0];" :: "l"(w + pplane * planeSize + 16));
-            asm volatile("prefetch.global.L1 [%0];" :: "l"(w + (pplane + 2) * planeSize));
-            asm volatile("prefetch.global.L1 [%0];" :: "l"(w + (pplane + 2) * planeSize + 16));
-        }
+        if (lane < 2 && cuX >= 9)
+            asm volatile("prefetch.global.L1 [%0];" :: "l"((const char*)(memoRow + (cuX - 9) * MEMO_N) + lane * 32));
 
         /* ---- neighbour MVs (slicetype.cpp:2117-2128): right, below, below-left, below-right ---- */
         int nb0 = 0, nb1 = 0, nb2 = 0, nb3 = 0, numc = 0;
         if (cuX < W - 1) { nb0 = prevMv; numc = 1; }
+        const long long tCu0 = SSTAT_CLOCK();
         if (!lastRow)
         {
-            /* the row below runs right to left: its column cuX - 1 is published last */
-            int bl = 0, br = 0;
+            /* the row below runs right to left: its column cuX - 1 is published last, and columns cuX, cuX + 1
+             * were already read as the below-left / below neighbours of the CU to the right */
+            const int br = belowX1, mb = belowX;
+            int bl = 0;
             if (cuX > 0) bl = hand_wait(below + cuX - 1);
-            const int mb = hand_wait(below + cuX);
-            if (cuX < W - 1) br = hand_wait(below + cuX + 1);
+            belowX1 = mb; belowX = bl;
             if (numc == 0) nb0 = mb; else nb1 = mb;
             numc++;
             if (cuX > 0) { if (numc == 1) nb1 = bl; else nb2 = bl; numc++; }
             if (cuX < W - 1) { if (numc == 2) nb2 = br; else nb3 = br; numc++; }
         }
-        LaSearch s;
-        la_search_begin(s, cuX, cuY, W, H, bidir, numc, nb0, nb1, nb2, nb3);
+        SSTAT_ADD(11, SSTAT_CLOCK() - tCu0);
+        SSTAT_ADD(0, 1);
 
-        /* ---- CAND: SATD at each neighbour MV, no mvcost (quads >= numc re-measure candidate 0) ---- */
-        if (numc)
+#define MEMO_FIND(v) ((e0.w >= 0 && e0.x == (v)) ? 0 : (e1.w >= 0 && e1.x == (v)) ? 1 : (e2.w >= 0 && e2.x == (v)) ? 2 : \
+                      (e3.w >= 0 && e3.x == (v)) ? 3 : -1)
+#define MEMO_SEL(k, f) ((k) == 0 ? e0.f : (k) == 1 ? e1.f : (k) == 2 ? e2.f : e3.f)
+        int outMv, outCost, skipCost = 0x7fffffff;
+        /* ---- fast path: every neighbour carries the same vector v (3 of 4 CUs).  The first candidate wins the
+         * strict-< chain whatever the costs, so MVP = v; its SATD only matters for the bidir skip rule, and only when v is
+         * zero (slicetype.cpp:2146-2149).  No pixels, no state machine: one memo lookup. ---- */
+        const bool allEq = (numc < 2 || nb1 == nb0) && (numc < 3 || nb2 == nb0) && (numc < 4 || nb3 == nb0);
+        const int fi = MEMO_FIND(nb0);
+        if (allEq && fi >= 0 && (nb0 != 0 || !bidir || numc == 0 || MEMO_SEL(fi, y) >= 0))
         {
-            const int p = la_cand_mv(s, q < numc ? q : 0);
-            typename Px<P>::Row4 r[4];
-            fetch_qpel<P>(refLane, planeSize, stride, la_mv_x(p), la_mv_y(p), r);
-            const int cost = quad_sum(satd4x4_abs<P>(fe, r)) >> 1;
-            la_upd_cand(s, __shfl_sync(FULL_MASK, cost, 0), __shfl_sync(FULL_MASK, cost, 4),
-                        __shfl_sync(FULL_MASK, cost, 8), __shfl_sync(FULL_MASK, cost, 12));
+            outMv = MEMO_SEL(fi, z); outCost = MEMO_SEL(fi, w);
+            if (nb0 == 0 && bidir && numc > 0) skipCost = MEMO_SEL(fi, y);
+            SSTAT_ADD(15, 1);
         }
-        const uint16_t* __restrict__ lutx = lut - s.mvpx;
-        const uint16_t* __restrict__ luty = lut - s.mvpy;
-
-        /* ---- START: q0 = qpel MVP (no mvcost), q1 = rounded MVP, q2 = zero ---- */
-        la_enter_start(s);
+        else
         {
-            const int qx = q == 0 ? s.pmx : (q == 1 ? ((s.pmx + 2) >> 2) * 4 : 0);
-            const int qy = q == 0 ? s.pmy : (q == 1 ? ((s.pmy + 2) >> 2) * 4 : 0);
-            typename Px<P>::Row4 r[4];
-            fetch_qpel<P>(refLane, planeSize, stride, qx, qy, r);
-            const int mvc = q == 0 ? 0 : lutx[qx] + luty[qy];
-            const int cost = quad_sum(sad4x4<P>(fe, r)) + mvc;
-            la_upd_start(s, __shfl_sync(FULL_MASK, cost, 0), __shfl_sync(FULL_MASK, cost, 4), __shfl_sync(FULL_MASK, cost, 8));
-        }
-
-        /* ---- HEX6 + HEX3 rounds: full-pel SAD + mvcost ---- */
-        {
-            const int fx = s.bmx + hex6dx, fy = s.bmy + hex6dy;
-            typename Px<P>::Row4 r[4];
-            fetch_off<P>(refLane, stride, s.bmy * stride + s.bmx + hex6off, r);
-            const int cost = quad_sum(sad4x4<P>(fe, r)) + lutx[fx * 4] + luty[fy * 4];
-            bool more = la_upd_hex6(s, warp_min_key(q < 6, cost, q));
-            while (more)
+            /* ---- candidate SATDs: from the memo when every neighbour MV was predicted ---- */
+            int k0 = 0, k1 = 0, k2 = 0, k3 = 0;
             {
-                const int hdx = la_hex2x((s.dir + q) & 7), hdy = la_hex2y((s.dir + q) & 7);
-                const int hx = s.bmx + hdx, hy = s.bmy + hdy;
-                typename Px<P>::Row4 r3[4];
-                fetch_off<P>(refLane, stride, hy * stride + hx, r3);
-                const int c3 = quad_sum(sad4x4<P>(fe, r3)) + lutx[hx * 4] + luty[hy * 4];
-                more = la_upd_hex3(s, warp_min_key(q < 3, c3, q));
+                bool ok = true;
+                if (numc > 0) { const int i = MEMO_FIND(nb0); k0 = MEMO_SEL(i, y); ok = ok && i >= 0 && k0 >= 0; }
+                if (numc > 1) { const int i = MEMO_FIND(nb1); k1 = MEMO_SEL(i, y); ok = ok && i >= 0 && k1 >= 0; }
+                if (numc > 2) { const int i = MEMO_FIND(nb2); k2 = MEMO_SEL(i, y); ok = ok && i >= 0 && k2 >= 0; }
+                if (numc > 3) { const int i = MEMO_FIND(nb3); k3 = MEMO_SEL(i, y); ok = ok && i >= 0 && k3 >= 0; }
+                if (!ok)
+                {
+                    /* the reference's CAND pass, straight from global memory: quad k measures neighbour k */
+                    typename Px<P>::Row4 fe[4], rr[4];
+#pragma unroll
+                    for (int y = 0; y < 4; y++)
+                        fe[y] = Px<P>::load_aligned(fencPlane + rowBase + 8 * cuX + y * stride);
+                    const int cmv = q == 0 ? nb0 : (q == 1 ? nb1 : (q == 2 ? nb2 : (q == 3 ? nb3 : 0)));
+                    fetch_qpel<P>(refPlane + rowBase + 8 * cuX, planeSize, stride, la_mv_x(cmv), la_mv_y(cmv), rr);
+                    const int cc = quad_sum(satd4x4_abs<P>(fe, rr)) >> 1;
+                    k0 = __shfl_sync(FULL_MASK, cc, 0); k1 = __shfl_sync(FULL_MASK, cc, 4);
+                    k2 = __shfl_sync(FULL_MASK, cc, 8); k3 = __shfl_sync(FULL_MASK, cc, 12);
+                    SSTAT_ADD(14, 1);
+                }
+            }
+            /* ---- the MVP, exactly as slicetype.cpp:2130-2150 ---- */
+            LaSearch s;
+            la_search_begin(s, cuX, cuY, W, H, bidir, numc, nb0, nb1, nb2, nb3);
+            la_upd_cand(s, k0, k1, k2, k3);
+            skipCost = s.skipCost;
+            const int mvp = la_pack_mv(s.mvpx, s.mvpy);
+            const int i = MEMO_FIND(mvp);
+            if (i >= 0) { outMv = MEMO_SEL(i, z); outCost = MEMO_SEL(i, w); }
+            else
+            {
+                /* nobody predicted this MVP: search it here, on the chain */
+                typename Px<P>::Row4 fe[4];
+#pragma unroll
+                for (int y = 0; y < 4; y++)
+                    fe[y] = Px<P>::load_aligned(fencPlane + rowBase + 8 * cuX + y * stride);
+                int cs;
+                bool cok;
+                const long long tS0 = SSTAT_CLOCK();
+                search_mv<P>(refPlane + 8 * cuY * stride + 8 * cuX, refPlane + rowBase + 8 * cuX, win, planeSize, stride, fe, lut, L, lane, bx, by,
+                             cuX, cuY, W, H, mvp, outMv, outCost, cs, cok);
+                SSTAT_ADD(10, SSTAT_CLOCK() - tS0);
+                SSTAT_ADD(1, 1);
             }
         }
+#undef MEMO_FIND
+#undef MEMO_SEL
+        /* bidir-only zero-MV skip shortcut (slicetype.cpp:2155-2159) */
+        if (skipCost < 64 && skipCost < outCost && bidir) { outCost = skipCost; outMv = 0; }
 
-        /* ---- SQ8: 8-point square ---- */
-        bool subpel;
-        {
-            const int fx = s.bmx + sq8dx, fy = s.bmy + sq8dy;
-            typename Px<P>::Row4 r[4];
-            fetch_off<P>(refLane, stride, s.bmy * stride + s.bmx + sq8off, r);
-            const int cost = quad_sum(sad4x4<P>(fe, r)) + lutx[fx * 4] + luty[fy * 4];
-            subpel = la_upd_sq8(s, warp_min_key(true, cost, q), lut);
-        }
-
-        if (subpel)
-        {
-            /* ---- HPEL: 4 half-pel SADs ---- */
-            {
-                const int qx = s.bmx + hpdx, qy = s.bmy + hpdy;
-                typename Px<P>::Row4 r[4];
-                fetch_qpel<P>(refLane, planeSize, stride, qx, qy, r);
-                const int cost = quad_sum(sad4x4<P>(fe, r)) + lutx[qx] + luty[qy];
-                la_upd_hpel(s, warp_min_key(q < 4, cost, q));
-            }
-            /* ---- QPEL: SATD re-measure (q0) + 4 quarter-pel SATDs ---- */
-            {
-                const int qx = s.bmx + qpdx, qy = s.bmy + qpdy;
-                typename Px<P>::Row4 r[4];
-                fetch_qpel<P>(refLane, planeSize, stride, qx, qy, r);
-                const int cost = (quad_sum(satd4x4_abs<P>(fe, r)) >> 1) + lutx[qx] + luty[qy];
-                const int c0 = __shfl_sync(FULL_MASK, cost, 0);
-                la_upd_qpel(s, c0, warp_min_key(q >= 1 && q < 5, cost, q));
-            }
-        }
-        la_finish_skip(s);
-
-        const int mvPacked = la_pack_mv(s.outx, s.outy);
+        const int mvPacked = outMv;
+        SSTAT_ADD(13, SSTAT_CLOCK() - tCu0);
         prevMv = mvPacked;
         if (lane == 0)
         {
@@ -275,9 +588,9 @@ search_kernel(const JobDev* __restrict__ jobs, const SearchItem* __restrict__ it
             myHand[cuX] = word;
             if (publishGlobal) myHandG[cuX] = word;
             mvMirror[cuXY] = mvPacked;
-            mcMirror[cuXY] = s.outcost;
+            mcMirror[cuXY] = outCost;
             mvOut[cuXY] = mvPacked;
-            mcOut[cuXY] = s.outcost;
+            mcOut[cuXY] = outCost;
         }
     }
 }

@@ -35,6 +35,13 @@ int evalQ(const pixel* fenc, const Refs& r, intptr_t off, int qx, int qy, int sa
 
 struct Acc { int64_t costEst, costEstAq; int intraMbs; };
 
+/* search-shape statistics (design data for the speculative kernel; read with emul_stats()) */
+enum { ST_TOTAL, ST_LASTROW, ST_MVP_IN_BELOW, ST_MVP_RIGHT_ONLY, ST_MVP_ZERO_NOCAND, ST_DISTINCT1, ST_DISTINCT2, ST_DISTINCT3,
+       ST_HEX_MOVED, ST_HEX3_ROUNDS, ST_SQ_MOVED, ST_PRE_WON, ST_SUBPEL, ST_HPEL_MOVED, ST_QPEL_MOVED, ST_OUT_EQ_MVP,
+       ST_LAST_EQ2, ST_LAST_TOTAL, ST_RIGHT_EQ_BELOWSET, ST_START_MOVED, ST_SKIP, ST_RIGHT_EQ2, ST_MVP_IN_BELOW_OR_R2,
+       ST_RESUME0, ST_RESUME1, ST_RESUME2, ST_RESUME3, ST_RESUME4, ST_RESUME5, ST_N };
+long long g_stats[ST_N];
+
 void emulCU(ola_ctx* c, ola_frame* fenc, ola_frame* fref0, ola_frame* fref1, const Refs& wref0,
             int cuX, int cuY, int d0, int d1, const int doSearch[2], int lastRow, Acc& acc)
 {
@@ -70,6 +77,8 @@ void emulCU(ola_ctx* c, ola_frame* fenc, ola_frame* fref0, ola_frame* fref1, con
         const Refs& ref = i ? r1 : wref0;
         LaSearch s;
         la_search_begin(s, cuX, cuY, W, H, bidir, numc, nb[0], nb[1], nb[2], nb[3]);
+        g_stats[ST_TOTAL]++;
+        if (lastRow) g_stats[ST_LASTROW]++;
         /* one pass = up to 8 candidates measured "in parallel", then one uniform update,
          * exactly the sequence of the CUDA search kernel */
         int cost[8];
@@ -97,28 +106,81 @@ void emulCU(ola_ctx* c, ola_frame* fenc, ola_frame* fref0, ola_frame* fref1, con
             }
             la_upd_cand(s, cost[0], cost[1], cost[2], cost[3]);
         }
-        la_enter_start(s);
         {
-            int c0 = evalQ(fb, ref, off, s.pmx, s.pmy, 0);
-            int c1 = LA_COST_MAX, c2 = LA_COST_MAX;
-            if (la_start_subpel(s))
+            int mvp = la_pack_mv(s.mvpx, s.mvpy);
+            int r2 = (cuX < W - 2) ? la_pack_mv(mv[cuXY + 2].x, mv[cuXY + 2].y) : 0;
+            if (!numc) g_stats[ST_MVP_ZERO_NOCAND]++;
+            if (lastRow && numc) { g_stats[ST_LAST_TOTAL]++; if (mvp == r2) g_stats[ST_LAST_EQ2]++; }
+            if (!lastRow)
             {
-                int rx = ((s.pmx + 2) >> 2) * 4, ry = ((s.pmy + 2) >> 2) * 4;
-                c1 = evalQ(fb, ref, off, rx, ry, 0) + la_mvcost(c->mvcost, s, rx, ry);
+                int first = (cuX < W - 1) ? 1 : 0, inb = 0, dist = 0;
+                for (int k = first; k < numc; k++)
+                {
+                    if (nb[k] == mvp) inb = 1;
+                    int dup = 0;
+                    for (int j = first; j < k; j++) dup |= nb[j] == nb[k];
+                    dist += !dup;
+                }
+                if (inb) g_stats[ST_MVP_IN_BELOW]++; else g_stats[ST_MVP_RIGHT_ONLY]++;
+                if (inb || mvp == r2) g_stats[ST_MVP_IN_BELOW_OR_R2]++;
+                g_stats[ST_DISTINCT1 + dist - 1]++;
+                if (first) { int e = 0; for (int k = 1; k < numc; k++) e |= nb[k] == nb[0]; if (e) g_stats[ST_RIGHT_EQ_BELOWSET]++; if (nb[0] == r2) g_stats[ST_RIGHT_EQ2]++; }
             }
-            if (la_start_nonzero(s))
-                c2 = evalQ(fb, ref, off, 0, 0, 0) + la_mvcost(c->mvcost, s, 0, 0);
-            la_upd_start(s, c0, c1, c2);
         }
+        la_enter_start(s);
+        /* ---- speculative pass: every position of the no-move path measured up front, exactly the
+         * candidate set of the CUDA kernel's search_mv() ---- */
+        int resume;
         {
+            const uint16_t* lut = c->mvcost;
+            const int bm0x = (s.pmx + 2) >> 2, bm0y = (s.pmy + 2) >> 2;
+            int c0 = evalQ(fb, ref, off, s.pmx, s.pmy, 0);
+            int c1 = evalQ(fb, ref, off, bm0x * 4, bm0y * 4, 0) + la_mvcost(lut, s, bm0x * 4, bm0y * 4);
+            int c2 = evalQ(fb, ref, off, 0, 0, 0) + la_mvcost(lut, s, 0, 0);
+            uint32_t hexKey = LA_KEY_NONE, sqKey = LA_KEY_NONE, hpelKey = LA_KEY_NONE, qpelKey = LA_KEY_NONE;
+            for (int q = 0; q < 6; q++)
+            {
+                int qx = (bm0x + la_hex2x(q + 1)) * 4, qy = (bm0y + la_hex2y(q + 1)) * 4;
+                uint32_t k = la_key(evalQ(fb, ref, off, qx, qy, 0) + la_mvcost(lut, s, qx, qy), q);
+                if (k < hexKey) hexKey = k;
+            }
             for (int q = 0; q < 8; q++)
             {
-                valid[q] = q < 6;
-                if (!valid[q]) continue;
-                int qx = (s.bmx + la_hex2x(q + 1)) * 4, qy = (s.bmy + la_hex2y(q + 1)) * 4;
-                cost[q] = evalQ(fb, ref, off, qx, qy, 0) + la_mvcost(c->mvcost, s, qx, qy);
+                int qx = (bm0x + la_sq1x(q + 1)) * 4, qy = (bm0y + la_sq1y(q + 1)) * 4;
+                uint32_t k = la_key(evalQ(fb, ref, off, qx, qy, 0) + la_mvcost(lut, s, qx, qy), q);
+                if (k < sqKey) sqKey = k;
             }
-            bool more = la_upd_hex6(s, Pass::minKey(cost, valid, 0, 8));
+            for (int q = 0; q < 4; q++)
+            {
+                int qx = s.pmx + la_sq1x(q + 1) * 2, qy = s.pmy + la_sq1y(q + 1) * 2;
+                uint32_t k = la_key(evalQ(fb, ref, off, qx, qy, 0) + la_mvcost(lut, s, qx, qy), q);
+                if (k < hpelKey) hpelKey = k;
+            }
+            int qc0 = evalQ(fb, ref, off, s.pmx, s.pmy, 1) + la_mvcost(lut, s, s.pmx, s.pmy);
+            for (int q = 1; q < 5; q++)
+            {
+                int qx = s.pmx + la_sq1x(q), qy = s.pmy + la_sq1y(q);
+                uint32_t k = la_key(evalQ(fb, ref, off, qx, qy, 1) + la_mvcost(lut, s, qx, qy), q);
+                if (k < qpelKey) qpelKey = k;
+            }
+            resume = la_fast_path(s, c0, c1, c2, hexKey, sqKey, hpelKey, qc0, qpelKey, lut);
+            g_stats[ST_RESUME0 + resume]++;
+        }
+        /* ---- one pass at a time from the stage the fast path stopped at ---- */
+        if (resume != LA_RESUME_DONE)
+        {
+            bool more = resume == LA_RESUME_HEX3;
+            if (resume == LA_RESUME_HEX6)
+            {
+                for (int q = 0; q < 8; q++)
+                {
+                    valid[q] = q < 6;
+                    if (!valid[q]) continue;
+                    int qx = (s.bmx + la_hex2x(q + 1)) * 4, qy = (s.bmy + la_hex2y(q + 1)) * 4;
+                    cost[q] = evalQ(fb, ref, off, qx, qy, 0) + la_mvcost(c->mvcost, s, qx, qy);
+                }
+                more = la_upd_hex6(s, Pass::minKey(cost, valid, 0, 8));
+            }
             int guard = 0;
             while (more && guard++ < 16)
             {
@@ -131,37 +193,42 @@ void emulCU(ola_ctx* c, ola_frame* fenc, ola_frame* fref0, ola_frame* fref1, con
                 }
                 more = la_upd_hex3(s, Pass::minKey(cost, valid, 0, 8));
             }
-        }
-        bool subpel;
-        {
-            for (int q = 0; q < 8; q++)
+            bool subpel = true;
+            if (resume <= LA_RESUME_SQ8)
             {
-                valid[q] = true;
-                int qx = (s.bmx + la_sq1x(q + 1)) * 4, qy = (s.bmy + la_sq1y(q + 1)) * 4;
-                cost[q] = evalQ(fb, ref, off, qx, qy, 0) + la_mvcost(c->mvcost, s, qx, qy);
+                for (int q = 0; q < 8; q++)
+                {
+                    valid[q] = true;
+                    int qx = (s.bmx + la_sq1x(q + 1)) * 4, qy = (s.bmy + la_sq1y(q + 1)) * 4;
+                    cost[q] = evalQ(fb, ref, off, qx, qy, 0) + la_mvcost(c->mvcost, s, qx, qy);
+                }
+                subpel = la_upd_sq8(s, Pass::minKey(cost, valid, 0, 8), c->mvcost);
             }
-            subpel = la_upd_sq8(s, Pass::minKey(cost, valid, 0, 8), c->mvcost);
-        }
-        if (subpel)
-        {
-            for (int q = 0; q < 8; q++)
+            if (subpel)
             {
-                valid[q] = q < 4;
-                if (!valid[q]) continue;
-                int qx = s.bmx + la_sq1x(q + 1) * 2, qy = s.bmy + la_sq1y(q + 1) * 2;
-                cost[q] = evalQ(fb, ref, off, qx, qy, 0) + la_mvcost(c->mvcost, s, qx, qy);
+                if (resume <= LA_RESUME_HPEL)
+                {
+                    for (int q = 0; q < 8; q++)
+                    {
+                        valid[q] = q < 4;
+                        if (!valid[q]) continue;
+                        int qx = s.bmx + la_sq1x(q + 1) * 2, qy = s.bmy + la_sq1y(q + 1) * 2;
+                        cost[q] = evalQ(fb, ref, off, qx, qy, 0) + la_mvcost(c->mvcost, s, qx, qy);
+                    }
+                    la_upd_hpel(s, Pass::minKey(cost, valid, 0, 8));
+                }
+                for (int q = 0; q < 8; q++)
+                {
+                    valid[q] = q >= 1 && q < 5;
+                    if (q >= 5) continue;
+                    int qx = s.bmx + la_sq1x(q), qy = s.bmy + la_sq1y(q);
+                    cost[q] = evalQ(fb, ref, off, qx, qy, 1) + la_mvcost(c->mvcost, s, qx, qy);
+                }
+                la_upd_qpel(s, cost[0], Pass::minKey(cost, valid, 0, 8));
             }
-            la_upd_hpel(s, Pass::minKey(cost, valid, 0, 8));
-            for (int q = 0; q < 8; q++)
-            {
-                valid[q] = q >= 1 && q < 5;
-                if (q >= 5) continue;
-                int qx = s.bmx + la_sq1x(q), qy = s.bmy + la_sq1y(q);
-                cost[q] = evalQ(fb, ref, off, qx, qy, 1) + la_mvcost(c->mvcost, s, qx, qy);
-            }
-            la_upd_qpel(s, cost[0], Pass::minKey(cost, valid, 0, 8));
         }
-        la_finish_skip(s);
+        { int oc = s.outcost; la_finish_skip(s); if (oc != s.outcost) g_stats[ST_SKIP]++; }
+        if (s.outx == s.mvpx && s.outy == s.mvpy) g_stats[ST_OUT_EQ_MVP]++;
         listCost[i] = s.outcost;
         fenc->mvCosts[i][dist][cuXY] = s.outcost;
         mv[cuXY].x = (int16_t)s.outx; mv[cuXY].y = (int16_t)s.outy;
@@ -192,6 +259,8 @@ void emulCU(ola_ctx* c, ola_frame* fenc, ola_frame* fref0, ola_frame* fref1, con
 }
 
 } // namespace
+
+extern "C" long long* emul_stats(void) { return g_stats; }
 
 extern "C" int emul_check_tables(void)
 {
