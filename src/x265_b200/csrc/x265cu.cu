@@ -84,7 +84,7 @@ struct x265cu_ctx
     x265cu_stats stats;
 
     int searchWarps;       /* CU rows (= warps) per commit CTA */
-    int searchSpec;        /* 0: commit kernel alone (no speculation kernel); experiments only */
+    int searchSpec;        /* refine iterations before the commit wavefront (0: none; experiments only) */
     long long dbgPlans[4];
 };
 
@@ -258,7 +258,7 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     c->bf = cfg->bframes;
     c->searchWarps = cfg->searchWarps > 0 ? cfg->searchWarps : 4;    /* CU rows (= warps) per commit CTA */
     if (c->searchWarps > SEARCH_MAX_GROUP_ROWS) c->searchWarps = SEARCH_MAX_GROUP_ROWS;
-    c->searchSpec = 1;
+    c->searchSpec = 3;
     memset(c->dbgPlans, 0, sizeof(c->dbgPlans));
     if (const char* e = getenv("X265CU_SEARCH_SPEC")) c->searchSpec = atoi(e);   /* tuning experiments only */
     if (search_smem_bytes<uint16_t>(c->searchWarps, (cfg->srcWidth / 2 + 7) / 8) > 48 * 1024)
@@ -768,7 +768,7 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     }
     size_t wavePlans[3] = { 0, 0, plans.size() };
     for (size_t k = 0; k < waveOf.size(); k++) if (waveOf[k] == 0) wavePlans[1]++;
-    const size_t memoPerSearch = nCU * MEMO_N * sizeof(int4);
+    const size_t memoPerSearch = nCU * MEMO_N * sizeof(int4) + 2 * alignUp(nCU * sizeof(int), 256);   /* memo + the two estimate fields */
     if (!plans.empty() && growDevice(c, &c->dMemo, &c->dMemoCap, plans.size() * memoPerSearch)) return X265CU_ECUDA;
 
     /* ---- commit work items: one per row group of every (search, cooperative slice) ---- */
@@ -779,6 +779,8 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     {
         SearchPlan& pl = plans[k];
         pl.memo = (int4*)(c->dMemo + k * memoPerSearch);
+        pl.field[0] = (int*)(c->dMemo + k * memoPerSearch + nCU * MEMO_N * sizeof(int4));
+        pl.field[1] = pl.field[0] + alignUp(nCU * sizeof(int), 256) / sizeof(int);
         if (k == wavePlans[1]) waveItems[1] = items.size();
         for (int s = 0; s < pl.numSlices; s++)
         {
@@ -895,15 +897,18 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
             if (!np) continue;
             dim3 sgrid((unsigned)((g.nCU + SPEC_WARPS - 1) / SPEC_WARPS), np);
             if (!c->searchSpec) CU_TRY(c, cudaMemsetAsync(c->dMemo + wavePlans[w] * memoPerSearch, 0xff, np * memoPerSearch, c->stream));
+            /* refine iterations: parallel work that shortens the commit chains; a wave with many searches is
+             * throughput-bound, not chain-bound, and gets a single one */
+            const int iters = np >= 32 ? (c->searchSpec < 1 ? c->searchSpec : 1) : c->searchSpec;
             if (c->pb == 1)
             {
-                if (c->searchSpec) spec_kernel<uint8_t><<<sgrid, SPEC_WARPS * 32, 0, c->stream>>>(dJobs, dPlans + wavePlans[w], g, dLutC);
-                search_kernel<uint8_t><<<ni, warps * 32, search_smem_bytes<uint8_t>(warps, g.wCU), c->stream>>>(dJobs, dPlans, dItems + waveItems[w], g, dLutC, dProg, warps);
+                for (int it = 0; it < iters; it++) refine_kernel<uint8_t><<<sgrid, SPEC_WARPS * 32, 0, c->stream>>>(dJobs, dPlans + wavePlans[w], g, dLutC, it);
+                search_kernel<uint8_t><<<ni, warps * 32, search_smem_bytes<uint8_t>(warps, g.wCU), c->stream>>>(dJobs, dPlans, dItems + waveItems[w], g, dLutC, dProg, warps, iters > 0 ? (iters - 1) & 1 : -1);
             }
             else
             {
-                if (c->searchSpec) spec_kernel<uint16_t><<<sgrid, SPEC_WARPS * 32, 0, c->stream>>>(dJobs, dPlans + wavePlans[w], g, dLutC);
-                search_kernel<uint16_t><<<ni, warps * 32, search_smem_bytes<uint16_t>(warps, g.wCU), c->stream>>>(dJobs, dPlans, dItems + waveItems[w], g, dLutC, dProg, warps);
+                for (int it = 0; it < iters; it++) refine_kernel<uint16_t><<<sgrid, SPEC_WARPS * 32, 0, c->stream>>>(dJobs, dPlans + wavePlans[w], g, dLutC, it);
+                search_kernel<uint16_t><<<ni, warps * 32, search_smem_bytes<uint16_t>(warps, g.wCU), c->stream>>>(dJobs, dPlans, dItems + waveItems[w], g, dLutC, dProg, warps, iters > 0 ? (iters - 1) & 1 : -1);
             }
         }
         CU_TRY(c, cudaGetLastError());
@@ -924,13 +929,31 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     int r = syncStream(c);
     if (r) return r;
 #ifdef X265CU_SEARCH_STATS
+    if (!plans.empty() && getenv("X265CU_TRACE_BATCH"))
+    {
+        static int batchNo = 0;
+        if (batchNo++ == atoi(getenv("X265CU_TRACE_BATCH")))
+        {
+            static unsigned long long tt[256][512]; static unsigned int te[256][512]; static int tn[256];
+            cudaMemcpyFromSymbol(tt, g_traceT, sizeof(tt)); cudaMemcpyFromSymbol(te, g_traceE, sizeof(te)); cudaMemcpyFromSymbol(tn, g_traceN, sizeof(tn));
+            unsigned long long t0 = ~0ull;
+            for (int r = 0; r < (int)hCU; r++) if (tn[r] > 0 && tt[r][0] < t0) t0 = tt[r][0];
+            for (int r = (int)hCU - 1; r >= 0; r--)
+            {
+                fprintf(stderr, "TRACE row %d:", r);
+                for (int i = 0; i < tn[r]; i++) fprintf(stderr, " %llu:%u/%u/%u", (tt[r][i] - t0) / 100, te[r][i] & 0xffff, (te[r][i] >> 16) & 0xff, te[r][i] >> 24);
+                fprintf(stderr, "\n");
+            }
+        }
+    }
     if (!plans.empty() && getenv("X265CU_STATS_PER_BATCH"))
     {
         unsigned long long h[32], z[32] = { 0 };
         cudaMemcpyFromSymbol(h, g_searchStats, sizeof(h));
         cudaMemcpyToSymbol(g_searchStats, z, sizeof(z));
-        fprintf(stderr, "batch: jobs %d searches %zu waves %d | cus %llu fast %llu cand-pass %llu chain-search %llu | cyc/CU total %.0f wait-below %.0f search %.0f\n",
-                n, plans.size(), numWaves, h[0], h[15], h[14], h[1], (double)h[13] / (h[0] ? h[0] : 1), (double)h[11] / (h[0] ? h[0] : 1), (double)h[10] / (h[0] ? h[0] : 1));
+        fprintf(stderr, "batch: jobs %d searches %zu waves %d | cus %llu fast %llu cand-pass %llu chain-search %llu steps %llu | serial %llu: cyc wait %.0f memo %.0f cand %.0f (per pass %.0f) mvp %.0f search %.0f (per search %.0f)\n",
+                n, plans.size(), numWaves, h[0], h[15], h[14], h[1], h[16], h[17], (double)h[20] / (h[17] ? h[17] : 1), (double)h[21] / (h[17] ? h[17] : 1),
+                (double)h[22] / (h[17] ? h[17] : 1), (double)h[25] / (h[26] ? h[26] : 1), (double)h[23] / (h[17] ? h[17] : 1), (double)h[24] / (h[17] ? h[17] : 1), (double)h[24] / (h[1] ? h[1] : 1));
     }
 #endif
 

@@ -19,16 +19,20 @@
  *    decisions on the costs; only when the search really moves does it fall back to
  *    one-pass-at-a-time evaluation, from the stage where the speculation stopped applying.
  *
- * 2. SPECULATION KERNEL (spec_kernel): every CU of every search in parallel, no dependencies.  A
- *    HINT field (the MVs an earlier, temporally adjacent search produced; zero when there is none)
- *    predicts the neighbours' MVs; for each distinct predicted vector the CU's full search is run
- *    and memoised per CU as {MVP, SATD at the MVP, resulting MV, resulting cost}.  Hints only ever
- *    select WHICH vectors get measured early, never a result.
+ * 2. REFINE KERNEL (refine_kernel), run a few times: every CU of every search in parallel, no
+ *    dependencies inside a launch.  Iteration k reads an ESTIMATE H_k of the search's MV field (H_0 = a
+ *    hint: the field an earlier, temporally adjacent search produced; zero when there is none), takes a
+ *    CU's neighbour MVs from it, runs the CU's full search for every such vector it has not measured
+ *    yet and memoises it per CU as {MVP, SATD at the MVP, resulting MV, resulting cost}; then it
+ *    evaluates the CU exactly as the reference would IF its neighbours had those MVs, which gives
+ *    H_k+1.  New vectors that this frame's pixels produce thus reach their neighbours' memos one CU
+ *    further per iteration -- in parallel instead of on the chain.  Estimates only ever select WHICH
+ *    vectors get measured early, never a result.
  *
- * 3. COMMIT KERNEL (search_kernel): the wavefront.  One warp per CU row; per CU it takes the real
+ * 3. COMMIT KERNEL (search_kernel): the wavefront.  One warp per CU row; per CU it takes the REAL
  *    neighbour MVs, looks their SATDs up in the memo (same MV => same pixels => same cost), picks
  *    the MVP exactly as the reference does (strict <, reference order, skipCost rule) and takes the
- *    memoised search result.  Pixels are only touched on the chain when a vector was not
+ *    memoised search result.  Pixels are only touched on the chain when a vector was never
  *    predicted (then: the reference's CAND pass and/or a one-shot search, inline).
  *
  * A finished CU publishes ONE 64-bit word {tag = 1, packed MV}; tag and data travel in the same
@@ -51,6 +55,7 @@ struct SearchPlan
     const int* hint;               /* packed MV field predicting this search's result, or NULL (zero field) */
     int hintNeg;                   /* the hint is the opposite list's field: negate it */
     int4* memo;                    /* [nCU][MEMO_N] {mvp, SATD at mvp or -1, result MV, result cost or -1 (empty)} */
+    int* field[2];                 /* [nCU] ping-pong estimates of the result field (refine iterations) */
 };
 
 /* one row group of a search: a CTA of the commit kernel */
@@ -63,7 +68,7 @@ struct SearchItem
     int subBase;                   /* hand-off row the group's BOTTOM row reads (the group below), -1: none */
 };
 
-#define MEMO_N 4
+#define MEMO_N 8
 #define SEARCH_MAX_GROUP_ROWS 16
 #define SEARCH_MAX_THREADS 256
 #define SPEC_WARPS 8
@@ -74,7 +79,14 @@ struct SearchItem
 __device__ unsigned long long g_searchStats[32];
 #define SSTAT_ADD(i, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_searchStats[i], (unsigned long long)(v)); } while (0)
 #define SSTAT_CLOCK() clock64()
+/* per-row step timeline of the commit kernel: [cuY][event] = {globaltimer ns, x0 | kind << 16 | n << 24} */
+__device__ unsigned long long g_traceT[256][512];
+__device__ unsigned int g_traceE[256][512];
+__device__ int g_traceN[256];
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define STRACE(row, x0, kind, n) do { if ((threadIdx.x & 31) == 0) { int i_ = g_traceN[row]; if (i_ < 512) { g_traceT[row][i_] = gtimer(); g_traceE[row][i_] = (unsigned)(x0) | ((unsigned)(kind) << 16) | ((unsigned)(n) << 24); g_traceN[row] = i_ + 1; } } } while (0)
 #else
+#define STRACE(row, x0, kind, n) do { } while (0)
 #define SSTAT_ADD(i, v) do { } while (0)
 #define SSTAT_CLOCK() 0ll
 #endif
@@ -278,6 +290,15 @@ __device__ __forceinline__ void search_mv(const P* __restrict__ refCU, const P* 
         const uint32_t sqKey = __reduce_min_sync(FULL_MASK, q < 6 ? la_key(cost3, q + 2) : la_key(cost2, q - 6));
         const int qc0 = __shfl_sync(FULL_MASK, cost4, 0);
         centerSatd = __shfl_sync(FULL_MASK, raw4, 0);
+        if (!candOk)
+        {
+            /* the MVP was clipped (picture edge): the neighbour's own vector is measured where it points, unclipped
+             * (slicetype.cpp:2138), straight from global memory */
+            Row4 rr[4];
+            fetch_qpel<P>(refLane, planeSize, stride, s.mvpx, s.mvpy, rr);
+            centerSatd = __shfl_sync(FULL_MASK, quad_sum(satd4x4_abs<P>(fe, rr)) >> 1, 0);
+            candOk = true;
+        }
         const uint32_t qpelKey = warp_min_key(q >= 1 && q < 5, cost4, q);
         resume = la_fast_path(s, c0, c1, c2, hexKey, sqKey, hpelKey, qc0, qpelKey, lut);
         SSTAT_ADD(4 + resume, 1);
@@ -338,7 +359,8 @@ __device__ __forceinline__ void search_mv(const P* __restrict__ refCU, const P* 
 }
 
 /* ===========================================================================================
- * spec_kernel: grid (ceil(nCU / SPEC_WARPS), searches), one warp per CU, no dependencies.
+ * refine_kernel: grid (ceil(nCU / SPEC_WARPS), searches), one warp per CU, no dependencies.
+ * Lane k (and k + 8, k + 16, k + 24) holds memo entry k of the CU, so a lookup is one ballot.
  * =========================================================================================== */
 __device__ __forceinline__ int hint_at(const int* __restrict__ hint, int neg, int idx)
 {
@@ -347,9 +369,15 @@ __device__ __forceinline__ int hint_at(const int* __restrict__ hint, int neg, in
     return neg ? la_pack_mv(-la_mv_x(h), -la_mv_y(h)) : h;
 }
 
+/* index of the memo entry for vector v (-1: none); e = this lane's entry */
+__device__ __forceinline__ int memo_find(const int4& e, int v)
+{
+    return __ffs(__ballot_sync(FULL_MASK, e.w >= 0 && e.x == v) & ((1u << MEMO_N) - 1)) - 1;
+}
+
 template <typename P>
 __global__ void __launch_bounds__(SPEC_WARPS * 32, 3)
-spec_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restrict__ plans, GeomDev g, const uint16_t* __restrict__ lut)
+refine_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restrict__ plans, GeomDev g, const uint16_t* __restrict__ lut, int iter)
 {
     __shared__ typename Px<P>::Row4 sWin[SPEC_WARPS][WIN_PITCH];
     const SearchPlan pl = plans[blockIdx.y];
@@ -359,88 +387,125 @@ spec_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restrict__ plan
     if (cuXY >= g.nCU) return;
     const int cuY = cuXY / W, cuX = cuXY - cuY * W;
     const JobDev* __restrict__ jp = jobs + pl.job;
-    const P* __restrict__ fencPlane = (const P*)jp->fenc;
+    const int bidir = jp->bidir;
+
+    /* the current estimate of the neighbours' MVs, in the reference's candidate order (slicetype.cpp:2117-2128);
+     * bottom row of a cooperative slice (or of the frame): no candidates from below (slicetype.cpp:1957-1968) */
+    const bool lastRow = cuY == H - 1 || (pl.numSlices > 1 && (cuY + 1) % pl.rowsPerSlice == 0 && (cuY + 1) / pl.rowsPerSlice < pl.numSlices);
+    const int* __restrict__ fin = iter == 0 ? pl.hint : pl.field[(iter - 1) & 1];
+    const int neg = iter == 0 ? pl.hintNeg : 0;
+    int nb0 = 0, nb1 = 0, nb2 = 0, nb3 = 0, numc = 0;
+    if (cuX < W - 1) { nb0 = hint_at(fin, neg, cuXY + 1); numc = 1; }
+    if (!lastRow)
+    {
+        const int mb = hint_at(fin, neg, cuXY + W);
+        if (numc == 0) nb0 = mb; else nb1 = mb;
+        numc++;
+        if (cuX > 0) { const int bl = hint_at(fin, neg, cuXY + W - 1); if (numc == 1) nb1 = bl; else nb2 = bl; numc++; }
+        if (cuX < W - 1) { const int br = hint_at(fin, neg, cuXY + W + 1); if (numc == 2) nb2 = br; else nb3 = br; numc++; }
+    }
+
+    int4* __restrict__ memo = pl.memo + (size_t)cuXY * MEMO_N;
+    int4 e = make_int4(0, -1, 0, -1);
+    if (iter > 0) e = memo[lane & (MEMO_N - 1)];
+    int n = __popc(__ballot_sync(FULL_MASK, e.w >= 0) & ((1u << MEMO_N) - 1));
+
+    /* ---- measure every neighbour vector the memo does not hold yet (no candidates at all: the MVP is zero) ---- */
+    const int nWant = numc ? numc : 1;
+    bool loaded = false;
+    typename Px<P>::Row4 fe[4];
     const P* __restrict__ refPlane = (const P*)(pl.list ? jp->ref1 : jp->ref0w);
     const int sub = lane & 3, bx = (sub & 1) * 4, by = (sub >> 1) * 4;
     const int stride = g.stride, planeSize = (int)g.planeSize;
-    const LaneGeom L = lane_geom(lane, stride);
-
-    /* bottom row of a cooperative slice (or of the frame): no candidates from below (slicetype.cpp:1957-1968) */
-    const bool lastRow = cuY == H - 1 || (pl.numSlices > 1 && (cuY + 1) % pl.rowsPerSlice == 0 && (cuY + 1) / pl.rowsPerSlice < pl.numSlices);
-    const bool hasR = cuX < W - 1, hasB = !lastRow, hasBL = hasB && cuX > 0, hasBR = hasB && hasR;
-    /* predicted neighbour MVs, most likely MVP first: below, right, below-left, below-right; the CU's own hint fills in */
-    int v0 = hasB ? hint_at(pl.hint, pl.hintNeg, cuXY + W) : (hasR ? hint_at(pl.hint, pl.hintNeg, cuXY + 1) : 0);
-    int v1 = hasR ? hint_at(pl.hint, pl.hintNeg, cuXY + 1) : v0;
-    int v2 = hasBL ? hint_at(pl.hint, pl.hintNeg, cuXY + W - 1) : v0;
-    int v3 = hasBR ? hint_at(pl.hint, pl.hintNeg, cuXY + W + 1) : v0;
-    int v4 = (hasB || hasR) ? hint_at(pl.hint, pl.hintNeg, cuXY) : 0;
-    /* keep the first MEMO_N distinct ones */
-    int mv[MEMO_N];
-    int n = 0;
+    const int rowBase = (8 * cuY + by) * stride + bx;
+#pragma unroll 1
+    for (int i = 0; i < nWant; i++)
     {
-        const int cand[5] = { v0, v1, v2, v3, v4 };
-#pragma unroll
-        for (int i = 0; i < 5; i++)
+        const int v = i == 0 ? nb0 : (i == 1 ? nb1 : (i == 2 ? nb2 : nb3));
+        if (memo_find(e, v) >= 0 || n >= MEMO_N) continue;
+        if (!loaded)
         {
-            bool dup = false;
+            const P* __restrict__ fencPlane = (const P*)jp->fenc;
 #pragma unroll
-            for (int k = 0; k < MEMO_N; k++) dup = dup || (k < n && mv[k] == cand[i]);
-            if (!dup && n < MEMO_N)
+            for (int y = 0; y < 4; y++)
+                fe[y] = Px<P>::load_aligned(fencPlane + rowBase + 8 * cuX + y * stride);
+            loaded = true;
+        }
+        const LaneGeom L = lane_geom(lane, stride);
+        int oMv, oCost, cs;
+        bool cok;
+        search_mv<P>(refPlane + 8 * cuY * stride + 8 * cuX, refPlane + rowBase + 8 * cuX, sWin[warp], planeSize, stride, fe, lut, L, lane, bx, by,
+                     cuX, cuY, W, H, v, oMv, oCost, cs, cok);
+        const int4 ne = make_int4(v, cok ? cs : -1, oMv, oCost);
+        if ((lane & (MEMO_N - 1)) == n) e = ne;
+        if (lane == n) memo[n] = ne;
+        n++;
+    }
+    if (iter == 0 && lane < MEMO_N && lane >= n) memo[lane] = e;     /* empty entries */
+
+    /* ---- what the reference would decide if the neighbours had these MVs: the next estimate ---- */
+    int outMv = fin ? hint_at(fin, neg, cuXY) : 0;
+    {
+        const int i0 = memo_find(e, nb0), i1 = memo_find(e, nb1), i2 = memo_find(e, nb2), i3 = memo_find(e, nb3);
+        const int k0 = __shfl_sync(FULL_MASK, e.y, i0 & 31), k1 = __shfl_sync(FULL_MASK, e.y, i1 & 31);
+        const int k2 = __shfl_sync(FULL_MASK, e.y, i2 & 31), k3 = __shfl_sync(FULL_MASK, e.y, i3 & 31);
+        const bool ok = (i0 >= 0 && (k0 >= 0 || numc == 0)) && (numc < 2 || (i1 >= 0 && k1 >= 0)) && (numc < 3 || (i2 >= 0 && k2 >= 0)) && (numc < 4 || (i3 >= 0 && k3 >= 0));
+        if (ok)
+        {
+            LaSearch s;
+            la_search_begin(s, cuX, cuY, W, H, bidir, numc, nb0, nb1, nb2, nb3);
+            la_upd_cand(s, k0, k1, k2, k3);
+            const int im = memo_find(e, la_pack_mv(s.mvpx, s.mvpy));     /* the MVP is one of the candidates (or zero): always found */
+            const int rMv = __shfl_sync(FULL_MASK, e.z, im & 31), rCost = __shfl_sync(FULL_MASK, e.w, im & 31);
+            if (im >= 0)
             {
-#pragma unroll
-                for (int k = 0; k < MEMO_N; k++) if (k == n) mv[k] = cand[i];
-                n++;
+                s.outx = la_mv_x(rMv); s.outy = la_mv_y(rMv); s.outcost = rCost;
+                la_finish_skip(s);
+                outMv = la_pack_mv(s.outx, s.outy);
             }
         }
     }
-    const int rowBase = (8 * cuY + by) * stride + bx;
-    typename Px<P>::Row4 fe[4];
-#pragma unroll
-    for (int y = 0; y < 4; y++)
-        fe[y] = Px<P>::load_aligned(fencPlane + rowBase + 8 * cuX + y * stride);
-    const P* __restrict__ refCU = refPlane + 8 * cuY * stride + 8 * cuX;
-    const P* __restrict__ refLane = refPlane + rowBase + 8 * cuX;
-    int4* __restrict__ memo = pl.memo + (size_t)cuXY * MEMO_N;
-#pragma unroll 1
-    for (int k = 0; k < MEMO_N; k++)
-    {
-        int4 e = make_int4(0, -1, 0, -1);
-        if (k < n)
-        {
-            int m = mv[0];
-#pragma unroll
-            for (int i = 1; i < MEMO_N; i++) if (i == k) m = mv[i];
-            int oMv, oCost, cs;
-            bool cok;
-            search_mv<P>(refCU, refLane, sWin[warp], planeSize, stride, fe, lut, L, lane, bx, by, cuX, cuY, W, H, m, oMv, oCost, cs, cok);
-            e = make_int4(m, cok ? cs : -1, oMv, oCost);
-        }
-        if (lane == 0) memo[k] = e;
-    }
+    if (lane == 0) pl.field[iter & 1][cuXY] = outMv;
 }
 
 /* ===========================================================================================
  * search_kernel (commit): one CTA per row group, one warp per CU row, wavefront over the rows.
+ *
+ * A row is a serial chain (each CU needs its right neighbour's MV), but the refined estimate
+ * predicts that MV almost everywhere, so the warp commits up to 32 CUs per STEP: lane i takes CU
+ * x0 - i, assumes its right neighbour's MV is the estimate (lane 0 knows the true one), reads the
+ * true MVs of the row below, and evaluates the CU from its memo entirely on its own (candidate
+ * SATDs, MVP by the reference's strict-< chain, memoised search result, skip rule).  Then the
+ * assumptions are checked against the actual results of the lanes to the right: the longest prefix
+ * of lanes whose inputs were all true is final and is published at once; the chain restarts at
+ * the first lane that assumed wrongly, waited for the row below, or met a vector its memo does
+ * not hold (that CU is then handled by the whole warp: CAND pass / one-shot search).
  * =========================================================================================== */
 template <typename P>
 __host__ __device__ inline size_t search_smem_bytes(int rows, int wCU)
 {
-    return (size_t)rows * wCU * sizeof(unsigned long long) + (size_t)rows * WIN_PITCH * sizeof(typename Px<P>::Row4);
+    return (size_t)rows * wCU * (sizeof(unsigned long long) + sizeof(int)) + (size_t)rows * WIN_PITCH * sizeof(typename Px<P>::Row4);
 }
 
 template <typename P>
 __global__ void __launch_bounds__(SEARCH_MAX_GROUP_ROWS * 32)
 search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restrict__ plans, const SearchItem* __restrict__ items, GeomDev g,
-              const uint16_t* __restrict__ lut, unsigned long long* gHand, int rowsMax)
+              const uint16_t* __restrict__ lut, unsigned long long* gHand, int rowsMax, int estIdx)
 {
-    extern __shared__ unsigned long long sHand[];  /* [rowsMax][W] hand-off words, then one window per warp */
+    extern __shared__ unsigned long long sHand[];  /* [rowsMax][W] hand-off words, [rowsMax][W] estimates, one window per warp */
     const SearchItem it = items[blockIdx.x];
     const SearchPlan pl = plans[it.search];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nRows = it.lastY - it.firstY + 1;
     const int W = g.wCU, H = g.hCU;
-    typename Px<P>::Row4* win = (typename Px<P>::Row4*)(sHand + rowsMax * W) + warp * WIN_PITCH;
-    for (int i = threadIdx.x; i < nRows * W; i += blockDim.x) sHand[i] = 0;
+    int* sEstAll = (int*)(sHand + rowsMax * W);
+    typename Px<P>::Row4* win = (typename Px<P>::Row4*)(sEstAll + rowsMax * W) + warp * WIN_PITCH;
+    for (int i = threadIdx.x; i < nRows * W; i += blockDim.x)
+    {
+        sHand[i] = 0;
+        const int r = i / W, x = i - r * W;
+        sEstAll[i] = estIdx >= 0 ? pl.field[estIdx][(it.lastY - r) * W + x] : 0;
+    }
     const JobDev* __restrict__ jp = jobs + pl.job;
     const int list = pl.list;
     __syncthreads();
@@ -448,8 +513,7 @@ search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restrict__ pl
 
     const int sub = lane & 3, bx = (sub & 1) * 4, by = (sub >> 1) * 4;
     const int stride = g.stride, planeSize = (int)g.planeSize;
-    const LaneGeom L = lane_geom(lane, stride);
-    const int q = L.q;
+    const int q = lane >> 2;
     const int bidir = jp->bidir;
     const P* __restrict__ fencPlane = (const P*)jp->fenc;
     const P* __restrict__ refPlane = (const P*)(list ? jp->ref1 : jp->ref0w);
@@ -466,131 +530,222 @@ search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restrict__ pl
     volatile unsigned long long* myHandG = gHand + (it.pubBase >= 0 ? it.pubBase : 0);
     volatile const unsigned long long* below = (warp == 0) ? (volatile const unsigned long long*)(gHand + (it.subBase >= 0 ? it.subBase : 0))
                                                            : (volatile const unsigned long long*)(sHand + (warp - 1) * W);
+    const int* sEst = sEstAll + warp * W;
     const int4* __restrict__ memoRow = pl.memo + (size_t)cuY * W * MEMO_N;
     const int rowBase = (8 * cuY + by) * stride + bx;
-    int prevMv = 0;                                /* MV of (cuX + 1, cuY): our own previous result */
-    int belowX = 0, belowX1 = 0;                   /* MVs of (cuX, cuY + 1) and (cuX + 1, cuY + 1): read while working on the CUs to the right */
-    if (!lastRow) belowX = hand_wait(below + W - 1);
-    /* memo of the CU being worked on / of the next one, in registers; lines further ahead are pulled into L1 */
-    int4 e0, e1, e2, e3, n0, n1, n2, n3;
-    n0 = memoRow[(W - 1) * MEMO_N + 0]; n1 = memoRow[(W - 1) * MEMO_N + 1];
-    n2 = memoRow[(W - 1) * MEMO_N + 2]; n3 = memoRow[(W - 1) * MEMO_N + 3];
-    if (lane < 16 && W - 2 - (lane >> 1) >= 0)
-        asm volatile("prefetch.global.L1 [%0];" :: "l"((const char*)(memoRow + (W - 2 - (lane >> 1)) * MEMO_N) + (lane & 1) * 32));
+    int prevMv = 0;                                /* true MV of (x0 + 1, cuY) */
+    int x0 = W - 1;                                /* rightmost CU not yet final */
+    int serialLeft = estIdx >= 0 ? 0 : 0x7fffffff; /* CUs to take one at a time before the next wide step (no estimate: all) */
+#ifdef X265CU_SEARCH_STATS
+    if (lane == 0) g_traceN[cuY] = 0;
+    STRACE(cuY, x0, 0, 0);
+#endif
+    /* the row's memo is read once per CU: pull it into L1 ahead of the chain */
+    for (int i = lane; i < W * 4; i += 32)
+        asm volatile("prefetch.global.L1 [%0];" :: "l"((const char*)memoRow + (size_t)i * 32));
 
-    for (int cuX = W - 1; cuX >= 0; cuX--)
+    while (x0 >= 0)
     {
-        e0 = n0; e1 = n1; e2 = n2; e3 = n3;
-        if (cuX > 0)
+        if (serialLeft == 0)
         {
-            const int4* __restrict__ mp = memoRow + (cuX - 1) * MEMO_N;
-            n0 = mp[0]; n1 = mp[1]; n2 = mp[2]; n3 = mp[3];
-        }
-        if (lane < 2 && cuX >= 9)
-            asm volatile("prefetch.global.L1 [%0];" :: "l"((const char*)(memoRow + (cuX - 9) * MEMO_N) + lane * 32));
-
-        /* ---- neighbour MVs (slicetype.cpp:2117-2128): right, below, below-left, below-right ---- */
-        int nb0 = 0, nb1 = 0, nb2 = 0, nb3 = 0, numc = 0;
-        if (cuX < W - 1) { nb0 = prevMv; numc = 1; }
-        const long long tCu0 = SSTAT_CLOCK();
-        if (!lastRow)
-        {
-            /* the row below runs right to left: its column cuX - 1 is published last, and columns cuX, cuX + 1
-             * were already read as the below-left / below neighbours of the CU to the right */
-            const int br = belowX1, mb = belowX;
-            int bl = 0;
-            if (cuX > 0) bl = hand_wait(below + cuX - 1);
-            belowX1 = mb; belowX = bl;
-            if (numc == 0) nb0 = mb; else nb1 = mb;
-            numc++;
-            if (cuX > 0) { if (numc == 1) nb1 = bl; else nb2 = bl; numc++; }
-            if (cuX < W - 1) { if (numc == 2) nb2 = br; else nb3 = br; numc++; }
-        }
-        SSTAT_ADD(11, SSTAT_CLOCK() - tCu0);
-        SSTAT_ADD(0, 1);
-
-#define MEMO_FIND(v) ((e0.w >= 0 && e0.x == (v)) ? 0 : (e1.w >= 0 && e1.x == (v)) ? 1 : (e2.w >= 0 && e2.x == (v)) ? 2 : \
-                      (e3.w >= 0 && e3.x == (v)) ? 3 : -1)
-#define MEMO_SEL(k, f) ((k) == 0 ? e0.f : (k) == 1 ? e1.f : (k) == 2 ? e2.f : e3.f)
-        int outMv, outCost, skipCost = 0x7fffffff;
-        /* ---- fast path: every neighbour carries the same vector v (3 of 4 CUs).  The first candidate wins the
-         * strict-< chain whatever the costs, so MVP = v; its SATD only matters for the bidir skip rule, and only when v is
-         * zero (slicetype.cpp:2146-2149).  No pixels, no state machine: one memo lookup. ---- */
-        const bool allEq = (numc < 2 || nb1 == nb0) && (numc < 3 || nb2 == nb0) && (numc < 4 || nb3 == nb0);
-        const int fi = MEMO_FIND(nb0);
-        if (allEq && fi >= 0 && (nb0 != 0 || !bidir || numc == 0 || MEMO_SEL(fi, y) >= 0))
-        {
-            outMv = MEMO_SEL(fi, z); outCost = MEMO_SEL(fi, w);
-            if (nb0 == 0 && bidir && numc > 0) skipCost = MEMO_SEL(fi, y);
-            SSTAT_ADD(15, 1);
-        }
-        else
-        {
-            /* ---- candidate SATDs: from the memo when every neighbour MV was predicted ---- */
-            int k0 = 0, k1 = 0, k2 = 0, k3 = 0;
+            /* ================= wide step: lane i evaluates CU x0 - i ================= */
+            const int cu = x0 - lane;
+            const bool valid = cu >= 0;
+            const int cx = valid ? cu : 0;
+            const bool hasR = cx < W - 1, hasB = !lastRow, hasBL = hasB && cx > 0, hasBR = hasB && hasR;
+            /* ---- true MVs of the row below (published right to left; every word's own tag is checked) ---- */
+            bool avail = true;
+            int mvB = 0, mvBL = 0, mvBR = 0;
+            if (hasB)
             {
-                bool ok = true;
-                if (numc > 0) { const int i = MEMO_FIND(nb0); k0 = MEMO_SEL(i, y); ok = ok && i >= 0 && k0 >= 0; }
-                if (numc > 1) { const int i = MEMO_FIND(nb1); k1 = MEMO_SEL(i, y); ok = ok && i >= 0 && k1 >= 0; }
-                if (numc > 2) { const int i = MEMO_FIND(nb2); k2 = MEMO_SEL(i, y); ok = ok && i >= 0 && k2 >= 0; }
-                if (numc > 3) { const int i = MEMO_FIND(nb3); k3 = MEMO_SEL(i, y); ok = ok && i >= 0 && k3 >= 0; }
-                if (!ok)
+                const unsigned long long wB = below[cx], wBL = below[hasBL ? cx - 1 : cx], wBR = below[hasBR ? cx + 1 : cx];
+                avail = (wB & wBL & wBR & HAND_TAG) != 0;
+                mvB = (int)(uint32_t)wB; mvBL = (int)(uint32_t)wBL; mvBR = (int)(uint32_t)wBR;
+            }
+            if (!__shfl_sync(FULL_MASK, avail, 0)) continue;          /* the chain's head waits for the row below */
+            SSTAT_ADD(16, 1);
+
+            /* ---- candidates in the reference's order (slicetype.cpp:2117-2128); the right neighbour's MV is an assumption for lanes > 0 ---- */
+            const int r = lane == 0 ? prevMv : sEst[hasR ? cx + 1 : cx];
+            int nb0 = 0, nb1 = 0, nb2 = 0, nb3 = 0, numc = 0;
+            if (hasR) { nb0 = r; numc = 1; }
+            if (hasB)
+            {
+                if (numc == 0) nb0 = mvB; else nb1 = mvB;
+                numc++;
+                if (hasBL) { if (numc == 1) nb1 = mvBL; else nb2 = mvBL; numc++; }
+                if (hasBR) { if (numc == 2) nb2 = mvBR; else nb3 = mvBR; numc++; }
+            }
+            /* ---- this lane's CU from its memo: SATD and search result of every candidate vector ---- */
+            int k0 = -1, k1 = -1, k2 = -1, k3 = -1;           /* candidate SATDs (-1: not in the memo) */
+            int m0 = 0, m1 = 0, m2 = 0, m3 = 0, c0 = -1, c1 = -1, c2 = -1, c3 = -1;   /* search result per candidate */
+            {
+                const int4* __restrict__ mp = memoRow + cx * MEMO_N;
+#pragma unroll 1
+                for (int k = 0; k < MEMO_N; k++)
                 {
-                    /* the reference's CAND pass, straight from global memory: quad k measures neighbour k */
-                    typename Px<P>::Row4 fe[4], rr[4];
-#pragma unroll
-                    for (int y = 0; y < 4; y++)
-                        fe[y] = Px<P>::load_aligned(fencPlane + rowBase + 8 * cuX + y * stride);
-                    const int cmv = q == 0 ? nb0 : (q == 1 ? nb1 : (q == 2 ? nb2 : (q == 3 ? nb3 : 0)));
-                    fetch_qpel<P>(refPlane + rowBase + 8 * cuX, planeSize, stride, la_mv_x(cmv), la_mv_y(cmv), rr);
-                    const int cc = quad_sum(satd4x4_abs<P>(fe, rr)) >> 1;
-                    k0 = __shfl_sync(FULL_MASK, cc, 0); k1 = __shfl_sync(FULL_MASK, cc, 4);
-                    k2 = __shfl_sync(FULL_MASK, cc, 8); k3 = __shfl_sync(FULL_MASK, cc, 12);
-                    SSTAT_ADD(14, 1);
+                    const int4 e = mp[k];
+                    if (e.w < 0) break;                       /* entries are filled front to back */
+                    if (e.x == nb0) { k0 = e.y; m0 = e.z; c0 = e.w; }
+                    if (e.x == nb1) { k1 = e.y; m1 = e.z; c1 = e.w; }
+                    if (e.x == nb2) { k2 = e.y; m2 = e.z; c2 = e.w; }
+                    if (e.x == nb3) { k3 = e.y; m3 = e.z; c3 = e.w; }
                 }
             }
-            /* ---- the MVP, exactly as slicetype.cpp:2130-2150 ---- */
-            LaSearch s;
-            la_search_begin(s, cuX, cuY, W, H, bidir, numc, nb0, nb1, nb2, nb3);
-            la_upd_cand(s, k0, k1, k2, k3);
-            skipCost = s.skipCost;
-            const int mvp = la_pack_mv(s.mvpx, s.mvpy);
-            const int i = MEMO_FIND(mvp);
-            if (i >= 0) { outMv = MEMO_SEL(i, z); outCost = MEMO_SEL(i, w); }
-            else
+            /* no candidates: the MVP is zero and no SATD is needed; otherwise every candidate needs its SATD */
+            const bool miss = numc == 0 ? c0 < 0 : (k0 < 0 || (numc > 1 && k1 < 0) || (numc > 2 && k2 < 0) || (numc > 3 && k3 < 0));
+            int outMv = 0, outCost = 0;
+            if (!miss)
             {
-                /* nobody predicted this MVP: search it here, on the chain */
-                typename Px<P>::Row4 fe[4];
+                LaSearch s;
+                la_search_begin(s, cx, cuY, W, H, bidir, numc, nb0, nb1, nb2, nb3);
+                la_upd_cand(s, k0, k1, k2, k3);
+                const int mvp = la_pack_mv(s.mvpx, s.mvpy);
+                /* the MVP is one of the candidates (or zero when there is none, which nb0 = 0 stands for) */
+                const int rm = mvp == nb0 ? m0 : (mvp == nb1 ? m1 : (mvp == nb2 ? m2 : m3));
+                const int rc = mvp == nb0 ? c0 : (mvp == nb1 ? c1 : (mvp == nb2 ? c2 : c3));
+                s.outx = la_mv_x(rm); s.outy = la_mv_y(rm); s.outcost = rc;
+                la_finish_skip(s);
+                outMv = la_pack_mv(s.outx, s.outy); outCost = s.outcost;
+            }
+            /* ---- which lanes computed from true inputs only: the prefix up to the first wrong assumption / wait / miss ---- */
+            const int rightMv = __shfl_up_sync(FULL_MASK, outMv, 1);
+            const bool good = valid && avail && !miss && (lane == 0 || rightMv == r);
+            const unsigned gm = __ballot_sync(FULL_MASK, good);
+            const int n = gm == FULL_MASK ? 32 : __ffs(~gm) - 1;
+            if (n > 0)
+            {
+                if (lane < n)
+                {
+                    const unsigned long long word = HAND_TAG | (uint32_t)outMv;
+                    const int cuXY = cu + cuY * W;
+                    myHand[cu] = word;
+                    if (publishGlobal) myHandG[cu] = word;
+                    mvMirror[cuXY] = outMv;
+                    mcMirror[cuXY] = outCost;
+                    mvOut[cuXY] = outMv;
+                    mcOut[cuXY] = outCost;
+                }
+                prevMv = __shfl_sync(FULL_MASK, outMv, n - 1);
+                x0 -= n;
+                SSTAT_ADD(0, n);
+                SSTAT_ADD(15, n);
+                /* a short prefix means the estimate is poor here (or the row below is just ahead): go one CU at a time for a while */
+                if (n < 4) serialLeft = 8;
+                STRACE(cuY, x0 + n, 1, n);
+                continue;
+            }
+        }
+        else serialLeft--;
+
+        /* ================= serial step: the whole warp works on CU x0 ================= */
+        {
+            const int cuX = x0;
+            const long long tp0 = SSTAT_CLOCK();
+            int nb0 = 0, nb1 = 0, nb2 = 0, nb3 = 0, numc = 0;
+            if (cuX < W - 1) { nb0 = prevMv; numc = 1; }
+            if (!lastRow)
+            {
+                /* the row below runs right to left: its column cuX - 1 is published last */
+                int bl = 0, br = 0;
+                if (cuX > 0) bl = hand_wait(below + cuX - 1);
+                const int mb = hand_wait(below + cuX);
+                if (cuX < W - 1) br = hand_wait(below + cuX + 1);
+                if (numc == 0) nb0 = mb; else nb1 = mb;
+                numc++;
+                if (cuX > 0) { if (numc == 1) nb1 = bl; else nb2 = bl; numc++; }
+                if (cuX < W - 1) { if (numc == 2) nb2 = br; else nb3 = br; numc++; }
+            }
+            const long long tp1 = SSTAT_CLOCK();
+            const int4 e = memoRow[cuX * MEMO_N + (lane & (MEMO_N - 1))];     /* lane k (mod MEMO_N) holds entry k */
+            const int i0 = memo_find(e, nb0), i1 = memo_find(e, nb1), i2 = memo_find(e, nb2), i3 = memo_find(e, nb3);
+            int k0 = __shfl_sync(FULL_MASK, e.y, i0 & 31), k1 = __shfl_sync(FULL_MASK, e.y, i1 & 31);
+            int k2 = __shfl_sync(FULL_MASK, e.y, i2 & 31), k3 = __shfl_sync(FULL_MASK, e.y, i3 & 31);
+            /* when every neighbour carries the same vector v the first candidate wins the strict-< chain whatever the costs;
+             * its SATD only matters for the bidir skip rule, and only when v is zero (slicetype.cpp:2146-2149) */
+            const bool allEq = (numc < 2 || nb1 == nb0) && (numc < 3 || nb2 == nb0) && (numc < 4 || nb3 == nb0);
+            const bool ok = (allEq && !(nb0 == 0 && bidir && numc > 0)) ||
+                            ((numc < 1 || (i0 >= 0 && k0 >= 0)) && (numc < 2 || (i1 >= 0 && k1 >= 0)) && (numc < 3 || (i2 >= 0 && k2 >= 0)) && (numc < 4 || (i3 >= 0 && k3 >= 0)));
+            typename Px<P>::Row4 fe[4];
+            const long long tp2 = SSTAT_CLOCK();
+            if (!ok)
+            {
+                /* the reference's CAND pass, straight from global memory: quad k measures neighbour k */
+                typename Px<P>::Row4 rr[4];
 #pragma unroll
                 for (int y = 0; y < 4; y++)
                     fe[y] = Px<P>::load_aligned(fencPlane + rowBase + 8 * cuX + y * stride);
+                const int cmv = q == 0 ? nb0 : (q == 1 ? nb1 : (q == 2 ? nb2 : (q == 3 ? nb3 : 0)));
+                fetch_qpel<P>(refPlane + rowBase + 8 * cuX, planeSize, stride, la_mv_x(cmv), la_mv_y(cmv), rr);
+                const int cc = quad_sum(satd4x4_abs<P>(fe, rr)) >> 1;
+                k0 = __shfl_sync(FULL_MASK, cc, 0); k1 = __shfl_sync(FULL_MASK, cc, 4);
+                k2 = __shfl_sync(FULL_MASK, cc, 8); k3 = __shfl_sync(FULL_MASK, cc, 12);
+                SSTAT_ADD(14, 1);
+            }
+            /* ---- the MVP, exactly as slicetype.cpp:2130-2150 ---- */
+            const long long tp3 = SSTAT_CLOCK();
+            LaSearch s;
+            la_search_begin(s, cuX, cuY, W, H, bidir, numc, nb0, nb1, nb2, nb3);
+            la_upd_cand(s, k0, k1, k2, k3);
+            const int mvp = la_pack_mv(s.mvpx, s.mvpy);
+            const int im = memo_find(e, mvp);
+            const long long tp4 = SSTAT_CLOCK();
+            int rMv, rCost;
+            if (im >= 0) { rMv = __shfl_sync(FULL_MASK, e.z, im); rCost = __shfl_sync(FULL_MASK, e.w, im); }
+            else
+            {
+                /* nobody predicted this MVP: search it here, on the chain */
+                if (ok)
+                {
+#pragma unroll
+                    for (int y = 0; y < 4; y++)
+                        fe[y] = Px<P>::load_aligned(fencPlane + rowBase + 8 * cuX + y * stride);
+                }
+                const LaneGeom L = lane_geom(lane, stride);
                 int cs;
                 bool cok;
-                const long long tS0 = SSTAT_CLOCK();
                 search_mv<P>(refPlane + 8 * cuY * stride + 8 * cuX, refPlane + rowBase + 8 * cuX, win, planeSize, stride, fe, lut, L, lane, bx, by,
-                             cuX, cuY, W, H, mvp, outMv, outCost, cs, cok);
-                SSTAT_ADD(10, SSTAT_CLOCK() - tS0);
+                             cuX, cuY, W, H, mvp, rMv, rCost, cs, cok);
                 SSTAT_ADD(1, 1);
             }
-        }
-#undef MEMO_FIND
-#undef MEMO_SEL
-        /* bidir-only zero-MV skip shortcut (slicetype.cpp:2155-2159) */
-        if (skipCost < 64 && skipCost < outCost && bidir) { outCost = skipCost; outMv = 0; }
-
-        const int mvPacked = outMv;
-        SSTAT_ADD(13, SSTAT_CLOCK() - tCu0);
-        prevMv = mvPacked;
-        if (lane == 0)
-        {
-            const unsigned long long word = HAND_TAG | (uint32_t)mvPacked;
-            const int cuXY = cuX + cuY * W;
-            myHand[cuX] = word;
-            if (publishGlobal) myHandG[cuX] = word;
-            mvMirror[cuXY] = mvPacked;
-            mcMirror[cuXY] = outCost;
-            mvOut[cuXY] = mvPacked;
-            mcOut[cuXY] = outCost;
+            const long long tp5 = SSTAT_CLOCK();
+            SSTAT_ADD(20, tp1 - tp0); SSTAT_ADD(21, tp2 - tp1); SSTAT_ADD(22, tp3 - tp2); SSTAT_ADD(23, tp4 - tp3); SSTAT_ADD(24, tp5 - tp4);
+            if (!ok) { SSTAT_ADD(25, tp3 - tp2); SSTAT_ADD(26, 1); }
+            s.outx = la_mv_x(rMv); s.outy = la_mv_y(rMv); s.outcost = rCost;
+            la_finish_skip(s);
+            const int mvPacked = la_pack_mv(s.outx, s.outy);
+            prevMv = mvPacked;
+            if (lane == 0)
+            {
+                const unsigned long long word = HAND_TAG | (uint32_t)mvPacked;
+                const int cuXY = cuX + cuY * W;
+                myHand[cuX] = word;
+                if (publishGlobal) myHandG[cuX] = word;
+                mvMirror[cuXY] = mvPacked;
+                mcMirror[cuXY] = s.outcost;
+                mvOut[cuXY] = mvPacked;
+                mcOut[cuXY] = s.outcost;
+            }
+            if (cuX > 0)
+            {
+                /* pull what the next CU of the chain is most likely to need into L1 while the result is being published:
+                 * its source block and the 13-row windows of the four planes around this CU's MV */
+                const int prow = lane & 15, pplane = lane >> 4;
+                const P* w = refPlane + (8 * cuY + (la_mv_y(mvPacked) >> 2) - 2 + prow) * stride + 8 * (cuX - 1) + (la_mv_x(mvPacked) >> 2) - 4;
+                if (prow < WIN_H)
+                {
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(w + pplane * planeSize));
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(w + pplane * planeSize + 20));
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(w + (pplane + 2) * planeSize));
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(w + (pplane + 2) * planeSize + 20));
+                }
+                if (lane < 8)
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(fencPlane + (8 * cuY + lane) * stride + 8 * (cuX - 1)));
+            }
+            x0--;
+            SSTAT_ADD(0, 1);
+            SSTAT_ADD(17, 1);
+            STRACE(cuY, x0 + 1, ok ? (im >= 0 ? 2 : 4) : (im >= 0 ? 3 : 5), 1);
         }
     }
 }
