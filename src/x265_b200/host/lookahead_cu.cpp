@@ -65,7 +65,13 @@ void Lookahead::mvcostTable(int bitDepth, uint16_t* out, int* lambdaInt)
     }
 }
 
-Lookahead::Lookahead() : m_ctx(NULL), m_mvcost(NULL), m_lambda(1), m_resident(false) { m_error[0] = 0; memset(&m_param, 0, sizeof(m_param)); }
+Lookahead::Lookahead() : m_ctx(NULL), m_mvcost(NULL), m_lambda(1), m_resident(false), m_lookAhead(true), m_versionCounter(0)
+{
+    m_error[0] = 0;
+    memset(&m_param, 0, sizeof(m_param));
+    memset(m_specStats, 0, sizeof(m_specStats));
+    if (const char* e = getenv("X265CU_LOOKAHEAD_CACHE")) m_lookAhead = atoi(e) != 0;
+}
 Lookahead::~Lookahead() { destroy(); }
 
 /* Lookahead::Lookahead + Lookahead::create, encoder/slicetype.cpp:490-591 */
@@ -125,6 +131,9 @@ bool Lookahead::create(const Param& p)
 
 void Lookahead::destroy()
 {
+    if (m_ctx && getenv("X265CU_LOOKAHEAD_STATS"))
+        fprintf(stderr, "look-ahead estimate cache: %lld launched ahead, %lld handed out, %lld requests computed on demand, %lld requests\n",
+                (long long)m_specStats[0], (long long)m_specStats[1], (long long)m_specStats[2], (long long)m_specStats[3]);
     if (m_ctx) { x265cu_close(m_ctx); m_ctx = NULL; }
     free(m_mvcost); m_mvcost = NULL;
 }
@@ -178,9 +187,21 @@ Lowres* Lookahead::allocLowres()
     return l;
 }
 
+/* a frame is being re-initialised or released: nothing computed ahead from it may survive */
+void Lookahead::forgetFrame(Lowres* l)
+{
+    std::map<int, Lowres*>::iterator it = m_byPoc.find(l->frameNum);
+    if (it != m_byPoc.end() && it->second == l) m_byPoc.erase(it);
+    for (size_t i = 0; i < m_spec.size();)
+        if (m_spec[i].fenc == l || m_spec[i].ref0 == l || m_spec[i].ref1 == l) { m_spec[i] = m_spec.back(); m_spec.pop_back(); }
+        else i++;
+    l->ready = false;
+}
+
 void Lookahead::freeLowres(Lowres* l)
 {
     if (!l) return;
+    forgetFrame(l);
     m_freeSlots.push_back(l->slot);
     x265cu_host_unregister(l->arena);
     free(l->arena);
@@ -190,6 +211,8 @@ void Lookahead::freeLowres(Lowres* l)
 /* Lowres::init, common/lowres.cpp:128-165 */
 void Lookahead::lowresReset(Lowres& l, int poc)
 {
+    forgetFrame(&l);
+    memset(l.mvVersion, 0, sizeof(l.mvVersion));
     l.frameNum = poc;
     memset(l.costEst, -1, sizeof(l.costEst));
     memset(l.weightedCostDelta, 0, sizeof(l.weightedCostDelta));
@@ -373,7 +396,10 @@ bool Lookahead::preLookahead(Lowres& l, const void* y, intptr_t yStride, const v
         else
             x265cu_frame_set_invqscale(m_ctx, l.slot, NULL);
     }
-    return lowresIntraEstimate(l);
+    if (!lowresIntraEstimate(l)) return false;
+    l.ready = true;
+    m_byPoc[poc] = &l;
+    return true;
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -390,25 +416,149 @@ void CostEstimateGroup::add(int p0, int p1, int b)
 
 bool CostEstimateGroup::finishBatch()
 {
-    bool ok = runEstimates(m_estimates, m_jobTotal, true);
+    std::vector<EstReq> reqs((size_t)m_jobTotal);
+    for (int i = 0; i < m_jobTotal; i++)
+    {
+        const Estimate& e = m_estimates[i];
+        EstReq r = { m_frames[e.b], m_frames[e.p0], m_frames[e.p1], e.b - e.p0, e.p1 - e.b, false };
+        reqs[i] = r;
+    }
+    bool ok = m_jobTotal ? runEstimates(&reqs[0], m_jobTotal, true) : true;
+    if (m_jobTotal)
+    {
+        /* a batch closes the run of one-by-one estimates: what was computed ahead and not asked for is dropped,
+         * the run becomes the pattern the next one is predicted from */
+        Lookahead& la = m_lookahead;
+        la.m_spec.clear();
+        if (!la.m_episode.empty())
+        {
+            la.m_history.push_back(la.m_episode);
+            if (la.m_history.size() > 3) la.m_history.erase(la.m_history.begin());
+            la.m_episode.clear();
+        }
+    }
     m_jobTotal = 0;
     return ok;
 }
 
+/* hand out an estimate that was computed ahead, if the request is exactly that computation */
+bool CostEstimateGroup::takeAhead(Lowres* fenc, Lowres* ref0, Lowres* ref1, int d0, int d1)
+{
+    Lookahead& la = m_lookahead;
+    const int n = la.m_cuCount, rows = la.m_8x8Height;
+    for (size_t i = 0; i < la.m_spec.size(); i++)
+    {
+        SpecEstimate& e = la.m_spec[i];
+        if (e.fenc != fenc || e.ref0 != ref0 || e.ref1 != ref1 || e.d0 != d0 || e.d1 != d1) continue;
+        if (e.fencNum != fenc->frameNum || e.ref0Num != ref0->frameNum || e.ref1Num != ref1->frameNum) continue;
+        const int s0 = fenc->lowresMvs[0][d0 - 1][0].x == 0x7FFF;
+        const int s1 = d1 > 0 && fenc->lowresMvs[1][d1 - 1][0].x == 0x7FFF;
+        if (s0 != e.doSearch[0] || s1 != e.doSearch[1]) continue;
+        /* the MV fields it consumed must be the ones that are official now */
+        if (!s0 && fenc->mvVersion[0][d0 - 1] != e.usedVersion[0]) continue;
+        if (d1 > 0 && !s1 && fenc->mvVersion[1][d1 - 1] != e.usedVersion[1]) continue;
+
+        if (!la.m_resident)
+        {
+            for (int l = 0; l < 2; l++)
+                if (e.doSearch[l])
+                {
+                    const int d = l ? d1 : d0;
+                    memcpy(fenc->lowresMvs[l][d - 1], &e.mvs[l][0], (size_t)n * 4);
+                    memcpy(fenc->lowresMvCosts[l][d - 1], &e.mvCosts[l][0], (size_t)n * 4);
+                }
+            memcpy(fenc->lowresCosts[d0][d1], &e.lowresCosts[0], (size_t)n * 2);
+            memcpy(fenc->rowSatds[d0][d1], &e.rowSatds[0], (size_t)rows * 4);
+        }
+        else
+        {
+            if (e.doSearch[0]) fenc->lowresMvs[0][d0 - 1][0].x = 0;
+            if (e.doSearch[1]) fenc->lowresMvs[1][d1 - 1][0].x = 0;
+            fenc->rowSatds[d0][d1][0] = 0;
+        }
+        for (int l = 0; l < 2; l++)
+            if (e.doSearch[l]) fenc->mvVersion[l][(l ? d1 : d0) - 1] = e.newVersion[l];
+        fenc->costEst[d0][d1] = e.res.costEst;
+        fenc->costEstAq[d0][d1] = e.res.costEstAq;
+        if (d1 == 0) fenc->intraMbs[d0] += e.res.intraMbs;
+        fenc->weightedRef[d0].present = 0;
+        if (e.wref.present) { fenc->weightedRef[d0] = e.wref; fenc->weightedCostDelta[d0] = e.wdelta; }
+        la.m_spec[i] = la.m_spec.back();
+        la.m_spec.pop_back();
+        la.m_specStats[1]++;
+        return true;
+    }
+    return false;
+}
+
 int64_t CostEstimateGroup::singleCost(int p0, int p1, int b, bool intraPenalty)
 {
+    Lookahead& la = m_lookahead;
     Lowres* fenc = m_frames[b];
+    const int d0 = b - p0, d1 = p1 - b;
     int64_t score;
-    if (fenc->costEst[b - p0][p1 - b] >= 0 && fenc->rowSatds[b - p0][p1 - b][0] != -1)
-        score = fenc->costEst[b - p0][p1 - b];
+    if (fenc->costEst[d0][d1] >= 0 && fenc->rowSatds[d0][d1][0] != -1)
+        score = fenc->costEst[d0][d1];
     else
     {
-        Estimate e = { p0, b, p1 };
-        if (!runEstimates(&e, 1, false)) return -1;
-        score = fenc->costEst[b - p0][p1 - b];
+        la.m_specStats[3]++;
+        const Lookahead::Request rq = { m_frames[p0]->frameNum, fenc->frameNum, m_frames[p1]->frameNum };
+        if (!takeAhead(fenc, m_frames[p0], m_frames[p1], d0, d1))
+        {
+            std::vector<EstReq> reqs;
+            EstReq r0 = { fenc, m_frames[p0], m_frames[p1], d0, d1, false };
+            reqs.push_back(r0);
+            /* The request was not foreseen: look for the same kind of request (same distances) in the recent history,
+             * shifted in time, and take the requests that followed it then as the ones about to be asked for now.
+             * Among the alignments whose predicted frames all exist, the one predicting most wins. */
+            if (la.m_lookAhead)
+            {
+                std::vector<EstReq> best;
+                for (int h = (int)la.m_history.size(); h >= 0; h--)
+                {
+                    const std::vector<Lookahead::Request>& ep = h == (int)la.m_history.size() ? la.m_episode : la.m_history[h];
+                    for (size_t k = 0; k < ep.size(); k++)
+                    {
+                        const int shift = rq.b - ep[k].b;
+                        if (shift == 0 || ep[k].b - ep[k].p0 != d0 || ep[k].p1 - ep[k].b != d1) continue;
+                        std::vector<EstReq> cand;
+                        bool valid = true;
+                        for (size_t i = k + 1; i < ep.size() && valid; i++)
+                        {
+                            const Lookahead::Request& q = ep[i];
+                            std::map<int, Lowres*>::iterator ib = la.m_byPoc.find(q.b + shift), i0 = la.m_byPoc.find(q.p0 + shift), i1 = la.m_byPoc.find(q.p1 + shift);
+                            if (ib == la.m_byPoc.end() || i0 == la.m_byPoc.end() || i1 == la.m_byPoc.end()) { valid = false; break; }
+                            Lowres *qb = ib->second, *q0 = i0->second, *q1 = i1->second;
+                            const int e0 = q.b - q.p0, e1 = q.p1 - q.b;
+                            if (!qb->ready || !q0->ready || !q1->ready) { valid = false; break; }
+                            if (e0 < 1 || e0 > la.m_param.bframes + 1 || e1 < 0 || e1 > la.m_param.bframes + 1) continue;
+                            if (qb->costEst[e0][e1] >= 0 && qb->rowSatds[e0][e1][0] != -1) continue;      /* already known */
+                            bool dup = qb == fenc && e0 == d0 && e1 == d1;
+                            for (size_t c = 0; c < cand.size(); c++)
+                                dup = dup || (cand[c].fenc == qb && cand[c].d0 == e0 && cand[c].d1 == e1);
+                            for (size_t c = 0; c < la.m_spec.size(); c++)      /* still pending from an earlier prediction */
+                                dup = dup || (la.m_spec[c].fenc == qb && la.m_spec[c].d0 == e0 && la.m_spec[c].d1 == e1);
+                            if (dup) continue;
+                            EstReq r = { qb, q0, q1, e0, e1, true };
+                            cand.push_back(r);
+                        }
+                        if (valid && cand.size() > best.size()) best.swap(cand);
+                    }
+                }
+                reqs.insert(reqs.end(), best.begin(), best.end());
+            }
+            if (getenv("X265CU_LOOKAHEAD_DEBUG"))
+                fprintf(stderr, "singleCost (%d,%d,%d): on demand, %d ahead, episode %d prev %d\n", rq.p0, rq.b, rq.p1, (int)reqs.size() - 1, (int)la.m_episode.size(), (int)la.m_history.size());
+            if (!runEstimates(&reqs[0], (int)reqs.size(), false)) return -1;
+            la.m_specStats[2]++;
+        }
+        else if (getenv("X265CU_LOOKAHEAD_DEBUG"))
+            fprintf(stderr, "singleCost (%d,%d,%d): handed out\n", rq.p0, rq.b, rq.p1);
+        la.m_episode.push_back(rq);
+        score = fenc->costEst[d0][d1];
     }
     if (intraPenalty)
-        score += score * fenc->intraMbs[b - p0] / (m_lookahead.ncu() * 8);
+        score += score * fenc->intraMbs[d0] / (m_lookahead.ncu() * 8);
     return score;
 }
 
@@ -449,59 +599,131 @@ WeightGuess weightGuess(const Lowres& fenc, const Lowres& ref, int depth)
 }
 } // namespace
 
-bool CostEstimateGroup::runEstimates(const Estimate* est, int n, bool batchMode)
+/* est[0..n): estimates to compute in ONE x265cu_estimate_batch call.  Entries flagged `ahead` are computed into the
+ * look-ahead cache instead of the frames' arrays; they may consume MV fields that an earlier entry of the same
+ * call produces (the cost kernel of a batch runs after all of its searches). */
+bool CostEstimateGroup::runEstimates(const EstReq* est, int n, bool batchMode)
 {
     Lookahead& la = m_lookahead;
     const Param& param = la.m_param;
+    const int nCU = la.m_cuCount, rows = la.m_8x8Height;
     std::vector<x265cu_job> jobs;
     std::vector<int> jobOf;                 /* index into est[] */
     std::vector<WeightGuess> guesses;
     std::vector<x265cu_weight_item> witems;
     std::vector<int> wjob;                  /* job index of each pair of weight items */
+    std::vector<WeightParam> wref;          /* per job: the weight decision for the L0 search */
+    std::vector<double> wdelta;
+    std::vector<int> specOf;                /* per job: index into la.m_spec, or -1 */
+    /* MV fields this call produces: (frame, list, distance) -> version */
+    struct Produced { Lowres* f; int l, d; uint64_t ver; };
+    std::vector<Produced> produced;
+    jobs.reserve((size_t)n);
+    const size_t specBase = la.m_spec.size();
+    la.m_spec.reserve(specBase + (size_t)n);   /* destination pointers into the entries must stay valid */
 
     for (int i = 0; i < n; i++)
     {
-        const int p0 = est[i].p0, p1 = est[i].p1, b = est[i].b;
-        Lowres* fenc = m_frames[b];
-        const int d0 = b - p0, d1 = p1 - b;
+        Lowres *fenc = est[i].fenc, *ref0 = est[i].ref0, *ref1 = est[i].ref1;
+        const int d0 = est[i].d0, d1 = est[i].d1;
         if (fenc->costEst[d0][d1] >= 0 && fenc->rowSatds[d0][d1][0] != -1)
             continue;                       /* cached (estimateFrameCost :1982) */
         x265cu_job j;
         memset(&j, 0, sizeof(j));
-        j.fenc = fenc->slot; j.ref0 = m_frames[p0]->slot; j.ref1 = m_frames[p1]->slot;
+        j.fenc = fenc->slot; j.ref0 = ref0->slot; j.ref1 = ref1->slot;
         j.d0 = d0; j.d1 = d1;
-        j.doSearch[0] = p0 < b && fenc->lowresMvs[0][d0 - 1][0].x == 0x7FFF;
-        j.doSearch[1] = p1 > b && fenc->lowresMvs[1][d1 - 1][0].x == 0x7FFF;
+        j.doSearch[0] = fenc->lowresMvs[0][d0 - 1][0].x == 0x7FFF;
+        j.doSearch[1] = d1 > 0 && fenc->lowresMvs[1][d1 - 1][0].x == 0x7FFF;
         j.sliced = !batchMode;
-        fenc->weightedRef[d0].present = 0;
+        uint64_t usedVersion[2] = { fenc->mvVersion[0][d0 - 1], d1 > 0 ? fenc->mvVersion[1][d1 - 1] : 0 };
+        uint64_t newVersion[2] = { 0, 0 };
+        bool usable = true;
+        for (int l = 0; l < 2; l++)
+        {
+            const int d = l ? d1 : d0;
+            if (!j.doSearch[l]) continue;
+            /* a field an earlier estimate of this call is already searching: consume that one (only look-ahead entries
+             * can meet this; the reference's own batches are independent) */
+            for (size_t k = 0; k < produced.size(); k++)
+                if (produced[k].f == fenc && produced[k].l == l && produced[k].d == d)
+                {
+                    if (!est[i].ahead) usable = false;
+                    j.doSearch[l] = 0;
+                    usedVersion[l] = produced[k].ver;
+                }
+            if (j.doSearch[l])
+            {
+                newVersion[l] = ++la.m_versionCounter;
+                Produced pr = { fenc, l, d, newVersion[l] };
+                produced.push_back(pr);
+            }
+        }
+        if (!usable) { snprintf(la.m_error, sizeof(la.m_error), "runEstimates: dependent estimates in one batch"); return false; }
+        WeightParam noWeight = { 0, 0, 0, 0 };
         if (param.bEnableWeightedPred && j.doSearch[0])
         {
-            WeightGuess g = weightGuess(*fenc, *m_frames[p0], param.bitDepth);
+            WeightGuess g = weightGuess(*fenc, *ref0, param.bitDepth);
             if (!g.skip)
             {
-                x265cu_weight_item w0 = { fenc->slot, m_frames[p0]->slot, 0, 0, 0, 0 };
-                x265cu_weight_item w1 = { fenc->slot, m_frames[p0]->slot, 1, g.curScale, g.mindenom, g.curOffset };
+                x265cu_weight_item w0 = { fenc->slot, ref0->slot, 0, 0, 0, 0 };
+                x265cu_weight_item w1 = { fenc->slot, ref0->slot, 1, g.curScale, g.mindenom, g.curOffset };
                 witems.push_back(w0); witems.push_back(w1);
                 wjob.push_back((int)jobs.size());
                 guesses.push_back(g);
             }
         }
-        for (int l = 0; l < 2; l++)
+        int specIdx = -1;
+        if (est[i].ahead)
         {
-            int d = l ? d1 : d0;
-            if (j.doSearch[l] && !la.m_resident)
+            SpecEstimate e;
+            e.fenc = fenc; e.ref0 = ref0; e.ref1 = ref1;
+            e.fencNum = fenc->frameNum; e.ref0Num = ref0->frameNum; e.ref1Num = ref1->frameNum;
+            e.d0 = d0; e.d1 = d1;
+            e.doSearch[0] = j.doSearch[0]; e.doSearch[1] = j.doSearch[1];
+            e.usedVersion[0] = usedVersion[0]; e.usedVersion[1] = usedVersion[1];
+            e.newVersion[0] = newVersion[0]; e.newVersion[1] = newVersion[1];
+            e.wref = noWeight; e.wdelta = 0;
+            memset(&e.res, 0, sizeof(e.res));
+            la.m_spec.push_back(e);
+            specIdx = (int)la.m_spec.size() - 1;
+            SpecEstimate& se = la.m_spec[specIdx];
+            if (!la.m_resident)
             {
-                j.mvs[l] = fenc->lowresMvs[l][d - 1];
-                j.mvCosts[l] = fenc->lowresMvCosts[l][d - 1];
+                for (int l = 0; l < 2; l++)
+                    if (j.doSearch[l])
+                    {
+                        se.mvs[l].resize((size_t)nCU * 4); se.mvCosts[l].resize((size_t)nCU * 4);
+                        j.mvs[l] = &se.mvs[l][0];
+                        j.mvCosts[l] = (int32_t*)&se.mvCosts[l][0];
+                    }
+                se.lowresCosts.resize((size_t)nCU * 2); se.rowSatds.resize((size_t)rows * 4);
+                j.lowresCosts = (uint16_t*)&se.lowresCosts[0];
+                j.rowSatds = (int32_t*)&se.rowSatds[0];
             }
         }
-        if (!la.m_resident)
+        else
         {
-            j.lowresCosts = fenc->lowresCosts[d0][d1];
-            j.rowSatds = fenc->rowSatds[d0][d1];
+            for (int l = 0; l < 2; l++)
+            {
+                int d = l ? d1 : d0;
+                if (j.doSearch[l] && !la.m_resident)
+                {
+                    j.mvs[l] = fenc->lowresMvs[l][d - 1];
+                    j.mvCosts[l] = fenc->lowresMvCosts[l][d - 1];
+                }
+                if (j.doSearch[l]) fenc->mvVersion[l][d - 1] = newVersion[l];
+            }
+            if (!la.m_resident)
+            {
+                j.lowresCosts = fenc->lowresCosts[d0][d1];
+                j.rowSatds = fenc->rowSatds[d0][d1];
+            }
         }
         jobs.push_back(j);
         jobOf.push_back(i);
+        wref.push_back(noWeight);
+        wdelta.push_back(0);
+        specOf.push_back(specIdx);
     }
     if (jobs.empty()) return true;
 
@@ -515,7 +737,6 @@ bool CostEstimateGroup::runEstimates(const Estimate* est, int n, bool batchMode)
         {
             x265cu_job& j = jobs[wjob[k]];
             const WeightGuess& g = guesses[k];
-            Lowres* fenc = m_frames[est[jobOf[wjob[k]]].b];
             unsigned int origscore = costs[2 * k], minscore = origscore;
             if (!minscore) continue;
             int minscale = g.minscale, mindenom = g.mindenom, minoff = 0, found = 0;
@@ -524,22 +745,36 @@ bool CostEstimateGroup::runEstimates(const Estimate* est, int n, bool batchMode)
             while (mindenom > 0 && !(minscale & 1)) { mindenom--; minscale >>= 1; }
             if (!found || (minscale == 1 << mindenom && minoff == 0) || (float)minscore / origscore > 0.998f)
                 continue;
-            fenc->weightedCostDelta[j.d0] = minscore / origscore;     /* unsigned integer division, as in the reference */
-            fenc->weightedRef[j.d0].present = 1;
-            fenc->weightedRef[j.d0].scale = minscale;
-            fenc->weightedRef[j.d0].denom = mindenom;
-            fenc->weightedRef[j.d0].offset = minoff;
+            wdelta[wjob[k]] = minscore / origscore;     /* unsigned integer division, as in the reference */
+            WeightParam wp = { 1, minscale, mindenom, minoff };
+            wref[wjob[k]] = wp;
             j.weighted = 1; j.wScale = minscale; j.wDenom = mindenom; j.wOffset = minoff;
         }
     }
 
     std::vector<x265cu_job_result> res(jobs.size());
     int r = x265cu_estimate_batch(la.m_ctx, (int)jobs.size(), &jobs[0], &res[0]);
-    if (r) { snprintf(la.m_error, sizeof(la.m_error), "x265cu_estimate_batch: %s", x265cu_last_error(la.m_ctx)); return false; }
+    if (r)
+    {
+        la.m_spec.resize(specBase);
+        snprintf(la.m_error, sizeof(la.m_error), "x265cu_estimate_batch: %s", x265cu_last_error(la.m_ctx));
+        return false;
+    }
     for (size_t k = 0; k < jobs.size(); k++)
     {
-        Lowres* fenc = m_frames[est[jobOf[k]].b];
         const int d0 = jobs[k].d0, d1 = jobs[k].d1;
+        if (specOf[k] >= 0)
+        {
+            SpecEstimate& e = la.m_spec[specOf[k]];
+            e.res = res[k];
+            e.wref = wref[k];
+            e.wdelta = wdelta[k];
+            la.m_specStats[0]++;
+            continue;
+        }
+        Lowres* fenc = est[jobOf[k]].fenc;
+        fenc->weightedRef[d0].present = 0;
+        if (wref[k].present) { fenc->weightedRef[d0] = wref[k]; fenc->weightedCostDelta[d0] = wdelta[k]; }
         fenc->costEst[d0][d1] = res[k].costEst;
         fenc->costEstAq[d0][d1] = res[k].costEstAq;
         if (d1 == 0)

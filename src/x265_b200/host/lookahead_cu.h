@@ -20,6 +20,7 @@
 
 #include <stdint.h>
 #include <stddef.h>
+#include <map>
 #include <vector>
 
 #include "../../../include/x265cu.h"
@@ -82,6 +83,30 @@ struct Lowres
     WeightParam weightedRef[BFRAME_MAX + 2];   /* reference keeps ReferencePlanes here; we keep the weight */
     uint8_t* arena;          /* one pinned allocation holding every array above */
     size_t arenaBytes;
+    /* bookkeeping of the look-ahead estimate cache (Lookahead::m_spec): the frame went through preLookahead();
+     * which search produced lowresMvs[l][d] (0: none yet) */
+    bool ready;
+    uint64_t mvVersion[2][BFRAME_MAX + 1];
+};
+
+/* One estimate computed AHEAD of its request (see CostEstimateGroup::singleCost).  The reference asks for
+ * the non-batch estimates of a slicetypeDecide call one by one, each a GPU round trip with a mostly idle
+ * GPU; their order repeats from mini-GOP to mini-GOP, so the estimates that are about to be asked for are
+ * launched together with the first one.  An entry is only ever handed out when the request that arrives
+ * is EXACTLY the computation that was done (same frames, same bDoSearch[] state, same MV fields consumed):
+ * a function of identical inputs, hence bit-identical to computing it on request. */
+struct SpecEstimate
+{
+    Lowres *fenc, *ref0, *ref1;
+    int fencNum, ref0Num, ref1Num;       /* frameNum of the three at compute time (slots are recycled) */
+    int d0, d1;
+    int doSearch[2];
+    uint64_t usedVersion[2];             /* version of lowresMvs[l][d] consumed (lists not searched by this estimate) */
+    uint64_t newVersion[2];              /* version of the fields this estimate's searches produced */
+    x265cu_job_result res;
+    WeightParam wref;
+    double wdelta;
+    std::vector<uint8_t> mvs[2], mvCosts[2], lowresCosts, rowSatds;   /* host copies (not in resident mode) */
 };
 
 class Lookahead
@@ -98,6 +123,15 @@ public:
     char m_error[512];
     std::vector<int> m_freeSlots;   /* device mirror slots not bound to a Lowres */
     bool m_resident;         /* inputs are device pointers and result arrays stay in HBM (only sums return) */
+    /* look-ahead estimate cache */
+    bool m_lookAhead;                          /* on by default; X265CU_LOOKAHEAD_CACHE=0 turns it off (experiments) */
+    std::map<int, Lowres*> m_byPoc;            /* frames that went through preLookahead(), by frameNum */
+    std::vector<SpecEstimate> m_spec;
+    struct Request { int p0, b, p1; };         /* frameNums */
+    std::vector<Request> m_episode;            /* non-batch estimates asked for since the last batch ... */
+    std::vector<std::vector<Request> > m_history;   /* ... and the runs before it (most recent last) */
+    uint64_t m_versionCounter;
+    int64_t m_specStats[4];                    /* launched ahead, handed out, requests computed alone, requests total */
 
     Lookahead();
     ~Lookahead();
@@ -106,6 +140,7 @@ public:
 
     Lowres* allocLowres();                 /* Lowres::create */
     void freeLowres(Lowres* l);
+    void forgetFrame(Lowres* l);            /* drop everything the look-ahead estimate cache derived from this frame */
     /* Lowres::init (lowres.cpp:128-165); luma = PicYuv::m_picOrg[0] padded as copyFromPicture does */
     bool lowresInit(Lowres& l, const void* luma, intptr_t stride, int poc, bool copyPlanesBack);
     /* LookaheadTLD::calcAdaptiveQuantFrame; planes padded like PicYuv */
@@ -139,7 +174,9 @@ public:
     int64_t singleCost(int p0, int p1, int b, bool intraPenalty = false);
 
 protected:
-    bool runEstimates(const Estimate* e, int n, bool batchMode);
+    struct EstReq { Lowres *fenc, *ref0, *ref1; int d0, d1; bool ahead; };
+    bool runEstimates(const EstReq* e, int n, bool batchMode);
+    bool takeAhead(Lowres* fenc, Lowres* ref0, Lowres* ref1, int d0, int d1);
 };
 
 } // namespace x265cu
