@@ -176,7 +176,12 @@ class Runner:
         self.calls = []
         for e in trace.events:
             if e[0] == "P":
-                self.calls.append(("P", e[1]["poc"]))
+                # consecutive pre-lookahead frames are one PreLookaheadGroup list (slicetype.cpp:831-856)
+                t = e[1]["poc"]
+                if self.calls and self.calls[-1][0] == "P":
+                    self.calls[-1][1].append(t)
+                else:
+                    self.calls.append(("P", [t]))
             elif e[0] in ("J", "B"):
                 jobs = [e[1]] if e[0] == "J" else e[1]
                 if not jobs:
@@ -186,6 +191,8 @@ class Runner:
                 fr = [self.frames.get(p) for p in range(lo, hi + 1)]
                 tr = [(j["p0"] - lo, j["p1"] - lo, j["b"] - lo) for j in jobs]
                 self.calls.append(("E", la.prepare_estimate(fr, tr), e[0] == "B"))
+        self.calls = [("P", c[1], la.prepare_pre_lookahead_batch([(self.frames[t],) + tuple(self.inputs[t]) + (t,) for t in c[1]])) if c[0] == "P" else c
+                      for c in self.calls]
         self.units = sum(j["s0"] + j["s1"] for j in trace.jobs())
         self.njobs = sum(1 for _ in trace.jobs())
 
@@ -193,9 +200,7 @@ class Runner:
         la = self.la
         for c in self.calls:
             if c[0] == "P":
-                t = c[1]
-                y, ys, u, v, cs = self.inputs[t]
-                la.pre_lookahead_ptr(self.frames[t], y, ys, u, v, cs, t, True)
+                la.pre_lookahead_batch_prepared(c[2], True)
             else:
                 la.estimate_prepared(c[1], c[2])
         la.sync()          # every output, including the asynchronous plane copy-backs, is on the host

@@ -85,20 +85,37 @@ class CuReplay:
             self.mismatches.append((what, got, want))
 
     def pre(self, e):
+        self.pre_list([e])
+
+    def pre_list(self, es):
+        """one PreLookaheadGroup list: a single frame goes through preLookahead(), several through preLookaheadBatch()"""
         cfg = self.cfg
-        poc = e["poc"]
-        for old in [p for p in self.frames if p < poc - self.keep]:
-            self.free.append(self.frames.pop(old))
-        f = self.free.pop() if self.free else self.la.frame_alloc()
-        if self.clip is not None:
-            y, u, v = self.clip.frames[poc]
+        items, keep = [], []
+        for e in es:
+            poc = e["poc"]
+            for old in [p for p in self.frames if p < min(x["poc"] for x in es) - self.keep]:
+                self.free.append(self.frames.pop(old))
+            f = self.free.pop() if self.free else self.la.frame_alloc()
+            if self.clip is not None:
+                y, u, v = self.clip.frames[poc]
+            else:
+                y, u, v = po.synth_padded(self.lib, cfg["depth"], cfg["width"], cfg["height"], poc, cfg["nframes"], cfg["seed"])
+            keep.append((y, u, v))
+            items.append((f, y.ctypes.data, y.strides[0] // y.itemsize, u.ctypes.data, v.ctypes.data, u.strides[0] // u.itemsize, poc))
+            self.frames[poc] = f
+            self.nframes += 1
+        if len(es) == 1:
+            self.la.pre_lookahead(items[0][0], keep[0][0], keep[0][1], keep[0][2], es[0]["poc"], self.planes_back)
         else:
-            y, u, v = po.synth_padded(self.lib, cfg["depth"], cfg["width"], cfg["height"], poc, cfg["nframes"], cfg["seed"])
-        self.la.pre_lookahead(f, y, u, v, poc, self.planes_back)
-        self.frames[poc] = f
-        self.nframes += 1
+            self.la.pre_lookahead_batch_prepared(self.la.prepare_pre_lookahead_batch(items), self.planes_back)
         if not self.check:
             return
+        for e, it in zip(es, items):
+            self._check_pre(e, it[0])
+
+    def _check_pre(self, e, f):
+        cfg = self.cfg
+        poc = e["poc"]
         la, tag = self.la, "P%d." % poc
         if self.planes_back:
             la.sync()      # the padded planes come back behind the compute stream
@@ -150,10 +167,19 @@ class CuReplay:
 
     def run(self, max_events=None, stop_on_mismatch=False):
         n = 0
+        pend = []
         for e in self.t.events:
             if e[0] == "P":
-                self.pre(e[1])
-            elif e[0] == "J":
+                pend.append(e[1])     # consecutive frames form one PreLookaheadGroup list
+                n += 1
+                if not (max_events and n >= max_events):
+                    continue
+            if pend:
+                self.pre_list(pend)
+                pend = []
+            if e[0] == "P":
+                break
+            if e[0] == "J":
                 self._run_jobs([e[1]], False)
             elif e[0] == "B" and e[1]:
                 self._run_jobs(e[1], True)
@@ -162,6 +188,8 @@ class CuReplay:
                 break
             if stop_on_mismatch and self.mismatches:
                 break
+        if pend:
+            self.pre_list(pend)
         return self.mismatches
 
 

@@ -115,6 +115,21 @@ int x265cu_frame_var(x265cu_ctx* ctx, const void* y, intptr_t yStride, const voi
 int x265cu_frame_init_var(x265cu_ctx* ctx, int slot, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride,
                           int planesAreDevice, void* planesOut, uint32_t* energy, uint64_t sums[6]);
 
+/* ---- the same for a LIST of frames, as PreLookaheadGroup::processTasks receives them (slicetype.cpp:831-856:
+ * m_preframes[0..m_jobTotal)): every upload and kernel of the list is enqueued back to back and the host waits
+ * once.  Fields as the arguments of x265cu_frame_init_var; sums points at 6 values. */
+typedef struct x265cu_frame_in
+{
+    int slot;
+    const void* y; intptr_t yStride;
+    const void* u; const void* v; intptr_t cStride;
+    int planesAreDevice;
+    void* planesOut;
+    uint32_t* energy;
+    uint64_t* sums;
+} x265cu_frame_in;
+int x265cu_frame_init_var_batch(x265cu_ctx* ctx, int n, const x265cu_frame_in* items);
+
 /* ---- LookaheadTLD::lowresIntraEstimate (slicetype.cpp:230-336).  Outputs (any may be NULL):
  * Lowres::intraCost, intraMode, lowresCosts[0][0], rowSatds[0][0]; sums[0] = costEst[0][0],
  * sums[1] = costEstAq[0][0]. */
@@ -127,6 +142,8 @@ typedef struct x265cu_intra_out
     int64_t sums[2];
 } x265cu_intra_out;
 int x265cu_intra(x265cu_ctx* ctx, int slot, x265cu_intra_out* out);
+/* the frames of one PreLookaheadGroup list in one go (one wait) */
+int x265cu_intra_batch(x265cu_ctx* ctx, int n, const int* slots, x265cu_intra_out* outs);
 
 /* ---- LookaheadTLD::weightCostLuma (slicetype.cpp:338-371): sum over all 8x8 of
  * min(SATD(weighted ref plane 0, fenc), intraCost).  weighted == 0 measures the plain reference.

@@ -65,7 +65,8 @@ class HostParams(C.Structure):
 ABI_SYMBOLS = (
     "x265cu_abi_version", "x265cu_device_count", "x265cu_open", "x265cu_close", "x265cu_last_error",
     "x265cu_get_geometry", "x265cu_sync", "x265cu_host_register", "x265cu_host_unregister",
-    "x265cu_frame_init", "x265cu_frame_set_invqscale", "x265cu_frame_var", "x265cu_frame_init_var", "x265cu_intra",
+    "x265cu_frame_init", "x265cu_frame_set_invqscale", "x265cu_frame_var", "x265cu_frame_init_var", "x265cu_frame_init_var_batch",
+    "x265cu_intra", "x265cu_intra_batch",
     "x265cu_weight_cost_batch", "x265cu_estimate_batch", "x265cu_pixelcmp_batch", "x265cu_pixelcmp_frames", "x265cu_int_peak",
     "x265cu_stats_enable", "x265cu_stats_get",
 )
@@ -123,6 +124,7 @@ def lib_host():
         L.x265cuh_frame_alloc.argtypes = [C.c_void_p]
         L.x265cuh_frame_free.argtypes = [C.c_void_p, C.c_void_p]
         L.x265cuh_pre_lookahead.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int]
+        L.x265cuh_pre_lookahead_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_int]
         L.x265cuh_estimate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.x265cuh_array.restype = C.c_void_p
         L.x265cuh_array.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
@@ -189,6 +191,18 @@ class Lookahead:
     def set_resident(self, on):
         """inputs become device pointers, result arrays stay in HBM (only sums return)"""
         self.L.x265cuh_set_resident(self.h, 1 if on else 0)
+
+    def prepare_pre_lookahead_batch(self, items):
+        """pre-marshal a PreLookaheadGroup list: items = [(frame, y, ys, u, v, cs, poc)] with raw pointers"""
+        n = len(items)
+        return (n, (C.c_void_p * n)(*[i[0] for i in items]), (C.c_void_p * n)(*[i[1] for i in items]),
+                (C.c_ssize_t * n)(*[i[2] for i in items]), (C.c_void_p * n)(*[i[3] for i in items]),
+                (C.c_void_p * n)(*[i[4] for i in items]), (C.c_ssize_t * n)(*[i[5] for i in items]), (C.c_int * n)(*[i[6] for i in items]))
+
+    def pre_lookahead_batch_prepared(self, prep, planes_back):
+        n, fr, y, ys, u, v, cs, pocs = prep
+        if self.L.x265cuh_pre_lookahead_batch(self.h, n, fr, y, ys, u, v, cs, pocs, 1 if planes_back else 0):
+            raise RuntimeError("pre_lookahead_batch failed: " + self.error())
 
     def pre_lookahead_ptr(self, frame, y, ys, u, v, cs, poc, planes_back):
         """raw-pointer form (host or, in resident mode, device addresses)"""

@@ -58,7 +58,8 @@ struct x265cu_ctx
     int* dMvs;
     int* dMvCosts;
     uint16_t* dLut;        /* base; centre at +65536 */
-    uint8_t* dSrc;         /* full-resolution luma staging */
+    uint8_t* dSrc;         /* full-resolution luma staging (strided-copy fallback) */
+    uint8_t* dSrcLin; size_t dSrcLinCap;   /* luma staging with the host's pitch (linear transfer) */
     int64_t srcPitch;      /* samples */
     unsigned long long* dSmall;   /* small scratch for sums */
 
@@ -67,6 +68,7 @@ struct x265cu_ctx
     uint8_t* hStage; size_t hStageCap;
     uint8_t* dArgs; size_t dArgsCap;       /* JobDev[], SearchItem[], int[] */
     uint8_t* hArgs; size_t hArgsCap;
+    uint8_t* hPre; size_t hPreCap;         /* pinned landing zone of batched pre-lookahead results */
     std::vector<void*> wPool;              /* weighted plane sets */
     uint8_t* dGeneric; size_t dGenericCap; /* pixelcmp / var scratch */
     uint8_t* dMemo; size_t dMemoCap;       /* search memo of a batch: [search][nCU][MEMO_N] int4 */
@@ -85,6 +87,9 @@ struct x265cu_ctx
 
     int searchWarps;       /* CU rows (= warps) per commit CTA */
     int searchSpec;        /* refine iterations before the commit wavefront (0: none; experiments only) */
+    int searchMode;        /* 0: plain kernel only, 1: speculative path only (with in-batch seed waves), 2: per search (default) */
+    int specMaxDist, specMaxPlans;   /* speculative path: hint at most this many frames away, batch of at most this many searches */
+    int plainWarps;        /* CU rows (= warps) per CTA of the plain kernel */
     long long dbgPlans[4];
 };
 
@@ -198,9 +203,10 @@ void freeAll(x265cu_ctx* c)
 {
     cudaFree(c->dPlanes); cudaFree(c->dIntraCost); cudaFree(c->dIntraMode); cudaFree(c->dInvQ);
     cudaFree(c->dLowresCosts); cudaFree(c->dRowSatds); cudaFree(c->dMvs); cudaFree(c->dMvCosts);
-    cudaFree(c->dLut); cudaFree(c->dSrc); cudaFree(c->dSmall); cudaFree(c->dStage); cudaFree(c->dArgs); cudaFree(c->dGeneric); cudaFree(c->dMemo);
+    cudaFree(c->dLut); cudaFree(c->dSrc); cudaFree(c->dSmall); cudaFree(c->dStage); cudaFree(c->dArgs); cudaFree(c->dGeneric); cudaFree(c->dMemo); cudaFree(c->dSrcLin);
     if (c->hStage) cudaFreeHost(c->hStage);
     if (c->hArgs) cudaFreeHost(c->hArgs);
+    if (c->hPre) cudaFreeHost(c->hPre);
     for (size_t i = 0; i < c->wPool.size(); i++) cudaFree(c->wPool[i]);
     for (size_t i = 0; i < c->freeEvents.size(); i++) cudaEventDestroy(c->freeEvents[i]);
     if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
@@ -247,7 +253,7 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     c->err[0] = 0;
     c->dPlanes = NULL; c->dIntraCost = NULL; c->dIntraMode = NULL; c->dInvQ = NULL; c->dLowresCosts = NULL; c->dRowSatds = NULL;
     c->dMvs = NULL; c->dMvCosts = NULL; c->dLut = NULL; c->dSrc = NULL; c->dSmall = NULL;
-    c->dStage = NULL; c->dStageCap = 0; c->hStage = NULL; c->hStageCap = 0; c->dArgs = NULL; c->dArgsCap = 0; c->hArgs = NULL; c->hArgsCap = 0;
+    c->dStage = NULL; c->dStageCap = 0; c->hStage = NULL; c->hStageCap = 0; c->dArgs = NULL; c->dArgsCap = 0; c->hArgs = NULL; c->hArgsCap = 0; c->hPre = NULL; c->hPreCap = 0; c->dSrcLin = NULL; c->dSrcLinCap = 0;
     c->dGeneric = NULL; c->dGenericCap = 0; c->dMemo = NULL; c->dMemoCap = 0;
     c->timing = false;
     memset(&c->stats, 0, sizeof(c->stats));
@@ -259,6 +265,13 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     c->searchWarps = cfg->searchWarps > 0 ? cfg->searchWarps : 4;    /* CU rows (= warps) per commit CTA */
     if (c->searchWarps > SEARCH_MAX_GROUP_ROWS) c->searchWarps = SEARCH_MAX_GROUP_ROWS;
     c->searchSpec = 3;
+    c->searchMode = 2; c->specMaxDist = 2; c->specMaxPlans = 4; c->plainWarps = 4;
+    if (const char* e = getenv("X265CU_SEARCH_MODE")) c->searchMode = atoi(e);
+    if (const char* e = getenv("X265CU_SPEC_MAX_DIST")) c->specMaxDist = atoi(e);
+    if (const char* e = getenv("X265CU_SPEC_MAX_PLANS")) c->specMaxPlans = atoi(e);
+    if (const char* e = getenv("X265CU_PLAIN_ROWS")) c->plainWarps = atoi(e);
+    if (c->plainWarps < 1) c->plainWarps = 1;
+    if (c->plainWarps > PLAIN_MAX_GROUP_ROWS) c->plainWarps = PLAIN_MAX_GROUP_ROWS;
     memset(c->dbgPlans, 0, sizeof(c->dbgPlans));
     if (const char* e = getenv("X265CU_SEARCH_SPEC")) c->searchSpec = atoi(e);   /* tuning experiments only */
     if (search_smem_bytes<uint16_t>(c->searchWarps, (cfg->srcWidth / 2 + 7) / 8) > 48 * 1024)
@@ -423,12 +436,12 @@ int x265cu_frame_init_var(x265cu_ctx* c, int slot, const void* y, intptr_t yStri
     return frameInitImpl(c, slot, y, yStride, planesAreDevice, planesOut, u, v, cStride, energy, sums);
 }
 
-static int frameInitImpl(x265cu_ctx* c, int slot, const void* luma, intptr_t srcStride, int lumaIsDevice, void* planesOut,
-                         const void* u, const void* v, intptr_t cStride, uint32_t* varEnergy, uint64_t* varSums)
+/* enqueue Lowres::init (and acEnergyCu's integer part when varEnergy != NULL) of one frame on the ctx stream; no
+ * synchronisation: varEnergy / varSums (6 x u64) are filled once the stream has drained.  Caller holds the lock. */
+static int frameInitEnqueue(x265cu_ctx* c, int slot, const void* luma, intptr_t srcStride, int lumaIsDevice, void* planesOut,
+                            const void* u, const void* v, intptr_t cStride, uint32_t* varEnergy, unsigned long long* varSums)
 {
-    if (!c || !luma || badSlot(c, slot) || srcStride < 2 * c->g.width + 1) return c ? fail(c, X265CU_EINVAL, "x265cu_frame_init: bad argument") : X265CU_EINVAL;
-    std::lock_guard<std::mutex> lk(c->mtx);
-    CU_TRY(c, cudaSetDevice(c->cfg.device));
+    if (!luma || badSlot(c, slot) || srcStride < 2 * c->g.width + 1) return fail(c, X265CU_EINVAL, "x265cu_frame_init: bad argument");
     const GeomDev& g = c->g;
     const void* src = luma;
     int64_t pitch = srcStride;
@@ -436,11 +449,26 @@ static int frameInitImpl(x265cu_ctx* c, int slot, const void* luma, intptr_t src
     {
         /* (2W+1) x (2H+1) samples for the downscale; that also covers the 16-aligned picture pixel_var reads */
         size_t wbytes = (size_t)(2 * g.width + 1) * c->pb;
-        CU_TRY(c, cudaMemcpy2DAsync(c->dSrc, (size_t)c->srcPitch * c->pb, luma, (size_t)srcStride * c->pb, wbytes, 2 * g.lines + 1,
-                                    cudaMemcpyHostToDevice, c->stream));
-        c->stats.h2dBytes += (int64_t)wbytes * (2 * g.lines + 1);
-        src = c->dSrc;
-        pitch = c->srcPitch;
+        const size_t rows = (size_t)2 * g.lines + 1;
+        if ((((size_t)srcStride * c->pb) & 7) == 0)
+        {
+            /* ONE linear transfer of the rows with the host's own pitch (the few margin bytes between rows ride along):
+             * a strided 2-D copy of ~2 KB rows reaches a fraction of the PCIe rate */
+            const size_t lin = (rows - 1) * (size_t)srcStride * c->pb + wbytes;
+            if (growDevice(c, &c->dSrcLin, &c->dSrcLinCap, lin + 256)) return X265CU_ECUDA;
+            CU_TRY(c, cudaMemcpyAsync(c->dSrcLin, luma, lin, cudaMemcpyHostToDevice, c->stream));
+            c->stats.h2dBytes += (int64_t)lin;
+            src = c->dSrcLin;
+            pitch = srcStride;
+        }
+        else
+        {
+            CU_TRY(c, cudaMemcpy2DAsync(c->dSrc, (size_t)c->srcPitch * c->pb, luma, (size_t)srcStride * c->pb, wbytes, rows,
+                                        cudaMemcpyHostToDevice, c->stream));
+            c->stats.h2dBytes += (int64_t)wbytes * rows;
+            src = c->dSrc;
+            pitch = c->srcPitch;
+        }
     }
     else if (((uintptr_t)luma & 7) || (((size_t)srcStride * c->pb) & 7))
         return fail(c, X265CU_EINVAL, "x265cu_frame_init: device luma must be 8-byte aligned with an 8-byte multiple pitch");
@@ -475,17 +503,19 @@ static int frameInitImpl(x265cu_ctx* c, int slot, const void* luma, intptr_t src
         /* acEnergyCu's integer work on the luma that is already on the device + the two chroma planes */
         const int W = c->cfg.srcWidth, H = c->cfg.srcHeight;
         const int bxN = (W + 15) / 16, byN = (H + 15) / 16;
-        const size_t cp = alignUp((size_t)bxN * 8, 64);
-        const size_t cBytes = cp * byN * 8 * c->pb;
+        /* chroma rows travel with the host's pitch in one linear transfer per plane, like the luma */
+        const size_t cp = (u && !lumaIsDevice) ? (size_t)cStride : alignUp((size_t)bxN * 8, 64);
+        const size_t cLin = ((size_t)byN * 8 - 1) * cp * c->pb + (size_t)bxN * 8 * c->pb;
+        const size_t cBytes = alignUp(cLin, 256);
         const size_t eBytes = alignUp((size_t)bxN * byN * 4, 256);
         if (growDevice(c, &c->dGeneric, &c->dGenericCap, 2 * cBytes + eBytes + 256)) return X265CU_ECUDA;
         uint8_t* dU = c->dGeneric; uint8_t* dV = dU + cBytes; unsigned int* dE = (unsigned int*)(dV + cBytes);
         int64_t cpitch = (int64_t)cp;
         if (u && !lumaIsDevice)
         {
-            CU_TRY(c, cudaMemcpy2DAsync(dU, cp * c->pb, u, (size_t)cStride * c->pb, (size_t)bxN * 8 * c->pb, byN * 8, cudaMemcpyHostToDevice, c->stream));
-            CU_TRY(c, cudaMemcpy2DAsync(dV, cp * c->pb, v, (size_t)cStride * c->pb, (size_t)bxN * 8 * c->pb, byN * 8, cudaMemcpyHostToDevice, c->stream));
-            c->stats.h2dBytes += (int64_t)(2 * (size_t)bxN * 8 * c->pb * byN * 8);
+            CU_TRY(c, cudaMemcpyAsync(dU, u, cLin, cudaMemcpyHostToDevice, c->stream));
+            CU_TRY(c, cudaMemcpyAsync(dV, v, cLin, cudaMemcpyHostToDevice, c->stream));
+            c->stats.h2dBytes += (int64_t)(2 * cLin);
         }
         else if (u) { dU = (uint8_t*)u; dV = (uint8_t*)v; cpitch = cStride; }
         CU_TRY(c, cudaMemsetAsync(c->dSmall, 0, 6 * sizeof(unsigned long long), c->stream));
@@ -499,14 +529,53 @@ static int frameInitImpl(x265cu_ctx* c, int slot, const void* luma, intptr_t src
         }
         CU_TRY(c, cudaGetLastError());
         CU_TRY(c, cudaMemcpyAsync(varEnergy, dE, (size_t)bxN * byN * 4, cudaMemcpyDeviceToHost, c->stream));
-        unsigned long long hs[6];
-        CU_TRY(c, cudaMemcpyAsync(hs, c->dSmall, sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
-        int r = syncStream(c);
-        for (int i = 0; i < 6; i++) varSums[i] = hs[i];
-        return r;
+        CU_TRY(c, cudaMemcpyAsync(varSums, c->dSmall, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     }
-    /* the caller may reuse its luma buffer as soon as we return */
-    return syncStream(c);
+    return X265CU_OK;
+}
+
+static int frameInitImpl(x265cu_ctx* c, int slot, const void* luma, intptr_t srcStride, int lumaIsDevice, void* planesOut,
+                         const void* u, const void* v, intptr_t cStride, uint32_t* varEnergy, uint64_t* varSums)
+{
+    if (!c) return X265CU_EINVAL;
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CU_TRY(c, cudaSetDevice(c->cfg.device));
+    unsigned long long hs[6] = { 0, 0, 0, 0, 0, 0 };
+    int r = frameInitEnqueue(c, slot, luma, srcStride, lumaIsDevice, planesOut, u, v, cStride, varEnergy, hs);
+    if (r) return r;
+    /* the caller may reuse its picture buffers as soon as we return */
+    r = syncStream(c);
+    if (varEnergy) for (int i = 0; i < 6; i++) varSums[i] = hs[i];
+    return r;
+}
+
+/* PreLookaheadGroup::processTasks hands a LIST of frames to the workers (slicetype.cpp:831-856): all uploads and
+ * kernels of the list are enqueued back to back and the host waits once */
+int x265cu_frame_init_var_batch(x265cu_ctx* c, int n, const x265cu_frame_in* items)
+{
+    if (!c || n < 0 || (n && !items)) return c ? fail(c, X265CU_EINVAL, "x265cu_frame_init_var_batch: bad argument") : X265CU_EINVAL;
+    if (!n) return X265CU_OK;
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CU_TRY(c, cudaSetDevice(c->cfg.device));
+    const int bxN = (c->cfg.srcWidth + 15) / 16, byN = (c->cfg.srcHeight + 15) / 16;
+    const size_t eBytes = alignUp((size_t)bxN * byN * 4, 64), per = eBytes + 64;
+    if (growHost(c, &c->hPre, &c->hPreCap, (size_t)n * per)) return X265CU_ECUDA;
+    for (int i = 0; i < n; i++)
+    {
+        const x265cu_frame_in& f = items[i];
+        if (!f.energy || !f.sums || ((f.u == NULL) != (f.v == NULL))) return fail(c, X265CU_EINVAL, "x265cu_frame_init_var_batch: bad item");
+        int r = frameInitEnqueue(c, f.slot, f.y, f.yStride, f.planesAreDevice, f.planesOut, f.u, f.v, f.cStride,
+                                 (uint32_t*)(c->hPre + (size_t)i * per), (unsigned long long*)(c->hPre + (size_t)i * per + eBytes));
+        if (r) { cudaStreamSynchronize(c->stream); return r; }
+    }
+    int r = syncStream(c);
+    if (r) return r;
+    for (int i = 0; i < n; i++)
+    {
+        memcpy(items[i].energy, c->hPre + (size_t)i * per, (size_t)bxN * byN * 4);
+        memcpy(items[i].sums, c->hPre + (size_t)i * per + eBytes, 6 * sizeof(uint64_t));
+    }
+    return X265CU_OK;
 }
 
 int x265cu_frame_set_invqscale(x265cu_ctx* c, int slot, const int32_t* invQ)
@@ -525,11 +594,10 @@ int x265cu_frame_set_invqscale(x265cu_ctx* c, int slot, const int32_t* invQ)
     return X265CU_OK;
 }
 
-int x265cu_intra(x265cu_ctx* c, int slot, x265cu_intra_out* out)
+/* enqueue lowresIntraEstimate of one frame; sums (2 x u64) land once the stream has drained.  Caller holds the lock. */
+static int intraEnqueue(x265cu_ctx* c, int slot, x265cu_intra_out* out, unsigned long long* sums)
 {
-    if (!c || badSlot(c, slot)) return c ? fail(c, X265CU_EINVAL, "x265cu_intra: bad slot") : X265CU_EINVAL;
-    std::lock_guard<std::mutex> lk(c->mtx);
-    CU_TRY(c, cudaSetDevice(c->cfg.device));
+    if (badSlot(c, slot)) return fail(c, X265CU_EINVAL, "x265cu_intra: bad slot");
     const GeomDev& g = c->g;
     IntraOutDev o;
     o.intraCost = slotIntraCost(c, slot);
@@ -551,18 +619,49 @@ int x265cu_intra(x265cu_ctx* c, int slot, x265cu_intra_out* out)
     CU_TRY(c, cudaGetLastError());
     if (out)
     {
-        unsigned long long sums[2] = { 0, 0 };
         if (out->intraCost) { CU_TRY(c, cudaMemcpyAsync(out->intraCost, o.intraCost, (size_t)g.nCU * 4, cudaMemcpyDeviceToHost, c->stream)); c->stats.d2hBytes += g.nCU * 4; }
         if (out->intraMode) { CU_TRY(c, cudaMemcpyAsync(out->intraMode, o.intraMode, (size_t)g.nCU, cudaMemcpyDeviceToHost, c->stream)); c->stats.d2hBytes += g.nCU; }
         if (out->lowresCosts) { CU_TRY(c, cudaMemcpyAsync(out->lowresCosts, o.lowresCosts, (size_t)g.nCU * 2, cudaMemcpyDeviceToHost, c->stream)); c->stats.d2hBytes += g.nCU * 2; }
         if (out->rowSatds) { CU_TRY(c, cudaMemcpyAsync(out->rowSatds, o.rowSatds, (size_t)g.hCU * 4, cudaMemcpyDeviceToHost, c->stream)); c->stats.d2hBytes += g.hCU * 4; }
-        CU_TRY(c, cudaMemcpyAsync(sums, c->dSmall, sizeof(sums), cudaMemcpyDeviceToHost, c->stream));
-        int r = syncStream(c);
-        out->sums[0] = (int64_t)sums[0];
-        out->sums[1] = (int64_t)sums[1];
-        return r;
+        CU_TRY(c, cudaMemcpyAsync(sums, c->dSmall, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     }
-    return syncStream(c);
+    return X265CU_OK;
+}
+
+int x265cu_intra(x265cu_ctx* c, int slot, x265cu_intra_out* out)
+{
+    if (!c) return X265CU_EINVAL;
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CU_TRY(c, cudaSetDevice(c->cfg.device));
+    unsigned long long sums[2] = { 0, 0 };
+    int r = intraEnqueue(c, slot, out, sums);
+    if (r) return r;
+    r = syncStream(c);
+    if (out) { out->sums[0] = (int64_t)sums[0]; out->sums[1] = (int64_t)sums[1]; }
+    return r;
+}
+
+int x265cu_intra_batch(x265cu_ctx* c, int n, const int* slots, x265cu_intra_out* outs)
+{
+    if (!c || n < 0 || (n && (!slots || !outs))) return c ? fail(c, X265CU_EINVAL, "x265cu_intra_batch: bad argument") : X265CU_EINVAL;
+    if (!n) return X265CU_OK;
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CU_TRY(c, cudaSetDevice(c->cfg.device));
+    if (growHost(c, &c->hPre, &c->hPreCap, (size_t)n * 16)) return X265CU_ECUDA;
+    for (int i = 0; i < n; i++)
+    {
+        int r = intraEnqueue(c, slots[i], &outs[i], (unsigned long long*)(c->hPre + (size_t)i * 16));
+        if (r) { cudaStreamSynchronize(c->stream); return r; }
+    }
+    int r = syncStream(c);
+    if (r) return r;
+    for (int i = 0; i < n; i++)
+    {
+        const unsigned long long* sm = (const unsigned long long*)(c->hPre + (size_t)i * 16);
+        outs[i].sums[0] = (int64_t)sm[0];
+        outs[i].sums[1] = (int64_t)sm[1];
+    }
+    return X265CU_OK;
 }
 
 /* -------------------------------------------------------------------------------------------- */
@@ -677,8 +776,7 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
      * temporally nearest frame for the same list and distance.  Searches of a batch that have no such
      * field yet are run in two WAVES: one seed per (list, distance) first, the others after it with the
      * seed's field as their hint. ---- */
-    std::vector<int> waveOf(plans.size(), 0);
-    int numWaves = plans.empty() ? 0 : 1;
+    std::vector<int> classOf(plans.size(), 0);   /* 0/1: speculative path, wave 0/1; 2: plain kernel */
     if (!plans.empty())
     {
         for (;;)
@@ -715,6 +813,7 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
         }
         const size_t perSlot = (size_t)2 * (c->bf + 1);
         const int maxStep = 8;
+        std::vector<int> hintDist(plans.size(), 0);
         for (size_t k = 0; k < plans.size(); k++)
         {
             SearchPlan& pl = plans[k];
@@ -726,12 +825,22 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
                 if ((int)sl == F || !c->slotPocKnown[sl] || !c->mvValid[sl * perSlot + (size_t)pl.list * (c->bf + 1) + (d - 1)]) continue;
                 long long dist = c->slotPoc[sl] - c->slotPoc[F];
                 if (dist < 0) dist = -dist;
-                if (dist < best) { best = dist; pl.hint = slotMvs(c, (int)sl, pl.list, d); }
+                if (dist < best) { best = dist; pl.hint = slotMvs(c, (int)sl, pl.list, d); hintDist[k] = (int)dist; }
             }
         }
-        /* in-batch seeds: per (list, distance) class still without a hint, the plan in the middle of the
-         * class's picture-order range goes first (wave 0, unhinted), the rest follow in wave 1 */
-        for (int l = 0; l < 2; l++)
+        /* Which kernel runs a search.  The speculative path (refine + commit) does more work per CU to shorten the
+         * dependent chain, which pays when the GPU is mostly idle (few searches in flight) AND the hint is close in
+         * time; a batch that fills the GPU, or a search without a good hint, takes the plain wavefront kernel. */
+        for (size_t k = 0; k < plans.size(); k++)
+        {
+            if (c->searchMode == 0) classOf[k] = 2;
+            else if (c->searchMode == 1) classOf[k] = 0;
+            else classOf[k] = (plans[k].hint && hintDist[k] <= c->specMaxDist && (int)plans.size() <= c->specMaxPlans) ? 0 : 2;
+            if (classOf[k] == 2) plans[k].hint = NULL;
+        }
+        /* (experiments, searchMode 1) in-batch seeds: per (list, distance) class still without a hint, the plan in the
+         * middle of the class's picture-order range goes first (wave 0, unhinted), the rest follow in wave 1 */
+        for (int l = 0; l < 2 && c->searchMode == 1; l++)
             for (int d = 1; d <= c->bf + 1; d++)
             {
                 std::vector<size_t> cls;
@@ -745,10 +854,10 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
                 const size_t seed = cls[cls.size() / 2];
                 const int* seedField = slotMvs(c, jobs[plans[seed].job].fenc, l, d);
                 for (size_t i = 0; i < cls.size(); i++)
-                    if (cls[i] != seed) { plans[cls[i]].hint = seedField; waveOf[cls[i]] = 1; numWaves = 2; }
+                    if (cls[i] != seed) { plans[cls[i]].hint = seedField; classOf[cls[i]] = 1; }
             }
 #ifdef X265CU_SEARCH_STATS
-        for (size_t k = 0; k < plans.size(); k++) { c->dbgPlans[0]++; if (plans[k].hint) c->dbgPlans[waveOf[k] ? 2 : 1]++; }
+        for (size_t k = 0; k < plans.size(); k++) { c->dbgPlans[0]++; if (classOf[k] != 2) c->dbgPlans[classOf[k] ? 2 : 1]++; }
 #endif
         /* fields this batch produces become hints for later batches */
         for (size_t k = 0; k < plans.size(); k++)
@@ -756,56 +865,65 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
             const x265cu_job& j = jobs[plans[k].job];
             c->mvValid[(size_t)j.fenc * perSlot + (size_t)plans[k].list * (c->bf + 1) + ((plans[k].list ? j.d1 : j.d0) - 1)] = 1;
         }
-        /* wave 0 first */
-        if (numWaves > 1)
+        /* order: speculative wave 0, speculative wave 1, plain */
         {
             std::vector<SearchPlan> sorted;
-            for (int w = 0; w < 2; w++)
+            for (int w = 0; w < 3; w++)
                 for (size_t k = 0; k < plans.size(); k++)
-                    if (waveOf[k] == w) sorted.push_back(plans[k]);
+                    if (classOf[k] == w) sorted.push_back(plans[k]);
             plans.swap(sorted);
         }
     }
-    size_t wavePlans[3] = { 0, 0, plans.size() };
-    for (size_t k = 0; k < waveOf.size(); k++) if (waveOf[k] == 0) wavePlans[1]++;
-    const size_t memoPerSearch = nCU * MEMO_N * sizeof(int4) + 2 * alignUp(nCU * sizeof(int), 256);   /* memo + the two estimate fields */
-    if (!plans.empty() && growDevice(c, &c->dMemo, &c->dMemoCap, plans.size() * memoPerSearch)) return X265CU_ECUDA;
+    size_t classPlans[4] = { 0, 0, 0, plans.size() };       /* first plan of each class */
+    for (size_t k = 0; k < classOf.size(); k++) { if (classOf[k] < 1) classPlans[1]++; if (classOf[k] < 2) classPlans[2]++; }
+    const size_t memoPerSearch = nCU * MEMO_N * sizeof(int4) + 3 * alignUp(nCU * sizeof(int), 256);   /* memo + the three estimate fields */
+    if (classPlans[2] && growDevice(c, &c->dMemo, &c->dMemoCap, classPlans[2] * memoPerSearch)) return X265CU_ECUDA;
 
     /* ---- commit work items: one per row group of every (search, cooperative slice) ---- */
-    int maxItemRows = 1;
+    int maxItemRows = 1, maxPlainRows = 1;
     int handRows = 0;            /* global hand-off rows (one per row group that has a group above it) */
-    size_t waveItems[3] = { 0, 0, 0 };
+    size_t classItems[4] = { 0, 0, 0, 0 };
     for (size_t k = 0; k < plans.size(); k++)
     {
         SearchPlan& pl = plans[k];
-        pl.memo = (int4*)(c->dMemo + k * memoPerSearch);
-        pl.field[0] = (int*)(c->dMemo + k * memoPerSearch + nCU * MEMO_N * sizeof(int4));
-        pl.field[1] = pl.field[0] + alignUp(nCU * sizeof(int), 256) / sizeof(int);
-        if (k == wavePlans[1]) waveItems[1] = items.size();
+        const bool plain = k >= classPlans[2];
+        if (!plain)
+        {
+            pl.memo = (int4*)(c->dMemo + k * memoPerSearch);
+            pl.field[0] = (int*)(c->dMemo + k * memoPerSearch + nCU * MEMO_N * sizeof(int4));
+            pl.field[1] = pl.field[0] + alignUp(nCU * sizeof(int), 256) / sizeof(int);
+            pl.field[2] = pl.field[1] + alignUp(nCU * sizeof(int), 256) / sizeof(int);
+        }
+        if (k == classPlans[1]) classItems[1] = items.size();
+        if (k == classPlans[2]) classItems[2] = items.size();
+        const int groupRows = plain ? c->plainWarps : c->searchWarps;
         for (int s = 0; s < pl.numSlices; s++)
         {
             const int sFirst = pl.numSlices > 1 ? pl.rowsPerSlice * s : 0;
             const int sLast = s == pl.numSlices - 1 ? g.hCU - 1 : pl.rowsPerSlice * (s + 1) - 1;
             /* row groups, bottom first: a group only waits for a group with a lower block index */
             int prevPub = -1;
-            for (int bottom = sLast; bottom >= sFirst; bottom -= c->searchWarps)
+            for (int bottom = sLast; bottom >= sFirst; bottom -= groupRows)
             {
                 SearchItem it;
                 it.search = (int)k;
                 it.sliceFirstY = sFirst;
                 it.sliceLastY = sLast;
                 it.lastY = bottom;
-                it.firstY = bottom - c->searchWarps + 1 > sFirst ? bottom - c->searchWarps + 1 : sFirst;
+                it.firstY = bottom - groupRows + 1 > sFirst ? bottom - groupRows + 1 : sFirst;
                 it.subBase = prevPub;                                   /* hand-off row of the group below */
                 it.pubBase = it.firstY > sFirst ? handRows++ * g.wCU : -1; /* the top group has nobody above */
                 prevPub = it.pubBase;
-                if (it.lastY - it.firstY + 1 > maxItemRows) maxItemRows = it.lastY - it.firstY + 1;
+                int& mr = plain ? maxPlainRows : maxItemRows;
+                if (it.lastY - it.firstY + 1 > mr) mr = it.lastY - it.firstY + 1;
                 items.push_back(it);
             }
         }
     }
-    if (wavePlans[1] == plans.size()) waveItems[1] = items.size();
-    waveItems[2] = items.size();
+    if (classPlans[1] == plans.size()) classItems[1] = items.size();
+    if (classPlans[2] == plans.size()) classItems[2] = items.size();
+    if (classPlans[1] == classPlans[2] && classPlans[2] < plans.size()) classItems[1] = classItems[2];
+    classItems[3] = items.size();
 
     size_t offJobs = 0;
     size_t offItems = alignUp(offJobs + (size_t)n * sizeof(JobDev), 256);
@@ -887,28 +1005,38 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
         const SearchPlan* dPlans = (const SearchPlan*)(c->dArgs + offPlans);
         const SearchItem* dItems = (const SearchItem*)(c->dArgs + offItems);
         const uint16_t* dLutC = c->dLut + 2 * 32768;
-        /* per wave -- speculation: every CU of every search in parallel (memo); then the commit wavefront:
-         * one CTA per row group, one warp per CU row of the group */
-        int warps = maxItemRows;
         unsigned long long* dProg = (unsigned long long*)(c->dArgs + offProg);
-        for (int w = 0; w < numWaves; w++)
+        /* plain wavefront kernel: one CTA per row group, one warp per CU row */
+        if (classItems[3] > classItems[2])
         {
-            const unsigned np = (unsigned)(wavePlans[w + 1] - wavePlans[w]), ni = (unsigned)(waveItems[w + 1] - waveItems[w]);
+            const unsigned ni = (unsigned)(classItems[3] - classItems[2]);
+            const size_t smem = (size_t)maxPlainRows * g.wCU * sizeof(unsigned long long);
+            if (c->pb == 1)
+                plain_search_kernel<uint8_t><<<ni, maxPlainRows * 32, smem, c->stream>>>(dJobs, dPlans, dItems + classItems[2], g, dLutC, dProg);
+            else
+                plain_search_kernel<uint16_t><<<ni, maxPlainRows * 32, smem, c->stream>>>(dJobs, dPlans, dItems + classItems[2], g, dLutC, dProg);
+        }
+        /* speculative path, per wave -- refine: every CU of every search in parallel (estimates + memo); then the commit
+         * wavefront: one CTA per row group, one warp per CU row of the group */
+        int warps = maxItemRows;
+        for (int w = 0; w < 2; w++)
+        {
+            const unsigned np = (unsigned)(classPlans[w + 1] - classPlans[w]), ni = (unsigned)(classItems[w + 1] - classItems[w]);
             if (!np) continue;
             dim3 sgrid((unsigned)((g.nCU + SPEC_WARPS - 1) / SPEC_WARPS), np);
-            if (!c->searchSpec) CU_TRY(c, cudaMemsetAsync(c->dMemo + wavePlans[w] * memoPerSearch, 0xff, np * memoPerSearch, c->stream));
+            if (!c->searchSpec) CU_TRY(c, cudaMemsetAsync(c->dMemo + classPlans[w] * memoPerSearch, 0xff, np * memoPerSearch, c->stream));
             /* refine iterations: parallel work that shortens the commit chains; a wave with many searches is
              * throughput-bound, not chain-bound, and gets a single one */
             const int iters = np >= 32 ? (c->searchSpec < 1 ? c->searchSpec : 1) : c->searchSpec;
             if (c->pb == 1)
             {
-                for (int it = 0; it < iters; it++) refine_kernel<uint8_t><<<sgrid, SPEC_WARPS * 32, 0, c->stream>>>(dJobs, dPlans + wavePlans[w], g, dLutC, it);
-                search_kernel<uint8_t><<<ni, warps * 32, search_smem_bytes<uint8_t>(warps, g.wCU), c->stream>>>(dJobs, dPlans, dItems + waveItems[w], g, dLutC, dProg, warps, iters > 0 ? (iters - 1) & 1 : -1);
+                for (int it = 0; it < iters; it++) refine_kernel<uint8_t><<<sgrid, SPEC_WARPS * 32, 0, c->stream>>>(dJobs, dPlans + classPlans[w], g, dLutC, it);
+                search_kernel<uint8_t><<<ni, warps * 32, search_smem_bytes<uint8_t>(warps, g.wCU), c->stream>>>(dJobs, dPlans, dItems + classItems[w], g, dLutC, dProg, warps, iters > 0 ? (iters - 1) % 3 : -1);
             }
             else
             {
-                for (int it = 0; it < iters; it++) refine_kernel<uint16_t><<<sgrid, SPEC_WARPS * 32, 0, c->stream>>>(dJobs, dPlans + wavePlans[w], g, dLutC, it);
-                search_kernel<uint16_t><<<ni, warps * 32, search_smem_bytes<uint16_t>(warps, g.wCU), c->stream>>>(dJobs, dPlans, dItems + waveItems[w], g, dLutC, dProg, warps, iters > 0 ? (iters - 1) & 1 : -1);
+                for (int it = 0; it < iters; it++) refine_kernel<uint16_t><<<sgrid, SPEC_WARPS * 32, 0, c->stream>>>(dJobs, dPlans + classPlans[w], g, dLutC, it);
+                search_kernel<uint16_t><<<ni, warps * 32, search_smem_bytes<uint16_t>(warps, g.wCU), c->stream>>>(dJobs, dPlans, dItems + classItems[w], g, dLutC, dProg, warps, iters > 0 ? (iters - 1) % 3 : -1);
             }
         }
         CU_TRY(c, cudaGetLastError());
@@ -951,8 +1079,8 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
         unsigned long long h[32], z[32] = { 0 };
         cudaMemcpyFromSymbol(h, g_searchStats, sizeof(h));
         cudaMemcpyToSymbol(g_searchStats, z, sizeof(z));
-        fprintf(stderr, "batch: jobs %d searches %zu waves %d | cus %llu fast %llu cand-pass %llu chain-search %llu steps %llu | serial %llu: cyc wait %.0f memo %.0f cand %.0f (per pass %.0f) mvp %.0f search %.0f (per search %.0f)\n",
-                n, plans.size(), numWaves, h[0], h[15], h[14], h[1], h[16], h[17], (double)h[20] / (h[17] ? h[17] : 1), (double)h[21] / (h[17] ? h[17] : 1),
+        fprintf(stderr, "batch: jobs %d searches %zu | cus %llu fast %llu cand-pass %llu chain-search %llu steps %llu | serial %llu: cyc wait %.0f memo %.0f cand %.0f (per pass %.0f) mvp %.0f search %.0f (per search %.0f)\n",
+                n, plans.size(), h[0], h[15], h[14], h[1], h[16], h[17], (double)h[20] / (h[17] ? h[17] : 1), (double)h[21] / (h[17] ? h[17] : 1),
                 (double)h[22] / (h[17] ? h[17] : 1), (double)h[25] / (h[26] ? h[26] : 1), (double)h[23] / (h[17] ? h[17] : 1), (double)h[24] / (h[17] ? h[17] : 1), (double)h[24] / (h[1] ? h[1] : 1));
     }
 #endif

@@ -55,7 +55,7 @@ struct SearchPlan
     const int* hint;               /* packed MV field predicting this search's result, or NULL (zero field) */
     int hintNeg;                   /* the hint is the opposite list's field: negate it */
     int4* memo;                    /* [nCU][MEMO_N] {mvp, SATD at mvp or -1, result MV, result cost or -1 (empty)} */
-    int* field[2];                 /* [nCU] ping-pong estimates of the result field (refine iterations) */
+    int* field[3];                 /* [nCU] estimates of the result field: refine iteration k writes field[k % 3] */
 };
 
 /* one row group of a search: a CTA of the commit kernel */
@@ -79,6 +79,7 @@ struct SearchItem
 __device__ unsigned long long g_searchStats[32];
 #define SSTAT_ADD(i, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_searchStats[i], (unsigned long long)(v)); } while (0)
 #define SSTAT_CLOCK() clock64()
+#define SSTAT_T(v) const long long v = clock64()
 /* per-row step timeline of the commit kernel: [cuY][event] = {globaltimer ns, x0 | kind << 16 | n << 24} */
 __device__ unsigned long long g_traceT[256][512];
 __device__ unsigned int g_traceE[256][512];
@@ -89,6 +90,7 @@ __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; a
 #define STRACE(row, x0, kind, n) do { } while (0)
 #define SSTAT_ADD(i, v) do { } while (0)
 #define SSTAT_CLOCK() 0ll
+#define SSTAT_T(v) do { } while (0)
 #endif
 
 /* two-source fetch at quarter-pel MV (qx, qy); when the MV is not odd both sources coincide and the
@@ -392,7 +394,7 @@ refine_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restrict__ pl
     /* the current estimate of the neighbours' MVs, in the reference's candidate order (slicetype.cpp:2117-2128);
      * bottom row of a cooperative slice (or of the frame): no candidates from below (slicetype.cpp:1957-1968) */
     const bool lastRow = cuY == H - 1 || (pl.numSlices > 1 && (cuY + 1) % pl.rowsPerSlice == 0 && (cuY + 1) / pl.rowsPerSlice < pl.numSlices);
-    const int* __restrict__ fin = iter == 0 ? pl.hint : pl.field[(iter - 1) & 1];
+    const int* __restrict__ fin = iter == 0 ? pl.hint : pl.field[(iter - 1) % 3];
     const int neg = iter == 0 ? pl.hintNeg : 0;
     int nb0 = 0, nb1 = 0, nb2 = 0, nb3 = 0, numc = 0;
     if (cuX < W - 1) { nb0 = hint_at(fin, neg, cuXY + 1); numc = 1; }
@@ -405,6 +407,27 @@ refine_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restrict__ pl
         if (cuX < W - 1) { const int br = hint_at(fin, neg, cuXY + W + 1); if (numc == 2) nb2 = br; else nb3 = br; numc++; }
     }
 
+    if (iter > 0)
+    {
+        /* same neighbour estimates as in the previous iteration: same memo, same outcome -- nothing to do */
+        const int* __restrict__ fprev = iter == 1 ? pl.hint : pl.field[(iter - 2) % 3];
+        const int nprev = iter == 1 ? pl.hintNeg : 0;
+        int p0 = 0, p1 = 0, p2 = 0, p3 = 0, pc = 0;
+        if (cuX < W - 1) { p0 = hint_at(fprev, nprev, cuXY + 1); pc = 1; }
+        if (!lastRow)
+        {
+            const int mb = hint_at(fprev, nprev, cuXY + W);
+            if (pc == 0) p0 = mb; else p1 = mb;
+            pc++;
+            if (cuX > 0) { const int bl = hint_at(fprev, nprev, cuXY + W - 1); if (pc == 1) p1 = bl; else p2 = bl; pc++; }
+            if (cuX < W - 1) { const int br = hint_at(fprev, nprev, cuXY + W + 1); if (pc == 2) p2 = br; else p3 = br; pc++; }
+        }
+        if (p0 == nb0 && p1 == nb1 && p2 == nb2 && p3 == nb3)
+        {
+            if (lane == 0) pl.field[iter % 3][cuXY] = fin[cuXY];
+            return;
+        }
+    }
     int4* __restrict__ memo = pl.memo + (size_t)cuXY * MEMO_N;
     int4 e = make_int4(0, -1, 0, -1);
     if (iter > 0) e = memo[lane & (MEMO_N - 1)];
@@ -418,6 +441,7 @@ refine_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restrict__ pl
     const int sub = lane & 3, bx = (sub & 1) * 4, by = (sub >> 1) * 4;
     const int stride = g.stride, planeSize = (int)g.planeSize;
     const int rowBase = (8 * cuY + by) * stride + bx;
+    const LaneGeom L = lane_geom(lane, stride);
 #pragma unroll 1
     for (int i = 0; i < nWant; i++)
     {
@@ -431,7 +455,6 @@ refine_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restrict__ pl
                 fe[y] = Px<P>::load_aligned(fencPlane + rowBase + 8 * cuX + y * stride);
             loaded = true;
         }
-        const LaneGeom L = lane_geom(lane, stride);
         int oMv, oCost, cs;
         bool cok;
         search_mv<P>(refPlane + 8 * cuY * stride + 8 * cuX, refPlane + rowBase + 8 * cuX, sWin[warp], planeSize, stride, fe, lut, L, lane, bx, by,
@@ -465,7 +488,7 @@ refine_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restrict__ pl
             }
         }
     }
-    if (lane == 0) pl.field[iter & 1][cuXY] = outMv;
+    if (lane == 0) pl.field[iter % 3][cuXY] = outMv;
 }
 
 /* ===========================================================================================
@@ -641,7 +664,7 @@ search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restrict__ pl
         /* ================= serial step: the whole warp works on CU x0 ================= */
         {
             const int cuX = x0;
-            const long long tp0 = SSTAT_CLOCK();
+            SSTAT_T(tp0);
             int nb0 = 0, nb1 = 0, nb2 = 0, nb3 = 0, numc = 0;
             if (cuX < W - 1) { nb0 = prevMv; numc = 1; }
             if (!lastRow)
@@ -656,7 +679,7 @@ search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restrict__ pl
                 if (cuX > 0) { if (numc == 1) nb1 = bl; else nb2 = bl; numc++; }
                 if (cuX < W - 1) { if (numc == 2) nb2 = br; else nb3 = br; numc++; }
             }
-            const long long tp1 = SSTAT_CLOCK();
+            SSTAT_T(tp1);
             const int4 e = memoRow[cuX * MEMO_N + (lane & (MEMO_N - 1))];     /* lane k (mod MEMO_N) holds entry k */
             const int i0 = memo_find(e, nb0), i1 = memo_find(e, nb1), i2 = memo_find(e, nb2), i3 = memo_find(e, nb3);
             int k0 = __shfl_sync(FULL_MASK, e.y, i0 & 31), k1 = __shfl_sync(FULL_MASK, e.y, i1 & 31);
@@ -667,7 +690,7 @@ search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restrict__ pl
             const bool ok = (allEq && !(nb0 == 0 && bidir && numc > 0)) ||
                             ((numc < 1 || (i0 >= 0 && k0 >= 0)) && (numc < 2 || (i1 >= 0 && k1 >= 0)) && (numc < 3 || (i2 >= 0 && k2 >= 0)) && (numc < 4 || (i3 >= 0 && k3 >= 0)));
             typename Px<P>::Row4 fe[4];
-            const long long tp2 = SSTAT_CLOCK();
+            SSTAT_T(tp2);
             if (!ok)
             {
                 /* the reference's CAND pass, straight from global memory: quad k measures neighbour k */
@@ -683,13 +706,13 @@ search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restrict__ pl
                 SSTAT_ADD(14, 1);
             }
             /* ---- the MVP, exactly as slicetype.cpp:2130-2150 ---- */
-            const long long tp3 = SSTAT_CLOCK();
+            SSTAT_T(tp3);
             LaSearch s;
             la_search_begin(s, cuX, cuY, W, H, bidir, numc, nb0, nb1, nb2, nb3);
             la_upd_cand(s, k0, k1, k2, k3);
             const int mvp = la_pack_mv(s.mvpx, s.mvpy);
             const int im = memo_find(e, mvp);
-            const long long tp4 = SSTAT_CLOCK();
+            SSTAT_T(tp4);
             int rMv, rCost;
             if (im >= 0) { rMv = __shfl_sync(FULL_MASK, e.z, im); rCost = __shfl_sync(FULL_MASK, e.w, im); }
             else
@@ -708,7 +731,7 @@ search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restrict__ pl
                              cuX, cuY, W, H, mvp, rMv, rCost, cs, cok);
                 SSTAT_ADD(1, 1);
             }
-            const long long tp5 = SSTAT_CLOCK();
+            SSTAT_T(tp5);
             SSTAT_ADD(20, tp1 - tp0); SSTAT_ADD(21, tp2 - tp1); SSTAT_ADD(22, tp3 - tp2); SSTAT_ADD(23, tp4 - tp3); SSTAT_ADD(24, tp5 - tp4);
             if (!ok) { SSTAT_ADD(25, tp3 - tp2); SSTAT_ADD(26, 1); }
             s.outx = la_mv_x(rMv); s.outy = la_mv_y(rMv); s.outcost = rCost;

@@ -1,0 +1,226 @@
+/* x265cu_search_plain.cuh -- the plain wavefront motion-search kernel (sm_100a).
+ *
+ * The search of one reference list of one estimate (encoder/slicetype.cpp:2106-2160 + the lowres branch of
+ * MotionEstimate::motionEstimate, encoder/motion.cpp:571-1172) WITHOUT speculation: one warp per CU row, rows advance
+ * as a wavefront, per CU the warp runs the la_core.h state machine one pass (<= 8 candidates, one per quad) at a time.
+ * Least work per CU, so it is what a batch runs when the GPU is filled by independent searches (throughput-bound) or
+ * when no usable hint field exists; x265cu_search.cuh holds the speculative path for latency-bound searches.
+ *
+ * Row groups of a few CU rows per CTA spread one slice over many SMs.  A finished CU publishes ONE 64-bit word
+ * {tag = 1, packed MV}: tag and data travel in the same naturally aligned 8-byte store, so there is no separate
+ * progress counter and no fence on the chain.  Inside a group the words live in shared memory, between groups in a
+ * global hand-off row (L2).  A group only waits for a group with a LOWER block index (launched earlier), so the scheme
+ * cannot deadlock even when a launch does not fit the GPU.  Passes are branch-free: every quad always measures a
+ * (valid-address) block and invalid candidates are masked out of the key reduction.
+ */
+#ifndef X265CU_SEARCH_PLAIN_CUH
+#define X265CU_SEARCH_PLAIN_CUH
+
+#define PLAIN_MAX_GROUP_ROWS 8
+
+template <typename P>
+__global__ void __launch_bounds__(PLAIN_MAX_GROUP_ROWS * 32, 3)
+plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restrict__ plans, const SearchItem* __restrict__ items, GeomDev g,
+                    const uint16_t* __restrict__ lut, unsigned long long* gHand)
+{
+    extern __shared__ unsigned long long sHand[];  /* [rows of the group][W] hand-off words */
+    const SearchItem it = items[blockIdx.x];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nRows = it.lastY - it.firstY + 1;
+    const int W = g.wCU, H = g.hCU;
+    for (int i = threadIdx.x; i < nRows * W; i += blockDim.x) sHand[i] = 0;
+    const SearchPlan pl = plans[it.search];
+    const JobDev* __restrict__ jp = jobs + pl.job;
+    const int list = pl.list;
+    {
+        /* Stream this group's band of the source plane and of the four reference planes into L2
+         * before the dependent chain starts: a single estimate reads frames that left L2 long
+         * ago, and a DRAM miss inside a pass stalls the whole chain for ~1 us.  Fire and forget. */
+        const int bandRows = (it.lastY - it.firstY + 1) * 8 + 64;           /* +-32 rows of search range */
+        const int bandTop = it.firstY * 8 - 32;
+        const int linesPerRow = (g.width + 64) * (int)sizeof(P) / 128 + 1;
+        const char* fencB = (const char*)jp->fenc;
+        const char* refB = (const char*)(list ? jp->ref1 : jp->ref0w);
+        const int total = bandRows * linesPerRow * 5;
+        for (int i = threadIdx.x; i < total; i += blockDim.x)
+        {
+            const int plane = i / (bandRows * linesPerRow);                  /* 0..3 reference planes, 4 = source */
+            const int rem = i - plane * bandRows * linesPerRow;
+            const int row = bandTop + rem / linesPerRow, line = rem % linesPerRow;
+            if (plane == 4 && (row < it.firstY * 8 || row >= (it.lastY + 1) * 8)) continue;
+            const char* base = plane == 4 ? fencB : refB + (int64_t)plane * g.planeSize * (int)sizeof(P);
+            const char* ptr = base + ((int64_t)row * g.stride - 32) * (int)sizeof(P) + line * 128;
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(ptr));
+        }
+    }
+    __syncthreads();
+    if (warp >= nRows) return;
+
+    const int q = lane >> 2, sub = lane & 3, bx = (sub & 1) * 4, by = (sub >> 1) * 4;
+    const int stride = g.stride, planeSize = (int)g.planeSize;
+    const int bidir = jp->bidir;
+    const P* __restrict__ fencPlane = (const P*)jp->fenc;
+    const P* __restrict__ refPlane = (const P*)(list ? jp->ref1 : jp->ref0w);
+    int* __restrict__ mvMirror = jp->mvs[list];
+    int* __restrict__ mcMirror = jp->mvCosts[list];
+    int* __restrict__ mvOut = jp->outMvs[list];
+    int* __restrict__ mcOut = jp->outMvCosts[list];
+
+    /* warp r owns row cuY = lastY - r; it depends on row cuY + 1 */
+    const int cuY = it.lastY - warp;
+    const bool lastRow = cuY == it.sliceLastY;              /* bottom row of the slice: no candidates from below */
+    const bool publishGlobal = warp == nRows - 1 && it.pubBase >= 0;
+    volatile unsigned long long* myHand = sHand + warp * W;
+    volatile unsigned long long* myHandG = gHand + (it.pubBase >= 0 ? it.pubBase : 0);
+    volatile const unsigned long long* below = (warp == 0) ? (volatile const unsigned long long*)(gHand + (it.subBase >= 0 ? it.subBase : 0))
+                                                           : (volatile const unsigned long long*)(sHand + (warp - 1) * W);
+
+    /* per-lane candidate geometry of the fixed-shape passes (motion.cpp:64-66 tables) */
+    const int hex6dx = la_hex2x((q + 1) & 7), hex6dy = la_hex2y((q + 1) & 7);
+    const int hex6off = hex6dy * stride + hex6dx;
+    const int sq8dx = la_sq1x(q + 1), sq8dy = la_sq1y(q + 1);
+    const int sq8off = sq8dy * stride + sq8dx;
+    const int hpdx = la_sq1x((q + 1) & 7) * 2, hpdy = la_sq1y((q + 1) & 7) * 2;   /* quarter-pel units */
+    const int qpdx = la_sq1x(q), qpdy = la_sq1y(q);
+
+    const int rowBase = (8 * cuY + by) * stride + bx;
+    int prevMv = 0;                                /* MV of (cuX + 1, cuY): our own previous result */
+    typename Px<P>::Row4 fe[4], feNext[4];
+#pragma unroll
+    for (int y = 0; y < 4; y++)
+        feNext[y] = Px<P>::load_aligned(fencPlane + rowBase + 8 * (W - 1) + y * stride);
+
+    for (int cuX = W - 1; cuX >= 0; cuX--)
+    {
+#pragma unroll
+        for (int y = 0; y < 4; y++) fe[y] = feNext[y];
+        if (cuX > 0)
+        {
+#pragma unroll
+            for (int y = 0; y < 4; y++)
+                feNext[y] = Px<P>::load_aligned(fencPlane + rowBase + 8 * (cuX - 1) + y * stride);
+        }
+        const P* __restrict__ refLane = refPlane + rowBase + 8 * cuX;
+        if (cuX > 0)
+        {
+            /* pull the likely window of the NEXT CU (same MV as our right neighbour, 8 samples to the
+             * left) into L1 while this CU is being searched: 16 rows x 4 planes, two sectors per row */
+            const int prow = (lane & 15) - 4, pplane = lane >> 4;
+            const P* w = refPlane + (8 * cuY + (la_mv_y(prevMv) >> 2) + prow) * stride + 8 * (cuX - 1) + (la_mv_x(prevMv) >> 2) - 4;
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(w + pplane * planeSize));
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(w + pplane * planeSize + 16));
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(w + (pplane + 2) * planeSize));
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(w + (pplane + 2) * planeSize + 16));
+        }
+
+        /* ---- neighbour MVs (slicetype.cpp:2117-2128): right, below, below-left, below-right ---- */
+        int nb0 = 0, nb1 = 0, nb2 = 0, nb3 = 0, numc = 0;
+        if (cuX < W - 1) { nb0 = prevMv; numc = 1; }
+        if (!lastRow)
+        {
+            /* the row below runs right to left: its column cuX - 1 is published last */
+            int bl = 0, br = 0;
+            if (cuX > 0) bl = hand_wait(below + cuX - 1);
+            const int mb = hand_wait(below + cuX);
+            if (cuX < W - 1) br = hand_wait(below + cuX + 1);
+            if (numc == 0) nb0 = mb; else nb1 = mb;
+            numc++;
+            if (cuX > 0) { if (numc == 1) nb1 = bl; else nb2 = bl; numc++; }
+            if (cuX < W - 1) { if (numc == 2) nb2 = br; else nb3 = br; numc++; }
+        }
+        LaSearch s;
+        la_search_begin(s, cuX, cuY, W, H, bidir, numc, nb0, nb1, nb2, nb3);
+
+        /* ---- CAND: SATD at each neighbour MV, no mvcost (quads >= numc re-measure candidate 0) ---- */
+        if (numc)
+        {
+            const int p = la_cand_mv(s, q < numc ? q : 0);
+            typename Px<P>::Row4 r[4];
+            fetch_qpel<P>(refLane, planeSize, stride, la_mv_x(p), la_mv_y(p), r);
+            const int cost = quad_sum(satd4x4_abs<P>(fe, r)) >> 1;
+            la_upd_cand(s, __shfl_sync(FULL_MASK, cost, 0), __shfl_sync(FULL_MASK, cost, 4),
+                        __shfl_sync(FULL_MASK, cost, 8), __shfl_sync(FULL_MASK, cost, 12));
+        }
+        const uint16_t* __restrict__ lutx = lut - s.mvpx;
+        const uint16_t* __restrict__ luty = lut - s.mvpy;
+
+        /* ---- START: q0 = qpel MVP (no mvcost), q1 = rounded MVP, q2 = zero ---- */
+        la_enter_start(s);
+        {
+            const int qx = q == 0 ? s.pmx : (q == 1 ? ((s.pmx + 2) >> 2) * 4 : 0);
+            const int qy = q == 0 ? s.pmy : (q == 1 ? ((s.pmy + 2) >> 2) * 4 : 0);
+            typename Px<P>::Row4 r[4];
+            fetch_qpel<P>(refLane, planeSize, stride, qx, qy, r);
+            const int mvc = q == 0 ? 0 : lutx[qx] + luty[qy];
+            const int cost = quad_sum(sad4x4<P>(fe, r)) + mvc;
+            la_upd_start(s, __shfl_sync(FULL_MASK, cost, 0), __shfl_sync(FULL_MASK, cost, 4), __shfl_sync(FULL_MASK, cost, 8));
+        }
+
+        /* ---- HEX6 + HEX3 rounds: full-pel SAD + mvcost ---- */
+        {
+            const int fx = s.bmx + hex6dx, fy = s.bmy + hex6dy;
+            typename Px<P>::Row4 r[4];
+            fetch_off<P>(refLane, stride, s.bmy * stride + s.bmx + hex6off, r);
+            const int cost = quad_sum(sad4x4<P>(fe, r)) + lutx[fx * 4] + luty[fy * 4];
+            bool more = la_upd_hex6(s, warp_min_key(q < 6, cost, q));
+            while (more)
+            {
+                const int hdx = la_hex2x((s.dir + q) & 7), hdy = la_hex2y((s.dir + q) & 7);
+                const int hx = s.bmx + hdx, hy = s.bmy + hdy;
+                typename Px<P>::Row4 r3[4];
+                fetch_off<P>(refLane, stride, hy * stride + hx, r3);
+                const int c3 = quad_sum(sad4x4<P>(fe, r3)) + lutx[hx * 4] + luty[hy * 4];
+                more = la_upd_hex3(s, warp_min_key(q < 3, c3, q));
+            }
+        }
+
+        /* ---- SQ8: 8-point square ---- */
+        bool subpel;
+        {
+            const int fx = s.bmx + sq8dx, fy = s.bmy + sq8dy;
+            typename Px<P>::Row4 r[4];
+            fetch_off<P>(refLane, stride, s.bmy * stride + s.bmx + sq8off, r);
+            const int cost = quad_sum(sad4x4<P>(fe, r)) + lutx[fx * 4] + luty[fy * 4];
+            subpel = la_upd_sq8(s, warp_min_key(true, cost, q), lut);
+        }
+
+        if (subpel)
+        {
+            /* ---- HPEL: 4 half-pel SADs ---- */
+            {
+                const int qx = s.bmx + hpdx, qy = s.bmy + hpdy;
+                typename Px<P>::Row4 r[4];
+                fetch_qpel<P>(refLane, planeSize, stride, qx, qy, r);
+                const int cost = quad_sum(sad4x4<P>(fe, r)) + lutx[qx] + luty[qy];
+                la_upd_hpel(s, warp_min_key(q < 4, cost, q));
+            }
+            /* ---- QPEL: SATD re-measure (q0) + 4 quarter-pel SATDs ---- */
+            {
+                const int qx = s.bmx + qpdx, qy = s.bmy + qpdy;
+                typename Px<P>::Row4 r[4];
+                fetch_qpel<P>(refLane, planeSize, stride, qx, qy, r);
+                const int cost = (quad_sum(satd4x4_abs<P>(fe, r)) >> 1) + lutx[qx] + luty[qy];
+                const int c0 = __shfl_sync(FULL_MASK, cost, 0);
+                la_upd_qpel(s, c0, warp_min_key(q >= 1 && q < 5, cost, q));
+            }
+        }
+        la_finish_skip(s);
+
+        const int mvPacked = la_pack_mv(s.outx, s.outy);
+        prevMv = mvPacked;
+        if (lane == 0)
+        {
+            const unsigned long long word = HAND_TAG | (uint32_t)mvPacked;
+            const int cuXY = cuX + cuY * W;
+            myHand[cuX] = word;
+            if (publishGlobal) myHandG[cuX] = word;
+            mvMirror[cuXY] = mvPacked;
+            mcMirror[cuXY] = s.outcost;
+            mvOut[cuXY] = mvPacked;
+            mcOut[cuXY] = s.outcost;
+        }
+    }
+}
+
+
+#endif /* X265CU_SEARCH_PLAIN_CUH */

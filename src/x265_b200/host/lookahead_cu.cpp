@@ -402,6 +402,66 @@ bool Lookahead::preLookahead(Lowres& l, const void* y, intptr_t yStride, const v
     return true;
 }
 
+/* PreLookaheadGroup::processTasks for its whole list m_preframes[0..m_jobTotal) (slicetype.cpp:831-856): the reference
+ * spreads the frames of the list over worker threads; here the uploads and kernels of all of them are enqueued back to
+ * back and the host waits once per stage (lowres + variance, then intra) instead of twice per frame. */
+bool Lookahead::preLookaheadBatch(int n, Lowres** ls, const PictureIn* pics, bool copyPlanesBack)
+{
+    const bool needVar = m_bAdaptiveQuant && (!(m_param.aqMode == 0 || m_param.aqStrength == 0) || m_param.bEnableWeightedPred);
+    if (!needVar || n < 2)
+    {
+        for (int i = 0; i < n; i++)
+            if (!preLookahead(*ls[i], pics[i].y, pics[i].yStride, pics[i].u, pics[i].v, pics[i].cStride, pics[i].poc, copyPlanesBack)) return false;
+        return true;
+    }
+    const int blocks = ((m_param.sourceWidth + 15) / 16) * ((m_param.sourceHeight + 15) / 16);
+    std::vector<uint32_t> energy((size_t)blocks * n);
+    std::vector<uint64_t> sums((size_t)6 * n);
+    std::vector<x265cu_frame_in> items((size_t)n);
+    for (int i = 0; i < n; i++)
+    {
+        lowresReset(*ls[i], pics[i].poc);
+        x265cu_frame_in& f = items[i];
+        f.slot = ls[i]->slot;
+        f.y = pics[i].y; f.yStride = pics[i].yStride; f.u = pics[i].u; f.v = pics[i].v; f.cStride = pics[i].cStride;
+        f.planesAreDevice = m_resident ? 1 : 0;
+        f.planesOut = (copyPlanesBack && !m_resident) ? ls[i]->buffer[0] : NULL;
+        f.energy = &energy[(size_t)blocks * i];
+        f.sums = &sums[(size_t)6 * i];
+    }
+    int r = x265cu_frame_init_var_batch(m_ctx, n, &items[0]);
+    if (r) { snprintf(m_error, sizeof(m_error), "x265cu_frame_init_var_batch: %s", x265cu_last_error(m_ctx)); return false; }
+    for (int i = 0; i < n; i++)
+        if (!calcAdaptiveQuantFrame(*ls[i], pics[i].y, pics[i].yStride, pics[i].u, pics[i].v, pics[i].cStride, items[i].energy, items[i].sums)) return false;
+
+    std::vector<x265cu_intra_out> outs((size_t)n);
+    std::vector<int> slots((size_t)n);
+    for (int i = 0; i < n; i++)
+    {
+        Lowres& l = *ls[i];
+        x265cu_intra_out& o = outs[i];
+        o.intraCost = l.intraCost; o.intraMode = l.intraMode;
+        o.lowresCosts = l.lowresCosts[0][0]; o.rowSatds = l.rowSatds[0][0];
+        if (m_resident)
+        {
+            o.intraCost = NULL; o.intraMode = NULL; o.lowresCosts = NULL; o.rowSatds = NULL;
+            l.rowSatds[0][0][0] = 0;
+        }
+        slots[i] = l.slot;
+    }
+    r = x265cu_intra_batch(m_ctx, n, &slots[0], &outs[0]);
+    if (r) { snprintf(m_error, sizeof(m_error), "x265cu_intra_batch: %s", x265cu_last_error(m_ctx)); return false; }
+    for (int i = 0; i < n; i++)
+    {
+        Lowres& l = *ls[i];
+        l.costEst[0][0] = outs[i].sums[0];
+        l.costEstAq[0][0] = outs[i].sums[1];
+        l.ready = true;
+        m_byPoc[pics[i].poc] = &l;
+    }
+    return true;
+}
+
 /* ------------------------------------------------------------------------------------------
  * CostEstimateGroup, encoder/slicetype.cpp:1899-2066
  * ---------------------------------------------------------------------------------------- */
@@ -842,6 +902,17 @@ void x265cuh_frame_free(void* la, void* f) { ((Lookahead*)la)->freeLowres((Lowre
 int x265cuh_pre_lookahead(void* la, void* frame, const void* y, intptr_t ys, const void* u, const void* v, intptr_t cs, int poc, int planesBack)
 {
     return ((Lookahead*)la)->preLookahead(*(Lowres*)frame, y, ys, u, v, cs, poc, planesBack != 0) ? 0 : -1;
+}
+
+int x265cuh_pre_lookahead_batch(void* la, int n, void** frames, const void* const* y, const intptr_t* ys, const void* const* u, const void* const* v,
+                                const intptr_t* cs, const int* pocs, int planesBack)
+{
+    std::vector<Lookahead::PictureIn> pics((size_t)n);
+    for (int i = 0; i < n; i++)
+    {
+        pics[i].y = y[i]; pics[i].yStride = ys[i]; pics[i].u = u[i]; pics[i].v = v[i]; pics[i].cStride = cs[i]; pics[i].poc = pocs[i];
+    }
+    return ((Lookahead*)la)->preLookaheadBatch(n, (Lowres**)frames, n ? &pics[0] : NULL, planesBack != 0) ? 0 : -1;
 }
 
 int x265cuh_estimate(void* h, void** frames, int nframes, const int* triples, int n, int batch, int64_t* scores)

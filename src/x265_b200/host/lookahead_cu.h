@@ -153,6 +153,10 @@ public:
     /* PreLookaheadGroup::processTasks for one frame */
     bool preLookahead(Lowres& l, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride, int poc, bool copyPlanesBack);
 
+    /* PreLookaheadGroup::processTasks for a list of frames: one wait per stage instead of two per frame */
+    struct PictureIn { const void* y; intptr_t yStride; const void* u; const void* v; intptr_t cStride; int poc; };
+    bool preLookaheadBatch(int n, Lowres** frames, const PictureIn* pics, bool copyPlanesBack);
+
     int64_t ncu() const { return m_8x8Blocks; }
     static void mvcostTable(int bitDepth, uint16_t* out131073, int* lambdaInt);
 };
@@ -203,6 +207,8 @@ uint32_t x265cuh_mvcost_crc(void* la);
 void* x265cuh_frame_alloc(void* la);
 void  x265cuh_frame_free(void* la, void* frame);
 int   x265cuh_pre_lookahead(void* la, void* frame, const void* y, intptr_t ys, const void* u, const void* v, intptr_t cs, int poc, int planesBack);
+int   x265cuh_pre_lookahead_batch(void* la, int n, void** frames, const void* const* y, const intptr_t* ys, const void* const* u, const void* const* v,
+                                  const intptr_t* cs, const int* pocs, int planesBack);
 /* jobs: n triples (p0, p1, b) as indices into frames[]; batch != 0 -> add()+finishBatch(), else singleCost() each */
 int   x265cuh_estimate(void* la, void** frames, int nframes, const int* triples, int n, int batch, int64_t* scores);
 /* array accessors for checks: which = 0 planes, 1 intraCost, 2 intraMode, 3 invQscale, 4 lowresCosts[d0][d1],
