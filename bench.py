@@ -169,7 +169,8 @@ class Runner:
             else:
                 # pinned host pictures (the encoder's PicYuv, registered once)
                 for a in (y, u, v):
-                    abi.lib_cu().x265cu_host_register(a.ctypes.data, a.nbytes)
+                    b = a.base if a.base is not None else a     # the picture is a view into its margin-padded buffer
+                    abi.lib_cu().x265cu_host_register(b.ctypes.data, b.nbytes)
                 self.keepalive += [y, u, v]
                 self.inputs[t] = (y.ctypes.data, y.strides[0] // y.itemsize, u.ctypes.data, v.ctypes.data, u.strides[0] // u.itemsize)
         # pre-marshal the call sequence
@@ -210,7 +211,8 @@ class Runner:
             self.la.frame_free(f)
         if not self.resident:
             for a in self.keepalive:
-                self.abi.lib_cu().x265cu_host_unregister(a.ctypes.data)
+                b = a.base if a.base is not None else a
+                self.abi.lib_cu().x265cu_host_unregister(b.ctypes.data)
         self.la.close()
 
 

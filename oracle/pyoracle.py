@@ -240,7 +240,12 @@ def pad_picture(p, extra, chroma_of=None):
         lw, lh = chroma_of
         padx = (((16 - (lw & 15)) & 15) + 1) >> 1
         pady = (((16 - (lh & 15)) & 15) + 1) >> 1
-    out = np.empty((h + pady, w + padx), p.dtype)
+    # rows live in a wider backing array, like PicYuv's planes inside their margins (picyuv.cpp:62-75): the view's
+    # row pitch is a multiple of 64 samples, as an encoder's picture buffers are
+    margin = 96 if chroma_of is None else 48
+    pitch = (w + padx + 2 * margin + 63) // 64 * 64
+    backing = np.zeros((h + pady, pitch), p.dtype)
+    out = backing[:, margin:margin + w + padx]
     out[:h, :w] = p
     out[:h, w:] = p[:, w - 1:w]
     out[h:, :] = out[h - 1:h, :]
@@ -355,9 +360,9 @@ class OracleReplay:
         poc = e["poc"]
         f = OFrame(self.lib, self.depth, w, h, 96, 80, cfg["bframes"], cfg["aqmode"] != 0)
         y, u, v = synth_padded(self.lib, self.depth, w, h, poc, cfg["nframes"], cfg["seed"])
-        self.lib.ola_frame_init(f.p, y.ctypes.data, y.shape[1], poc)
+        self.lib.ola_frame_init(f.p, y.ctypes.data, y.strides[0] // y.itemsize, poc)
         if cfg["aqmode"] or cfg["weightp"]:
-            self.lib.ola_aq_frame(f.p, y.ctypes.data, y.shape[1], u.ctypes.data, v.ctypes.data, u.shape[1],
+            self.lib.ola_aq_frame(f.p, y.ctypes.data, y.strides[0] // y.itemsize, u.ctypes.data, v.ctypes.data, u.strides[0] // u.itemsize,
                                   cfg["aqmode"], cfg["aqStrength"], cfg["weightp"])
         self.lib.ola_intra_estimate(f.p, 1 if self.depth == 8 else 16)
         tag = "P%d." % poc

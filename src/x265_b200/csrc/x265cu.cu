@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <vector>
 
@@ -60,6 +61,9 @@ struct x265cu_ctx
     uint16_t* dLut;        /* base; centre at +65536 */
     uint8_t* dSrc;         /* full-resolution luma staging (strided-copy fallback) */
     uint8_t* dSrcLin; size_t dSrcLinCap;   /* luma staging with the host's pitch (linear transfer) */
+    uint8_t* dUp; size_t dUpCap;           /* per-frame staging of a batched pre-lookahead list */
+    cudaStream_t upStream;                 /* its uploads */
+    std::vector<cudaEvent_t> upEvents;
     int64_t srcPitch;      /* samples */
     unsigned long long* dSmall;   /* small scratch for sums */
 
@@ -203,7 +207,9 @@ void freeAll(x265cu_ctx* c)
 {
     cudaFree(c->dPlanes); cudaFree(c->dIntraCost); cudaFree(c->dIntraMode); cudaFree(c->dInvQ);
     cudaFree(c->dLowresCosts); cudaFree(c->dRowSatds); cudaFree(c->dMvs); cudaFree(c->dMvCosts);
-    cudaFree(c->dLut); cudaFree(c->dSrc); cudaFree(c->dSmall); cudaFree(c->dStage); cudaFree(c->dArgs); cudaFree(c->dGeneric); cudaFree(c->dMemo); cudaFree(c->dSrcLin);
+    cudaFree(c->dLut); cudaFree(c->dSrc); cudaFree(c->dSmall); cudaFree(c->dStage); cudaFree(c->dArgs); cudaFree(c->dGeneric); cudaFree(c->dMemo); cudaFree(c->dSrcLin); cudaFree(c->dUp);
+    if (c->upStream) cudaStreamDestroy(c->upStream);
+    for (size_t i = 0; i < c->upEvents.size(); i++) cudaEventDestroy(c->upEvents[i]);
     if (c->hStage) cudaFreeHost(c->hStage);
     if (c->hArgs) cudaFreeHost(c->hArgs);
     if (c->hPre) cudaFreeHost(c->hPre);
@@ -253,7 +259,7 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     c->err[0] = 0;
     c->dPlanes = NULL; c->dIntraCost = NULL; c->dIntraMode = NULL; c->dInvQ = NULL; c->dLowresCosts = NULL; c->dRowSatds = NULL;
     c->dMvs = NULL; c->dMvCosts = NULL; c->dLut = NULL; c->dSrc = NULL; c->dSmall = NULL;
-    c->dStage = NULL; c->dStageCap = 0; c->hStage = NULL; c->hStageCap = 0; c->dArgs = NULL; c->dArgsCap = 0; c->hArgs = NULL; c->hArgsCap = 0; c->hPre = NULL; c->hPreCap = 0; c->dSrcLin = NULL; c->dSrcLinCap = 0;
+    c->dStage = NULL; c->dStageCap = 0; c->hStage = NULL; c->hStageCap = 0; c->dArgs = NULL; c->dArgsCap = 0; c->hArgs = NULL; c->hArgsCap = 0; c->hPre = NULL; c->hPreCap = 0; c->dSrcLin = NULL; c->dSrcLinCap = 0; c->dUp = NULL; c->dUpCap = 0; c->upStream = NULL;
     c->dGeneric = NULL; c->dGenericCap = 0; c->dMemo = NULL; c->dMemoCap = 0;
     c->timing = false;
     memset(&c->stats, 0, sizeof(c->stats));
@@ -438,14 +444,22 @@ int x265cu_frame_init_var(x265cu_ctx* c, int slot, const void* y, intptr_t yStri
 
 /* enqueue Lowres::init (and acEnergyCu's integer part when varEnergy != NULL) of one frame on the ctx stream; no
  * synchronisation: varEnergy / varSums (6 x u64) are filled once the stream has drained.  Caller holds the lock. */
+struct Uploaded { const uint8_t *y, *u, *v; };   /* picture already on the device with the host's pitches (batched uploads) */
+
 static int frameInitEnqueue(x265cu_ctx* c, int slot, const void* luma, intptr_t srcStride, int lumaIsDevice, void* planesOut,
-                            const void* u, const void* v, intptr_t cStride, uint32_t* varEnergy, unsigned long long* varSums)
+                            const void* u, const void* v, intptr_t cStride, uint32_t* varEnergy, unsigned long long* varSums,
+                            const Uploaded* up = NULL)
 {
     if (!luma || badSlot(c, slot) || srcStride < 2 * c->g.width + 1) return fail(c, X265CU_EINVAL, "x265cu_frame_init: bad argument");
     const GeomDev& g = c->g;
     const void* src = luma;
     int64_t pitch = srcStride;
-    if (!lumaIsDevice)
+    if (up)
+    {
+        src = up->y;
+        pitch = srcStride;
+    }
+    else if (!lumaIsDevice)
     {
         /* (2W+1) x (2H+1) samples for the downscale; that also covers the 16-aligned picture pixel_var reads */
         size_t wbytes = (size_t)(2 * g.width + 1) * c->pb;
@@ -511,7 +525,8 @@ static int frameInitEnqueue(x265cu_ctx* c, int slot, const void* luma, intptr_t 
         if (growDevice(c, &c->dGeneric, &c->dGenericCap, 2 * cBytes + eBytes + 256)) return X265CU_ECUDA;
         uint8_t* dU = c->dGeneric; uint8_t* dV = dU + cBytes; unsigned int* dE = (unsigned int*)(dV + cBytes);
         int64_t cpitch = (int64_t)cp;
-        if (u && !lumaIsDevice)
+        if (u && up) { dU = (uint8_t*)up->u; dV = (uint8_t*)up->v; }
+        else if (u && !lumaIsDevice)
         {
             CU_TRY(c, cudaMemcpyAsync(dU, u, cLin, cudaMemcpyHostToDevice, c->stream));
             CU_TRY(c, cudaMemcpyAsync(dV, v, cLin, cudaMemcpyHostToDevice, c->stream));
@@ -560,16 +575,70 @@ int x265cu_frame_init_var_batch(x265cu_ctx* c, int n, const x265cu_frame_in* ite
     const int bxN = (c->cfg.srcWidth + 15) / 16, byN = (c->cfg.srcHeight + 15) / 16;
     const size_t eBytes = alignUp((size_t)bxN * byN * 4, 64), per = eBytes + 64;
     if (growHost(c, &c->hPre, &c->hPreCap, (size_t)n * per)) return X265CU_ECUDA;
+    const bool dbgPre = getenv("X265CU_PRE_DEBUG") != NULL;
+    std::chrono::steady_clock::time_point tA = std::chrono::steady_clock::now(), tB = tA, tC = tA;
+    /* host pictures: every frame gets its own staging area and its uploads run on the upload stream, so frame i + 1
+     * crosses PCIe while frame i is being downscaled / measured (one linear transfer per plane, host pitch kept) */
+    const GeomDev& g = c->g;
+    const size_t lumaRows = (size_t)2 * g.lines + 1, chromaRows = (size_t)byN * 8;
+    bool pipelined = true;
+    std::vector<size_t> off((size_t)n + 1, 0);
     for (int i = 0; i < n; i++)
     {
         const x265cu_frame_in& f = items[i];
-        if (!f.energy || !f.sums || ((f.u == NULL) != (f.v == NULL))) return fail(c, X265CU_EINVAL, "x265cu_frame_init_var_batch: bad item");
-        int r = frameInitEnqueue(c, f.slot, f.y, f.yStride, f.planesAreDevice, f.planesOut, f.u, f.v, f.cStride,
-                                 (uint32_t*)(c->hPre + (size_t)i * per), (unsigned long long*)(c->hPre + (size_t)i * per + eBytes));
-        if (r) { cudaStreamSynchronize(c->stream); return r; }
+        if (!f.energy || !f.sums || ((f.u == NULL) != (f.v == NULL)) || !f.y) return fail(c, X265CU_EINVAL, "x265cu_frame_init_var_batch: bad item");
+        if (f.planesAreDevice || !f.u || (((size_t)f.yStride * c->pb) & 7) || f.yStride < 2 * g.width + 1) pipelined = false;
+        const size_t yLin = (lumaRows - 1) * (size_t)f.yStride * c->pb + (size_t)(2 * g.width + 1) * c->pb;
+        const size_t cLin = f.u ? (chromaRows - 1) * (size_t)f.cStride * c->pb + (size_t)bxN * 8 * c->pb : 0;
+        off[i + 1] = off[i] + alignUp(yLin, 256) + 2 * alignUp(cLin, 256);
     }
+    if (pipelined)
+    {
+        if (growDevice(c, &c->dUp, &c->dUpCap, off[n] + 256)) return X265CU_ECUDA;
+        if (!c->upStream) CU_TRY(c, cudaStreamCreateWithFlags(&c->upStream, cudaStreamNonBlocking));
+        while ((int)c->upEvents.size() < n)
+        {
+            cudaEvent_t e;
+            CU_TRY(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->upEvents.push_back(e);
+        }
+        for (int i = 0; i < n; i++)
+        {
+            const x265cu_frame_in& f = items[i];
+            const size_t yLin = (lumaRows - 1) * (size_t)f.yStride * c->pb + (size_t)(2 * g.width + 1) * c->pb;
+            const size_t cLin = (chromaRows - 1) * (size_t)f.cStride * c->pb + (size_t)bxN * 8 * c->pb;
+            uint8_t* dY = c->dUp + off[i]; uint8_t* dU = dY + alignUp(yLin, 256); uint8_t* dV = dU + alignUp(cLin, 256);
+            CU_TRY(c, cudaMemcpyAsync(dY, f.y, yLin, cudaMemcpyHostToDevice, c->upStream));
+            CU_TRY(c, cudaMemcpyAsync(dU, f.u, cLin, cudaMemcpyHostToDevice, c->upStream));
+            CU_TRY(c, cudaMemcpyAsync(dV, f.v, cLin, cudaMemcpyHostToDevice, c->upStream));
+            CU_TRY(c, cudaEventRecord(c->upEvents[i], c->upStream));
+            c->stats.h2dBytes += (int64_t)(yLin + 2 * cLin);
+        }
+    }
+    tB = std::chrono::steady_clock::now();
+    for (int i = 0; i < n; i++)
+    {
+        const x265cu_frame_in& f = items[i];
+        Uploaded up;
+        if (pipelined)
+        {
+            const size_t yLin = (lumaRows - 1) * (size_t)f.yStride * c->pb + (size_t)(2 * g.width + 1) * c->pb;
+            const size_t cLin = (chromaRows - 1) * (size_t)f.cStride * c->pb + (size_t)bxN * 8 * c->pb;
+            up.y = c->dUp + off[i]; up.u = up.y + alignUp(yLin, 256); up.v = up.u + alignUp(cLin, 256);
+            CU_TRY(c, cudaStreamWaitEvent(c->stream, c->upEvents[i], 0));
+        }
+        int r = frameInitEnqueue(c, f.slot, f.y, f.yStride, f.planesAreDevice, f.planesOut, f.u, f.v, f.cStride,
+                                 (uint32_t*)(c->hPre + (size_t)i * per), (unsigned long long*)(c->hPre + (size_t)i * per + eBytes),
+                                 pipelined ? &up : NULL);
+        if (r) { cudaStreamSynchronize(c->stream); if (c->upStream) cudaStreamSynchronize(c->upStream); return r; }
+    }
+    tC = std::chrono::steady_clock::now();
     int r = syncStream(c);
     if (r) return r;
+    if (dbgPre)
+        fprintf(stderr, "  frame_init_var_batch n=%d pipelined=%d: upload submit %.2f ms, enqueue %.2f ms, wait %.2f ms\n", n, (int)pipelined,
+                std::chrono::duration<double, std::milli>(tB - tA).count(), std::chrono::duration<double, std::milli>(tC - tB).count(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tC).count());
     for (int i = 0; i < n; i++)
     {
         memcpy(items[i].energy, c->hPre + (size_t)i * per, (size_t)bxN * byN * 4);

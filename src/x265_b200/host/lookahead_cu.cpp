@@ -1,5 +1,6 @@
 /* lookahead_cu.cpp -- see lookahead_cu.h.  Host layer above the C ABI; float decisions only. */
 #include "lookahead_cu.h"
+#include <chrono>
 
 #include <math.h>
 #include <stdio.h>
@@ -429,10 +430,14 @@ bool Lookahead::preLookaheadBatch(int n, Lowres** ls, const PictureIn* pics, boo
         f.energy = &energy[(size_t)blocks * i];
         f.sums = &sums[(size_t)6 * i];
     }
+    const bool dbg = getenv("X265CU_PRE_DEBUG") != NULL;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     int r = x265cu_frame_init_var_batch(m_ctx, n, &items[0]);
     if (r) { snprintf(m_error, sizeof(m_error), "x265cu_frame_init_var_batch: %s", x265cu_last_error(m_ctx)); return false; }
+    std::chrono::steady_clock::time_point t1 = std::chrono::steady_clock::now();
     for (int i = 0; i < n; i++)
         if (!calcAdaptiveQuantFrame(*ls[i], pics[i].y, pics[i].yStride, pics[i].u, pics[i].v, pics[i].cStride, items[i].energy, items[i].sums)) return false;
+    std::chrono::steady_clock::time_point t2 = std::chrono::steady_clock::now();
 
     std::vector<x265cu_intra_out> outs((size_t)n);
     std::vector<int> slots((size_t)n);
@@ -451,6 +456,13 @@ bool Lookahead::preLookaheadBatch(int n, Lowres** ls, const PictureIn* pics, boo
     }
     r = x265cu_intra_batch(m_ctx, n, &slots[0], &outs[0]);
     if (r) { snprintf(m_error, sizeof(m_error), "x265cu_intra_batch: %s", x265cu_last_error(m_ctx)); return false; }
+    if (dbg)
+    {
+        std::chrono::steady_clock::time_point t3 = std::chrono::steady_clock::now();
+        fprintf(stderr, "preLookaheadBatch n=%d: init+var %.2f ms, AQ host %.2f ms, intra %.2f ms\n", n,
+                std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count(),
+                std::chrono::duration<double, std::milli>(t3 - t2).count());
+    }
     for (int i = 0; i < n; i++)
     {
         Lowres& l = *ls[i];

@@ -25,7 +25,7 @@ for resident in (True, False):
     for c in r.calls:
         t0 = time.perf_counter()
         if c[0] == "P":
-            r.la.pre_lookahead_batch_prepared(c[2], True)
+            r.la.pre_lookahead_batch_prepared(c[2], os.environ.get('PLANES_BACK', '1') == '1')
             k = "P"
         else:
             r.la.estimate_prepared(c[1], c[2])
