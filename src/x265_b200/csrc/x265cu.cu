@@ -537,6 +537,7 @@ static int frameInitEnqueue(x265cu_ctx* c, int slot, const void* luma, intptr_t 
         {
             KernelScope ks(c, X265CU_K_VAR);
             int blocks = (bxN * byN + 7) / 8;
+            if (blocks > 148 * 8) blocks = 148 * 8;      /* warps stride over the 16x16 blocks */
             if (c->pb == 1)
                 frame_var_kernel<uint8_t><<<blocks, 256, 0, c->stream>>>((const uint8_t*)src, pitch, u ? (const uint8_t*)dU : NULL, u ? (const uint8_t*)dV : NULL, cpitch, bxN, byN, dE, c->dSmall);
             else
@@ -1327,6 +1328,7 @@ int x265cu_frame_var(x265cu_ctx* c, const void* y, intptr_t yStride, const void*
     {
         KernelScope ks(c, X265CU_K_VAR);
         int blocks = (bxN * byN + 7) / 8;
+            if (blocks > 148 * 8) blocks = 148 * 8;      /* warps stride over the 16x16 blocks */
         if (c->pb == 1)
             frame_var_kernel<uint8_t><<<blocks, 256, 0, c->stream>>>((const uint8_t*)dY, ypitch, u ? (const uint8_t*)dU : NULL, u ? (const uint8_t*)dV : NULL, cpitch, bxN, byN, dE, c->dSmall);
         else

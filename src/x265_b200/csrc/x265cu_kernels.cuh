@@ -487,51 +487,67 @@ __global__ void __launch_bounds__(256) int_peak_kernel(int mode, int iters, unsi
 
 /* ===========================================================================================
  * frame_var: pixel_var<16> (luma) + pixel_var<8> (Cb, Cr) per 16x16 block, acEnergyCu
- * (slicetype.cpp:48-93).  One warp per 16x16 block.  sums6: wp_sum[0..2], wp_ssd[0..2].
+ * (slicetype.cpp:48-93).  One warp per 16x16 block, blocks strided over a grid sized to the GPU;
+ * the six frame sums (wp_sum[0..2], wp_ssd[0..2]) are kept per warp, reduced per CTA in shared
+ * memory and added to sums6 with six atomics per CTA.  8-bit rows that are 8-byte aligned are read
+ * as one 64-bit word per lane and summed with the packed-byte instructions.
  * =========================================================================================== */
 template <typename P>
 __global__ void __launch_bounds__(256) frame_var_kernel(const P* __restrict__ y, int64_t ys, const P* __restrict__ u, const P* __restrict__ v, int64_t cs,
                                                          int blocksX, int blocksY, unsigned int* __restrict__ energy, unsigned long long* __restrict__ sums6)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int blk = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (blk >= blocksX * blocksY) return;
-    const int bxi = blk % blocksX, byi = blk / blocksX;
-    /* luma: 256 samples, 8 per lane */
-    unsigned int sum = 0, sqr = 0;
+    __shared__ unsigned long long sAcc[6];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warpsPerCta = blockDim.x >> 5;
+    if (threadIdx.x < 6) sAcc[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned long long acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0, acc4 = 0, acc5 = 0;
+    const bool packed = sizeof(P) == 1 && (((uintptr_t)y | (uintptr_t)(ys * (int64_t)sizeof(P))) & 7) == 0;
+    for (int blk = blockIdx.x * warpsPerCta + warp; blk < blocksX * blocksY; blk += gridDim.x * warpsPerCta)
     {
-        const P* p = y + (int64_t)(16 * byi + (lane >> 1)) * ys + 16 * bxi + (lane & 1) * 8;
-#pragma unroll
-        for (int i = 0; i < 8; i++) { unsigned int t = p[i]; sum += t; sqr += t * t; }
-    }
-    sum = (unsigned int)warp_sum((int)sum); sqr = (unsigned int)warp_sum((int)sqr);
-    unsigned int var = sqr - (unsigned int)(((unsigned long long)sum * sum) >> 8);
-    unsigned int s1 = 0, q1 = 0, s2 = 0, q2 = 0;
-    if (u && v)
-    {
-        const int64_t co = (int64_t)(8 * byi + (lane >> 2)) * cs + 8 * bxi + (lane & 3) * 2;
-#pragma unroll
-        for (int i = 0; i < 2; i++)
+        const int bxi = blk % blocksX, byi = blk / blocksX;
+        /* luma: 256 samples, 8 per lane */
+        unsigned int sum = 0, sqr = 0;
         {
-            unsigned int a = u[co + i], b = v[co + i];
-            s1 += a; q1 += a * a; s2 += b; q2 += b * b;
+            const P* p = y + (int64_t)(16 * byi + (lane >> 1)) * ys + 16 * bxi + (lane & 1) * 8;
+            if (packed)
+            {
+                const uint2 w = __ldg((const uint2*)p);
+                sum = __vsadu4(w.x, 0) + __vsadu4(w.y, 0);
+                sqr = __dp4a(w.x, w.x, __dp4a(w.y, w.y, 0u));
+            }
+            else
+            {
+#pragma unroll
+                for (int i = 0; i < 8; i++) { unsigned int t = p[i]; sum += t; sqr += t * t; }
+            }
         }
-        s1 = (unsigned int)warp_sum((int)s1); q1 = (unsigned int)warp_sum((int)q1);
-        s2 = (unsigned int)warp_sum((int)s2); q2 = (unsigned int)warp_sum((int)q2);
-        var += q1 - (unsigned int)(((unsigned long long)s1 * s1) >> 6);
-        var += q2 - (unsigned int)(((unsigned long long)s2 * s2) >> 6);
+        sum = (unsigned int)warp_sum((int)sum); sqr = (unsigned int)warp_sum((int)sqr);
+        unsigned int var = sqr - (unsigned int)(((unsigned long long)sum * sum) >> 8);
+        unsigned int s1 = 0, q1 = 0, s2 = 0, q2 = 0;
+        if (u && v)
+        {
+            const int64_t co = (int64_t)(8 * byi + (lane >> 2)) * cs + 8 * bxi + (lane & 3) * 2;
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+            {
+                unsigned int a = u[co + i], b = v[co + i];
+                s1 += a; q1 += a * a; s2 += b; q2 += b * b;
+            }
+            s1 = (unsigned int)warp_sum((int)s1); q1 = (unsigned int)warp_sum((int)q1);
+            s2 = (unsigned int)warp_sum((int)s2); q2 = (unsigned int)warp_sum((int)q2);
+            var += q1 - (unsigned int)(((unsigned long long)s1 * s1) >> 6);
+            var += q2 - (unsigned int)(((unsigned long long)s2 * s2) >> 6);
+        }
+        if (lane == 0) energy[blk] = var;
+        acc0 += sum; acc3 += sqr; acc1 += s1; acc4 += q1; acc2 += s2; acc5 += q2;
     }
     if (lane == 0)
     {
-        energy[blk] = var;
-        atomicAdd(&sums6[0], (unsigned long long)sum);
-        atomicAdd(&sums6[3], (unsigned long long)sqr);
-        if (u && v)
-        {
-            atomicAdd(&sums6[1], (unsigned long long)s1); atomicAdd(&sums6[4], (unsigned long long)q1);
-            atomicAdd(&sums6[2], (unsigned long long)s2); atomicAdd(&sums6[5], (unsigned long long)q2);
-        }
+        atomicAdd(&sAcc[0], acc0); atomicAdd(&sAcc[3], acc3);
+        if (u && v) { atomicAdd(&sAcc[1], acc1); atomicAdd(&sAcc[4], acc4); atomicAdd(&sAcc[2], acc2); atomicAdd(&sAcc[5], acc5); }
     }
+    __syncthreads();
+    if (threadIdx.x < 6 && sAcc[threadIdx.x]) atomicAdd(&sums6[threadIdx.x], sAcc[threadIdx.x]);
 }
 
 #endif /* X265CU_KERNELS_CUH */

@@ -39,6 +39,31 @@ def test_replay_720p(mods, name):
     _replay(mods, name)
 
 
+@pytest.mark.parametrize("mode", ["0", "1"])
+@pytest.mark.parametrize("name", ["c0_720p", "c0_720p10", "odd8"])
+def test_replay_search_paths(mods, monkeypatch, name, mode):
+    """every search through ONE kernel path (the default picks per search): 0 = the plain wavefront kernel only,
+    1 = the speculative path only (refine iterations + memoised wide commit, in-batch seed waves)"""
+    monkeypatch.setenv("X265CU_SEARCH_MODE", mode)
+    _replay(mods, name)
+
+
+@pytest.mark.parametrize("rows", ["2", "8"])
+def test_replay_row_groups(mods, monkeypatch, rows):
+    """other row-group sizes of both search kernels (hand-off between CTAs through global memory at other rows)"""
+    monkeypatch.setenv("X265CU_PLAIN_ROWS", rows)
+    monkeypatch.setenv("X265CU_SEARCH_MODE", "2")
+    monkeypatch.setenv("X265CU_SPEC_MAX_PLANS", "64")
+    _replay(mods, "c0_720p")
+
+
+def test_replay_without_lookahead_cache(mods, monkeypatch):
+    """the host layer's look-ahead estimate cache off: every non-batch estimate computed on request"""
+    monkeypatch.setenv("X265CU_LOOKAHEAD_CACHE", "0")
+    _replay(mods, "c0_720p")
+    _replay(mods, "pool3_720p")
+
+
 def test_replay_config1_1080p(mods):
     """BASELINE.json configs[1]: 1080p, b-adapt 2, rc-lookahead 40, cuTree on (the bench workload)"""
     _replay(mods, "c1_1080p")
