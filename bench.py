@@ -411,10 +411,15 @@ def main():
     kms = {k: v / args.steps for k, v in st["ms"].items()}
     klaunch = {k: v / args.steps for k, v in st["launches"].items()}
     dom = max(("lowres", "intra", "search", "cost", "weight", "var"), key=lambda k: kms[k])
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/traffic.json holds
+    # dram__bytes_read.sum + dram__bytes_write.sum of the captured launch and how many units that launch processed);
+    # scaled to the units of an average launch here, like `achieved`
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
-    except (OSError, ValueError):
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        if tj and cfg["width"] == tj.get("width") and klaunch[dom] > 0:
+            traffic = tj["dram_bytes"] / tj["units"] * (units if dom == "search" else nframes) / klaunch[dom]
+    except (OSError, ValueError, KeyError):
         pass
     if dom in alg and kms[dom] > 0:
         per_launch_bytes = alg[dom] / max(klaunch[dom], 1)
@@ -422,9 +427,11 @@ def main():
         achieved = per_launch_bytes / (avg_ms * 1e-3) / 1e9
     else:
         achieved = 0.0
-    roofline = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+    kname = {"search": "plain_search_kernel (+ refine_kernel / search_kernel for small batches with a close hint)"}.get(dom, dom + "_kernel")
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "peak_source": peak_src,
-                "note": "the dominant kernel (wavefront motion search) is bound by dependent integer work, not HBM: see int_roofline"}
+                "note": "the dominant kernel family (wavefront motion search) is bound by the dependent chain of integer passes per CU, "
+                        "not by HBM: its DRAM traffic is below the algorithmic bytes (planes are shared through L2); see int_roofline"}
     # integer roofline of the search kernel: SAD/SATD pixel-ops actually performed per searched CU-list
     # (~20 SAD + ~9 SATD 8x8 per search -> (20*2 + 9*7) * 64 int ops before packing)
     ops_per_search_cu = (20 * 2 + 9 * 7) * 64
@@ -464,6 +471,8 @@ def main():
         "config": {"workload": DESCRIPTIONS.get(args.workload, args.workload), "trace": args.workload, "frames_per_step": nframes,
                    "estimates_per_step": njobs, "searches_per_step": units, "resolution": "%dx%d" % (cfg["width"], cfg["height"]),
                    "streams": world, "parallelism": "%d independent stream(s), one per GPU, no collective on the cost path" % world,
+                   "search_path": os.environ.get("X265CU_SEARCH_MODE", "2 (per search: plain wavefront kernel, or refine + commit for small batches with a close hint)"),
+                   "lookahead_cache": os.environ.get("X265CU_LOOKAHEAD_CACHE", "1 (non-batch estimates predicted from the request history ride in one launch)"),
                    "l2": "working set per step (%d frames x 4 padded planes + sources, > 300 MB) exceeds the 126 MB L2; no explicit flush" % nframes,
                    "parity": parity},
         "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,

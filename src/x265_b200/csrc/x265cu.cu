@@ -1070,7 +1070,14 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     }
     if (!items.empty())
     {
-        KernelScope ks(c, X265CU_K_SEARCH);
+        /* kernels this batch launches for its searches: the plain kernel, and per speculative wave its refine iterations + commit */
+        int nKernels = classItems[3] > classItems[2] ? 1 : 0;
+        for (int w = 0; w < 2; w++)
+        {
+            const size_t np = classPlans[w + 1] - classPlans[w];
+            if (np) nKernels += 1 + (np >= 32 ? (c->searchSpec < 1 ? c->searchSpec : 1) : c->searchSpec);
+        }
+        KernelScope ks(c, X265CU_K_SEARCH, nKernels);
         const JobDev* dJobs = (const JobDev*)(c->dArgs + offJobs);
         const SearchPlan* dPlans = (const SearchPlan*)(c->dArgs + offPlans);
         const SearchItem* dItems = (const SearchItem*)(c->dArgs + offItems);

@@ -125,7 +125,8 @@ __device__ __forceinline__ uint32_t warp_min_key(bool valid, int cost, int q)
     return __reduce_min_sync(FULL_MASK, key);
 }
 
-/* wait for a published hand-off word and return its MV */
+/* wait for a published hand-off word and return its MV (plain spinning: backing off with nanosleep was measured
+ * and changes nothing -- the schedulers already favour the warps that have work) */
 __device__ __forceinline__ int hand_wait(volatile const unsigned long long* e)
 {
     unsigned long long v;

@@ -17,9 +17,12 @@
 #define X265CU_SEARCH_PLAIN_CUH
 
 #define PLAIN_MAX_GROUP_ROWS 8
+#ifndef PLAIN_MIN_CTAS
+#define PLAIN_MIN_CTAS 3
+#endif
 
 template <typename P>
-__global__ void __launch_bounds__(PLAIN_MAX_GROUP_ROWS * 32, 3)
+__global__ void __launch_bounds__(PLAIN_MAX_GROUP_ROWS * 32, PLAIN_MIN_CTAS)
 plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restrict__ plans, const SearchItem* __restrict__ items, GeomDev g,
                     const uint16_t* __restrict__ lut, unsigned long long* gHand)
 {
