@@ -66,7 +66,7 @@ void Lookahead::mvcostTable(int bitDepth, uint16_t* out, int* lambdaInt)
     }
 }
 
-Lookahead::Lookahead() : m_ctx(NULL), m_mvcost(NULL), m_lambda(1), m_resident(false), m_lookAhead(true), m_versionCounter(0)
+Lookahead::Lookahead() : m_ctx(NULL), m_mvcost(NULL), m_lambda(1), m_resident(false), m_lookAhead(true), m_versionCounter(0), m_newestReady(0), m_episodeNewest(0)
 {
     m_error[0] = 0;
     memset(&m_param, 0, sizeof(m_param));
@@ -400,6 +400,7 @@ bool Lookahead::preLookahead(Lowres& l, const void* y, intptr_t yStride, const v
     if (!lowresIntraEstimate(l)) return false;
     l.ready = true;
     m_byPoc[poc] = &l;
+    m_newestReady++;
     return true;
 }
 
@@ -470,6 +471,7 @@ bool Lookahead::preLookaheadBatch(int n, Lowres** ls, const PictureIn* pics, boo
         l.costEstAq[0][0] = outs[i].sums[1];
         l.ready = true;
         m_byPoc[pics[i].poc] = &l;
+        m_newestReady++;
     }
     return true;
 }
@@ -486,29 +488,70 @@ void CostEstimateGroup::add(int p0, int p1, int b)
         finishBatch();
 }
 
+/* the still unknown estimates of ep[first..) shifted by `shift` frames, as look-ahead requests (non-batch estimates:
+ * cooperative slices).  valid = every frame they need exists and went through preLookahead(). */
+void CostEstimateGroup::predictFrom(const std::vector<Lookahead::Request>& ep, size_t first, int shift, Lowres* skipFenc, int skipD0, int skipD1,
+                                    const std::vector<EstReq>& already, std::vector<EstReq>& out, bool& valid)
+{
+    Lookahead& la = m_lookahead;
+    valid = true;
+    for (size_t i = first; i < ep.size(); i++)
+    {
+        const Lookahead::Request& q = ep[i];
+        std::map<int, Lowres*>::iterator ib = la.m_byPoc.find(q.b + shift), i0 = la.m_byPoc.find(q.p0 + shift), i1 = la.m_byPoc.find(q.p1 + shift);
+        if (ib == la.m_byPoc.end() || i0 == la.m_byPoc.end() || i1 == la.m_byPoc.end()) { valid = false; return; }
+        Lowres *qb = ib->second, *q0 = i0->second, *q1 = i1->second;
+        const int e0 = q.b - q.p0, e1 = q.p1 - q.b;
+        if (!qb->ready || !q0->ready || !q1->ready) { valid = false; return; }
+        if (e0 < 1 || e0 > la.m_param.bframes + 1 || e1 < 0 || e1 > la.m_param.bframes + 1) continue;
+        if (qb->costEst[e0][e1] >= 0 && qb->rowSatds[e0][e1][0] != -1) continue;      /* already known */
+        bool dup = qb == skipFenc && e0 == skipD0 && e1 == skipD1;
+        for (size_t c = 0; c < out.size(); c++)
+            dup = dup || (out[c].fenc == qb && out[c].d0 == e0 && out[c].d1 == e1);
+        for (size_t c = 0; c < already.size(); c++)
+            dup = dup || (already[c].fenc == qb && already[c].d0 == e0 && already[c].d1 == e1);
+        for (size_t c = 0; c < la.m_spec.size(); c++)      /* still pending from an earlier prediction */
+            dup = dup || (la.m_spec[c].fenc == qb && la.m_spec[c].d0 == e0 && la.m_spec[c].d1 == e1);
+        if (dup) continue;
+        EstReq r = { qb, q0, q1, e0, e1, true, true };
+        out.push_back(r);
+    }
+}
+
 bool CostEstimateGroup::finishBatch()
 {
+    Lookahead& la = m_lookahead;
     std::vector<EstReq> reqs((size_t)m_jobTotal);
     for (int i = 0; i < m_jobTotal; i++)
     {
         const Estimate& e = m_estimates[i];
-        EstReq r = { m_frames[e.b], m_frames[e.p0], m_frames[e.p1], e.b - e.p0, e.p1 - e.b, false };
+        EstReq r = { m_frames[e.b], m_frames[e.p0], m_frames[e.p1], e.b - e.p0, e.p1 - e.b, false, false };
         reqs[i] = r;
     }
-    bool ok = m_jobTotal ? runEstimates(&reqs[0], m_jobTotal, true) : true;
-    if (m_jobTotal)
+    if (m_jobTotal && !la.m_episode.empty())
     {
         /* a batch closes the run of one-by-one estimates: what was computed ahead and not asked for is dropped,
          * the run becomes the pattern the next one is predicted from */
-        Lookahead& la = m_lookahead;
         la.m_spec.clear();
-        if (!la.m_episode.empty())
+        la.m_history.push_back(la.m_episode);
+        la.m_historyNewest.push_back(la.m_episodeNewest);
+        if (la.m_history.size() > 3) { la.m_history.erase(la.m_history.begin()); la.m_historyNewest.erase(la.m_historyNewest.begin()); }
+        la.m_episode.clear();
+        /* ... and the next run is about to begin: it will most likely repeat the last one, shifted by as many frames
+         * as have arrived since that one began.  Its estimates ride along in this batch's launch. */
+        if (la.m_lookAhead)
         {
-            la.m_history.push_back(la.m_episode);
-            if (la.m_history.size() > 3) la.m_history.erase(la.m_history.begin());
-            la.m_episode.clear();
+            const int shift = la.m_newestReady - la.m_historyNewest.back();
+            std::vector<EstReq> ahead;
+            bool valid = false;
+            if (shift > 0) predictFrom(la.m_history.back(), 0, shift, NULL, 0, 0, reqs, ahead, valid);
+            if (valid) reqs.insert(reqs.end(), ahead.begin(), ahead.end());
+            if (getenv("X265CU_LOOKAHEAD_DEBUG"))
+                fprintf(stderr, "finishBatch: %d jobs, shift %d (newest %d, then %d), pattern of %d, valid %d, %d ahead\n", m_jobTotal, shift,
+                        la.m_newestReady, la.m_historyNewest.back(), (int)la.m_history.back().size(), (int)valid, (int)ahead.size());
         }
     }
+    bool ok = reqs.empty() ? true : runEstimates(&reqs[0], (int)reqs.size());
     m_jobTotal = 0;
     return ok;
 }
@@ -578,7 +621,7 @@ int64_t CostEstimateGroup::singleCost(int p0, int p1, int b, bool intraPenalty)
         if (!takeAhead(fenc, m_frames[p0], m_frames[p1], d0, d1))
         {
             std::vector<EstReq> reqs;
-            EstReq r0 = { fenc, m_frames[p0], m_frames[p1], d0, d1, false };
+            EstReq r0 = { fenc, m_frames[p0], m_frames[p1], d0, d1, false, true };
             reqs.push_back(r0);
             /* The request was not foreseen: look for the same kind of request (same distances) in the recent history,
              * shifted in time, and take the requests that followed it then as the ones about to be asked for now.
@@ -595,25 +638,7 @@ int64_t CostEstimateGroup::singleCost(int p0, int p1, int b, bool intraPenalty)
                         if (shift == 0 || ep[k].b - ep[k].p0 != d0 || ep[k].p1 - ep[k].b != d1) continue;
                         std::vector<EstReq> cand;
                         bool valid = true;
-                        for (size_t i = k + 1; i < ep.size() && valid; i++)
-                        {
-                            const Lookahead::Request& q = ep[i];
-                            std::map<int, Lowres*>::iterator ib = la.m_byPoc.find(q.b + shift), i0 = la.m_byPoc.find(q.p0 + shift), i1 = la.m_byPoc.find(q.p1 + shift);
-                            if (ib == la.m_byPoc.end() || i0 == la.m_byPoc.end() || i1 == la.m_byPoc.end()) { valid = false; break; }
-                            Lowres *qb = ib->second, *q0 = i0->second, *q1 = i1->second;
-                            const int e0 = q.b - q.p0, e1 = q.p1 - q.b;
-                            if (!qb->ready || !q0->ready || !q1->ready) { valid = false; break; }
-                            if (e0 < 1 || e0 > la.m_param.bframes + 1 || e1 < 0 || e1 > la.m_param.bframes + 1) continue;
-                            if (qb->costEst[e0][e1] >= 0 && qb->rowSatds[e0][e1][0] != -1) continue;      /* already known */
-                            bool dup = qb == fenc && e0 == d0 && e1 == d1;
-                            for (size_t c = 0; c < cand.size(); c++)
-                                dup = dup || (cand[c].fenc == qb && cand[c].d0 == e0 && cand[c].d1 == e1);
-                            for (size_t c = 0; c < la.m_spec.size(); c++)      /* still pending from an earlier prediction */
-                                dup = dup || (la.m_spec[c].fenc == qb && la.m_spec[c].d0 == e0 && la.m_spec[c].d1 == e1);
-                            if (dup) continue;
-                            EstReq r = { qb, q0, q1, e0, e1, true };
-                            cand.push_back(r);
-                        }
+                        predictFrom(ep, k + 1, shift, fenc, d0, d1, std::vector<EstReq>(), cand, valid);
                         if (valid && cand.size() > best.size()) best.swap(cand);
                     }
                 }
@@ -621,11 +646,12 @@ int64_t CostEstimateGroup::singleCost(int p0, int p1, int b, bool intraPenalty)
             }
             if (getenv("X265CU_LOOKAHEAD_DEBUG"))
                 fprintf(stderr, "singleCost (%d,%d,%d): on demand, %d ahead, episode %d prev %d\n", rq.p0, rq.b, rq.p1, (int)reqs.size() - 1, (int)la.m_episode.size(), (int)la.m_history.size());
-            if (!runEstimates(&reqs[0], (int)reqs.size(), false)) return -1;
+            if (!runEstimates(&reqs[0], (int)reqs.size())) return -1;
             la.m_specStats[2]++;
         }
         else if (getenv("X265CU_LOOKAHEAD_DEBUG"))
             fprintf(stderr, "singleCost (%d,%d,%d): handed out\n", rq.p0, rq.b, rq.p1);
+        if (la.m_episode.empty()) la.m_episodeNewest = la.m_newestReady;
         la.m_episode.push_back(rq);
         score = fenc->costEst[d0][d1];
     }
@@ -674,7 +700,7 @@ WeightGuess weightGuess(const Lowres& fenc, const Lowres& ref, int depth)
 /* est[0..n): estimates to compute in ONE x265cu_estimate_batch call.  Entries flagged `ahead` are computed into the
  * look-ahead cache instead of the frames' arrays; they may consume MV fields that an earlier entry of the same
  * call produces (the cost kernel of a batch runs after all of its searches). */
-bool CostEstimateGroup::runEstimates(const EstReq* est, int n, bool batchMode)
+bool CostEstimateGroup::runEstimates(const EstReq* est, int n)
 {
     Lookahead& la = m_lookahead;
     const Param& param = la.m_param;
@@ -706,7 +732,7 @@ bool CostEstimateGroup::runEstimates(const EstReq* est, int n, bool batchMode)
         j.d0 = d0; j.d1 = d1;
         j.doSearch[0] = fenc->lowresMvs[0][d0 - 1][0].x == 0x7FFF;
         j.doSearch[1] = d1 > 0 && fenc->lowresMvs[1][d1 - 1][0].x == 0x7FFF;
-        j.sliced = !batchMode;
+        j.sliced = est[i].sliced;
         uint64_t usedVersion[2] = { fenc->mvVersion[0][d0 - 1], d1 > 0 ? fenc->mvVersion[1][d1 - 1] : 0 };
         uint64_t newVersion[2] = { 0, 0 };
         bool usable = true;

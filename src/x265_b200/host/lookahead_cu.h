@@ -130,6 +130,8 @@ public:
     struct Request { int p0, b, p1; };         /* frameNums */
     std::vector<Request> m_episode;            /* non-batch estimates asked for since the last batch ... */
     std::vector<std::vector<Request> > m_history;   /* ... and the runs before it (most recent last) */
+    std::vector<int> m_historyNewest;          /* how many frames had gone through preLookahead() when each of those runs began */
+    int m_newestReady, m_episodeNewest;        /* ... now / when the current run began (a stream's frames arrive in order) */
     uint64_t m_versionCounter;
     int64_t m_specStats[4];                    /* launched ahead, handed out, requests computed alone, requests total */
 
@@ -178,8 +180,10 @@ public:
     int64_t singleCost(int p0, int p1, int b, bool intraPenalty = false);
 
 protected:
-    struct EstReq { Lowres *fenc, *ref0, *ref1; int d0, d1; bool ahead; };
-    bool runEstimates(const EstReq* e, int n, bool batchMode);
+    struct EstReq { Lowres *fenc, *ref0, *ref1; int d0, d1; bool ahead; bool sliced; };
+    bool runEstimates(const EstReq* e, int n);
+    void predictFrom(const std::vector<Lookahead::Request>& ep, size_t first, int shift, Lowres* skipFenc, int skipD0, int skipD1,
+                     const std::vector<EstReq>& already, std::vector<EstReq>& out, bool& valid);
     bool takeAhead(Lowres* fenc, Lowres* ref0, Lowres* ref1, int d0, int d1);
 };
 
