@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <chrono>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -1162,7 +1163,11 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     }
 #endif
 
-    /* scatter to the caller's Lowres arrays */
+    /* scatter to the caller's Lowres arrays; a big batch's few hundred MB are spread over several host threads
+     * (a single memcpy stream runs at a fraction of the PCIe rate the data arrived with) */
+    struct Copy { void* dst; const void* src; size_t bytes; };
+    std::vector<Copy> copies;
+    size_t copyBytes = 0;
     for (int i = 0; i < n; i++)
     {
         const x265cu_job& j = jobs[i];
@@ -1175,18 +1180,36 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
         res.reserved = 0;
         res.costEst = j.d1 > 0 ? res.costEstRaw * 100 / (130 + c->cfg.bFrameBias) : res.costEstRaw;   /* slicetype.cpp:2053-2057 */
         if (!wantArrays) continue;
-        if (j.rowSatds) memcpy(j.rowSatds, rec, hCU * 4);
+        if (j.rowSatds) { Copy cp = { j.rowSatds, rec, hCU * 4 }; copies.push_back(cp); copyBytes += cp.bytes; }
         rec += alignUp(hCU * 4, 16);
-        if (j.lowresCosts) memcpy(j.lowresCosts, rec, nCU * 2);
+        if (j.lowresCosts) { Copy cp = { j.lowresCosts, rec, nCU * 2 }; copies.push_back(cp); copyBytes += cp.bytes; }
         rec += alignUp(nCU * 2, 16);
         for (int l = 0; l < 2; l++)
             if (j.doSearch[l])
             {
-                if (j.mvs[l]) memcpy(j.mvs[l], rec, nCU * 4);
+                if (j.mvs[l]) { Copy cp = { j.mvs[l], rec, nCU * 4 }; copies.push_back(cp); copyBytes += cp.bytes; }
                 rec += alignUp(nCU * 4, 16);
-                if (j.mvCosts[l]) memcpy(j.mvCosts[l], rec, nCU * 4);
+                if (j.mvCosts[l]) { Copy cp = { j.mvCosts[l], rec, nCU * 4 }; copies.push_back(cp); copyBytes += cp.bytes; }
                 rec += alignUp(nCU * 4, 16);
             }
+    }
+    unsigned nThreads = 1;
+    if (copyBytes > ((size_t)8 << 20))
+    {
+        nThreads = std::thread::hardware_concurrency() / 2;
+        if (nThreads > 8) nThreads = 8;
+        if (nThreads < 1) nThreads = 1;
+    }
+    if (nThreads <= 1)
+        for (size_t k = 0; k < copies.size(); k++) memcpy(copies[k].dst, copies[k].src, copies[k].bytes);
+    else
+    {
+        const Copy* cp = &copies[0];
+        const size_t nc = copies.size();
+        std::vector<std::thread> workers;
+        for (unsigned t = 0; t < nThreads; t++)
+            workers.push_back(std::thread([cp, nc, t, nThreads]() { for (size_t k = t; k < nc; k += nThreads) memcpy(cp[k].dst, cp[k].src, cp[k].bytes); }));
+        for (size_t t = 0; t < workers.size(); t++) workers[t].join();
     }
     return X265CU_OK;
 }
