@@ -1,6 +1,7 @@
 /* lookahead_cu.cpp -- see lookahead_cu.h.  Host layer above the C ABI; float decisions only. */
 #include "lookahead_cu.h"
 #include <chrono>
+#include <thread>
 
 #include <math.h>
 #include <stdio.h>
@@ -436,8 +437,30 @@ bool Lookahead::preLookaheadBatch(int n, Lowres** ls, const PictureIn* pics, boo
     int r = x265cu_frame_init_var_batch(m_ctx, n, &items[0]);
     if (r) { snprintf(m_error, sizeof(m_error), "x265cu_frame_init_var_batch: %s", x265cu_last_error(m_ctx)); return false; }
     std::chrono::steady_clock::time_point t1 = std::chrono::steady_clock::now();
-    for (int i = 0; i < n; i++)
-        if (!calcAdaptiveQuantFrame(*ls[i], pics[i].y, pics[i].yStride, pics[i].u, pics[i].v, pics[i].cStride, items[i].energy, items[i].sums)) return false;
+    {
+        /* the float mapping of calcAdaptiveQuantFrame is per frame and independent: the reference runs the frames of the
+         * list on different workers, so do we (same code, same flags, same results) */
+        unsigned nThreads = std::thread::hardware_concurrency() / 2;
+        if (nThreads > 8) nThreads = 8;
+        if ((int)nThreads > n / 2) nThreads = (unsigned)(n / 2);
+        if (nThreads <= 1)
+        {
+            for (int i = 0; i < n; i++)
+                if (!calcAdaptiveQuantFrame(*ls[i], pics[i].y, pics[i].yStride, pics[i].u, pics[i].v, pics[i].cStride, items[i].energy, items[i].sums)) return false;
+        }
+        else
+        {
+            std::vector<std::thread> workers;
+            std::vector<char> okFlags((size_t)n, 1);
+            for (unsigned t = 0; t < nThreads; t++)
+                workers.push_back(std::thread([&, t]() {
+                    for (int i = (int)t; i < n; i += (int)nThreads)
+                        okFlags[i] = calcAdaptiveQuantFrame(*ls[i], pics[i].y, pics[i].yStride, pics[i].u, pics[i].v, pics[i].cStride, items[i].energy, items[i].sums) ? 1 : 0;
+                }));
+            for (size_t t = 0; t < workers.size(); t++) workers[t].join();
+            for (int i = 0; i < n; i++) if (!okFlags[i]) return false;
+        }
+    }
     std::chrono::steady_clock::time_point t2 = std::chrono::steady_clock::now();
 
     std::vector<x265cu_intra_out> outs((size_t)n);
