@@ -993,6 +993,22 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     }
     if (classPlans[1] == plans.size()) classItems[1] = items.size();
     if (classPlans[2] == plans.size()) classItems[2] = items.size();
+    /* Launch order of the plain kernel's CTAs.  A group becomes useful once the group below it is a few CUs ahead, so
+     * with the groups of one search in consecutive blocks a batch that does not fit the GPU fills its CTA slots with the
+     * upper groups of a few searches, most of them waiting for the wavefront to reach them.  Ordered by LEVEL (the
+     * bottom groups of every search and slice first, then the second groups, ...) the resident CTAs are the ones whose
+     * lower neighbour is running right now.  A group still only waits for a lower block index. */
+    if (items.size() - classItems[2] > 1)
+    {
+        std::vector<std::pair<int, SearchItem> > keyed;
+        for (size_t k = classItems[2]; k < items.size(); k++)
+        {
+            const SearchItem& it = items[k];
+            keyed.push_back(std::make_pair((it.sliceLastY - it.lastY) / c->plainWarps, it));
+        }
+        std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<int, SearchItem>& a, const std::pair<int, SearchItem>& b) { return a.first < b.first; });
+        for (size_t k = 0; k < keyed.size(); k++) items[classItems[2] + k] = keyed[k].second;
+    }
     if (classPlans[1] == classPlans[2] && classPlans[2] < plans.size()) classItems[1] = classItems[2];
     classItems[3] = items.size();
 
