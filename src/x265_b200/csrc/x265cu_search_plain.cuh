@@ -134,8 +134,13 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
         LaSearch s;
         la_search_begin(s, cuX, cuY, W, H, bidir, numc, nb0, nb1, nb2, nb3);
 
-        /* ---- CAND: SATD at each neighbour MV, no mvcost (quads >= numc re-measure candidate 0) ---- */
-        if (numc)
+        /* ---- CAND: SATD at each neighbour MV, no mvcost (quads >= numc re-measure candidate 0).  When every neighbour
+         * carries the same vector (3 of 4 CUs) the first candidate wins the strict-< chain whatever the costs, and its
+         * SATD is only consulted by the bidir skip rule for the zero vector (slicetype.cpp:2146-2149): nothing to measure. ---- */
+        const bool sameCand = numc > 0 && (numc < 2 || nb1 == nb0) && (numc < 3 || nb2 == nb0) && (numc < 4 || nb3 == nb0) && !(nb0 == 0 && bidir);
+        if (sameCand)
+            la_upd_cand(s, 0, 0, 0, 0);
+        else if (numc)
         {
             const int p = la_cand_mv(s, q < numc ? q : 0);
             typename Px<P>::Row4 r[4];
