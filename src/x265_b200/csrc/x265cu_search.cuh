@@ -176,8 +176,10 @@ __device__ __forceinline__ LaneGeom lane_geom(int lane, int stride)
  * row loads.  Origin (full-pel, relative to the CU): wx0 = ((pm.x >> 2) - 2) & ~3, wy0 = (pm.y >> 2) - 2.
  * Covers the hexagon (+-2) and the square (+-1) around round(pm) and every half-/quarter-pel point
  * within +-2 quarter samples of pm, i.e. all 26 positions of the no-move path. */
+#ifndef WIN_W
 #define WIN_W 16
 #define WIN_H 13
+#endif
 #define WIN_ROW_UNITS (WIN_W / 4)
 #define WIN_PLANE_UNITS (WIN_H * WIN_ROW_UNITS)
 #define WIN_UNITS (4 * WIN_PLANE_UNITS)

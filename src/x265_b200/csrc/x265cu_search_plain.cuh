@@ -17,20 +17,57 @@
 #define X265CU_SEARCH_PLAIN_CUH
 
 #define PLAIN_MAX_GROUP_ROWS 8
+#ifndef PWIN_MX
+#define PWIN_MX 2      /* window margin left of / above the first candidate's full-pel position */
+#define PWIN_MY 2
+#endif
 #ifndef PLAIN_MIN_CTAS
 #define PLAIN_MIN_CTAS 3
 #endif
 
-template <typename P>
+/* WIN variant (used when a launch fills the GPU): in that regime the kernel is bound by the L1 tag stage -- a warp-wide
+ * 4-byte load of 8 candidate blocks touches ~8-16 cache lines, ~900 such line look-ups per CU -- not by issue slots.
+ * So the 13 x 16 x 4-plane window around the first candidate vector is staged once per CU in shared memory with
+ * row-coalesced loads (56 line look-ups), and every pass whose 8 candidates lie inside it (warp-uniform test) reads
+ * shared memory; a pass that leaves the window reads global memory as before. */
+template <typename P, bool WIN>
+__device__ __forceinline__ void pfetch_qpel(const P* __restrict__ refLane, int planeSize, int stride, const typename Px<P>::Row4* win,
+                                            int lx, int ly, int qx, int qy, typename Px<P>::Row4 out[4])
+{
+    if (WIN)
+    {
+        const int qx2 = qx + (qx & 1), qy2 = qy + (qy & 1);
+        const int ax = lx + (qx >> 2), ay = ly + (qy >> 2), bx = lx + (qx2 >> 2), by = ly + (qy2 >> 2);
+        const bool ok = (unsigned)ax <= (unsigned)(WIN_W - 4) && (unsigned)bx <= (unsigned)(WIN_W - 4) &&
+                        (unsigned)ay <= (unsigned)(WIN_H - 4) && (unsigned)by <= (unsigned)(WIN_H - 4);
+        if (__all_sync(FULL_MASK, ok)) { win_qpel<P>(win, lx, ly, qx, qy, out); return; }
+    }
+    fetch_qpel<P>(refLane, planeSize, stride, qx, qy, out);
+}
+
+template <typename P, bool WIN>
+__device__ __forceinline__ void pfetch_fpel(const P* __restrict__ refLane, int stride, const typename Px<P>::Row4* win,
+                                            int lx, int ly, int fx, int fy, typename Px<P>::Row4 out[4])
+{
+    if (WIN)
+    {
+        const bool ok = (unsigned)(lx + fx) <= (unsigned)(WIN_W - 4) && (unsigned)(ly + fy) <= (unsigned)(WIN_H - 4);
+        if (__all_sync(FULL_MASK, ok)) { win_fpel<P>(win, lx, ly, fx, fy, out); return; }
+    }
+    fetch_off<P>(refLane, stride, fy * stride + fx, out);
+}
+
+template <typename P, bool WIN>
 __global__ void __launch_bounds__(PLAIN_MAX_GROUP_ROWS * 32, PLAIN_MIN_CTAS)
 plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restrict__ plans, const SearchItem* __restrict__ items, GeomDev g,
                     const uint16_t* __restrict__ lut, unsigned long long* gHand)
 {
-    extern __shared__ unsigned long long sHand[];  /* [rows of the group][W] hand-off words */
+    extern __shared__ unsigned long long sHand[];  /* [blockDim / 32][W] hand-off words (+ one window per warp, WIN) */
     const SearchItem it = items[blockIdx.x];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nRows = it.lastY - it.firstY + 1;
     const int W = g.wCU, H = g.hCU;
+    typename Px<P>::Row4* win = (typename Px<P>::Row4*)(sHand + (blockDim.x >> 5) * W) + warp * WIN_PITCH;
     for (int i = threadIdx.x; i < nRows * W; i += blockDim.x) sHand[i] = 0;
     const SearchPlan pl = plans[it.search];
     const JobDev* __restrict__ jp = jobs + pl.job;
@@ -80,13 +117,19 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
 
     /* per-lane candidate geometry of the fixed-shape passes (motion.cpp:64-66 tables) */
     const int hex6dx = la_hex2x((q + 1) & 7), hex6dy = la_hex2y((q + 1) & 7);
-    const int hex6off = hex6dy * stride + hex6dx;
     const int sq8dx = la_sq1x(q + 1), sq8dy = la_sq1y(q + 1);
-    const int sq8off = sq8dy * stride + sq8dx;
     const int hpdx = la_sq1x((q + 1) & 7) * 2, hpdy = la_sq1y((q + 1) & 7) * 2;   /* quarter-pel units */
     const int qpdx = la_sq1x(q), qpdy = la_sq1y(q);
 
     const int rowBase = (8 * cuY + by) * stride + bx;
+    /* WIN: source offset of each window unit this lane stages (unit i = lane + 32 k: plane, row, 4-sample column) */
+    int wOff[(WIN_UNITS + 31) / 32];
+#pragma unroll
+    for (int k = 0; k < (WIN_UNITS + 31) / 32; k++)
+    {
+        const int i = lane + 32 * k, plane = i / WIN_PLANE_UNITS, rem = i - plane * WIN_PLANE_UNITS;
+        wOff[k] = plane * planeSize + (rem / WIN_ROW_UNITS) * stride + (rem % WIN_ROW_UNITS) * 4;
+    }
     int prevMv = 0;                                /* MV of (cuX + 1, cuY): our own previous result */
     typename Px<P>::Row4 fe[4], feNext[4];
 #pragma unroll
@@ -131,6 +174,19 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
             if (cuX > 0) { if (numc == 1) nb1 = bl; else nb2 = bl; numc++; }
             if (cuX < W - 1) { if (numc == 2) nb2 = br; else nb3 = br; numc++; }
         }
+        int lx = 0, ly = 0;
+        if (WIN)
+        {
+            /* stage the window around the first candidate vector (the most likely MVP) */
+            const int wx0 = ((la_mv_x(nb0) >> 2) - PWIN_MX) & ~3, wy0 = (la_mv_y(nb0) >> 2) - PWIN_MY;
+            const P* __restrict__ wbase = refPlane + (8 * cuY + wy0) * stride + 8 * cuX + wx0;
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < (WIN_UNITS + 31) / 32; k++)
+                if (lane + 32 * k < WIN_UNITS) win[lane + 32 * k] = Px<P>::load_aligned(wbase + wOff[k]);
+            __syncwarp();
+            lx = bx - wx0; ly = by - wy0;
+        }
         LaSearch s;
         la_search_begin(s, cuX, cuY, W, H, bidir, numc, nb0, nb1, nb2, nb3);
 
@@ -144,7 +200,7 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
         {
             const int p = la_cand_mv(s, q < numc ? q : 0);
             typename Px<P>::Row4 r[4];
-            fetch_qpel<P>(refLane, planeSize, stride, la_mv_x(p), la_mv_y(p), r);
+            pfetch_qpel<P, WIN>(refLane, planeSize, stride, win, lx, ly, la_mv_x(p), la_mv_y(p), r);
             const int cost = quad_sum(satd4x4_abs<P>(fe, r)) >> 1;
             la_upd_cand(s, __shfl_sync(FULL_MASK, cost, 0), __shfl_sync(FULL_MASK, cost, 4),
                         __shfl_sync(FULL_MASK, cost, 8), __shfl_sync(FULL_MASK, cost, 12));
@@ -158,7 +214,7 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
             const int qx = q == 0 ? s.pmx : (q == 1 ? ((s.pmx + 2) >> 2) * 4 : 0);
             const int qy = q == 0 ? s.pmy : (q == 1 ? ((s.pmy + 2) >> 2) * 4 : 0);
             typename Px<P>::Row4 r[4];
-            fetch_qpel<P>(refLane, planeSize, stride, qx, qy, r);
+            pfetch_qpel<P, WIN>(refLane, planeSize, stride, win, lx, ly, qx, qy, r);
             const int mvc = q == 0 ? 0 : lutx[qx] + luty[qy];
             const int cost = quad_sum(sad4x4<P>(fe, r)) + mvc;
             la_upd_start(s, __shfl_sync(FULL_MASK, cost, 0), __shfl_sync(FULL_MASK, cost, 4), __shfl_sync(FULL_MASK, cost, 8));
@@ -168,7 +224,7 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
         {
             const int fx = s.bmx + hex6dx, fy = s.bmy + hex6dy;
             typename Px<P>::Row4 r[4];
-            fetch_off<P>(refLane, stride, s.bmy * stride + s.bmx + hex6off, r);
+            pfetch_fpel<P, WIN>(refLane, stride, win, lx, ly, fx, fy, r);
             const int cost = quad_sum(sad4x4<P>(fe, r)) + lutx[fx * 4] + luty[fy * 4];
             bool more = la_upd_hex6(s, warp_min_key(q < 6, cost, q));
             while (more)
@@ -176,7 +232,7 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
                 const int hdx = la_hex2x((s.dir + q) & 7), hdy = la_hex2y((s.dir + q) & 7);
                 const int hx = s.bmx + hdx, hy = s.bmy + hdy;
                 typename Px<P>::Row4 r3[4];
-                fetch_off<P>(refLane, stride, hy * stride + hx, r3);
+                pfetch_fpel<P, WIN>(refLane, stride, win, lx, ly, hx, hy, r3);
                 const int c3 = quad_sum(sad4x4<P>(fe, r3)) + lutx[hx * 4] + luty[hy * 4];
                 more = la_upd_hex3(s, warp_min_key(q < 3, c3, q));
             }
@@ -187,7 +243,7 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
         {
             const int fx = s.bmx + sq8dx, fy = s.bmy + sq8dy;
             typename Px<P>::Row4 r[4];
-            fetch_off<P>(refLane, stride, s.bmy * stride + s.bmx + sq8off, r);
+            pfetch_fpel<P, WIN>(refLane, stride, win, lx, ly, fx, fy, r);
             const int cost = quad_sum(sad4x4<P>(fe, r)) + lutx[fx * 4] + luty[fy * 4];
             subpel = la_upd_sq8(s, warp_min_key(true, cost, q), lut);
         }
@@ -198,7 +254,7 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
             {
                 const int qx = s.bmx + hpdx, qy = s.bmy + hpdy;
                 typename Px<P>::Row4 r[4];
-                fetch_qpel<P>(refLane, planeSize, stride, qx, qy, r);
+                pfetch_qpel<P, WIN>(refLane, planeSize, stride, win, lx, ly, qx, qy, r);
                 const int cost = quad_sum(sad4x4<P>(fe, r)) + lutx[qx] + luty[qy];
                 la_upd_hpel(s, warp_min_key(q < 4, cost, q));
             }
@@ -206,7 +262,7 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
             {
                 const int qx = s.bmx + qpdx, qy = s.bmy + qpdy;
                 typename Px<P>::Row4 r[4];
-                fetch_qpel<P>(refLane, planeSize, stride, qx, qy, r);
+                pfetch_qpel<P, WIN>(refLane, planeSize, stride, win, lx, ly, qx, qy, r);
                 const int cost = (quad_sum(satd4x4_abs<P>(fe, r)) >> 1) + lutx[qx] + luty[qy];
                 const int c0 = __shfl_sync(FULL_MASK, cost, 0);
                 la_upd_qpel(s, c0, warp_min_key(q >= 1 && q < 5, cost, q));
