@@ -195,7 +195,10 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
          * SATD is only consulted by the bidir skip rule for the zero vector (slicetype.cpp:2146-2149): nothing to measure. ---- */
         const bool sameCand = numc > 0 && (numc < 2 || nb1 == nb0) && (numc < 3 || nb2 == nb0) && (numc < 4 || nb3 == nb0) && !(nb0 == 0 && bidir);
         if (sameCand)
-            la_upd_cand(s, 0, 0, 0, 0);
+        {
+            /* la_upd_cand with equal candidates: the first one becomes the MVP, skipCost stays untouched */
+            s.mvpx = la_mv_x(nb0); s.mvpy = la_mv_y(nb0);
+        }
         else if (numc)
         {
             const int p = la_cand_mv(s, q < numc ? q : 0);
