@@ -95,7 +95,7 @@ struct x265cu_ctx
     int searchMode;        /* 0: plain kernel only, 1: speculative path only (with in-batch seed waves), 2: per search (default) */
     int specMaxDist, specMaxPlans;   /* speculative path: hint at most this many frames away, batch of at most this many searches */
     int plainWarps;        /* CU rows (= warps) per CTA of the plain kernel */
-    int plainWin;          /* plain kernel's shared-memory window variant: 1 always (default), 0 never, -1 only for launches that fill the GPU */
+    int plainWin;          /* plain kernel's shared-memory window variant: -2 for 8-bit samples (default; measured 5 % slower at 16 bit), 1 always, 0 never, -1 only for launches that fill the GPU */
     long long dbgPlans[4];
 };
 
@@ -277,7 +277,7 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     if (const char* e = getenv("X265CU_SEARCH_MODE")) c->searchMode = atoi(e);
     if (const char* e = getenv("X265CU_SPEC_MAX_DIST")) c->specMaxDist = atoi(e);
     if (const char* e = getenv("X265CU_SPEC_MAX_PLANS")) c->specMaxPlans = atoi(e);
-    c->plainWin = 1;
+    c->plainWin = -2;
     if (const char* e = getenv("X265CU_PLAIN_WIN")) c->plainWin = atoi(e);
     if (const char* e = getenv("X265CU_PLAIN_ROWS")) c->plainWarps = atoi(e);
     if (c->plainWarps < 1) c->plainWarps = 1;
@@ -1108,7 +1108,7 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
         {
             const unsigned ni = (unsigned)(classItems[3] - classItems[2]);
             /* a launch that fills the GPU is bound by L1 line look-ups: it stages each CU's window in shared memory */
-            const bool winVariant = c->plainWin == 1 || (c->plainWin < 0 && ni >= 1024);
+            const bool winVariant = c->plainWin == 1 || (c->plainWin == -1 && ni >= 1024) || (c->plainWin == -2 && c->pb == 1);
             const size_t pbRow4 = c->pb == 1 ? 4 : 8;
             const size_t smem = (size_t)maxPlainRows * g.wCU * sizeof(unsigned long long) + (winVariant ? (size_t)maxPlainRows * WIN_PITCH * pbRow4 : 0);
             if (c->pb == 1)
