@@ -101,6 +101,13 @@ struct x265cu_ctx
 
 namespace {
 
+/* host threads for the memcpy scatter of a big batch (X265CU_HOST_THREADS overrides; several ranks share the cores) */
+unsigned hostThreads()
+{
+    if (const char* e = getenv("X265CU_HOST_THREADS")) return (unsigned)atoi(e);
+    return std::thread::hardware_concurrency() / 4;
+}
+
 #define CU_TRY(ctx, call)                                                                           \
     do {                                                                                            \
         cudaError_t e_ = (call);                                                                    \
@@ -1224,7 +1231,7 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     unsigned nThreads = 1;
     if (copyBytes > ((size_t)8 << 20))
     {
-        nThreads = std::thread::hardware_concurrency() / 2;
+        nThreads = hostThreads();
         if (nThreads > 8) nThreads = 8;
         if (nThreads < 1) nThreads = 1;
     }

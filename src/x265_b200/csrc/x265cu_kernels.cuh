@@ -168,32 +168,35 @@ __global__ void __launch_bounds__(128) cost_kernel(const JobDev* __restrict__ jo
         RefPlanes<P> r1 = { (const P*)job.ref1, g.planeSize, g.stride };
         const int q = lane >> 2, sub = lane & 3, bx = (sub & 1) * 4, by = (sub >> 1) * 4;
         const int nWarps = blockDim.x >> 5;
-        for (int base = warp * 4; base < W; base += nWarps * 4)
+        /* a warp takes 8 adjacent CUs (one per quad) and measures both bidir candidates of each: the average of the two
+         * motion-compensated blocks, then the average of the two co-located blocks (aligned rows: one load per row) */
+        for (int base = warp * 8; base < W; base += nWarps * 8)
         {
-            const int cuX = base + (q >> 1);
-            const int cand = q & 1;
+            const int cuX = base + q;
             const int valid = cuX < W;
             const int cuXY = (valid ? cuX : 0) + cuY * W;
-            int part = 0;
-            int mv0 = 0, mv1 = 0;
+            int partMc = 0, partCo = 0;
             if (valid)
             {
-                mv0 = job.mvs[0][cuXY]; mv1 = job.mvs[1][cuXY];
+                const int mv0 = job.mvs[0][cuXY], mv1 = job.mvs[1][cuXY];
                 const int px = 8 * cuX + bx, py = 8 * cuY + by;
                 typename Px<P>::Row4 fe[4], a[4], b[4];
 #pragma unroll
                 for (int y = 0; y < 4; y++)
                     fe[y] = Px<P>::load_aligned(fencPlane + (int64_t)(py + y) * g.stride + px);
-                int m0 = cand == 0 ? mv0 : 0, m1 = cand == 0 ? mv1 : 0;
-                mc_fetch4x4<P>(r0, px, py, la_mv_x(m0), la_mv_y(m0), a);
-                mc_fetch4x4<P>(r1, px, py, la_mv_x(m1), la_mv_y(m1), b);
+                mc_fetch4x4<P>(r0, px, py, la_mv_x(mv0), la_mv_y(mv0), a);
+                mc_fetch4x4<P>(r1, px, py, la_mv_x(mv1), la_mv_y(mv1), b);
 #pragma unroll
                 for (int y = 0; y < 4; y++) a[y] = Px<P>::avg(a[y], b[y]);
-                part = satd4x4_abs<P>(fe, a);
+                partMc = satd4x4_abs<P>(fe, a);
+#pragma unroll
+                for (int y = 0; y < 4; y++)
+                    a[y] = Px<P>::avg(Px<P>::load_aligned(r0.p0 + (int64_t)(py + y) * g.stride + px),
+                                      Px<P>::load_aligned(r1.p0 + (int64_t)(py + y) * g.stride + px));
+                partCo = satd4x4_abs<P>(fe, a);
             }
-            int cost = quad_sum(part) >> 1;
-            int other = __shfl_down_sync(FULL_MASK, cost, 4);   /* co-located candidate of the same CU */
-            if (valid && cand == 0 && sub == 0)
+            const int cost = quad_sum(partMc) >> 1, other = quad_sum(partCo) >> 1;
+            if (valid && sub == 0)
             {
                 LaCuResult res = la_cu_finish(cuX, cuY, W, H, 1, job.mvCosts[0][cuXY], job.mvCosts[1][cuXY], cost, other,
                                               job.intraCost[cuXY], hasQ, hasQ ? job.invQ[cuXY] : 256);

@@ -10,6 +10,13 @@
 
 namespace x265cu {
 
+/* host threads for the per-frame float AQ mapping of a pre-lookahead list (X265CU_HOST_THREADS overrides) */
+static unsigned hostThreads()
+{
+    if (const char* e = getenv("X265CU_HOST_THREADS")) return (unsigned)atoi(e);
+    return std::thread::hardware_concurrency() / 4;
+}
+
 namespace {
 inline int imin(int a, int b) { return a < b ? a : b; }
 inline int imax(int a, int b) { return a > b ? a : b; }
@@ -440,7 +447,7 @@ bool Lookahead::preLookaheadBatch(int n, Lowres** ls, const PictureIn* pics, boo
     {
         /* the float mapping of calcAdaptiveQuantFrame is per frame and independent: the reference runs the frames of the
          * list on different workers, so do we (same code, same flags, same results) */
-        unsigned nThreads = std::thread::hardware_concurrency() / 2;
+        unsigned nThreads = hostThreads();
         if (nThreads > 8) nThreads = 8;
         if ((int)nThreads > n / 2) nThreads = (unsigned)(n / 2);
         if (nThreads <= 1)
