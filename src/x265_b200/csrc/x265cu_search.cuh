@@ -295,7 +295,9 @@ __device__ __forceinline__ void search_mv(const P* __restrict__ refCU, const P* 
         const uint32_t sqKey = __reduce_min_sync(FULL_MASK, q < 6 ? la_key(cost3, q + 2) : la_key(cost2, q - 6));
         const int qc0 = __shfl_sync(FULL_MASK, cost4, 0);
         centerSatd = __shfl_sync(FULL_MASK, raw4, 0);
-        if (!candOk)
+        /* (only for a vector that is a plausible neighbour MV, i.e. at most a CU + search slack beyond the clipped one:
+         * estimates are not trusted to point inside the padded planes) */
+        if (!candOk && abs(s.mvpx - s.pmx) <= 96 && abs(s.mvpy - s.pmy) <= 96)
         {
             /* the MVP was clipped (picture edge): the neighbour's own vector is measured where it points, unclipped
              * (slicetype.cpp:2138), straight from global memory */
