@@ -74,6 +74,7 @@ struct x265cu_ctx
     uint8_t* dArgs; size_t dArgsCap;       /* JobDev[], SearchItem[], int[] */
     uint8_t* hArgs; size_t hArgsCap;
     uint8_t* hPre; size_t hPreCap;         /* pinned landing zone of batched pre-lookahead results */
+    uint8_t* dPre; size_t dPreCap;         /* its device mirror */
     std::vector<void*> wPool;              /* weighted plane sets */
     uint8_t* dGeneric; size_t dGenericCap; /* pixelcmp / var scratch */
     uint8_t* dMemo; size_t dMemoCap;       /* search memo of a batch: [search][nCU][MEMO_N] int4 */
@@ -97,6 +98,8 @@ struct x265cu_ctx
     int plainWarps;        /* CU rows (= warps) per CTA of the plain kernel */
     int plainWin;          /* plain kernel's shared-memory window variant: -2 for 8-bit samples (default; measured 5 % slower at 16 bit), 1 always, 0 never, -1 only for launches that fill the GPU */
     long long dbgPlans[4];
+    double hostMs[4], planMs[4];      /* estimate_batch host time: planning, enqueue, wait, scatter (X265CU_HOST_PROFILE) */
+    long long hostCalls;
 };
 
 namespace {
@@ -216,7 +219,7 @@ void freeAll(x265cu_ctx* c)
 {
     cudaFree(c->dPlanes); cudaFree(c->dIntraCost); cudaFree(c->dIntraMode); cudaFree(c->dInvQ);
     cudaFree(c->dLowresCosts); cudaFree(c->dRowSatds); cudaFree(c->dMvs); cudaFree(c->dMvCosts);
-    cudaFree(c->dLut); cudaFree(c->dSrc); cudaFree(c->dSmall); cudaFree(c->dStage); cudaFree(c->dArgs); cudaFree(c->dGeneric); cudaFree(c->dMemo); cudaFree(c->dSrcLin); cudaFree(c->dUp);
+    cudaFree(c->dLut); cudaFree(c->dSrc); cudaFree(c->dSmall); cudaFree(c->dStage); cudaFree(c->dArgs); cudaFree(c->dGeneric); cudaFree(c->dMemo); cudaFree(c->dSrcLin); cudaFree(c->dUp); cudaFree(c->dPre);
     if (c->upStream) cudaStreamDestroy(c->upStream);
     for (size_t i = 0; i < c->upEvents.size(); i++) cudaEventDestroy(c->upEvents[i]);
     if (c->hStage) cudaFreeHost(c->hStage);
@@ -268,7 +271,7 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     c->err[0] = 0;
     c->dPlanes = NULL; c->dIntraCost = NULL; c->dIntraMode = NULL; c->dInvQ = NULL; c->dLowresCosts = NULL; c->dRowSatds = NULL;
     c->dMvs = NULL; c->dMvCosts = NULL; c->dLut = NULL; c->dSrc = NULL; c->dSmall = NULL;
-    c->dStage = NULL; c->dStageCap = 0; c->hStage = NULL; c->hStageCap = 0; c->dArgs = NULL; c->dArgsCap = 0; c->hArgs = NULL; c->hArgsCap = 0; c->hPre = NULL; c->hPreCap = 0; c->dSrcLin = NULL; c->dSrcLinCap = 0; c->dUp = NULL; c->dUpCap = 0; c->upStream = NULL;
+    c->dStage = NULL; c->dStageCap = 0; c->hStage = NULL; c->hStageCap = 0; c->dArgs = NULL; c->dArgsCap = 0; c->hArgs = NULL; c->hArgsCap = 0; c->hPre = NULL; c->hPreCap = 0; c->dPre = NULL; c->dPreCap = 0; c->dSrcLin = NULL; c->dSrcLinCap = 0; c->dUp = NULL; c->dUpCap = 0; c->upStream = NULL;
     c->dGeneric = NULL; c->dGenericCap = 0; c->dMemo = NULL; c->dMemoCap = 0;
     c->timing = false;
     memset(&c->stats, 0, sizeof(c->stats));
@@ -290,6 +293,7 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     if (c->plainWarps < 1) c->plainWarps = 1;
     if (c->plainWarps > PLAIN_MAX_GROUP_ROWS) c->plainWarps = PLAIN_MAX_GROUP_ROWS;
     memset(c->dbgPlans, 0, sizeof(c->dbgPlans));
+    memset(c->hostMs, 0, sizeof(c->hostMs)); memset(c->planMs, 0, sizeof(c->planMs)); c->hostCalls = 0;
     if (const char* e = getenv("X265CU_SEARCH_SPEC")) c->searchSpec = atoi(e);   /* tuning experiments only */
     if (search_smem_bytes<uint16_t>(c->searchWarps, (cfg->srcWidth / 2 + 7) / 8) > 48 * 1024)
     {
@@ -366,6 +370,9 @@ void x265cu_close(x265cu_ctx* c)
     cudaSetDevice(c->cfg.device);
     cudaStreamSynchronize(c->stream);
     if (c->copyStream) cudaStreamSynchronize(c->copyStream);
+    if (getenv("X265CU_HOST_PROFILE"))
+        fprintf(stderr, "x265cu_estimate_batch host time over %lld calls: planning %.2f ms (jobs %.2f, hints %.2f, items %.2f, args %.2f), enqueue %.2f ms, wait %.2f ms, scatter %.2f ms\n",
+                c->hostCalls, c->hostMs[0], c->planMs[0], c->planMs[1], c->planMs[2], c->planMs[3], c->hostMs[1], c->hostMs[2], c->hostMs[3]);
 #ifdef X265CU_SEARCH_STATS
     {
         unsigned long long h[32];
@@ -457,9 +464,12 @@ int x265cu_frame_init_var(x265cu_ctx* c, int slot, const void* y, intptr_t yStri
  * synchronisation: varEnergy / varSums (6 x u64) are filled once the stream has drained.  Caller holds the lock. */
 struct Uploaded { const uint8_t *y, *u, *v; };   /* picture already on the device with the host's pitches (batched uploads) */
 
+/* results of a batched list live in per-frame device buffers (zeroed / copied back once for the whole list) */
+struct BatchOut { unsigned int* dEnergy; unsigned long long* dSums; };
+
 static int frameInitEnqueue(x265cu_ctx* c, int slot, const void* luma, intptr_t srcStride, int lumaIsDevice, void* planesOut,
                             const void* u, const void* v, intptr_t cStride, uint32_t* varEnergy, unsigned long long* varSums,
-                            const Uploaded* up = NULL)
+                            const Uploaded* up = NULL, const BatchOut* bo = NULL)
 {
     if (!luma || badSlot(c, slot) || srcStride < 2 * c->g.width + 1) return fail(c, X265CU_EINVAL, "x265cu_frame_init: bad argument");
     const GeomDev& g = c->g;
@@ -544,19 +554,24 @@ static int frameInitEnqueue(x265cu_ctx* c, int slot, const void* luma, intptr_t 
             c->stats.h2dBytes += (int64_t)(2 * cLin);
         }
         else if (u) { dU = (uint8_t*)u; dV = (uint8_t*)v; cpitch = cStride; }
-        CU_TRY(c, cudaMemsetAsync(c->dSmall, 0, 6 * sizeof(unsigned long long), c->stream));
+        unsigned long long* dSums = c->dSmall;
+        if (bo) { dE = bo->dEnergy; dSums = bo->dSums; }
+        else CU_TRY(c, cudaMemsetAsync(c->dSmall, 0, 6 * sizeof(unsigned long long), c->stream));
         {
             KernelScope ks(c, X265CU_K_VAR);
             int blocks = (bxN * byN + 7) / 8;
             if (blocks > 148 * 8) blocks = 148 * 8;      /* warps stride over the 16x16 blocks */
             if (c->pb == 1)
-                frame_var_kernel<uint8_t><<<blocks, 256, 0, c->stream>>>((const uint8_t*)src, pitch, u ? (const uint8_t*)dU : NULL, u ? (const uint8_t*)dV : NULL, cpitch, bxN, byN, dE, c->dSmall);
+                frame_var_kernel<uint8_t><<<blocks, 256, 0, c->stream>>>((const uint8_t*)src, pitch, u ? (const uint8_t*)dU : NULL, u ? (const uint8_t*)dV : NULL, cpitch, bxN, byN, dE, dSums);
             else
-                frame_var_kernel<uint16_t><<<blocks, 256, 0, c->stream>>>((const uint16_t*)src, pitch, u ? (const uint16_t*)dU : NULL, u ? (const uint16_t*)dV : NULL, cpitch, bxN, byN, dE, c->dSmall);
+                frame_var_kernel<uint16_t><<<blocks, 256, 0, c->stream>>>((const uint16_t*)src, pitch, u ? (const uint16_t*)dU : NULL, u ? (const uint16_t*)dV : NULL, cpitch, bxN, byN, dE, dSums);
         }
         CU_TRY(c, cudaGetLastError());
-        CU_TRY(c, cudaMemcpyAsync(varEnergy, dE, (size_t)bxN * byN * 4, cudaMemcpyDeviceToHost, c->stream));
-        CU_TRY(c, cudaMemcpyAsync(varSums, c->dSmall, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        if (!bo)
+        {
+            CU_TRY(c, cudaMemcpyAsync(varEnergy, dE, (size_t)bxN * byN * 4, cudaMemcpyDeviceToHost, c->stream));
+            CU_TRY(c, cudaMemcpyAsync(varSums, c->dSmall, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        }
     }
     return X265CU_OK;
 }
@@ -587,6 +602,9 @@ int x265cu_frame_init_var_batch(x265cu_ctx* c, int n, const x265cu_frame_in* ite
     const int bxN = (c->cfg.srcWidth + 15) / 16, byN = (c->cfg.srcHeight + 15) / 16;
     const size_t eBytes = alignUp((size_t)bxN * byN * 4, 64), per = eBytes + 64;
     if (growHost(c, &c->hPre, &c->hPreCap, (size_t)n * per)) return X265CU_ECUDA;
+    /* device mirror of that landing zone: [frame][energy | 6 sums]; zeroed and copied back once for the whole list */
+    if (growDevice(c, &c->dPre, &c->dPreCap, (size_t)n * per)) return X265CU_ECUDA;
+    CU_TRY(c, cudaMemsetAsync(c->dPre, 0, (size_t)n * per, c->stream));
     const bool dbgPre = getenv("X265CU_PRE_DEBUG") != NULL;
     std::chrono::steady_clock::time_point tA = std::chrono::steady_clock::now(), tB = tA, tC = tA;
     /* host pictures: every frame gets its own staging area and its uploads run on the upload stream, so frame i + 1
@@ -639,11 +657,13 @@ int x265cu_frame_init_var_batch(x265cu_ctx* c, int n, const x265cu_frame_in* ite
             up.y = c->dUp + off[i]; up.u = up.y + alignUp(yLin, 256); up.v = up.u + alignUp(cLin, 256);
             CU_TRY(c, cudaStreamWaitEvent(c->stream, c->upEvents[i], 0));
         }
+        BatchOut bo = { (unsigned int*)(c->dPre + (size_t)i * per), (unsigned long long*)(c->dPre + (size_t)i * per + eBytes) };
         int r = frameInitEnqueue(c, f.slot, f.y, f.yStride, f.planesAreDevice, f.planesOut, f.u, f.v, f.cStride,
                                  (uint32_t*)(c->hPre + (size_t)i * per), (unsigned long long*)(c->hPre + (size_t)i * per + eBytes),
-                                 pipelined ? &up : NULL);
+                                 pipelined ? &up : NULL, &bo);
         if (r) { cudaStreamSynchronize(c->stream); if (c->upStream) cudaStreamSynchronize(c->upStream); return r; }
     }
+    CU_TRY(c, cudaMemcpyAsync(c->hPre, c->dPre, (size_t)n * per, cudaMemcpyDeviceToHost, c->stream));
     tC = std::chrono::steady_clock::now();
     int r = syncStream(c);
     if (r) return r;
@@ -676,7 +696,7 @@ int x265cu_frame_set_invqscale(x265cu_ctx* c, int slot, const int32_t* invQ)
 }
 
 /* enqueue lowresIntraEstimate of one frame; sums (2 x u64) land once the stream has drained.  Caller holds the lock. */
-static int intraEnqueue(x265cu_ctx* c, int slot, x265cu_intra_out* out, unsigned long long* sums)
+static int intraEnqueue(x265cu_ctx* c, int slot, x265cu_intra_out* out, unsigned long long* sums, unsigned long long* dBatchSums = NULL)
 {
     if (badSlot(c, slot)) return fail(c, X265CU_EINVAL, "x265cu_intra: bad slot");
     const GeomDev& g = c->g;
@@ -685,10 +705,10 @@ static int intraEnqueue(x265cu_ctx* c, int slot, x265cu_intra_out* out, unsigned
     o.intraMode = slotIntraMode(c, slot);
     o.lowresCosts = slotLowresCosts(c, slot, 0, 0);
     o.rowSatds = slotRowSatds(c, slot, 0, 0);
-    o.sums = c->dSmall;
+    o.sums = dBatchSums ? dBatchSums : c->dSmall;
     o.invQ = c->hasInvQ[slot] ? slotInvQ(c, slot) : NULL;
     CU_TRY(c, cudaMemsetAsync(o.rowSatds, 0, (size_t)g.hCU * sizeof(int), c->stream));
-    CU_TRY(c, cudaMemsetAsync(c->dSmall, 0, 2 * sizeof(unsigned long long), c->stream));
+    if (!dBatchSums) CU_TRY(c, cudaMemsetAsync(c->dSmall, 0, 2 * sizeof(unsigned long long), c->stream));
     {
         KernelScope ks(c, X265CU_K_INTRA);
         int blocks = (g.nCU + 7) / 8;
@@ -704,7 +724,7 @@ static int intraEnqueue(x265cu_ctx* c, int slot, x265cu_intra_out* out, unsigned
         if (out->intraMode) { CU_TRY(c, cudaMemcpyAsync(out->intraMode, o.intraMode, (size_t)g.nCU, cudaMemcpyDeviceToHost, c->stream)); c->stats.d2hBytes += g.nCU; }
         if (out->lowresCosts) { CU_TRY(c, cudaMemcpyAsync(out->lowresCosts, o.lowresCosts, (size_t)g.nCU * 2, cudaMemcpyDeviceToHost, c->stream)); c->stats.d2hBytes += g.nCU * 2; }
         if (out->rowSatds) { CU_TRY(c, cudaMemcpyAsync(out->rowSatds, o.rowSatds, (size_t)g.hCU * 4, cudaMemcpyDeviceToHost, c->stream)); c->stats.d2hBytes += g.hCU * 4; }
-        CU_TRY(c, cudaMemcpyAsync(sums, c->dSmall, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        if (!dBatchSums) CU_TRY(c, cudaMemcpyAsync(sums, c->dSmall, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     }
     return X265CU_OK;
 }
@@ -728,12 +748,14 @@ int x265cu_intra_batch(x265cu_ctx* c, int n, const int* slots, x265cu_intra_out*
     if (!n) return X265CU_OK;
     std::lock_guard<std::mutex> lk(c->mtx);
     CU_TRY(c, cudaSetDevice(c->cfg.device));
-    if (growHost(c, &c->hPre, &c->hPreCap, (size_t)n * 16)) return X265CU_ECUDA;
+    if (growHost(c, &c->hPre, &c->hPreCap, (size_t)n * 16) || growDevice(c, &c->dPre, &c->dPreCap, (size_t)n * 16)) return X265CU_ECUDA;
+    CU_TRY(c, cudaMemsetAsync(c->dPre, 0, (size_t)n * 16, c->stream));
     for (int i = 0; i < n; i++)
     {
-        int r = intraEnqueue(c, slots[i], &outs[i], (unsigned long long*)(c->hPre + (size_t)i * 16));
+        int r = intraEnqueue(c, slots[i], &outs[i], (unsigned long long*)(c->hPre + (size_t)i * 16), (unsigned long long*)(c->dPre + (size_t)i * 16));
         if (r) { cudaStreamSynchronize(c->stream); return r; }
     }
+    CU_TRY(c, cudaMemcpyAsync(c->hPre, c->dPre, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
     int r = syncStream(c);
     if (r) return r;
     for (int i = 0; i < n; i++)
@@ -805,6 +827,7 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     CU_TRY(c, cudaSetDevice(c->cfg.device));
     const GeomDev& g = c->g;
     const size_t nCU = (size_t)g.nCU, hCU = (size_t)g.hCU;
+    const std::chrono::steady_clock::time_point tH0 = std::chrono::steady_clock::now();
 
     /* ---- plan: per-job packed record + one SearchPlan per (job, list) searched ---- */
     std::vector<size_t> recOff(n);
@@ -853,6 +876,7 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
         c->wPool.push_back(p);
     }
 
+    const std::chrono::steady_clock::time_point tP1 = std::chrono::steady_clock::now();
     /* ---- hints for the speculation kernel (speed only, never a result): a finished MV field of the
      * temporally nearest frame for the same list and distance.  Searches of a batch that have no such
      * field yet are run in two WAVES: one seed per (list, distance) first, the others after it with the
@@ -960,6 +984,7 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     const size_t memoPerSearch = nCU * MEMO_N * sizeof(int4) + 3 * alignUp(nCU * sizeof(int), 256);   /* memo + the three estimate fields */
     if (classPlans[2] && growDevice(c, &c->dMemo, &c->dMemoCap, classPlans[2] * memoPerSearch)) return X265CU_ECUDA;
 
+    const std::chrono::steady_clock::time_point tP2 = std::chrono::steady_clock::now();
     /* ---- commit work items: one per row group of every (search, cooperative slice) ---- */
     int maxItemRows = 1, maxPlainRows = 1;
     int handRows = 0;            /* global hand-off rows (one per row group that has a group above it) */
@@ -1022,6 +1047,7 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     if (classPlans[1] == classPlans[2] && classPlans[2] < plans.size()) classItems[1] = classItems[2];
     classItems[3] = items.size();
 
+    const std::chrono::steady_clock::time_point tP3 = std::chrono::steady_clock::now();
     size_t offJobs = 0;
     size_t offItems = alignUp(offJobs + (size_t)n * sizeof(JobDev), 256);
     size_t offPlans = alignUp(offItems + items.size() * sizeof(SearchItem), 256);
@@ -1079,6 +1105,7 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
         hw[k].scale = j.wScale;
         weightArgs(c, j.wScale, j.wDenom, j.wOffset, &hw[k].round, &hw[k].shift, &hw[k].offset);
     }
+    const std::chrono::steady_clock::time_point tH1 = std::chrono::steady_clock::now();
     CU_TRY(c, cudaMemcpyAsync(c->dArgs, c->hArgs, offProg, cudaMemcpyHostToDevice, c->stream));
     c->stats.h2dBytes += (int64_t)offProg;
     CU_TRY(c, cudaMemsetAsync(c->dStage, 0, sumsBytes, c->stream));
@@ -1167,8 +1194,10 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     const size_t back = wantArrays ? total : (size_t)n * 32;
     CU_TRY(c, cudaMemcpyAsync(c->hStage, c->dStage, back, cudaMemcpyDeviceToHost, c->stream));
     c->stats.d2hBytes += (int64_t)back;
+    const std::chrono::steady_clock::time_point tH2 = std::chrono::steady_clock::now();
     int r = syncStream(c);
     if (r) return r;
+    const std::chrono::steady_clock::time_point tH3 = std::chrono::steady_clock::now();
 #ifdef X265CU_SEARCH_STATS
     if (!plans.empty() && getenv("X265CU_TRACE_BATCH"))
     {
@@ -1246,6 +1275,15 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
             workers.push_back(std::thread([cp, nc, t, nThreads]() { for (size_t k = t; k < nc; k += nThreads) memcpy(cp[k].dst, cp[k].src, cp[k].bytes); }));
         for (size_t t = 0; t < workers.size(); t++) workers[t].join();
     }
+    c->planMs[0] += std::chrono::duration<double, std::milli>(tP1 - tH0).count();
+    c->planMs[1] += std::chrono::duration<double, std::milli>(tP2 - tP1).count();
+    c->planMs[2] += std::chrono::duration<double, std::milli>(tP3 - tP2).count();
+    c->planMs[3] += std::chrono::duration<double, std::milli>(tH1 - tP3).count();
+    c->hostMs[0] += std::chrono::duration<double, std::milli>(tH1 - tH0).count();
+    c->hostMs[1] += std::chrono::duration<double, std::milli>(tH2 - tH1).count();
+    c->hostMs[2] += std::chrono::duration<double, std::milli>(tH3 - tH2).count();
+    c->hostMs[3] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tH3).count();
+    c->hostCalls++;
     return X265CU_OK;
 }
 

@@ -39,4 +39,6 @@ for resident in (True, False):
     total = time.perf_counter() - t_all
     print("resident" if resident else "host-buffers", "total %.1f ms:" % (total * 1e3),
           ", ".join("%s %.1f ms / %d calls" % (k, v[0] * 1e3, v[1]) for k, v in acc.items()))
+    for _ in range(int(os.environ.get('EXTRA_STEPS', '0'))):
+        r.step()
     r.close()
