@@ -57,6 +57,15 @@ def test_replay_row_groups(mods, monkeypatch, rows):
     _replay(mods, "c0_720p")
 
 
+@pytest.mark.parametrize("name,win", [("c0_720p", "0"), ("c0_720p10", "1"), ("odd8", "1")])
+def test_replay_plain_window_variants(mods, monkeypatch, name, win):
+    """the plain kernel's shared-memory window variant is on for 8-bit and off for 16-bit samples by default:
+    cover the other setting of each (and odd picture sizes through the window)"""
+    monkeypatch.setenv("X265CU_PLAIN_WIN", win)
+    monkeypatch.setenv("X265CU_SEARCH_MODE", "0")
+    _replay(mods, name)
+
+
 def test_replay_without_lookahead_cache(mods, monkeypatch):
     """the host layer's look-ahead estimate cache off: every non-batch estimate computed on request"""
     monkeypatch.setenv("X265CU_LOOKAHEAD_CACHE", "0")
