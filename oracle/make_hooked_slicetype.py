@@ -15,6 +15,8 @@ Hook sites (reference file:line in x265_1.9/source/encoder/slicetype.cpp):
   :1919 CostEstimateGroup::finishBatch() entry, :1925 before its job counters are reset
   :2053 in estimateFrameCost(), after a non-cached estimate has been computed, before the
         B-frame scaling of the score
+  :1668-1701 after each memset of a frame's propagateCost in Lookahead::cuTree
+  :1839 end of Lookahead::estimateCUPropagate (before its optional cuTreeFinish), :1862 end of cuTreeFinish
 """
 import re
 import sys
@@ -60,6 +62,20 @@ def main():
     j = find(r'^\s*if \(b != p1\)\s*$', i)
     inserts.append((j, '        x265ref_hook_job(m_frames, p0, p1, b, bDoSearch[0], bDoSearch[1], m_batchMode, '
                        '(!m_batchMode && m_lookahead.m_numCoopSlices > 1 && ((p1 > b) || bDoSearch[0] || bDoSearch[1])));'))
+
+    # cuTree: every memset of a propagateCost array, the end of each propagate step, the end of cuTreeFinish
+    i = find(r'^void Lookahead::cuTree\(Lowres \*\*frames, int numframes, bool bIntra\)')
+    j = find(r'^void Lookahead::estimateCUPropagate\(', i)
+    rx = re.compile(r'^(\s*)memset\((frames\[\w+\])->propagateCost, 0, m_cuCount \* sizeof\(uint16_t\)\);')
+    for k in range(i, j):
+        m = rx.match(lines[k])
+        if m:
+            inserts.append((k + 1, '%sx265ref_hook_ctzero(%s);' % (m.group(1), m.group(2))))
+    k = find(r'^\s*if \(m_param->rc\.vbvBufferSize && m_param->lookaheadDepth && referenced\)', j)
+    inserts.append((k, '    x265ref_hook_propagate(frames, averageDuration, p0, p1, b, referenced);'))
+    i = find(r'^void Lookahead::cuTreeFinish\(')
+    k = find(r'^\}', i)
+    inserts.append((k, '    x265ref_hook_ctfinish(frame, averageDuration, ref0Distance);'))
 
     for idx, text in sorted(inserts, key=lambda t: -t[0]):
         lines.insert(idx, text)

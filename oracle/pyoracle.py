@@ -41,7 +41,8 @@ class Frame(C.Structure):
                 ("costEstAq", (C.c_int64 * (BFMAX + 2)) * (BFMAX + 2)),
                 ("intraMbs", C.c_int * (BFMAX + 2)),
                 ("wp_ssd", C.c_uint64 * 3), ("wp_sum", C.c_uint64 * 3), ("frameVariance", C.c_uint64),
-                ("weightedCostDelta", C.c_double * (BFMAX + 2))]
+                ("weightedCostDelta", C.c_double * (BFMAX + 2)),
+                ("propagateCost", C.c_void_p)]
 
 
 def build_oracle():
@@ -80,6 +81,10 @@ def oracle(depth=8, emul=False):
     L.ola_estimate.restype = C.c_int64
     L.ola_estimate.argtypes = [C.c_void_p, C.POINTER(Frame), C.POINTER(Frame), C.POINTER(Frame)] + [C.c_int] * 6 + \
                               [C.POINTER(Weight), C.POINTER(Weight)]
+    L.ola_propagate_cost.argtypes = [C.c_void_p] * 5 + [C.POINTER(C.c_double), C.c_int]
+    L.ola_cutree_zero.argtypes = [C.POINTER(Frame)]
+    L.ola_estimate_cu_propagate.argtypes = [C.POINTER(Frame)] * 3 + [C.c_int] * 3 + [C.c_double, C.c_int, C.c_int, C.c_int]
+    L.ola_cutree_finish.argtypes = [C.POINTER(Frame), C.c_double, C.c_int, C.c_int, C.c_int, C.c_double]
     L.ola_weights_analyse.argtypes = [C.c_void_p, C.POINTER(Frame), C.POINTER(Frame), C.POINTER(Weight)]
     L.ola_weight_cost_luma.restype = C.c_uint32
     L.ola_weight_cost_luma.argtypes = [C.c_void_p, C.POINTER(Frame), C.POINTER(Frame), C.POINTER(Weight)]
@@ -133,6 +138,7 @@ def ref(depth=8):
     L.x265ref_var8.restype = C.c_uint64
     L.x265ref_var8.argtypes = [C.c_void_p, C.c_ssize_t]
     L.x265ref_exp2fix8.argtypes = [C.c_double]
+    L.x265ref_propagate_cost.argtypes = [C.c_void_p] * 5 + [C.POINTER(C.c_double), C.c_int]
     L.x265ref_mvcost_table.argtypes = [C.c_void_p]
     L.x265ref_run_lookahead.restype = C.c_double
     L.x265ref_run_lookahead.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
@@ -153,8 +159,8 @@ def ref_run_lookahead(depth, width, height, nframes, seed, opts, pool_threads, t
                                    trace.encode() if trace else None, dump.encode() if dump else None, st, stats)
     if secs < 0:
         raise RuntimeError("x265ref_run_lookahead failed: %r" % secs)
-    keys = ("pre", "jobs", "searchL0", "searchL1", "batches", "decided")
-    return secs, list(st), dict(zip(keys, list(stats)[:6]))
+    keys = ("pre", "jobs", "searchL0", "searchL1", "batches", "decided", "propagates")
+    return secs, list(st), dict(zip(keys, list(stats)[:7]))
 
 
 # ------------------------------------------------------------------------------------------
@@ -210,6 +216,12 @@ class OFrame:
     def mv_costs(self, lst, d):
         return _view(self.c.mvCosts[lst][d - 1], np.int32, self.g.nCU)
 
+    def propagate_cost(self):
+        return _view(self.c.propagateCost, np.uint16, self.g.nCU)
+
+    def qp_cutree_offset(self):
+        return _view(self.c.qpCuTreeOffset, np.float64, self.g.nCU)
+
 
 def crc(a):
     return zlib.crc32(np.ascontiguousarray(a).tobytes()) & 0xFFFFFFFF
@@ -257,7 +269,8 @@ def pad_picture(p, extra, chroma_of=None):
 # ------------------------------------------------------------------------------------------
 class Trace:
     def __init__(self, path):
-        self.events = []   # ("P", dict) | ("B", [jobs]) | ("J", dict) | ("D", poc, type)
+        # ("P", dict) | ("B", [jobs]) | ("J", dict) | ("D", poc, type) | cuTree: ("M", poc) | ("X", dict) | ("F", dict)
+        self.events = []
         self.cfg = {}
         batch = None
         with open(path) as f:
@@ -277,6 +290,17 @@ class Trace:
                 elif k == "L":
                     self.cfg["lutCrc"] = int(t[1], 16)
                     self.cfg["lambda"] = int(t[2])
+                elif k == "T":
+                    self.cfg.update(fpsNum=int(t[1]), fpsDenom=int(t[2]), qCompress=float(t[3]), weightedBiPred=int(t[4]),
+                                    vbvBufferSize=int(t[5]))
+                elif k == "M":
+                    self.events.append(("M", int(t[1])))
+                elif k == "X":
+                    self.events.append(("X", dict(p0=int(t[1]), b=int(t[2]), p1=int(t[3]), referenced=int(t[4]),
+                                                   avgDuration=float(t[5]), ref0=int(t[6], 16), ref1=int(t[7], 16), own=int(t[8], 16))))
+                elif k == "F":
+                    self.events.append(("F", dict(poc=int(t[1]), ref0Distance=int(t[2]), avgDuration=float(t[3]),
+                                                   qpCuTreeOffset=int(t[4], 16), propagateCost=int(t[5], 16))))
                 elif k == "P":
                     self.events.append(("P", dict(poc=int(t[1]), planes=int(t[2], 16), intraCost=int(t[3], 16),
                                                    intraMode=int(t[4], 16), lowresCosts=int(t[5], 16), rowSatds=int(t[6], 16),
@@ -343,6 +367,7 @@ class OracleReplay:
         self.keep = keep if keep is not None else cfg["lookahead"] + cfg["bframes"] + 8
         self.mismatches = []
         self.njobs = 0
+        self.npropagate = 0
 
     def close(self):
         for f in self.frames.values():
@@ -409,11 +434,42 @@ class OracleReplay:
         self._check(tag + "rowSatds", crc(fenc.row_satds(d0, d1)), j["rowSatds"])
         self.njobs += 1
 
+    # ---- cuTree
+    def ct_zero(self, poc):
+        self.lib.ola_cutree_zero(self.frames[poc].p)
+
+    def ct_propagate(self, x):
+        cfg = self.t.cfg
+        fenc, r0, r1 = self.frames[x["b"]], self.frames[x["p0"]], self.frames[x["p1"]]
+        d0, d1 = x["b"] - x["p0"], x["p1"] - x["b"]
+        self.lib.ola_estimate_cu_propagate(fenc.p, r0.p, r1.p, d0, d1, x["referenced"], x["avgDuration"], cfg["fpsNum"], cfg["fpsDenom"],
+                                           cfg["weightedBiPred"])
+        tag = "X%d/%d/%d." % (x["p0"], x["b"], x["p1"])
+        self._check(tag + "ref0", crc(r0.propagate_cost()), x["ref0"])
+        if d1 > 0:
+            self._check(tag + "ref1", crc(r1.propagate_cost()), x["ref1"])
+        own = fenc.propagate_cost()
+        self._check(tag + "own", crc(own if x["referenced"] else own[:fenc.g.wCU]), x["own"])
+        self.npropagate += 1
+
+    def ct_finish(self, e):
+        cfg = self.t.cfg
+        f = self.frames[e["poc"]]
+        self.lib.ola_cutree_finish(f.p, e["avgDuration"], cfg["fpsNum"], cfg["fpsDenom"], e["ref0Distance"], 5.0 * (1.0 - cfg["qCompress"]))
+        self._check("F%d.propagateCost" % e["poc"], crc(f.propagate_cost()), e["propagateCost"])
+        self._check("F%d.qpCuTreeOffset" % e["poc"], crc(f.qp_cutree_offset()), e["qpCuTreeOffset"])
+
     def run(self, max_events=None):
         n = 0
         for e in self.t.events:
             if e[0] == "P":
                 self.pre(e[1])
+            elif e[0] == "M":
+                self.ct_zero(e[1])
+            elif e[0] == "X":
+                self.ct_propagate(e[1])
+            elif e[0] == "F":
+                self.ct_finish(e[1])
             elif e[0] == "J":
                 self.job(e[1])
             elif e[0] == "B":

@@ -19,6 +19,12 @@ void x265ref_hook_batch(int begin, int njobs);
 void x265ref_hook_job(X265_NS::Lowres** frames, int p0, int p1, int b, int search0, int search1, int batchMode, int sliced);
 /* slicetype.cpp:486 -- weightsAnalyse accepted a weight for (fenc, ref) */
 void x265ref_hook_weight(int fencPoc, int refPoc, int scale, int denom, int offset);
+/* slicetype.cpp:1668-1701 -- Lookahead::cuTree zeroed a frame's propagateCost */
+void x265ref_hook_ctzero(X265_NS::Lowres* frame);
+/* slicetype.cpp:1839 -- Lookahead::estimateCUPropagate finished its scatter loop */
+void x265ref_hook_propagate(X265_NS::Lowres** frames, double averageDuration, int p0, int p1, int b, int referenced);
+/* slicetype.cpp:1862 -- Lookahead::cuTreeFinish wrote qpCuTreeOffset */
+void x265ref_hook_ctfinish(X265_NS::Lowres* frame, double averageDuration, int ref0Distance);
 }
 
 #endif

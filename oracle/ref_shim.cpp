@@ -65,7 +65,7 @@ struct TraceState
     FILE* dump;
     pthread_mutex_t lock;
     int wCU, hCU, nCU, bframes;
-    long nPre, nJob, nSearch[2], nBatch;
+    long nPre, nJob, nSearch[2], nBatch, nPropagate;
 } g_ts;
 std::map<std::pair<int, int>, std::vector<int> > g_weights; /* (fencPoc, refPoc) -> scale, denom, offset */
 
@@ -195,6 +195,48 @@ extern "C" void x265ref_hook_job(Lowres** frames, int p0, int p1, int b, int sea
     pthread_mutex_unlock(&g_ts.lock);
 }
 
+/* ---- cuTree: which arrays Lookahead::cuTree zeroed, every propagate step with the state of the
+ * reference frames' propagateCost after it, every cuTreeFinish with the qpCuTreeOffset it wrote */
+extern "C" void x265ref_hook_ctzero(Lowres* frame)
+{
+    pthread_mutex_lock(&g_ts.lock);
+    if (g_ts.trace) fprintf(g_ts.trace, "M %d\n", frame->frameNum);
+    pthread_mutex_unlock(&g_ts.lock);
+}
+
+extern "C" void x265ref_hook_propagate(Lowres** frames, double averageDuration, int p0, int p1, int b, int referenced)
+{
+    pthread_mutex_lock(&g_ts.lock);
+    if (g_ts.trace)
+    {
+        int n = g_ts.nCU;
+        uint32_t c0 = crc32(frames[p0]->propagateCost, n * sizeof(uint16_t));
+        uint32_t c1 = p1 != b ? crc32(frames[p1]->propagateCost, n * sizeof(uint16_t)) : 0;
+        /* a non-referenced frame only has its first row defined (zeroed by the step itself) */
+        uint32_t cb = referenced ? crc32(frames[b]->propagateCost, n * sizeof(uint16_t)) : crc32(frames[b]->propagateCost, g_ts.wCU * sizeof(uint16_t));
+        fprintf(g_ts.trace, "X %d %d %d %d %.17g %08x %08x %08x\n", frames[p0]->frameNum, frames[b]->frameNum, frames[p1]->frameNum, referenced,
+                averageDuration, c0, c1, cb);
+        dumpArray("PRP0", frames[p0]->frameNum, frames[b]->frameNum, frames[p1]->frameNum, referenced, frames[p0]->propagateCost, n * sizeof(uint16_t));
+        if (p1 != b)
+            dumpArray("PRP1", frames[p0]->frameNum, frames[b]->frameNum, frames[p1]->frameNum, referenced, frames[p1]->propagateCost, n * sizeof(uint16_t));
+    }
+    g_ts.nPropagate++;
+    pthread_mutex_unlock(&g_ts.lock);
+}
+
+extern "C" void x265ref_hook_ctfinish(Lowres* frame, double averageDuration, int ref0Distance)
+{
+    pthread_mutex_lock(&g_ts.lock);
+    if (g_ts.trace)
+    {
+        int n = g_ts.nCU;
+        fprintf(g_ts.trace, "F %d %d %.17g %08x %08x\n", frame->frameNum, ref0Distance, averageDuration,
+                crc32(frame->qpCuTreeOffset, n * sizeof(double)), crc32(frame->propagateCost, n * sizeof(uint16_t)));
+        dumpArray("QPCT", frame->frameNum, ref0Distance, 0, 0, frame->qpCuTreeOffset, n * sizeof(double));
+    }
+    pthread_mutex_unlock(&g_ts.lock);
+}
+
 /* ================================================================ (1) primitives */
 extern "C" {
 
@@ -258,7 +300,7 @@ uint32_t x265ref_crc32(const void* p, size_t n) { crcInit(); return crc32(p, n);
  * opts: name/value pairs for x265_param_parse (value may be NULL); "preset"/"tune" are consumed
  * first.  poolThreads: size of the single worker pool (results depend on it).
  * sliceTypesOut[nframes]: decided X265_TYPE_* per POC.  statsOut[8]: nPre, nJobs, nSearchL0,
- * nSearchL1, nBatches, 0, 0, 0.  Returns wall seconds of the lookahead (input generation
+ * nSearchL1, nBatches, decided, nPropagate, 0.  Returns wall seconds of the lookahead (input generation
  * excluded: all frames are generated and copied into PicYuv before the clock starts), < 0 on error. */
 double x265ref_run_lookahead(int width, int height, int nframes, uint32_t seed,
                              const char** optNames, const char** optValues, int nopts, int poolThreads,
@@ -329,6 +371,8 @@ double x265ref_run_lookahead(int width, int height, int nframes, uint32_t seed,
             x265ref_mvcost_table(&lut[0]);
             fprintf(g_ts.trace, "L %08x %d\n", crc32(&lut[0], lut.size() * sizeof(uint16_t)), x265ref_lambda_int());
         }
+        /* what cuTree reads beyond the above: frame rate, cuTree strength (5 * (1 - qcomp)), weighted bipred, VBV */
+        fprintf(g_ts.trace, "T %u %u %.17g %d %d\n", p->fpsNum, p->fpsDenom, p->rc.qCompress, p->bEnableWeightedBiPred, p->rc.vbvBufferSize);
     }
 
     /* generate all input frames up front */
@@ -383,7 +427,7 @@ double x265ref_run_lookahead(int width, int height, int nframes, uint32_t seed,
     if (statsOut)
     {
         statsOut[0] = g_ts.nPre; statsOut[1] = g_ts.nJob; statsOut[2] = g_ts.nSearch[0]; statsOut[3] = g_ts.nSearch[1];
-        statsOut[4] = g_ts.nBatch; statsOut[5] = decided; statsOut[6] = statsOut[7] = 0;
+        statsOut[4] = g_ts.nBatch; statsOut[5] = decided; statsOut[6] = g_ts.nPropagate; statsOut[7] = 0;
     }
     if (g_ts.trace) { fprintf(g_ts.trace, "Z %d\n", decided); fclose(g_ts.trace); g_ts.trace = NULL; }
     if (g_ts.dump) { fclose(g_ts.dump); g_ts.dump = NULL; }

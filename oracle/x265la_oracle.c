@@ -120,6 +120,7 @@ ola_frame* ola_frame_create(int srcW, int srcH, int marginX, int marginY, int bf
     }
     f->intraCost = (int32_t*)calloc(n, sizeof(int32_t));
     f->intraMode = (uint8_t*)calloc(n, 1);
+    f->propagateCost = (uint16_t*)calloc(n, sizeof(uint16_t));
     if (aq)
     {
         f->invQscale = (int32_t*)calloc(n, sizeof(int32_t));
@@ -145,7 +146,7 @@ ola_frame* ola_frame_create(int srcW, int srcH, int marginX, int marginY, int bf
 void ola_frame_destroy(ola_frame* f)
 {
     if (!f) return;
-    free(f->buffer[0]); free(f->intraCost); free(f->intraMode);
+    free(f->buffer[0]); free(f->intraCost); free(f->intraMode); free(f->propagateCost);
     free(f->invQscale); free(f->qpAqOffset); free(f->qpCuTreeOffset); free(f->blockVariance);
     for (int i = 0; i < f->bframes + 2; i++)
         for (int j = 0; j < f->bframes + 2; j++) { free(f->rowSatds[i][j]); free(f->lowresCosts[i][j]); }
@@ -1173,4 +1174,127 @@ int64_t ola_estimate(ola_ctx* c, ola_frame* fenc, ola_frame* ref0, ola_frame* re
         score = score * 100 / (130 + c->bFrameBias);
     fenc->costEst[d0][d1] = score;
     return score;
+}
+
+
+/* ================================================================================================
+ * cuTree propagation
+ * ============================================================================================== */
+
+/* estimateCUPropagateCost, common/pixel.cpp:848-874 (the #else branch, the one compiled).  The order of the
+ * double operations is the one the reference's object code performs (checked against its disassembly: the
+ * int32 product intraCost*invQscale wraps, then ((double)product * (fpsFactor/256) + propagateIn) *
+ * (intra - min(intra, inter)) / intra + 0.5, truncated; every step is an IEEE-754 round-to-nearest operation,
+ * no contraction), so plain C without -ffast-math reproduces it. */
+void ola_propagate_cost(int* dst, const uint16_t* propagateIn, const int32_t* intraCosts, const uint16_t* interCosts,
+                        const int32_t* invQscales, const double* fpsFactor, int len)
+{
+    volatile double fps = *fpsFactor * (1.0 / 256);
+    for (int i = 0; i < len; i++)
+    {
+        int intra = intraCosts[i];
+        int inter = interCosts[i] & 0x3FFF;                       /* LOWRES_COST_MASK, slicetype.h:41 */
+        if (inter > intra) inter = intra;
+        int32_t prod = (int32_t)((uint32_t)intra * (uint32_t)invQscales[i]);
+        volatile double amount = (double)prod * fps;
+        amount = amount + (double)propagateIn[i];
+        volatile double r = amount * (double)(intra - inter);
+        r = r / (double)intra;
+        r = r + 0.5;
+        /* cvttsd2si: out-of-range and NaN give INT_MIN */
+        dst[i] = (r >= -2147483648.0 && r < 2147483648.0) ? (int)r : (int)0x80000000;
+    }
+}
+
+/* memset(frames[x]->propagateCost, 0, ...) in Lookahead::cuTree, slicetype.cpp:1668-1701 */
+void ola_cutree_zero(ola_frame* f)
+{
+    memset(f->propagateCost, 0, (size_t)f->g.nCU * sizeof(uint16_t));
+}
+
+static double ola_clip_duration(double f)     /* CLIP_DURATION, slicetype.cpp:44 */
+{
+    return f < 0.01 ? 0.01 : (f > 1.00 ? 1.00 : f);
+}
+
+#define OLA_CLIP_ADD(s, x) (s) = (uint16_t)((int)(s) + (x) < 65535 ? (int)(s) + (x) : 65535)
+
+/* Lookahead::estimateCUPropagate, slicetype.cpp:1741-1839 (without the VBV-only cuTreeFinish at its end, which
+ * the caller issues).  fenc = frames[b], ref0 = frames[p0], ref1 = frames[p1]. */
+void ola_estimate_cu_propagate(ola_frame* fenc, ola_frame* ref0, ola_frame* ref1, int d0, int d1, int referenced,
+                               double averageDuration, int fpsNum, int fpsDenom, int weightedBiPred)
+{
+    const int wCU = fenc->g.wCU, hCU = fenc->g.hCU;
+    uint16_t* refCosts[2] = { ref0->propagateCost, ref1->propagateCost };
+    int32_t distScaleFactor = ((d0 << 8) + ((d0 + d1) >> 1)) / (d0 + d1);
+    int32_t bipredWeight = weightedBiPred ? 64 - (distScaleFactor >> 2) : 32;
+    int32_t bipredWeights[2] = { bipredWeight, 64 - bipredWeight };
+    int listDist[2] = { d0 - 1, d1 - 1 };
+    int* scratch = (int*)calloc((size_t)wCU, sizeof(int));
+    uint16_t* propagateCost = fenc->propagateCost;
+    double fpsFactor = ola_clip_duration((double)fpsDenom / fpsNum) / ola_clip_duration(averageDuration);
+    const uint16_t* lowresCosts = fenc->lowresCosts[d0][d1];
+
+    if (!referenced)
+        memset(fenc->propagateCost, 0, (size_t)wCU * sizeof(uint16_t));
+
+    for (int blocky = 0; blocky < hCU; blocky++)
+    {
+        int cuIndex = blocky * wCU;
+        ola_propagate_cost(scratch, propagateCost, fenc->intraCost + cuIndex, lowresCosts + cuIndex,
+                           fenc->invQscale + cuIndex, &fpsFactor, wCU);
+        if (referenced)
+            propagateCost += wCU;
+        for (int blockx = 0; blockx < wCU; blockx++, cuIndex++)
+        {
+            int32_t amount = scratch[blockx];
+            if (amount <= 0) continue;                             /* intra block */
+            int32_t listsUsed = lowresCosts[cuIndex] >> 14;
+            for (int list = 0; list < 2; list++)
+            {
+                if (!((listsUsed >> list) & 1)) continue;
+                int32_t listamount = amount;
+                if (listsUsed == 3)
+                    listamount = (listamount * bipredWeights[list] + 32) >> 6;
+                const ola_mv* mvs = fenc->mvs[list][listDist[list]];
+                if (!mvs[cuIndex].x && !mvs[cuIndex].y)
+                {
+                    OLA_CLIP_ADD(refCosts[list][cuIndex], listamount);
+                    continue;
+                }
+                int32_t x = mvs[cuIndex].x, y = mvs[cuIndex].y;
+                int32_t cux = (x >> 5) + blockx, cuy = (y >> 5) + blocky;
+                int32_t idx0 = cux + cuy * wCU;
+                x &= 31; y &= 31;
+                int32_t wgt[4] = { (32 - y) * (32 - x), (32 - y) * x, y * (32 - x), y * x };
+                for (int k = 0; k < 4; k++)
+                {
+                    int tx = cux + (k & 1), ty = cuy + (k >> 1);
+                    /* both the all-inside branch and the per-corner branch reduce to: the corner is a CU of the frame */
+                    if (tx >= 0 && tx < wCU && ty >= 0 && ty < hCU)
+                        OLA_CLIP_ADD(refCosts[list][idx0 + (k & 1) + (k >> 1) * wCU], (listamount * wgt[k] + 512) >> 10);
+                }
+            }
+        }
+    }
+    free(scratch);
+}
+
+/* Lookahead::cuTreeFinish, slicetype.cpp:1844-1862.  cuTreeStrength = 5.0 * (1.0 - qCompress) (slicetype.cpp:514). */
+void ola_cutree_finish(ola_frame* f, double averageDuration, int fpsNum, int fpsDenom, int ref0Distance, double cuTreeStrength)
+{
+    int fpsFactor = (int)(ola_clip_duration(averageDuration) / ola_clip_duration((double)fpsDenom / fpsNum) * 256);
+    double weightdelta = 0.0;
+    if (ref0Distance && f->weightedCostDelta[ref0Distance - 1] > 0)
+        weightdelta = 1.0 - f->weightedCostDelta[ref0Distance - 1];
+    for (int i = 0; i < f->g.nCU; i++)
+    {
+        int intracost = (f->intraCost[i] * f->invQscale[i] + 128) >> 8;
+        if (intracost)
+        {
+            int propagateCost = (f->propagateCost[i] * fpsFactor + 128) >> 8;
+            double log2_ratio = log2((double)(intracost + propagateCost)) - log2((double)intracost) + weightdelta;
+            f->qpCuTreeOffset[i] = f->qpAqOffset[i] - cuTreeStrength * log2_ratio;
+        }
+    }
 }

@@ -75,6 +75,7 @@ typedef struct ola_frame
     uint64_t wp_ssd[3], wp_sum[3];
     uint64_t frameVariance;
     double weightedCostDelta[OLA_BFRAME_MAX + 2];
+    uint16_t* propagateCost;    /* Lowres::propagateCost (cuTree) */
 } ola_frame;
 
 typedef struct ola_weight
@@ -138,6 +139,14 @@ void ola_apply_weight(ola_ctx* c, ola_frame* ref, const ola_weight* w);
  * run ola_weights_analyse when weightp && search0, else use *weight as given. */
 int64_t ola_estimate(ola_ctx* c, ola_frame* fenc, ola_frame* ref0, ola_frame* ref1, int d0, int d1,
                      int search0, int search1, int sliced, int weightp, const ola_weight* weight, ola_weight* usedWeight);
+
+/* cuTree propagation */
+void ola_propagate_cost(int* dst, const uint16_t* propagateIn, const int32_t* intraCosts, const uint16_t* interCosts,
+                        const int32_t* invQscales, const double* fpsFactor, int len);
+void ola_cutree_zero(ola_frame* f);
+void ola_estimate_cu_propagate(ola_frame* fenc, ola_frame* ref0, ola_frame* ref1, int d0, int d1, int referenced,
+                               double averageDuration, int fpsNum, int fpsDenom, int weightedBiPred);
+void ola_cutree_finish(ola_frame* f, double averageDuration, int fpsNum, int fpsDenom, int ref0Distance, double cuTreeStrength);
 
 /* helpers for tests */
 void ola_lowres_mc(pixel* const planes[4], intptr_t stride, intptr_t blockOffset, int qx, int qy, pixel* blk);

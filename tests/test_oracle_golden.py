@@ -18,6 +18,10 @@ def run(name, **kw):
     try:
         mm = r.run()
         assert r.njobs == sum(1 for _ in t.jobs())
+        # cuTree: every propagate step (ref/own propagateCost CRCs) and every cuTreeFinish (qpCuTreeOffset CRC)
+        assert r.npropagate == sum(1 for e in t.events if e[0] == "X")
+        if t.cfg["cutree"]:
+            assert r.npropagate > 0 and any(e[0] == "F" for e in t.events)
         assert not mm, "%s: %d mismatches, first %r" % (name, len(mm), mm[:5])
     finally:
         r.close()
@@ -72,6 +76,8 @@ def test_dump_arrays(name, depth):
                 assert r.frames[a].intra_mode().tobytes() == data
             elif tag == "INVQ":
                 assert r.frames[a].inv_qscale().tobytes() == data
+            elif tag == "QPCT" and (a, b) == max((k[1], k[2]) for k in dump if k[0] == "QPCT" and k[1] == a):
+                pass    # qpCuTreeOffset is overwritten by later cuTree runs; the CRC of each run is checked in the replay
             else:
                 continue
             checked += 1

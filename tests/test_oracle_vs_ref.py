@@ -149,3 +149,26 @@ def test_mvcost_table_and_exp2fix8(depth):
     assert O.ola_lambda_int() == R.x265ref_lambda_int()
     for x in np.linspace(-60, 60, 4001):
         assert O.ola_exp2fix8(float(x)) == R.x265ref_exp2fix8(float(x))
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_propagate_cost(depth):
+    """estimateCUPropagateCost (pixel.cpp:848-874; harness recipe pixelharness.cpp check_propagateCost-like: random
+    uint16 propagate-in / inter costs, int32 intra costs and inverse qscales, a double fps factor), all lengths incl.
+    the vector loop's tail, extremes included"""
+    O, R = po.oracle(depth), po.ref(depth)
+    rng = np.random.default_rng(5)
+    for it in range(60):
+        n = int(rng.integers(1, 300))
+        pin = rng.integers(0, 65536, n).astype(np.uint16)
+        intra = rng.integers(1, 1 << (14 + 2 * (depth > 8)), n).astype(np.int32)
+        inter = rng.integers(0, 65536, n).astype(np.uint16)
+        invq = rng.integers(1, 4096, n).astype(np.int32)
+        if it % 5 == 0:
+            intra[: n // 2] = 1
+            invq[n // 2:] = 1 << 20     # the int32 product wraps
+        fps = C.c_double(float(rng.uniform(0.01, 100.0)) if it % 3 else 1.0)
+        a, b = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        O.ola_propagate_cost(a.ctypes.data, pin.ctypes.data, intra.ctypes.data, inter.ctypes.data, invq.ctypes.data, C.byref(fps), n)
+        R.x265ref_propagate_cost(b.ctypes.data, pin.ctypes.data, intra.ctypes.data, inter.ctypes.data, invq.ctypes.data, C.byref(fps), n)
+        assert np.array_equal(a, b), (it, n)
