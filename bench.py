@@ -142,7 +142,8 @@ class Runner:
         for s in ([slices] + list(range(2, 17)) if slices else [0]):
             la = abi.Lookahead(cfg["width"], cfg["height"], cfg["depth"], cfg["bframes"], cfg["lookahead"], s, cfg["pool"], cfg["weightp"],
                                cfg["aqmode"], cfg["aqStrength"], cfg["bFrameBias"], device, n + 2, stream=stream,
-                               search_warps=env_int("X265CU_SEARCH_ROWS", 0))
+                               search_warps=env_int("X265CU_SEARCH_ROWS", 0), fps_num=cfg.get("fpsNum", 30), fps_denom=cfg.get("fpsDenom", 1),
+                               qcompress=cfg.get("qCompress", 0.6), weighted_bipred=cfg.get("weightedBiPred", 0))
             if not slices or (la.numCoopSlices, la.numRowsPerSlice) == (cfg["numCoopSlices"], cfg["numRowsPerSlice"]):
                 break
             la.close()
@@ -174,6 +175,9 @@ class Runner:
                 self.keepalive += [y, u, v]
                 self.inputs[t] = (y.ctypes.data, y.strides[0] // y.itemsize, u.ctypes.data, v.ctypes.data, u.strides[0] // u.itemsize)
         # pre-marshal the call sequence
+        import ctypes as C
+        cutree = env_int("X265CU_BENCH_CUTREE", 1) != 0
+        self.npropagate = 0
         self.calls = []
         for e in trace.events:
             if e[0] == "P":
@@ -192,6 +196,16 @@ class Runner:
                 fr = [self.frames.get(p) for p in range(lo, hi + 1)]
                 tr = [(j["p0"] - lo, j["p1"] - lo, j["b"] - lo) for j in jobs]
                 self.calls.append(("E", la.prepare_estimate(fr, tr), e[0] == "B"))
+            elif e[0] == "M" and cutree:
+                # cuTree: the memsets, propagate steps and cuTreeFinish calls of Lookahead::cuTree, in place
+                self.calls.append(("M", self.frames[e[1]]))
+            elif e[0] == "X" and cutree:
+                x = e[1]
+                fr = [self.frames.get(p) for p in range(x["p0"], x["p1"] + 1)]
+                self.calls.append(("X", (C.c_void_p * len(fr))(*fr), len(fr), x["p1"] - x["p0"], x["b"] - x["p0"], x["referenced"], x["avgDuration"]))
+                self.npropagate += 1
+            elif e[0] == "F" and cutree:
+                self.calls.append(("F", self.frames[e[1]["poc"]], e[1]["avgDuration"], e[1]["ref0Distance"]))
         self.calls = [("P", c[1], la.prepare_pre_lookahead_batch([(self.frames[t],) + tuple(self.inputs[t]) + (t,) for t in c[1]])) if c[0] == "P" else c
                       for c in self.calls]
         self.units = sum(j["s0"] + j["s1"] for j in trace.jobs())
@@ -199,11 +213,19 @@ class Runner:
 
     def step(self):
         la = self.la
+        L, h = la.L, la.h
         for c in self.calls:
             if c[0] == "P":
                 la.pre_lookahead_batch_prepared(c[2], True)
-            else:
+            elif c[0] == "E":
                 la.estimate_prepared(c[1], c[2])
+            elif c[0] == "X":
+                if L.x265cuh_cutree_propagate(h, c[1], c[2], 0, c[3], c[4], c[5], c[6]):
+                    raise RuntimeError("estimateCUPropagate failed: " + la.error())
+            elif c[0] == "M":
+                L.x265cuh_cutree_zero(h, c[1])
+            else:
+                la.cutree_finish(c[1], c[2], c[3])
         la.sync()          # every output, including the asynchronous plane copy-backs, is on the host
 
     def close(self):
@@ -333,11 +355,11 @@ def main():
     if not args.no_parity and not args.profile_mode:
         r = replay.CuReplay(trace, device=local, check=True, clip=clip)
         mm = r.run()
-        nchk = r.njobs
+        nchk, nprop = r.njobs, r.npropagate
         r.close()
         if mm:
             raise SystemExit("bench.py: parity FAILED on %s: %d mismatches, first %r" % (args.workload, len(mm), mm[0]))
-        parity = "bit-exact vs x265 1.9 reference trace: %d frames, %d estimates, every output array CRC" % (nframes, nchk)
+        parity = "bit-exact vs x265 1.9 reference trace: %d frames, %d estimates, %d cuTree propagate steps, every output array CRC" % (nframes, nchk, nprop)
 
     stream = torch.cuda.current_stream().cuda_stream
     sampler = ClockSampler(local)
@@ -378,6 +400,8 @@ def main():
         satd = {"gpix_per_s": pix / (best * 1e-3) / 1e9, "pairs": len(a), "ms": best}
     except Exception as ex:  # pragma: no cover - reported, not fatal
         satd = {"error": str(ex)}
+    ct_value = res.la.cutree_stats()
+    npropagate = res.npropagate
     res.close()
 
     # ---- e2e: host buffers in, all arrays back ----
@@ -388,6 +412,7 @@ def main():
     ms_e2e = timed(torch, dist, world, e2e.step, args.steps)
     st_e2e = e2e.la.stats(reset=True)
     units, njobs = e2e.units, e2e.njobs
+    ct_e2e = e2e.la.cutree_stats()
     e2e.close()
     clocks = sampler.stop()
 
@@ -420,7 +445,7 @@ def main():
     }
     kms = {k: v / args.steps for k, v in st["ms"].items()}
     klaunch = {k: v / args.steps for k, v in st["launches"].items()}
-    dom = max(("lowres", "intra", "search", "cost", "weight", "var"), key=lambda k: kms[k])
+    dom = max(("lowres", "intra", "search", "cost", "weight", "var", "cutree"), key=lambda k: kms[k])
     # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/traffic.json holds
     # dram__bytes_read.sum + dram__bytes_write.sum of the captured launch and how many units that launch processed);
     # scaled to the units of an average launch here, like `achieved`
@@ -484,6 +509,8 @@ def main():
                    "search_path": os.environ.get("X265CU_SEARCH_MODE", "2 (per search: plain wavefront kernel, or refine + commit for small batches with a close hint)"),
                    "lookahead_cache": os.environ.get("X265CU_LOOKAHEAD_CACHE", "1 (non-batch estimates predicted from the request history ride in one launch)"),
                    "l2": "working set per step (%d frames x 4 padded planes + sources, > 300 MB) exceeds the 126 MB L2; no explicit flush" % nframes,
+                   "cutree": "%d propagate steps per step on the GPU (estimateCUPropagate, SURVEY 8f-1), one launch per run of steps; "
+                             "mirrors found stale: %d resident / %d e2e (re-uploaded)" % (npropagate, ct_value["reuploads"], ct_e2e["reuploads"]),
                    "parity": parity},
         "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": st_e2e["h2d"] // args.steps, "d2h_bytes_per_step": st_e2e["d2h"] // args.steps},

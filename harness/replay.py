@@ -49,14 +49,16 @@ class CuReplay:
         self.cfg = cfg
         # lookaheadSlices as the user gave it is not in the trace; numCoopSlices is: reproduce it
         slices = cfg["numCoopSlices"] if cfg["numCoopSlices"] > 1 else 0
+        ct = dict(fps_num=cfg.get("fpsNum", 30), fps_denom=cfg.get("fpsDenom", 1), qcompress=cfg.get("qCompress", 0.6),
+                  weighted_bipred=cfg.get("weightedBiPred", 0))
         self.la = abi.Lookahead(cfg["width"], cfg["height"], cfg["depth"], cfg["bframes"], cfg["lookahead"], slices,
-                                cfg["pool"], cfg["weightp"], cfg["aqmode"], cfg["aqStrength"], cfg["bFrameBias"], device, slots)
+                                cfg["pool"], cfg["weightp"], cfg["aqmode"], cfg["aqStrength"], cfg["bFrameBias"], device, slots, **ct)
         if slices and (self.la.numCoopSlices, self.la.numRowsPerSlice) != (cfg["numCoopSlices"], cfg["numRowsPerSlice"]):
             # numCoopSlices = H8 / rowsPerSlice is not invertible in general; fall back to a search
             self.la.close()
             for s in range(2, 17):
                 self.la = abi.Lookahead(cfg["width"], cfg["height"], cfg["depth"], cfg["bframes"], cfg["lookahead"], s,
-                                        cfg["pool"], cfg["weightp"], cfg["aqmode"], cfg["aqStrength"], cfg["bFrameBias"], device, slots)
+                                        cfg["pool"], cfg["weightp"], cfg["aqmode"], cfg["aqStrength"], cfg["bFrameBias"], device, slots, **ct)
                 if (self.la.numCoopSlices, self.la.numRowsPerSlice) == (cfg["numCoopSlices"], cfg["numRowsPerSlice"]):
                     break
                 self.la.close()
@@ -71,6 +73,8 @@ class CuReplay:
         self.mismatches = []
         self.njobs = 0
         self.nframes = 0
+        self.npropagate = 0
+        self.cutree = True      # replay the cuTree events (M/X/F) of the trace
         self.lib = po.oracle(cfg["depth"])
 
     def close(self):
@@ -165,6 +169,29 @@ class CuReplay:
             self._chk(tag + "lowresCosts", la.crc(f, 4, d0, d1), j["lowresCosts"])
             self._chk(tag + "rowSatds", la.crc(f, 5, d0, d1), j["rowSatds"])
 
+    # ---- cuTree: the memsets, propagate steps and cuTreeFinish calls of Lookahead::cuTree, in the
+    # reference's order, interleaved with its estimates exactly as the trace recorded them
+    def ct_propagate(self, x):
+        lo, hi = x["p0"], x["p1"]
+        frames = [self.frames.get(p) for p in range(lo, hi + 1)]
+        self.la.cutree_propagate(frames, 0, hi - lo, x["b"] - lo, x["referenced"], x["avgDuration"])
+        self.npropagate += 1
+        if not self.check:
+            return
+        la, tag = self.la, "X%d/%d/%d." % (x["p0"], x["b"], x["p1"])
+        self._chk(tag + "ref0", la.crc(self.frames[x["p0"]], 8), x["ref0"])
+        if x["p1"] != x["b"]:
+            self._chk(tag + "ref1", la.crc(self.frames[x["p1"]], 8), x["ref1"])
+        self._chk(tag + "own", la.crc(self.frames[x["b"]], 8, 0 if x["referenced"] else 1), x["own"])
+
+    def ct_finish(self, e):
+        f = self.frames[e["poc"]]
+        self.la.cutree_finish(f, e["avgDuration"], e["ref0Distance"])
+        if not self.check:
+            return
+        self._chk("F%d.propagateCost" % e["poc"], self.la.crc(f, 8), e["propagateCost"])
+        self._chk("F%d.qpCuTreeOffset" % e["poc"], self.la.crc(f, 9), e["qpCuTreeOffset"])
+
     def run(self, max_events=None, stop_on_mismatch=False):
         n = 0
         pend = []
@@ -183,6 +210,12 @@ class CuReplay:
                 self._run_jobs([e[1]], False)
             elif e[0] == "B" and e[1]:
                 self._run_jobs(e[1], True)
+            elif self.cutree and e[0] == "M":
+                self.la.cutree_zero(self.frames[e[1]])
+            elif self.cutree and e[0] == "X":
+                self.ct_propagate(e[1])
+            elif self.cutree and e[0] == "F":
+                self.ct_finish(e[1])
             n += 1
             if max_events and n >= max_events:
                 break
@@ -199,7 +232,8 @@ def replay_trace(name, device=0, max_events=None, check=True):
     try:
         t0 = time.time()
         mm = r.run(max_events=max_events)
-        return dict(name=name, jobs=r.njobs, frames=r.nframes, seconds=time.time() - t0, mismatches=mm)
+        return dict(name=name, jobs=r.njobs, frames=r.nframes, propagates=r.npropagate, cutree=r.la.cutree_stats(),
+                    seconds=time.time() - t0, mismatches=mm)
     finally:
         r.close()
 
@@ -230,13 +264,15 @@ def smoke():
         want = lib.ola_satd8x8(a.ctypes.data + int(o), 64, b.ctypes.data + int(o), 64)
         if want != out[i]:
             return False, "satd mismatch at %d: %d vs %d" % (i, out[i], want)
-    return True, "tiny8 replay (%d frames, %d estimates) bit-exact vs reference trace; SATD batch == oracle" % (res["frames"], res["jobs"])
+    return True, "tiny8 replay (%d frames, %d estimates, %d cuTree propagate steps) bit-exact vs reference trace; SATD batch == oracle" % (
+        res["frames"], res["jobs"], res["propagates"])
 
 
 if __name__ == "__main__":
     names = sys.argv[1:] or ["tiny8"]
     for nm in names:
         r = replay_trace(nm)
-        print("%-12s frames %d jobs %d  %.2fs  mismatches %d" % (nm, r["frames"], r["jobs"], r["seconds"], len(r["mismatches"])))
+        print("%-12s frames %d jobs %d propagates %d %r  %.2fs  mismatches %d" % (nm, r["frames"], r["jobs"], r["propagates"], r["cutree"],
+                                                                                r["seconds"], len(r["mismatches"])))
         for m in r["mismatches"][:12]:
             print("    ", m)

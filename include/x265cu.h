@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define X265CU_ABI_VERSION 1
+#define X265CU_ABI_VERSION 2
 #define X265CU_BFRAME_MAX 16
 
 enum
@@ -186,6 +186,31 @@ typedef struct x265cu_job_result
 } x265cu_job_result;
 int x265cu_estimate_batch(x265cu_ctx* ctx, int n, const x265cu_job* jobs, x265cu_job_result* results);
 
+/* ---- cuTree propagation: Lookahead::estimateCUPropagate (slicetype.cpp:1741-1839) with its
+ * primitive estimateCUPropagateCost (common/pixel.cpp:848-874), and the memsets of Lowres::propagateCost in
+ * Lookahead::cuTree (slicetype.cpp:1668-1701).  The device keeps one propagateCost array per frame slot next to
+ * the arrays the estimates left there (intraCost, invQscaleFactor, lowresCosts[d0][d1], lowresMvs[l][d]), so a
+ * cuTree pass uploads nothing.  One call takes the ops of a (part of a) cuTree pass IN THE REFERENCE'S ORDER and
+ * runs them as one launch; outSlots/outPropagateCost name the frames whose propagateCost (cuCount uint16 each)
+ * the host wants back (cuTreeFinish reads it, slicetype.cpp:1844-1862; its log2 math stays on the host). */
+enum { X265CU_CT_ZERO = 0, X265CU_CT_PROPAGATE = 1 };
+typedef struct x265cu_cutree_op
+{
+    int kind;                     /* X265CU_CT_ZERO: memset(frames[fenc]->propagateCost, 0, cuCount * 2) */
+    int fenc, ref0, ref1;         /* frame slots of frames[b], frames[p0], frames[p1] */
+    int d0, d1;                   /* b - p0, p1 - b: lowresCosts[d0][d1], lowresMvs[0][d0-1], lowresMvs[1][d1-1] */
+    int referenced;               /* estimateCUPropagate's `referenced` */
+    int bipredWeight;             /* bipredWeights[0] (slicetype.cpp:1745-1746): 32 without weighted bipred */
+    double fpsFactor;             /* CLIP_DURATION(fpsDenom / fpsNum) / CLIP_DURATION(averageDuration) (:1754) */
+} x265cu_cutree_op;
+int x265cu_cutree_run(x265cu_ctx* ctx, int n, const x265cu_cutree_op* ops, int nOut, const int* outSlots, uint16_t* const* outPropagateCost);
+/* overwrite the device's propagateCost of a frame with the host's (hosts that keep the cuTree control flow and
+ * its memsets/swaps on their side: INTEGRATION.md) */
+int x265cu_frame_set_propagate(x265cu_ctx* ctx, int slot, const uint16_t* propagateCost);
+/* overwrite a device mirror with the host's array: which = 4 lowresCosts[d0][d1], 6 lowresMvs[list = d0][d1 - 1]
+ * (numbering of the host layer's accessors).  Only needed when the host knows the mirror is not the official array. */
+int x265cu_frame_set_array(x265cu_ctx* ctx, int slot, int which, int d0, int d1, const void* data);
+
 /* ---- EncoderPrimitives kernels as batch operations (common/pixel.cpp:39-118,143-322):
  * pu[LUMA_8x8].sad / .satd, cu[BLOCK_8x8].sa8d, cu[BLOCK_16x16].sa8d over n block pairs taken at
  * sample offsets offA[i] / offB[i] of two buffers with strides strideA / strideB (samples).
@@ -204,7 +229,7 @@ int x265cu_int_peak(x265cu_ctx* ctx, double* gopsVabsdiff4, double* gopsIadd);
 
 /* ---- instrumentation: device time (ms, CUDA events on the ctx stream) and launch counts
  * accumulated since the last reset, per kernel family. */
-enum { X265CU_K_LOWRES = 0, X265CU_K_INTRA, X265CU_K_SEARCH, X265CU_K_COST, X265CU_K_WEIGHT, X265CU_K_PIXEL, X265CU_K_VAR, X265CU_K_COUNT };
+enum { X265CU_K_LOWRES = 0, X265CU_K_INTRA, X265CU_K_SEARCH, X265CU_K_COST, X265CU_K_WEIGHT, X265CU_K_PIXEL, X265CU_K_VAR, X265CU_K_CUTREE, X265CU_K_COUNT };
 typedef struct x265cu_stats
 {
     double ms[X265CU_K_COUNT];

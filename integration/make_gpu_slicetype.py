@@ -8,6 +8,7 @@ reference source (one-line anchors only).  The copy lives under oracle/_ref/ (gi
   :851   PreLookaheadGroup::processTasks  -> x265glue_pre        (GPU lowres planes + intra estimate)
   :486   weightsAnalyse accepted a weight  -> x265glue_weight
   :2007  estimateFrameCost, before the CPU loops -> `if (x265glue_estimate(...)) {} else <CPU loops>`
+  :1760  estimateCUPropagate, before its CU loops -> `if (x265glue_propagate(...)) {} else <CPU loops>` (cuTree)
 """
 import re
 import sys
@@ -34,6 +35,9 @@ def main():
     i = find(r'CostEstimateGroup::estimateFrameCost\(LookaheadTLD& tld')
     j = find(r'^\s*if \(!m_batchMode && m_lookahead\.m_numCoopSlices > 1', i)
     inserts.append((j, '        if (x265glue_estimate(&m_lookahead, m_frames, p0, p1, b, bDoSearch, m_batchMode)) { } else'))
+    i = find(r'^void Lookahead::estimateCUPropagate\(')
+    j = find(r'^\s*for \(uint16_t blocky = 0; blocky < m_8x8Height; blocky\+\+\)', i)
+    inserts.append((j, '    if (x265glue_propagate(this, frames, fpsFactor, bipredWeight, p0, p1, b, referenced)) { } else'))
     for idx, text in sorted(inserts, key=lambda t: -t[0]):
         lines.insert(idx, text)
     open(out_path, "w").write("\n".join(lines))

@@ -140,3 +140,27 @@ extern "C" int x265glue_estimate(Lookahead* la, Lowres** frames, int p0, int p1,
     if (p1 == b) fenc->intraMbs[d0] += r.intraMbs;
     return 1;
 }
+
+extern "C" int x265glue_propagate(Lookahead* la, Lowres** frames, double fpsFactor, int bipredWeight, int p0, int p1, int b, int referenced)
+{
+    pthread_mutex_lock(&g_lock);
+    GlueState& st = g_states[la];
+    const int sb = slotOf(st, frames[b]), s0 = slotOf(st, frames[p0]), s1 = slotOf(st, frames[p1]);
+    pthread_mutex_unlock(&g_lock);
+    /* x265 keeps cuTree's control flow and its memsets, so the arrays it owns are the truth before every step */
+    if (referenced && x265cu_frame_set_propagate(st.ctx, sb, frames[b]->propagateCost)) die("x265cu_frame_set_propagate", st.ctx);
+    if (x265cu_frame_set_propagate(st.ctx, s0, frames[p0]->propagateCost)) die("x265cu_frame_set_propagate", st.ctx);
+    if (p1 != b && x265cu_frame_set_propagate(st.ctx, s1, frames[p1]->propagateCost)) die("x265cu_frame_set_propagate", st.ctx);
+    x265cu_cutree_op op;
+    memset(&op, 0, sizeof(op));
+    op.kind = X265CU_CT_PROPAGATE;
+    op.fenc = sb; op.ref0 = s0; op.ref1 = s1;
+    op.d0 = b - p0; op.d1 = p1 - b;
+    op.referenced = referenced;
+    op.bipredWeight = bipredWeight;
+    op.fpsFactor = fpsFactor;
+    int outSlots[2] = { s0, s1 };
+    uint16_t* outs[2] = { frames[p0]->propagateCost, frames[p1]->propagateCost };
+    if (x265cu_cutree_run(st.ctx, 1, &op, p1 != b ? 2 : 1, outSlots, outs)) die("x265cu_cutree_run", st.ctx);
+    return 1;
+}

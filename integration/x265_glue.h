@@ -19,6 +19,9 @@ void x265glue_pre(X265_NS::Lookahead* la, X265_NS::Frame* frame);
 void x265glue_weight(int scale, int denom, int offset);
 /* estimateFrameCost, non-cached branch: run the estimate on the GPU; returns 1 when done */
 int x265glue_estimate(X265_NS::Lookahead* la, X265_NS::Lowres** frames, int p0, int p1, int b, const bool* bDoSearch, int batchMode);
+/* estimateCUPropagate, instead of its CU loops: one propagate step on the GPU (the cuTree control flow, its memsets
+ * and cuTreeFinish stay x265's; the propagateCost arrays of the frames involved travel with the call); returns 1 */
+int x265glue_propagate(X265_NS::Lookahead* la, X265_NS::Lowres** frames, double fpsFactor, int bipredWeight, int p0, int p1, int b, int referenced);
 }
 
 #endif

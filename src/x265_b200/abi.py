@@ -14,7 +14,7 @@ LIB_CU = os.path.join(PKG, "libx265cu.so")
 LIB_HOST = os.path.join(PKG, "libx265cu_host.so")
 
 BFMAX = 16
-K_NAMES = ("lowres", "intra", "search", "cost", "weight", "pixel", "var")
+K_NAMES = ("lowres", "intra", "search", "cost", "weight", "pixel", "var", "cutree")
 
 
 class Config(C.Structure):
@@ -51,14 +51,20 @@ class JobResult(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [("ms", C.c_double * 7), ("launches", C.c_int64 * 7), ("h2dBytes", C.c_int64), ("d2hBytes", C.c_int64)]
+    _fields_ = [("ms", C.c_double * 8), ("launches", C.c_int64 * 8), ("h2dBytes", C.c_int64), ("d2hBytes", C.c_int64)]
 
 
 class HostParams(C.Structure):
     _fields_ = [("sourceWidth", C.c_int), ("sourceHeight", C.c_int), ("bitDepth", C.c_int), ("maxCUSize", C.c_int),
                 ("bframes", C.c_int), ("lookaheadDepth", C.c_int), ("lookaheadSlices", C.c_int), ("poolWorkers", C.c_int),
                 ("bEnableWeightedPred", C.c_int), ("aqMode", C.c_int), ("aqStrength", C.c_double),
-                ("bFrameBias", C.c_int), ("device", C.c_int), ("frameSlots", C.c_int), ("stream", C.c_void_p), ("searchWarps", C.c_int)]
+                ("bFrameBias", C.c_int), ("device", C.c_int), ("frameSlots", C.c_int), ("stream", C.c_void_p), ("searchWarps", C.c_int),
+                ("fpsNum", C.c_int), ("fpsDenom", C.c_int), ("qCompress", C.c_double), ("bEnableWeightedBiPred", C.c_int)]
+
+
+class CutreeOp(C.Structure):
+    _fields_ = [("kind", C.c_int), ("fenc", C.c_int), ("ref0", C.c_int), ("ref1", C.c_int), ("d0", C.c_int), ("d1", C.c_int),
+                ("referenced", C.c_int), ("bipredWeight", C.c_int), ("fpsFactor", C.c_double)]
 
 
 # every symbol include/x265cu.h declares (tests check that the library exports all of them)
@@ -69,6 +75,7 @@ ABI_SYMBOLS = (
     "x265cu_intra", "x265cu_intra_batch",
     "x265cu_weight_cost_batch", "x265cu_estimate_batch", "x265cu_pixelcmp_batch", "x265cu_pixelcmp_frames", "x265cu_int_peak",
     "x265cu_stats_enable", "x265cu_stats_get",
+    "x265cu_cutree_run", "x265cu_frame_set_propagate", "x265cu_frame_set_array",
 )
 
 _cu = None
@@ -98,6 +105,9 @@ def lib_cu():
                                             C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.x265cu_pixelcmp_frames.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
         L.x265cu_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.x265cu_cutree_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(CutreeOp), C.c_int, C.c_void_p, C.c_void_p]
+        L.x265cu_frame_set_propagate.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.x265cu_frame_set_array.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.x265cu_stats_enable.argtypes = [C.c_void_p, C.c_int]
         L.x265cu_stats_get.argtypes = [C.c_void_p, C.POINTER(Stats), C.c_int]
         _cu = L
@@ -129,6 +139,10 @@ def lib_host():
         L.x265cuh_array.restype = C.c_void_p
         L.x265cuh_array.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
         L.x265cuh_frame_scalars.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.x265cuh_cutree_zero.argtypes = [C.c_void_p, C.c_void_p]
+        L.x265cuh_cutree_propagate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]
+        L.x265cuh_cutree_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int]
+        L.x265cuh_cutree_stats.argtypes = [C.c_void_p, C.c_void_p]
         L.x265cuh_crc32.restype = C.c_uint32
         L.x265cuh_crc32.argtypes = [C.c_void_p, C.c_size_t]
         L.x265cuh_error.restype = C.c_char_p
@@ -141,10 +155,11 @@ class Lookahead:
     """Python handle on x265cu::Lookahead (host/lookahead_cu.h)."""
 
     def __init__(self, width, height, depth=8, bframes=4, lookahead=20, slices=8, pool=16, weightp=1, aq_mode=1,
-                 aq_strength=1.0, bframe_bias=0, device=0, slots=0, ctu=64, stream=None, search_warps=0):
+                 aq_strength=1.0, bframe_bias=0, device=0, slots=0, ctu=64, stream=None, search_warps=0,
+                 fps_num=30, fps_denom=1, qcompress=0.6, weighted_bipred=0):
         self.L = lib_host()
         p = HostParams(width, height, depth, ctu, bframes, lookahead, slices, pool, weightp, aq_mode, aq_strength, bframe_bias, device, slots,
-                       stream, search_warps)
+                       stream, search_warps, fps_num, fps_denom, qcompress, weighted_bipred)
         err = C.create_string_buffer(512)
         self.h = self.L.x265cuh_open(C.byref(p), err, 512)
         if not self.h:
@@ -249,6 +264,24 @@ class Lookahead:
         if not p or not nb.value:
             return 0
         return int(self.L.x265cuh_crc32(p, nb.value))
+
+    # ---- cuTree propagation (host/lookahead_cu.h: cuTreeZero / estimateCUPropagate / cuTreeFinish)
+    def cutree_zero(self, frame):
+        self.L.x265cuh_cutree_zero(self.h, frame)
+
+    def cutree_propagate(self, frames, p0, p1, b, referenced, average_duration):
+        fr = (C.c_void_p * len(frames))(*frames)
+        if self.L.x265cuh_cutree_propagate(self.h, fr, len(frames), p0, p1, b, referenced, average_duration):
+            raise RuntimeError("estimateCUPropagate failed: " + self.error())
+
+    def cutree_finish(self, frame, average_duration, ref0_distance):
+        if self.L.x265cuh_cutree_finish(self.h, frame, average_duration, ref0_distance):
+            raise RuntimeError("cuTreeFinish failed: " + self.error())
+
+    def cutree_stats(self):
+        o = (C.c_int64 * 3)()
+        self.L.x265cuh_cutree_stats(self.h, o)
+        return dict(zip(("steps", "runs", "reuploads"), list(o)))
 
     def scalars(self, frame, d0, d1):
         o = (C.c_int64 * 9)()

@@ -14,6 +14,7 @@
  */
 #include "../../../include/x265cu.h"
 #include "x265cu_kernels.cuh"
+#include "x265cu_cutree.cuh"
 
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -59,6 +60,9 @@ struct x265cu_ctx
     int* dRowSatds;
     int* dMvs;
     int* dMvCosts;
+    unsigned long long* dPropagate;        /* [slot][nCU] Lowres::propagateCost accumulators (x265cu_cutree.cuh) */
+    uint16_t* dPropOut; size_t dPropOutCap; /* clamped uint16 copies on their way to the host */
+    uint16_t* hPropOut; size_t hPropOutCap;
     uint16_t* dLut;        /* base; centre at +65536 */
     uint8_t* dSrc;         /* full-resolution luma staging (strided-copy fallback) */
     uint8_t* dSrcLin; size_t dSrcLinCap;   /* luma staging with the host's pitch (linear transfer) */
@@ -219,6 +223,7 @@ void freeAll(x265cu_ctx* c)
 {
     cudaFree(c->dPlanes); cudaFree(c->dIntraCost); cudaFree(c->dIntraMode); cudaFree(c->dInvQ);
     cudaFree(c->dLowresCosts); cudaFree(c->dRowSatds); cudaFree(c->dMvs); cudaFree(c->dMvCosts);
+    cudaFree(c->dPropagate); cudaFree(c->dPropOut); if (c->hPropOut) cudaFreeHost(c->hPropOut);
     cudaFree(c->dLut); cudaFree(c->dSrc); cudaFree(c->dSmall); cudaFree(c->dStage); cudaFree(c->dArgs); cudaFree(c->dGeneric); cudaFree(c->dMemo); cudaFree(c->dSrcLin); cudaFree(c->dUp); cudaFree(c->dPre);
     if (c->upStream) cudaStreamDestroy(c->upStream);
     for (size_t i = 0; i < c->upEvents.size(); i++) cudaEventDestroy(c->upEvents[i]);
@@ -273,6 +278,7 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     c->dMvs = NULL; c->dMvCosts = NULL; c->dLut = NULL; c->dSrc = NULL; c->dSmall = NULL;
     c->dStage = NULL; c->dStageCap = 0; c->hStage = NULL; c->hStageCap = 0; c->dArgs = NULL; c->dArgsCap = 0; c->hArgs = NULL; c->hArgsCap = 0; c->hPre = NULL; c->hPreCap = 0; c->dPre = NULL; c->dPreCap = 0; c->dSrcLin = NULL; c->dSrcLinCap = 0; c->dUp = NULL; c->dUpCap = 0; c->upStream = NULL;
     c->dGeneric = NULL; c->dGenericCap = 0; c->dMemo = NULL; c->dMemoCap = 0;
+    c->dPropagate = NULL; c->dPropOut = NULL; c->dPropOutCap = 0; c->hPropOut = NULL; c->hPropOutCap = 0;
     c->timing = false;
     memset(&c->stats, 0, sizeof(c->stats));
     c->stream = NULL; c->ownStream = false; c->copyStream = NULL; c->evKernel = NULL;
@@ -348,6 +354,8 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     OPEN_TRY(cudaMalloc((void**)&c->dMvCosts, S * t1 * n * sizeof(int)));
     OPEN_TRY(cudaMemsetAsync(c->dMvs, 0, S * t1 * n * sizeof(int), c->stream));
     OPEN_TRY(cudaMemsetAsync(c->dMvCosts, 0, S * t1 * n * sizeof(int), c->stream));
+    OPEN_TRY(cudaMalloc((void**)&c->dPropagate, S * n * sizeof(unsigned long long)));
+    OPEN_TRY(cudaMemsetAsync(c->dPropagate, 0, S * n * sizeof(unsigned long long), c->stream));
     OPEN_TRY(cudaMalloc((void**)&c->dLut, (4 * 32768 + 1) * sizeof(uint16_t)));
     OPEN_TRY(cudaMemcpyAsync(c->dLut, cfg->mvcost - 2 * 32768, (4 * 32768 + 1) * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
     c->srcPitch = (int64_t)alignUp((size_t)(2 * g.width + 1), 64);
@@ -763,6 +771,130 @@ int x265cu_intra_batch(x265cu_ctx* c, int n, const int* slots, x265cu_intra_out*
         const unsigned long long* sm = (const unsigned long long*)(c->hPre + (size_t)i * 16);
         outs[i].sums[0] = (int64_t)sm[0];
         outs[i].sums[1] = (int64_t)sm[1];
+    }
+    return X265CU_OK;
+}
+
+/* ---- cuTree propagation (x265cu_cutree.cuh) ---- */
+int x265cu_frame_set_propagate(x265cu_ctx* c, int slot, const uint16_t* propagateCost)
+{
+    if (!c || badSlot(c, slot) || !propagateCost) return c ? fail(c, X265CU_EINVAL, "x265cu_frame_set_propagate: bad argument") : X265CU_EINVAL;
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CU_TRY(c, cudaSetDevice(c->cfg.device));
+    const size_t n = (size_t)c->g.nCU;
+    if (growHost(c, (uint8_t**)&c->hPropOut, &c->hPropOutCap, n * sizeof(unsigned long long))) return X265CU_ECUDA;
+    /* the staging area is reused: earlier copies out of / into it must have finished */
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    unsigned long long* w = (unsigned long long*)c->hPropOut;
+    for (size_t i = 0; i < n; i++) w[i] = propagateCost[i];
+    CU_TRY(c, cudaMemcpyAsync(c->dPropagate + (size_t)slot * n, w, n * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    c->stats.h2dBytes += (int64_t)(n * sizeof(unsigned long long));
+    return X265CU_OK;
+}
+
+int x265cu_frame_set_array(x265cu_ctx* c, int slot, int which, int d0, int d1, const void* data)
+{
+    if (!c || badSlot(c, slot) || !data) return c ? fail(c, X265CU_EINVAL, "x265cu_frame_set_array: bad argument") : X265CU_EINVAL;
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CU_TRY(c, cudaSetDevice(c->cfg.device));
+    const size_t n = (size_t)c->g.nCU;
+    void* dst; size_t bytes;
+    if (which == 4 && d0 >= 0 && d0 < c->bf + 2 && d1 >= 0 && d1 < c->bf + 2) { dst = slotLowresCosts(c, slot, d0, d1); bytes = n * sizeof(uint16_t); }
+    else if (which == 6 && (d0 == 0 || d0 == 1) && d1 >= 1 && d1 <= c->bf + 1) { dst = slotMvs(c, slot, d0, d1); bytes = n * sizeof(int); }
+    else return fail(c, X265CU_EINVAL, "x265cu_frame_set_array: unknown array");
+    /* stream-ordered before the kernels that read it; waits, so the caller's array may change afterwards */
+    CU_TRY(c, cudaMemcpyAsync(dst, data, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    c->stats.h2dBytes += (int64_t)bytes;
+    return X265CU_OK;
+}
+
+int x265cu_cutree_run(x265cu_ctx* c, int n, const x265cu_cutree_op* ops, int nOut, const int* outSlots, uint16_t* const* outPropagateCost)
+{
+    if (!c || n < 0 || nOut < 0 || (n && !ops) || (nOut && (!outSlots || !outPropagateCost)))
+        return c ? fail(c, X265CU_EINVAL, "x265cu_cutree_run: bad argument") : X265CU_EINVAL;
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CU_TRY(c, cudaSetDevice(c->cfg.device));
+    const int bf = c->bf;
+    const size_t nCU = (size_t)c->g.nCU;
+    for (int i = 0; i < n; i++)
+    {
+        const x265cu_cutree_op& o = ops[i];
+        if (badSlot(c, o.fenc)) return fail(c, X265CU_EINVAL, "x265cu_cutree_run: bad frame slot");
+        if (o.kind == X265CU_CT_ZERO) continue;
+        if (o.kind != X265CU_CT_PROPAGATE) return fail(c, X265CU_EINVAL, "x265cu_cutree_run: unknown op");
+        if (badSlot(c, o.ref0) || badSlot(c, o.ref1) || o.d0 < 1 || o.d0 > bf + 1 || o.d1 < 0 || o.d1 > bf + 1)
+            return fail(c, X265CU_EINVAL, "x265cu_cutree_run: bad references");
+        if (!c->hasInvQ[o.fenc]) return fail(c, X265CU_EINVAL, "x265cu_cutree_run: frame has no invQscaleFactor (cuTree needs the AQ arrays)");
+    }
+    for (int i = 0; i < nOut; i++)
+        if (badSlot(c, outSlots[i]) || !outPropagateCost[i]) return fail(c, X265CU_EINVAL, "x265cu_cutree_run: bad output");
+    if (n + nOut == 0) return X265CU_OK;
+    if (nOut)
+    {
+        if (growDevice(c, (uint8_t**)&c->dPropOut, &c->dPropOutCap, (size_t)nOut * nCU * sizeof(uint16_t))) return X265CU_ECUDA;
+        if (growHost(c, (uint8_t**)&c->hPropOut, &c->hPropOutCap, (size_t)nOut * nCU * sizeof(unsigned long long))) return X265CU_ECUDA;
+    }
+
+    CutreeArgs a;
+    a.wCU = c->g.wCU; a.hCU = c->g.hCU; a.nCU = c->g.nCU;
+    a.costTables = (bf + 2) * (bf + 2); a.mvFields = 2 * (bf + 1);
+    a.intraCost = c->dIntraCost; a.invQ = c->dInvQ; a.lowresCosts = c->dLowresCosts; a.mvs = c->dMvs;
+    a.acc = c->dPropagate; a.out = c->dPropOut;
+    a.nOps = 0;
+
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3(CUTREE_CTAS); lc.blockDim = dim3(CUTREE_THREADS); lc.dynamicSmemBytes = 0; lc.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CUTREE_CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    lc.attrs = attr; lc.numAttrs = 1;
+
+    {
+        KernelScope ks(c, X265CU_K_CUTREE, 0);
+        /* ops in the caller's order, then one PACK per requested output; CUTREE_MAX_OPS per launch (launches of
+         * one stream run in order, so a longer list simply continues in the next launch) */
+        for (int i = 0; i < n + nOut; i++)
+        {
+            CutreeOpDev& d = a.ops[a.nOps++];
+            memset(&d, 0, sizeof(d));
+            if (i < n)
+            {
+                const x265cu_cutree_op& o = ops[i];
+                d.kind = o.kind == X265CU_CT_ZERO ? CT_OP_ZERO : CT_OP_PROPAGATE;
+                d.fenc = o.fenc;
+                if (d.kind == CT_OP_PROPAGATE)
+                {
+                    d.ref0 = o.ref0; d.ref1 = o.ref1;
+                    d.costOfs = o.d0 * (bf + 2) + o.d1;
+                    d.mvOfs0 = o.d0 - 1;
+                    d.mvOfs1 = o.d1 > 0 ? (bf + 1) + o.d1 - 1 : -1;
+                    d.referenced = o.referenced != 0;
+                    d.bipredWeight = o.bipredWeight;
+                    d.fps = o.fpsFactor * (1.0 / 256);      /* exact scaling, as the reference's `*fpsFactor / 256` */
+                }
+            }
+            else
+            {
+                d.kind = CT_OP_PACK; d.fenc = outSlots[i - n]; d.outIndex = i - n;
+            }
+            if (a.nOps == CUTREE_MAX_OPS || i == n + nOut - 1)
+            {
+                CU_TRY(c, cudaLaunchKernelEx(&lc, cutree_kernel, a));
+                c->stats.launches[X265CU_K_CUTREE]++;
+                a.nOps = 0;
+            }
+        }
+    }
+    if (nOut)
+    {
+        CU_TRY(c, cudaMemcpyAsync(c->hPropOut, c->dPropOut, (size_t)nOut * nCU * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
+        if (syncStream(c)) return X265CU_ECUDA;
+        for (int i = 0; i < nOut; i++)
+            memcpy(outPropagateCost[i], c->hPropOut + (size_t)i * nCU, nCU * sizeof(uint16_t));
+        c->stats.d2hBytes += (int64_t)((size_t)nOut * nCU * sizeof(uint16_t));
     }
     return X265CU_OK;
 }

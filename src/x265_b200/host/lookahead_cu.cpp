@@ -88,6 +88,11 @@ bool Lookahead::create(const Param& p)
 {
     m_param = p;
     if (!m_param.maxCUSize) m_param.maxCUSize = 64;
+    if (m_param.fpsNum <= 0 || m_param.fpsDenom <= 0) { m_param.fpsNum = 30; m_param.fpsDenom = 1; }
+    if (m_param.qCompress <= 0) m_param.qCompress = 0.6;
+    m_cuTreeStrength = 5.0 * (1.0 - m_param.qCompress);      /* slicetype.cpp:511 */
+    m_ctStats[0] = m_ctStats[1] = m_ctStats[2] = 0;
+    m_ctOps.clear();
     m_8x8Height = ((p.sourceHeight / 2) + 7) >> 3;
     m_8x8Width = ((p.sourceWidth / 2) + 7) >> 3;
     m_cuCount = m_8x8Width * m_8x8Height;
@@ -155,7 +160,7 @@ Lowres* Lookahead::allocLowres()
     const int bf = m_param.bframes, n = m_cuCount, rows = m_8x8Height;
     const size_t pb = m_geom.pixelBytes;
     size_t bytes = alignUp((size_t)4 * m_geom.planeSize * pb, 64);
-    bytes += alignUp((size_t)n * 4, 64) + alignUp((size_t)n, 64);                         /* intraCost, intraMode */
+    bytes += alignUp((size_t)n * 4, 64) + alignUp((size_t)n, 64) + alignUp((size_t)n * 2, 64);   /* intraCost, intraMode, propagateCost */
     bytes += 2 * alignUp((size_t)n * 8, 64) + 2 * alignUp((size_t)n * 4, 64);             /* qpAq, qpCuTree, invQ, blockVariance */
     bytes += (size_t)(bf + 2) * (bf + 2) * (alignUp((size_t)rows * 4, 64) + alignUp((size_t)n * 2, 64));
     bytes += (size_t)2 * (bf + 1) * 2 * alignUp((size_t)n * 4, 64);
@@ -172,6 +177,7 @@ Lowres* Lookahead::allocLowres()
     p += alignUp((size_t)4 * m_geom.planeSize * pb, 64);
     l->intraCost = (int32_t*)p; p += alignUp((size_t)n * 4, 64);
     l->intraMode = p; p += alignUp((size_t)n, 64);
+    l->propagateCost = (uint16_t*)p; p += alignUp((size_t)n * 2, 64);
     l->qpAqOffset = (double*)p; p += alignUp((size_t)n * 8, 64);
     l->qpCuTreeOffset = (double*)p; p += alignUp((size_t)n * 8, 64);
     l->invQscaleFactor = (int*)p; p += alignUp((size_t)n * 4, 64);
@@ -221,7 +227,11 @@ void Lookahead::freeLowres(Lowres* l)
 void Lookahead::lowresReset(Lowres& l, int poc)
 {
     forgetFrame(&l);
+    if (!m_ctOps.empty()) cuTreeRun(NULL, 0);   /* queued cuTree steps still read this frame's old arrays */
     memset(l.mvVersion, 0, sizeof(l.mvVersion));
+    memset(l.devMvVersion, 0, sizeof(l.devMvVersion));
+    memset(l.costStamp, 0, sizeof(l.costStamp));
+    memset(l.devCostStamp, 0, sizeof(l.devCostStamp));
     l.frameNum = poc;
     memset(l.costEst, -1, sizeof(l.costEst));
     memset(l.weightedCostDelta, 0, sizeof(l.weightedCostDelta));
@@ -623,6 +633,7 @@ bool CostEstimateGroup::takeAhead(Lowres* fenc, Lowres* ref0, Lowres* ref1, int 
         }
         for (int l = 0; l < 2; l++)
             if (e.doSearch[l]) fenc->mvVersion[l][(l ? d1 : d0) - 1] = e.newVersion[l];
+        fenc->costStamp[d0][d1] = e.costStamp;
         fenc->costEst[d0][d1] = e.res.costEst;
         fenc->costEstAq[d0][d1] = e.res.costEstAq;
         if (d1 == 0) fenc->intraMbs[d0] += e.res.intraMbs;
@@ -784,8 +795,11 @@ bool CostEstimateGroup::runEstimates(const EstReq* est, int n)
                 newVersion[l] = ++la.m_versionCounter;
                 Produced pr = { fenc, l, d, newVersion[l] };
                 produced.push_back(pr);
+                fenc->devMvVersion[l][d - 1] = newVersion[l];     /* this launch overwrites the device mirror of the field */
             }
         }
+        const uint64_t costStamp = ++la.m_versionCounter;
+        fenc->devCostStamp[d0][d1] = costStamp;                   /* ... and of lowresCosts[d0][d1] */
         if (!usable) { snprintf(la.m_error, sizeof(la.m_error), "runEstimates: dependent estimates in one batch"); return false; }
         WeightParam noWeight = { 0, 0, 0, 0 };
         if (param.bEnableWeightedPred && j.doSearch[0])
@@ -810,6 +824,7 @@ bool CostEstimateGroup::runEstimates(const EstReq* est, int n)
             e.doSearch[0] = j.doSearch[0]; e.doSearch[1] = j.doSearch[1];
             e.usedVersion[0] = usedVersion[0]; e.usedVersion[1] = usedVersion[1];
             e.newVersion[0] = newVersion[0]; e.newVersion[1] = newVersion[1];
+            e.costStamp = costStamp;
             e.wref = noWeight; e.wdelta = 0;
             memset(&e.res, 0, sizeof(e.res));
             la.m_spec.push_back(e);
@@ -841,6 +856,7 @@ bool CostEstimateGroup::runEstimates(const EstReq* est, int n)
                 }
                 if (j.doSearch[l]) fenc->mvVersion[l][d - 1] = newVersion[l];
             }
+            fenc->costStamp[d0][d1] = costStamp;
             if (!la.m_resident)
             {
                 j.lowresCosts = fenc->lowresCosts[d0][d1];
@@ -854,6 +870,8 @@ bool CostEstimateGroup::runEstimates(const EstReq* est, int n)
         specOf.push_back(specIdx);
     }
     if (jobs.empty()) return true;
+    /* queued cuTree steps read the mirrors as they are now: they go first (same stream, no wait) */
+    if (!la.m_ctOps.empty() && !la.cuTreeRun(NULL, 0)) return false;
 
     /* second half of weightsAnalyse (slicetype.cpp:432-487): the two SATD sweeps run on the GPU */
     if (!witems.empty())
@@ -918,7 +936,124 @@ bool CostEstimateGroup::runEstimates(const EstReq* est, int n)
     return true;
 }
 
+/* ================================================================================================
+ * cuTree propagation
+ * ============================================================================================== */
+static inline double clipDuration(double f) { return f < 0.01 ? 0.01 : (f > 1.00 ? 1.00 : f); }   /* CLIP_DURATION, ratecontrol.h:47 */
+
+/* memset(frames[x]->propagateCost, 0, m_cuCount * sizeof(uint16_t)), slicetype.cpp:1668-1701 */
+void Lookahead::cuTreeZero(Lowres& f)
+{
+    x265cu_cutree_op op;
+    memset(&op, 0, sizeof(op));
+    op.kind = X265CU_CT_ZERO;
+    op.fenc = f.slot;
+    m_ctOps.push_back(op);
+    memset(f.propagateCost, 0, (size_t)m_cuCount * sizeof(uint16_t));
+    f.propagateStale = false;       /* host and (once the queue ran) device agree: all zero */
+}
+
+/* Lookahead::estimateCUPropagate, slicetype.cpp:1741-1839 (the VBV-only cuTreeFinish at its end is the caller's) */
+bool Lookahead::estimateCUPropagate(Lowres** frames, double averageDuration, int p0, int p1, int b, int referenced)
+{
+    Lowres *fenc = frames[b], *ref0 = frames[p0], *ref1 = frames[p1];
+    const int d0 = b - p0, d1 = p1 - b;
+    if (!fenc || !ref0 || !ref1 || d0 < 1 || d1 < 0 || d0 > m_param.bframes + 1 || d1 > m_param.bframes + 1)
+    {
+        snprintf(m_error, sizeof(m_error), "estimateCUPropagate: bad frames (%d, %d, %d)", p0, b, p1);
+        return false;
+    }
+    if (!fenc->invQscaleFactor) { snprintf(m_error, sizeof(m_error), "estimateCUPropagate: cuTree needs the AQ arrays (aq-mode 0)"); return false; }
+    /* the kernel reads the device mirrors of lowresCosts[d0][d1] and of the MV fields: they must be the official
+     * arrays (an estimate computed ahead and never asked for may have overwritten a mirror) */
+    struct { bool stale; int which, a, b; const void* host; } need[3] = {
+        { fenc->costStamp[d0][d1] != fenc->devCostStamp[d0][d1], 4, d0, d1, fenc->lowresCosts[d0][d1] },
+        { fenc->mvVersion[0][d0 - 1] != fenc->devMvVersion[0][d0 - 1], 6, 0, d0, fenc->lowresMvs[0][d0 - 1] },
+        { d1 > 0 && fenc->mvVersion[1][d1 - 1] != fenc->devMvVersion[1][d1 - 1], 6, 1, d1, d1 > 0 ? fenc->lowresMvs[1][d1 - 1] : NULL } };
+    for (int i = 0; i < 3; i++)
+    {
+        if (!need[i].stale) continue;
+        /* resident mode has no host copy: the mirror is all there is (the estimate handed out from the look-ahead
+         * cache then also only exists as that mirror); counted, reported by the bench, expected to stay 0 */
+        if (m_resident) { m_ctStats[2]++; continue; }
+        if (!cuTreeRun(NULL, 0)) return false;     /* queued steps read the mirror as it is now */
+        if (x265cu_frame_set_array(m_ctx, fenc->slot, need[i].which, need[i].a, need[i].b, need[i].host))
+        {
+            snprintf(m_error, sizeof(m_error), "x265cu_frame_set_array: %s", x265cu_last_error(m_ctx));
+            return false;
+        }
+        if (i == 0) fenc->devCostStamp[d0][d1] = fenc->costStamp[d0][d1];
+        else fenc->devMvVersion[need[i].a][need[i].b - 1] = fenc->mvVersion[need[i].a][need[i].b - 1];
+        m_ctStats[2]++;
+    }
+    x265cu_cutree_op op;
+    memset(&op, 0, sizeof(op));
+    op.kind = X265CU_CT_PROPAGATE;
+    op.fenc = fenc->slot; op.ref0 = ref0->slot; op.ref1 = ref1->slot;
+    op.d0 = d0; op.d1 = d1;
+    op.referenced = referenced;
+    const int distScaleFactor = ((d0 << 8) + ((p1 - p0) >> 1)) / (p1 - p0);
+    op.bipredWeight = m_param.bEnableWeightedBiPred ? 64 - (distScaleFactor >> 2) : 32;
+    op.fpsFactor = clipDuration((double)m_param.fpsDenom / m_param.fpsNum) / clipDuration(averageDuration);
+    m_ctOps.push_back(op);
+    ref0->propagateStale = true;
+    if (d1 > 0) ref1->propagateStale = true;
+    if (!referenced) fenc->propagateStale = true;     /* its first row is zeroed by the step */
+    m_ctStats[0]++;
+    return true;
+}
+
+/* run the queued steps in one launch; fetch[] = frames whose propagateCost the host wants now */
+bool Lookahead::cuTreeRun(Lowres** fetch, int nFetch)
+{
+    std::vector<int> slots;
+    std::vector<uint16_t*> outs;
+    for (int i = 0; i < nFetch; i++)
+        if (fetch[i]->propagateStale && !m_resident) { slots.push_back(fetch[i]->slot); outs.push_back(fetch[i]->propagateCost); }
+    /* resident mode: the arrays stay in HBM; one frame's worth still comes back per fetch so that the host waits for
+     * the device exactly where the reference's caller needs the result */
+    if (m_resident && nFetch) { slots.push_back(fetch[0]->slot); outs.push_back(fetch[0]->propagateCost); }
+    if (m_ctOps.empty() && slots.empty()) return true;
+    int r = x265cu_cutree_run(m_ctx, (int)m_ctOps.size(), m_ctOps.empty() ? NULL : &m_ctOps[0], (int)slots.size(),
+                              slots.empty() ? NULL : &slots[0], outs.empty() ? NULL : &outs[0]);
+    m_ctOps.clear();
+    if (r) { snprintf(m_error, sizeof(m_error), "x265cu_cutree_run: %s", x265cu_last_error(m_ctx)); return false; }
+    for (int i = 0; i < nFetch; i++) fetch[i]->propagateStale = false;
+    m_ctStats[1]++;
+    return true;
+}
+
+const uint16_t* Lookahead::propagateCost(Lowres& f)
+{
+    Lowres* p = &f;
+    if ((f.propagateStale || !m_ctOps.empty()) && !cuTreeRun(&p, 1)) return NULL;
+    return f.propagateCost;
+}
+
+/* Lookahead::cuTreeFinish, slicetype.cpp:1844-1862: float mapping on the host (compiled like the reference) */
+bool Lookahead::cuTreeFinish(Lowres* frame, double averageDuration, int ref0Distance)
+{
+    if (!cuTreeRun(&frame, 1)) return false;
+    if (m_resident) return true;         /* intraCost / qpAqOffset are not on the host in resident mode */
+    int fpsFactor = (int)(clipDuration(averageDuration) / clipDuration((double)m_param.fpsDenom / m_param.fpsNum) * 256);
+    double weightdelta = 0.0;
+    if (ref0Distance && frame->weightedCostDelta[ref0Distance - 1] > 0)
+        weightdelta = (1.0 - frame->weightedCostDelta[ref0Distance - 1]);
+    for (int cuIndex = 0; cuIndex < m_cuCount; cuIndex++)
+    {
+        int intracost = (frame->intraCost[cuIndex] * frame->invQscaleFactor[cuIndex] + 128) >> 8;
+        if (intracost)
+        {
+            int propagateCost = (frame->propagateCost[cuIndex] * fpsFactor + 128) >> 8;
+            double log2_ratio = log2((double)(intracost + propagateCost)) - log2((double)intracost) + weightdelta;
+            frame->qpCuTreeOffset[cuIndex] = frame->qpAqOffset[cuIndex] - m_cuTreeStrength * log2_ratio;
+        }
+    }
+    return true;
+}
+
 } // namespace x265cu
+
 
 /* ================================================================================================
  * flat C view
@@ -933,6 +1068,7 @@ void* x265cuh_open(const x265cuh_params* p, char* err, int errLen)
     memset(&q, 0, sizeof(q));
     q.sourceWidth = p->sourceWidth; q.sourceHeight = p->sourceHeight; q.bitDepth = p->bitDepth; q.maxCUSize = p->maxCUSize;
     q.bframes = p->bframes; q.lookaheadDepth = p->lookaheadDepth; q.lookaheadSlices = p->lookaheadSlices; q.poolWorkers = p->poolWorkers;
+    q.fpsNum = p->fpsNum; q.fpsDenom = p->fpsDenom; q.qCompress = p->qCompress; q.bEnableWeightedBiPred = p->bEnableWeightedBiPred;
     q.bEnableWeightedPred = p->bEnableWeightedPred; q.aqMode = p->aqMode; q.aqStrength = p->aqStrength;
     q.bFrameBias = p->bFrameBias; q.device = p->device; q.frameSlots = p->frameSlots;
     q.stream = p->stream; q.searchWarps = p->searchWarps;
@@ -1023,9 +1159,24 @@ const void* x265cuh_array(void* h, void* frame, int which, int d0, int d1, size_
     case 5: *bytes = (size_t)la->m_8x8Height * 4; return l->rowSatds[d0][d1];
     case 6: *bytes = n * 4; return l->lowresMvs[d0][d1 - 1];
     case 7: *bytes = n * 4; return l->lowresMvCosts[d0][d1 - 1];
+    case 8: *bytes = d0 ? (size_t)la->m_8x8Width * 2 : n * 2; return la->propagateCost(*l);
+    case 9: *bytes = l->qpCuTreeOffset ? n * 8 : 0; return l->qpCuTreeOffset;
+    case 10: *bytes = l->qpAqOffset ? n * 8 : 0; return l->qpAqOffset;
     default: *bytes = 0; return NULL;
     }
 }
+
+void x265cuh_cutree_zero(void* la, void* frame) { ((Lookahead*)la)->cuTreeZero(*(Lowres*)frame); }
+int x265cuh_cutree_propagate(void* la, void** frames, int nframes, int p0, int p1, int b, int referenced, double averageDuration)
+{
+    if (p0 < 0 || p1 >= nframes || b < p0 || b > p1) return -1;
+    return ((Lookahead*)la)->estimateCUPropagate((Lowres**)frames, averageDuration, p0, p1, b, referenced) ? 0 : -1;
+}
+int x265cuh_cutree_finish(void* la, void* frame, double averageDuration, int ref0Distance)
+{
+    return ((Lookahead*)la)->cuTreeFinish((Lowres*)frame, averageDuration, ref0Distance) ? 0 : -1;
+}
+void x265cuh_cutree_stats(void* la, int64_t* o) { for (int i = 0; i < 3; i++) o[i] = ((Lookahead*)la)->m_ctStats[i]; }
 
 void x265cuh_frame_scalars(void* frame, int d0, int d1, int64_t* o)
 {

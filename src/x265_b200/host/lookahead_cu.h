@@ -8,12 +8,15 @@
  *   ::calcAdaptiveQuantFrame()  <-> LookaheadTLD::calcAdaptiveQuantFrame  slicetype.cpp:95-228
  *   ::weightsAnalyse()          <-> LookaheadTLD::weightsAnalyse   slicetype.cpp:391-488
  *   x265cu::CostEstimateGroup   <-> class CostEstimateGroup        encoder/slicetype.h:199-240
+ *   ::cuTreeZero/estimateCUPropagate/cuTreeFinish <-> the memsets of Lookahead::cuTree (slicetype.cpp:1668-1701),
+ *                                   Lookahead::estimateCUPropagate (:1741-1839), Lookahead::cuTreeFinish (:1844-1862)
  *
  * Everything integer and data-parallel runs on the GPU through the C ABI; the small float decisions
  * (AQ strength mapping, weight guesses, mvcost table) stay here on the host, compiled with the
  * reference's flags (-ffast-math) because the bitstream depends on them.
- * The slice-type decision, scenecut, cuTree and VBV logic of x265 are consumers of this layer and
- * are NOT re-implemented (out of scope: they stay x265's own code).
+ * The slice-type decision, scenecut, the control flow of cuTree and the VBV logic of x265 are consumers of this
+ * layer and are NOT re-implemented (out of scope: they stay x265's own code); of cuTree, the
+ * per-CU propagation runs on the GPU, its log2 mapping to QP offsets stays on the host.
  */
 #ifndef X265CU_LOOKAHEAD_CU_H
 #define X265CU_LOOKAHEAD_CU_H
@@ -49,6 +52,10 @@ struct Param
     int frameSlots;          /* 0 = lookaheadDepth + bframes + 8 */
     void* stream;            /* cudaStream_t to run on (NULL: own stream) */
     int searchWarps;         /* 0 = default */
+    /* cuTree (0 = the x265 defaults: 30/1 fps, qcomp 0.6) */
+    int fpsNum, fpsDenom;
+    double qCompress;        /* rc.qCompress: m_cuTreeStrength = 5 * (1 - qCompress), slicetype.cpp:511 */
+    int bEnableWeightedBiPred;
 };
 
 struct WeightParam { int present, scale, denom, offset; };
@@ -81,12 +88,18 @@ struct Lowres
     uint64_t frameVariance;
     double weightedCostDelta[BFRAME_MAX + 2];
     WeightParam weightedRef[BFRAME_MAX + 2];   /* reference keeps ReferencePlanes here; we keep the weight */
+    uint16_t* propagateCost; /* cuTree; on the host only as far as it was fetched (Lookahead::propagateCost()) */
     uint8_t* arena;          /* one pinned allocation holding every array above */
     size_t arenaBytes;
     /* bookkeeping of the look-ahead estimate cache (Lookahead::m_spec): the frame went through preLookahead();
      * which search produced lowresMvs[l][d] (0: none yet) */
     bool ready;
     uint64_t mvVersion[2][BFRAME_MAX + 1];
+    /* which computation last wrote the DEVICE mirror of lowresMvs[l][d] / lowresCosts[d0][d1], and which one the
+     * official (host) lowresCosts[d0][d1] came from: cuTree reads the mirrors and must read the official arrays */
+    uint64_t devMvVersion[2][BFRAME_MAX + 1];
+    uint64_t costStamp[BFRAME_MAX + 2][BFRAME_MAX + 2], devCostStamp[BFRAME_MAX + 2][BFRAME_MAX + 2];
+    bool propagateStale;     /* the device holds a newer propagateCost than the host array */
 };
 
 /* One estimate computed AHEAD of its request (see CostEstimateGroup::singleCost).  The reference asks for
@@ -103,6 +116,7 @@ struct SpecEstimate
     int doSearch[2];
     uint64_t usedVersion[2];             /* version of lowresMvs[l][d] consumed (lists not searched by this estimate) */
     uint64_t newVersion[2];              /* version of the fields this estimate's searches produced */
+    uint64_t costStamp;                  /* id of this computation (Lowres::costStamp) */
     x265cu_job_result res;
     WeightParam wref;
     double wdelta;
@@ -159,6 +173,20 @@ public:
     struct PictureIn { const void* y; intptr_t yStride; const void* u; const void* v; intptr_t cStride; int poc; };
     bool preLookaheadBatch(int n, Lowres** frames, const PictureIn* pics, bool copyPlanesBack);
 
+    /* ---- cuTree propagation.  The three calls replace, one to one, what Lookahead::cuTree does
+     * to Lowres::propagateCost: its memsets (slicetype.cpp:1668-1701), estimateCUPropagate (:1741-1839) and
+     * cuTreeFinish (:1844-1862).  Zero and propagate steps are only QUEUED (they run on the device in one launch
+     * per run of steps, in order); cuTreeFinish and propagateCost() run the queue and fetch what they read. */
+    std::vector<x265cu_cutree_op> m_ctOps;
+    std::vector<Lowres*> m_ctTouched;
+    double m_cuTreeStrength;
+    int64_t m_ctStats[3];                   /* propagate steps, launches (queue runs), mirrors re-uploaded */
+    void cuTreeZero(Lowres& f);
+    bool estimateCUPropagate(Lowres** frames, double averageDuration, int p0, int p1, int b, int referenced);
+    bool cuTreeFinish(Lowres* frame, double averageDuration, int ref0Distance);
+    bool cuTreeRun(Lowres** fetch, int nFetch);
+    const uint16_t* propagateCost(Lowres& f);   /* the host copy, fetched if the device is ahead */
+
     int64_t ncu() const { return m_8x8Blocks; }
     static void mvcostTable(int bitDepth, uint16_t* out131073, int* lambdaInt);
 };
@@ -199,6 +227,9 @@ typedef struct x265cuh_params
     int bFrameBias, device, frameSlots;
     void* stream;
     int searchWarps;
+    int fpsNum, fpsDenom;
+    double qCompress;
+    int bEnableWeightedBiPred;
 } x265cuh_params;
 void* x265cuh_open(const x265cuh_params* p, char* err, int errLen);
 void  x265cuh_close(void* la);
@@ -215,8 +246,14 @@ int   x265cuh_pre_lookahead_batch(void* la, int n, void** frames, const void* co
                                   const intptr_t* cs, const int* pocs, int planesBack);
 /* jobs: n triples (p0, p1, b) as indices into frames[]; batch != 0 -> add()+finishBatch(), else singleCost() each */
 int   x265cuh_estimate(void* la, void** frames, int nframes, const int* triples, int n, int batch, int64_t* scores);
+/* cuTree: the three calls of x265cu::Lookahead (frames[] indexed like the reference's: p0, p1, b) */
+void  x265cuh_cutree_zero(void* la, void* frame);
+int   x265cuh_cutree_propagate(void* la, void** frames, int nframes, int p0, int p1, int b, int referenced, double averageDuration);
+int   x265cuh_cutree_finish(void* la, void* frame, double averageDuration, int ref0Distance);
+void  x265cuh_cutree_stats(void* la, int64_t* out3);
 /* array accessors for checks: which = 0 planes, 1 intraCost, 2 intraMode, 3 invQscale, 4 lowresCosts[d0][d1],
- * 5 rowSatds[d0][d1], 6 lowresMvs[list=d0][d1-1], 7 lowresMvCosts[list=d0][d1-1]; returns pointer and byte size */
+ * 5 rowSatds[d0][d1], 6 lowresMvs[list=d0][d1-1], 7 lowresMvCosts[list=d0][d1-1], 8 propagateCost (fetched from the
+ * device if it is ahead; d0 != 0: only the first CU row), 9 qpCuTreeOffset, 10 qpAqOffset; returns pointer and byte size */
 const void* x265cuh_array(void* la, void* frame, int which, int d0, int d1, size_t* bytes);
 void  x265cuh_frame_scalars(void* frame, int d0, int d1, int64_t* out9);  /* costEst, costEstAq, intraMbs[d0], wp_ssd0, wp_sum0, weighted, scale, denom, offset */
 uint32_t x265cuh_crc32(const void* p, size_t n);

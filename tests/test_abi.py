@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(built):
     L = abi.lib_cu()
     for name in header_functions():
         assert hasattr(L, name), name
-    assert L.x265cu_abi_version() == 1
+    assert L.x265cu_abi_version() == 2
 
 
 def test_no_torch_or_cxx_types_in_signatures():
