@@ -882,6 +882,7 @@ int x265cu_cutree_run(x265cu_ctx* c, int n, const x265cu_cutree_op* ops, int nOu
             }
             if (a.nOps == CUTREE_MAX_OPS || i == n + nOut - 1)
             {
+                cutree_mark_phases(a.ops, a.nOps);
                 CU_TRY(c, cudaLaunchKernelEx(&lc, cutree_kernel, a));
                 c->stats.launches[X265CU_K_CUTREE]++;
                 a.nOps = 0;

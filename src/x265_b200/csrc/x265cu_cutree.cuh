@@ -9,7 +9,9 @@
  * scatters into the propagateCost of b's references.  One launch runs the whole chain: a thread-block cluster of
  * CUTREE_CTAS CTAs (8, the portable maximum), every step spread over all of its threads, the hardware cluster
  * barrier between steps (no grid-wide software barrier, no launch per step: a step is only nCU = 8160 / 32400
- * small work items, i.e. launch-latency bound on its own).
+ * small work items, i.e. launch-latency bound on its own).  Steps that do not depend on each other share a PHASE
+ * (no barrier between them): zeroing frames nobody is touching, and propagate steps that only ADD into common
+ * frames (adds commute); the host marks the phase ends (cutree_mark_phases below).
  *
  * Exactness.
  *  - The propagate amount uses double arithmetic in the reference.  Its object code performs, per CU,
@@ -27,7 +29,7 @@
 
 #define CUTREE_CTAS 8
 #define CUTREE_THREADS 1024
-#define CUTREE_MAX_OPS 80
+#define CUTREE_MAX_OPS 64      /* keeps the kernel parameter block under 4 KB */
 
 enum { CT_OP_ZERO = 0, CT_OP_PROPAGATE = 1, CT_OP_PACK = 2 };
 
@@ -40,6 +42,7 @@ struct CutreeOpDev
     int referenced;
     int bipredWeight;           /* bipredWeights[0]; [1] = 64 - it */
     int outIndex;               /* PACK: which staging area */
+    int barrierAfter;           /* the next op depends on this phase: cluster barrier before it */
     double fps;                 /* fpsFactor / 256 (exact: power of two) */
 };
 
@@ -157,10 +160,52 @@ __global__ void __launch_bounds__(CUTREE_THREADS, 1) cutree_kernel(const __grid_
             if (!op.referenced)
                 for (int cu = tid; cu < wCU; cu += nThreads) __stcg(own + cu, 0ull);
         }
-        /* the next step reads what this one accumulated: make the atomics/stores visible cluster-wide */
-        __threadfence();
-        cluster.sync();
+        /* the next step reads (or must be ordered after) what this phase accumulated: make the atomics/stores
+         * visible cluster-wide.  barrierAfter is uniform over the cluster (kernel parameter). */
+        if (op.barrierAfter)
+        {
+            __threadfence();
+            cluster.sync();
+        }
     }
+}
+
+/* Host side: which ops may share a phase.  Per op, the frame arrays it READS, ADDS into (atomic, commutative) and
+ * WRITES (plain stores).  Op k+1 joins the phase of op k unless it reads or writes an array the phase adds into or
+ * writes, or adds into / writes an array the phase reads or writes (two ops adding into the same array are fine). */
+static inline void cutree_mark_phases(CutreeOpDev* ops, int n)
+{
+    enum { R = 1, A = 2, W = 4 };
+    struct Use { int slot, how; };
+    Use phase[4 * CUTREE_MAX_OPS];
+    int nPhase = 0;
+    for (int k = 0; k < n; k++)
+    {
+        Use u[3];
+        int nu = 0;
+        const CutreeOpDev& o = ops[k];
+        if (o.kind == CT_OP_ZERO) { u[nu].slot = o.fenc; u[nu++].how = W; }
+        else if (o.kind == CT_OP_PACK) { u[nu].slot = o.fenc; u[nu++].how = R; }
+        else
+        {
+            u[nu].slot = o.fenc; u[nu++].how = o.referenced ? R : W;      /* non-referenced: its first row is zeroed */
+            u[nu].slot = o.ref0; u[nu++].how = A;
+            if (o.mvOfs1 >= 0) { u[nu].slot = o.ref1; u[nu++].how = A; }
+        }
+        bool conflict = false;
+        for (int i = 0; i < nu && !conflict; i++)
+            for (int j = 0; j < nPhase && !conflict; j++)
+                if (phase[j].slot == u[i].slot && !(phase[j].how == A && u[i].how == A) && !(phase[j].how == R && u[i].how == R))
+                    conflict = true;
+        if (conflict)
+        {
+            ops[k - 1].barrierAfter = 1;
+            nPhase = 0;
+        }
+        for (int i = 0; i < nu; i++) phase[nPhase++] = u[i];
+        ops[k].barrierAfter = 0;
+    }
+    if (n) ops[n - 1].barrierAfter = 1;    /* the launch ends a phase (kernel boundary orders the rest) */
 }
 
 #endif /* X265CU_CUTREE_CUH */

@@ -152,7 +152,7 @@ def test_propagate_adversarial(mods, depth):
 
 
 def test_long_op_list_spans_launches(mods):
-    """more ops than one launch holds (CUTREE_MAX_OPS = 80): the list continues in the next launch, in order"""
+    """more ops than one launch holds (CUTREE_MAX_OPS = 64): the list continues in the next launch, in order"""
     po, abi = mods
     rig = Rig(po, abi, 8, 352, 208, 3, 5, 5)
     try:
