@@ -61,6 +61,7 @@ struct x265cu_ctx
     int* dMvs;
     int* dMvCosts;
     unsigned long long* dPropagate;        /* [slot][nCU] Lowres::propagateCost accumulators (x265cu_cutree.cuh) */
+    int cutreeCtas;                        /* grid of the cooperative cuTree kernel (one CTA per SM) */
     uint16_t* dPropOut; size_t dPropOutCap; /* clamped uint16 copies on their way to the host */
     uint16_t* hPropOut; size_t hPropOutCap;
     uint16_t* dLut;        /* base; centre at +65536 */
@@ -278,6 +279,7 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     c->dMvs = NULL; c->dMvCosts = NULL; c->dLut = NULL; c->dSrc = NULL; c->dSmall = NULL;
     c->dStage = NULL; c->dStageCap = 0; c->hStage = NULL; c->hStageCap = 0; c->dArgs = NULL; c->dArgsCap = 0; c->hArgs = NULL; c->hArgsCap = 0; c->hPre = NULL; c->hPreCap = 0; c->dPre = NULL; c->dPreCap = 0; c->dSrcLin = NULL; c->dSrcLinCap = 0; c->dUp = NULL; c->dUpCap = 0; c->upStream = NULL;
     c->dGeneric = NULL; c->dGenericCap = 0; c->dMemo = NULL; c->dMemoCap = 0;
+    c->cutreeCtas = 0;
     c->dPropagate = NULL; c->dPropOut = NULL; c->dPropOutCap = 0; c->hPropOut = NULL; c->hPropOutCap = 0;
     c->timing = false;
     memset(&c->stats, 0, sizeof(c->stats));
@@ -844,12 +846,22 @@ int x265cu_cutree_run(x265cu_ctx* c, int n, const x265cu_cutree_op* ops, int nOu
     a.acc = c->dPropagate; a.out = c->dPropOut;
     a.nOps = 0;
 
+    /* cooperative launch: one CTA per SM, all co-resident (grid barrier between the phases) */
+    if (c->cutreeCtas <= 0)
+    {
+        int sms = 0, perSm = 0;
+        CU_TRY(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->cfg.device));
+        CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, cutree_kernel, CUTREE_THREADS, 0));
+        if (sms < 1 || perSm < 1) return fail(c, X265CU_ECUDA, "x265cu_cutree_run: the cuTree kernel does not fit an SM");
+        c->cutreeCtas = sms;
+        if (const char* e = getenv("X265CU_CUTREE_CTAS")) { int v = atoi(e); if (v >= 1 && v <= sms * perSm) c->cutreeCtas = v; }
+    }
     cudaLaunchConfig_t lc;
     memset(&lc, 0, sizeof(lc));
-    lc.gridDim = dim3(CUTREE_CTAS); lc.blockDim = dim3(CUTREE_THREADS); lc.dynamicSmemBytes = 0; lc.stream = c->stream;
+    lc.gridDim = dim3(c->cutreeCtas); lc.blockDim = dim3(CUTREE_THREADS); lc.dynamicSmemBytes = 0; lc.stream = c->stream;
     cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CUTREE_CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
     lc.attrs = attr; lc.numAttrs = 1;
 
     {
@@ -882,7 +894,7 @@ int x265cu_cutree_run(x265cu_ctx* c, int n, const x265cu_cutree_op* ops, int nOu
             }
             if (a.nOps == CUTREE_MAX_OPS || i == n + nOut - 1)
             {
-                cutree_mark_phases(a.ops, a.nOps);
+                cutree_schedule(a.ops, a.nOps);
                 CU_TRY(c, cudaLaunchKernelEx(&lc, cutree_kernel, a));
                 c->stats.launches[X265CU_K_CUTREE]++;
                 a.nOps = 0;

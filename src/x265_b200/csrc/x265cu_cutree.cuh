@@ -6,12 +6,17 @@
  * lowresCosts[d0][d1], lowresMvs[l][d]); nothing is uploaded for it.
  *
  * A cuTree pass is a CHAIN of steps: step k reads the propagateCost of frame b that steps < k accumulated and
- * scatters into the propagateCost of b's references.  One launch runs the whole chain: a thread-block cluster of
- * CUTREE_CTAS CTAs (8, the portable maximum), every step spread over all of its threads, the hardware cluster
- * barrier between steps (no grid-wide software barrier, no launch per step: a step is only nCU = 8160 / 32400
- * small work items, i.e. launch-latency bound on its own).  Steps that do not depend on each other share a PHASE
- * (no barrier between them): zeroing frames nobody is touching, and propagate steps that only ADD into common
- * frames (adds commute); the host marks the phase ends (cutree_mark_phases below).
+ * scatters into the propagateCost of b's references; a step is only nCU = 8160 / 32400 small work items, so on its
+ * own it is launch-latency bound.  One COOPERATIVE launch (one CTA per SM) runs a whole pass:
+ *  - the host schedules the steps into PHASES of mutually independent steps (cutree_schedule below: zeroing first,
+ *    then every non-referenced B frame, then the serial chain through the reference frames: about k + 2 phases for
+ *    k mini-GOPs instead of 6k steps);
+ *  - the CUs of all steps of a phase are one pool of work items spread over the whole grid;
+ *  - a grid barrier separates the phases.
+ * Measured on c1_1080p (16 passes of up to 60 steps per 60 frames): a launch per pass on an 8-CTA cluster with the
+ * hardware cluster barrier between steps took 1.75 ms per 60 frames whatever the number of barriers -- it was bound
+ * by the instruction throughput of its 8 SMs (about 250 instructions per CU: the double division, the index
+ * division, eight predicated atomics); hence the whole-GPU grid.
  *
  * Exactness.
  *  - The propagate amount uses double arithmetic in the reference.  Its object code performs, per CU,
@@ -27,8 +32,7 @@
 
 #include <cooperative_groups.h>
 
-#define CUTREE_CTAS 8
-#define CUTREE_THREADS 1024
+#define CUTREE_THREADS 512
 #define CUTREE_MAX_OPS 64      /* keeps the kernel parameter block under 4 KB */
 
 enum { CT_OP_ZERO = 0, CT_OP_PROPAGATE = 1, CT_OP_PACK = 2 };
@@ -76,136 +80,170 @@ __device__ __forceinline__ int cutree_amount(int intra, int interRaw, int invQ, 
     return (r >= -2147483648.0 && r < 2147483648.0) ? __double2int_rz(r) : (int)0x80000000;
 }
 
+__device__ __forceinline__ void cutree_prefetch_l2(const void* p)
+{
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+}
+
 __device__ __forceinline__ void cutree_clip_add(unsigned long long* cell, int x)
 {
     if (x <= 0) return;                               /* adding 0 changes nothing; negatives cannot occur for legal inputs */
     atomicAdd(cell, (unsigned long long)(x < 65535 ? x : 65535));
 }
 
-__global__ void __launch_bounds__(CUTREE_THREADS, 1) cutree_kernel(const __grid_constant__ CutreeArgs a)
+/* one work item = one CU of one op */
+__device__ __forceinline__ void cutree_item(const CutreeArgs& a, const CutreeOpDev& op, int cu)
 {
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    const int tid = blockIdx.x * CUTREE_THREADS + threadIdx.x;
-    const int nThreads = gridDim.x * CUTREE_THREADS;
     const int wCU = a.wCU, hCU = a.hCU, nCU = a.nCU;
-
-    for (int k = 0; k < a.nOps; k++)
+    unsigned long long* own = a.acc + (size_t)op.fenc * nCU;
+    if (op.kind == CT_OP_ZERO)
     {
-        const CutreeOpDev& op = a.ops[k];
-        unsigned long long* own = a.acc + (size_t)op.fenc * nCU;
-        if (op.kind == CT_OP_ZERO)
-        {
-            for (int cu = tid; cu < nCU; cu += nThreads) __stcg(own + cu, 0ull);
-        }
-        else if (op.kind == CT_OP_PACK)
-        {
-            uint16_t* o = a.out + (size_t)op.outIndex * nCU;
-            for (int cu = tid; cu < nCU; cu += nThreads)
-            {
-                const unsigned long long v = __ldcg(own + cu);
-                o[cu] = (uint16_t)(v < 65535ull ? v : 65535ull);
-            }
-        }
-        else
-        {
-            const int* intraCost = a.intraCost + (size_t)op.fenc * nCU;
-            const int* invQ = a.invQ + (size_t)op.fenc * nCU;
-            const uint16_t* costs = a.lowresCosts + ((size_t)op.fenc * a.costTables + op.costOfs) * nCU;
-            unsigned long long* refAcc[2] = { a.acc + (size_t)op.ref0 * nCU, a.acc + (size_t)op.ref1 * nCU };
-            const int* mvField[2] = { op.mvOfs0 >= 0 ? a.mvs + ((size_t)op.fenc * a.mvFields + op.mvOfs0) * nCU : NULL,
-                                      op.mvOfs1 >= 0 ? a.mvs + ((size_t)op.fenc * a.mvFields + op.mvOfs1) * nCU : NULL };
-            const int bw[2] = { op.bipredWeight, 64 - op.bipredWeight };
-            for (int cu = tid; cu < nCU; cu += nThreads)
-            {
-                unsigned in = 0;
-                if (op.referenced)
-                {
-                    const unsigned long long v = __ldcg(own + cu);
-                    in = (unsigned)(v < 65535ull ? v : 65535ull);
-                }
-                const int cost = costs[cu];
-                const int amount = cutree_amount(intraCost[cu], cost, invQ[cu], in, op.fps);
-                if (amount <= 0) continue;            /* "don't propagate for an intra block" */
-                const int listsUsed = cost >> 14;
-                const int blocky = cu / wCU, blockx = cu - blocky * wCU;
+        __stcg(own + cu, 0ull);
+        return;
+    }
+    if (op.kind == CT_OP_PACK)
+    {
+        const unsigned long long v = __ldcg(own + cu);
+        a.out[(size_t)op.outIndex * nCU + cu] = (uint16_t)(v < 65535ull ? v : 65535ull);
+        return;
+    }
+    const size_t f = (size_t)op.fenc;
+    unsigned in = 0;
+    if (op.referenced)
+    {
+        const unsigned long long v = __ldcg(own + cu);
+        in = (unsigned)(v < 65535ull ? v : 65535ull);
+    }
+    /* every load of the item is issued before anything is consumed: one L2 round trip */
+    const int cost = a.lowresCosts[(f * a.costTables + op.costOfs) * nCU + cu];
+    const int mvBoth[2] = { a.mvs[(f * a.mvFields + op.mvOfs0) * nCU + cu],
+                            op.mvOfs1 >= 0 ? a.mvs[(f * a.mvFields + op.mvOfs1) * nCU + cu] : 0 };
+    const int amount = cutree_amount(a.intraCost[f * nCU + cu], cost, a.invQ[f * nCU + cu], in, op.fps);
+    /* "for non-referred frames the source costs are always zero, so just memset one row and re-use it" (:1757): the
+     * first row of b's own array is zeroed by the step (nothing reads or adds into it in this phase) */
+    if (!op.referenced && cu < wCU) __stcg(own + cu, 0ull);
+    if (amount <= 0) return;                      /* "don't propagate for an intra block" */
+    const int listsUsed = cost >> 14;
+    const int blocky = cu / wCU, blockx = cu - blocky * wCU;
+    const int bw[2] = { op.bipredWeight, 64 - op.bipredWeight };
 #pragma unroll
-                for (int list = 0; list < 2; list++)
-                {
-                    if (!((listsUsed >> list) & 1) || !mvField[list]) continue;
-                    int listamount = amount;
-                    if (listsUsed == 3)
-                        listamount = (listamount * bw[list] + 32) >> 6;
-                    const int mv = mvField[list][cu];
-                    unsigned long long* ref = refAcc[list];
-                    if (!mv)
-                    {
-                        cutree_clip_add(ref + cu, listamount);
-                        continue;
-                    }
-                    int x = (short)(mv & 0xFFFF), y = mv >> 16;
-                    const int cux = (x >> 5) + blockx, cuy = (y >> 5) + blocky;
-                    x &= 31; y &= 31;
-                    const int idx0 = cux + cuy * wCU;
-                    const bool inX0 = cux >= 0 && cux < wCU, inX1 = cux + 1 >= 0 && cux + 1 < wCU;
-                    const bool inY0 = cuy >= 0 && cuy < hCU, inY1 = cuy + 1 >= 0 && cuy + 1 < hCU;
-                    if (inX0 && inY0) cutree_clip_add(ref + idx0, (listamount * ((32 - y) * (32 - x)) + 512) >> 10);
-                    if (inX1 && inY0) cutree_clip_add(ref + idx0 + 1, (listamount * ((32 - y) * x) + 512) >> 10);
-                    if (inX0 && inY1) cutree_clip_add(ref + idx0 + wCU, (listamount * (y * (32 - x)) + 512) >> 10);
-                    if (inX1 && inY1) cutree_clip_add(ref + idx0 + wCU + 1, (listamount * (y * x) + 512) >> 10);
-                }
-            }
-            /* "for non-referred frames the source costs are always zero, so just memset one row and re-use it" (:1757):
-             * the first row of b's own array is zeroed by the step */
-            if (!op.referenced)
-                for (int cu = tid; cu < wCU; cu += nThreads) __stcg(own + cu, 0ull);
-        }
-        /* the next step reads (or must be ordered after) what this phase accumulated: make the atomics/stores
-         * visible cluster-wide.  barrierAfter is uniform over the cluster (kernel parameter). */
-        if (op.barrierAfter)
+    for (int list = 0; list < 2; list++)
+    {
+        if (!((listsUsed >> list) & 1) || (list && op.mvOfs1 < 0)) continue;
+        int listamount = amount;
+        if (listsUsed == 3)
+            listamount = (listamount * bw[list] + 32) >> 6;
+        const int mv = mvBoth[list];
+        unsigned long long* ref = a.acc + (size_t)(list ? op.ref1 : op.ref0) * nCU;
+        if (!mv)
         {
-            __threadfence();
-            cluster.sync();
+            cutree_clip_add(ref + cu, listamount);
+            continue;
         }
+        int x = (short)(mv & 0xFFFF), y = mv >> 16;
+        const int cux = (x >> 5) + blockx, cuy = (y >> 5) + blocky;
+        x &= 31; y &= 31;
+        const int idx0 = cux + cuy * wCU;
+        const bool inX0 = cux >= 0 && cux < wCU, inX1 = cux + 1 >= 0 && cux + 1 < wCU;
+        const bool inY0 = cuy >= 0 && cuy < hCU, inY1 = cuy + 1 >= 0 && cuy + 1 < hCU;
+        if (inX0 && inY0) cutree_clip_add(ref + idx0, (listamount * ((32 - y) * (32 - x)) + 512) >> 10);
+        if (inX1 && inY0) cutree_clip_add(ref + idx0 + 1, (listamount * ((32 - y) * x) + 512) >> 10);
+        if (inX0 && inY1) cutree_clip_add(ref + idx0 + wCU, (listamount * (y * (32 - x)) + 512) >> 10);
+        if (inX1 && inY1) cutree_clip_add(ref + idx0 + wCU + 1, (listamount * (y * x) + 512) >> 10);
     }
 }
 
-/* Host side: which ops may share a phase.  Per op, the frame arrays it READS, ADDS into (atomic, commutative) and
- * WRITES (plain stores).  Op k+1 joins the phase of op k unless it reads or writes an array the phase adds into or
- * writes, or adds into / writes an array the phase reads or writes (two ops adding into the same array are fine). */
-static inline void cutree_mark_phases(CutreeOpDev* ops, int n)
+__global__ void __launch_bounds__(CUTREE_THREADS, 1) cutree_kernel(const __grid_constant__ CutreeArgs a)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const int tid = blockIdx.x * CUTREE_THREADS + threadIdx.x;
+    const int nThreads = gridDim.x * CUTREE_THREADS;
+    const int nCU = a.nCU;
+
+    /* The chain only carries the accumulators; what a step reads besides them (costs, intra costs, inverse qscales,
+     * vectors) was written by kernels long ago and sits in HBM.  Pull all of it into L2 up front, for every step of
+     * the launch at once, so that no phase of the chain waits for DRAM. */
+    for (int item = tid; item < a.nOps * nCU; item += nThreads)
+    {
+        const int k = item / nCU, cu = item - k * nCU;
+        const CutreeOpDev& op = a.ops[k];
+        if (op.kind != CT_OP_PROPAGATE || (cu & 7)) continue;      /* one prefetch per 32-byte sector of the 4-byte arrays */
+        const size_t f = (size_t)op.fenc;
+        cutree_prefetch_l2(a.lowresCosts + (f * a.costTables + op.costOfs) * nCU + cu);
+        cutree_prefetch_l2(a.intraCost + f * nCU + cu);
+        cutree_prefetch_l2(a.invQ + f * nCU + cu);
+        cutree_prefetch_l2(a.mvs + (f * a.mvFields + op.mvOfs0) * nCU + cu);
+        if (op.mvOfs1 >= 0) cutree_prefetch_l2(a.mvs + (f * a.mvFields + op.mvOfs1) * nCU + cu);
+    }
+
+    /* phases: ops [k0, k1) are independent of each other (cutree_schedule); their CUs are ONE pool of work items
+     * spread over the whole grid; the next phase reads what this one accumulated, so a grid barrier (with its
+     * fences) separates them.  Phase bounds come from the kernel parameters: uniform over the grid. */
+    for (int k0 = 0; k0 < a.nOps;)
+    {
+        int k1 = k0;
+        while (!a.ops[k1].barrierAfter) k1++;
+        k1++;
+        const int total = (k1 - k0) * nCU;
+        for (int item = tid; item < total; item += nThreads)
+        {
+            const int k = item / nCU;
+            cutree_item(a, a.ops[k0 + k], item - k * nCU);
+        }
+        k0 = k1;
+        if (k0 < a.nOps) grid.sync();
+    }
+}
+
+/* Host side: schedule the ops of one launch into PHASES.  Per op, the frame arrays it READS, ADDS into (atomic,
+ * commutative) and WRITES (plain stores).  Two ops conflict when they use a common array other than both adding
+ * into it or both reading it; conflicting ops keep their order, everything else may move.  Each op gets the level
+ * 1 + max(level of the earlier ops it conflicts with) (as-soon-as-possible schedule), ops are sorted by level
+ * (stably), one phase per level.  A cuTree pass over k mini-GOPs is then not 6k steps long but about k + 2: the
+ * zeroing comes first, the non-referenced B frames (which read no accumulator) next, and only the chain
+ * P <- P <- P ... through the reference frames stays serial. */
+static inline void cutree_schedule(CutreeOpDev* ops, int n)
 {
     enum { R = 1, A = 2, W = 4 };
     struct Use { int slot, how; };
-    Use phase[4 * CUTREE_MAX_OPS];
-    int nPhase = 0;
+    Use use[CUTREE_MAX_OPS][3];
+    int nUse[CUTREE_MAX_OPS], level[CUTREE_MAX_OPS];
     for (int k = 0; k < n; k++)
     {
-        Use u[3];
-        int nu = 0;
         const CutreeOpDev& o = ops[k];
-        if (o.kind == CT_OP_ZERO) { u[nu].slot = o.fenc; u[nu++].how = W; }
-        else if (o.kind == CT_OP_PACK) { u[nu].slot = o.fenc; u[nu++].how = R; }
+        int nu = 0;
+        if (o.kind == CT_OP_ZERO) { use[k][nu].slot = o.fenc; use[k][nu++].how = W; }
+        else if (o.kind == CT_OP_PACK) { use[k][nu].slot = o.fenc; use[k][nu++].how = R; }
         else
         {
-            u[nu].slot = o.fenc; u[nu++].how = o.referenced ? R : W;      /* non-referenced: its first row is zeroed */
-            u[nu].slot = o.ref0; u[nu++].how = A;
-            if (o.mvOfs1 >= 0) { u[nu].slot = o.ref1; u[nu++].how = A; }
+            use[k][nu].slot = o.fenc; use[k][nu++].how = o.referenced ? R : W;    /* non-referenced: its first row is zeroed */
+            use[k][nu].slot = o.ref0; use[k][nu++].how = A;
+            if (o.mvOfs1 >= 0) { use[k][nu].slot = o.ref1; use[k][nu++].how = A; }
         }
-        bool conflict = false;
-        for (int i = 0; i < nu && !conflict; i++)
-            for (int j = 0; j < nPhase && !conflict; j++)
-                if (phase[j].slot == u[i].slot && !(phase[j].how == A && u[i].how == A) && !(phase[j].how == R && u[i].how == R))
-                    conflict = true;
-        if (conflict)
+        nUse[k] = nu;
+        level[k] = 0;
+        for (int e = 0; e < k; e++)
         {
-            ops[k - 1].barrierAfter = 1;
-            nPhase = 0;
+            bool conflict = false;
+            for (int i = 0; i < nu && !conflict; i++)
+                for (int j = 0; j < nUse[e] && !conflict; j++)
+                    if (use[e][j].slot == use[k][i].slot && !(use[e][j].how == A && use[k][i].how == A) && !(use[e][j].how == R && use[k][i].how == R))
+                        conflict = true;
+            if (conflict && level[e] + 1 > level[k]) level[k] = level[e] + 1;
         }
-        for (int i = 0; i < nu; i++) phase[nPhase++] = u[i];
-        ops[k].barrierAfter = 0;
     }
-    if (n) ops[n - 1].barrierAfter = 1;    /* the launch ends a phase (kernel boundary orders the rest) */
+    CutreeOpDev sorted[CUTREE_MAX_OPS];
+    int m = 0, maxLevel = 0;
+    for (int k = 0; k < n; k++) if (level[k] > maxLevel) maxLevel = level[k];
+    for (int l = 0; l <= maxLevel; l++)
+    {
+        const int first = m;
+        for (int k = 0; k < n; k++)
+            if (level[k] == l) { sorted[m] = ops[k]; sorted[m].barrierAfter = 0; m++; }
+        if (m > first) sorted[m - 1].barrierAfter = 1;
+    }
+    for (int k = 0; k < n; k++) ops[k] = sorted[k];
 }
 
 #endif /* X265CU_CUTREE_CUH */

@@ -211,6 +211,9 @@ void Lookahead::forgetFrame(Lowres* l)
         if (m_spec[i].fenc == l || m_spec[i].ref0 == l || m_spec[i].ref1 == l) { m_spec[i] = m_spec.back(); m_spec.pop_back(); }
         else i++;
     l->ready = false;
+    for (size_t i = 0; i < m_ctTouched.size();)
+        if (m_ctTouched[i] == l) { m_ctTouched[i] = m_ctTouched.back(); m_ctTouched.pop_back(); }
+        else i++;
 }
 
 void Lookahead::freeLowres(Lowres* l)
@@ -996,29 +999,43 @@ bool Lookahead::estimateCUPropagate(Lowres** frames, double averageDuration, int
     op.bipredWeight = m_param.bEnableWeightedBiPred ? 64 - (distScaleFactor >> 2) : 32;
     op.fpsFactor = clipDuration((double)m_param.fpsDenom / m_param.fpsNum) / clipDuration(averageDuration);
     m_ctOps.push_back(op);
-    ref0->propagateStale = true;
-    if (d1 > 0) ref1->propagateStale = true;
-    if (!referenced) fenc->propagateStale = true;     /* its first row is zeroed by the step */
+    ref0->propagateStale = true; m_ctTouched.push_back(ref0);
+    if (d1 > 0) { ref1->propagateStale = true; m_ctTouched.push_back(ref1); }
+    if (!referenced) { fenc->propagateStale = true; m_ctTouched.push_back(fenc); }    /* its first row is zeroed by the step */
     m_ctStats[0]++;
     return true;
 }
 
-/* run the queued steps in one launch; fetch[] = frames whose propagateCost the host wants now */
+/* run the queued steps in one launch.  nFetch != 0: the host wants fetch[0]'s propagateCost now -- every array the
+ * pass touched comes back with it (a few 16 KB arrays in the same copy), so that the Lowres arrays are complete
+ * after a cuTreeFinish and the pass's second cuTreeFinish (b-pyramid middle frame) needs no launch of its own. */
 bool Lookahead::cuTreeRun(Lowres** fetch, int nFetch)
 {
     std::vector<int> slots;
     std::vector<uint16_t*> outs;
-    for (int i = 0; i < nFetch; i++)
-        if (fetch[i]->propagateStale && !m_resident) { slots.push_back(fetch[i]->slot); outs.push_back(fetch[i]->propagateCost); }
-    /* resident mode: the arrays stay in HBM; one frame's worth still comes back per fetch so that the host waits for
-     * the device exactly where the reference's caller needs the result */
-    if (m_resident && nFetch) { slots.push_back(fetch[0]->slot); outs.push_back(fetch[0]->propagateCost); }
+    std::vector<Lowres*> got;
+    if (nFetch)
+    {
+        for (int i = 0; i < nFetch; i++) m_ctTouched.push_back(fetch[i]);
+        for (size_t i = 0; i < m_ctTouched.size(); i++)
+        {
+            Lowres* l = m_ctTouched[i];
+            if (!l->propagateStale) continue;
+            l->propagateStale = false;                 /* also de-duplicates */
+            slots.push_back(l->slot); outs.push_back(l->propagateCost); got.push_back(l);
+        }
+        m_ctTouched.clear();
+    }
     if (m_ctOps.empty() && slots.empty()) return true;
     int r = x265cu_cutree_run(m_ctx, (int)m_ctOps.size(), m_ctOps.empty() ? NULL : &m_ctOps[0], (int)slots.size(),
                               slots.empty() ? NULL : &slots[0], outs.empty() ? NULL : &outs[0]);
     m_ctOps.clear();
-    if (r) { snprintf(m_error, sizeof(m_error), "x265cu_cutree_run: %s", x265cu_last_error(m_ctx)); return false; }
-    for (int i = 0; i < nFetch; i++) fetch[i]->propagateStale = false;
+    if (r)
+    {
+        for (size_t i = 0; i < got.size(); i++) got[i]->propagateStale = true;
+        snprintf(m_error, sizeof(m_error), "x265cu_cutree_run: %s", x265cu_last_error(m_ctx));
+        return false;
+    }
     m_ctStats[1]++;
     return true;
 }
@@ -1034,7 +1051,7 @@ const uint16_t* Lookahead::propagateCost(Lowres& f)
 bool Lookahead::cuTreeFinish(Lowres* frame, double averageDuration, int ref0Distance)
 {
     if (!cuTreeRun(&frame, 1)) return false;
-    if (m_resident) return true;         /* intraCost / qpAqOffset are not on the host in resident mode */
+    if (m_resident) return true;         /* intraCost / qpAqOffset are not on the host in resident mode (propagateCost is) */
     int fpsFactor = (int)(clipDuration(averageDuration) / clipDuration((double)m_param.fpsDenom / m_param.fpsNum) * 256);
     double weightdelta = 0.0;
     if (ref0Distance && frame->weightedCostDelta[ref0Distance - 1] > 0)
