@@ -196,16 +196,21 @@ class Runner:
                 fr = [self.frames.get(p) for p in range(lo, hi + 1)]
                 tr = [(j["p0"] - lo, j["p1"] - lo, j["b"] - lo) for j in jobs]
                 self.calls.append(("E", la.prepare_estimate(fr, tr), e[0] == "B"))
-            elif e[0] == "M" and cutree:
-                # cuTree: the memsets, propagate steps and cuTreeFinish calls of Lookahead::cuTree, in place
-                self.calls.append(("M", self.frames[e[1]]))
-            elif e[0] == "X" and cutree:
-                x = e[1]
-                fr = [self.frames.get(p) for p in range(x["p0"], x["p1"] + 1)]
-                self.calls.append(("X", (C.c_void_p * len(fr))(*fr), len(fr), x["p1"] - x["p0"], x["b"] - x["p0"], x["referenced"], x["avgDuration"]))
-                self.npropagate += 1
-            elif e[0] == "F" and cutree:
-                self.calls.append(("F", self.frames[e[1]["poc"]], e[1]["avgDuration"], e[1]["ref0Distance"]))
+            elif e[0] in ("M", "X", "F") and cutree:
+                # cuTree: the memsets, propagate steps and cuTreeFinish calls of Lookahead::cuTree, in place;
+                # a run of them is marshalled once (like the estimates) so that Python's per-call cost stays out
+                if not (self.calls and self.calls[-1][0] == "T"):
+                    self.calls.append(("T", []))
+                if e[0] == "M":
+                    self.calls[-1][1].append(("M", self.frames[e[1]]))
+                elif e[0] == "X":
+                    x = e[1]
+                    self.calls[-1][1].append(("X", self.frames[x["b"]], self.frames[x["p0"]], self.frames[x["p1"]], x["b"] - x["p0"],
+                                              x["p1"] - x["b"], x["referenced"], x["avgDuration"]))
+                    self.npropagate += 1
+                else:
+                    self.calls[-1][1].append(("F", self.frames[e[1]["poc"]], e[1]["avgDuration"], e[1]["ref0Distance"]))
+        self.calls = [("T", la.prepare_cutree_sequence(c[1])) if c[0] == "T" else c for c in self.calls]
         self.calls = [("P", c[1], la.prepare_pre_lookahead_batch([(self.frames[t],) + tuple(self.inputs[t]) + (t,) for t in c[1]])) if c[0] == "P" else c
                       for c in self.calls]
         self.units = sum(j["s0"] + j["s1"] for j in trace.jobs())
@@ -213,19 +218,13 @@ class Runner:
 
     def step(self):
         la = self.la
-        L, h = la.L, la.h
         for c in self.calls:
             if c[0] == "P":
                 la.pre_lookahead_batch_prepared(c[2], True)
             elif c[0] == "E":
                 la.estimate_prepared(c[1], c[2])
-            elif c[0] == "X":
-                if L.x265cuh_cutree_propagate(h, c[1], c[2], 0, c[3], c[4], c[5], c[6]):
-                    raise RuntimeError("estimateCUPropagate failed: " + la.error())
-            elif c[0] == "M":
-                L.x265cuh_cutree_zero(h, c[1])
             else:
-                la.cutree_finish(c[1], c[2], c[3])
+                la.cutree_sequence_prepared(c[1])
         la.sync()          # every output, including the asynchronous plane copy-backs, is on the host
 
     def close(self):

@@ -143,6 +143,7 @@ def lib_host():
         L.x265cuh_cutree_propagate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]
         L.x265cuh_cutree_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int]
         L.x265cuh_cutree_stats.argtypes = [C.c_void_p, C.c_void_p]
+        L.x265cuh_cutree_sequence.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8
         L.x265cuh_crc32.restype = C.c_uint32
         L.x265cuh_crc32.argtypes = [C.c_void_p, C.c_size_t]
         L.x265cuh_error.restype = C.c_char_p
@@ -277,6 +278,25 @@ class Lookahead:
     def cutree_finish(self, frame, average_duration, ref0_distance):
         if self.L.x265cuh_cutree_finish(self.h, frame, average_duration, ref0_distance):
             raise RuntimeError("cuTreeFinish failed: " + self.error())
+
+    def prepare_cutree_sequence(self, calls):
+        """pre-marshal a run of cuTree calls: ("M", frame) | ("X", fenc, ref0, ref1, d0, d1, referenced, avgDuration) |
+        ("F", frame, avgDuration, ref0Distance)"""
+        n = len(calls)
+        kind, fenc, r0, r1 = (C.c_int * n)(), (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_void_p * n)()
+        d0, d1, arg, dur = (C.c_int * n)(), (C.c_int * n)(), (C.c_int * n)(), (C.c_double * n)()
+        for i, c in enumerate(calls):
+            if c[0] == "M":
+                kind[i], fenc[i] = 0, c[1]
+            elif c[0] == "X":
+                kind[i], fenc[i], r0[i], r1[i], d0[i], d1[i], arg[i], dur[i] = 1, c[1], c[2], c[3], c[4], c[5], c[6], c[7]
+            else:
+                kind[i], fenc[i], dur[i], arg[i] = 2, c[1], c[2], c[3]
+        return (n, kind, fenc, r0, r1, d0, d1, arg, dur)
+
+    def cutree_sequence_prepared(self, prep):
+        if self.L.x265cuh_cutree_sequence(self.h, *prep):
+            raise RuntimeError("cuTree sequence failed: " + self.error())
 
     def cutree_stats(self):
         o = (C.c_int64 * 3)()

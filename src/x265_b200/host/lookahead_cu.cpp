@@ -1193,6 +1193,25 @@ int x265cuh_cutree_finish(void* la, void* frame, double averageDuration, int ref
 {
     return ((Lookahead*)la)->cuTreeFinish((Lowres*)frame, averageDuration, ref0Distance) ? 0 : -1;
 }
+int x265cuh_cutree_sequence(void* h, int n, const int* kind, void* const* fenc, void* const* ref0, void* const* ref1,
+                            const int* d0, const int* d1, const int* arg, const double* averageDuration)
+{
+    Lookahead* la = (Lookahead*)h;
+    Lowres* fr[2 * BFRAME_MAX + 4];
+    for (int i = 0; i < n; i++)
+    {
+        if (kind[i] == 0) la->cuTreeZero(*(Lowres*)fenc[i]);
+        else if (kind[i] == 1)
+        {
+            if (d0[i] < 1 || d1[i] < 0 || d0[i] + d1[i] > 2 * BFRAME_MAX + 2) return -1;
+            memset(fr, 0, sizeof(fr));
+            fr[0] = (Lowres*)ref0[i]; fr[d0[i] + d1[i]] = (Lowres*)ref1[i]; fr[d0[i]] = (Lowres*)fenc[i];
+            if (!la->estimateCUPropagate(fr, averageDuration[i], 0, d0[i] + d1[i], d0[i], arg[i])) return -1;
+        }
+        else if (!la->cuTreeFinish((Lowres*)fenc[i], averageDuration[i], arg[i])) return -1;
+    }
+    return 0;
+}
 void x265cuh_cutree_stats(void* la, int64_t* o) { for (int i = 0; i < 3; i++) o[i] = ((Lookahead*)la)->m_ctStats[i]; }
 
 void x265cuh_frame_scalars(void* frame, int d0, int d1, int64_t* o)

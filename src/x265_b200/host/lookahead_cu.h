@@ -251,6 +251,11 @@ void  x265cuh_cutree_zero(void* la, void* frame);
 int   x265cuh_cutree_propagate(void* la, void** frames, int nframes, int p0, int p1, int b, int referenced, double averageDuration);
 int   x265cuh_cutree_finish(void* la, void* frame, double averageDuration, int ref0Distance);
 void  x265cuh_cutree_stats(void* la, int64_t* out3);
+/* a run of those calls in one go (pre-marshalled replays: the per-call cost of the caller's language stays out of the
+ * measurement): kind 0 = zero(fenc), 1 = propagate(ref0, fenc, ref1 at distances d0, d1; arg = referenced),
+ * 2 = finish(fenc; arg = ref0Distance) */
+int   x265cuh_cutree_sequence(void* la, int n, const int* kind, void* const* fenc, void* const* ref0, void* const* ref1,
+                              const int* d0, const int* d1, const int* arg, const double* averageDuration);
 /* array accessors for checks: which = 0 planes, 1 intraCost, 2 intraMode, 3 invQscale, 4 lowresCosts[d0][d1],
  * 5 rowSatds[d0][d1], 6 lowresMvs[list=d0][d1-1], 7 lowresMvCosts[list=d0][d1-1], 8 propagateCost (fetched from the
  * device if it is ahead; d0 != 0: only the first CU row), 9 qpCuTreeOffset, 10 qpAqOffset; returns pointer and byte size */
