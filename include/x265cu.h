@@ -81,8 +81,9 @@ void x265cu_close(x265cu_ctx* ctx);
 const char* x265cu_last_error(const x265cu_ctx* ctx);   /* ctx may be NULL: last open() error */
 int  x265cu_get_geometry(const x265cu_ctx* ctx, x265cu_geometry* out);
 int  x265cu_sync(x265cu_ctx* ctx);
-/* pin + map a host array the library will read/write often (Lowres arrays, PicYuv planes);
- * optional, only affects copy speed */
+/* pin + map a host array the library will read/write often (Lowres arrays, PicYuv planes); optional, only affects
+ * speed: copies become asynchronous, and result arrays of x265cu_estimate_batch whose destination lies in a
+ * registered range are written there by the GPU itself instead of being staged and memcpy'd by a host thread */
 int  x265cu_host_register(void* ptr, size_t bytes);
 int  x265cu_host_unregister(void* ptr);
 
@@ -229,7 +230,7 @@ int x265cu_int_peak(x265cu_ctx* ctx, double* gopsVabsdiff4, double* gopsIadd);
 
 /* ---- instrumentation: device time (ms, CUDA events on the ctx stream) and launch counts
  * accumulated since the last reset, per kernel family. */
-enum { X265CU_K_LOWRES = 0, X265CU_K_INTRA, X265CU_K_SEARCH, X265CU_K_COST, X265CU_K_WEIGHT, X265CU_K_PIXEL, X265CU_K_VAR, X265CU_K_CUTREE, X265CU_K_COUNT };
+enum { X265CU_K_LOWRES = 0, X265CU_K_INTRA, X265CU_K_SEARCH, X265CU_K_COST, X265CU_K_WEIGHT, X265CU_K_PIXEL, X265CU_K_VAR, X265CU_K_CUTREE, X265CU_K_RESULTS, X265CU_K_COUNT };
 typedef struct x265cu_stats
 {
     double ms[X265CU_K_COUNT];

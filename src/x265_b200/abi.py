@@ -14,7 +14,7 @@ LIB_CU = os.path.join(PKG, "libx265cu.so")
 LIB_HOST = os.path.join(PKG, "libx265cu_host.so")
 
 BFMAX = 16
-K_NAMES = ("lowres", "intra", "search", "cost", "weight", "pixel", "var", "cutree")
+K_NAMES = ("lowres", "intra", "search", "cost", "weight", "pixel", "var", "cutree", "results")
 
 
 class Config(C.Structure):
@@ -51,7 +51,7 @@ class JobResult(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [("ms", C.c_double * 8), ("launches", C.c_int64 * 8), ("h2dBytes", C.c_int64), ("d2hBytes", C.c_int64)]
+    _fields_ = [("ms", C.c_double * 9), ("launches", C.c_int64 * 9), ("h2dBytes", C.c_int64), ("d2hBytes", C.c_int64)]
 
 
 class HostParams(C.Structure):

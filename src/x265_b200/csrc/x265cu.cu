@@ -22,6 +22,7 @@
 #include <string.h>
 #include <algorithm>
 #include <chrono>
+#include <map>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -29,6 +30,23 @@
 namespace {
 
 char g_openError[512] = "";
+
+/* host ranges registered through x265cu_host_register, with their device-side alias (mapped pinned memory): result
+ * arrays whose destination lies in one of them are written there by a kernel instead of being staged and memcpy'd */
+struct HostRange { uintptr_t base; size_t bytes; uintptr_t dev; };
+std::mutex g_regMtx;
+std::map<uintptr_t, HostRange> g_reg;
+
+uint8_t* mappedAlias(const void* p, size_t bytes)
+{
+    std::lock_guard<std::mutex> lk(g_regMtx);
+    std::map<uintptr_t, HostRange>::const_iterator it = g_reg.upper_bound((uintptr_t)p);
+    if (it == g_reg.begin()) return NULL;
+    --it;
+    const HostRange& r = it->second;
+    if ((uintptr_t)p < r.base || (uintptr_t)p + bytes > r.base + r.bytes) return NULL;
+    return (uint8_t*)(r.dev + ((uintptr_t)p - r.base));
+}
 
 struct PendingEvent { int kind; cudaEvent_t a, b; };
 
@@ -62,6 +80,7 @@ struct x265cu_ctx
     int* dMvCosts;
     unsigned long long* dPropagate;        /* [slot][nCU] Lowres::propagateCost accumulators (x265cu_cutree.cuh) */
     int cutreeCtas;                        /* grid of the cooperative cuTree kernel (one CTA per SM) */
+    bool mappedResults;                    /* result arrays go straight into mapped pinned destinations (X265CU_MAPPED_RESULTS=0: always staged) */
     uint16_t* dPropOut; size_t dPropOutCap; /* clamped uint16 copies on their way to the host */
     uint16_t* hPropOut; size_t hPropOutCap;
     uint16_t* dLut;        /* base; centre at +65536 */
@@ -280,6 +299,7 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     c->dStage = NULL; c->dStageCap = 0; c->hStage = NULL; c->hStageCap = 0; c->dArgs = NULL; c->dArgsCap = 0; c->hArgs = NULL; c->hArgsCap = 0; c->hPre = NULL; c->hPreCap = 0; c->dPre = NULL; c->dPreCap = 0; c->dSrcLin = NULL; c->dSrcLinCap = 0; c->dUp = NULL; c->dUpCap = 0; c->upStream = NULL;
     c->dGeneric = NULL; c->dGenericCap = 0; c->dMemo = NULL; c->dMemoCap = 0;
     c->cutreeCtas = 0;
+    c->mappedResults = !(getenv("X265CU_MAPPED_RESULTS") && atoi(getenv("X265CU_MAPPED_RESULTS")) == 0);
     c->dPropagate = NULL; c->dPropOut = NULL; c->dPropOutCap = 0; c->hPropOut = NULL; c->hPropOutCap = 0;
     c->timing = false;
     memset(&c->stats, 0, sizeof(c->stats));
@@ -422,14 +442,28 @@ int x265cu_sync(x265cu_ctx* c)
 int x265cu_host_register(void* ptr, size_t bytes)
 {
     if (!ptr || !bytes) return X265CU_EINVAL;
-    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    /* pinned AND mapped: copies to it are asynchronous, and result arrays can be written into it by a kernel */
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
     if (e != cudaSuccess) { cudaGetLastError(); return X265CU_ECUDA; }
+    void* dev = NULL;
+    if (cudaHostGetDevicePointer(&dev, ptr, 0) == cudaSuccess && dev)
+    {
+        std::lock_guard<std::mutex> lk(g_regMtx);
+        HostRange r = { (uintptr_t)ptr, bytes, (uintptr_t)dev };
+        g_reg[(uintptr_t)ptr] = r;
+    }
+    else
+        cudaGetLastError();
     return X265CU_OK;
 }
 
 int x265cu_host_unregister(void* ptr)
 {
     if (!ptr) return X265CU_EINVAL;
+    {
+        std::lock_guard<std::mutex> lk(g_regMtx);
+        g_reg.erase((uintptr_t)ptr);
+    }
     cudaError_t e = cudaHostUnregister(ptr);
     if (e != cudaSuccess) { cudaGetLastError(); return X265CU_ECUDA; }
     return X265CU_OK;
@@ -1198,7 +1232,39 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     size_t offPlans = alignUp(offItems + items.size() * sizeof(SearchItem), 256);
     size_t offCost = alignUp(offPlans + plans.size() * sizeof(SearchPlan), 256);
     size_t offW = alignUp(offCost + costIdx.size() * sizeof(int), 256);
-    size_t offProg = alignUp(offW + weightedJobs.size() * sizeof(WeightDev), 256);   /* device only: wavefront progress */
+    /* where each result array goes: straight into the caller's array when that lies in mapped pinned memory
+     * (x265cu_host_register) -- a kernel writes it there over PCIe, nothing is staged or memcpy'd on the host --
+     * otherwise through the pinned staging area and a host memcpy */
+    struct HostCopy { void* dst; size_t srcOff; size_t bytes; };
+    std::vector<HostCopy> hostCopies;
+    std::vector<ScatterDev> devCopies;
+    size_t devCopyBytes = 0;
+    if (wantArrays)
+    {
+        for (int i = 0; i < n; i++)
+        {
+            const x265cu_job& j = jobs[i];
+            size_t off = recOff[i];
+            void* dsts[6]; size_t offs[6], lens[6]; int nd = 0;
+            dsts[nd] = j.rowSatds; offs[nd] = off; lens[nd++] = hCU * 4; off += alignUp(hCU * 4, 16);
+            dsts[nd] = j.lowresCosts; offs[nd] = off; lens[nd++] = nCU * 2; off += alignUp(nCU * 2, 16);
+            for (int l = 0; l < 2; l++)
+                if (j.doSearch[l])
+                {
+                    dsts[nd] = j.mvs[l]; offs[nd] = off; lens[nd++] = nCU * 4; off += alignUp(nCU * 4, 16);
+                    dsts[nd] = j.mvCosts[l]; offs[nd] = off; lens[nd++] = nCU * 4; off += alignUp(nCU * 4, 16);
+                }
+            for (int k = 0; k < nd; k++)
+            {
+                if (!dsts[k]) continue;
+                uint8_t* alias = c->mappedResults ? mappedAlias(dsts[k], lens[k]) : NULL;
+                if (alias) { ScatterDev sd = { NULL, alias, (unsigned)lens[k], (unsigned)offs[k] }; devCopies.push_back(sd); devCopyBytes += lens[k]; }
+                else { HostCopy hc = { dsts[k], offs[k], lens[k] }; hostCopies.push_back(hc); }
+            }
+        }
+    }
+    size_t offScat = alignUp(offW + weightedJobs.size() * sizeof(WeightDev), 256);
+    size_t offProg = alignUp(offScat + devCopies.size() * sizeof(ScatterDev), 256);   /* device only: wavefront progress */
     size_t argBytes = 8 + alignUp(offProg + (size_t)handRows * g.wCU * sizeof(unsigned long long), 256);
     if (growHost(c, &c->hArgs, &c->hArgsCap, argBytes) || growDevice(c, &c->dArgs, &c->dArgsCap, argBytes)) return X265CU_ECUDA;
     if (growDevice(c, &c->dStage, &c->dStageCap, total) || growHost(c, &c->hStage, &c->hStageCap, total)) return X265CU_ECUDA;
@@ -1249,6 +1315,10 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
         hw[k].dst = c->wPool[k];
         hw[k].scale = j.wScale;
         weightArgs(c, j.wScale, j.wDenom, j.wOffset, &hw[k].round, &hw[k].shift, &hw[k].offset);
+    }
+    {
+        ScatterDev* hs = (ScatterDev*)(c->hArgs + offScat);
+        for (size_t k = 0; k < devCopies.size(); k++) { hs[k] = devCopies[k]; hs[k].src = c->dStage + devCopies[k].srcOff; }
     }
     const std::chrono::steady_clock::time_point tH1 = std::chrono::steady_clock::now();
     CU_TRY(c, cudaMemcpyAsync(c->dArgs, c->hArgs, offProg, cudaMemcpyHostToDevice, c->stream));
@@ -1336,9 +1406,15 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
             cost_kernel<uint16_t><<<grid, 128, 0, c->stream>>>((const JobDev*)(c->dArgs + offJobs), (const int*)(c->dArgs + offCost), g);
         CU_TRY(c, cudaGetLastError());
     }
-    const size_t back = wantArrays ? total : (size_t)n * 32;
+    if (!devCopies.empty())
+    {
+        KernelScope ks(c, X265CU_K_RESULTS);
+        scatter_results_kernel<<<(unsigned)devCopies.size(), 256, 0, c->stream>>>((const ScatterDev*)(c->dArgs + offScat));
+        CU_TRY(c, cudaGetLastError());
+    }
+    const size_t back = !hostCopies.empty() ? total : (size_t)n * 32;
     CU_TRY(c, cudaMemcpyAsync(c->hStage, c->dStage, back, cudaMemcpyDeviceToHost, c->stream));
-    c->stats.d2hBytes += (int64_t)back;
+    c->stats.d2hBytes += (int64_t)(back + devCopyBytes);
     const std::chrono::steady_clock::time_point tH2 = std::chrono::steady_clock::now();
     int r = syncStream(c);
     if (r) return r;
@@ -1380,7 +1456,6 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     for (int i = 0; i < n; i++)
     {
         const x265cu_job& j = jobs[i];
-        const uint8_t* rec = c->hStage + recOff[i];
         const unsigned long long* sums = (const unsigned long long*)(c->hStage + (size_t)i * 32);
         x265cu_job_result& res = results[i];
         res.costEstRaw = (int64_t)sums[0];
@@ -1388,19 +1463,11 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
         res.intraMbs = (int32_t)sums[2];
         res.reserved = 0;
         res.costEst = j.d1 > 0 ? res.costEstRaw * 100 / (130 + c->cfg.bFrameBias) : res.costEstRaw;   /* slicetype.cpp:2053-2057 */
-        if (!wantArrays) continue;
-        if (j.rowSatds) { Copy cp = { j.rowSatds, rec, hCU * 4 }; copies.push_back(cp); copyBytes += cp.bytes; }
-        rec += alignUp(hCU * 4, 16);
-        if (j.lowresCosts) { Copy cp = { j.lowresCosts, rec, nCU * 2 }; copies.push_back(cp); copyBytes += cp.bytes; }
-        rec += alignUp(nCU * 2, 16);
-        for (int l = 0; l < 2; l++)
-            if (j.doSearch[l])
-            {
-                if (j.mvs[l]) { Copy cp = { j.mvs[l], rec, nCU * 4 }; copies.push_back(cp); copyBytes += cp.bytes; }
-                rec += alignUp(nCU * 4, 16);
-                if (j.mvCosts[l]) { Copy cp = { j.mvCosts[l], rec, nCU * 4 }; copies.push_back(cp); copyBytes += cp.bytes; }
-                rec += alignUp(nCU * 4, 16);
-            }
+    }
+    for (size_t k = 0; k < hostCopies.size(); k++)
+    {
+        Copy cp = { hostCopies[k].dst, c->hStage + hostCopies[k].srcOff, hostCopies[k].bytes };
+        copies.push_back(cp); copyBytes += cp.bytes;
     }
     unsigned nThreads = 1;
     if (copyBytes > ((size_t)8 << 20))
@@ -1409,7 +1476,8 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
         if (nThreads > 8) nThreads = 8;
         if (nThreads < 1) nThreads = 1;
     }
-    if (nThreads <= 1)
+    if (copies.empty()) { }
+    else if (nThreads <= 1)
         for (size_t k = 0; k < copies.size(); k++) memcpy(copies[k].dst, copies[k].src, copies[k].bytes);
     else
     {

@@ -21,6 +21,26 @@
 
 #define X265CU_SA8D_16x16_K 3
 
+/* one result array of a batch on its way from the device staging area into the caller's (mapped, pinned) host array */
+struct ScatterDev { const uint8_t* src; uint8_t* dst; unsigned bytes; unsigned srcOff; };
+
+/* CTA per array: 16-byte coalesced stores over PCIe (both sides are 16-byte aligned: staging records and the host
+ * layer's arrays are), byte tail */
+__global__ void __launch_bounds__(256) scatter_results_kernel(const ScatterDev* __restrict__ e)
+{
+    const ScatterDev s = e[blockIdx.x];
+    unsigned done = 0;
+    if ((((size_t)s.src | (size_t)s.dst) & 15) == 0)
+    {
+        const unsigned n16 = s.bytes >> 4;
+        const uint4* a = (const uint4*)s.src;
+        uint4* b = (uint4*)s.dst;
+        for (unsigned i = threadIdx.x; i < n16; i += blockDim.x) b[i] = a[i];
+        done = n16 << 4;
+    }
+    for (unsigned i = done + threadIdx.x; i < s.bytes; i += blockDim.x) s.dst[i] = s.src[i];
+}
+
 struct GeomDev
 {
     int width, lines, stride, marginX, marginY, paddedLines;

@@ -1056,13 +1056,23 @@ bool Lookahead::cuTreeFinish(Lowres* frame, double averageDuration, int ref0Dist
     double weightdelta = 0.0;
     if (ref0Distance && frame->weightedCostDelta[ref0Distance - 1] > 0)
         weightdelta = (1.0 - frame->weightedCostDelta[ref0Distance - 1]);
+    /* X265_LOG2 of small positive integers, memoised: the arguments are integers (costs), the same few thousand
+     * values come back frame after frame, and a cached result of the same libm call is the same double */
+    if (m_log2Lut.empty()) m_log2Lut.assign((size_t)1 << 20, -1.0);
+    double* lut = &m_log2Lut[0];
+    const int lutSize = (int)m_log2Lut.size();
     for (int cuIndex = 0; cuIndex < m_cuCount; cuIndex++)
     {
         int intracost = (frame->intraCost[cuIndex] * frame->invQscaleFactor[cuIndex] + 128) >> 8;
         if (intracost)
         {
             int propagateCost = (frame->propagateCost[cuIndex] * fpsFactor + 128) >> 8;
-            double log2_ratio = log2((double)(intracost + propagateCost)) - log2((double)intracost) + weightdelta;
+            const int a = intracost + propagateCost, b = intracost;
+            double la, lb;
+            if (a > 0 && a < lutSize) { la = lut[a]; if (la < 0) la = lut[a] = log2((double)a); } else la = log2((double)a);
+            if (b > 0 && b < lutSize) { lb = lut[b]; if (lb < 0) lb = lut[b] = log2((double)b); } else lb = log2((double)b);
+            volatile double diff = la - lb;          /* evaluated left to right, as the reference's object code does */
+            double log2_ratio = diff + weightdelta;
             frame->qpCuTreeOffset[cuIndex] = frame->qpAqOffset[cuIndex] - m_cuTreeStrength * log2_ratio;
         }
     }

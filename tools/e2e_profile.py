@@ -20,13 +20,16 @@ for resident in (True, False):
     r = bench.Runner(trace, clip, None, 0, resident, torch)
     for _ in range(2):
         r.step()
-    acc = {"P": [0.0, 0], "B": [0.0, 0], "J": [0.0, 0], "sync": [0.0, 0]}
+    acc = {"P": [0.0, 0], "B": [0.0, 0], "J": [0.0, 0], "T": [0.0, 0], "sync": [0.0, 0]}
     t_all = time.perf_counter()
     for c in r.calls:
         t0 = time.perf_counter()
         if c[0] == "P":
             r.la.pre_lookahead_batch_prepared(c[2], os.environ.get('PLANES_BACK', '1') == '1')
             k = "P"
+        elif c[0] == "T":
+            r.la.cutree_sequence_prepared(c[1])
+            k = "T"
         else:
             r.la.estimate_prepared(c[1], c[2])
             k = "B" if c[2] else "J"
