@@ -131,6 +131,19 @@ typedef struct x265cu_frame_in
 } x265cu_frame_in;
 int x265cu_frame_init_var_batch(x265cu_ctx* ctx, int n, const x265cu_frame_in* items);
 
+/* ---- the whole of PreLookaheadGroup::processTasks for its list (slicetype.cpp:831-856) as ONE pipelined call:
+ * x265cu_frame_init_var_batch, the host's float AQ mapping and x265cu_intra_batch, a few frames at a time.  As soon
+ * as the energies/sums of frames [first, first + count) are on the host, `aq(user, first, count, invQscale)` is
+ * called (on the calling thread, no library call allowed inside): it runs the float part of
+ * calcAdaptiveQuantFrame (slicetype.cpp:163-207) for those frames -- on several threads if it likes, as the
+ * reference spreads the frames of a list over its workers -- and stores each frame's invQscaleFactor pointer (or
+ * NULL: no AQ arrays) in invQscale[0..count); the library publishes them and starts lowresIntraEstimate of those
+ * frames on a second stream while the pictures of the later frames are still crossing PCIe.  count is 1 for short
+ * lists and up to 8 for long ones.  outs[i] as in x265cu_intra. */
+typedef void (*x265cu_aq_fn)(void* user, int first, int count, const int32_t** invQscale);
+struct x265cu_intra_out;
+int x265cu_pre_lookahead_batch(x265cu_ctx* ctx, int n, const x265cu_frame_in* items, x265cu_aq_fn aq, void* user, struct x265cu_intra_out* outs);
+
 /* ---- LookaheadTLD::lowresIntraEstimate (slicetype.cpp:230-336).  Outputs (any may be NULL):
  * Lowres::intraCost, intraMode, lowresCosts[0][0], rowSatds[0][0]; sums[0] = costEst[0][0],
  * sums[1] = costEstAq[0][0]. */

@@ -88,6 +88,8 @@ struct x265cu_ctx
     uint8_t* dSrcLin; size_t dSrcLinCap;   /* luma staging with the host's pitch (linear transfer) */
     uint8_t* dUp; size_t dUpCap;           /* per-frame staging of a batched pre-lookahead list */
     cudaStream_t upStream;                 /* its uploads */
+    cudaStream_t intraStream;              /* x265cu_pre_lookahead_batch: intra estimates run beside the uploads of later frames */
+    std::vector<cudaEvent_t> preEvents;    /* per frame of the list: lowres planes + energies/sums done */
     std::vector<cudaEvent_t> upEvents;
     int64_t srcPitch;      /* samples */
     unsigned long long* dSmall;   /* small scratch for sums */
@@ -188,15 +190,15 @@ cudaEvent_t getEvent(x265cu_ctx* c)
 
 struct KernelScope
 {
-    x265cu_ctx* c; int kind; cudaEvent_t a, b; bool on;
-    KernelScope(x265cu_ctx* ctx, int k, int launches = 1) : c(ctx), kind(k), on(ctx->timing)
+    x265cu_ctx* c; int kind; cudaEvent_t a, b; bool on; cudaStream_t st;
+    KernelScope(x265cu_ctx* ctx, int k, int launches = 1, cudaStream_t stream = NULL) : c(ctx), kind(k), on(ctx->timing), st(stream ? stream : ctx->stream)
     {
         c->stats.launches[kind] += launches;
-        if (on) { a = getEvent(c); b = getEvent(c); cudaEventRecord(a, c->stream); }
+        if (on) { a = getEvent(c); b = getEvent(c); cudaEventRecord(a, st); }
     }
     ~KernelScope()
     {
-        if (on) { cudaEventRecord(b, c->stream); PendingEvent p = { kind, a, b }; c->pending.push_back(p); }
+        if (on) { cudaEventRecord(b, st); PendingEvent p = { kind, a, b }; c->pending.push_back(p); }
     }
 };
 
@@ -246,6 +248,8 @@ void freeAll(x265cu_ctx* c)
     cudaFree(c->dPropagate); cudaFree(c->dPropOut); if (c->hPropOut) cudaFreeHost(c->hPropOut);
     cudaFree(c->dLut); cudaFree(c->dSrc); cudaFree(c->dSmall); cudaFree(c->dStage); cudaFree(c->dArgs); cudaFree(c->dGeneric); cudaFree(c->dMemo); cudaFree(c->dSrcLin); cudaFree(c->dUp); cudaFree(c->dPre);
     if (c->upStream) cudaStreamDestroy(c->upStream);
+    if (c->intraStream) cudaStreamDestroy(c->intraStream);
+    for (size_t i = 0; i < c->preEvents.size(); i++) cudaEventDestroy(c->preEvents[i]);
     for (size_t i = 0; i < c->upEvents.size(); i++) cudaEventDestroy(c->upEvents[i]);
     if (c->hStage) cudaFreeHost(c->hStage);
     if (c->hArgs) cudaFreeHost(c->hArgs);
@@ -296,7 +300,7 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     c->err[0] = 0;
     c->dPlanes = NULL; c->dIntraCost = NULL; c->dIntraMode = NULL; c->dInvQ = NULL; c->dLowresCosts = NULL; c->dRowSatds = NULL;
     c->dMvs = NULL; c->dMvCosts = NULL; c->dLut = NULL; c->dSrc = NULL; c->dSmall = NULL;
-    c->dStage = NULL; c->dStageCap = 0; c->hStage = NULL; c->hStageCap = 0; c->dArgs = NULL; c->dArgsCap = 0; c->hArgs = NULL; c->hArgsCap = 0; c->hPre = NULL; c->hPreCap = 0; c->dPre = NULL; c->dPreCap = 0; c->dSrcLin = NULL; c->dSrcLinCap = 0; c->dUp = NULL; c->dUpCap = 0; c->upStream = NULL;
+    c->dStage = NULL; c->dStageCap = 0; c->hStage = NULL; c->hStageCap = 0; c->dArgs = NULL; c->dArgsCap = 0; c->hArgs = NULL; c->hArgsCap = 0; c->hPre = NULL; c->hPreCap = 0; c->dPre = NULL; c->dPreCap = 0; c->dSrcLin = NULL; c->dSrcLinCap = 0; c->dUp = NULL; c->dUpCap = 0; c->upStream = NULL; c->intraStream = NULL;
     c->dGeneric = NULL; c->dGenericCap = 0; c->dMemo = NULL; c->dMemoCap = 0;
     c->cutreeCtas = 0;
     c->mappedResults = !(getenv("X265CU_MAPPED_RESULTS") && atoi(getenv("X265CU_MAPPED_RESULTS")) == 0);
@@ -637,18 +641,48 @@ static int frameInitImpl(x265cu_ctx* c, int slot, const void* luma, intptr_t src
 
 /* PreLookaheadGroup::processTasks hands a LIST of frames to the workers (slicetype.cpp:831-856): all uploads and
  * kernels of the list are enqueued back to back and the host waits once */
+static int preBatchImpl(x265cu_ctx* c, int n, const x265cu_frame_in* items, x265cu_aq_fn aq, void* user, x265cu_intra_out* outs);
+static int intraEnqueue(x265cu_ctx* c, int slot, x265cu_intra_out* out, unsigned long long* sums, unsigned long long* dBatchSums, cudaStream_t st);
+
 int x265cu_frame_init_var_batch(x265cu_ctx* c, int n, const x265cu_frame_in* items)
 {
     if (!c || n < 0 || (n && !items)) return c ? fail(c, X265CU_EINVAL, "x265cu_frame_init_var_batch: bad argument") : X265CU_EINVAL;
     if (!n) return X265CU_OK;
     std::lock_guard<std::mutex> lk(c->mtx);
     CU_TRY(c, cudaSetDevice(c->cfg.device));
+    return preBatchImpl(c, n, items, NULL, NULL, NULL);
+}
+
+int x265cu_pre_lookahead_batch(x265cu_ctx* c, int n, const x265cu_frame_in* items, x265cu_aq_fn aq, void* user, x265cu_intra_out* outs)
+{
+    if (!c || n < 0 || (n && (!items || !aq || !outs))) return c ? fail(c, X265CU_EINVAL, "x265cu_pre_lookahead_batch: bad argument") : X265CU_EINVAL;
+    if (!n) return X265CU_OK;
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CU_TRY(c, cudaSetDevice(c->cfg.device));
+    return preBatchImpl(c, n, items, aq, user, outs);
+}
+
+/* aq == NULL: lowres planes + variance of the list, one wait.  aq != NULL: per frame, as soon as its energies/sums
+ * are on the host, the caller's float AQ mapping, then invQscaleFactor upload + intra estimate on the intra stream */
+static int preBatchImpl(x265cu_ctx* c, int n, const x265cu_frame_in* items, x265cu_aq_fn aq, void* user, x265cu_intra_out* outs)
+{
     const int bxN = (c->cfg.srcWidth + 15) / 16, byN = (c->cfg.srcHeight + 15) / 16;
     const size_t eBytes = alignUp((size_t)bxN * byN * 4, 64), per = eBytes + 64;
-    if (growHost(c, &c->hPre, &c->hPreCap, (size_t)n * per)) return X265CU_ECUDA;
+    const size_t intraSumsOff = alignUp((size_t)n * per, 256);      /* [n x 16 bytes] intra sums behind the var records */
+    if (growHost(c, &c->hPre, &c->hPreCap, intraSumsOff + (size_t)n * 16)) return X265CU_ECUDA;
     /* device mirror of that landing zone: [frame][energy | 6 sums]; zeroed and copied back once for the whole list */
-    if (growDevice(c, &c->dPre, &c->dPreCap, (size_t)n * per)) return X265CU_ECUDA;
-    CU_TRY(c, cudaMemsetAsync(c->dPre, 0, (size_t)n * per, c->stream));
+    if (growDevice(c, &c->dPre, &c->dPreCap, intraSumsOff + (size_t)n * 16)) return X265CU_ECUDA;
+    CU_TRY(c, cudaMemsetAsync(c->dPre, 0, intraSumsOff + (size_t)n * 16, c->stream));
+    if (aq)
+    {
+        if (!c->intraStream) CU_TRY(c, cudaStreamCreateWithFlags(&c->intraStream, cudaStreamNonBlocking));
+        while ((int)c->preEvents.size() < n)
+        {
+            cudaEvent_t e;
+            CU_TRY(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->preEvents.push_back(e);
+        }
+    }
     const bool dbgPre = getenv("X265CU_PRE_DEBUG") != NULL;
     std::chrono::steady_clock::time_point tA = std::chrono::steady_clock::now(), tB = tA, tC = tA;
     /* host pictures: every frame gets its own staging area and its uploads run on the upload stream, so frame i + 1
@@ -706,6 +740,63 @@ int x265cu_frame_init_var_batch(x265cu_ctx* c, int n, const x265cu_frame_in* ite
                                  (uint32_t*)(c->hPre + (size_t)i * per), (unsigned long long*)(c->hPre + (size_t)i * per + eBytes),
                                  pipelined ? &up : NULL, &bo);
         if (r) { cudaStreamSynchronize(c->stream); if (c->upStream) cudaStreamSynchronize(c->upStream); return r; }
+        if (aq)
+        {
+            /* this frame's record comes back on its own, and an event tells the host (and the intra stream) it is done */
+            CU_TRY(c, cudaMemcpyAsync(c->hPre + (size_t)i * per, c->dPre + (size_t)i * per, per, cudaMemcpyDeviceToHost, c->stream));
+            CU_TRY(c, cudaEventRecord(c->preEvents[i], c->stream));
+        }
+    }
+    if (aq)
+    {
+        tC = std::chrono::steady_clock::now();
+        int rc = X265CU_OK;
+        const int chunk = n >= 12 ? 8 : 1;
+        for (int first = 0; first < n && !rc; first += chunk)
+        {
+            const int count = first + chunk <= n ? chunk : n - first;
+            if (cudaEventSynchronize(c->preEvents[first + count - 1]) != cudaSuccess) { rc = fail(c, X265CU_ECUDA, "x265cu_pre_lookahead_batch: event wait failed"); break; }
+            const int32_t* invQs[8] = { NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL };
+            for (int i = first; i < first + count; i++)
+            {
+                memcpy(items[i].energy, c->hPre + (size_t)i * per, (size_t)bxN * byN * 4);
+                memcpy(items[i].sums, c->hPre + (size_t)i * per + eBytes, 6 * sizeof(uint64_t));
+            }
+            aq(user, first, count, invQs);                      /* the host's float AQ mapping of these frames */
+            cudaStreamWaitEvent(c->intraStream, c->preEvents[first + count - 1], 0);
+            for (int i = first; i < first + count && !rc; i++)
+            {
+                const int32_t* invQ = invQs[i - first];
+                const int slot = items[i].slot;
+                c->hasInvQ[slot] = invQ != NULL;
+                if (invQ)
+                {
+                    if (cudaMemcpyAsync(slotInvQ(c, slot), invQ, (size_t)g.nCU * sizeof(int), cudaMemcpyHostToDevice, c->intraStream) != cudaSuccess)
+                    { rc = fail(c, X265CU_ECUDA, "x265cu_pre_lookahead_batch: invQscale upload failed"); break; }
+                    c->stats.h2dBytes += (int64_t)g.nCU * sizeof(int);
+                }
+                rc = intraEnqueue(c, slot, &outs[i], (unsigned long long*)(c->hPre + intraSumsOff + (size_t)i * 16),
+                                  (unsigned long long*)(c->dPre + intraSumsOff + (size_t)i * 16), c->intraStream);
+            }
+        }
+        if (!rc && cudaMemcpyAsync(c->hPre + intraSumsOff, c->dPre + intraSumsOff, (size_t)n * 16, cudaMemcpyDeviceToHost, c->intraStream) != cudaSuccess)
+            rc = fail(c, X265CU_ECUDA, "x265cu_pre_lookahead_batch: copy failed");
+        cudaError_t e1 = cudaStreamSynchronize(c->intraStream);
+        int r2 = syncStream(c);
+        if (rc) return rc;
+        if (e1 != cudaSuccess) return fail(c, X265CU_ECUDA, cudaGetErrorString(e1));
+        if (r2) return r2;
+        for (int i = 0; i < n; i++)
+        {
+            const unsigned long long* sm = (const unsigned long long*)(c->hPre + intraSumsOff + (size_t)i * 16);
+            outs[i].sums[0] = (int64_t)sm[0];
+            outs[i].sums[1] = (int64_t)sm[1];
+        }
+        if (dbgPre)
+            fprintf(stderr, "  pre_lookahead_batch n=%d pipelined=%d: upload submit %.2f ms, enqueue %.2f ms, per-frame AQ + intra + wait %.2f ms\n", n, (int)pipelined,
+                    std::chrono::duration<double, std::milli>(tB - tA).count(), std::chrono::duration<double, std::milli>(tC - tB).count(),
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tC).count());
+        return X265CU_OK;
     }
     CU_TRY(c, cudaMemcpyAsync(c->hPre, c->dPre, (size_t)n * per, cudaMemcpyDeviceToHost, c->stream));
     tC = std::chrono::steady_clock::now();
@@ -740,8 +831,10 @@ int x265cu_frame_set_invqscale(x265cu_ctx* c, int slot, const int32_t* invQ)
 }
 
 /* enqueue lowresIntraEstimate of one frame; sums (2 x u64) land once the stream has drained.  Caller holds the lock. */
-static int intraEnqueue(x265cu_ctx* c, int slot, x265cu_intra_out* out, unsigned long long* sums, unsigned long long* dBatchSums = NULL)
+static int intraEnqueue(x265cu_ctx* c, int slot, x265cu_intra_out* out, unsigned long long* sums, unsigned long long* dBatchSums,
+                        cudaStream_t st)
 {
+    if (!st) st = c->stream;
     if (badSlot(c, slot)) return fail(c, X265CU_EINVAL, "x265cu_intra: bad slot");
     const GeomDev& g = c->g;
     IntraOutDev o;
@@ -751,24 +844,24 @@ static int intraEnqueue(x265cu_ctx* c, int slot, x265cu_intra_out* out, unsigned
     o.rowSatds = slotRowSatds(c, slot, 0, 0);
     o.sums = dBatchSums ? dBatchSums : c->dSmall;
     o.invQ = c->hasInvQ[slot] ? slotInvQ(c, slot) : NULL;
-    CU_TRY(c, cudaMemsetAsync(o.rowSatds, 0, (size_t)g.hCU * sizeof(int), c->stream));
-    if (!dBatchSums) CU_TRY(c, cudaMemsetAsync(c->dSmall, 0, 2 * sizeof(unsigned long long), c->stream));
+    CU_TRY(c, cudaMemsetAsync(o.rowSatds, 0, (size_t)g.hCU * sizeof(int), st));
+    if (!dBatchSums) CU_TRY(c, cudaMemsetAsync(c->dSmall, 0, 2 * sizeof(unsigned long long), st));
     {
-        KernelScope ks(c, X265CU_K_INTRA);
+        KernelScope ks(c, X265CU_K_INTRA, 1, st);
         int blocks = (g.nCU + 7) / 8;
         if (c->pb == 1)
-            intra_kernel<uint8_t><<<blocks, 256, 0, c->stream>>>((const uint8_t*)slotPlane0(c, slot), g, c->cfg.lookaheadLambda, c->pixelMax, o);
+            intra_kernel<uint8_t><<<blocks, 256, 0, st>>>((const uint8_t*)slotPlane0(c, slot), g, c->cfg.lookaheadLambda, c->pixelMax, o);
         else
-            intra_kernel<uint16_t><<<blocks, 256, 0, c->stream>>>((const uint16_t*)slotPlane0(c, slot), g, c->cfg.lookaheadLambda, c->pixelMax, o);
+            intra_kernel<uint16_t><<<blocks, 256, 0, st>>>((const uint16_t*)slotPlane0(c, slot), g, c->cfg.lookaheadLambda, c->pixelMax, o);
     }
     CU_TRY(c, cudaGetLastError());
     if (out)
     {
-        if (out->intraCost) { CU_TRY(c, cudaMemcpyAsync(out->intraCost, o.intraCost, (size_t)g.nCU * 4, cudaMemcpyDeviceToHost, c->stream)); c->stats.d2hBytes += g.nCU * 4; }
-        if (out->intraMode) { CU_TRY(c, cudaMemcpyAsync(out->intraMode, o.intraMode, (size_t)g.nCU, cudaMemcpyDeviceToHost, c->stream)); c->stats.d2hBytes += g.nCU; }
-        if (out->lowresCosts) { CU_TRY(c, cudaMemcpyAsync(out->lowresCosts, o.lowresCosts, (size_t)g.nCU * 2, cudaMemcpyDeviceToHost, c->stream)); c->stats.d2hBytes += g.nCU * 2; }
-        if (out->rowSatds) { CU_TRY(c, cudaMemcpyAsync(out->rowSatds, o.rowSatds, (size_t)g.hCU * 4, cudaMemcpyDeviceToHost, c->stream)); c->stats.d2hBytes += g.hCU * 4; }
-        if (!dBatchSums) CU_TRY(c, cudaMemcpyAsync(sums, c->dSmall, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        if (out->intraCost) { CU_TRY(c, cudaMemcpyAsync(out->intraCost, o.intraCost, (size_t)g.nCU * 4, cudaMemcpyDeviceToHost, st)); c->stats.d2hBytes += g.nCU * 4; }
+        if (out->intraMode) { CU_TRY(c, cudaMemcpyAsync(out->intraMode, o.intraMode, (size_t)g.nCU, cudaMemcpyDeviceToHost, st)); c->stats.d2hBytes += g.nCU; }
+        if (out->lowresCosts) { CU_TRY(c, cudaMemcpyAsync(out->lowresCosts, o.lowresCosts, (size_t)g.nCU * 2, cudaMemcpyDeviceToHost, st)); c->stats.d2hBytes += g.nCU * 2; }
+        if (out->rowSatds) { CU_TRY(c, cudaMemcpyAsync(out->rowSatds, o.rowSatds, (size_t)g.hCU * 4, cudaMemcpyDeviceToHost, st)); c->stats.d2hBytes += g.hCU * 4; }
+        if (!dBatchSums) CU_TRY(c, cudaMemcpyAsync(sums, c->dSmall, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     }
     return X265CU_OK;
 }
@@ -779,7 +872,7 @@ int x265cu_intra(x265cu_ctx* c, int slot, x265cu_intra_out* out)
     std::lock_guard<std::mutex> lk(c->mtx);
     CU_TRY(c, cudaSetDevice(c->cfg.device));
     unsigned long long sums[2] = { 0, 0 };
-    int r = intraEnqueue(c, slot, out, sums);
+    int r = intraEnqueue(c, slot, out, sums, NULL, NULL);
     if (r) return r;
     r = syncStream(c);
     if (out) { out->sums[0] = (int64_t)sums[0]; out->sums[1] = (int64_t)sums[1]; }
@@ -796,7 +889,7 @@ int x265cu_intra_batch(x265cu_ctx* c, int n, const int* slots, x265cu_intra_out*
     CU_TRY(c, cudaMemsetAsync(c->dPre, 0, (size_t)n * 16, c->stream));
     for (int i = 0; i < n; i++)
     {
-        int r = intraEnqueue(c, slots[i], &outs[i], (unsigned long long*)(c->hPre + (size_t)i * 16), (unsigned long long*)(c->dPre + (size_t)i * 16));
+        int r = intraEnqueue(c, slots[i], &outs[i], (unsigned long long*)(c->hPre + (size_t)i * 16), (unsigned long long*)(c->dPre + (size_t)i * 16), NULL);
         if (r) { cudaStreamSynchronize(c->stream); return r; }
     }
     CU_TRY(c, cudaMemcpyAsync(c->hPre, c->dPre, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));

@@ -264,7 +264,7 @@ bool Lookahead::lowresInit(Lowres& l, const void* luma, intptr_t stride, int poc
 /* LookaheadTLD::calcAdaptiveQuantFrame, encoder/slicetype.cpp:95-228 (no quantOffsets).
  * The per-block AC energy and the wp sums come from the GPU; the mapping below is the host float. */
 bool Lookahead::calcAdaptiveQuantFrame(Lowres& l, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride,
-                                       const uint32_t* preEnergy, const uint64_t* preSums)
+                                       const uint32_t* preEnergy, const uint64_t* preSums, bool publish)
 {
     const Param& param = m_param;
     int maxCol = param.sourceWidth, maxRow = param.sourceHeight;
@@ -368,6 +368,7 @@ bool Lookahead::calcAdaptiveQuantFrame(Lowres& l, const void* y, intptr_t yStrid
             l.wp_ssd[i] = ssd - (sum * sum + (width[i] * height[i]) / 2) / (width[i] * height[i]);
         }
     }
+    if (!publish) return true;     /* x265cu_pre_lookahead_batch uploads the array this call returns to it */
     int r = x265cu_frame_set_invqscale(m_ctx, l.slot, l.invQscaleFactor);
     if (r) { snprintf(m_error, sizeof(m_error), "x265cu_frame_set_invqscale: %s", x265cu_last_error(m_ctx)); return false; }
     return true;
@@ -452,39 +453,7 @@ bool Lookahead::preLookaheadBatch(int n, Lowres** ls, const PictureIn* pics, boo
         f.energy = &energy[(size_t)blocks * i];
         f.sums = &sums[(size_t)6 * i];
     }
-    const bool dbg = getenv("X265CU_PRE_DEBUG") != NULL;
-    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
-    int r = x265cu_frame_init_var_batch(m_ctx, n, &items[0]);
-    if (r) { snprintf(m_error, sizeof(m_error), "x265cu_frame_init_var_batch: %s", x265cu_last_error(m_ctx)); return false; }
-    std::chrono::steady_clock::time_point t1 = std::chrono::steady_clock::now();
-    {
-        /* the float mapping of calcAdaptiveQuantFrame is per frame and independent: the reference runs the frames of the
-         * list on different workers, so do we (same code, same flags, same results) */
-        unsigned nThreads = hostThreads();
-        if (nThreads > 8) nThreads = 8;
-        if ((int)nThreads > n / 2) nThreads = (unsigned)(n / 2);
-        if (nThreads <= 1)
-        {
-            for (int i = 0; i < n; i++)
-                if (!calcAdaptiveQuantFrame(*ls[i], pics[i].y, pics[i].yStride, pics[i].u, pics[i].v, pics[i].cStride, items[i].energy, items[i].sums)) return false;
-        }
-        else
-        {
-            std::vector<std::thread> workers;
-            std::vector<char> okFlags((size_t)n, 1);
-            for (unsigned t = 0; t < nThreads; t++)
-                workers.push_back(std::thread([&, t]() {
-                    for (int i = (int)t; i < n; i += (int)nThreads)
-                        okFlags[i] = calcAdaptiveQuantFrame(*ls[i], pics[i].y, pics[i].yStride, pics[i].u, pics[i].v, pics[i].cStride, items[i].energy, items[i].sums) ? 1 : 0;
-                }));
-            for (size_t t = 0; t < workers.size(); t++) workers[t].join();
-            for (int i = 0; i < n; i++) if (!okFlags[i]) return false;
-        }
-    }
-    std::chrono::steady_clock::time_point t2 = std::chrono::steady_clock::now();
-
     std::vector<x265cu_intra_out> outs((size_t)n);
-    std::vector<int> slots((size_t)n);
     for (int i = 0; i < n; i++)
     {
         Lowres& l = *ls[i];
@@ -496,17 +465,42 @@ bool Lookahead::preLookaheadBatch(int n, Lowres** ls, const PictureIn* pics, boo
             o.intraCost = NULL; o.intraMode = NULL; o.lowresCosts = NULL; o.rowSatds = NULL;
             l.rowSatds[0][0][0] = 0;
         }
-        slots[i] = l.slot;
     }
-    r = x265cu_intra_batch(m_ctx, n, &slots[0], &outs[0]);
-    if (r) { snprintf(m_error, sizeof(m_error), "x265cu_intra_batch: %s", x265cu_last_error(m_ctx)); return false; }
-    if (dbg)
+    /* one pipelined call: while the pictures of the later frames are still crossing PCIe, the float AQ mapping of
+     * frame i runs here (callback, same code and flags as ever) and its intra estimate starts on the GPU */
+    struct AqCtx { Lookahead* la; Lowres** ls; const PictureIn* pics; const x265cu_frame_in* items; bool ok; } actx = { this, ls, pics, &items[0], true };
+    struct Aq
     {
-        std::chrono::steady_clock::time_point t3 = std::chrono::steady_clock::now();
-        fprintf(stderr, "preLookaheadBatch n=%d: init+var %.2f ms, AQ host %.2f ms, intra %.2f ms\n", n,
-                std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count(),
-                std::chrono::duration<double, std::milli>(t3 - t2).count());
-    }
+        static void one(AqCtx* a, int i)
+        {
+            if (!a->la->calcAdaptiveQuantFrame(*a->ls[i], a->pics[i].y, a->pics[i].yStride, a->pics[i].u, a->pics[i].v, a->pics[i].cStride,
+                                               a->items[i].energy, a->items[i].sums, false))
+                a->ok = false;
+        }
+        static void run(void* user, int first, int count, const int32_t** invQ)
+        {
+            AqCtx* a = (AqCtx*)user;
+            /* the mapping is per frame and independent: the reference runs the frames of the list on different workers,
+             * so do we for a run of several frames (same code, same flags, same results) */
+            unsigned nThreads = hostThreads();
+            if (nThreads > 4) nThreads = 4;
+            if ((int)nThreads > count / 2) nThreads = (unsigned)(count / 2);
+            if (nThreads <= 1)
+                for (int i = first; i < first + count; i++) one(a, i);
+            else
+            {
+                std::vector<std::thread> workers;
+                for (unsigned t = 1; t < nThreads; t++)
+                    workers.push_back(std::thread([a, first, count, t, nThreads]() { for (int i = first + (int)t; i < first + count; i += (int)nThreads) one(a, i); }));
+                for (int i = first; i < first + count; i += (int)nThreads) one(a, i);
+                for (size_t t = 0; t < workers.size(); t++) workers[t].join();
+            }
+            for (int i = 0; i < count; i++) invQ[i] = a->ls[first + i]->invQscaleFactor;
+        }
+    };
+    int r = x265cu_pre_lookahead_batch(m_ctx, n, &items[0], Aq::run, &actx, &outs[0]);
+    if (r) { snprintf(m_error, sizeof(m_error), "x265cu_pre_lookahead_batch: %s", x265cu_last_error(m_ctx)); return false; }
+    if (!actx.ok) return false;
     for (int i = 0; i < n; i++)
     {
         Lowres& l = *ls[i];

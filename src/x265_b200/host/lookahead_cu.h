@@ -161,7 +161,7 @@ public:
     bool lowresInit(Lowres& l, const void* luma, intptr_t stride, int poc, bool copyPlanesBack);
     /* LookaheadTLD::calcAdaptiveQuantFrame; planes padded like PicYuv */
     bool calcAdaptiveQuantFrame(Lowres& l, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride,
-                                const uint32_t* preEnergy = NULL, const uint64_t* preSums = NULL);
+                                const uint32_t* preEnergy = NULL, const uint64_t* preSums = NULL, bool publish = true);
     void lowresReset(Lowres& l, int poc);   /* the host-side resets of Lowres::init */
     /* the padded planes of preLookahead(copyPlanesBack) are complete on the host after sync() */
     bool sync() { return x265cu_sync(m_ctx) == 0; }
