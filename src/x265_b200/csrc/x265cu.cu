@@ -65,6 +65,13 @@ struct x265cu_ctx
     cudaStream_t copyStream;               /* device->host copies of the padded planes run behind the compute stream */
     std::vector<cudaEvent_t> planesCopied; /* per slot: last planes copy-back finished */
     std::vector<char> planesPending;
+    /* copy-backs of a pre-lookahead LIST are held back until the next estimate batch is running (or x265cu_sync):
+     * while the list's pictures are being uploaded, PCIe is the bottleneck and a copy the other way slows it down;
+     * while the estimates compute, the bus is idle */
+    std::vector<cudaEvent_t> planesReady;  /* per slot: the lowres kernel that produced the planes finished */
+    struct DeferredPlanes { int slot; void* dst; };
+    std::vector<DeferredPlanes> deferredPlanes;
+    bool deferPlanes;
     cudaEvent_t evKernel;
     std::mutex mtx;
     char err[512];
@@ -222,6 +229,23 @@ int syncStream(x265cu_ctx* c)
     return 0;
 }
 
+/* issue the held-back plane copy-backs on the copy stream (each behind the kernel that produced its planes) */
+int flushDeferredPlanes(x265cu_ctx* c)
+{
+    const size_t bytes = (size_t)4 * c->g.planeSize * c->pb;
+    for (size_t k = 0; k < c->deferredPlanes.size(); k++)
+    {
+        const int slot = c->deferredPlanes[k].slot;
+        CU_TRY(c, cudaStreamWaitEvent(c->copyStream, c->planesReady[slot], 0));
+        CU_TRY(c, cudaMemcpyAsync(c->deferredPlanes[k].dst, c->dPlanes + (size_t)slot * 4 * c->g.planeSize * c->pb, bytes, cudaMemcpyDeviceToHost, c->copyStream));
+        CU_TRY(c, cudaEventRecord(c->planesCopied[slot], c->copyStream));
+        c->planesPending[slot] = 1;
+        c->stats.d2hBytes += (int64_t)bytes;
+    }
+    c->deferredPlanes.clear();
+    return 0;
+}
+
 /* ---- mirrors ---- */
 inline uint8_t* slotBuffer(x265cu_ctx* c, int slot) { return c->dPlanes + (size_t)slot * 4 * c->g.planeSize * c->pb; }
 inline uint8_t* slotPlane0(x265cu_ctx* c, int slot) { return slotBuffer(c, slot) + (size_t)c->g.padOffset * c->pb; }
@@ -260,6 +284,7 @@ void freeAll(x265cu_ctx* c)
     if (c->copyStream) cudaStreamDestroy(c->copyStream);
     if (c->evKernel) cudaEventDestroy(c->evKernel);
     for (size_t i = 0; i < c->planesCopied.size(); i++) if (c->planesCopied[i]) cudaEventDestroy(c->planesCopied[i]);
+    for (size_t i = 0; i < c->planesReady.size(); i++) if (c->planesReady[i]) cudaEventDestroy(c->planesReady[i]);
 }
 
 } // namespace
@@ -364,6 +389,10 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     OPEN_TRY(cudaEventCreateWithFlags(&c->evKernel, cudaEventDisableTiming));
     c->planesCopied.assign(cfg->numFrameSlots, (cudaEvent_t)NULL);
     c->planesPending.assign(cfg->numFrameSlots, 0);
+    c->planesReady.assign(cfg->numFrameSlots, (cudaEvent_t)NULL);
+    c->deferPlanes = false;
+    for (int i = 0; i < cfg->numFrameSlots; i++)
+        OPEN_TRY(cudaEventCreateWithFlags(&c->planesReady[i], cudaEventDisableTiming));
     for (int i = 0; i < cfg->numFrameSlots; i++)
         OPEN_TRY(cudaEventCreateWithFlags(&c->planesCopied[i], cudaEventDisableTiming));
 
@@ -437,6 +466,7 @@ int x265cu_sync(x265cu_ctx* c)
 {
     if (!c) return X265CU_EINVAL;
     std::lock_guard<std::mutex> lk(c->mtx);
+    if (flushDeferredPlanes(c)) return X265CU_ECUDA;
     int r = syncStream(c);
     CU_TRY(c, cudaStreamSynchronize(c->copyStream));     /* pending plane copy-backs have landed */
     for (size_t i = 0; i < c->planesPending.size(); i++) c->planesPending[i] = 0;
@@ -555,6 +585,8 @@ static int frameInitEnqueue(x265cu_ctx* c, int slot, const void* luma, intptr_t 
     }
     else if (((uintptr_t)luma & 7) || (((size_t)srcStride * c->pb) & 7))
         return fail(c, X265CU_EINVAL, "x265cu_frame_init: device luma must be 8-byte aligned with an 8-byte multiple pitch");
+    for (size_t k = 0; k < c->deferredPlanes.size(); k++)
+        if (c->deferredPlanes[k].slot == slot) { int fr = flushDeferredPlanes(c); if (fr) return fr; break; }   /* a held-back copy of this slot's old planes */
     if (c->planesPending[slot])
         CU_TRY(c, cudaStreamWaitEvent(c->stream, c->planesCopied[slot], 0));   /* do not overwrite planes still being copied out */
     /* a new picture in this slot: its order and its MV fields are unknown again */
@@ -570,7 +602,13 @@ static int frameInitEnqueue(x265cu_ctx* c, int slot, const void* luma, intptr_t 
             lowres_init_kernel<uint16_t><<<grid, 256, 0, c->stream>>>((const uint16_t*)src, pitch, (uint16_t*)slotBuffer(c, slot), g);
     }
     CU_TRY(c, cudaGetLastError());
-    if (planesOut)
+    if (planesOut && c->deferPlanes)
+    {
+        CU_TRY(c, cudaEventRecord(c->planesReady[slot], c->stream));
+        x265cu_ctx::DeferredPlanes d = { slot, planesOut };
+        c->deferredPlanes.push_back(d);
+    }
+    else if (planesOut)
     {
         /* the planes travel back on the copy stream, behind the compute stream: complete after x265cu_sync() */
         size_t bytes = (size_t)4 * g.planeSize * c->pb;
@@ -664,7 +702,15 @@ int x265cu_pre_lookahead_batch(x265cu_ctx* c, int n, const x265cu_frame_in* item
 
 /* aq == NULL: lowres planes + variance of the list, one wait.  aq != NULL: per frame, as soon as its energies/sums
  * are on the host, the caller's float AQ mapping, then invQscaleFactor upload + intra estimate on the intra stream */
+static int preBatchImpl2(x265cu_ctx* c, int n, const x265cu_frame_in* items, x265cu_aq_fn aq, void* user, x265cu_intra_out* outs);
 static int preBatchImpl(x265cu_ctx* c, int n, const x265cu_frame_in* items, x265cu_aq_fn aq, void* user, x265cu_intra_out* outs)
+{
+    c->deferPlanes = !(getenv("X265CU_DEFER_PLANES") && atoi(getenv("X265CU_DEFER_PLANES")) == 0);
+    int r = preBatchImpl2(c, n, items, aq, user, outs);
+    c->deferPlanes = false;
+    return r;
+}
+static int preBatchImpl2(x265cu_ctx* c, int n, const x265cu_frame_in* items, x265cu_aq_fn aq, void* user, x265cu_intra_out* outs)
 {
     const int bxN = (c->cfg.srcWidth + 15) / 16, byN = (c->cfg.srcHeight + 15) / 16;
     const size_t eBytes = alignUp((size_t)bxN * byN * 4, 64), per = eBytes + 64;
@@ -1499,6 +1545,8 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
             cost_kernel<uint16_t><<<grid, 128, 0, c->stream>>>((const JobDev*)(c->dArgs + offJobs), (const int*)(c->dArgs + offCost), g);
         CU_TRY(c, cudaGetLastError());
     }
+    /* the bus is idle while these kernels run: now the held-back plane copy-backs of the last pre-lookahead list go */
+    if (!c->deferredPlanes.empty() && flushDeferredPlanes(c)) return X265CU_ECUDA;
     if (!devCopies.empty())
     {
         KernelScope ks(c, X265CU_K_RESULTS);
