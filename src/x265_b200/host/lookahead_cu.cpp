@@ -498,9 +498,26 @@ bool Lookahead::preLookaheadBatch(int n, Lowres** ls, const PictureIn* pics, boo
             for (int i = 0; i < count; i++) invQ[i] = a->ls[first + i]->invQscaleFactor;
         }
     };
-    int r = x265cu_pre_lookahead_batch(m_ctx, n, &items[0], Aq::run, &actx, &outs[0]);
-    if (r) { snprintf(m_error, sizeof(m_error), "x265cu_pre_lookahead_batch: %s", x265cu_last_error(m_ctx)); return false; }
-    if (!actx.ok) return false;
+    if (getenv("X265CU_PRE_PIPELINE") && atoi(getenv("X265CU_PRE_PIPELINE")) == 0)
+    {
+        /* the same work as three calls with a wait after each (tests: both forms must give identical results) */
+        int r3 = x265cu_frame_init_var_batch(m_ctx, n, &items[0]);
+        if (r3) { snprintf(m_error, sizeof(m_error), "x265cu_frame_init_var_batch: %s", x265cu_last_error(m_ctx)); return false; }
+        std::vector<int> slots((size_t)n);
+        for (int i = 0; i < n; i++)
+        {
+            if (!calcAdaptiveQuantFrame(*ls[i], pics[i].y, pics[i].yStride, pics[i].u, pics[i].v, pics[i].cStride, items[i].energy, items[i].sums)) return false;
+            slots[i] = ls[i]->slot;
+        }
+        r3 = x265cu_intra_batch(m_ctx, n, &slots[0], &outs[0]);
+        if (r3) { snprintf(m_error, sizeof(m_error), "x265cu_intra_batch: %s", x265cu_last_error(m_ctx)); return false; }
+    }
+    else
+    {
+        int r = x265cu_pre_lookahead_batch(m_ctx, n, &items[0], Aq::run, &actx, &outs[0]);
+        if (r) { snprintf(m_error, sizeof(m_error), "x265cu_pre_lookahead_batch: %s", x265cu_last_error(m_ctx)); return false; }
+        if (!actx.ok) return false;
+    }
     for (int i = 0; i < n; i++)
     {
         Lowres& l = *ls[i];

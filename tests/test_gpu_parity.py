@@ -24,6 +24,7 @@ def _replay(mods, name, max_events=None):
     replay, po, abi = mods
     res = replay.replay_trace(name, max_events=max_events)
     assert res["jobs"] > 0 and res["frames"] > 0
+    assert res["propagates"] > 0 and res["cutree"]["reuploads"] == 0     # cuTree steps replayed; no stale device mirror met
     assert not res["mismatches"], "%s: %d mismatches, first: %r" % (name, len(res["mismatches"]), res["mismatches"][:5])
     return res
 
@@ -71,6 +72,16 @@ def test_replay_without_lookahead_cache(mods, monkeypatch):
     monkeypatch.setenv("X265CU_LOOKAHEAD_CACHE", "0")
     _replay(mods, "c0_720p")
     _replay(mods, "pool3_720p")
+
+
+@pytest.mark.parametrize("var,val", [("X265CU_PRE_PIPELINE", "0"), ("X265CU_MAPPED_RESULTS", "0"), ("X265CU_DEFER_PLANES", "0")])
+def test_replay_transfer_variants(mods, monkeypatch, var, val):
+    """the other setting of each host<->device transfer strategy: pre-lookahead list as three calls instead of the pipelined
+    one, result arrays through pinned staging + host memcpy instead of straight into mapped destinations, plane copy-backs
+    issued at once instead of held back until the next estimate batch"""
+    monkeypatch.setenv(var, val)
+    _replay(mods, "c0_720p")
+    _replay(mods, "tiny10")
 
 
 def test_replay_config1_1080p(mods):
