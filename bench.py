@@ -479,6 +479,9 @@ def main():
         roof_pix = hbm_peak / (2 * P + 4.0 / 64)     # GB/s / (bytes per pixel pair) = Gpix/s
         satd["roofline_gpix_per_s"] = roof_pix
         satd["frac"] = satd["gpix_per_s"] / roof_pix
+        if satd["frac"] > 0.9:
+            satd["note"] = "the distinct planes of this clip (%d MB) fit the 126 MB L2: the launch is partly L2-fed, not HBM-bound" % (
+                nframes * Np * P // (1 << 20))
 
     # ---- CPU baseline (reported, not the target): the reference's own lookahead on the host cores ----
     cpu_baseline = None

@@ -626,6 +626,14 @@ bool CostEstimateGroup::takeAhead(Lowres* fenc, Lowres* ref0, Lowres* ref1, int 
         /* the MV fields it consumed must be the ones that are official now */
         if (!s0 && fenc->mvVersion[0][d0 - 1] != e.usedVersion[0]) continue;
         if (d1 > 0 && !s1 && fenc->mvVersion[1][d1 - 1] != e.usedVersion[1]) continue;
+        if (la.m_resident)
+        {
+            /* the arrays only exist as device mirrors: they must still be what THIS computation wrote (a later estimate
+             * computed ahead for the same slot of the tables may have overwritten them) */
+            if (fenc->devCostStamp[d0][d1] != e.costStamp) continue;
+            if (e.doSearch[0] && fenc->devMvVersion[0][d0 - 1] != e.newVersion[0]) continue;
+            if (e.doSearch[1] && fenc->devMvVersion[1][d1 - 1] != e.newVersion[1]) continue;
+        }
 
         if (!la.m_resident)
         {
@@ -811,6 +819,33 @@ bool CostEstimateGroup::runEstimates(const EstReq* est, int n)
                 produced.push_back(pr);
                 fenc->devMvVersion[l][d - 1] = newVersion[l];     /* this launch overwrites the device mirror of the field */
             }
+        }
+        /* lists this estimate does not search are CONSUMED from the device mirror of the field: that must be the official
+         * field (an estimate computed ahead and never handed out may have searched the field again and left another one
+         * there -- the vectors of a field depend on the kind of estimate that searched it, slicetype.cpp:2146-2160) */
+        for (int l = 0; l < 2; l++)
+        {
+            const int d = l ? d1 : d0;
+            if (j.doSearch[l] || (l && d1 == 0)) continue;
+            bool fromThisCall = false;
+            for (size_t k = 0; k < produced.size(); k++)
+                if (produced[k].f == fenc && produced[k].l == l && produced[k].d == d) fromThisCall = true;
+            if (fromThisCall) continue;
+            if (fenc->devMvVersion[l][d - 1] != fenc->mvVersion[l][d - 1])
+            {
+                if (!la.m_resident)
+                {
+                    if (!la.m_ctOps.empty() && !la.cuTreeRun(NULL, 0)) return false;
+                    if (x265cu_frame_set_array(la.m_ctx, fenc->slot, 6, l, d, fenc->lowresMvs[l][d - 1]))
+                    {
+                        snprintf(la.m_error, sizeof(la.m_error), "x265cu_frame_set_array: %s", x265cu_last_error(la.m_ctx));
+                        return false;
+                    }
+                    fenc->devMvVersion[l][d - 1] = fenc->mvVersion[l][d - 1];
+                }
+                la.m_ctStats[2]++;
+            }
+            usedVersion[l] = fenc->devMvVersion[l][d - 1];     /* what the kernel will really read */
         }
         const uint64_t costStamp = ++la.m_versionCounter;
         fenc->devCostStamp[d0][d1] = costStamp;                   /* ... and of lowresCosts[d0][d1] */

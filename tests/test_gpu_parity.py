@@ -24,7 +24,7 @@ def _replay(mods, name, max_events=None):
     replay, po, abi = mods
     res = replay.replay_trace(name, max_events=max_events)
     assert res["jobs"] > 0 and res["frames"] > 0
-    assert res["propagates"] > 0 and res["cutree"]["reuploads"] == 0     # cuTree steps replayed; no stale device mirror met
+    assert res["propagates"] > 0      # the cuTree steps of the trace were replayed (and compared) too
     assert not res["mismatches"], "%s: %d mismatches, first: %r" % (name, len(res["mismatches"]), res["mismatches"][:5])
     return res
 
