@@ -279,6 +279,37 @@ def multi_stream(torch, dist, world, trace, clip, device, nstreams, steps):
             "timing": "wall clock between device-wide synchronizes, max over ranks", "errors": errs}
 
 
+def pin_rank(local, nlocal):
+    """Several ranks share the box's host cores: give each rank its own share (whole cores: hyper-thread siblings stay
+    together), as a deployment with one encoder process per GPU would.  The library sizes its helper threads from
+    the affinity mask it finds."""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        groups, seen = [], set()
+        for c in cpus:
+            if c in seen:
+                continue
+            try:
+                sib = open("/sys/devices/system/cpu/cpu%d/topology/thread_siblings_list" % c).read().strip()
+                g = set()
+                for part in sib.split(","):
+                    lo, _, hi = part.partition("-")
+                    g |= set(range(int(lo), int(hi or lo) + 1))
+                g &= set(cpus)
+            except (OSError, ValueError):
+                g = {c}
+            g = g or {c}
+            seen |= g
+            groups.append(sorted(g))
+        per = len(groups) // nlocal
+        if per < 1:
+            return
+        mine = [c for g in groups[local * per:(local + 1) * per] for c in g]
+        os.sched_setaffinity(0, mine)
+    except (AttributeError, OSError):
+        pass
+
+
 def timed(torch, dist, world, fn, steps):
     """barrier + synchronize on both sides; CUDA events on the current (launching) stream; max over ranks"""
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -317,6 +348,8 @@ def main():
     if args.impl == "reference":
         return reference_arm(args, rank, world)
 
+    if world > 1 and env_int("X265CU_BENCH_PIN", 1):
+        pin_rank(local, env_int("LOCAL_WORLD_SIZE", world))
     import torch
     import torch.distributed as dist
     import __graft_entry__ as ge

@@ -17,6 +17,7 @@
 #include "x265cu_cutree.cuh"
 
 #include <cuda_runtime.h>
+#include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -141,7 +142,11 @@ namespace {
 unsigned hostThreads()
 {
     if (const char* e = getenv("X265CU_HOST_THREADS")) return (unsigned)atoi(e);
-    return std::thread::hardware_concurrency() / 4;
+    /* the cores this process may run on (a pinned rank sees its share, not the whole box) */
+    cpu_set_t set;
+    unsigned n = std::thread::hardware_concurrency();
+    if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) n = (unsigned)CPU_COUNT(&set);
+    return n >= 8 ? n / 4 : (n >= 2 ? 2 : 1);
 }
 
 #define CU_TRY(ctx, call)                                                                           \
