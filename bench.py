@@ -417,19 +417,31 @@ def main():
     res.la.stats_enable(False)
     int_peak = (abi.C.c_double(), abi.C.c_double())
     abi.lib_cu().x265cu_int_peak(res.la.ctx, abi.C.byref(int_peak[0]), abi.C.byref(int_peak[1]))
-    # SATD primitive throughput (HBM-bound kernel): all frame pairs (t, t+1) in one launch
+    # SATD primitive throughput (the HBM-bound kernel).  One launch reads every one of the 4 planes (full-pel + the three
+    # half-pel planes lowresMC reads) of every frame exactly ONCE: disjoint pairs (2t, 2t+1) per plane, so nothing is re-read
+    # inside a launch; the L2 is flushed before every timed launch (a 512 MB buffer is read), so every byte comes from HBM.
     satd = None
     try:
         import numpy as np
         slots = np.array([abi.lib_host().x265cuh_frame_slot(res.frames[t]) for t in range(nframes)], np.int32)
-        a, b = np.ascontiguousarray(np.tile(slots[:-1], 8)), np.ascontiguousarray(np.tile(slots[1:], 8))
+        ev, od = slots[0:nframes - 1:2], slots[1:nframes:2]
+        a = np.ascontiguousarray(np.concatenate([ev] * 4))
+        b = np.ascontiguousarray(np.concatenate([od] * 4))
+        pl = np.ascontiguousarray(np.repeat(np.arange(4, dtype=np.int32), len(ev)))
+        flush = torch.zeros(128 << 20, dtype=torch.int32, device="cuda")     # 512 MB
         msf = abi.C.c_float()
-        best = None
-        for _ in range(4):
-            abi.lib_cu().x265cu_pixelcmp_frames(res.la.ctx, 1, len(a), a.ctypes.data, b.ctypes.data, None, abi.C.byref(msf))
-            best = msf.value if best is None else min(best, msf.value)
+        times = []
+        for _ in range(7):
+            flush.sum()                   # a READ of 512 MB: the L2 ends up full of clean lines of another buffer (a write would
+            torch.cuda.synchronize()      # leave dirty lines whose write-back competes with the timed kernel's reads)
+            abi.lib_cu().x265cu_pixelcmp_planes(res.la.ctx, 1, len(a), a.ctypes.data, pl.ctypes.data, b.ctypes.data, pl.ctypes.data, None, abi.C.byref(msf))
+            times.append(msf.value)
+        del flush
+        med = sorted(times[2:])[len(times[2:]) // 2]
         pix = len(a) * res.la.nCU * 64
-        satd = {"gpix_per_s": pix / (best * 1e-3) / 1e9, "pairs": len(a), "ms": best}
+        satd = {"gpix_per_s": pix / (med * 1e-3) / 1e9, "pairs": len(a), "ms": med,
+                "method": "one launch over the 4 planes of all frames, every plane read once, L2 flushed before each of 5 timed launches (median)",
+                "bytes_per_launch": int(pix * 2 * (1 if cfg["depth"] == 8 else 2) + len(a) * res.la.nCU * 4)}
     except Exception as ex:  # pragma: no cover - reported, not fatal
         satd = {"error": str(ex)}
     ct_value = res.la.cutree_stats()
@@ -512,9 +524,7 @@ def main():
         roof_pix = hbm_peak / (2 * P + 4.0 / 64)     # GB/s / (bytes per pixel pair) = Gpix/s
         satd["roofline_gpix_per_s"] = roof_pix
         satd["frac"] = satd["gpix_per_s"] / roof_pix
-        if satd["frac"] > 0.9:
-            satd["note"] = "the distinct planes of this clip (%d MB) fit the 126 MB L2: the launch is partly L2-fed, not HBM-bound" % (
-                nframes * Np * P // (1 << 20))
+
 
     # ---- CPU baseline (reported, not the target): the reference's own lookahead on the host cores ----
     cpu_baseline = None

@@ -237,6 +237,10 @@ int x265cu_pixelcmp_batch(x265cu_ctx* ctx, int kind, const void* bufA, size_t sa
  * resident, ONE launch; out (host, may be NULL) gets nPairs * cuCount results.  Returns the
  * kernel's device time in milliseconds through *ms when ms != NULL (CUDA events on the ctx stream). */
 int x265cu_pixelcmp_frames(x265cu_ctx* ctx, int kind, int nPairs, const int* slotsA, const int* slotsB, int32_t* out, float* ms);
+/* the same with a plane index per operand (0 = full-pel, 1..3 = the H, V, C half-pel planes lowresMC reads,
+ * common/lowres.h:62-81); planesA / planesB may be NULL (plane 0) */
+int x265cu_pixelcmp_planes(x265cu_ctx* ctx, int kind, int nPairs, const int* slotsA, const int* planesA, const int* slotsB, const int* planesB,
+                           int32_t* out, float* ms);
 /* measured integer-issue peaks of this GPU in Gop/s (packed |a-b| accumulate = the SAD inner op;
  * plain 32-bit adds): the roofline the search/cost kernels are judged against */
 int x265cu_int_peak(x265cu_ctx* ctx, double* gopsVabsdiff4, double* gopsIadd);

@@ -73,7 +73,7 @@ ABI_SYMBOLS = (
     "x265cu_get_geometry", "x265cu_sync", "x265cu_host_register", "x265cu_host_unregister",
     "x265cu_frame_init", "x265cu_frame_set_invqscale", "x265cu_frame_var", "x265cu_frame_init_var", "x265cu_frame_init_var_batch",
     "x265cu_intra", "x265cu_intra_batch", "x265cu_pre_lookahead_batch",
-    "x265cu_weight_cost_batch", "x265cu_estimate_batch", "x265cu_pixelcmp_batch", "x265cu_pixelcmp_frames", "x265cu_int_peak",
+    "x265cu_weight_cost_batch", "x265cu_estimate_batch", "x265cu_pixelcmp_batch", "x265cu_pixelcmp_frames", "x265cu_pixelcmp_planes", "x265cu_int_peak",
     "x265cu_stats_enable", "x265cu_stats_get",
     "x265cu_cutree_run", "x265cu_frame_set_propagate", "x265cu_frame_set_array",
 )
@@ -104,6 +104,7 @@ def lib_cu():
         L.x265cu_pixelcmp_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_ssize_t, C.c_void_p, C.c_size_t, C.c_ssize_t,
                                             C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.x265cu_pixelcmp_frames.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+        L.x265cu_pixelcmp_planes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
         L.x265cu_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.x265cu_cutree_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(CutreeOp), C.c_int, C.c_void_p, C.c_void_p]
         L.x265cu_frame_set_propagate.argtypes = [C.c_void_p, C.c_int, C.c_void_p]

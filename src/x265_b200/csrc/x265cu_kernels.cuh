@@ -431,6 +431,69 @@ __global__ void __launch_bounds__(256) pixelcmp_batch_kernel(int kind, const P* 
     if (valid && sub == 0) out[idx] = result;
 }
 
+/* 8 samples of a row in one load (8 or 16 bytes), as the two 4-sample halves the 4x4 measures take */
+template <typename P> struct Wide8;
+template <> struct Wide8<uint8_t>
+{
+    static __device__ __forceinline__ void load(const uint8_t* p, Px<uint8_t>::Row4& a, Px<uint8_t>::Row4& b)
+    {
+        const uint2 w = __ldg((const uint2*)p);
+        a.v = w.x; b.v = w.y;
+    }
+};
+template <> struct Wide8<uint16_t>
+{
+    static __device__ __forceinline__ void load(const uint16_t* p, Px<uint16_t>::Row4& a, Px<uint16_t>::Row4& b)
+    {
+        const uint4 w = __ldg((const uint4*)p);
+        a.lo = w.x; a.hi = w.y; b.lo = w.z; b.hi = w.w;
+    }
+};
+
+/* SAD / SATD of every aligned 8x8 block of plane 0 of pairs of frames, wide form: a lane takes the upper or lower
+ * 8x4 half of a CU (two 4x4 blocks, one 8- or 16-byte load per row and plane), a warp 16 horizontally adjacent CUs
+ * per group and GROUPS groups at once, all loads of an iteration in flight before the first is consumed
+ * (8-bit, GROUPS = 2: 16 x 8 bytes per lane).  Half as many load instructions per sample as the quad form below and
+ * twice the bytes in flight per thread; the quad form stays for SA8D, whose 8x8 transform needs the quad layout. */
+template <typename P, int GROUPS>
+__global__ void __launch_bounds__(256) pixelcmp_frames_wide_kernel(int kind, const void* const* __restrict__ planes, GeomDev g, int* __restrict__ out)
+{
+    typedef typename Px<P>::Row4 Row4;
+    const P* A = (const P*)planes[2 * blockIdx.y];
+    const P* B = (const P*)planes[2 * blockIdx.y + 1];
+    out += (int64_t)blockIdx.y * g.nCU;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
+    const int c = lane >> 1, half = lane & 1;
+    for (int base = (blockIdx.x * nWarps + warp) * 16 * GROUPS; base < g.nCU; base += gridDim.x * nWarps * 16 * GROUPS)
+    {
+        Row4 fa[GROUPS][2][4], fb[GROUPS][2][4];
+#pragma unroll
+        for (int gi = 0; gi < GROUPS; gi++)
+        {
+            const int mb = base + gi * 16 + c;
+            const int valid = mb < g.nCU;
+            const int cuX = valid ? mb % g.wCU : 0, cuY = valid ? mb / g.wCU : 0;
+            const int64_t off = (int64_t)(8 * cuY + 4 * half) * g.stride + 8 * cuX;
+#pragma unroll
+            for (int y = 0; y < 4; y++)
+            {
+                Wide8<P>::load(A + off + (int64_t)y * g.stride, fa[gi][0][y], fa[gi][1][y]);
+                Wide8<P>::load(B + off + (int64_t)y * g.stride, fb[gi][0][y], fb[gi][1][y]);
+            }
+        }
+#pragma unroll
+        for (int gi = 0; gi < GROUPS; gi++)
+        {
+            const int mb = base + gi * 16 + c;
+            int v = kind == 0 ? sad4x4<P>(fa[gi][0], fb[gi][0]) + sad4x4<P>(fa[gi][1], fb[gi][1])
+                              : satd4x4_abs<P>(fa[gi][0], fb[gi][0]) + satd4x4_abs<P>(fa[gi][1], fb[gi][1]);
+            v += __shfl_xor_sync(FULL_MASK, v, 1);
+            if (kind == 1) v >>= 1;
+            if (mb < g.nCU && half == 0) out[mb] = v;
+        }
+    }
+}
+
 /* every aligned 8x8 block of plane 0 of pairs of frames (the HBM-bound "SATD Gpix/s" kernel):
  * a warp covers 8 horizontally adjacent CUs, so each load instruction touches full 32-byte sectors.
  * grid = (blocks, pairs); planes[2 * pair], planes[2 * pair + 1] = sample (0,0) of the two planes. */

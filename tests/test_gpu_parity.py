@@ -153,3 +153,51 @@ def test_bad_arguments_fail_loudly(mods):
         assert b"bad job" in L.x265cu_last_error(la.ctx)
     finally:
         la.close()
+
+
+@pytest.mark.parametrize("wide", ["0", "1", "2"])
+@pytest.mark.parametrize("name", ["odd8", "tiny10"])
+def test_pixelcmp_frames(mods, monkeypatch, name, wide):
+    """the device-resident whole-frame form of the primitives (the "SATD Gpix/s" kernel of the bench): SAD / SATD / SA8D
+    of every aligned 8x8 block of frame pairs, all three kernel forms (quad, wide x1, wide x2), odd CU counts (odd8:
+    23 x 13 CUs), against the oracle on the planes the GPU itself produced (those are CRC-checked by the replay)"""
+    replay, po, abi = mods
+    monkeypatch.setenv("X265CU_PIXELCMP_WIDE", wide)
+    t = po.Trace(replay.trace_path(name))
+    r = replay.CuReplay(t, check=False)
+    try:
+        r.run(max_events=6)
+        la, L = r.la, abi.lib_cu()
+        la.sync()
+        pocs = sorted(r.frames)[:4]
+        lib = po.oracle(t.cfg["depth"])
+        dt = po.pixel_dtype(t.cfg["depth"])
+        planes = {p: la.array(r.frames[p], 0, dtype=dt).copy() for p in pocs}
+        slots = {p: abi.lib_host().x265cuh_frame_slot(r.frames[p]) for p in pocs}
+        pairs = [(pocs[0], pocs[1]), (pocs[2], pocs[1]), (pocs[3], pocs[3]), (pocs[0], pocs[3])]
+        a = np.array([slots[x] for x, _ in pairs], np.int32)
+        b = np.array([slots[y] for _, y in pairs], np.int32)
+        pad = la.padOffset
+        for kind, fn in ((0, "ola_sad8x8"), (1, "ola_satd8x8"), (2, "ola_sa8d8x8")):
+            out = np.zeros(len(pairs) * la.nCU, np.int32)
+            assert L.x265cu_pixelcmp_frames(la.ctx, kind, len(pairs), a.ctypes.data, b.ctypes.data, out.ctypes.data, None) == 0
+            for k, (x, y) in enumerate(pairs):
+                pa, pb = planes[x], planes[y]
+                want = np.array([getattr(lib, fn)(pa.ctypes.data + (pad + 8 * (cu // la.wCU) * la.stride + 8 * (cu % la.wCU)) * pa.itemsize, la.stride,
+                                                  pb.ctypes.data + (pad + 8 * (cu // la.wCU) * la.stride + 8 * (cu % la.wCU)) * pb.itemsize, la.stride)
+                                 for cu in range(la.nCU)], np.int32)
+                got = out[k * la.nCU:(k + 1) * la.nCU]
+                assert np.array_equal(got, want), (name, wide, kind, k, np.flatnonzero(got != want)[:6])
+        # plane selection: half-pel planes H (1) against C (3) of the first pair
+        pA, pB = np.array([1], np.int32), np.array([3], np.int32)
+        out = np.zeros(la.nCU, np.int32)
+        assert L.x265cu_pixelcmp_planes(la.ctx, 1, 1, a.ctypes.data, pA.ctypes.data, b.ctypes.data, pB.ctypes.data, out.ctypes.data, None) == 0
+        x, y = pairs[0]
+        offA, offB = la.planeSize * 1, la.planeSize * 3
+        want = np.array([lib.ola_satd8x8(planes[x].ctypes.data + (offA + pad + 8 * (cu // la.wCU) * la.stride + 8 * (cu % la.wCU)) * planes[x].itemsize, la.stride,
+                                         planes[y].ctypes.data + (offB + pad + 8 * (cu // la.wCU) * la.stride + 8 * (cu % la.wCU)) * planes[y].itemsize, la.stride)
+                         for cu in range(la.nCU)], np.int32)
+        assert np.array_equal(out, want), (name, wide, "planes")
+        assert L.x265cu_pixelcmp_planes(la.ctx, 1, 1, a.ctypes.data, np.array([4], np.int32).ctypes.data, b.ctypes.data, None, None, None) == -1
+    finally:
+        r.close()
