@@ -1720,6 +1720,7 @@ int x265cu_pixelcmp_planes(x265cu_ctx* c, int kind, int nPairs, const int* slots
     const int cusPerWarp = wide ? 16 * wide : 8;
     int bx = ((g.nCU + cusPerWarp - 1) / cusPerWarp + 7) / 8;
     if (bx > 148 * 4) bx = 148 * 4;
+    if (const char* e = getenv("X265CU_PIXELCMP_BX")) { int v = atoi(e); if (v >= 1 && v < bx) bx = v; }   /* experiments: fewer, looping CTAs */
     if (bx < 1) bx = 1;
     dim3 grid(bx, nPairs);
     const void* const* dPl = (const void* const*)(c->dGeneric + outBytes);
