@@ -1720,7 +1720,11 @@ int x265cu_pixelcmp_planes(x265cu_ctx* c, int kind, int nPairs, const int* slots
     const int cusPerWarp = wide ? 16 * wide : 8;
     int bx = ((g.nCU + cusPerWarp - 1) / cusPerWarp + 7) / 8;
     if (bx > 148 * 4) bx = 148 * 4;
-    if (const char* e = getenv("X265CU_PIXELCMP_BX")) { int v = atoi(e); if (v >= 1 && v < bx) bx = v; }   /* experiments: fewer, looping CTAs */
+    /* wide form, 8-bit samples: at most 32 CTAs per pair, their warps loop over the rest of the plane (measured cold at 4K,
+     * fraction of the HBM roofline: 254 CTAs per pair 0.75, 32: 0.82, 16: 0.80, 8: 0.73, 4: 0.59; at 16 bit, where a warp
+     * moves twice the bytes, the full grid measured better: 0.94 against 0.89 -- profiles/README.md) */
+    if (wide && c->pb == 1 && bx > 32) bx = 32;
+    if (const char* e = getenv("X265CU_PIXELCMP_BX")) { int v = atoi(e); if (v >= 1 && v < bx) bx = v; }   /* experiments */
     if (bx < 1) bx = 1;
     dim3 grid(bx, nPairs);
     const void* const* dPl = (const void* const*)(c->dGeneric + outBytes);

@@ -155,14 +155,16 @@ def test_bad_arguments_fail_loudly(mods):
         la.close()
 
 
-@pytest.mark.parametrize("wide", ["0", "1", "2"])
+@pytest.mark.parametrize("wide", ["0", "1", "2", "1 looping"])
 @pytest.mark.parametrize("name", ["odd8", "tiny10"])
 def test_pixelcmp_frames(mods, monkeypatch, name, wide):
     """the device-resident whole-frame form of the primitives (the "SATD Gpix/s" kernel of the bench): SAD / SATD / SA8D
     of every aligned 8x8 block of frame pairs, all three kernel forms (quad, wide x1, wide x2), odd CU counts (odd8:
     23 x 13 CUs), against the oracle on the planes the GPU itself produced (those are CRC-checked by the replay)"""
     replay, po, abi = mods
-    monkeypatch.setenv("X265CU_PIXELCMP_WIDE", wide)
+    monkeypatch.setenv("X265CU_PIXELCMP_WIDE", wide.split()[0])
+    if "looping" in wide:
+        monkeypatch.setenv("X265CU_PIXELCMP_BX", "1")      # one CTA per pair: its warps loop over the whole plane
     t = po.Trace(replay.trace_path(name))
     r = replay.CuReplay(t, check=False)
     try:
