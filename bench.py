@@ -177,6 +177,7 @@ class Runner:
         # pre-marshal the call sequence
         import ctypes as C
         cutree = env_int("X265CU_BENCH_CUTREE", 1) != 0
+        self.prefetch = env_int("X265CU_BENCH_PREFETCH", 0) != 0
         self.npropagate = 0
         self.calls = []
         for e in trace.events:
@@ -213,6 +214,11 @@ class Runner:
         self.calls = [("T", la.prepare_cutree_sequence(c[1])) if c[0] == "T" else c for c in self.calls]
         self.calls = [("P", c[1], la.prepare_pre_lookahead_batch([(self.frames[t],) + tuple(self.inputs[t]) + (t,) for t in c[1]])) if c[0] == "P" else c
                       for c in self.calls]
+        # each P call also carries the prepared list that follows it (None for the last)
+        pidx = [i for i, c in enumerate(self.calls) if c[0] == "P"]
+        for k, i in enumerate(pidx):
+            nxt = self.calls[pidx[k + 1]][2] if k + 1 < len(pidx) else None
+            self.calls[i] = self.calls[i] + (nxt,)
         self.units = sum(j["s0"] + j["s1"] for j in trace.jobs())
         self.njobs = sum(1 for _ in trace.jobs())
 
@@ -221,6 +227,12 @@ class Runner:
         for c in self.calls:
             if c[0] == "P":
                 la.pre_lookahead_batch_prepared(c[2], True)
+                # X265CU_BENCH_PREFETCH=1: the pictures of the NEXT list arrive in the input queue while this one's slicetypeDecide
+                # runs (Lookahead::addPicture) and their uploads start now.  Off by default: measured 31.9 ms against 31.4 ms per
+                # step -- the bulk uploads share the host-to-device copy engine with the small argument uploads of the estimate
+                # batches, which then wait behind them on the critical path.
+                if self.prefetch and c[3] is not None and not self.resident:
+                    la.add_pictures_prepared(c[3])
             elif c[0] == "E":
                 la.estimate_prepared(c[1], c[2])
             else:

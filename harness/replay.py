@@ -111,7 +111,12 @@ class CuReplay:
         if len(es) == 1:
             self.la.pre_lookahead(items[0][0], keep[0][0], keep[0][1], keep[0][2], es[0]["poc"], self.planes_back)
         else:
-            self.la.pre_lookahead_batch_prepared(self.la.prepare_pre_lookahead_batch(items), self.planes_back)
+            prep = self.la.prepare_pre_lookahead_batch(items)
+            # Lookahead::addPicture for every other frame of the list: the pre-lookahead must take pictures uploaded ahead
+            # and pictures it uploads itself side by side
+            ahead = self.la.prepare_pre_lookahead_batch(items[::2])
+            self.la.add_pictures_prepared(ahead)
+            self.la.pre_lookahead_batch_prepared(prep, self.planes_back)
         if not self.check:
             return
         for e, it in zip(es, items):

@@ -131,6 +131,13 @@ typedef struct x265cu_frame_in
 } x265cu_frame_in;
 int x265cu_frame_init_var_batch(x265cu_ctx* ctx, int n, const x265cu_frame_in* items);
 
+/* ---- Lookahead::addPicture (slicetype.cpp:633-650): a picture has arrived in the lookahead's input queue.  Optional.
+ * Starts the upload of the picture into a staging area of the slot (asynchronous, on the upload stream) and returns;
+ * the pre-lookahead of the frame (x265cu_pre_lookahead_batch / x265cu_frame_init_var_batch with the same pointers and
+ * strides for this slot) then finds the picture on the device instead of uploading it while the GPU waits.  The
+ * picture must not change between this call and that pre-lookahead; the next initialisation of the slot consumes it. */
+int x265cu_frame_upload(x265cu_ctx* ctx, int slot, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride);
+
 /* ---- the whole of PreLookaheadGroup::processTasks for its list (slicetype.cpp:831-856) as ONE pipelined call:
  * x265cu_frame_init_var_batch, the host's float AQ mapping and x265cu_intra_batch, a few frames at a time.  As soon
  * as the energies/sums of frames [first, first + count) are on the host, `aq(user, first, count, invQscale)` is

@@ -72,7 +72,7 @@ ABI_SYMBOLS = (
     "x265cu_abi_version", "x265cu_device_count", "x265cu_open", "x265cu_close", "x265cu_last_error",
     "x265cu_get_geometry", "x265cu_sync", "x265cu_host_register", "x265cu_host_unregister",
     "x265cu_frame_init", "x265cu_frame_set_invqscale", "x265cu_frame_var", "x265cu_frame_init_var", "x265cu_frame_init_var_batch",
-    "x265cu_intra", "x265cu_intra_batch", "x265cu_pre_lookahead_batch",
+    "x265cu_intra", "x265cu_intra_batch", "x265cu_pre_lookahead_batch", "x265cu_frame_upload",
     "x265cu_weight_cost_batch", "x265cu_estimate_batch", "x265cu_pixelcmp_batch", "x265cu_pixelcmp_frames", "x265cu_pixelcmp_planes", "x265cu_int_peak",
     "x265cu_stats_enable", "x265cu_stats_get",
     "x265cu_cutree_run", "x265cu_frame_set_propagate", "x265cu_frame_set_array",
@@ -136,6 +136,7 @@ def lib_host():
         L.x265cuh_frame_free.argtypes = [C.c_void_p, C.c_void_p]
         L.x265cuh_pre_lookahead.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int]
         L.x265cuh_pre_lookahead_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_int]
+        L.x265cuh_add_pictures.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6
         L.x265cuh_estimate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.x265cuh_array.restype = C.c_void_p
         L.x265cuh_array.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
@@ -220,6 +221,12 @@ class Lookahead:
         n, fr, y, ys, u, v, cs, pocs = prep
         if self.L.x265cuh_pre_lookahead_batch(self.h, n, fr, y, ys, u, v, cs, pocs, 1 if planes_back else 0):
             raise RuntimeError("pre_lookahead_batch failed: " + self.error())
+
+    def add_pictures_prepared(self, prep):
+        """Lookahead::addPicture for the frames of a prepared list: their uploads start now (asynchronous)"""
+        n, fr, y, ys, u, v, cs, _pocs = prep
+        if self.L.x265cuh_add_pictures(self.h, n, fr, y, ys, u, v, cs):
+            raise RuntimeError("addPicture failed: " + self.error())
 
     def pre_lookahead_ptr(self, frame, y, ys, u, v, cs, poc, planes_back):
         """raw-pointer form (host or, in resident mode, device addresses)"""

@@ -97,6 +97,9 @@ struct x265cu_ctx
     uint8_t* dUp; size_t dUpCap;           /* per-frame staging of a batched pre-lookahead list */
     cudaStream_t upStream;                 /* its uploads */
     cudaStream_t intraStream;              /* x265cu_pre_lookahead_batch: intra estimates run beside the uploads of later frames */
+    /* x265cu_frame_upload: a picture uploaded ahead of its pre-lookahead, per slot */
+    struct SlotUpload { const void* y; const void* u; const void* v; intptr_t ys, cs; uint8_t* d; size_t cap; cudaEvent_t done, read; bool valid, everRead; };
+    std::vector<SlotUpload> slotUp;
     std::vector<cudaEvent_t> preEvents;    /* per frame of the list: lowres planes + energies/sums done */
     std::vector<cudaEvent_t> upEvents;
     int64_t srcPitch;      /* samples */
@@ -278,6 +281,12 @@ void freeAll(x265cu_ctx* c)
     cudaFree(c->dLut); cudaFree(c->dSrc); cudaFree(c->dSmall); cudaFree(c->dStage); cudaFree(c->dArgs); cudaFree(c->dGeneric); cudaFree(c->dMemo); cudaFree(c->dSrcLin); cudaFree(c->dUp); cudaFree(c->dPre);
     if (c->upStream) cudaStreamDestroy(c->upStream);
     if (c->intraStream) cudaStreamDestroy(c->intraStream);
+    for (size_t i = 0; i < c->slotUp.size(); i++)
+    {
+        cudaFree(c->slotUp[i].d);
+        if (c->slotUp[i].done) cudaEventDestroy(c->slotUp[i].done);
+        if (c->slotUp[i].read) cudaEventDestroy(c->slotUp[i].read);
+    }
     for (size_t i = 0; i < c->preEvents.size(); i++) cudaEventDestroy(c->preEvents[i]);
     for (size_t i = 0; i < c->upEvents.size(); i++) cudaEventDestroy(c->upEvents[i]);
     if (c->hStage) cudaFreeHost(c->hStage);
@@ -396,6 +405,11 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     c->planesPending.assign(cfg->numFrameSlots, 0);
     c->planesReady.assign(cfg->numFrameSlots, (cudaEvent_t)NULL);
     c->deferPlanes = false;
+    {
+        x265cu_ctx::SlotUpload z;
+        memset(&z, 0, sizeof(z));
+        c->slotUp.assign(cfg->numFrameSlots, z);
+    }
     for (int i = 0; i < cfg->numFrameSlots; i++)
         OPEN_TRY(cudaEventCreateWithFlags(&c->planesReady[i], cudaEventDisableTiming));
     for (int i = 0; i < cfg->numFrameSlots; i++)
@@ -674,6 +688,7 @@ static int frameInitImpl(x265cu_ctx* c, int slot, const void* luma, intptr_t src
     std::lock_guard<std::mutex> lk(c->mtx);
     CU_TRY(c, cudaSetDevice(c->cfg.device));
     unsigned long long hs[6] = { 0, 0, 0, 0, 0, 0 };
+    if (!badSlot(c, slot)) c->slotUp[slot].valid = false;      /* this initialisation supersedes a picture uploaded ahead */
     int r = frameInitEnqueue(c, slot, luma, srcStride, lumaIsDevice, planesOut, u, v, cStride, varEnergy, hs);
     if (r) return r;
     /* the caller may reuse its picture buffers as soon as we return */
@@ -684,6 +699,41 @@ static int frameInitImpl(x265cu_ctx* c, int slot, const void* luma, intptr_t src
 
 /* PreLookaheadGroup::processTasks hands a LIST of frames to the workers (slicetype.cpp:831-856): all uploads and
  * kernels of the list are enqueued back to back and the host waits once */
+int x265cu_frame_upload(x265cu_ctx* c, int slot, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride)
+{
+    if (!c || badSlot(c, slot) || !y || !u || !v) return c ? fail(c, X265CU_EINVAL, "x265cu_frame_upload: bad argument") : X265CU_EINVAL;
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CU_TRY(c, cudaSetDevice(c->cfg.device));
+    const GeomDev& g = c->g;
+    if ((((size_t)yStride * c->pb) & 7) || yStride < 2 * g.width + 1)
+        return X265CU_OK;                       /* a pitch the linear transfer cannot take: the pre-lookahead uploads as usual */
+    const int bxN = (c->cfg.srcWidth + 15) / 16, byN = (c->cfg.srcHeight + 15) / 16;
+    const size_t lumaRows = (size_t)2 * g.lines + 1, chromaRows = (size_t)byN * 8;
+    const size_t yLin = (lumaRows - 1) * (size_t)yStride * c->pb + (size_t)(2 * g.width + 1) * c->pb;
+    const size_t cLin = (chromaRows - 1) * (size_t)cStride * c->pb + (size_t)bxN * 8 * c->pb;
+    const size_t need = alignUp(yLin, 256) + 2 * alignUp(cLin, 256) + 256;
+    x265cu_ctx::SlotUpload& su = c->slotUp[slot];
+    if (!c->upStream) CU_TRY(c, cudaStreamCreateWithFlags(&c->upStream, cudaStreamNonBlocking));
+    if (!su.done) { CU_TRY(c, cudaEventCreateWithFlags(&su.done, cudaEventDisableTiming)); CU_TRY(c, cudaEventCreateWithFlags(&su.read, cudaEventDisableTiming)); }
+    if (su.cap < need)
+    {
+        if (su.d) { CU_TRY(c, cudaStreamSynchronize(c->stream)); CU_TRY(c, cudaStreamSynchronize(c->upStream)); cudaFree(su.d); su.d = NULL; su.cap = 0; }
+        CU_TRY(c, cudaMalloc((void**)&su.d, need));
+        su.cap = need;
+        su.everRead = false;
+    }
+    /* the kernels that read the slot's previous picture from this area must be done with it */
+    if (su.everRead) CU_TRY(c, cudaStreamWaitEvent(c->upStream, su.read, 0));
+    uint8_t* dY = su.d; uint8_t* dU = dY + alignUp(yLin, 256); uint8_t* dV = dU + alignUp(cLin, 256);
+    CU_TRY(c, cudaMemcpyAsync(dY, y, yLin, cudaMemcpyHostToDevice, c->upStream));
+    CU_TRY(c, cudaMemcpyAsync(dU, u, cLin, cudaMemcpyHostToDevice, c->upStream));
+    CU_TRY(c, cudaMemcpyAsync(dV, v, cLin, cudaMemcpyHostToDevice, c->upStream));
+    CU_TRY(c, cudaEventRecord(su.done, c->upStream));
+    c->stats.h2dBytes += (int64_t)(yLin + 2 * cLin);
+    su.y = y; su.u = u; su.v = v; su.ys = yStride; su.cs = cStride; su.valid = true;
+    return X265CU_OK;
+}
+
 static int preBatchImpl(x265cu_ctx* c, int n, const x265cu_frame_in* items, x265cu_aq_fn aq, void* user, x265cu_intra_out* outs);
 static int intraEnqueue(x265cu_ctx* c, int slot, x265cu_intra_out* out, unsigned long long* sums, unsigned long long* dBatchSums, cudaStream_t st);
 
@@ -766,6 +816,9 @@ static int preBatchImpl2(x265cu_ctx* c, int n, const x265cu_frame_in* items, x26
             const x265cu_frame_in& f = items[i];
             const size_t yLin = (lumaRows - 1) * (size_t)f.yStride * c->pb + (size_t)(2 * g.width + 1) * c->pb;
             const size_t cLin = (chromaRows - 1) * (size_t)f.cStride * c->pb + (size_t)bxN * 8 * c->pb;
+            const x265cu_ctx::SlotUpload& su = c->slotUp[f.slot];
+            if (su.valid && su.y == f.y && su.u == f.u && su.v == f.v && su.ys == f.yStride && su.cs == f.cStride)
+                continue;                       /* uploaded ahead by x265cu_frame_upload */
             uint8_t* dY = c->dUp + off[i]; uint8_t* dU = dY + alignUp(yLin, 256); uint8_t* dV = dU + alignUp(cLin, 256);
             CU_TRY(c, cudaMemcpyAsync(dY, f.y, yLin, cudaMemcpyHostToDevice, c->upStream));
             CU_TRY(c, cudaMemcpyAsync(dU, f.u, cLin, cudaMemcpyHostToDevice, c->upStream));
@@ -779,18 +832,35 @@ static int preBatchImpl2(x265cu_ctx* c, int n, const x265cu_frame_in* items, x26
     {
         const x265cu_frame_in& f = items[i];
         Uploaded up;
+        bool staged = false;
         if (pipelined)
         {
             const size_t yLin = (lumaRows - 1) * (size_t)f.yStride * c->pb + (size_t)(2 * g.width + 1) * c->pb;
             const size_t cLin = (chromaRows - 1) * (size_t)f.cStride * c->pb + (size_t)bxN * 8 * c->pb;
-            up.y = c->dUp + off[i]; up.u = up.y + alignUp(yLin, 256); up.v = up.u + alignUp(cLin, 256);
-            CU_TRY(c, cudaStreamWaitEvent(c->stream, c->upEvents[i], 0));
+            x265cu_ctx::SlotUpload& su = c->slotUp[f.slot];
+            staged = su.valid && su.y == f.y && su.u == f.u && su.v == f.v && su.ys == f.yStride && su.cs == f.cStride;
+            if (staged)
+            {
+                up.y = su.d; up.u = up.y + alignUp(yLin, 256); up.v = up.u + alignUp(cLin, 256);
+                CU_TRY(c, cudaStreamWaitEvent(c->stream, su.done, 0));
+            }
+            else
+            {
+                up.y = c->dUp + off[i]; up.u = up.y + alignUp(yLin, 256); up.v = up.u + alignUp(cLin, 256);
+                CU_TRY(c, cudaStreamWaitEvent(c->stream, c->upEvents[i], 0));
+            }
         }
         BatchOut bo = { (unsigned int*)(c->dPre + (size_t)i * per), (unsigned long long*)(c->dPre + (size_t)i * per + eBytes) };
         int r = frameInitEnqueue(c, f.slot, f.y, f.yStride, f.planesAreDevice, f.planesOut, f.u, f.v, f.cStride,
                                  (uint32_t*)(c->hPre + (size_t)i * per), (unsigned long long*)(c->hPre + (size_t)i * per + eBytes),
                                  pipelined ? &up : NULL, &bo);
         if (r) { cudaStreamSynchronize(c->stream); if (c->upStream) cudaStreamSynchronize(c->upStream); return r; }
+        c->slotUp[f.slot].valid = false;        /* consumed (or superseded by this initialisation) */
+        if (staged)
+        {
+            CU_TRY(c, cudaEventRecord(c->slotUp[f.slot].read, c->stream));
+            c->slotUp[f.slot].everRead = true;
+        }
         if (aq)
         {
             /* this frame's record comes back on its own, and an event tells the host (and the intra stream) it is done */

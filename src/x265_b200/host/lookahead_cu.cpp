@@ -225,6 +225,9 @@ void Lookahead::freeLowres(Lowres* l)
 {
     if (!l) return;
     forgetFrame(l);
+    /* copies into this frame's arrays may still be queued or in flight (plane copy-backs run behind the compute stream and
+     * those of a pre-lookahead list are held back until the next estimate batch): let them land before the memory goes */
+    if (m_ctx) x265cu_sync(m_ctx);
     m_freeSlots.push_back(l->slot);
     x265cu_host_unregister(l->arena);
     free(l->arena);
@@ -428,6 +431,16 @@ bool Lookahead::preLookahead(Lowres& l, const void* y, intptr_t yStride, const v
     l.ready = true;
     m_byPoc[poc] = &l;
     m_newestReady++;
+    return true;
+}
+
+/* Lookahead::addPicture, encoder/slicetype.cpp:633-650: start the picture's upload when it enters the input queue */
+bool Lookahead::addPicture(Lowres& l, const PictureIn& pic)
+{
+    if (m_resident || !pic.y || !pic.u || !pic.v) return true;      /* nothing to upload ahead */
+    if (getenv("X265CU_PREFETCH") && atoi(getenv("X265CU_PREFETCH")) == 0) return true;
+    int r = x265cu_frame_upload(m_ctx, l.slot, pic.y, pic.yStride, pic.u, pic.v, pic.cStride);
+    if (r) { snprintf(m_error, sizeof(m_error), "x265cu_frame_upload: %s", x265cu_last_error(m_ctx)); return false; }
     return true;
 }
 
@@ -1184,6 +1197,17 @@ void x265cuh_frame_free(void* la, void* f) { ((Lookahead*)la)->freeLowres((Lowre
 int x265cuh_pre_lookahead(void* la, void* frame, const void* y, intptr_t ys, const void* u, const void* v, intptr_t cs, int poc, int planesBack)
 {
     return ((Lookahead*)la)->preLookahead(*(Lowres*)frame, y, ys, u, v, cs, poc, planesBack != 0) ? 0 : -1;
+}
+
+int x265cuh_add_pictures(void* la, int n, void** frames, const void* const* y, const intptr_t* ys, const void* const* u, const void* const* v,
+                         const intptr_t* cs)
+{
+    for (int i = 0; i < n; i++)
+    {
+        Lookahead::PictureIn p = { y[i], ys[i], u[i], v[i], cs[i], 0 };
+        if (!((Lookahead*)la)->addPicture(*(Lowres*)frames[i], p)) return -1;
+    }
+    return 0;
 }
 
 int x265cuh_pre_lookahead_batch(void* la, int n, void** frames, const void* const* y, const intptr_t* ys, const void* const* u, const void* const* v,

@@ -172,6 +172,9 @@ public:
     /* PreLookaheadGroup::processTasks for a list of frames: one wait per stage instead of two per frame */
     struct PictureIn { const void* y; intptr_t yStride; const void* u; const void* v; intptr_t cStride; int poc; };
     bool preLookaheadBatch(int n, Lowres** frames, const PictureIn* pics, bool copyPlanesBack);
+    /* Lookahead::addPicture (slicetype.cpp:633-650): the picture has arrived in the input queue; its upload starts now
+     * (asynchronous) instead of when its pre-lookahead runs.  Optional; the picture must not change until then. */
+    bool addPicture(Lowres& l, const PictureIn& pic);
 
     /* ---- cuTree propagation.  The three calls replace, one to one, what Lookahead::cuTree does
      * to Lowres::propagateCost: its memsets (slicetype.cpp:1668-1701), estimateCUPropagate (:1741-1839) and
@@ -245,6 +248,8 @@ void  x265cuh_frame_free(void* la, void* frame);
 int   x265cuh_pre_lookahead(void* la, void* frame, const void* y, intptr_t ys, const void* u, const void* v, intptr_t cs, int poc, int planesBack);
 int   x265cuh_pre_lookahead_batch(void* la, int n, void** frames, const void* const* y, const intptr_t* ys, const void* const* u, const void* const* v,
                                   const intptr_t* cs, const int* pocs, int planesBack);
+int   x265cuh_add_pictures(void* la, int n, void** frames, const void* const* y, const intptr_t* ys, const void* const* u, const void* const* v,
+                           const intptr_t* cs);
 /* jobs: n triples (p0, p1, b) as indices into frames[]; batch != 0 -> add()+finishBatch(), else singleCost() each */
 int   x265cuh_estimate(void* la, void** frames, int nframes, const int* triples, int n, int batch, int64_t* scores);
 /* cuTree: the three calls of x265cu::Lookahead (frames[] indexed like the reference's: p0, p1, b) */
