@@ -7,10 +7,14 @@
  *   intraCost   [slot][nCU] i32      intraMode [slot][nCU] u8      invQ [slot][nCU] i32
  *   lowresCosts [slot][bf+2][bf+2][nCU] u16         rowSatds [slot][bf+2][bf+2][hCU] i32
  *   mvs         [slot][2][bf+1][nCU] (int16 x, int16 y)      mvCosts [slot][2][bf+1][nCU] i32
+ *   propagate   [slot][nCU] u64                     cuTree accumulators (x265cu_cutree.cuh)
  *   wplanes     pool of weighted 4-plane copies (one per weighted job of a batch)
- * Results of a batch are also written to one packed device record per job and reach the host in a
- * single device->host copy into pinned staging, from where they are scattered to the caller's
- * Lowres arrays.
+ * Results of a batch are also written to one packed device record per job.  From there each array goes straight
+ * into the caller's Lowres array when that lies in mapped pinned memory (x265cu_host_register: scatter_results_kernel
+ * writes it over PCIe), otherwise through one device->host copy into pinned staging and a host memcpy; the 32-byte
+ * sums of every job always come back by copy.
+ * Streams: the ctx's compute stream; an upload stream (pictures of a pre-lookahead list / x265cu_frame_upload); an
+ * intra stream (intra estimates of a list beside the uploads of its later frames); a copy stream (plane copy-backs).
  */
 #include "../../../include/x265cu.h"
 #include "x265cu_kernels.cuh"
