@@ -1791,6 +1791,8 @@ int x265cu_pixelcmp_planes(x265cu_ctx* c, int kind, int nPairs, const int* slots
      * the HBM roofline at 8 bit against 0.65 for the quad form), 2 = two groups, 0 = the quad form, which SA8D always takes) */
     int wide = kind < 2 ? 1 : 0;
     if (const char* e = getenv("X265CU_PIXELCMP_WIDE")) { int v = atoi(e); if (kind < 2 && v >= 0 && v <= 2) wide = v; }
+    /* its 8-sample loads need planes whose rows start on 8-sample boundaries (true for every x265 margin: CTU + 32) */
+    if ((g.padOffset & 7) || (g.stride & 7) || (g.planeSize & 7)) wide = 0;
     const int cusPerWarp = wide ? 16 * wide : 8;
     int bx = ((g.nCU + cusPerWarp - 1) / cusPerWarp + 7) / 8;
     if (bx > 148 * 4) bx = 148 * 4;
