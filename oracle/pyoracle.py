@@ -90,6 +90,8 @@ def oracle(depth=8, emul=False):
     L.ola_weight_cost_luma.argtypes = [C.c_void_p, C.POINTER(Frame), C.POINTER(Frame), C.POINTER(Weight)]
     for n in ("ola_sad8x8", "ola_satd8x8", "ola_satd4x4", "ola_sa8d8x8", "ola_sa8d16x16"):
         getattr(L, n).argtypes = [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t]
+    for n in ("ola_pu_sad", "ola_pu_satd"):
+        getattr(L, n).argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t]
     L.ola_pixelavg8x8.argtypes = [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t]
     L.ola_frame_init_lowres.argtypes = [C.c_void_p] * 5 + [C.c_ssize_t, C.c_ssize_t, C.c_int, C.c_int]
     L.ola_extend_border.argtypes = [C.c_void_p, C.c_ssize_t] + [C.c_int] * 4
@@ -125,6 +127,8 @@ def ref(depth=8):
     L.x265ref_setup()
     for n in ("x265ref_sad8x8", "x265ref_satd8x8", "x265ref_sa8d8x8", "x265ref_sa8d16x16"):
         getattr(L, n).argtypes = [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t]
+    for n in ("x265ref_pu_sad", "x265ref_pu_satd"):
+        getattr(L, n).argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t]
     L.x265ref_sad_x3_8x8.argtypes = [C.c_void_p] * 4 + [C.c_ssize_t, C.c_void_p]
     L.x265ref_sad_x4_8x8.argtypes = [C.c_void_p] * 5 + [C.c_ssize_t, C.c_void_p]
     L.x265ref_pixelavg8x8.argtypes = [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t]

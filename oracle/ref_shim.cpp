@@ -278,6 +278,9 @@ void x265ref_weight_pp(const pixel* src, pixel* dst, intptr_t stride, int w, int
 { primitives.weight_pp(src, dst, stride, w, h, w0, round, shift, offset); }
 uint64_t x265ref_var16(const pixel* p, intptr_t s) { return primitives.cu[BLOCK_16x16].var(p, s); }
 uint64_t x265ref_var8(const pixel* p, intptr_t s) { return primitives.cu[BLOCK_8x8].var(p, s); }
+/* pu[partitionFromSizes(w, h)].sad / .satd: the 25 luma PU shapes */
+int x265ref_pu_sad(int w, int h, const pixel* a, intptr_t sa, const pixel* b, intptr_t sb) { return primitives.pu[partitionFromSizes(w, h)].sad(a, sa, b, sb); }
+int x265ref_pu_satd(int w, int h, const pixel* a, intptr_t sa, const pixel* b, intptr_t sb) { return primitives.pu[partitionFromSizes(w, h)].satd(a, sa, b, sb); }
 void x265ref_propagate_cost(int* dst, const uint16_t* pin, const int32_t* intra, const uint16_t* inter, const int32_t* invq, const double* fps, int len)
 { primitives.propagateCost(dst, pin, intra, inter, invq, fps, len); }
 

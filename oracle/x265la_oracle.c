@@ -1298,3 +1298,31 @@ void ola_cutree_finish(ola_frame* f, double averageDuration, int fpsNum, int fps
         }
     }
 }
+
+
+/* ================================================================================================
+ * full-resolution PU primitives
+ * ============================================================================================== */
+
+/* sad<lx, ly>, common/pixel.cpp:39-55 */
+int ola_pu_sad(int w, int h, const pixel* a, intptr_t sa, const pixel* b, intptr_t sb)
+{
+    int sum = 0;
+    for (int y = 0; y < h; y++, a += sa, b += sb)
+        for (int x = 0; x < w; x++)
+            sum += abs((int)a[x] - (int)b[x]);
+    return sum;
+}
+
+/* pu[LUMA_WxH].satd, common/pixel.cpp:979-1003: satd8<w, h> (sum of satd_8x4 over 8x4 tiles, :232-242) for widths that are
+ * multiples of 8, satd4<w, h> (sum of satd_4x4 over 4x4 tiles, :220-230) for widths 4 and 12.  satd_8x4 (:192-218) halves the
+ * packed sum of its two 4x4 Hadamard abs-sums; each of those is even (the coefficients of a 4x4 Hadamard sum to 16 * d00), so
+ * every shape is the sum over its 4x4 tiles of (abs-sum >> 1) = ola_satd4x4. */
+int ola_pu_satd(int w, int h, const pixel* a, intptr_t sa, const pixel* b, intptr_t sb)
+{
+    int sum = 0;
+    for (int y = 0; y < h; y += 4)
+        for (int x = 0; x < w; x += 4)
+            sum += ola_satd4x4(a + y * sa + x, sa, b + y * sb + x, sb);
+    return sum;
+}

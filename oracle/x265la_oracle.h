@@ -148,6 +148,11 @@ void ola_estimate_cu_propagate(ola_frame* fenc, ola_frame* ref0, ola_frame* ref1
                                double averageDuration, int fpsNum, int fpsDenom, int weightedBiPred);
 void ola_cutree_finish(ola_frame* f, double averageDuration, int fpsNum, int fpsDenom, int ref0Distance, double cuTreeStrength);
 
+/* full-resolution PU primitives (oracle side only so far): pu[LUMA_WxH].sad / .satd for the 25 luma PU
+ * shapes (pixel.cpp:39-118, 192-242, 954-1004) */
+int ola_pu_sad(int w, int h, const pixel* a, intptr_t sa, const pixel* b, intptr_t sb);
+int ola_pu_satd(int w, int h, const pixel* a, intptr_t sa, const pixel* b, intptr_t sb);
+
 /* helpers for tests */
 void ola_lowres_mc(pixel* const planes[4], intptr_t stride, intptr_t blockOffset, int qx, int qy, pixel* blk);
 uint32_t ola_crc32(const void* p, size_t n);

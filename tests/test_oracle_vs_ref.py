@@ -172,3 +172,24 @@ def test_propagate_cost(depth):
         O.ola_propagate_cost(a.ctypes.data, pin.ctypes.data, intra.ctypes.data, inter.ctypes.data, invq.ctypes.data, C.byref(fps), n)
         R.x265ref_propagate_cost(b.ctypes.data, pin.ctypes.data, intra.ctypes.data, inter.ctypes.data, invq.ctypes.data, C.byref(fps), n)
         assert np.array_equal(a, b), (it, n)
+
+
+PU_SHAPES = [(4, 4), (8, 8), (16, 16), (32, 32), (64, 64), (4, 8), (8, 4), (16, 8), (8, 16), (16, 12), (12, 16), (16, 4), (4, 16),
+             (32, 16), (16, 32), (32, 24), (24, 32), (32, 8), (8, 32), (64, 32), (32, 64), (64, 48), (48, 64), (64, 16), (16, 64)]
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_pu_sad_satd_all_shapes(depth):
+    """the 25 luma PU shapes of pu[].sad / pu[].satd (pixel.cpp:954-1003), check_pixelcmp recipe (pixelharness.cpp:80-99):
+    random / all-min / all-max buffers, stride 64 against an odd stride, stepping offsets (oracle side)"""
+    O, R = po.oracle(depth), po.ref(depth)
+    B = bufs(depth, 23, n=64 * 160)
+    for (w, h) in PU_SHAPES:
+        for ia, a in enumerate(B[:3]):
+            for b in (B[0], B[3 + ia % 2]):
+                for it in range(12):
+                    oa, ob = (it * 32) % 1500, (it * 37 + 5) % 1500
+                    for name in ("sad", "satd"):
+                        got = getattr(O, "ola_pu_" + name)(w, h, ptr(a, oa), 64, ptr(b, ob), 67)
+                        want = getattr(R, "x265ref_pu_" + name)(w, h, ptr(a, oa), 64, ptr(b, ob), 67)
+                        assert got == want, (depth, w, h, name, it)
