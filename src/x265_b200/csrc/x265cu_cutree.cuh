@@ -18,6 +18,9 @@
  * by the instruction throughput of its 8 SMs (about 250 instructions per CU: the double division, the index
  * division, eight predicated atomics); hence the whole-GPU grid.
  *
+ * The per-CU work itself lives in x265cu_cutree_core.h, compiled for the device here and for the CPU by
+ * tests/cutree_emul.cpp (emulation against the oracle in the CPU test suite), like la_core.h for the motion search.
+ *
  * Exactness.
  *  - The propagate amount uses double arithmetic in the reference.  Its object code performs, per CU,
  *    cvt(int32 intra*invQ) * (fpsFactor/256) + cvt(in), * cvt(intra - min(intra, inter)), / cvt(intra), + 0.5,
@@ -32,110 +35,21 @@
 
 #include <cooperative_groups.h>
 
-#include "x265cu_cutree_sched.h"
+#include "x265cu_cutree_core.h"
 
 #define CUTREE_THREADS 512
-struct CutreeArgs
+/* memory operations of the device: the accumulators live in L2 (no L1 copies survive a grid barrier), adds are 64-bit
+ * reductions */
+struct CutreeDeviceMem
 {
-    int nOps;
-    int wCU, hCU, nCU;
-    int costTables;             /* (bf + 2)^2 */
-    int mvFields;               /* 2 * (bf + 1) */
-    const int* intraCost;       /* [slot][nCU] */
-    const int* invQ;            /* [slot][nCU] */
-    const uint16_t* lowresCosts;/* [slot][costTables][nCU] */
-    const int* mvs;             /* [slot][mvFields][nCU] packed int16 x | int16 y << 16 */
-    unsigned long long* acc;    /* [slot][nCU] propagateCost accumulators */
-    uint16_t* out;              /* [outIndex][nCU] clamped copies for the host */
-    CutreeOpDev ops[CUTREE_MAX_OPS];
+    static __device__ __forceinline__ unsigned long long load(const unsigned long long* p) { return __ldcg(p); }
+    static __device__ __forceinline__ void store(unsigned long long* p, unsigned long long v) { __stcg(p, v); }
+    static __device__ __forceinline__ void add(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }
 };
-
-/* estimateCUPropagateCost for one CU */
-__device__ __forceinline__ int cutree_amount(int intra, int interRaw, int invQ, unsigned in, double fps)
-{
-    int inter = interRaw & 0x3FFF;                    /* LOWRES_COST_MASK */
-    inter = inter < intra ? inter : intra;
-    const int prod = (int)((unsigned)intra * (unsigned)invQ);
-    double r = __dmul_rn((double)prod, fps);
-    r = __dadd_rn(r, (double)in);
-    r = __dmul_rn(r, (double)(intra - inter));
-    r = __ddiv_rn(r, (double)intra);
-    r = __dadd_rn(r, 0.5);
-    /* cvttsd2si: NaN and out-of-range give INT_MIN (never propagated: the caller tests > 0) */
-    return (r >= -2147483648.0 && r < 2147483648.0) ? __double2int_rz(r) : (int)0x80000000;
-}
 
 __device__ __forceinline__ void cutree_prefetch_l2(const void* p)
 {
     asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
-}
-
-__device__ __forceinline__ void cutree_clip_add(unsigned long long* cell, int x)
-{
-    if (x <= 0) return;                               /* adding 0 changes nothing; negatives cannot occur for legal inputs */
-    atomicAdd(cell, (unsigned long long)(x < 65535 ? x : 65535));
-}
-
-/* one work item = one CU of one op */
-__device__ __forceinline__ void cutree_item(const CutreeArgs& a, const CutreeOpDev& op, int cu)
-{
-    const int wCU = a.wCU, hCU = a.hCU, nCU = a.nCU;
-    unsigned long long* own = a.acc + (size_t)op.fenc * nCU;
-    if (op.kind == CT_OP_ZERO)
-    {
-        __stcg(own + cu, 0ull);
-        return;
-    }
-    if (op.kind == CT_OP_PACK)
-    {
-        const unsigned long long v = __ldcg(own + cu);
-        a.out[(size_t)op.outIndex * nCU + cu] = (uint16_t)(v < 65535ull ? v : 65535ull);
-        return;
-    }
-    const size_t f = (size_t)op.fenc;
-    unsigned in = 0;
-    if (op.referenced)
-    {
-        const unsigned long long v = __ldcg(own + cu);
-        in = (unsigned)(v < 65535ull ? v : 65535ull);
-    }
-    /* every load of the item is issued before anything is consumed: one L2 round trip */
-    const int cost = a.lowresCosts[(f * a.costTables + op.costOfs) * nCU + cu];
-    const int mvBoth[2] = { a.mvs[(f * a.mvFields + op.mvOfs0) * nCU + cu],
-                            op.mvOfs1 >= 0 ? a.mvs[(f * a.mvFields + op.mvOfs1) * nCU + cu] : 0 };
-    const int amount = cutree_amount(a.intraCost[f * nCU + cu], cost, a.invQ[f * nCU + cu], in, op.fps);
-    /* "for non-referred frames the source costs are always zero, so just memset one row and re-use it" (:1757): the
-     * first row of b's own array is zeroed by the step (nothing reads or adds into it in this phase) */
-    if (!op.referenced && cu < wCU) __stcg(own + cu, 0ull);
-    if (amount <= 0) return;                      /* "don't propagate for an intra block" */
-    const int listsUsed = cost >> 14;
-    const int blocky = cu / wCU, blockx = cu - blocky * wCU;
-    const int bw[2] = { op.bipredWeight, 64 - op.bipredWeight };
-#pragma unroll
-    for (int list = 0; list < 2; list++)
-    {
-        if (!((listsUsed >> list) & 1) || (list && op.mvOfs1 < 0)) continue;
-        int listamount = amount;
-        if (listsUsed == 3)
-            listamount = (listamount * bw[list] + 32) >> 6;
-        const int mv = mvBoth[list];
-        unsigned long long* ref = a.acc + (size_t)(list ? op.ref1 : op.ref0) * nCU;
-        if (!mv)
-        {
-            cutree_clip_add(ref + cu, listamount);
-            continue;
-        }
-        int x = (short)(mv & 0xFFFF), y = mv >> 16;
-        const int cux = (x >> 5) + blockx, cuy = (y >> 5) + blocky;
-        x &= 31; y &= 31;
-        const int idx0 = cux + cuy * wCU;
-        const bool inX0 = cux >= 0 && cux < wCU, inX1 = cux + 1 >= 0 && cux + 1 < wCU;
-        const bool inY0 = cuy >= 0 && cuy < hCU, inY1 = cuy + 1 >= 0 && cuy + 1 < hCU;
-        if (inX0 && inY0) cutree_clip_add(ref + idx0, (listamount * ((32 - y) * (32 - x)) + 512) >> 10);
-        if (inX1 && inY0) cutree_clip_add(ref + idx0 + 1, (listamount * ((32 - y) * x) + 512) >> 10);
-        if (inX0 && inY1) cutree_clip_add(ref + idx0 + wCU, (listamount * (y * (32 - x)) + 512) >> 10);
-        if (inX1 && inY1) cutree_clip_add(ref + idx0 + wCU + 1, (listamount * (y * x) + 512) >> 10);
-    }
 }
 
 __global__ void __launch_bounds__(CUTREE_THREADS, 1) cutree_kernel(const __grid_constant__ CutreeArgs a)
@@ -174,7 +88,7 @@ __global__ void __launch_bounds__(CUTREE_THREADS, 1) cutree_kernel(const __grid_
         for (int item = tid; item < total; item += nThreads)
         {
             const int k = item / nCU;
-            cutree_item(a, a.ops[k0 + k], item - k * nCU);
+            cutree_item<CutreeDeviceMem>(a, a.ops[k0 + k], item - k * nCU);
         }
         k0 = k1;
         if (k0 < a.nOps) grid.sync();
