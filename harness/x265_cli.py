@@ -17,6 +17,18 @@ REF = os.path.join(ROOT, "oracle", "_ref")
 CLI_CASES = {
     "cli_720p": (8, 1280, 720, 24, 1234, ["--preset", "medium", "--bframes", "4", "--rc-lookahead", "20"]),
     "cli_360p_b2": (8, 640, 368, 30, 77, ["--preset", "fast", "--bframes", "2", "--rc-lookahead", "12", "--b-adapt", "1"]),
+    # weighted bi-prediction: cuTree's bipred weights differ from 32, B slices run the explicit weight analysis on the lowres MVs
+    "cli_360p_weightb": (8, 640, 368, 24, 5, ["--preset", "medium", "--bframes", "3", "--rc-lookahead", "15", "--weightb"]),
+    # VBV + ABR: cuTreeFinish inside every referenced propagate step, vbvLookahead / frameCostRecalculate reading rowSatds and
+    # lowresCosts.  One frame thread: with several, x265's row-level VBV feedback depends on frame-encoder timing.
+    "cli_360p_vbv": (8, 640, 368, 24, 5, ["--preset", "medium", "--bframes", "3", "--rc-lookahead", "15", "--bitrate", "1000",
+                                          "--vbv-bufsize", "1500", "--vbv-maxrate", "1500", "--frame-threads", "1"]),
+    # (VBV together with --weightb is NOT a usable golden: the stock x265 1.9 binary itself writes different bitstreams for that
+    # combination depending on thread timing -- three different md5s under `taskset -c 0`, `taskset -c 0,1`, `nice -n 19` --
+    # because the B-slice weight analysis of the frame encoders reads lowresMvs[][] fields that vbvLookahead's late estimates
+    # are still filling in; each option alone is timing-stable.)
+    # the 10-bit build (16-bit pixel kernels) inside the real encoder
+    "cli_360p_10bit": (10, 640, 368, 20, 9, ["--preset", "medium", "--bframes", "3", "--rc-lookahead", "12"]),
 }
 # results depend on the pool size: pin it to values every machine can provide
 PIN = ["--pools", "4", "--frame-threads", "2"]
@@ -50,7 +62,7 @@ def run_case(kind, name, workdir=None, keep=False):
         write_clip(yuv, depth, w, h, n, seed)
     out = os.path.join(d, "%s_%s.hevc" % (name, kind))
     cmd = [exe, "--input", yuv, "--input-res", "%dx%d" % (w, h), "--fps", "30", "--input-depth", str(depth), "--frames", str(n),
-           "--log-level", "error", "--no-progress"] + opts + PIN + ["-o", out]
+           "--log-level", "error", "--no-progress"] + opts + (PIN[:2] if "--frame-threads" in opts else PIN) + ["-o", out]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1200)
     if r.returncode != 0:
         raise RuntimeError("%s failed: %s" % (" ".join(cmd), r.stdout[-800:]))

@@ -2,7 +2,8 @@
 (oracle/_ref/x265_cu8: stock encoder objects + integration/x265_glue.cpp + libx265cu.so) must write
 the SAME BITSTREAM as the stock CLI (oracle/_ref/x265_ref8) -- every slice-type decision, cuTree
 QP offset and rate-control input downstream of the lookahead outputs is then identical.
-Golden md5s of the stock CLI are committed (tests/golden/cli_md5.json, harness/x265_cli.py)."""
+Golden md5s of the stock CLI are committed (tests/golden/cli_md5.json, harness/x265_cli.py): 720p medium, 360p fast/b-adapt 1,
+--weightb, VBV + ABR, and the 10-bit build; only option sets for which the stock binary is timing-stable (see harness/x265_cli.py)."""
 import json
 import os
 
