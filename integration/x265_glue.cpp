@@ -1,166 +1,484 @@
-/* x265_glue.cpp -- the x265-side binding of libx265cu.so, inside the real x265 1.9 encoder.
+/* x265_glue.cpp -- the x265-side binding of libx265cu.so, inside the real x265 1.9 encoder (see x265_glue.h).
  *
- * INTEGRATION PROOF (test infrastructure, built by integration/build_x265_cu.py into
- * oracle/_ref/x265_cu<depth>): compiled WITH the reference's headers, linked with the reference's
- * objects and with libx265cu.so.  It performs, on the real `Lowres`/`Lookahead` objects, exactly
- * the edits INTEGRATION.md describes, so that the unchanged host code (slicetypeDecide, scenecut,
- * cuTree, rate control, the whole encoder) consumes what the GPU produced.  The CLI built this way
- * must write the same bitstream as the stock CLI (tests/test_gpu_x265_cli.py).
+ * Compiled WITH the reference's headers and linked with the reference's objects, libx265cu_host.so and libx265cu.so
+ * (integration/build_x265_cu.py).  It is a thin adapter: every x265 `Lowres` gets a shadow `x265cu::Lowres` whose ARRAYS
+ * ARE x265's own arrays (pinned + mapped, so the GPU writes results in place), the call-outs translate x265's calls into
+ * the host layer's (src/x265_b200/host/lookahead_cu.{h,cpp}: batching, look-ahead estimate cache, weightsAnalyse float
+ * guesses, calcAdaptiveQuantFrame float mapping, cuTree queue) and mirror the scalar members (costEst, costEstAq, intraMbs,
+ * weightedCostDelta, wp_sum/wp_ssd) back into x265's struct.  Everything else -- slicetypeDecide, slicetypeAnalyse,
+ * scenecut, slicetypePath, cuTree's control flow and cuTreeFinish's log2 mapping, vbvLookahead, frameCostRecalculate, rate
+ * control -- is x265's unchanged code consuming those arrays.  No CPU fallback: a failing GPU call aborts the encoder.
  */
 #include "common.h"
 #include "frame.h"
 #include "picyuv.h"
 #include "lowres.h"
 #include "slicetype.h"
-#include "bitcost.h"
-#include "motion.h"
+#include "threadpool.h"
 
 #include "x265_glue.h"
 #include "x265cu.h"
+#include "lookahead_cu.h"
 
 #include <map>
+#include <vector>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <pthread.h>
 
-using namespace X265_NS;
+namespace xr = X265_NS;
+
+/* observation hooks of the trace harness (harness/x265_la_driver.cpp); absent in the CLI build */
+extern "C" {
+void x265ref_hook_pre(xr::Frame* frame) __attribute__((weak));
+void x265ref_hook_batch(int begin, int njobs) __attribute__((weak));
+void x265ref_hook_job(xr::Lowres** frames, int p0, int p1, int b, int search0, int search1, int batchMode, int sliced) __attribute__((weak));
+void x265ref_hook_weight(int fencPoc, int refPoc, int scale, int denom, int offset) __attribute__((weak));
+void x265ref_hook_ctzero(xr::Lowres* frame) __attribute__((weak));
+void x265ref_hook_propagate(xr::Lowres** frames, double averageDuration, int p0, int p1, int b, int referenced) __attribute__((weak));
+void x265ref_hook_ctfinish(xr::Lowres* frame, double averageDuration, int ref0Distance) __attribute__((weak));
+int x265la_trace_level(void) __attribute__((weak));
+}
 
 namespace {
 
-struct ExposeBitCost : public BitCost
+void die(const char* what, const char* why)
 {
-    const uint16_t* table() const { return m_cost; }
-};
-
-struct GlueState
-{
-    x265cu_ctx* ctx;
-    std::map<Lowres*, int> slots;
-    int nextSlot, numSlots;
-};
-
-pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
-std::map<Lookahead*, GlueState> g_states;
-__thread int t_weight[4];    /* present, scale, denom, offset: set by weightsAnalyse on this thread */
-
-void die(const char* what, x265cu_ctx* ctx)
-{
-    fprintf(stderr, "x265 [error]: lookahead GPU path: %s: %s\n", what, x265cu_last_error(ctx));
+    fprintf(stderr, "x265 [error]: lookahead GPU path: %s: %s\n", what, why ? why : "");
     abort();      /* no CPU fallback */
 }
 
-GlueState& stateOf(Lookahead* la, PicYuv* pic)
+int traceLevel() { return x265la_trace_level ? x265la_trace_level() : 0; }
+
+/* ------------------------------------------------------------------------------------------------ pinned memory */
+struct Block { size_t bytes; int live; bool arena; };
+pthread_mutex_t g_memLock = PTHREAD_MUTEX_INITIALIZER;
+std::map<uintptr_t, Block> g_blocks;            /* base -> block */
+__thread uint8_t* t_arena;                      /* arena of the Lowres::create running on this thread */
+__thread size_t t_arenaBytes, t_arenaUsed;
+
+void* pinnedBlock(size_t bytes, bool arena)
 {
-    std::map<Lookahead*, GlueState>::iterator it = g_states.find(la);
-    if (it != g_states.end()) return it->second;
-    GlueState st;
-    st.nextSlot = 0;
-    st.numSlots = la->m_param->lookaheadDepth + la->m_param->bframes + 2 * X265_MAX(la->m_param->frameNumThreads, 1) + 24;
-    ExposeBitCost bc;
-    bc.setQP(X265_LOOKAHEAD_QP);
-    x265cu_config cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.srcWidth = pic->m_picWidth; cfg.srcHeight = pic->m_picHeight;
-    cfg.bitDepth = X265_DEPTH;
-    cfg.marginX = pic->m_lumaMarginX; cfg.marginY = pic->m_lumaMarginY;
-    cfg.bframes = la->m_param->bframes;
-    cfg.numFrameSlots = st.numSlots;
-    cfg.numCoopSlices = la->m_numCoopSlices; cfg.numRowsPerSlice = la->m_numRowsPerSlice;
-    cfg.bFrameBias = la->m_param->bFrameBias;
-    cfg.lookaheadLambda = (int)x265_lambda_tab[X265_LOOKAHEAD_QP];
-    cfg.mvcost = bc.table();
-    cfg.device = getenv("X265CU_DEVICE") ? atoi(getenv("X265CU_DEVICE")) : 0;
-    if (x265cu_open(&cfg, &st.ctx) != X265CU_OK) die("x265cu_open", NULL);
-    return g_states[la] = st;
+    void* p = NULL;
+    bytes = (bytes + 4095) & ~(size_t)4095;
+    if (posix_memalign(&p, 4096, bytes)) return NULL;
+    x265cu_host_register(p, bytes);             /* failure (no device here) only costs speed: the memory is still memory */
+    Block b = { bytes, 0, arena };
+    pthread_mutex_lock(&g_memLock);
+    g_blocks[(uintptr_t)p] = b;
+    pthread_mutex_unlock(&g_memLock);
+    return p;
 }
 
-int slotOf(GlueState& st, Lowres* l)
+struct GlueState
 {
-    std::map<Lowres*, int>::iterator it = st.slots.find(l);
-    if (it != st.slots.end()) return it->second;
-    if (st.nextSlot >= st.numSlots) { fprintf(stderr, "x265 [error]: lookahead GPU path: out of frame slots\n"); abort(); }
-    return st.slots[l] = st.nextSlot++;
+    x265cu::Lookahead la;
+    std::map<xr::Lowres*, x265cu::Lowres*> shadows;
+};
+
+pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+std::map<xr::Lookahead*, GlueState*> g_states;
+
+GlueState* stateOf(xr::Lookahead* la)
+{
+    pthread_mutex_lock(&g_lock);
+    std::map<xr::Lookahead*, GlueState*>::iterator it = g_states.find(la);
+    GlueState* st = it == g_states.end() ? NULL : it->second;
+    pthread_mutex_unlock(&g_lock);
+    if (!st) die("no GPU context for this Lookahead", "x265glue_open was not called (Lookahead::create)");
+    return st;
+}
+
+void fillArrays(x265cu::Lowres& a, xr::Lowres* xl, int bframes)
+{
+    memset(&a, 0, sizeof(a));
+    for (int i = 0; i < 4; i++) { a.buffer[i] = xl->buffer[i]; a.lowresPlane[i] = xl->lowresPlane[i]; }
+    a.intraCost = xl->intraCost; a.intraMode = xl->intraMode; a.propagateCost = xl->propagateCost;
+    a.qpAqOffset = xl->qpAqOffset; a.qpCuTreeOffset = xl->qpCuTreeOffset; a.invQscaleFactor = xl->invQscaleFactor;
+    a.blockVariance = xl->blockVariance;
+    for (int i = 0; i < bframes + 2; i++)
+        for (int j = 0; j < bframes + 2; j++) { a.rowSatds[i][j] = xl->rowSatds[i][j]; a.lowresCosts[i][j] = xl->lowresCosts[i][j]; }
+    for (int i = 0; i < bframes + 1; i++)
+        for (int l = 0; l < 2; l++)
+        {
+            a.lowresMvs[l][i] = reinterpret_cast<x265cu::MV*>(xl->lowresMvs[l][i]);
+            a.lowresMvCosts[l][i] = xl->lowresMvCosts[l][i];
+        }
+}
+
+/* the shadow of an x265 Lowres (created on first sight).  Out of device slots: frames older than the last non-B frame
+ * never take part in an estimate again (frames[0] = m_lastNonB is the oldest frame any call names) and give theirs up. */
+x265cu::Lowres* shadowOf(GlueState* st, xr::Lookahead* xla, xr::Lowres* xl)
+{
+    std::map<xr::Lowres*, x265cu::Lowres*>::iterator it = st->shadows.find(xl);
+    if (it != st->shadows.end())
+    {
+        x265cu::Lowres* sh = it->second;
+        if (sh->buffer[0] == xl->buffer[0] && sh->intraCost == xl->intraCost)
+        {
+            sh->propagateCost = xl->propagateCost;      /* cuTree swaps these pointers (rc-lookahead 0) */
+            return sh;
+        }
+        st->la.freeLowres(sh);                          /* the Lowres at this address was destroyed and re-created */
+        st->shadows.erase(it);
+    }
+    if (st->la.m_freeSlots.empty())
+    {
+        const int oldest = xla->m_lastNonB ? xla->m_lastNonB->frameNum : 0;
+        for (it = st->shadows.begin(); it != st->shadows.end();)
+            if (it->first != xl && it->first != xla->m_lastNonB && it->second->frameNum < oldest)
+            {
+                st->la.freeLowres(it->second);
+                st->shadows.erase(it++);
+            }
+            else
+                ++it;
+    }
+    x265cu::Lowres a;
+    fillArrays(a, xl, st->la.m_param.bframes);
+    if (xl->lumaStride != st->la.m_geom.stride || xl->buffer[1] - xl->buffer[0] != st->la.m_geom.planeSize ||
+        xl->lowresPlane[0] - xl->buffer[0] != st->la.m_geom.padOffset)
+        die("Lowres geometry", "Lowres::create and x265cu_get_geometry disagree");
+    x265cu::Lowres* sh = st->la.adoptLowres(a);
+    if (!sh) die("adoptLowres", st->la.m_error);
+    sh->frameNum = -1;
+    st->shadows[xl] = sh;
+    return sh;
+}
+
+x265cu::Lowres* knownShadow(GlueState* st, xr::Lookahead* xla, xr::Lowres* xl)
+{
+    x265cu::Lowres* sh = shadowOf(st, xla, xl);
+    if (!sh->ready) die("estimate", "a frame that did not go through the pre-lookahead");
+    return sh;
+}
+
+/* what estimateFrameCost leaves in the struct besides the arrays (slicetype.cpp:1999-2057) */
+void mirrorEstimate(xr::Lowres* fenc, const x265cu::Lowres* sh, int d0, int d1)
+{
+    fenc->costEst[d0][d1] = sh->costEst[d0][d1];
+    fenc->costEstAq[d0][d1] = sh->costEstAq[d0][d1];
+    fenc->intraMbs[d0] = sh->intraMbs[d0];
+    fenc->weightedRef[d0].isWeighted = sh->weightedRef[d0].present != 0;
+    fenc->weightedCostDelta[d0] = sh->weightedCostDelta[d0];
+}
+
+void traceJob(xr::Lowres** frames, const x265cu::Lowres* sh, int p0, int p1, int b, int s0, int s1, int batchMode, int sliced)
+{
+    if (!traceLevel() || !x265ref_hook_job) return;
+    const int d0 = b - p0;
+    if (s0 && sh->weightedRef[d0].present && x265ref_hook_weight)
+        x265ref_hook_weight(frames[b]->frameNum, frames[p0]->frameNum, sh->weightedRef[d0].scale, sh->weightedRef[d0].denom, sh->weightedRef[d0].offset);
+    /* the reference's observation point lies before the B-frame scaling of the score (slicetype.cpp:2053) */
+    const int d1 = p1 - b;
+    const int64_t stored = frames[b]->costEst[d0][d1];
+    frames[b]->costEst[d0][d1] = sh->costEstRaw[d0][d1];
+    x265ref_hook_job(frames, p0, p1, b, s0, s1, batchMode, sliced);
+    frames[b]->costEst[d0][d1] = stored;
 }
 
 } // namespace
 
-extern "C" void x265glue_pre(Lookahead* la, Frame* frame)
+/* ================================================================================================ memory */
+extern "C" void* x265glue_malloc(size_t bytes)
 {
-    pthread_mutex_lock(&g_lock);
-    GlueState& st = stateOf(la, frame->m_fencPic);
-    Lowres& l = frame->m_lowres;
-    int slot = slotOf(st, &l);
-    pthread_mutex_unlock(&g_lock);
-    /* Lowres::init pixel work (lowres.cpp:155-164): planes come back into Lowres::buffer[0] */
-    if (x265cu_frame_init(st.ctx, slot, frame->m_fencPic->m_picOrg[0], frame->m_fencPic->m_stride, 0, l.buffer[0])) die("x265cu_frame_init", st.ctx);
-    if (x265cu_frame_set_invqscale(st.ctx, slot, l.invQscaleFactor)) die("x265cu_frame_set_invqscale", st.ctx);
-    /* lowresIntraEstimate (slicetype.cpp:230-336) */
-    x265cu_intra_out o;
-    o.intraCost = l.intraCost; o.intraMode = l.intraMode; o.lowresCosts = l.lowresCosts[0][0]; o.rowSatds = l.rowSatds[0][0];
-    if (x265cu_intra(st.ctx, slot, &o)) die("x265cu_intra", st.ctx);
-    l.costEst[0][0] = o.sums[0];
-    l.costEstAq[0][0] = o.sums[1];
-    if (x265cu_sync(st.ctx)) die("x265cu_sync", st.ctx);   /* the padded planes have landed */
-    t_weight[0] = 0;
-}
-
-extern "C" void x265glue_weight(int scale, int denom, int offset)
-{
-    t_weight[0] = 1; t_weight[1] = scale; t_weight[2] = denom; t_weight[3] = offset;
-}
-
-extern "C" int x265glue_estimate(Lookahead* la, Lowres** frames, int p0, int p1, int b, const bool* bDoSearch, int batchMode)
-{
-    Lowres* fenc = frames[b];
-    pthread_mutex_lock(&g_lock);
-    GlueState& st = g_states[la];
-    x265cu_job j;
-    memset(&j, 0, sizeof(j));
-    j.fenc = slotOf(st, fenc); j.ref0 = slotOf(st, frames[p0]); j.ref1 = slotOf(st, frames[p1]);
-    pthread_mutex_unlock(&g_lock);
-    const int d0 = b - p0, d1 = p1 - b;
-    j.d0 = d0; j.d1 = d1;
-    j.doSearch[0] = bDoSearch[0]; j.doSearch[1] = bDoSearch[1];
-    j.sliced = !batchMode;
-    if (bDoSearch[0] && fenc->weightedRef[d0].isWeighted)
+    if (t_arena)
     {
-        /* weightsAnalyse ran on this thread just before (slicetype.cpp:2001-2002) */
-        j.weighted = 1; j.wScale = t_weight[1]; j.wDenom = t_weight[2]; j.wOffset = t_weight[3];
+        size_t at = (t_arenaUsed + 63) & ~(size_t)63;
+        if (at + bytes <= t_arenaBytes)
+        {
+            t_arenaUsed = at + bytes;
+            pthread_mutex_lock(&g_memLock);
+            g_blocks[(uintptr_t)t_arena].live++;
+            pthread_mutex_unlock(&g_memLock);
+            return t_arena + at;
+        }
     }
-    t_weight[0] = 0;
-    if (bDoSearch[0]) { j.mvs[0] = fenc->lowresMvs[0][d0 - 1]; j.mvCosts[0] = fenc->lowresMvCosts[0][d0 - 1]; }
-    if (bDoSearch[1]) { j.mvs[1] = fenc->lowresMvs[1][d1 - 1]; j.mvCosts[1] = fenc->lowresMvCosts[1][d1 - 1]; }
-    j.lowresCosts = fenc->lowresCosts[d0][d1];
-    j.rowSatds = fenc->rowSatds[d0][d1];
-    x265cu_job_result r;
-    if (x265cu_estimate_batch(st.ctx, 1, &j, &r)) die("x265cu_estimate_batch", st.ctx);
-    /* the caller scales the B score and stores it (slicetype.cpp:2053-2057) */
-    fenc->costEst[d0][d1] = r.costEstRaw;
-    fenc->costEstAq[d0][d1] = r.costEstAq;
-    if (p1 == b) fenc->intraMbs[d0] += r.intraMbs;
+    void* p = pinnedBlock(bytes, false);
+    if (p)
+    {
+        pthread_mutex_lock(&g_memLock);
+        g_blocks[(uintptr_t)p].live = 1;
+        pthread_mutex_unlock(&g_memLock);
+    }
+    return p;
+}
+
+extern "C" void x265glue_free(void* p)
+{
+    if (!p) return;
+    void* release = NULL;
+    pthread_mutex_lock(&g_memLock);
+    std::map<uintptr_t, Block>::iterator it = g_blocks.upper_bound((uintptr_t)p);
+    if (it != g_blocks.begin())
+    {
+        --it;
+        if ((uintptr_t)p < it->first + it->second.bytes)
+        {
+            if (--it->second.live <= 0)
+            {
+                release = (void*)it->first;
+                g_blocks.erase(it);
+            }
+            pthread_mutex_unlock(&g_memLock);
+            if (release)
+            {
+                x265cu_host_unregister(release);
+                free(release);
+            }
+            return;
+        }
+    }
+    pthread_mutex_unlock(&g_memLock);
+    free(p);        /* not ours */
+}
+
+extern "C" void x265glue_arena_begin(size_t bytes)
+{
+    t_arena = (uint8_t*)pinnedBlock(bytes, true);
+    t_arenaBytes = t_arena ? ((bytes + 4095) & ~(size_t)4095) : 0;
+    t_arenaUsed = 0;
+}
+
+extern "C" void x265glue_arena_end(void)
+{
+    if (t_arena)
+    {
+        /* nothing was carved out of it (Lowres::create failed early): give it back */
+        void* release = NULL;
+        pthread_mutex_lock(&g_memLock);
+        std::map<uintptr_t, Block>::iterator it = g_blocks.find((uintptr_t)t_arena);
+        if (it != g_blocks.end() && it->second.live == 0) { release = t_arena; g_blocks.erase(it); }
+        pthread_mutex_unlock(&g_memLock);
+        if (release) { x265cu_host_unregister(release); free(release); }
+    }
+    t_arena = NULL; t_arenaBytes = t_arenaUsed = 0;
+}
+
+/* upper bound of what Lowres::create allocates (lowres.cpp:30-95), each array padded to 64 bytes */
+extern "C" size_t x265glue_lowres_bytes(int picWidth, int picHeight, int marginX, int marginY, int bframes, int pixelBytes)
+{
+    int width = picWidth / 2, lines = picHeight / 2;
+    size_t stride = (size_t)width + 2 * marginX;
+    if (stride & 31) stride += 32 - (stride & 31);
+    const size_t cols = (width + 7) >> 3, rows = (lines + 7) >> 3, n = cols * rows;
+    lines = (int)rows * 8;
+    const size_t planesize = stride * (lines + 2 * marginY);
+    size_t bytes = 4 * planesize * pixelBytes + 64;
+    bytes += n * (8 + 4 + 8 + 4) + 4 * 64;                              /* qpAqOffset, invQscaleFactor, qpCuTreeOffset, blockVariance */
+    bytes += n * (2 + 4 + 1) + 3 * 64;                                  /* propagateCost, intraCost, intraMode */
+    bytes += (size_t)(bframes + 2) * (bframes + 2) * (rows * 4 + n * 2 + 2 * 64);
+    bytes += (size_t)(bframes + 1) * 4 * (n * 4 + 64);
+    return bytes + 4096;
+}
+
+extern "C" int x265glue_active(void) { return 1; }
+
+/* ================================================================================================ context */
+extern "C" void x265glue_open(xr::Lookahead* la)
+{
+    const x265_param* p = la->m_param;
+    if (p->rc.bStatRead && p->rc.cuTree)
+        die("x265glue_open", "cuTree offsets from a stats file (2-pass) are not supported by the GPU lookahead");
+    x265cu::Param q;
+    memset(&q, 0, sizeof(q));
+    q.sourceWidth = p->sourceWidth; q.sourceHeight = p->sourceHeight;
+    q.bitDepth = X265_DEPTH;
+    q.maxCUSize = (int)xr::g_maxCUSize;
+    q.bframes = p->bframes;
+    q.lookaheadDepth = p->lookaheadDepth;
+    q.lookaheadSlices = p->lookaheadSlices;
+    q.poolWorkers = la->m_pool ? la->m_pool->m_numWorkers : 0;
+    q.forceCoopSlices = la->m_numCoopSlices; q.forceRowsPerSlice = la->m_numRowsPerSlice;   /* slicetype.cpp:534-558, as computed there */
+    q.bEnableWeightedPred = p->bEnableWeightedPred;
+    q.bEnableWeightedBiPred = p->bEnableWeightedBiPred;
+    q.aqMode = p->rc.aqMode; q.aqStrength = p->rc.aqStrength;
+    q.bFrameBias = p->bFrameBias;
+    q.device = getenv("X265CU_DEVICE") ? atoi(getenv("X265CU_DEVICE")) : 0;
+    q.frameSlots = getenv("X265CU_FRAME_SLOTS") ? atoi(getenv("X265CU_FRAME_SLOTS"))
+                                                : p->lookaheadDepth + p->bframes + 2 * X265_MAX(p->frameNumThreads, 1) + 24;
+    q.fpsNum = (int)p->fpsNum; q.fpsDenom = (int)p->fpsDenom;
+    q.qCompress = p->rc.qCompress;
+    GlueState* st = new GlueState;
+    if (!st->la.create(q)) die("x265cu_open", st->la.m_error);
+    if (st->la.m_8x8Width != la->m_8x8Width || st->la.m_8x8Height != la->m_8x8Height || st->la.m_8x8Blocks != la->m_8x8Blocks ||
+        st->la.m_numCoopSlices != la->m_numCoopSlices || st->la.m_numRowsPerSlice != la->m_numRowsPerSlice)
+        die("x265glue_open", "lookahead geometry differs from Lookahead::Lookahead");
+    pthread_mutex_lock(&g_lock);
+    g_states[la] = st;
+    pthread_mutex_unlock(&g_lock);
+}
+
+extern "C" void x265glue_close(xr::Lookahead* la)
+{
+    pthread_mutex_lock(&g_lock);
+    std::map<xr::Lookahead*, GlueState*>::iterator it = g_states.find(la);
+    GlueState* st = it == g_states.end() ? NULL : it->second;
+    if (st) g_states.erase(it);
+    pthread_mutex_unlock(&g_lock);
+    if (!st) return;
+    for (std::map<xr::Lowres*, x265cu::Lowres*>::iterator s = st->shadows.begin(); s != st->shadows.end(); ++s)
+        st->la.freeLowres(s->second);
+    st->shadows.clear();
+    st->la.destroy();
+    delete st;
+}
+
+/* ================================================================================================ pre-lookahead */
+extern "C" void x265glue_pre_list(xr::Lookahead* la, xr::Frame** frames, int n)
+{
+    GlueState* st = stateOf(la);
+    std::vector<x265cu::Lowres*> ls((size_t)n);
+    std::vector<x265cu::Lookahead::PictureIn> pics((size_t)n);
+    for (int i = 0; i < n; i++)
+    {
+        xr::Frame* f = frames[i];
+        /* the per-frame resets of Lowres::init (lowres.cpp:130-153); its pixel work is skipped in this build */
+        f->m_lowres.init(f->m_fencPic, f->m_poc);
+        ls[i] = shadowOf(st, la, &f->m_lowres);
+        xr::PicYuv* pic = f->m_fencPic;
+        x265cu::Lookahead::PictureIn in = { pic->m_picOrg[0], pic->m_stride, pic->m_picOrg[1], pic->m_picOrg[2], pic->m_strideC, f->m_poc, f->m_quantOffsets };
+        pics[i] = in;
+    }
+    /* ONE pipelined call for the list: uploads, lowres + variance kernels, float AQ mapping (callback, host), intra */
+    if (!st->la.preLookaheadBatch(n, &ls[0], &pics[0], true)) die("preLookaheadBatch", st->la.m_error);
+    for (int i = 0; i < n; i++)
+    {
+        xr::Lowres& xl = frames[i]->m_lowres;
+        const x265cu::Lowres* sh = ls[i];
+        xl.costEst[0][0] = sh->costEst[0][0];
+        xl.costEstAq[0][0] = sh->costEstAq[0][0];
+        for (int k = 0; k < 3; k++) { xl.wp_ssd[k] = sh->wp_ssd[k]; xl.wp_sum[k] = sh->wp_sum[k]; }
+        xl.frameVariance = sh->frameVariance;
+        frames[i]->m_lowresInit = true;
+    }
+    if (traceLevel() && x265ref_hook_pre)
+    {
+        if (!st->la.sync()) die("x265cu_sync", x265cu_last_error(st->la.m_ctx));     /* the hook checksums the planes */
+        for (int i = 0; i < n; i++) x265ref_hook_pre(frames[i]);
+    }
+}
+
+/* ================================================================================================ estimates */
+extern "C" void x265glue_ensure(xr::Lookahead* la, xr::Lowres** frames, int p0, int p1, int b)
+{
+    xr::Lowres* fenc = frames[b];
+    const int d0 = b - p0, d1 = p1 - b;
+    if (fenc->costEst[d0][d1] >= 0 && fenc->rowSatds[d0][d1][0] != -1)
+        return;                                         /* cached (slicetype.cpp:1982) */
+    if (p0 == b) die("estimateFrameCost", "I frame estimates should always be pre-calculated");
+    GlueState* st = stateOf(la);
+    const int s0 = p0 < b && fenc->lowresMvs[0][d0 - 1][0].x == 0x7FFF;
+    const int s1 = p1 > b && fenc->lowresMvs[1][d1 - 1][0].x == 0x7FFF;
+    std::vector<x265cu::Lowres*> fr((size_t)(d0 + d1 + 1), (x265cu::Lowres*)NULL);
+    fr[0] = knownShadow(st, la, frames[p0]);
+    fr[d0 + d1] = knownShadow(st, la, frames[p1]);
+    fr[d0] = knownShadow(st, la, fenc);
+    x265cu::CostEstimateGroup grp(st->la, &fr[0]);
+    if (grp.singleCost(0, d0 + d1, d0, false) < 0) die("singleCost", st->la.m_error);
+    mirrorEstimate(fenc, fr[d0], d0, d1);
+    traceJob(frames, fr[d0], p0, p1, b, s0, s1, 0, la->m_numCoopSlices > 1 && (p1 > b || s0 || s1));
+}
+
+extern "C" int x265glue_finish_batch(xr::Lookahead* la, xr::Lowres** frames, const int* est, int n)
+{
+    if (traceLevel() && x265ref_hook_batch) x265ref_hook_batch(1, n);
+    if (n > 0)
+    {
+        GlueState* st = stateOf(la);
+        int lo = est[0], hi = est[2];
+        for (int i = 0; i < n; i++) { lo = X265_MIN(lo, est[3 * i]); hi = X265_MAX(hi, est[3 * i + 2]); }
+        std::vector<x265cu::Lowres*> fr((size_t)(hi - lo + 1), (x265cu::Lowres*)NULL);
+        std::vector<int> state((size_t)n);              /* bit 0/1: searches L0/L1, bit 2: was cached */
+        x265cu::CostEstimateGroup* grp = new x265cu::CostEstimateGroup(st->la, &fr[0]);
+        for (int i = 0; i < n; i++)
+        {
+            const int p0 = est[3 * i], b = est[3 * i + 1], p1 = est[3 * i + 2], d0 = b - p0, d1 = p1 - b;
+            xr::Lowres* fenc = frames[b];
+            if (!fr[p0 - lo]) fr[p0 - lo] = knownShadow(st, la, frames[p0]);
+            if (!fr[p1 - lo]) fr[p1 - lo] = knownShadow(st, la, frames[p1]);
+            if (!fr[b - lo]) fr[b - lo] = knownShadow(st, la, fenc);
+            state[i] = (p0 < b && fenc->lowresMvs[0][d0 - 1][0].x == 0x7FFF ? 1 : 0) | (p1 > b && fenc->lowresMvs[1][d1 - 1][0].x == 0x7FFF ? 2 : 0) |
+                       (fenc->costEst[d0][d1] >= 0 && fenc->rowSatds[d0][d1][0] != -1 ? 4 : 0);
+            grp->add(p0 - lo, p1 - lo, b - lo);
+        }
+        /* the whole batch -- every frame pair and B-frame candidate x265 queued -- is ONE x265cu_estimate_batch */
+        if (!grp->finishBatch()) die("finishBatch", st->la.m_error);
+        delete grp;
+        for (int i = 0; i < n; i++)
+        {
+            if (state[i] & 4) continue;
+            const int p0 = est[3 * i], b = est[3 * i + 1], p1 = est[3 * i + 2];
+            mirrorEstimate(frames[b], fr[b - lo], b - p0, p1 - b);
+            traceJob(frames, fr[b - lo], p0, p1, b, state[i] & 1, (state[i] >> 1) & 1, 1, 0);
+        }
+    }
+    if (traceLevel() && x265ref_hook_batch) x265ref_hook_batch(0, n);
     return 1;
 }
 
-extern "C" int x265glue_propagate(Lookahead* la, Lowres** frames, double fpsFactor, int bipredWeight, int p0, int p1, int b, int referenced)
+/* ================================================================================================ cuTree */
+extern "C" void x265glue_ct_zero(xr::Lookahead* la, xr::Lowres* frame)
 {
-    pthread_mutex_lock(&g_lock);
-    GlueState& st = g_states[la];
-    const int sb = slotOf(st, frames[b]), s0 = slotOf(st, frames[p0]), s1 = slotOf(st, frames[p1]);
-    pthread_mutex_unlock(&g_lock);
-    /* x265 keeps cuTree's control flow and its memsets, so the arrays it owns are the truth before every step */
-    if (referenced && x265cu_frame_set_propagate(st.ctx, sb, frames[b]->propagateCost)) die("x265cu_frame_set_propagate", st.ctx);
-    if (x265cu_frame_set_propagate(st.ctx, s0, frames[p0]->propagateCost)) die("x265cu_frame_set_propagate", st.ctx);
-    if (p1 != b && x265cu_frame_set_propagate(st.ctx, s1, frames[p1]->propagateCost)) die("x265cu_frame_set_propagate", st.ctx);
-    x265cu_cutree_op op;
-    memset(&op, 0, sizeof(op));
-    op.kind = X265CU_CT_PROPAGATE;
-    op.fenc = sb; op.ref0 = s0; op.ref1 = s1;
-    op.d0 = b - p0; op.d1 = p1 - b;
-    op.referenced = referenced;
-    op.bipredWeight = bipredWeight;
-    op.fpsFactor = fpsFactor;
-    int outSlots[2] = { s0, s1 };
-    uint16_t* outs[2] = { frames[p0]->propagateCost, frames[p1]->propagateCost };
-    if (x265cu_cutree_run(st.ctx, 1, &op, p1 != b ? 2 : 1, outSlots, outs)) die("x265cu_cutree_run", st.ctx);
+    GlueState* st = stateOf(la);
+    st->la.cuTreeZero(*shadowOf(st, la, frame));
+    if (traceLevel() && x265ref_hook_ctzero) x265ref_hook_ctzero(frame);
+}
+
+extern "C" int x265glue_propagate(xr::Lookahead* la, xr::Lowres** frames, double averageDuration, int p0, int p1, int b, int referenced)
+{
+    GlueState* st = stateOf(la);
+    const int d0 = b - p0, d1 = p1 - b;
+    std::vector<x265cu::Lowres*> fr((size_t)(d0 + d1 + 1), (x265cu::Lowres*)NULL);
+    fr[0] = knownShadow(st, la, frames[p0]);
+    fr[d0 + d1] = knownShadow(st, la, frames[p1]);
+    fr[d0] = knownShadow(st, la, frames[b]);
+    /* queued: the steps of a cuTree pass run as one launch when its cuTreeFinish asks for the result */
+    if (!st->la.estimateCUPropagate(&fr[0], averageDuration, 0, d0 + d1, d0, referenced)) die("estimateCUPropagate", st->la.m_error);
+    if (traceLevel() >= 2)
+    {
+        /* full trace: the state of the arrays after EVERY step is checksummed, so every step is run and fetched now */
+        if (!st->la.propagateCost(*fr[0]) || !st->la.propagateCost(*fr[d0 + d1]) || !st->la.propagateCost(*fr[d0]))
+            die("propagateCost", st->la.m_error);
+    }
+    if (traceLevel() && x265ref_hook_propagate && traceLevel() >= 2) x265ref_hook_propagate(frames, averageDuration, p0, p1, b, referenced);
     return 1;
+}
+
+extern "C" void x265glue_ct_fetch(xr::Lookahead* la, xr::Lowres* frame)
+{
+    GlueState* st = stateOf(la);
+    if (!st->la.propagateCost(*shadowOf(st, la, frame))) die("propagateCost", st->la.m_error);
+}
+
+extern "C" void x265glue_ct_finished(xr::Lookahead*, xr::Lowres* frame, double averageDuration, int ref0Distance)
+{
+    if (traceLevel() && x265ref_hook_ctfinish) x265ref_hook_ctfinish(frame, averageDuration, ref0Distance);
+}
+
+/* rc-lookahead 0 (slicetype.cpp:1663-1675, 1732-1737): cuTree swaps the propagateCost POINTERS of two frames.  The device
+ * keeps one accumulator per frame slot, so both arrays are brought to the host before the swap and sent back after it. */
+extern "C" void x265glue_ct_preswap(xr::Lookahead* la, xr::Lowres* a, xr::Lowres* b)
+{
+    GlueState* st = stateOf(la);
+    if (!st->la.propagateCost(*shadowOf(st, la, a)) || !st->la.propagateCost(*shadowOf(st, la, b))) die("propagateCost", st->la.m_error);
+}
+
+extern "C" void x265glue_ct_postswap(xr::Lookahead* la, xr::Lowres* a, xr::Lowres* b)
+{
+    GlueState* st = stateOf(la);
+    xr::Lowres* two[2] = { a, b };
+    for (int i = 0; i < 2; i++)
+    {
+        x265cu::Lowres* sh = shadowOf(st, la, two[i]);      /* re-points the shadow at the swapped array */
+        if (x265cu_frame_set_propagate(st->la.m_ctx, sh->slot, sh->propagateCost)) die("x265cu_frame_set_propagate", x265cu_last_error(st->la.m_ctx));
+        sh->propagateStale = false;
+    }
+}
+
+extern "C" void x265glue_sync(xr::Lookahead* la)
+{
+    GlueState* st = stateOf(la);
+    if (!st->la.sync()) die("x265cu_sync", x265cu_last_error(st->la.m_ctx));
 }

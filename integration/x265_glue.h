@@ -1,9 +1,22 @@
-/* x265_glue.h -- call-outs compiled into a temporary GPU-hooked copy of x265 1.9's
- * encoder/slicetype.cpp (see make_gpu_slicetype.py).  INTEGRATION PROOF, test infrastructure:
- * it shows the five edits of INTEGRATION.md working inside the real encoder and lets the
- * encoder-level bit-exactness (slice types, bitstream md5) be checked against the stock binary. */
+/* x265_glue.h -- the x265-side binding of libx265cu.so: call-outs compiled into temporary copies of x265 1.9's
+ * encoder/slicetype.cpp, common/lowres.cpp and common/picyuv.cpp (integration/make_gpu_sources.py inserts them at the
+ * sites INTEGRATION.md names; no reference source is held here).  With them x265's OWN lookahead -- slicetypeDecide,
+ * slicetypeAnalyse, scenecut, slicetypePath, the control flow of cuTree, vbvLookahead, its thread pool -- is the host
+ * and every cost estimate, pre-lookahead frame and cuTree propagate step runs on the GPU:
+ *
+ *   PreLookaheadGroup::processTasks  -> x265glue_pre_list      the whole list in ONE x265cu_pre_lookahead_batch
+ *   CostEstimateGroup::finishBatch   -> x265glue_finish_batch  the whole batch in ONE x265cu_estimate_batch
+ *   CostEstimateGroup::estimateFrameCost -> x265glue_ensure    singleCost through the look-ahead estimate cache
+ *   LookaheadTLD::weightsAnalyse     -> inside the two above   (x265cu_weight_cost_batch; float guesses on the host)
+ *   Lookahead::cuTree memsets / estimateCUPropagate / cuTreeFinish -> x265glue_ct_*   queued, one launch per pass
+ *   Lowres::create / PicYuv::create  -> x265glue_malloc        pinned + mapped host arrays (results written in place)
+ *
+ * Built into oracle/_ref/libx265gpu<depth>.so (lookahead-only driver: bench.py e2e, trace parity) and
+ * oracle/_ref/x265_cu<depth> (the full x265 CLI: bitstream md5 parity) by integration/build_x265_cu.py. */
 #ifndef X265_GLUE_H
 #define X265_GLUE_H
+
+#include <stddef.h>
 
 namespace X265_NS {
 class Frame;
@@ -12,16 +25,39 @@ struct Lowres;
 }
 
 extern "C" {
-/* after PreLookaheadGroup::processTasks finished a frame on the CPU: redo Lowres::init's pixel work
- * and lowresIntraEstimate on the GPU and OVERWRITE the host arrays with the GPU's results */
-void x265glue_pre(X265_NS::Lookahead* la, X265_NS::Frame* frame);
-/* weightsAnalyse accepted a weight for (fenc, ref) on this thread */
-void x265glue_weight(int scale, int denom, int offset);
-/* estimateFrameCost, non-cached branch: run the estimate on the GPU; returns 1 when done */
-int x265glue_estimate(X265_NS::Lookahead* la, X265_NS::Lowres** frames, int p0, int p1, int b, const bool* bDoSearch, int batchMode);
-/* estimateCUPropagate, instead of its CU loops: one propagate step on the GPU (the cuTree control flow, its memsets
- * and cuTreeFinish stay x265's; the propagateCost arrays of the frames involved travel with the call); returns 1 */
-int x265glue_propagate(X265_NS::Lookahead* la, X265_NS::Lowres** frames, double fpsFactor, int bipredWeight, int p0, int p1, int b, int referenced);
+/* ---- memory: Lowres::create (lowres.cpp:30-95) and PicYuv::create (picyuv.cpp:51-88) allocate through these */
+void*  x265glue_malloc(size_t bytes);
+void   x265glue_free(void* p);
+/* the allocations of one Lowres::create come out of one pinned arena of this size (x265glue_lowres_bytes) */
+void   x265glue_arena_begin(size_t bytes);
+void   x265glue_arena_end(void);
+size_t x265glue_lowres_bytes(int picWidth, int picHeight, int marginX, int marginY, int bframes, int pixelBytes);
+/* 1: the pixel work of Lowres::init (frameInitLowres + 4x extendPicBorder, lowres.cpp:155-164) is the GPU's */
+int    x265glue_active(void);
+
+/* ---- Lookahead::create / destroy (slicetype.cpp:586-631) */
+void x265glue_open(X265_NS::Lookahead* la);
+void x265glue_close(X265_NS::Lookahead* la);
+/* ---- PreLookaheadGroup::processTasks (slicetype.cpp:831-856): the list m_preframes[first .. first + n) */
+void x265glue_pre_list(X265_NS::Lookahead* la, X265_NS::Frame** frames, int n);
+/* ---- CostEstimateGroup::estimateFrameCost (slicetype.cpp:1977-2066), first statement: make the estimate (p0, p1, b)
+ * exist in frames[b] (arrays and costEst/costEstAq/intraMbs/weightedCostDelta); the cached branch then returns it */
+void x265glue_ensure(X265_NS::Lookahead* la, X265_NS::Lowres** frames, int p0, int p1, int b);
+/* ---- CostEstimateGroup::finishBatch (slicetype.cpp:1919-1926): estimates = m_estimates as (p0, b, p1) triples */
+int  x265glue_finish_batch(X265_NS::Lookahead* la, X265_NS::Lowres** frames, const int* estimates, int n);
+/* ---- Lookahead::cuTree (slicetype.cpp:1640-1739): after each memset of a propagateCost array; around its std::swap */
+void x265glue_ct_zero(X265_NS::Lookahead* la, X265_NS::Lowres* frame);
+void x265glue_ct_preswap(X265_NS::Lookahead* la, X265_NS::Lowres* a, X265_NS::Lowres* b);
+void x265glue_ct_postswap(X265_NS::Lookahead* la, X265_NS::Lowres* a, X265_NS::Lowres* b);
+/* ---- Lookahead::estimateCUPropagate (slicetype.cpp:1741-1839) instead of its CU loops; returns 1 */
+int  x265glue_propagate(X265_NS::Lookahead* la, X265_NS::Lowres** frames, double averageDuration, int p0, int p1, int b, int referenced);
+/* ---- Lookahead::cuTreeFinish (slicetype.cpp:1844-1862), first statement: frame->propagateCost is complete on the host */
+void x265glue_ct_fetch(X265_NS::Lookahead* la, X265_NS::Lowres* frame);
+/* ... and its last statement (observation only: trace harness) */
+void x265glue_ct_finished(X265_NS::Lookahead* la, X265_NS::Lowres* frame, double averageDuration, int ref0Distance);
+/* ---- Lookahead::slicetypeDecide (slicetype.cpp:1005), before the mini-GOP is handed to the output queue: the padded
+ * lowres planes copied back for weightPrediction.cpp have landed */
+void x265glue_sync(X265_NS::Lookahead* la);
 }
 
 #endif

@@ -14,7 +14,8 @@ Products (per bit depth D in {8,10}):
                                     copy made by make_hooked_slicetype.py (trace/dump call-outs
                                     only; arithmetic untouched; a second, un-hooked object is
                                     kept as slicetype_plain.o to prove the hooks change nothing)
-  oracle/_ref/libx265ref<D>.so      shim (ref_shim.cpp): C primitives table + lookahead driver
+  oracle/_ref/libx265ref<D>.so      shim (ref_shim.cpp): C primitives table; + the lookahead-only driver with its
+                                    observation hooks (harness/x265_la_driver.cpp)
   oracle/_ref/x265_ref<D>           the stock CLI (bitstream md5 checks)
 
 Usage: python oracle/build_ref.py [--depths 8,10] [--jobs N] [--cli]
@@ -113,10 +114,11 @@ def build_depth(depth, jobs, cli):
 
     # shim .so: reference primitives + lookahead driver with hooks
     shim_src = os.path.join(HERE, "ref_shim.cpp")
+    drv_src = os.path.join(os.path.dirname(HERE), "harness", "x265_la_driver.cpp")   # lookahead-only driver + observation hooks
     shim = os.path.join(OUT, "libx265ref%d.so" % depth)
-    deps = [shim_src, lib, os.path.join(HERE, "ref_hooks.h"), os.path.join(HERE, "synth.h")]
+    deps = [shim_src, drv_src, lib, os.path.join(HERE, "ref_hooks.h"), os.path.join(HERE, "synth.h")]
     if os.path.exists(shim_src) and not newer(shim, *deps):
-        run(["g++"] + F + ["-shared", shim_src, "-o", shim, "-Wl,--whole-archive", lib, "-Wl,--no-whole-archive",
+        run(["g++"] + F + ["-shared", shim_src, drv_src, "-o", shim, "-Wl,--whole-archive", lib, "-Wl,--no-whole-archive",
                             "-lpthread", "-ldl", "-lm"])
 
     if cli:

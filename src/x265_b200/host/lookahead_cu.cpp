@@ -102,7 +102,7 @@ bool Lookahead::create(const Param& p)
     m_8x8Width = ((p.sourceWidth / 2) + 7) >> 3;
     m_cuCount = m_8x8Width * m_8x8Height;
     m_8x8Blocks = m_8x8Width > 2 && m_8x8Height > 2 ? (m_cuCount + 4 - 2 * (m_8x8Width + m_8x8Height)) : m_cuCount;
-    m_bAdaptiveQuant = p.aqMode || p.bEnableWeightedPred;
+    m_bAdaptiveQuant = p.aqMode || p.bEnableWeightedPred || p.bEnableWeightedBiPred;   /* slicetype.cpp:517 */
     int slices = p.lookaheadSlices;
     if (slices && !p.poolWorkers) slices = 0;
     if (slices && p.sourceHeight < 720) slices = 0;
@@ -117,6 +117,11 @@ bool Lookahead::create(const Param& p)
     {
         m_numRowsPerSlice = m_8x8Height;
         m_numCoopSlices = 1;
+    }
+    if (p.forceCoopSlices > 0 && p.forceRowsPerSlice > 0)
+    {
+        m_numCoopSlices = p.forceCoopSlices;
+        m_numRowsPerSlice = p.forceRowsPerSlice;
     }
     m_mvcost = (uint16_t*)malloc((4 * 32768 + 1) * sizeof(uint16_t));
     if (!m_mvcost) return false;
@@ -207,6 +212,23 @@ Lowres* Lookahead::allocLowres()
     return l;
 }
 
+/* x265's own `struct Lowres` behind this layer: the arrays are the caller's */
+Lowres* Lookahead::adoptLowres(const Lowres& arrays)
+{
+    if (m_freeSlots.empty()) { snprintf(m_error, sizeof(m_error), "adoptLowres: no free frame slot"); return NULL; }
+    Lowres* l = (Lowres*)calloc(1, sizeof(Lowres));
+    if (!l) return NULL;
+    *l = arrays;
+    l->arena = NULL; l->arenaBytes = 0;
+    l->width = m_geom.width; l->lines = m_geom.lines; l->lumaStride = m_geom.stride; l->bframes = m_param.bframes;
+    l->ready = false; l->propagateStale = false;
+    memset(l->mvVersion, 0, sizeof(l->mvVersion)); memset(l->devMvVersion, 0, sizeof(l->devMvVersion));
+    memset(l->costStamp, 0, sizeof(l->costStamp)); memset(l->devCostStamp, 0, sizeof(l->devCostStamp));
+    l->slot = m_freeSlots.back();
+    m_freeSlots.pop_back();
+    return l;
+}
+
 /* a frame is being re-initialised or released: nothing computed ahead from it may survive */
 void Lookahead::forgetFrame(Lowres* l)
 {
@@ -229,8 +251,11 @@ void Lookahead::freeLowres(Lowres* l)
      * those of a pre-lookahead list are held back until the next estimate batch): let them land before the memory goes */
     if (m_ctx) x265cu_sync(m_ctx);
     m_freeSlots.push_back(l->slot);
-    x265cu_host_unregister(l->arena);
-    free(l->arena);
+    if (l->arena)
+    {
+        x265cu_host_unregister(l->arena);
+        free(l->arena);
+    }
     free(l);
 }
 
@@ -269,16 +294,17 @@ bool Lookahead::lowresInit(Lowres& l, const void* luma, intptr_t stride, int poc
     return true;
 }
 
-/* LookaheadTLD::calcAdaptiveQuantFrame, encoder/slicetype.cpp:95-228 (no quantOffsets).
+/* LookaheadTLD::calcAdaptiveQuantFrame, encoder/slicetype.cpp:95-228.
  * The per-block AC energy and the wp sums come from the GPU; the mapping below is the host float. */
 bool Lookahead::calcAdaptiveQuantFrame(Lowres& l, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride,
-                                       const uint32_t* preEnergy, const uint64_t* preSums, bool publish)
+                                       const uint32_t* preEnergy, const uint64_t* preSums, bool publish, const float* quantOffsets)
 {
     const Param& param = m_param;
     int maxCol = param.sourceWidth, maxRow = param.sourceHeight;
     const int blocksX = (maxCol + 15) / 16, blocksY = (maxRow + 15) / 16;
     const int blockCount = m_cuCount;
-    const bool needVar = !(param.aqMode == 0 || param.aqStrength == 0) || param.bEnableWeightedPred;
+    const bool bWeighted = param.bEnableWeightedPred || param.bEnableWeightedBiPred;      /* slicetype.cpp:138,211 */
+    const bool needVar = !(param.aqMode == 0 || param.aqStrength == 0) || bWeighted;
     std::vector<uint32_t> energy((size_t)blocksX * blocksY);
     uint64_t sums[6] = { 0, 0, 0, 0, 0, 0 };
     if (needVar && preEnergy)
@@ -299,9 +325,18 @@ bool Lookahead::calcAdaptiveQuantFrame(Lowres& l, const void* y, intptr_t yStrid
     {
         if (param.aqMode && param.aqStrength == 0)
         {
-            memset(l.qpCuTreeOffset, 0, blockCount * sizeof(double));
-            memset(l.qpAqOffset, 0, blockCount * sizeof(double));
-            for (int i = 0; i < blockCount; i++) l.invQscaleFactor[i] = 256;
+            if (quantOffsets)
+                for (int i = 0; i < blockCount; i++)
+                {
+                    l.qpCuTreeOffset[i] = l.qpAqOffset[i] = quantOffsets[i];
+                    l.invQscaleFactor[i] = exp2fix8(l.qpCuTreeOffset[i]);
+                }
+            else
+            {
+                memset(l.qpCuTreeOffset, 0, blockCount * sizeof(double));
+                memset(l.qpAqOffset, 0, blockCount * sizeof(double));
+                for (int i = 0; i < blockCount; i++) l.invQscaleFactor[i] = 256;
+            }
         }
     }
     else
@@ -358,13 +393,15 @@ bool Lookahead::calcAdaptiveQuantFrame(Lowres& l, const void* y, intptr_t yStrid
                     uint32_t e = energy[blockXY];
                     qp_adj = strength * (log2((double)(e > 1 ? e : 1)) - (14.427f + 2 * (param.bitDepth - 8)));
                 }
+                if (quantOffsets != NULL)
+                    qp_adj += quantOffsets[blockXY];
                 l.qpAqOffset[blockXY] = qp_adj;
                 l.qpCuTreeOffset[blockXY] = qp_adj;
                 l.invQscaleFactor[blockXY] = exp2fix8(qp_adj);
                 blockXY++;
             }
     }
-    if (param.bEnableWeightedPred)
+    if (bWeighted)
     {
         maxCol = ((maxCol + 8) >> 4) << 4;
         maxRow = ((maxRow + 8) >> 4) << 4;
@@ -402,9 +439,10 @@ bool Lookahead::lowresIntraEstimate(Lowres& l)
 }
 
 /* PreLookaheadGroup::processTasks for one frame, encoder/slicetype.cpp:831-856 */
-bool Lookahead::preLookahead(Lowres& l, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride, int poc, bool copyPlanesBack)
+bool Lookahead::preLookahead(Lowres& l, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride, int poc, bool copyPlanesBack,
+                             const float* quantOffsets)
 {
-    const bool needVar = m_bAdaptiveQuant && (!(m_param.aqMode == 0 || m_param.aqStrength == 0) || m_param.bEnableWeightedPred);
+    const bool needVar = m_bAdaptiveQuant && (!(m_param.aqMode == 0 || m_param.aqStrength == 0) || m_param.bEnableWeightedPred || m_param.bEnableWeightedBiPred);
     if (needVar)
     {
         /* Lowres::init and acEnergyCu share one upload of the picture */
@@ -415,14 +453,14 @@ bool Lookahead::preLookahead(Lowres& l, const void* y, intptr_t yStride, const v
         int r = x265cu_frame_init_var(m_ctx, l.slot, y, yStride, u, v, cStride, m_resident ? 1 : 0,
                                       (copyPlanesBack && !m_resident) ? l.buffer[0] : NULL, &energy[0], sums);
         if (r) { snprintf(m_error, sizeof(m_error), "x265cu_frame_init_var: %s", x265cu_last_error(m_ctx)); return false; }
-        if (!calcAdaptiveQuantFrame(l, y, yStride, u, v, cStride, &energy[0], sums)) return false;
+        if (!calcAdaptiveQuantFrame(l, y, yStride, u, v, cStride, &energy[0], sums, true, quantOffsets)) return false;
     }
     else
     {
         if (!lowresInit(l, y, yStride, poc, copyPlanesBack)) return false;
         if (m_bAdaptiveQuant)
         {
-            if (!calcAdaptiveQuantFrame(l, y, yStride, u, v, cStride, NULL, NULL)) return false;
+            if (!calcAdaptiveQuantFrame(l, y, yStride, u, v, cStride, NULL, NULL, true, quantOffsets)) return false;
         }
         else
             x265cu_frame_set_invqscale(m_ctx, l.slot, NULL);
@@ -449,11 +487,11 @@ bool Lookahead::addPicture(Lowres& l, const PictureIn& pic)
  * back and the host waits once per stage (lowres + variance, then intra) instead of twice per frame. */
 bool Lookahead::preLookaheadBatch(int n, Lowres** ls, const PictureIn* pics, bool copyPlanesBack)
 {
-    const bool needVar = m_bAdaptiveQuant && (!(m_param.aqMode == 0 || m_param.aqStrength == 0) || m_param.bEnableWeightedPred);
+    const bool needVar = m_bAdaptiveQuant && (!(m_param.aqMode == 0 || m_param.aqStrength == 0) || m_param.bEnableWeightedPred || m_param.bEnableWeightedBiPred);
     if (!needVar || n < 2)
     {
         for (int i = 0; i < n; i++)
-            if (!preLookahead(*ls[i], pics[i].y, pics[i].yStride, pics[i].u, pics[i].v, pics[i].cStride, pics[i].poc, copyPlanesBack)) return false;
+            if (!preLookahead(*ls[i], pics[i].y, pics[i].yStride, pics[i].u, pics[i].v, pics[i].cStride, pics[i].poc, copyPlanesBack, pics[i].quantOffsets)) return false;
         return true;
     }
     const int blocks = ((m_param.sourceWidth + 15) / 16) * ((m_param.sourceHeight + 15) / 16);
@@ -492,7 +530,7 @@ bool Lookahead::preLookaheadBatch(int n, Lowres** ls, const PictureIn* pics, boo
         static void one(AqCtx* a, int i)
         {
             if (!a->la->calcAdaptiveQuantFrame(*a->ls[i], a->pics[i].y, a->pics[i].yStride, a->pics[i].u, a->pics[i].v, a->pics[i].cStride,
-                                               a->items[i].energy, a->items[i].sums, false))
+                                               a->items[i].energy, a->items[i].sums, false, a->pics[i].quantOffsets))
                 a->ok = false;
         }
         static void run(void* user, int first, int count, const int32_t** invQ)
@@ -524,7 +562,7 @@ bool Lookahead::preLookaheadBatch(int n, Lowres** ls, const PictureIn* pics, boo
         std::vector<int> slots((size_t)n);
         for (int i = 0; i < n; i++)
         {
-            if (!calcAdaptiveQuantFrame(*ls[i], pics[i].y, pics[i].yStride, pics[i].u, pics[i].v, pics[i].cStride, items[i].energy, items[i].sums)) return false;
+            if (!calcAdaptiveQuantFrame(*ls[i], pics[i].y, pics[i].yStride, pics[i].u, pics[i].v, pics[i].cStride, items[i].energy, items[i].sums, true, pics[i].quantOffsets)) return false;
             slots[i] = ls[i]->slot;
         }
         r3 = x265cu_intra_batch(m_ctx, n, &slots[0], &outs[0]);
@@ -675,6 +713,7 @@ bool CostEstimateGroup::takeAhead(Lowres* fenc, Lowres* ref0, Lowres* ref1, int 
             if (e.doSearch[l]) fenc->mvVersion[l][(l ? d1 : d0) - 1] = e.newVersion[l];
         fenc->costStamp[d0][d1] = e.costStamp;
         fenc->costEst[d0][d1] = e.res.costEst;
+        fenc->costEstRaw[d0][d1] = e.res.costEstRaw;
         fenc->costEstAq[d0][d1] = e.res.costEstAq;
         if (d1 == 0) fenc->intraMbs[d0] += e.res.intraMbs;
         fenc->weightedRef[d0].present = 0;
@@ -989,6 +1028,7 @@ bool CostEstimateGroup::runEstimates(const EstReq* est, int n)
         fenc->weightedRef[d0].present = 0;
         if (wref[k].present) { fenc->weightedRef[d0] = wref[k]; fenc->weightedCostDelta[d0] = wdelta[k]; }
         fenc->costEst[d0][d1] = res[k].costEst;
+        fenc->costEstRaw[d0][d1] = res[k].costEstRaw;
         fenc->costEstAq[d0][d1] = res[k].costEstAq;
         if (d1 == 0)
             fenc->intraMbs[d0] += res[k].intraMbs;
@@ -1204,7 +1244,7 @@ int x265cuh_add_pictures(void* la, int n, void** frames, const void* const* y, c
 {
     for (int i = 0; i < n; i++)
     {
-        Lookahead::PictureIn p = { y[i], ys[i], u[i], v[i], cs[i], 0 };
+        Lookahead::PictureIn p = { y[i], ys[i], u[i], v[i], cs[i], 0, NULL };
         if (!((Lookahead*)la)->addPicture(*(Lowres*)frames[i], p)) return -1;
     }
     return 0;
@@ -1217,6 +1257,7 @@ int x265cuh_pre_lookahead_batch(void* la, int n, void** frames, const void* cons
     for (int i = 0; i < n; i++)
     {
         pics[i].y = y[i]; pics[i].yStride = ys[i]; pics[i].u = u[i]; pics[i].v = v[i]; pics[i].cStride = cs[i]; pics[i].poc = pocs[i];
+        pics[i].quantOffsets = NULL;
     }
     return ((Lookahead*)la)->preLookaheadBatch(n, (Lowres**)frames, n ? &pics[0] : NULL, planesBack != 0) ? 0 : -1;
 }

@@ -56,6 +56,9 @@ struct Param
     int fpsNum, fpsDenom;
     double qCompress;        /* rc.qCompress: m_cuTreeStrength = 5 * (1 - qCompress), slicetype.cpp:511 */
     int bEnableWeightedBiPred;
+    /* cooperative-slice geometry as the host computed it (Lookahead::Lookahead, slicetype.cpp:534-558); 0 = derive it here
+     * from lookaheadSlices / poolWorkers / sourceHeight */
+    int forceCoopSlices, forceRowsPerSlice;
 };
 
 struct WeightParam { int present, scale, denom, offset; };
@@ -72,6 +75,7 @@ struct Lowres
     void* lowresPlane[4];
     int64_t costEst[BFRAME_MAX + 2][BFRAME_MAX + 2];
     int64_t costEstAq[BFRAME_MAX + 2][BFRAME_MAX + 2];
+    int64_t costEstRaw[BFRAME_MAX + 2][BFRAME_MAX + 2];   /* before the B-frame scaling (slicetype.cpp:2053-2057); observation only */
     int32_t* rowSatds[BFRAME_MAX + 2][BFRAME_MAX + 2];
     int intraMbs[BFRAME_MAX + 2];
     int32_t* intraCost;
@@ -155,22 +159,29 @@ public:
     void destroy();
 
     Lowres* allocLowres();                 /* Lowres::create */
+    /* a Lowres whose arrays are the CALLER's (x265's own `struct Lowres`): every pointer member of `arrays`
+     * is taken as is, nothing is allocated or registered here (the caller pins its arrays if it wants asynchronous,
+     * in-place results); scalars (costEst ...) live in the returned object and are the caller's to mirror */
+    Lowres* adoptLowres(const Lowres& arrays);
     void freeLowres(Lowres* l);
     void forgetFrame(Lowres* l);            /* drop everything the look-ahead estimate cache derived from this frame */
     /* Lowres::init (lowres.cpp:128-165); luma = PicYuv::m_picOrg[0] padded as copyFromPicture does */
     bool lowresInit(Lowres& l, const void* luma, intptr_t stride, int poc, bool copyPlanesBack);
     /* LookaheadTLD::calcAdaptiveQuantFrame; planes padded like PicYuv */
     bool calcAdaptiveQuantFrame(Lowres& l, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride,
-                                const uint32_t* preEnergy = NULL, const uint64_t* preSums = NULL, bool publish = true);
+                                const uint32_t* preEnergy = NULL, const uint64_t* preSums = NULL, bool publish = true,
+                                const float* quantOffsets = NULL);
     void lowresReset(Lowres& l, int poc);   /* the host-side resets of Lowres::init */
     /* the padded planes of preLookahead(copyPlanesBack) are complete on the host after sync() */
     bool sync() { return x265cu_sync(m_ctx) == 0; }
     bool lowresIntraEstimate(Lowres& l);
     /* PreLookaheadGroup::processTasks for one frame */
-    bool preLookahead(Lowres& l, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride, int poc, bool copyPlanesBack);
+    bool preLookahead(Lowres& l, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride, int poc, bool copyPlanesBack,
+                      const float* quantOffsets = NULL);
 
     /* PreLookaheadGroup::processTasks for a list of frames: one wait per stage instead of two per frame */
-    struct PictureIn { const void* y; intptr_t yStride; const void* u; const void* v; intptr_t cStride; int poc; };
+    struct PictureIn { const void* y; intptr_t yStride; const void* u; const void* v; intptr_t cStride; int poc;
+                       const float* quantOffsets;   /* Frame::m_quantOffsets (x265_picture::quantOffsets), or NULL */ };
     bool preLookaheadBatch(int n, Lowres** frames, const PictureIn* pics, bool copyPlanesBack);
     /* Lookahead::addPicture (slicetype.cpp:633-650): the picture has arrived in the input queue; its upload starts now
      * (asynchronous) instead of when its pre-lookahead runs.  Optional; the picture must not change until then. */
