@@ -9,9 +9,12 @@ the host layer (x265cu::Lookahead / CostEstimateGroup) and the C ABI.
 
   value   device-resident: source pictures already in HBM, result arrays stay in HBM mirrors
           (only the per-estimate sums return); the host float decisions still run.
-  e2e     the reference-facing call path with HOST buffers: pictures are uploaded from pinned host
-          memory and every Lowres output array (planes, MVs, costs...) is copied back, inside the
-          timed region.
+  e2e     the reference-facing call path with HOST buffers, with x265 1.9's OWN lookahead as the host
+          (oracle/_ref/libx265gpu<depth>.so: the reference's objects with slicetype.cpp / lowres.cpp /
+          picyuv.cpp bound to libx265cu.so, integration/): pictures are uploaded from x265's pinned
+          PicYuv, every Lowres output array (planes, MVs, costs...) lands in x265's own arrays, and
+          x265's slicetypeDecide / scenecut / slicetypePath / cuTree control flow run inside the clock.
+  configs the same measurements for the other BASELINE configs (4K 8-bit, 4K 10-bit), N = 1.
   --impl reference   the UNMODIFIED x265 1.9 lookahead (oracle/_ref, C primitives) on the host
           cores, same clip and options, all threads.
 
@@ -92,35 +95,33 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------
 def reference_arm(args, rank, world):
-    """`--impl reference`: the reference's own CPU lookahead on the host cores (rank 0 only)."""
+    """`--impl reference`: the reference's own CPU lookahead on the host cores (rank 0 only; ONE CPU stream whatever --gpus)."""
     if rank != 0:
         return 0
     from harness.workloads import WORKLOADS, DESCRIPTIONS
     depth, w, h, nframes, seed, _pool, opts, _ = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
     pool = min(64, cores)          # one x265 thread pool holds at most 64 workers (threadpool.h:44)
-    times = []
-    kind = "reference"
-    for it in range(args.warmup + args.steps):
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "harness", "refrun.py"), args.workload, str(pool)],
-                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
-        if r.returncode != 0 or not r.stdout.strip():
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref lookahead driver failed: " + r.stderr.strip()[-200:]}))
-            return 0
-        out = json.loads(r.stdout.strip().splitlines()[-1])
-        kind = out["kind"]
-        if it >= args.warmup:
-            times.append(out["seconds"])
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "harness", "refrun.py"), args.workload, str(pool), str(args.warmup + args.steps), "ref"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    if r.returncode != 0 or not r.stdout.strip():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref lookahead driver failed: " + r.stderr.strip()[-200:]}))
+        return 0
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    kind = out["kind"]
+    times = out["seconds"][args.warmup:] or out["seconds"]
     total = sum(times)
     value = nframes * len(times) / total
     line = {
         "impl": "reference", "metric": "lookahead_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True,
+        "steps": len(times), "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8" if depth == 8 else "u16", "data": "synthetic",
         "config": {"workload": DESCRIPTIONS.get(args.workload, args.workload), "trace": args.workload, "frames_per_step": nframes,
-                   "resolution": "%dx%d" % (w, h), "bit_depth": depth},
+                   "resolution": "%dx%d" % (w, h), "bit_depth": depth,
+                   "streams": "1 CPU stream on all host cores whatever --gpus (a throughput baseline, not a per-stream ratio at N > 1)"},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": pool, "kind": kind,
-                         "sample": "whole workload (%d frames) per step, x265 1.9 Lookahead only (no frame encoders), C primitives (no asm: no yasm/nasm in the image), pool of %d threads" % (nframes, pool)},
+                         "sample": "whole workload (%d frames) per step, x265 1.9 Lookahead only (no frame encoders; harness/x265_la_driver.cpp, the "
+                                   "driver the GPU arm's e2e uses), C primitives (no asm: no yasm/nasm in the image), pool of %d threads" % (nframes, pool)},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -341,83 +342,86 @@ def timed(torch, dist, world, fn, steps):
     return float(ms.item())
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c1_1080p")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-parity", action="store_true")
-    ap.add_argument("--streams", type=int, default=8, help="auxiliary multi-stream measurement: streams per GPU (0/1 = skip)")
-    ap.add_argument("--profile-mode", action="store_true",
-                    help="short run for ncu: device-resident runner only, 1 warm-up + 1 timed step, no parity/e2e/baseline")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if (args.impl == "ours" and not args.profile_mode) else args.warmup
-    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+class X265Host:
+    """e2e arm: x265 1.9's OWN Lookahead (slicetypeDecide, slicetypeAnalyse, scenecut, slicetypePath, cuTree control flow, thread
+    pool) as the host of the GPU path -- oracle/_ref/libx265gpu<depth>.so = the reference's objects with slicetype.cpp / lowres.cpp /
+    picyuv.cpp bound to libx265cu.so (integration/).  Same lookahead-only driver, clip and pool size as `--impl reference`."""
 
-    if args.impl == "reference":
-        return reference_arm(args, rank, world)
+    def __init__(self, workload, device):
+        from harness import x265host as xh
+        from harness.workloads import WORKLOADS
+        self.xh = xh
+        depth, w, h, n, seed, pool, opts, _ = WORKLOADS[workload]
+        if not xh.available(depth, True):
+            raise RuntimeError("oracle/_ref/libx265gpu%d.so is not built (integration/build_x265_cu.py needs the reference tree at build time)" % depth)
+        os.environ["X265CU_DEVICE"] = str(device)
+        self.workload, self.n, self.pool = workload, n, pool
+        self.d = xh.LaDriver(depth, w, h, n, seed, opts, pool, True)
 
-    if world > 1 and env_int("X265CU_BENCH_PIN", 1):
-        pin_rank(local, env_int("LOCAL_WORLD_SIZE", world))
-    import torch
-    import torch.distributed as dist
-    import __graft_entry__ as ge
-    if rank == 0 or not os.path.exists(os.path.join(ROOT, "src", "x265_b200", "libx265cu.so")):
-        ge.build()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        # NCCL announces its version on stdout at communicator creation: keep stdout to the one JSON line
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
+    def totals(self):
+        import ctypes as C
+        t = (C.c_longlong * 8)()
+        self.d.L.x265glue_totals(t)
+        return list(t)
+
+    def parity(self, golden):
+        import tempfile
+        fd, path = tempfile.mkstemp(suffix=".trace")
+        os.close(fd)
         try:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-            dist.barrier()
-            torch.cuda.synchronize()
+            _, _, stats = self.d.run(trace=path, level=1)
+            mm = self.xh.compare_traces(path, golden, 1)
         finally:
-            sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
+            os.remove(path)
+        return mm, stats
 
+    def step(self):
+        return self.d.run()[0]
+
+    def close(self):
+        self.d.close()
+
+
+def hbm_peak():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    return (float(peaks.get("hbm_gbs", 6650.0)),
+            "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)")
+
+
+def measure(args, workload, torch, dist, world, local, rank, headline):
+    """every number of one workload: parity gates, value (resident), e2e (x265 as the host), kernel times, rooflines"""
     from harness import replay
     from harness.workloads import DESCRIPTIONS
     from oracle import pyoracle as po
     from src.x265_b200 import abi
 
-    trace = po.Trace(replay.trace_path(args.workload))
+    trace = po.Trace(replay.trace_path(workload))
     cfg = trace.cfg
     nframes = cfg["nframes"]
     clip = replay.Clip(cfg)
+    out = {"trace": workload, "workload": DESCRIPTIONS.get(workload, workload), "resolution": "%dx%d" % (cfg["width"], cfg["height"]),
+           "bit_depth": cfg["depth"], "frames_per_step": nframes}
 
-    # ---- parity gate on this very workload, through the same call path ----
+    # ---- parity gate on this very workload, through the replay call path (every array CRC of every estimate and cuTree step) ----
     parity = "skipped"
-    if not args.no_parity and not args.profile_mode:
+    if not args.no_parity:
         r = replay.CuReplay(trace, device=local, check=True, clip=clip)
         mm = r.run()
         nchk, nprop = r.njobs, r.npropagate
         r.close()
         if mm:
-            raise SystemExit("bench.py: parity FAILED on %s: %d mismatches, first %r" % (args.workload, len(mm), mm[0]))
+            raise SystemExit("bench.py: parity FAILED on %s: %d mismatches, first %r" % (workload, len(mm), mm[0]))
         parity = "bit-exact vs x265 1.9 reference trace: %d frames, %d estimates, %d cuTree propagate steps, every output array CRC" % (nframes, nchk, nprop)
+    out["parity"] = parity
 
     stream = torch.cuda.current_stream().cuda_stream
     sampler = ClockSampler(local)
 
-    if args.profile_mode:
-        res = Runner(trace, clip, stream, local, True, torch)
-        res.step()
-        ms = timed(torch, dist, world, res.step, 1)
-        st = res.la.stats()
-        res.close()
-        print(json.dumps({"profile_mode": True, "ms_per_step": ms, "launches": st["launches"]}))
-        return 0
-
-    # ---- value: device-resident ----
+    # ---- value: device-resident replay ----
     res = Runner(trace, clip, stream, local, True, torch)
     for _ in range(args.warmup):
         res.step()
@@ -458,123 +462,246 @@ def main():
         satd = {"error": str(ex)}
     ct_value = res.la.cutree_stats()
     npropagate = res.npropagate
+    units, njobs = res.units, res.njobs
     res.close()
 
-    # ---- e2e: host buffers in, all arrays back ----
-    e2e = Runner(trace, clip, stream, local, False, torch)
-    for _ in range(args.warmup):
-        e2e.step()
-    e2e.la.stats(reset=True)
-    ms_e2e = timed(torch, dist, world, e2e.step, args.steps)
-    st_e2e = e2e.la.stats(reset=True)
-    units, njobs = e2e.units, e2e.njobs
-    ct_e2e = e2e.la.cutree_stats()
-    e2e.close()
+    # ---- e2e: x265's own lookahead as the host (host pictures in, every Lowres array + planes back, host decisions in the clock) ----
+    e2e = None
+    try:
+        host = X265Host(workload, local)
+    except RuntimeError as ex:
+        host = None
+        e2e = {"value": None, "unit": "frames/s", "error": str(ex)}
+    if host:
+        mmh, hstats = ([], None) if args.no_parity else host.parity(replay.trace_path(workload))
+        if mmh:
+            raise SystemExit("bench.py: x265-host parity FAILED on %s: %d differences, first %r" % (workload, len(mmh), mmh[0]))
+        for _ in range(max(args.warmup - (0 if args.no_parity else 1), 1)):
+            host.step()
+        t0 = host.totals()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        secs = [host.step() for _ in range(args.steps)]
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - w0
+        t1 = host.totals()
+        tt = torch.tensor([sum(secs), wall], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        lookahead_s, wall_s = float(tt[0].item()), float(tt[1].item())
+        host.close()
+        e2e = {"value": world * nframes * args.steps / lookahead_s, "unit": "frames/s", "ms_per_step": 1e3 * lookahead_s / args.steps,
+               "h2d_bytes_per_step": (t1[1] - t0[1]) // args.steps, "d2h_bytes_per_step": (t1[2] - t0[2]) // args.steps,
+               "gpu_launches_per_step": (t1[3] - t0[3]) // args.steps,
+               "host": "x265 1.9's own Lookahead (slicetypeDecide / slicetypeAnalyse / scenecut / slicetypePath / cuTree control flow / thread pool of "
+                       "%d) bound to libx265cu.so; pictures in pinned PicYuv, every Lowres array and the padded planes back in x265's own arrays" % host.pool,
+               "clock": "the lookahead-only driver's clock (first addPicture -> last decided picture; Lookahead::create / x265cu_open outside, as for "
+                        "--impl reference), max over ranks; wall incl. open/close per step: %.2f ms" % (1e3 * wall_s / args.steps),
+               "parity": "skipped" if args.no_parity else "trace of this host == reference trace: %d estimates, every array CRC, every cuTreeFinish, every "
+                         "slice-type decision" % (hstats["jobs"] if hstats else 0),
+               "lookahead_cache": "%d of %d non-batch requests served from estimates launched ahead" % (t1[5] - t0[5], t1[7] - t0[7])}
+
+    # ---- auxiliary: the same call sequence replayed through the host layer with host buffers (no x265 in the loop) ----
+    e2e_replay = None
+    if headline and not args.quick:
+        rp = Runner(trace, clip, stream, local, False, torch)
+        for _ in range(args.warmup):
+            rp.step()
+        rp.la.stats(reset=True)
+        ms_rp = timed(torch, dist, world, rp.step, args.steps)
+        st_rp = rp.la.stats(reset=True)
+        rp.close()
+        e2e_replay = {"value": world * nframes * args.steps / (ms_rp * 1e-3), "unit": "frames/s", "ms_per_step": ms_rp / args.steps,
+                      "h2d_bytes_per_step": st_rp["h2d"] // args.steps, "d2h_bytes_per_step": st_rp["d2h"] // args.steps,
+                      "what": "the trace's calls replayed through x265cu::Lookahead with pinned host buffers, pre-marshalled (round 1's e2e)"}
     clocks = sampler.stop()
+
+    # ---- rooflines ----
+    hbm, peak_src = hbm_peak()
+    P = 1 if cfg["depth"] == 8 else 2
+    nCU = ((cfg["width"] // 2 + 7) // 8) * ((cfg["height"] // 2 + 7) // 8)
+    Np = nCU * 64
+    Nfull = cfg["width"] * cfg["height"]
+    alg = {   # algorithmic bytes per step
+        "lowres": 8 * Np * P * nframes,                        # A: per frame
+        "var": (Nfull + Nfull // 2) * P * nframes,             # luma + Cb + Cr read once per frame
+        "intra": (Np * P + 7 * nCU) * nframes,                 # B: per frame
+        "search": (5 * Np * P + 8 * nCU) * units,              # C: per (frame, list, distance) searched
+    }
+    kms = {k: v / args.steps for k, v in st["ms"].items()}
+    klaunch = {k: v / args.steps for k, v in st["launches"].items()}
+    dom = max(("lowres", "intra", "search", "cost", "weight", "var", "cutree"), key=lambda k: kms[k])
+    prof = {}
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except (OSError, ValueError):
+        pass
+    sm_mhz = clocks.get("sm_mhz") or 1965.0
+    issue_peak = 148 * 4 * sm_mhz * 1e6 / 1e9           # G warp-instructions / s: 4 schedulers per SM, one instruction per cycle each
+    roofline = None
+    pk = prof.get("search", {}).get(workload) or prof.get("search", {}).get("c1_1080p" if cfg["width"] == 1920 else "c2_4k")
+    if dom == "search" and pk and kms["search"] > 0:
+        # the search family is bound by instruction issue (ncu: DRAM traffic below the algorithmic bytes, ALU pipe 60-65 %): warp
+        # instructions per searched CU from the committed `ncu --set full` capture x the CUs searched per step / the measured kernel time
+        ginst = pk["warp_inst_per_cu"] * nCU * units / 1e9
+        achieved = ginst / (kms["search"] * 1e-3)
+        roofline = {"bound": "issue", "kernel": "plain_search_kernel (+ refine_kernel / search_kernel for small batches with a close hint)",
+                    "achieved": achieved, "peak": issue_peak, "unit": "Gwarp-inst/s", "frac": achieved / issue_peak,
+                    "peak_source": "148 SMs x 4 schedulers x %.0f MHz (median SM clock sampled during the timed region)" % sm_mhz,
+                    "traffic": pk["dram_bytes"] / pk["units"] * units / max(klaunch["search"], 1),
+                    "inst_source": pk.get("source"),
+                    "note": "per step, i.e. averaged over every search launch (small latency-bound launches included); the captured "
+                            "launch alone issued %.2f of 4 warp-inst/cycle/SM" % pk.get("ipc", 0)}
+    hbm_block = {}
+    for k in ("search", "lowres", "var", "intra"):
+        if kms.get(k, 0) > 0:
+            ach = alg[k] / (kms[k] * 1e-3) / 1e9
+            hbm_block[k] = {"achieved": ach, "frac": ach / hbm, "ms_per_step": kms[k], "launches_per_step": klaunch[k],
+                            "algorithmic_bytes_per_step": alg[k], "traffic": (prof.get(k, {}).get(workload) or {}).get("dram_bytes_per_unit")}
+    if roofline is None:
+        d = hbm_block.get(dom, {"achieved": 0.0, "frac": 0.0})
+        roofline = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": d["achieved"], "peak": hbm, "unit": "GB/s", "frac": d["frac"],
+                    "traffic": d.get("traffic"), "peak_source": peak_src}
+    if satd and "gpix_per_s" in satd:
+        roof_pix = hbm / (2 * P + 4.0 / 64)     # GB/s / (bytes per pixel pair) = Gpix/s
+        satd["roofline_gpix_per_s"] = roof_pix
+        satd["frac"] = satd["gpix_per_s"] / roof_pix
+        satd["gb_per_s"] = satd["bytes_per_launch"] / (satd["ms"] * 1e-3) / 1e9
+
+    # ---- CPU baseline (reported, not the target): the reference's own lookahead on the host cores ----
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1 and rank == 0:
+        cores = os.cpu_count() or 1
+        pool = min(64, cores)
+        rr = subprocess.run([sys.executable, os.path.join(ROOT, "harness", "refrun.py"), workload, str(pool), "1", "ref"],
+                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        try:
+            o = json.loads(rr.stdout.strip().splitlines()[-1])
+            sec = o["seconds"][-1]
+            cpu_baseline = {"value": nframes / sec, "unit": "frames/s", "cores": o["threads"], "kind": o["kind"],
+                            "sample": "the whole workload once (%d frames, %.1f s): x265 1.9 Lookahead only, same driver as the e2e arm, C primitives "
+                                      "(asm build impossible: no yasm/nasm in the image)" % (nframes, sec)}
+        except (ValueError, IndexError, KeyError):
+            cpu_baseline = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "failed: " + rr.stderr.strip()[-160:]}
+
+    out.update({
+        "value": world * nframes * args.steps / (ms_value * 1e-3), "ms_per_step": ms_value / args.steps,
+        "e2e": e2e, "e2e_replay": e2e_replay, "estimates_per_step": njobs, "searches_per_step": units,
+        "gpu_launches": int(sum(st["launches"].values())),
+        "kernel_ms_per_step": kms, "kernel_launches_per_step": klaunch,
+        "roofline": roofline, "hbm_roofline": {"peak": hbm, "unit": "GB/s", "peak_source": peak_src, "kernels": hbm_block},
+        "int_peak_gops": {"vabsdiff4": int_peak[0].value, "iadd": int_peak[1].value},
+        "satd_8x8": satd, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        "cutree": "%d propagate steps per step on the GPU (estimateCUPropagate, SURVEY 8f-1), one launch per run of steps; "
+                  "mirrors found stale: %d (re-uploaded)" % (npropagate, ct_value["reuploads"]),
+    })
+    return out, trace, clip
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c1_1080p")
+    ap.add_argument("--configs", default="c2_4k,c3_4k10", help="further BASELINE configs measured into the line's `configs` array (N = 1 only; '' = none)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="headline workload only, no auxiliary measurements")
+    ap.add_argument("--streams", type=int, default=8, help="auxiliary multi-stream measurement: streams per GPU (0/1 = skip)")
+    ap.add_argument("--profile-mode", action="store_true",
+                    help="short run for ncu: device-resident runner only, 1 warm-up + 1 timed step, no parity/e2e/baseline")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if (args.impl == "ours" and not args.profile_mode) else args.warmup
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+
+    if args.impl == "reference":
+        return reference_arm(args, rank, world)
+
+    if world > 1 and env_int("X265CU_BENCH_PIN", 1):
+        pin_rank(local, env_int("LOCAL_WORLD_SIZE", world))
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    if rank == 0 or not os.path.exists(os.path.join(ROOT, "src", "x265_b200", "libx265cu.so")):
+        ge.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        # NCCL announces its version on stdout at communicator creation: keep stdout to the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
+
+    if args.profile_mode:
+        from harness import replay
+        from oracle import pyoracle as po
+        trace = po.Trace(replay.trace_path(args.workload))
+        clip = replay.Clip(trace.cfg)
+        res = Runner(trace, clip, torch.cuda.current_stream().cuda_stream, local, True, torch)
+        res.step()
+        ms = timed(torch, dist, world, res.step, 1)
+        st = res.la.stats()
+        res.close()
+        print(json.dumps({"profile_mode": True, "ms_per_step": ms, "launches": st["launches"]}))
+        return 0
+
+    head, trace, clip = measure(args, args.workload, torch, dist, world, local, rank, True)
 
     # ---- auxiliary: several independent streams per GPU (the production shape, BASELINE configs[4]) ----
     multi = None
-    if args.streams > 1:
+    if args.streams > 1 and not args.quick:
         multi = multi_stream(torch, dist, world, trace, clip, local, args.streams, max(1, min(args.steps, 2)))
+    del trace, clip
+
+    # ---- the other BASELINE configs, same measurements (N = 1: the target config of north_star is 4K rc-lookahead 40) ----
+    configs = []
+    if world == 1 and not args.quick:
+        for wl in [w for w in args.configs.split(",") if w and w != args.workload]:
+            c, _, _ = measure(args, wl, torch, dist, world, local, rank, False)
+            configs.append(c)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel ----
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except (OSError, ValueError):
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    P = 1 if cfg["depth"] == 8 else 2
-    nCU = ((cfg["width"] // 2 + 7) // 8) * ((cfg["height"] // 2 + 7) // 8)
-    Np = nCU * 64
-    # SURVEY.md §8(d) algorithmic bytes per unit
-    alg = {
-        "lowres": 8 * Np * P * nframes,                         # A: per frame
-        "intra": (Np * P + 7 * nCU) * nframes,                  # B: per frame
-        "search": (5 * Np * P + 8 * nCU) * units,               # C: per (frame, list, distance) searched
-    }
-    kms = {k: v / args.steps for k, v in st["ms"].items()}
-    klaunch = {k: v / args.steps for k, v in st["launches"].items()}
-    dom = max(("lowres", "intra", "search", "cost", "weight", "var", "cutree"), key=lambda k: kms[k])
-    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/traffic.json holds
-    # dram__bytes_read.sum + dram__bytes_write.sum of the captured launch and how many units that launch processed);
-    # scaled to the units of an average launch here, like `achieved`
-    traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
-        if tj and cfg["width"] == tj.get("width") and klaunch[dom] > 0:
-            traffic = tj["dram_bytes"] / tj["units"] * (units if dom == "search" else nframes) / klaunch[dom]
-    except (OSError, ValueError, KeyError):
-        pass
-    if dom in alg and kms[dom] > 0:
-        per_launch_bytes = alg[dom] / max(klaunch[dom], 1)
-        avg_ms = kms[dom] / max(klaunch[dom], 1)
-        achieved = per_launch_bytes / (avg_ms * 1e-3) / 1e9
-    else:
-        achieved = 0.0
-    kname = {"search": "plain_search_kernel (+ refine_kernel / search_kernel for small batches with a close hint)"}.get(dom, dom + "_kernel")
-    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": traffic, "peak_source": peak_src,
-                "note": "the dominant kernel family (wavefront motion search) is bound by the dependent chain of integer passes per CU, "
-                        "not by HBM: its DRAM traffic is below the algorithmic bytes (planes are shared through L2); see int_roofline"}
-    # integer roofline of the search kernel: SAD/SATD pixel-ops actually performed per searched CU-list
-    # (~20 SAD + ~9 SATD 8x8 per search -> (20*2 + 9*7) * 64 int ops before packing)
-    ops_per_search_cu = (20 * 2 + 9 * 7) * 64
-    int_ops = ops_per_search_cu * nCU * units
-    int_roofline = {"achieved_gops": int_ops / (kms["search"] * 1e-3) / 1e9 if kms["search"] > 0 else 0.0,
-                    "peak_gops_vabsdiff4": int_peak[0].value, "peak_gops_iadd": int_peak[1].value,
-                    "ops_model": "(20 SAD*2 + 9 SATD*7 ops/px)*64 px per searched CU-list, un-packed (SURVEY.md 8d)"}
-    if int_peak[1].value > 0:
-        int_roofline["frac_of_iadd_peak"] = int_roofline["achieved_gops"] / int_peak[1].value
-    if satd and "gpix_per_s" in satd:
-        roof_pix = hbm_peak / (2 * P + 4.0 / 64)     # GB/s / (bytes per pixel pair) = Gpix/s
-        satd["roofline_gpix_per_s"] = roof_pix
-        satd["frac"] = satd["gpix_per_s"] / roof_pix
+    def compact(c):
+        keep = ("trace", "workload", "resolution", "bit_depth", "frames_per_step", "value", "ms_per_step", "e2e", "estimates_per_step",
+                "searches_per_step", "kernel_ms_per_step", "kernel_launches_per_step", "roofline", "hbm_roofline", "satd_8x8", "cpu_baseline", "parity")
+        return {k: c[k] for k in keep if k in c}
 
-
-    # ---- CPU baseline (reported, not the target): the reference's own lookahead on the host cores ----
-    cpu_baseline = None
-    if not args.no_cpu_baseline and world == 1:
-        cores = os.cpu_count() or 1
-        pool = min(64, cores)
-        rr = subprocess.run([sys.executable, os.path.join(ROOT, "harness", "refrun.py"), args.workload, str(pool)],
-                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
-        try:
-            o = json.loads(rr.stdout.strip().splitlines()[-1])
-            cpu_baseline = {"value": nframes / o["seconds"], "unit": "frames/s", "cores": o["threads"], "kind": o["kind"],
-                            "sample": "the whole workload once (%d frames, %.1f s): x265 1.9 Lookahead only, C primitives "
-                                      "(asm build impossible: no yasm/nasm)" % (nframes, o["seconds"])}
-        except (ValueError, IndexError, KeyError):
-            cpu_baseline = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "failed: " + rr.stderr.strip()[-160:]}
-
-    launches = int(sum(st["launches"].values()))
-    value = world * nframes * args.steps / (ms_value * 1e-3)
-    e2e_value = world * nframes * args.steps / (ms_e2e * 1e-3)
     line = {
-        "metric": "lookahead_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8" if cfg["depth"] == 8 else "u16", "data": "synthetic",
-        "config": {"workload": DESCRIPTIONS.get(args.workload, args.workload), "trace": args.workload, "frames_per_step": nframes,
-                   "estimates_per_step": njobs, "searches_per_step": units, "resolution": "%dx%d" % (cfg["width"], cfg["height"]),
+        "metric": "lookahead_frames_per_s", "value": head["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8" if head["bit_depth"] == 8 else "u16", "data": "synthetic",
+        "config": {"workload": head["workload"], "trace": head["trace"], "frames_per_step": head["frames_per_step"],
+                   "estimates_per_step": head["estimates_per_step"], "searches_per_step": head["searches_per_step"], "resolution": head["resolution"],
                    "streams": world, "parallelism": "%d independent stream(s), one per GPU, no collective on the cost path" % world,
                    "search_path": os.environ.get("X265CU_SEARCH_MODE", "2 (per search: plain wavefront kernel, or refine + commit for small batches with a close hint)"),
                    "lookahead_cache": os.environ.get("X265CU_LOOKAHEAD_CACHE", "1 (non-batch estimates predicted from the request history ride in one launch)"),
-                   "l2": "working set per step (%d frames x 4 padded planes + sources, > 300 MB) exceeds the 126 MB L2; no explicit flush" % nframes,
-                   "cutree": "%d propagate steps per step on the GPU (estimateCUPropagate, SURVEY 8f-1), one launch per run of steps; "
-                             "mirrors found stale: %d resident / %d e2e (re-uploaded)" % (npropagate, ct_value["reuploads"], ct_e2e["reuploads"]),
-                   "parity": parity},
-        "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": st_e2e["h2d"] // args.steps, "d2h_bytes_per_step": st_e2e["d2h"] // args.steps},
-        "gpu_launches": launches,
-        "kernel_ms_per_step": kms, "kernel_launches_per_step": klaunch,
-        "roofline": roofline, "int_roofline": int_roofline, "satd_8x8": satd,
-        "cpu_baseline": cpu_baseline, "clocks": clocks, "multi_stream": multi,
+                   "l2": "working set per step (%d frames x 4 padded planes + sources, > 300 MB) exceeds the 126 MB L2; no explicit flush" % head["frames_per_step"],
+                   "cutree": head["cutree"], "parity": head["parity"],
+                   "value_is": "device-resident replay of the reference's call sequence (pictures in HBM, arrays stay in HBM)",
+                   "e2e_is": "x265 1.9's own lookahead as the host, host pictures in, every Lowres array back (see e2e.host)"},
+        "e2e": head["e2e"], "e2e_replay": head["e2e_replay"],
+        "gpu_launches": head["gpu_launches"],
+        "kernel_ms_per_step": head["kernel_ms_per_step"], "kernel_launches_per_step": head["kernel_launches_per_step"],
+        "roofline": head["roofline"], "hbm_roofline": head["hbm_roofline"], "int_peak_gops": head["int_peak_gops"], "satd_8x8": head["satd_8x8"],
+        "cpu_baseline": head["cpu_baseline"], "clocks": head["clocks"], "multi_stream": multi,
+        "configs": [compact(head)] + [compact(c) for c in configs],
     }
     print(json.dumps(line))
     if world > 1:

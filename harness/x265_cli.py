@@ -29,6 +29,15 @@ CLI_CASES = {
     # are still filling in; each option alone is timing-stable.)
     # the 10-bit build (16-bit pixel kernels) inside the real encoder
     "cli_360p_10bit": (10, 640, 368, 20, 9, ["--preset", "medium", "--bframes", "3", "--rc-lookahead", "12"]),
+    # weightb WITHOUT weightp: calcAdaptiveQuantFrame must still produce wp_sum / wp_ssd (slicetype.cpp:138,211)
+    "cli_360p_weightb_only": (8, 640, 368, 24, 5, ["--preset", "medium", "--bframes", "3", "--rc-lookahead", "15", "--weightb", "--no-weightp"]),
+    # BASELINE.json configs at full size: [0] 1080p x 60 medium / bframes 4 / rc-lookahead 20 (the CLI line BASELINE states),
+    # [1] the same clip with --b-adapt 2 --rc-lookahead 40 + cuTree, [2] 4K 8-bit --rc-lookahead 40 --bframes 8 (16 frames),
+    # [3] the 10-bit 4K build with --preset slow (12 frames)
+    "cli_c0_1080p": (8, 1920, 1080, 60, 1234, ["--preset", "medium", "--bframes", "4", "--rc-lookahead", "20"]),
+    "cli_c1_1080p": (8, 1920, 1080, 60, 1234, ["--preset", "medium", "--bframes", "4", "--rc-lookahead", "40", "--b-adapt", "2"]),
+    "cli_c2_4k": (8, 3840, 2160, 16, 4321, ["--preset", "medium", "--bframes", "8", "--rc-lookahead", "40", "--b-adapt", "2"]),
+    "cli_c3_4k10": (10, 3840, 2160, 12, 4321, ["--preset", "slow"]),
 }
 # results depend on the pool size: pin it to values every machine can provide
 PIN = ["--pools", "4", "--frame-threads", "2"]
@@ -77,8 +86,18 @@ if __name__ == "__main__":
     import json
     kind = sys.argv[1] if len(sys.argv) > 1 else "ref"
     res = {}
+    import time
+    only = [a for a in sys.argv[2:] if not a.startswith("--")]
+    old = {}
+    if kind == "ref" and only:
+        old = json.load(open(os.path.join(ROOT, "tests", "golden", "cli_md5.json")))
+    res.update(old)
     for nm in CLI_CASES:
+        if only and nm not in only:
+            continue
+        t0 = time.time()
         md5, size, _ = run_case(kind, nm)
+        print("%.1f s" % (time.time() - t0), end=" ")
         res[nm] = {"md5": md5, "bytes": size}
         print(nm, md5, size, flush=True)
     if kind == "ref" and "--write-golden" in sys.argv:

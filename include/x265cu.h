@@ -86,6 +86,10 @@ int  x265cu_sync(x265cu_ctx* ctx);
  * registered range are written there by the GPU itself instead of being staged and memcpy'd by a host thread */
 int  x265cu_host_register(void* ptr, size_t bytes);
 int  x265cu_host_unregister(void* ptr);
+/* Work buffers a context grew on demand (argument / staging areas of x265cu_estimate_batch and friends) are kept in a
+ * process-wide pool when the context closes and handed to the next context of the same device, so that an encoder
+ * opened after another one starts warm (cudaMalloc / cudaMallocHost synchronise the device).  This frees the pool. */
+void x265cu_trim(void);
 
 /* ---- Lowres::init (common/lowres.cpp:128-165): frame_init_lowres_core (common/pixel.cpp:549-573)
  * + extendPicBorder x4 (pixel.cpp:908-922).  `luma` points at PicYuv::m_picOrg[0]; the caller's

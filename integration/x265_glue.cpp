@@ -26,6 +26,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <pthread.h>
+#include <time.h>
 
 namespace xr = X265_NS;
 
@@ -75,10 +76,32 @@ struct GlueState
 {
     x265cu::Lookahead la;
     std::map<xr::Lowres*, x265cu::Lowres*> shadows;
+    /* X265CU_GLUE_PROFILE=1: wall seconds and calls per call-out, printed by x265glue_close */
+    bool profile;
+    double secs[6];
+    long calls[6];
+    struct timespec opened;
+};
+
+enum { T_PRE = 0, T_SINGLE, T_BATCH, T_CTFETCH, T_SYNC, T_OTHER };
+
+struct Timed
+{
+    GlueState* st; int k; struct timespec t0;
+    Timed(GlueState* s, int kind) : st(s), k(kind) { if (st->profile) clock_gettime(CLOCK_MONOTONIC, &t0); }
+    ~Timed()
+    {
+        if (!st->profile) return;
+        struct timespec t1;
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        st->secs[k] += (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+        st->calls[k]++;
+    }
 };
 
 pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
 std::map<xr::Lookahead*, GlueState*> g_states;
+int64_t g_totals[8];        /* over every context closed so far: contexts, h2d bytes, d2h bytes, kernel launches, look-ahead cache stats[4] */
 
 GlueState* stateOf(xr::Lookahead* la)
 {
@@ -142,7 +165,7 @@ x265cu::Lowres* shadowOf(GlueState* st, xr::Lookahead* xla, xr::Lowres* xl)
         die("Lowres geometry", "Lowres::create and x265cu_get_geometry disagree");
     x265cu::Lowres* sh = st->la.adoptLowres(a);
     if (!sh) die("adoptLowres", st->la.m_error);
-    sh->frameNum = -1;
+    sh->frameNum = xl->frameNum;                        /* (Lowres::init ran: x265glue_pre_list) */
     st->shadows[xl] = sh;
     return sh;
 }
@@ -301,10 +324,13 @@ extern "C" void x265glue_open(xr::Lookahead* la)
     q.fpsNum = (int)p->fpsNum; q.fpsDenom = (int)p->fpsDenom;
     q.qCompress = p->rc.qCompress;
     GlueState* st = new GlueState;
+    st->profile = getenv("X265CU_GLUE_PROFILE") && atoi(getenv("X265CU_GLUE_PROFILE"));
+    memset(st->secs, 0, sizeof(st->secs)); memset(st->calls, 0, sizeof(st->calls));
     if (!st->la.create(q)) die("x265cu_open", st->la.m_error);
     if (st->la.m_8x8Width != la->m_8x8Width || st->la.m_8x8Height != la->m_8x8Height || st->la.m_8x8Blocks != la->m_8x8Blocks ||
         st->la.m_numCoopSlices != la->m_numCoopSlices || st->la.m_numRowsPerSlice != la->m_numRowsPerSlice)
         die("x265glue_open", "lookahead geometry differs from Lookahead::Lookahead");
+    clock_gettime(CLOCK_MONOTONIC, &st->opened);
     pthread_mutex_lock(&g_lock);
     g_states[la] = st;
     pthread_mutex_unlock(&g_lock);
@@ -318,6 +344,28 @@ extern "C" void x265glue_close(xr::Lookahead* la)
     if (st) g_states.erase(it);
     pthread_mutex_unlock(&g_lock);
     if (!st) return;
+    {
+        x265cu_stats xs;
+        if (x265cu_stats_get(st->la.m_ctx, &xs, 0) == 0)
+        {
+            pthread_mutex_lock(&g_lock);
+            g_totals[0]++; g_totals[1] += xs.h2dBytes; g_totals[2] += xs.d2hBytes;
+            for (int k = 0; k < X265CU_K_COUNT; k++) g_totals[3] += xs.launches[k];
+            for (int k = 0; k < 4; k++) g_totals[4 + k] += st->la.m_specStats[k];
+            pthread_mutex_unlock(&g_lock);
+        }
+    }
+    if (st->profile)
+    {
+        struct timespec t1;
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        static const char* names[6] = { "pre_list", "singleCost", "finishBatch", "cuTree fetch", "sync", "other" };
+        double sum = 0;
+        for (int k = 0; k < 6; k++) sum += st->secs[k];
+        fprintf(stderr, "x265glue: %.1f ms since open, %.1f ms inside the GPU call-outs:", 1e3 * ((double)(t1.tv_sec - st->opened.tv_sec) + 1e-9 * (double)(t1.tv_nsec - st->opened.tv_nsec)), 1e3 * sum);
+        for (int k = 0; k < 6; k++) fprintf(stderr, " %s %.1f ms / %ld;", names[k], 1e3 * st->secs[k], st->calls[k]);
+        fprintf(stderr, "\n");
+    }
     for (std::map<xr::Lowres*, x265cu::Lowres*>::iterator s = st->shadows.begin(); s != st->shadows.end(); ++s)
         st->la.freeLowres(s->second);
     st->shadows.clear();
@@ -325,10 +373,19 @@ extern "C" void x265glue_close(xr::Lookahead* la)
     delete st;
 }
 
+/* totals over every context closed so far (bench.py: bytes per step, launches per step) */
+extern "C" void x265glue_totals(long long* out8)
+{
+    pthread_mutex_lock(&g_lock);
+    memcpy(out8, g_totals, sizeof(g_totals));
+    pthread_mutex_unlock(&g_lock);
+}
+
 /* ================================================================================================ pre-lookahead */
 extern "C" void x265glue_pre_list(xr::Lookahead* la, xr::Frame** frames, int n)
 {
     GlueState* st = stateOf(la);
+    Timed timed(st, T_PRE);
     std::vector<x265cu::Lowres*> ls((size_t)n);
     std::vector<x265cu::Lookahead::PictureIn> pics((size_t)n);
     for (int i = 0; i < n; i++)
@@ -369,6 +426,7 @@ extern "C" void x265glue_ensure(xr::Lookahead* la, xr::Lowres** frames, int p0, 
         return;                                         /* cached (slicetype.cpp:1982) */
     if (p0 == b) die("estimateFrameCost", "I frame estimates should always be pre-calculated");
     GlueState* st = stateOf(la);
+    Timed timed(st, T_SINGLE);
     const int s0 = p0 < b && fenc->lowresMvs[0][d0 - 1][0].x == 0x7FFF;
     const int s1 = p1 > b && fenc->lowresMvs[1][d1 - 1][0].x == 0x7FFF;
     std::vector<x265cu::Lowres*> fr((size_t)(d0 + d1 + 1), (x265cu::Lowres*)NULL);
@@ -387,6 +445,7 @@ extern "C" int x265glue_finish_batch(xr::Lookahead* la, xr::Lowres** frames, con
     if (n > 0)
     {
         GlueState* st = stateOf(la);
+        Timed timed(st, T_BATCH);
         int lo = est[0], hi = est[2];
         for (int i = 0; i < n; i++) { lo = X265_MIN(lo, est[3 * i]); hi = X265_MAX(hi, est[3 * i + 2]); }
         std::vector<x265cu::Lowres*> fr((size_t)(hi - lo + 1), (x265cu::Lowres*)NULL);
@@ -422,6 +481,7 @@ extern "C" int x265glue_finish_batch(xr::Lookahead* la, xr::Lowres** frames, con
 extern "C" void x265glue_ct_zero(xr::Lookahead* la, xr::Lowres* frame)
 {
     GlueState* st = stateOf(la);
+    Timed timed(st, T_OTHER);
     st->la.cuTreeZero(*shadowOf(st, la, frame));
     if (traceLevel() && x265ref_hook_ctzero) x265ref_hook_ctzero(frame);
 }
@@ -429,6 +489,7 @@ extern "C" void x265glue_ct_zero(xr::Lookahead* la, xr::Lowres* frame)
 extern "C" int x265glue_propagate(xr::Lookahead* la, xr::Lowres** frames, double averageDuration, int p0, int p1, int b, int referenced)
 {
     GlueState* st = stateOf(la);
+    Timed timed(st, T_OTHER);
     const int d0 = b - p0, d1 = p1 - b;
     std::vector<x265cu::Lowres*> fr((size_t)(d0 + d1 + 1), (x265cu::Lowres*)NULL);
     fr[0] = knownShadow(st, la, frames[p0]);
@@ -449,6 +510,7 @@ extern "C" int x265glue_propagate(xr::Lookahead* la, xr::Lowres** frames, double
 extern "C" void x265glue_ct_fetch(xr::Lookahead* la, xr::Lowres* frame)
 {
     GlueState* st = stateOf(la);
+    Timed timed(st, T_CTFETCH);
     if (!st->la.propagateCost(*shadowOf(st, la, frame))) die("propagateCost", st->la.m_error);
 }
 
@@ -480,5 +542,6 @@ extern "C" void x265glue_ct_postswap(xr::Lookahead* la, xr::Lowres* a, xr::Lowre
 extern "C" void x265glue_sync(xr::Lookahead* la)
 {
     GlueState* st = stateOf(la);
+    Timed timed(st, T_SYNC);
     if (!st->la.sync()) die("x265cu_sync", x265cu_last_error(st->la.m_ctx));
 }

@@ -58,6 +58,9 @@ void x265glue_ct_finished(X265_NS::Lookahead* la, X265_NS::Lowres* frame, double
 /* ---- Lookahead::slicetypeDecide (slicetype.cpp:1005), before the mini-GOP is handed to the output queue: the padded
  * lowres planes copied back for weightPrediction.cpp have landed */
 void x265glue_sync(X265_NS::Lookahead* la);
+/* ---- harness: totals over every context closed so far: contexts, h2d bytes, d2h bytes, kernel launches,
+ * look-ahead estimate cache (launched ahead, handed out, computed on demand, requests) */
+void x265glue_totals(long long* out8);
 }
 
 #endif

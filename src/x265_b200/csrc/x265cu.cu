@@ -174,13 +174,44 @@ int fail(x265cu_ctx* c, int code, const char* msg)
 
 inline size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+/* Work buffers (argument / staging / memo areas) grow on demand.  cudaMalloc / cudaMallocHost / cudaFree cost 0.1-10 ms
+ * each and synchronise the device, so a buffer a context no longer needs (it grew, or the context closed) goes to a
+ * process-wide pool per device and the next request of any context is served from there: a new encoder instance in a
+ * process that has run one before starts warm.  x265cu_trim() empties the pool. */
+struct PooledBuf { void* p; size_t cap; int device; };
+std::mutex g_poolMtx;
+std::vector<PooledBuf> g_devPool, g_hostPool;
+
+void* poolTake(std::vector<PooledBuf>& pool, int device, size_t need, size_t* cap)
+{
+    std::lock_guard<std::mutex> lk(g_poolMtx);
+    int best = -1;
+    for (size_t i = 0; i < pool.size(); i++)
+        if (pool[i].device == device && pool[i].cap >= need && (best < 0 || pool[i].cap < pool[(size_t)best].cap)) best = (int)i;
+    if (best < 0) return NULL;
+    void* p = pool[(size_t)best].p;
+    *cap = pool[(size_t)best].cap;
+    pool[(size_t)best] = pool.back();
+    pool.pop_back();
+    return p;
+}
+
+void poolGive(std::vector<PooledBuf>& pool, int device, void* p, size_t cap)
+{
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_poolMtx);
+    PooledBuf b = { p, cap, device };
+    pool.push_back(b);
+}
+
 int growDevice(x265cu_ctx* c, uint8_t** p, size_t* cap, size_t need)
 {
     if (*cap >= need) return 0;
     CU_TRY(c, cudaStreamSynchronize(c->stream));
-    if (*p) cudaFree(*p);
+    poolGive(g_devPool, c->cfg.device, *p, *cap);
     *p = NULL; *cap = 0;
     size_t n = alignUp(need + need / 2, 1 << 20);
+    if ((*p = (uint8_t*)poolTake(g_devPool, c->cfg.device, need, cap)) != NULL) return 0;
     CU_TRY(c, cudaMalloc((void**)p, n));
     *cap = n;
     return 0;
@@ -190,9 +221,10 @@ int growHost(x265cu_ctx* c, uint8_t** p, size_t* cap, size_t need)
 {
     if (*cap >= need) return 0;
     CU_TRY(c, cudaStreamSynchronize(c->stream));
-    if (*p) cudaFreeHost(*p);
+    poolGive(g_hostPool, c->cfg.device, *p, *cap);
     *p = NULL; *cap = 0;
     size_t n = alignUp(need + need / 2, 1 << 20);
+    if ((*p = (uint8_t*)poolTake(g_hostPool, c->cfg.device, need, cap)) != NULL) return 0;
     CU_TRY(c, cudaMallocHost((void**)p, n));
     *cap = n;
     return 0;
@@ -281,22 +313,27 @@ void freeAll(x265cu_ctx* c)
 {
     cudaFree(c->dPlanes); cudaFree(c->dIntraCost); cudaFree(c->dIntraMode); cudaFree(c->dInvQ);
     cudaFree(c->dLowresCosts); cudaFree(c->dRowSatds); cudaFree(c->dMvs); cudaFree(c->dMvCosts);
-    cudaFree(c->dPropagate); cudaFree(c->dPropOut); if (c->hPropOut) cudaFreeHost(c->hPropOut);
-    cudaFree(c->dLut); cudaFree(c->dSrc); cudaFree(c->dSmall); cudaFree(c->dStage); cudaFree(c->dArgs); cudaFree(c->dGeneric); cudaFree(c->dMemo); cudaFree(c->dSrcLin); cudaFree(c->dUp); cudaFree(c->dPre);
+    cudaFree(c->dPropagate);
+    cudaFree(c->dLut); cudaFree(c->dSrc); cudaFree(c->dSmall);
+    /* the on-demand work buffers go back to the process-wide pool (growDevice / growHost); every stream of the context is
+     * idle here (x265cu_close waited for them) */
+    const int dev = c->cfg.device;
+    poolGive(g_devPool, dev, c->dPropOut, c->dPropOutCap); poolGive(g_hostPool, dev, c->hPropOut, c->hPropOutCap);
+    poolGive(g_devPool, dev, c->dStage, c->dStageCap); poolGive(g_devPool, dev, c->dArgs, c->dArgsCap);
+    poolGive(g_devPool, dev, c->dGeneric, c->dGenericCap); poolGive(g_devPool, dev, c->dMemo, c->dMemoCap);
+    poolGive(g_devPool, dev, c->dSrcLin, c->dSrcLinCap); poolGive(g_devPool, dev, c->dUp, c->dUpCap); poolGive(g_devPool, dev, c->dPre, c->dPreCap);
+    poolGive(g_hostPool, dev, c->hStage, c->hStageCap); poolGive(g_hostPool, dev, c->hArgs, c->hArgsCap); poolGive(g_hostPool, dev, c->hPre, c->hPreCap);
+    for (size_t i = 0; i < c->wPool.size(); i++) poolGive(g_devPool, dev, c->wPool[i], (size_t)4 * c->g.planeSize * c->pb + 256);
     if (c->upStream) cudaStreamDestroy(c->upStream);
     if (c->intraStream) cudaStreamDestroy(c->intraStream);
     for (size_t i = 0; i < c->slotUp.size(); i++)
     {
-        cudaFree(c->slotUp[i].d);
+        poolGive(g_devPool, dev, c->slotUp[i].d, c->slotUp[i].cap);
         if (c->slotUp[i].done) cudaEventDestroy(c->slotUp[i].done);
         if (c->slotUp[i].read) cudaEventDestroy(c->slotUp[i].read);
     }
     for (size_t i = 0; i < c->preEvents.size(); i++) cudaEventDestroy(c->preEvents[i]);
     for (size_t i = 0; i < c->upEvents.size(); i++) cudaEventDestroy(c->upEvents[i]);
-    if (c->hStage) cudaFreeHost(c->hStage);
-    if (c->hArgs) cudaFreeHost(c->hArgs);
-    if (c->hPre) cudaFreeHost(c->hPre);
-    for (size_t i = 0; i < c->wPool.size(); i++) cudaFree(c->wPool[i]);
     for (size_t i = 0; i < c->freeEvents.size(); i++) cudaEventDestroy(c->freeEvents[i]);
     if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
     if (c->copyStream) cudaStreamDestroy(c->copyStream);
@@ -456,6 +493,8 @@ void x265cu_close(x265cu_ctx* c)
     cudaSetDevice(c->cfg.device);
     cudaStreamSynchronize(c->stream);
     if (c->copyStream) cudaStreamSynchronize(c->copyStream);
+    if (c->upStream) cudaStreamSynchronize(c->upStream);
+    if (c->intraStream) cudaStreamSynchronize(c->intraStream);
     if (getenv("X265CU_HOST_PROFILE"))
         fprintf(stderr, "x265cu_estimate_batch host time over %lld calls: planning %.2f ms (jobs %.2f, hints %.2f, items %.2f, args %.2f), enqueue %.2f ms, wait %.2f ms, scatter %.2f ms\n",
                 c->hostCalls, c->hostMs[0], c->planMs[0], c->planMs[1], c->planMs[2], c->planMs[3], c->hostMs[1], c->hostMs[2], c->hostMs[3]);
@@ -524,6 +563,15 @@ int x265cu_host_unregister(void* ptr)
     cudaError_t e = cudaHostUnregister(ptr);
     if (e != cudaSuccess) { cudaGetLastError(); return X265CU_ECUDA; }
     return X265CU_OK;
+}
+
+void x265cu_trim(void)
+{
+    std::lock_guard<std::mutex> lk(g_poolMtx);
+    for (size_t i = 0; i < g_devPool.size(); i++) { cudaSetDevice(g_devPool[i].device); cudaFree(g_devPool[i].p); }
+    for (size_t i = 0; i < g_hostPool.size(); i++) cudaFreeHost(g_hostPool[i].p);
+    g_devPool.clear();
+    g_hostPool.clear();
 }
 
 int x265cu_stats_enable(x265cu_ctx* c, int timing)
@@ -721,9 +769,12 @@ int x265cu_frame_upload(x265cu_ctx* c, int slot, const void* y, intptr_t yStride
     if (!su.done) { CU_TRY(c, cudaEventCreateWithFlags(&su.done, cudaEventDisableTiming)); CU_TRY(c, cudaEventCreateWithFlags(&su.read, cudaEventDisableTiming)); }
     if (su.cap < need)
     {
-        if (su.d) { CU_TRY(c, cudaStreamSynchronize(c->stream)); CU_TRY(c, cudaStreamSynchronize(c->upStream)); cudaFree(su.d); su.d = NULL; su.cap = 0; }
-        CU_TRY(c, cudaMalloc((void**)&su.d, need));
-        su.cap = need;
+        if (su.d) { CU_TRY(c, cudaStreamSynchronize(c->stream)); CU_TRY(c, cudaStreamSynchronize(c->upStream)); poolGive(g_devPool, c->cfg.device, su.d, su.cap); su.d = NULL; su.cap = 0; }
+        size_t got = 0;
+        void* sp = poolTake(g_devPool, c->cfg.device, need, &got);
+        if (sp && got > 2 * need) { poolGive(g_devPool, c->cfg.device, sp, got); sp = NULL; }
+        if (sp) { su.d = (uint8_t*)sp; su.cap = got; }
+        else { CU_TRY(c, cudaMalloc((void**)&su.d, need)); su.cap = need; }
         su.everRead = false;
     }
     /* the kernels that read the slot's previous picture from this area must be done with it */
@@ -1268,8 +1319,11 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     /* weighted reference pool */
     while (c->wPool.size() < weightedJobs.size())
     {
-        void* p = NULL;
-        CU_TRY(c, cudaMalloc(&p, (size_t)4 * g.planeSize * c->pb + 256));
+        const size_t wBytes = (size_t)4 * g.planeSize * c->pb + 256;
+        size_t got = 0;
+        void* p = poolTake(g_devPool, c->cfg.device, wBytes, &got);
+        if (p && got != wBytes) { poolGive(g_devPool, c->cfg.device, p, got); p = NULL; }    /* only an area of exactly this use */
+        if (!p) CU_TRY(c, cudaMalloc(&p, wBytes));
         c->wPool.push_back(p);
     }
 
