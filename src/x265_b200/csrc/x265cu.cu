@@ -137,6 +137,10 @@ struct x265cu_ctx
     int searchMode;        /* 0: plain kernel only, 1: speculative path only (with in-batch seed waves), 2: per search (default) */
     int specMaxDist, specMaxPlans;   /* speculative path: hint at most this many frames away, batch of at most this many searches */
     int plainWarps;        /* CU rows (= warps) per CTA of the plain kernel */
+    int plainOneShot;      /* plain kernel with a window: the no-move positions of a search measured in one burst (la_fast_path) */
+    int plainOct;          /* plain wavefront search: 1 = octet kernel (x265cu_search_oct.cuh, default), 0 = quad kernel (x265cu_search_plain.cuh) */
+    int octWarps;          /* octet kernel: bands of 4 CU rows (= warps) per CTA */
+    int octSlack, octSleep, octSleepFull, octFullWarps;   /* hand-off waits: extra distance (columns) and poll interval (ns) of launches with >= octFullWarps warps */
     int plainWin;          /* plain kernel's shared-memory window variant: -2 for 8-bit samples (default; measured 5 % slower at 16 bit), 1 always, 0 never, -1 only for launches that fill the GPU */
     long long dbgPlans[4];
     double hostMs[4], planMs[4];      /* estimate_batch host time: planning, enqueue, wait, scatter (X265CU_HOST_PROFILE) */
@@ -402,6 +406,26 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     c->plainWin = -2;
     if (const char* e = getenv("X265CU_PLAIN_WIN")) c->plainWin = atoi(e);
     if (const char* e = getenv("X265CU_PLAIN_ROWS")) c->plainWarps = atoi(e);
+    c->plainOneShot = 0;      /* measured: no gain at 1080p, 10 % slower at 4K (profiles/README.md, round 2) */
+    if (const char* e = getenv("X265CU_PLAIN_ONESHOT")) c->plainOneShot = atoi(e) != 0;
+    c->plainOct = 0; c->octWarps = 2;
+    if (const char* e = getenv("X265CU_PLAIN_OCT")) c->plainOct = atoi(e) != 0;
+    if (const char* e = getenv("X265CU_OCT_WARPS")) c->octWarps = atoi(e);
+    c->octSlack = 4; c->octSleep = 32; c->octSleepFull = 256; c->octFullWarps = 148 * 8;
+    if (const char* e = getenv("X265CU_OCT_SLACK")) c->octSlack = atoi(e);
+    if (const char* e = getenv("X265CU_OCT_SLEEP")) c->octSleep = atoi(e);
+    if (const char* e = getenv("X265CU_OCT_SLEEP_FULL")) c->octSleepFull = atoi(e);
+    if (const char* e = getenv("X265CU_OCT_FULL_WARPS")) c->octFullWarps = atoi(e);
+    if (c->octWarps < 1) c->octWarps = 1;
+    if (c->octWarps > OCT_MAX_WARPS) c->octWarps = OCT_MAX_WARPS;
+    {
+        const int smemMax = 96 * 1024;
+        cudaFuncSetAttribute(oct_search_kernel<uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax);
+        cudaFuncSetAttribute(oct_search_kernel<uint8_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax);
+        cudaFuncSetAttribute(oct_search_kernel<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax);
+        cudaFuncSetAttribute(oct_search_kernel<uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax);
+        while (c->octWarps > 1 && oct_smem_bytes<uint16_t>(c->octWarps, (cfg->srcWidth / 2 + 7) / 8) > (size_t)smemMax) c->octWarps--;
+    }
     if (c->plainWarps < 1) c->plainWarps = 1;
     if (c->plainWarps > PLAIN_MAX_GROUP_ROWS) c->plainWarps = PLAIN_MAX_GROUP_ROWS;
     memset(c->dbgPlans, 0, sizeof(c->dbgPlans));
@@ -498,6 +522,18 @@ void x265cu_close(x265cu_ctx* c)
     if (getenv("X265CU_HOST_PROFILE"))
         fprintf(stderr, "x265cu_estimate_batch host time over %lld calls: planning %.2f ms (jobs %.2f, hints %.2f, items %.2f, args %.2f), enqueue %.2f ms, wait %.2f ms, scatter %.2f ms\n",
                 c->hostCalls, c->hostMs[0], c->planMs[0], c->planMs[1], c->planMs[2], c->planMs[3], c->hostMs[1], c->hostMs[2], c->hostMs[3]);
+#ifdef X265CU_PLAIN_CLOCKS
+    {
+        unsigned long long h[16];
+        cudaMemcpyFromSymbol(h, g_plainClk, sizeof(h));
+        static const char* nm[10] = { "loop", "fenc+prefetch+neighbours(wait)", "window", "begin+CAND", "START", "HEX", "SQ8", "HPEL", "QPEL", "publish" };
+        const double n = h[15] ? (double)h[15] : 1.0;
+        fprintf(stderr, "plain kernel, cycles per CU step of warp 0 (%llu steps):", h[15]);
+        double tot = 0;
+        for (int i = 0; i < 10; i++) { fprintf(stderr, " %s %.0f;", nm[i], h[i] / n); tot += h[i] / n; }
+        fprintf(stderr, " total %.0f\n", tot);
+    }
+#endif
 #ifdef X265CU_SEARCH_STATS
     {
         unsigned long long h[32];
@@ -1453,7 +1489,7 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
         }
         if (k == classPlans[1]) classItems[1] = items.size();
         if (k == classPlans[2]) classItems[2] = items.size();
-        const int groupRows = plain ? c->plainWarps : c->searchWarps;
+        const int groupRows = plain ? (c->plainOct ? 4 * c->octWarps : c->plainWarps) : c->searchWarps;
         for (int s = 0; s < pl.numSlices; s++)
         {
             const int sFirst = pl.numSlices > 1 ? pl.rowsPerSlice * s : 0;
@@ -1490,7 +1526,7 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
         for (size_t k = classItems[2]; k < items.size(); k++)
         {
             const SearchItem& it = items[k];
-            keyed.push_back(std::make_pair((it.sliceLastY - it.lastY) / c->plainWarps, it));
+            keyed.push_back(std::make_pair((it.sliceLastY - it.lastY) / (c->plainOct ? 4 * c->octWarps : c->plainWarps), it));
         }
         std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<int, SearchItem>& a, const std::pair<int, SearchItem>& b) { return a.first < b.first; });
         for (size_t k = 0; k < keyed.size(); k++) items[classItems[2] + k] = keyed[k].second;
@@ -1537,7 +1573,7 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     }
     size_t offScat = alignUp(offW + weightedJobs.size() * sizeof(WeightDev), 256);
     size_t offProg = alignUp(offScat + devCopies.size() * sizeof(ScatterDev), 256);   /* device only: wavefront progress */
-    size_t argBytes = 8 + alignUp(offProg + (size_t)handRows * g.wCU * sizeof(unsigned long long), 256);
+    size_t argBytes = alignUp(offProg + (size_t)handRows * g.wCU * sizeof(unsigned long long) + sizeof(SearchCtl), 256);
     if (growHost(c, &c->hArgs, &c->hArgsCap, argBytes) || growDevice(c, &c->dArgs, &c->dArgsCap, argBytes)) return X265CU_ECUDA;
     if (growDevice(c, &c->dStage, &c->dStageCap, total) || growHost(c, &c->hStage, &c->hStageCap, total)) return X265CU_ECUDA;
 
@@ -1597,7 +1633,7 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     c->stats.h2dBytes += (int64_t)offProg;
     CU_TRY(c, cudaMemsetAsync(c->dStage, 0, sumsBytes, c->stream));
     if (!items.empty())
-        CU_TRY(c, cudaMemsetAsync(c->dArgs + offProg, 0, (size_t)handRows * g.wCU * sizeof(unsigned long long) + 8, c->stream));
+        CU_TRY(c, cudaMemsetAsync(c->dArgs + offProg, 0, (size_t)handRows * g.wCU * sizeof(unsigned long long) + sizeof(SearchCtl), c->stream));
 
     if (!weightedJobs.empty())
     {
@@ -1624,8 +1660,32 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
         const SearchItem* dItems = (const SearchItem*)(c->dArgs + offItems);
         const uint16_t* dLutC = c->dLut + 2 * 32768;
         unsigned long long* dProg = (unsigned long long*)(c->dArgs + offProg);
+        SearchCtl* dCtl = (SearchCtl*)(dProg + (size_t)handRows * g.wCU);      /* tickets + error word, zeroed with the hand-off rows */
         /* plain wavefront kernel: one CTA per row group, one warp per CU row */
-        if (classItems[3] > classItems[2])
+        if (classItems[3] > classItems[2] && c->plainOct)
+        {
+            /* octet kernel: a warp = a band of 4 CU rows in lock step, an octet per CU (x265cu_search_oct.cuh) */
+            const unsigned ni = (unsigned)(classItems[3] - classItems[2]);
+            const int bands = (maxPlainRows + 3) / 4;
+            const bool winVariant = c->plainWin != 0;
+            /* a launch that fills the GPU is throughput-bound: its bands keep a distance and poll rarely */
+            const bool full = ni * (unsigned)bands >= (unsigned)c->octFullWarps;
+            const int octSlack = full ? c->octSlack : 0;
+            const unsigned octSleep = full ? (unsigned)c->octSleepFull : (unsigned)c->octSleep;
+            if (c->pb == 1)
+            {
+                const size_t smem = oct_smem_bytes<uint8_t>(bands, g.wCU);
+                if (winVariant) oct_search_kernel<uint8_t, true><<<ni, bands * 32, smem, c->stream>>>(dJobs, dPlans, dItems + classItems[2], g, dLutC, dProg, dCtl, octSlack, octSleep);
+                else oct_search_kernel<uint8_t, false><<<ni, bands * 32, smem, c->stream>>>(dJobs, dPlans, dItems + classItems[2], g, dLutC, dProg, dCtl, octSlack, octSleep);
+            }
+            else
+            {
+                const size_t smem = oct_smem_bytes<uint16_t>(bands, g.wCU);
+                if (winVariant) oct_search_kernel<uint16_t, true><<<ni, bands * 32, smem, c->stream>>>(dJobs, dPlans, dItems + classItems[2], g, dLutC, dProg, dCtl, octSlack, octSleep);
+                else oct_search_kernel<uint16_t, false><<<ni, bands * 32, smem, c->stream>>>(dJobs, dPlans, dItems + classItems[2], g, dLutC, dProg, dCtl, octSlack, octSleep);
+            }
+        }
+        else if (classItems[3] > classItems[2])
         {
             const unsigned ni = (unsigned)(classItems[3] - classItems[2]);
             /* a launch that fills the GPU is bound by L1 line look-ups: it stages each CU's window in shared memory */
@@ -1634,13 +1694,15 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
             const size_t smem = (size_t)maxPlainRows * g.wCU * sizeof(unsigned long long) + (winVariant ? (size_t)maxPlainRows * WIN_PITCH * pbRow4 : 0);
             if (c->pb == 1)
             {
-                if (winVariant) plain_search_kernel<uint8_t, true><<<ni, maxPlainRows * 32, smem, c->stream>>>(dJobs, dPlans, dItems + classItems[2], g, dLutC, dProg);
-                else plain_search_kernel<uint8_t, false><<<ni, maxPlainRows * 32, smem, c->stream>>>(dJobs, dPlans, dItems + classItems[2], g, dLutC, dProg);
+                if (winVariant && c->plainOneShot) plain_search_kernel<uint8_t, true, true><<<ni, maxPlainRows * 32, smem, c->stream>>>(dJobs, dPlans, dItems + classItems[2], g, dLutC, dProg, &dCtl->ticket[0]);
+                else if (winVariant) plain_search_kernel<uint8_t, true, false><<<ni, maxPlainRows * 32, smem, c->stream>>>(dJobs, dPlans, dItems + classItems[2], g, dLutC, dProg, &dCtl->ticket[0]);
+                else plain_search_kernel<uint8_t, false, false><<<ni, maxPlainRows * 32, smem, c->stream>>>(dJobs, dPlans, dItems + classItems[2], g, dLutC, dProg, &dCtl->ticket[0]);
             }
             else
             {
-                if (winVariant) plain_search_kernel<uint16_t, true><<<ni, maxPlainRows * 32, smem, c->stream>>>(dJobs, dPlans, dItems + classItems[2], g, dLutC, dProg);
-                else plain_search_kernel<uint16_t, false><<<ni, maxPlainRows * 32, smem, c->stream>>>(dJobs, dPlans, dItems + classItems[2], g, dLutC, dProg);
+                if (winVariant && c->plainOneShot) plain_search_kernel<uint16_t, true, true><<<ni, maxPlainRows * 32, smem, c->stream>>>(dJobs, dPlans, dItems + classItems[2], g, dLutC, dProg, &dCtl->ticket[0]);
+                else if (winVariant) plain_search_kernel<uint16_t, true, false><<<ni, maxPlainRows * 32, smem, c->stream>>>(dJobs, dPlans, dItems + classItems[2], g, dLutC, dProg, &dCtl->ticket[0]);
+                else plain_search_kernel<uint16_t, false, false><<<ni, maxPlainRows * 32, smem, c->stream>>>(dJobs, dPlans, dItems + classItems[2], g, dLutC, dProg, &dCtl->ticket[0]);
             }
         }
         /* speculative path, per wave -- refine: every CU of every search in parallel (estimates + memo); then the commit
@@ -1658,15 +1720,17 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
             if (c->pb == 1)
             {
                 for (int it = 0; it < iters; it++) refine_kernel<uint8_t><<<sgrid, SPEC_WARPS * 32, 0, c->stream>>>(dJobs, dPlans + classPlans[w], g, dLutC, it);
-                search_kernel<uint8_t><<<ni, warps * 32, search_smem_bytes<uint8_t>(warps, g.wCU), c->stream>>>(dJobs, dPlans, dItems + classItems[w], g, dLutC, dProg, warps, iters > 0 ? (iters - 1) % 3 : -1);
+                search_kernel<uint8_t><<<ni, warps * 32, search_smem_bytes<uint8_t>(warps, g.wCU), c->stream>>>(dJobs, dPlans, dItems + classItems[w], g, dLutC, dProg, warps, iters > 0 ? (iters - 1) % 3 : -1, &dCtl->ticket[1 + w]);
             }
             else
             {
                 for (int it = 0; it < iters; it++) refine_kernel<uint16_t><<<sgrid, SPEC_WARPS * 32, 0, c->stream>>>(dJobs, dPlans + classPlans[w], g, dLutC, it);
-                search_kernel<uint16_t><<<ni, warps * 32, search_smem_bytes<uint16_t>(warps, g.wCU), c->stream>>>(dJobs, dPlans, dItems + classItems[w], g, dLutC, dProg, warps, iters > 0 ? (iters - 1) % 3 : -1);
+                search_kernel<uint16_t><<<ni, warps * 32, search_smem_bytes<uint16_t>(warps, g.wCU), c->stream>>>(dJobs, dPlans, dItems + classItems[w], g, dLutC, dProg, warps, iters > 0 ? (iters - 1) % 3 : -1, &dCtl->ticket[1 + w]);
             }
         }
         CU_TRY(c, cudaGetLastError());
+        /* the control words come back with the results: a hand-off wait that gave up is reported, never silent */
+        CU_TRY(c, cudaMemcpyAsync(c->hArgs + offProg, dCtl, sizeof(SearchCtl), cudaMemcpyDeviceToHost, c->stream));
     }
     if (!costIdx.empty())
     {
@@ -1692,6 +1756,8 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     const std::chrono::steady_clock::time_point tH2 = std::chrono::steady_clock::now();
     int r = syncStream(c);
     if (r) return r;
+    if (!items.empty() && ((const SearchCtl*)(c->hArgs + offProg))->error)
+        return fail(c, X265CU_ECUDA, "x265cu_estimate_batch: a wavefront hand-off wait timed out (search results incomplete)");
     const std::chrono::steady_clock::time_point tH3 = std::chrono::steady_clock::now();
 #ifdef X265CU_SEARCH_STATS
     if (!plans.empty() && getenv("X265CU_TRACE_BATCH"))

@@ -74,6 +74,19 @@ struct SearchItem
 #define SPEC_WARPS 8
 #define HAND_TAG (1ull << 32)
 
+/* control words behind the hand-off rows (zeroed with them before every launch).  A CTA takes its work item from a
+ * ticket instead of blockIdx: items are ordered so that an item only waits for items before it, and an item is only
+ * ever taken by a CTA that is already running, so every wait ends whatever order the hardware starts blocks in. */
+struct SearchCtl { unsigned int ticket[4]; unsigned int error; unsigned int pad[3]; };
+
+__device__ __forceinline__ int take_ticket(unsigned int* counter)
+{
+    __shared__ int sTicket;
+    if (threadIdx.x == 0) sTicket = (int)atomicAdd(counter, 1u);
+    __syncthreads();
+    return sTicket;
+}
+
 /* optional instrumentation for kernel tuning (compile with -DX265CU_SEARCH_STATS; never in the shipped library) */
 #ifdef X265CU_SEARCH_STATS
 __device__ unsigned long long g_searchStats[32];
@@ -518,10 +531,10 @@ __host__ __device__ inline size_t search_smem_bytes(int rows, int wCU)
 template <typename P>
 __global__ void __launch_bounds__(SEARCH_MAX_GROUP_ROWS * 32)
 search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restrict__ plans, const SearchItem* __restrict__ items, GeomDev g,
-              const uint16_t* __restrict__ lut, unsigned long long* gHand, int rowsMax, int estIdx)
+              const uint16_t* __restrict__ lut, unsigned long long* gHand, int rowsMax, int estIdx, unsigned int* ticket)
 {
     extern __shared__ unsigned long long sHand[];  /* [rowsMax][W] hand-off words, [rowsMax][W] estimates, one window per warp */
-    const SearchItem it = items[blockIdx.x];
+    const SearchItem it = items[take_ticket(ticket)];
     const SearchPlan pl = plans[it.search];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nRows = it.lastY - it.firstY + 1;

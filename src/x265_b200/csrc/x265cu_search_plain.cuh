@@ -9,8 +9,9 @@
  * Row groups of a few CU rows per CTA spread one slice over many SMs.  A finished CU publishes ONE 64-bit word
  * {tag = 1, packed MV}: tag and data travel in the same naturally aligned 8-byte store, so there is no separate
  * progress counter and no fence on the chain.  Inside a group the words live in shared memory, between groups in a
- * global hand-off row (L2).  A group only waits for a group with a LOWER block index (launched earlier), so the scheme
- * cannot deadlock even when a launch does not fit the GPU.  Passes are branch-free: every quad always measures a
+ * global hand-off row (L2).  A group only waits for an EARLIER work item, and items are taken from an atomic ticket
+ * (take_ticket), i.e. by CTAs that are already running: the scheme cannot deadlock even when a launch does not fit the
+ * GPU, whatever order the hardware starts blocks in.  Passes are branch-free: every quad always measures a
  * (valid-address) block and invalid candidates are masked out of the key reduction.
  */
 #ifndef X265CU_SEARCH_PLAIN_CUH
@@ -20,6 +21,13 @@
 #ifndef PWIN_MX
 #define PWIN_MX 2      /* window margin left of / above the first candidate's full-pel position */
 #define PWIN_MY 2
+#endif
+/* -DX265CU_PLAIN_CLOCKS (never in the shipped library): cycles per phase of a CU step, summed over the steps of warp 0 of every CTA */
+#ifdef X265CU_PLAIN_CLOCKS
+__device__ unsigned long long g_plainClk[16];
+#define PCLK(i) do { const long long now_ = clock64(); if (warp == 0 && lane == 0 && gridDim.x < 700) atomicAdd(&g_plainClk[i], (unsigned long long)(now_ - tPhase)); tPhase = now_; } while (0)
+#else
+#define PCLK(i) do { } while (0)
 #endif
 #ifndef PLAIN_MIN_CTAS
 #define PLAIN_MIN_CTAS 3
@@ -57,13 +65,13 @@ __device__ __forceinline__ void pfetch_fpel(const P* __restrict__ refLane, int s
     fetch_off<P>(refLane, stride, fy * stride + fx, out);
 }
 
-template <typename P, bool WIN>
+template <typename P, bool WIN, bool ONESHOT>
 __global__ void __launch_bounds__(PLAIN_MAX_GROUP_ROWS * 32, PLAIN_MIN_CTAS)
 plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restrict__ plans, const SearchItem* __restrict__ items, GeomDev g,
-                    const uint16_t* __restrict__ lut, unsigned long long* gHand)
+                    const uint16_t* __restrict__ lut, unsigned long long* gHand, unsigned int* ticket)
 {
     extern __shared__ unsigned long long sHand[];  /* [blockDim / 32][W] hand-off words (+ one window per warp, WIN) */
-    const SearchItem it = items[blockIdx.x];
+    const SearchItem it = items[take_ticket(ticket)];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nRows = it.lastY - it.firstY + 1;
     const int W = g.wCU, H = g.hCU;
@@ -136,8 +144,12 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
     for (int y = 0; y < 4; y++)
         feNext[y] = Px<P>::load_aligned(fencPlane + rowBase + 8 * (W - 1) + y * stride);
 
+#ifdef X265CU_PLAIN_CLOCKS
+    long long tPhase = clock64();
+#endif
     for (int cuX = W - 1; cuX >= 0; cuX--)
     {
+        PCLK(0);
 #pragma unroll
         for (int y = 0; y < 4; y++) fe[y] = feNext[y];
         if (cuX > 0)
@@ -174,6 +186,7 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
             if (cuX > 0) { if (numc == 1) nb1 = bl; else nb2 = bl; numc++; }
             if (cuX < W - 1) { if (numc == 2) nb2 = br; else nb3 = br; numc++; }
         }
+        PCLK(1);
         int lx = 0, ly = 0;
         if (WIN)
         {
@@ -187,6 +200,7 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
             __syncwarp();
             lx = bx - wx0; ly = by - wy0;
         }
+        PCLK(2);
         LaSearch s;
         la_search_begin(s, cuX, cuY, W, H, bidir, numc, nb0, nb1, nb2, nb3);
 
@@ -211,9 +225,73 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
         const uint16_t* __restrict__ lutx = lut - s.mvpx;
         const uint16_t* __restrict__ luty = lut - s.mvpy;
 
-        /* ---- START: q0 = qpel MVP (no mvcost), q1 = rounded MVP, q2 = zero ---- */
+        PCLK(3);
         la_enter_start(s);
+        int resume = LA_RESUME_HEX6;
+        if (ONESHOT)
         {
+            /* ---- one-shot: when nothing moves, every position the search visits is known once the MVP is (la_fast_path):
+             * they are all measured in ONE burst of four independent rounds from the window, and the reference's decisions
+             * are replayed on the costs.  A step's latency is then one pass instead of five dependent ones; a search that
+             * does move (~15 % of the CUs) resumes pass by pass below. ---- */
+            const int bm0x = (s.pmx + 2) >> 2, bm0y = (s.pmy + 2) >> 2;
+            {
+                /* the burst needs the window around the clipped MVP; it is usually where the first candidate put it */
+                const int wx0 = ((s.pmx >> 2) - PWIN_MX) & ~3, wy0 = (s.pmy >> 2) - PWIN_MY;
+                if (bx - wx0 != lx || by - wy0 != ly)
+                {
+                    const P* __restrict__ wbase = refPlane + (8 * cuY + wy0) * stride + 8 * cuX + wx0;
+                    __syncwarp();
+#pragma unroll
+                    for (int k = 0; k < (WIN_UNITS + 31) / 32; k++)
+                        if (lane + 32 * k < WIN_UNITS) win[lane + 32 * k] = Px<P>::load_aligned(wbase + wOff[k]);
+                    __syncwarp();
+                    lx = bx - wx0; ly = by - wy0;
+                }
+            }
+            /* round 1: q0 qpel MVP (no mvcost), q1 rounded MVP, q3..6 the 4 half-pel points around pm */
+            int cost1;
+            {
+                const int hq = (q >= 3 && q < 7) ? q - 2 : 0;
+                const int qx = (q == 1 ? bm0x * 4 : s.pmx) + la_sq1x(hq) * 2;
+                const int qy = (q == 1 ? bm0y * 4 : s.pmy) + la_sq1y(hq) * 2;
+                typename Px<P>::Row4 r[4];
+                win_qpel<P>(win, lx, ly, qx, qy, r);
+                const int mvc = q == 0 ? 0 : lutx[qx] + luty[qy];
+                cost1 = quad_sum(sad4x4<P>(fe, r)) + mvc;
+            }
+            /* rounds 2, 3: hexagon (6) + square points 1, 2 | square points 3..8 + the zero MV (from global memory) */
+            int cost2, cost3;
+            {
+                const int r2x = bm0x + (q < 6 ? la_hex2x(q + 1) : la_sq1x(q - 5)), r2y = bm0y + (q < 6 ? la_hex2y(q + 1) : la_sq1y(q - 5));
+                const int r3x = q < 6 ? bm0x + la_sq1x(q + 3) : 0, r3y = q < 6 ? bm0y + la_sq1y(q + 3) : 0;
+                typename Px<P>::Row4 r2[4], r3[4];
+                win_fpel<P>(win, lx, ly, r2x, r2y, r2);
+                if (q < 6) win_fpel<P>(win, lx, ly, r3x, r3y, r3);
+                else fetch_off<P>(refLane, stride, 0, r3);
+                cost2 = quad_sum(sad4x4<P>(fe, r2)) + lutx[r2x * 4] + luty[r2y * 4];
+                cost3 = quad_sum(sad4x4<P>(fe, r3)) + lutx[r3x * 4] + luty[r3y * 4];
+            }
+            /* round 4: SATD at pm and the 4 quarter-pel points around it */
+            int cost4;
+            {
+                const int k = q < 5 ? q : 0;
+                const int qx = s.pmx + la_sq1x(k), qy = s.pmy + la_sq1y(k);
+                typename Px<P>::Row4 r[4];
+                win_qpel<P>(win, lx, ly, qx, qy, r);
+                cost4 = (quad_sum(satd4x4_abs<P>(fe, r)) >> 1) + lutx[qx] + luty[qy];
+            }
+            const int c0 = __shfl_sync(FULL_MASK, cost1, 0), c1 = __shfl_sync(FULL_MASK, cost1, 4), c2 = __shfl_sync(FULL_MASK, cost3, 24);
+            const uint32_t hpelKey = warp_min_key(q >= 3 && q < 7, cost1, q - 3);
+            const uint32_t hexKey = warp_min_key(q < 6, cost2, q);
+            const uint32_t sqKey = __reduce_min_sync(FULL_MASK, q < 6 ? la_key(cost3, q + 2) : la_key(cost2, q - 6));
+            const int qc0 = __shfl_sync(FULL_MASK, cost4, 0);
+            const uint32_t qpelKey = warp_min_key(q >= 1 && q < 5, cost4, q);
+            resume = la_fast_path(s, c0, c1, c2, hexKey, sqKey, hpelKey, qc0, qpelKey, lut);
+        }
+        else
+        {
+            /* ---- START: q0 = qpel MVP (no mvcost), q1 = rounded MVP, q2 = zero ---- */
             const int qx = q == 0 ? s.pmx : (q == 1 ? ((s.pmx + 2) >> 2) * 4 : 0);
             const int qy = q == 0 ? s.pmy : (q == 1 ? ((s.pmy + 2) >> 2) * 4 : 0);
             typename Px<P>::Row4 r[4];
@@ -222,14 +300,20 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
             const int cost = quad_sum(sad4x4<P>(fe, r)) + mvc;
             la_upd_start(s, __shfl_sync(FULL_MASK, cost, 0), __shfl_sync(FULL_MASK, cost, 4), __shfl_sync(FULL_MASK, cost, 8));
         }
+        PCLK(4);
 
-        /* ---- HEX6 + HEX3 rounds: full-pel SAD + mvcost ---- */
+        if (resume != LA_RESUME_DONE)
         {
-            const int fx = s.bmx + hex6dx, fy = s.bmy + hex6dy;
-            typename Px<P>::Row4 r[4];
-            pfetch_fpel<P, WIN>(refLane, stride, win, lx, ly, fx, fy, r);
-            const int cost = quad_sum(sad4x4<P>(fe, r)) + lutx[fx * 4] + luty[fy * 4];
-            bool more = la_upd_hex6(s, warp_min_key(q < 6, cost, q));
+            /* ---- HEX6 + HEX3 rounds: full-pel SAD + mvcost ---- */
+            bool more = resume == LA_RESUME_HEX3;
+            if (resume == LA_RESUME_HEX6)
+            {
+                const int fx = s.bmx + hex6dx, fy = s.bmy + hex6dy;
+                typename Px<P>::Row4 r[4];
+                pfetch_fpel<P, WIN>(refLane, stride, win, lx, ly, fx, fy, r);
+                const int cost = quad_sum(sad4x4<P>(fe, r)) + lutx[fx * 4] + luty[fy * 4];
+                more = la_upd_hex6(s, warp_min_key(q < 6, cost, q));
+            }
             while (more)
             {
                 const int hdx = la_hex2x((s.dir + q) & 7), hdy = la_hex2y((s.dir + q) & 7);
@@ -239,38 +323,43 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
                 const int c3 = quad_sum(sad4x4<P>(fe, r3)) + lutx[hx * 4] + luty[hy * 4];
                 more = la_upd_hex3(s, warp_min_key(q < 3, c3, q));
             }
-        }
+            PCLK(5);
 
-        /* ---- SQ8: 8-point square ---- */
-        bool subpel;
-        {
-            const int fx = s.bmx + sq8dx, fy = s.bmy + sq8dy;
-            typename Px<P>::Row4 r[4];
-            pfetch_fpel<P, WIN>(refLane, stride, win, lx, ly, fx, fy, r);
-            const int cost = quad_sum(sad4x4<P>(fe, r)) + lutx[fx * 4] + luty[fy * 4];
-            subpel = la_upd_sq8(s, warp_min_key(true, cost, q), lut);
-        }
-
-        if (subpel)
-        {
-            /* ---- HPEL: 4 half-pel SADs ---- */
+            /* ---- SQ8: 8-point square ---- */
+            bool subpel = true;
+            if (resume <= LA_RESUME_SQ8)
             {
-                const int qx = s.bmx + hpdx, qy = s.bmy + hpdy;
+                const int fx = s.bmx + sq8dx, fy = s.bmy + sq8dy;
                 typename Px<P>::Row4 r[4];
-                pfetch_qpel<P, WIN>(refLane, planeSize, stride, win, lx, ly, qx, qy, r);
-                const int cost = quad_sum(sad4x4<P>(fe, r)) + lutx[qx] + luty[qy];
-                la_upd_hpel(s, warp_min_key(q < 4, cost, q));
+                pfetch_fpel<P, WIN>(refLane, stride, win, lx, ly, fx, fy, r);
+                const int cost = quad_sum(sad4x4<P>(fe, r)) + lutx[fx * 4] + luty[fy * 4];
+                subpel = la_upd_sq8(s, warp_min_key(true, cost, q), lut);
             }
-            /* ---- QPEL: SATD re-measure (q0) + 4 quarter-pel SATDs ---- */
+            PCLK(6);
+            if (subpel)
             {
-                const int qx = s.bmx + qpdx, qy = s.bmy + qpdy;
-                typename Px<P>::Row4 r[4];
-                pfetch_qpel<P, WIN>(refLane, planeSize, stride, win, lx, ly, qx, qy, r);
-                const int cost = (quad_sum(satd4x4_abs<P>(fe, r)) >> 1) + lutx[qx] + luty[qy];
-                const int c0 = __shfl_sync(FULL_MASK, cost, 0);
-                la_upd_qpel(s, c0, warp_min_key(q >= 1 && q < 5, cost, q));
+                /* ---- HPEL: 4 half-pel SADs ---- */
+                if (resume <= LA_RESUME_HPEL)
+                {
+                    const int qx = s.bmx + hpdx, qy = s.bmy + hpdy;
+                    typename Px<P>::Row4 r[4];
+                    pfetch_qpel<P, WIN>(refLane, planeSize, stride, win, lx, ly, qx, qy, r);
+                    const int cost = quad_sum(sad4x4<P>(fe, r)) + lutx[qx] + luty[qy];
+                    la_upd_hpel(s, warp_min_key(q < 4, cost, q));
+                }
+                PCLK(7);
+                /* ---- QPEL: SATD re-measure (q0) + 4 quarter-pel SATDs ---- */
+                {
+                    const int qx = s.bmx + qpdx, qy = s.bmy + qpdy;
+                    typename Px<P>::Row4 r[4];
+                    pfetch_qpel<P, WIN>(refLane, planeSize, stride, win, lx, ly, qx, qy, r);
+                    const int cost = (quad_sum(satd4x4_abs<P>(fe, r)) >> 1) + lutx[qx] + luty[qy];
+                    const int c0 = __shfl_sync(FULL_MASK, cost, 0);
+                    la_upd_qpel(s, c0, warp_min_key(q >= 1 && q < 5, cost, q));
+                }
             }
         }
+        PCLK(8);
         la_finish_skip(s);
 
         const int mvPacked = la_pack_mv(s.outx, s.outy);
@@ -286,6 +375,10 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
             mvOut[cuXY] = mvPacked;
             mcOut[cuXY] = s.outcost;
         }
+        PCLK(9);
+#ifdef X265CU_PLAIN_CLOCKS
+        if (warp == 0 && lane == 0 && gridDim.x < 700) atomicAdd(&g_plainClk[15], 1ull);
+#endif
     }
 }
 
