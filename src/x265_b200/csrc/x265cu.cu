@@ -532,6 +532,33 @@ void x265cu_close(x265cu_ctx* c)
         double tot = 0;
         for (int i = 0; i < 10; i++) { fprintf(stderr, " %s %.0f;", nm[i], h[i] / n); tot += h[i] / n; }
         fprintf(stderr, " total %.0f\n", tot);
+        {
+            unsigned long long hb[16], hc[8];
+            cudaMemcpyFromSymbol(hb, g_plainClkB, sizeof(hb)); cudaMemcpyFromSymbol(hc, g_plainCnt, sizeof(hc));
+            const double nb = hb[15] ? (double)hb[15] : 1.0;
+            fprintf(stderr, "  the picture's bottom CU row (%llu steps):", hb[15]);
+            double tb = 0;
+            for (int i = 0; i < 10; i++) { fprintf(stderr, " %s %.0f;", nm[i], hb[i] / nb); tb += hb[i] / nb; }
+            fprintf(stderr, " total %.0f | per step: CAND passes %.2f, HEX3 rounds %.2f\n", tb, hc[1] / nb, hc[2] / nb);
+        }
+        if (const char* path = getenv("X265CU_PLAIN_TRACE"))
+        {
+            static unsigned long long tt[160][256]; static unsigned int tw[160][256];
+            cudaMemcpyFromSymbol(tt, g_plainTraceT, sizeof(tt)); cudaMemcpyFromSymbol(tw, g_plainTraceW, sizeof(tw));
+            if (FILE* f = fopen(path, "w"))
+            {
+                unsigned long long t0 = ~0ull;
+                for (int r = 0; r < 160; r++) for (int i = 0; i < 256; i++) if (tt[r][i] && tt[r][i] < t0) t0 = tt[r][i];
+                for (int r = 0; r < 160; r++)
+                {
+                    if (!tt[r][0]) continue;
+                    fprintf(f, "row %d:", r);
+                    for (int i = 0; i < 256 && tt[r][i]; i++) fprintf(f, " %llu/%u", tt[r][i] - t0, tw[r][i]);
+                    fprintf(f, "\n");
+                }
+                fclose(f);
+            }
+        }
     }
 #endif
 #ifdef X265CU_SEARCH_STATS
@@ -827,6 +854,7 @@ int x265cu_frame_upload(x265cu_ctx* c, int slot, const void* y, intptr_t yStride
 
 static int preBatchImpl(x265cu_ctx* c, int n, const x265cu_frame_in* items, x265cu_aq_fn aq, void* user, x265cu_intra_out* outs);
 static int intraEnqueue(x265cu_ctx* c, int slot, x265cu_intra_out* out, unsigned long long* sums, unsigned long long* dBatchSums, cudaStream_t st);
+static int intraEnqueueBatch(x265cu_ctx* c, int count, const int* slots, x265cu_intra_out* const* outs, unsigned long long* dBatchSums, cudaStream_t st);
 
 int x265cu_frame_init_var_batch(x265cu_ctx* c, int n, const x265cu_frame_in* items)
 {
@@ -919,7 +947,122 @@ static int preBatchImpl2(x265cu_ctx* c, int n, const x265cu_frame_in* items, x26
         }
     }
     tB = std::chrono::steady_clock::now();
-    for (int i = 0; i < n; i++)
+    /* Frames whose picture is on the device (uploaded through the staging areas, or device pointers) go through the kernels
+     * a CHUNK at a time: one lowres launch (blockIdx.z = frame) and one variance launch (blockIdx.y = frame) per chunk, one
+     * copy of the chunk's records, one event.  Host mode keeps chunks short so that the first kernels start while the later
+     * pictures are still crossing PCIe. */
+    bool chunked = pipelined;
+    if (!pipelined)
+    {
+        chunked = true;
+        for (int i = 0; i < n; i++)
+            if (!items[i].planesAreDevice || ((uintptr_t)items[i].y & 7) || (((size_t)items[i].yStride * c->pb) & 7)) chunked = false;
+    }
+    if (getenv("X265CU_PRE_CHUNKED") && atoi(getenv("X265CU_PRE_CHUNKED")) == 0) chunked = false;
+    const int chunkMax = !chunked ? 1 : (pipelined ? (n >= 12 ? 4 : 2) : PRE_BATCH);
+    std::vector<int> chunkFirst;
+    for (int first = 0; first < n; first += chunkMax) chunkFirst.push_back(first);
+    chunkFirst.push_back(n);
+    if (aq)
+        while (c->preEvents.size() < chunkFirst.size())
+        {
+            cudaEvent_t e;
+            CU_TRY(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->preEvents.push_back(e);
+        }
+    for (size_t ch = 0; ch + 1 < chunkFirst.size() && chunked; ch++)
+    {
+        const int first = chunkFirst[ch], count = chunkFirst[ch + 1] - first;
+        LowresBatch lb; VarBatch vb;
+        memset(&lb, 0, sizeof(lb)); memset(&vb, 0, sizeof(vb));
+        bool staged[PRE_BATCH];
+        for (int k2 = 0; k2 < count; k2++)
+        {
+            const int i = first + k2;
+            const x265cu_frame_in& f = items[i];
+            if (badSlot(c, f.slot) || f.yStride < 2 * g.width + 1) return fail(c, X265CU_EINVAL, "x265cu_frame_init_var_batch: bad slot or stride");
+            const size_t yLin = (lumaRows - 1) * (size_t)f.yStride * c->pb + (size_t)(2 * g.width + 1) * c->pb;
+            const size_t cLin = f.u ? (chromaRows - 1) * (size_t)f.cStride * c->pb + (size_t)bxN * 8 * c->pb : 0;
+            staged[k2] = false;
+            if (pipelined)
+            {
+                x265cu_ctx::SlotUpload& su = c->slotUp[f.slot];
+                staged[k2] = su.valid && su.y == f.y && su.u == f.u && su.v == f.v && su.ys == f.yStride && su.cs == f.cStride;
+                const uint8_t* base = staged[k2] ? su.d : c->dUp + off[i];
+                lb.src[k2] = base; vb.y[k2] = base; vb.u[k2] = base + alignUp(yLin, 256); vb.v[k2] = base + alignUp(yLin, 256) + alignUp(cLin, 256);
+                CU_TRY(c, cudaStreamWaitEvent(c->stream, staged[k2] ? su.done : c->upEvents[i], 0));
+            }
+            else
+            {
+                lb.src[k2] = f.y; vb.y[k2] = f.y; vb.u[k2] = f.u; vb.v[k2] = f.v;
+            }
+            lb.planes[k2] = slotBuffer(c, f.slot);
+            lb.pitch[k2] = f.yStride; vb.ys[k2] = f.yStride; vb.cs[k2] = f.cStride;
+            vb.energy[k2] = (unsigned int*)(c->dPre + (size_t)i * per);
+            vb.sums[k2] = (unsigned long long*)(c->dPre + (size_t)i * per + eBytes);
+            for (size_t d = 0; d < c->deferredPlanes.size(); d++)
+                if (c->deferredPlanes[d].slot == f.slot) { int fr = flushDeferredPlanes(c); if (fr) return fr; break; }   /* a held-back copy of this slot's old planes */
+            if (c->planesPending[f.slot])
+                CU_TRY(c, cudaStreamWaitEvent(c->stream, c->planesCopied[f.slot], 0));   /* do not overwrite planes still being copied out */
+            c->slotPocKnown[f.slot] = 0;       /* a new picture in this slot: its order and its MV fields are unknown again */
+            std::fill(c->mvValid.begin() + (size_t)f.slot * 2 * (c->bf + 1), c->mvValid.begin() + (size_t)(f.slot + 1) * 2 * (c->bf + 1), 0);
+        }
+        {
+            KernelScope ks(c, X265CU_K_LOWRES);
+            const int padW = g.width + 2 * g.marginX;
+            dim3 grid((padW / 4 + 255) / 256, g.paddedLines, count);
+            if (c->pb == 1) lowres_init_batch_kernel<uint8_t><<<grid, 256, 0, c->stream>>>(lb, g);
+            else lowres_init_batch_kernel<uint16_t><<<grid, 256, 0, c->stream>>>(lb, g);
+        }
+        CU_TRY(c, cudaGetLastError());
+        for (int k2 = 0; k2 < count; k2++)
+        {
+            const x265cu_frame_in& f = items[first + k2];
+            if (f.planesOut && c->deferPlanes)
+            {
+                CU_TRY(c, cudaEventRecord(c->planesReady[f.slot], c->stream));
+                x265cu_ctx::DeferredPlanes d = { f.slot, f.planesOut };
+                c->deferredPlanes.push_back(d);
+            }
+            else if (f.planesOut)
+            {
+                const size_t bytes = (size_t)4 * g.planeSize * c->pb;
+                CU_TRY(c, cudaEventRecord(c->evKernel, c->stream));
+                CU_TRY(c, cudaStreamWaitEvent(c->copyStream, c->evKernel, 0));
+                CU_TRY(c, cudaMemcpyAsync(f.planesOut, slotBuffer(c, f.slot), bytes, cudaMemcpyDeviceToHost, c->copyStream));
+                CU_TRY(c, cudaEventRecord(c->planesCopied[f.slot], c->copyStream));
+                c->planesPending[f.slot] = 1;
+                c->stats.d2hBytes += (int64_t)bytes;
+            }
+        }
+        {
+            KernelScope ks(c, X265CU_K_VAR);
+            int blocks = (bxN * byN + 7) / 8;
+            const int cap = 148 * 8 / count > 148 ? 148 * 8 / count : 148;      /* warps stride over the 16x16 blocks */
+            if (blocks > cap) blocks = cap;
+            dim3 grid(blocks, count);
+            if (c->pb == 1) frame_var_batch_kernel<uint8_t><<<grid, 256, 0, c->stream>>>(vb, bxN, byN);
+            else frame_var_batch_kernel<uint16_t><<<grid, 256, 0, c->stream>>>(vb, bxN, byN);
+        }
+        CU_TRY(c, cudaGetLastError());
+        for (int k2 = 0; k2 < count; k2++)
+        {
+            const x265cu_frame_in& f = items[first + k2];
+            c->slotUp[f.slot].valid = false;        /* consumed (or superseded by this initialisation) */
+            if (staged[k2])
+            {
+                CU_TRY(c, cudaEventRecord(c->slotUp[f.slot].read, c->stream));
+                c->slotUp[f.slot].everRead = true;
+            }
+        }
+        if (aq)
+        {
+            /* the chunk's records come back in one copy, and an event tells the host (and the intra stream) they are there */
+            CU_TRY(c, cudaMemcpyAsync(c->hPre + (size_t)first * per, c->dPre + (size_t)first * per, (size_t)count * per, cudaMemcpyDeviceToHost, c->stream));
+            CU_TRY(c, cudaEventRecord(c->preEvents[ch], c->stream));
+        }
+    }
+    for (int i = 0; i < n && !chunked; i++)
     {
         const x265cu_frame_in& f = items[i];
         Uploaded up;
@@ -963,11 +1106,10 @@ static int preBatchImpl2(x265cu_ctx* c, int n, const x265cu_frame_in* items, x26
     {
         tC = std::chrono::steady_clock::now();
         int rc = X265CU_OK;
-        const int chunk = n >= 12 ? 8 : 1;
-        for (int first = 0; first < n && !rc; first += chunk)
+        for (size_t ch = 0; ch + 1 < chunkFirst.size() && !rc; ch++)
         {
-            const int count = first + chunk <= n ? chunk : n - first;
-            if (cudaEventSynchronize(c->preEvents[first + count - 1]) != cudaSuccess) { rc = fail(c, X265CU_ECUDA, "x265cu_pre_lookahead_batch: event wait failed"); break; }
+            const int first = chunkFirst[ch], count = chunkFirst[ch + 1] - first;
+            if (cudaEventSynchronize(c->preEvents[chunked ? ch : (size_t)(first + count - 1)]) != cudaSuccess) { rc = fail(c, X265CU_ECUDA, "x265cu_pre_lookahead_batch: event wait failed"); break; }
             const int32_t* invQs[8] = { NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL };
             for (int i = first; i < first + count; i++)
             {
@@ -975,11 +1117,14 @@ static int preBatchImpl2(x265cu_ctx* c, int n, const x265cu_frame_in* items, x26
                 memcpy(items[i].sums, c->hPre + (size_t)i * per + eBytes, 6 * sizeof(uint64_t));
             }
             aq(user, first, count, invQs);                      /* the host's float AQ mapping of these frames */
-            cudaStreamWaitEvent(c->intraStream, c->preEvents[first + count - 1], 0);
+            cudaStreamWaitEvent(c->intraStream, c->preEvents[chunked ? ch : (size_t)(first + count - 1)], 0);
+            int slots[PRE_BATCH];
+            x265cu_intra_out* po[PRE_BATCH];
             for (int i = first; i < first + count && !rc; i++)
             {
                 const int32_t* invQ = invQs[i - first];
                 const int slot = items[i].slot;
+                slots[i - first] = slot; po[i - first] = &outs[i];
                 c->hasInvQ[slot] = invQ != NULL;
                 if (invQ)
                 {
@@ -987,9 +1132,8 @@ static int preBatchImpl2(x265cu_ctx* c, int n, const x265cu_frame_in* items, x26
                     { rc = fail(c, X265CU_ECUDA, "x265cu_pre_lookahead_batch: invQscale upload failed"); break; }
                     c->stats.h2dBytes += (int64_t)g.nCU * sizeof(int);
                 }
-                rc = intraEnqueue(c, slot, &outs[i], (unsigned long long*)(c->hPre + intraSumsOff + (size_t)i * 16),
-                                  (unsigned long long*)(c->dPre + intraSumsOff + (size_t)i * 16), c->intraStream);
             }
+            if (!rc) rc = intraEnqueueBatch(c, count, slots, po, (unsigned long long*)(c->dPre + intraSumsOff + (size_t)first * 16), c->intraStream);
         }
         if (!rc && cudaMemcpyAsync(c->hPre + intraSumsOff, c->dPre + intraSumsOff, (size_t)n * 16, cudaMemcpyDeviceToHost, c->intraStream) != cudaSuccess)
             rc = fail(c, X265CU_ECUDA, "x265cu_pre_lookahead_batch: copy failed");
@@ -1078,6 +1222,79 @@ static int intraEnqueue(x265cu_ctx* c, int slot, x265cu_intra_out* out, unsigned
     return X265CU_OK;
 }
 
+/* lowresIntraEstimate of a few frames in one launch (blockIdx.y = frame); host destinations in mapped pinned memory are
+ * written by one small scatter launch, others by copies.  dBatchSums: [count][2] u64, zeroed by the caller. */
+static int intraEnqueueBatch(x265cu_ctx* c, int count, const int* slots, x265cu_intra_out* const* outs, unsigned long long* dBatchSums, cudaStream_t st)
+{
+    if (!st) st = c->stream;
+    const GeomDev& g = c->g;
+    for (int first = 0; first < count; first += INTRA_BATCH)
+    {
+        const int m = count - first < INTRA_BATCH ? count - first : INTRA_BATCH;
+        IntraBatch ib;
+        memset(&ib, 0, sizeof(ib));
+        for (int k = 0; k < m; k++)
+        {
+            const int slot = slots[first + k];
+            if (badSlot(c, slot)) return fail(c, X265CU_EINVAL, "x265cu_intra: bad slot");
+            IntraOutDev& o = ib.o[k];
+            ib.plane0[k] = slotPlane0(c, slot);
+            o.intraCost = slotIntraCost(c, slot);
+            o.intraMode = slotIntraMode(c, slot);
+            o.lowresCosts = slotLowresCosts(c, slot, 0, 0);
+            o.rowSatds = slotRowSatds(c, slot, 0, 0);
+            o.sums = dBatchSums + (size_t)(first + k) * 2;
+            o.invQ = c->hasInvQ[slot] ? slotInvQ(c, slot) : NULL;
+            CU_TRY(c, cudaMemsetAsync(o.rowSatds, 0, (size_t)g.hCU * sizeof(int), st));
+        }
+        {
+            KernelScope ks(c, X265CU_K_INTRA, 1, st);
+            dim3 grid((g.nCU + 7) / 8, m);
+            if (c->pb == 1) intra_batch_kernel<uint8_t><<<grid, 256, 0, st>>>(ib, g, c->cfg.lookaheadLambda, c->pixelMax);
+            else intra_batch_kernel<uint16_t><<<grid, 256, 0, st>>>(ib, g, c->cfg.lookaheadLambda, c->pixelMax);
+        }
+        CU_TRY(c, cudaGetLastError());
+        ScatterBatch sb;
+        int ns = 0;
+        for (int k = 0; k < m; k++)
+        {
+            x265cu_intra_out* out = outs[first + k];
+            if (!out) continue;
+            const IntraOutDev& o = ib.o[k];
+            void* dst[4] = { out->intraCost, out->intraMode, out->lowresCosts, out->rowSatds };
+            const void* src[4] = { o.intraCost, o.intraMode, o.lowresCosts, o.rowSatds };
+            const size_t len[4] = { (size_t)g.nCU * 4, (size_t)g.nCU, (size_t)g.nCU * 2, (size_t)g.hCU * 4 };
+            for (int a = 0; a < 4; a++)
+            {
+                if (!dst[a]) continue;
+                uint8_t* alias = c->mappedResults ? mappedAlias(dst[a], len[a]) : NULL;
+                if (alias)
+                {
+                    ScatterDev e = { (const uint8_t*)src[a], alias, (unsigned)len[a], 0 };
+                    sb.e[ns++] = e;
+                    if (ns == SCATTER_SMALL)
+                    {
+                        KernelScope ks(c, X265CU_K_RESULTS, 1, st);
+                        scatter_small_kernel<<<ns, 256, 0, st>>>(sb);
+                        CU_TRY(c, cudaGetLastError());
+                        ns = 0;
+                    }
+                }
+                else
+                    CU_TRY(c, cudaMemcpyAsync(dst[a], src[a], len[a], cudaMemcpyDeviceToHost, st));
+                c->stats.d2hBytes += (int64_t)len[a];
+            }
+        }
+        if (ns)
+        {
+            KernelScope ks(c, X265CU_K_RESULTS, 1, st);
+            scatter_small_kernel<<<ns, 256, 0, st>>>(sb);
+            CU_TRY(c, cudaGetLastError());
+        }
+    }
+    return X265CU_OK;
+}
+
 int x265cu_intra(x265cu_ctx* c, int slot, x265cu_intra_out* out)
 {
     if (!c) return X265CU_EINVAL;
@@ -1099,9 +1316,10 @@ int x265cu_intra_batch(x265cu_ctx* c, int n, const int* slots, x265cu_intra_out*
     CU_TRY(c, cudaSetDevice(c->cfg.device));
     if (growHost(c, &c->hPre, &c->hPreCap, (size_t)n * 16) || growDevice(c, &c->dPre, &c->dPreCap, (size_t)n * 16)) return X265CU_ECUDA;
     CU_TRY(c, cudaMemsetAsync(c->dPre, 0, (size_t)n * 16, c->stream));
-    for (int i = 0; i < n; i++)
     {
-        int r = intraEnqueue(c, slots[i], &outs[i], (unsigned long long*)(c->hPre + (size_t)i * 16), (unsigned long long*)(c->dPre + (size_t)i * 16), NULL);
+        std::vector<x265cu_intra_out*> po((size_t)n);
+        for (int i = 0; i < n; i++) po[i] = &outs[i];
+        int r = intraEnqueueBatch(c, n, slots, &po[0], (unsigned long long*)c->dPre, NULL);
         if (r) { cudaStreamSynchronize(c->stream); return r; }
     }
     CU_TRY(c, cudaMemcpyAsync(c->hPre, c->dPre, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));

@@ -34,8 +34,11 @@ __device__ __forceinline__ int intra_swap(int hor, int k)
     return (hor && k > 0) ? (k <= 16 ? k + 16 : k - 16) : k;
 }
 
+#define INTRA_BATCH 8
+struct IntraBatch { const void* plane0[INTRA_BATCH]; IntraOutDev o[INTRA_BATCH]; };
+
 template <typename P>
-__global__ void __launch_bounds__(256) intra_kernel(const P* __restrict__ plane0, GeomDev g, int lambda, int pixelMax, IntraOutDev o)
+__device__ __forceinline__ void intra_body(const P* __restrict__ plane0, const GeomDev& g, int lambda, int pixelMax, const IntraOutDev& o)
 {
     __shared__ P sNb[8][2][36];
     __shared__ short sExt[8][8][INTRA_EXT];
@@ -221,6 +224,19 @@ __global__ void __launch_bounds__(256) intra_kernel(const P* __restrict__ plane0
         }
         atomicAdd(&o.rowSatds[cuY], icostAq);
     }
+}
+
+template <typename P>
+__global__ void __launch_bounds__(256) intra_kernel(const P* __restrict__ plane0, GeomDev g, int lambda, int pixelMax, IntraOutDev o)
+{
+    intra_body<P>(plane0, g, lambda, pixelMax, o);
+}
+
+/* the frames of a pre-lookahead list in one launch: blockIdx.y = frame */
+template <typename P>
+__global__ void __launch_bounds__(256) intra_batch_kernel(IntraBatch b, GeomDev g, int lambda, int pixelMax)
+{
+    intra_body<P>((const P*)b.plane0[blockIdx.y], g, lambda, pixelMax, b.o[blockIdx.y]);
 }
 
 #endif /* X265CU_INTRA_CUH */

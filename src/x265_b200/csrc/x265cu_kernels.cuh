@@ -41,6 +41,24 @@ __global__ void __launch_bounds__(256) scatter_results_kernel(const ScatterDev* 
     for (unsigned i = done + threadIdx.x; i < s.bytes; i += blockDim.x) s.dst[i] = s.src[i];
 }
 
+/* the same with the entries passed by value (no argument upload): the intra outputs of a few frames */
+#define SCATTER_SMALL 32
+struct ScatterBatch { ScatterDev e[SCATTER_SMALL]; };
+__global__ void __launch_bounds__(256) scatter_small_kernel(ScatterBatch b)
+{
+    const ScatterDev s = b.e[blockIdx.x];
+    unsigned done = 0;
+    if ((((size_t)s.src | (size_t)s.dst) & 15) == 0)
+    {
+        const unsigned n16 = s.bytes >> 4;
+        const uint4* a = (const uint4*)s.src;
+        uint4* d = (uint4*)s.dst;
+        for (unsigned i = threadIdx.x; i < n16; i += blockDim.x) d[i] = a[i];
+        done = n16 << 4;
+    }
+    for (unsigned i = done + threadIdx.x; i < s.bytes; i += blockDim.x) s.dst[i] = s.src[i];
+}
+
 struct GeomDev
 {
     int width, lines, stride, marginX, marginY, paddedLines;
@@ -62,8 +80,14 @@ __device__ __forceinline__ int lowres_px(const P* r0, const P* r1, int c0, int c
     return (a + b + 1) >> 1;
 }
 
+/* frames of one pre-lookahead list share a launch: blockIdx.z (lowres) / blockIdx.y (variance, intra) = frame */
+#define PRE_BATCH 8
+struct LowresBatch { const void* src[PRE_BATCH]; void* planes[PRE_BATCH]; int64_t pitch[PRE_BATCH]; };
+struct VarBatch { const void* y[PRE_BATCH]; const void* u[PRE_BATCH]; const void* v[PRE_BATCH]; unsigned int* energy[PRE_BATCH]; unsigned long long* sums[PRE_BATCH];
+                  int64_t ys[PRE_BATCH], cs[PRE_BATCH]; };
+
 template <typename P>
-__global__ void __launch_bounds__(256) lowres_init_kernel(const P* __restrict__ src, int64_t srcPitch, P* __restrict__ planes, GeomDev g)
+__device__ __forceinline__ void lowres_init_body(const P* __restrict__ src, int64_t srcPitch, P* __restrict__ planes, const GeomDev& g)
 {
     const int oy = blockIdx.y;                                  /* padded row */
     const int ox0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4; /* padded column of the first of 4 samples */
@@ -117,6 +141,18 @@ __global__ void __launch_bounds__(256) lowres_init_kernel(const P* __restrict__ 
         {
             d0[i] = (P)o0[i]; dh[i] = (P)oh[i]; dv[i] = (P)ov[i]; dc[i] = (P)oc[i];
         }
+}
+
+template <typename P>
+__global__ void __launch_bounds__(256) lowres_init_kernel(const P* __restrict__ src, int64_t srcPitch, P* __restrict__ planes, GeomDev g)
+{
+    lowres_init_body<P>(src, srcPitch, planes, g);
+}
+
+template <typename P>
+__global__ void __launch_bounds__(256) lowres_init_batch_kernel(LowresBatch b, GeomDev g)
+{
+    lowres_init_body<P>((const P*)b.src[blockIdx.z], b.pitch[blockIdx.z], (P*)b.planes[blockIdx.z], g);
 }
 
 #include "x265cu_intra.cuh"
@@ -580,8 +616,8 @@ __global__ void __launch_bounds__(256) int_peak_kernel(int mode, int iters, unsi
  * as one 64-bit word per lane and summed with the packed-byte instructions.
  * =========================================================================================== */
 template <typename P>
-__global__ void __launch_bounds__(256) frame_var_kernel(const P* __restrict__ y, int64_t ys, const P* __restrict__ u, const P* __restrict__ v, int64_t cs,
-                                                         int blocksX, int blocksY, unsigned int* __restrict__ energy, unsigned long long* __restrict__ sums6)
+__device__ __forceinline__ void frame_var_body(const P* __restrict__ y, int64_t ys, const P* __restrict__ u, const P* __restrict__ v, int64_t cs,
+                                               int blocksX, int blocksY, unsigned int* __restrict__ energy, unsigned long long* __restrict__ sums6)
 {
     __shared__ unsigned long long sAcc[6];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warpsPerCta = blockDim.x >> 5;
@@ -635,6 +671,20 @@ __global__ void __launch_bounds__(256) frame_var_kernel(const P* __restrict__ y,
     }
     __syncthreads();
     if (threadIdx.x < 6 && sAcc[threadIdx.x]) atomicAdd(&sums6[threadIdx.x], sAcc[threadIdx.x]);
+}
+
+template <typename P>
+__global__ void __launch_bounds__(256) frame_var_kernel(const P* __restrict__ y, int64_t ys, const P* __restrict__ u, const P* __restrict__ v, int64_t cs,
+                                                         int blocksX, int blocksY, unsigned int* __restrict__ energy, unsigned long long* __restrict__ sums6)
+{
+    frame_var_body<P>(y, ys, u, v, cs, blocksX, blocksY, energy, sums6);
+}
+
+template <typename P>
+__global__ void __launch_bounds__(256) frame_var_batch_kernel(VarBatch b, int blocksX, int blocksY)
+{
+    const int f = blockIdx.y;
+    frame_var_body<P>((const P*)b.y[f], b.ys[f], (const P*)b.u[f], (const P*)b.v[f], b.cs[f], blocksX, blocksY, b.energy[f], b.sums[f]);
 }
 
 #endif /* X265CU_KERNELS_CUH */

@@ -25,9 +25,16 @@
 /* -DX265CU_PLAIN_CLOCKS (never in the shipped library): cycles per phase of a CU step, summed over the steps of warp 0 of every CTA */
 #ifdef X265CU_PLAIN_CLOCKS
 __device__ unsigned long long g_plainClk[16];
-#define PCLK(i) do { const long long now_ = clock64(); if (warp == 0 && lane == 0 && gridDim.x < 700) atomicAdd(&g_plainClk[i], (unsigned long long)(now_ - tPhase)); tPhase = now_; } while (0)
+__device__ unsigned long long g_plainClkB[16];   /* the same for the picture's bottom CU row (cuY == H - 1), all launches of < 700 CTAs */
+__device__ unsigned long long g_plainCnt[8];    /* bottom row: steps, CAND passes, HEX3 rounds, window misses (START, HEX6, SQ8, HPEL/QPEL) */
+__device__ unsigned long long g_plainTraceT[160][256];   /* [cuY][step]: globaltimer (ns) at the end of the step, launches of <= 24 CTAs */
+__device__ unsigned int g_plainTraceW[160][256];         /* cycles the step spent waiting for the row below */
+__device__ __forceinline__ unsigned long long gtimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define PCLK(i) do { const long long now_ = clock64(); if (lane == 0 && gridDim.x < 700) { if (lastRow && cuY != H - 1) atomicAdd(&g_plainClk[i], (unsigned long long)(now_ - tPhase)); if (cuY == H - 1) atomicAdd(&g_plainClkB[i], (unsigned long long)(now_ - tPhase)); } tPhase = now_; } while (0)
+#define PCNT(i, v) do { if (lane == 0 && gridDim.x < 700 && cuY == H - 1) atomicAdd(&g_plainCnt[i], (unsigned long long)(v)); } while (0)
 #else
 #define PCLK(i) do { } while (0)
+#define PCNT(i, v) do { } while (0)
 #endif
 #ifndef PLAIN_MIN_CTAS
 #define PLAIN_MIN_CTAS 3
@@ -139,6 +146,8 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
         wOff[k] = plane * planeSize + (rem / WIN_ROW_UNITS) * stride + (rem % WIN_ROW_UNITS) * 4;
     }
     int prevMv = 0;                                /* MV of (cuX + 1, cuY): our own previous result */
+    int prevBl = 0, prevMb = 0;                    /* MVs of (cuX, cuY + 1) and (cuX + 1, cuY + 1) as read in the step before */
+    unsigned long long nextWord = (!lastRow && W > 1) ? below[W - 2] : 0;   /* hand-off word of this step's below-left, loaded ahead */
     typename Px<P>::Row4 fe[4], feNext[4];
 #pragma unroll
     for (int y = 0; y < 4; y++)
@@ -150,6 +159,10 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
     for (int cuX = W - 1; cuX >= 0; cuX--)
     {
         PCLK(0);
+#ifdef X265CU_PLAIN_CLOCKS
+        const long long tStep0 = clock64();
+        long long tWaited = 0;
+#endif
 #pragma unroll
         for (int y = 0; y < 4; y++) fe[y] = feNext[y];
         if (cuX > 0)
@@ -176,17 +189,30 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
         if (cuX < W - 1) { nb0 = prevMv; numc = 1; }
         if (!lastRow)
         {
-            /* the row below runs right to left: its column cuX - 1 is published last */
-            int bl = 0, br = 0;
-            if (cuX > 0) bl = hand_wait(below + cuX - 1);
-            const int mb = hand_wait(below + cuX);
-            if (cuX < W - 1) br = hand_wait(below + cuX + 1);
+            /* the row below runs right to left: its column cuX - 1 is published last.  Only that word is new in this step
+             * (below and below-right were the below-left of the two steps before), and its load was issued one step ago:
+             * a row that lags the one below finds the word there, and a poll of the L2 hand-off row (~1 us round trip for
+             * the bottom row of a CTA) is no longer on the chain of every step */
+            int bl = 0, br = 0, mb;
+            if (cuX > 0)
+            {
+                unsigned long long w = nextWord;
+                while (!(w & HAND_TAG)) w = below[cuX - 1];
+                bl = (int)(uint32_t)w;
+            }
+            if (cuX == W - 1) mb = hand_wait(below + cuX); else mb = prevBl;
+            if (cuX < W - 1) br = prevMb;
+            prevMb = mb; prevBl = bl;
+            if (cuX > 1) nextWord = below[cuX - 2];
             if (numc == 0) nb0 = mb; else nb1 = mb;
             numc++;
             if (cuX > 0) { if (numc == 1) nb1 = bl; else nb2 = bl; numc++; }
             if (cuX < W - 1) { if (numc == 2) nb2 = br; else nb3 = br; numc++; }
         }
         PCLK(1);
+#ifdef X265CU_PLAIN_CLOCKS
+        tWaited = clock64() - tStep0;
+#endif
         int lx = 0, ly = 0;
         if (WIN)
         {
@@ -215,6 +241,7 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
         }
         else if (numc)
         {
+            PCNT(1, 1);
             const int p = la_cand_mv(s, q < numc ? q : 0);
             typename Px<P>::Row4 r[4];
             pfetch_qpel<P, WIN>(refLane, planeSize, stride, win, lx, ly, la_mv_x(p), la_mv_y(p), r);
@@ -316,6 +343,7 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
             }
             while (more)
             {
+                PCNT(2, 1);
                 const int hdx = la_hex2x((s.dir + q) & 7), hdy = la_hex2y((s.dir + q) & 7);
                 const int hx = s.bmx + hdx, hy = s.bmy + hdy;
                 typename Px<P>::Row4 r3[4];
@@ -377,7 +405,9 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
         }
         PCLK(9);
 #ifdef X265CU_PLAIN_CLOCKS
-        if (warp == 0 && lane == 0 && gridDim.x < 700) atomicAdd(&g_plainClk[15], 1ull);
+        if (lane == 0 && gridDim.x < 700 && lastRow && cuY != H - 1) atomicAdd(&g_plainClk[15], 1ull);
+        if (lane == 0 && gridDim.x < 700 && cuY == H - 1) atomicAdd(&g_plainClkB[15], 1ull);
+        if (lane == 0 && gridDim.x <= 24 && cuY < 160 && W <= 256) { g_plainTraceT[cuY][W - 1 - cuX] = gtimer_ns(); g_plainTraceW[cuY][W - 1 - cuX] = (unsigned int)tWaited; }
 #endif
     }
 }
