@@ -31,6 +31,10 @@ CLI_CASES = {
     "cli_360p_10bit": (10, 640, 368, 20, 9, ["--preset", "medium", "--bframes", "3", "--rc-lookahead", "12"]),
     # weightb WITHOUT weightp: calcAdaptiveQuantFrame must still produce wp_sum / wp_ssd (slicetype.cpp:138,211)
     "cli_360p_weightb_only": (8, 640, 368, 24, 5, ["--preset", "medium", "--bframes", "3", "--rc-lookahead", "15", "--weightb", "--no-weightp"]),
+    # luma AND chroma fade after the scene cut (seed bit 30, oracle/synth.h): weightAnalyse of the frame encoders runs its motion
+    # compensation and its weight sweeps on all three planes (on the GPU in the x265_cu build)
+    "cli_360p_fade": (8, 640, 368, 30, 0x40000005, ["--preset", "medium", "--bframes", "3", "--rc-lookahead", "15", "--weightb"]),
+    "cli_360p_fade10": (10, 640, 368, 24, 0x40000009, ["--preset", "medium", "--bframes", "3", "--rc-lookahead", "12"]),
     # BASELINE.json configs at full size: [0] 1080p x 60 medium / bframes 4 / rc-lookahead 20 (the CLI line BASELINE states),
     # [1] the same clip with --b-adapt 2 --rc-lookahead 40 + cuTree, [2] 4K 8-bit --rc-lookahead 40 --bframes 8 (16 frames),
     # [3] the 10-bit 4K build with --preset slow (12 frames)

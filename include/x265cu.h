@@ -181,6 +181,17 @@ typedef struct x265cu_weight_item
 } x265cu_weight_item;
 int x265cu_weight_cost_batch(x265cu_ctx* ctx, int n, const x265cu_weight_item* items, uint32_t* costs);
 
+/* ---- explicit weighted-prediction analysis of the frame encoders, weightAnalyse (encoder/weightPrediction.cpp:222-505):
+ * its three pixel loops on planes that are already on the device.  x265cu_wp_prepare names the (slice, list, plane) being
+ * analysed: the source frame and its list-0/1 reference by slot, plane 0 = lowres luma (Lowres::lowresPlane, intraCost limits
+ * every 8x8 SATD), 1 / 2 = the full-resolution Cb / Cr planes (kept on the device by x265cu_frame_init_var* /
+ * x265cu_pre_lookahead_batch).  lowresMvs != NULL (Lowres::lowresMvs[list][diffPoc - 1], host, cuCount vectors): the
+ * reference is motion compensated first -- mcLuma (:59-90) / mcChroma (:92-166, 4-tap filters of common/ipfilter.cpp).
+ * x265cu_wp_cost then measures weightCost (:168-220) for n candidate weights in one launch (weighted == 0: the plain
+ * reference = origscore).  The float guesses, the sweep with its early exits and the acceptance test stay the host's. */
+int x265cu_wp_prepare(x265cu_ctx* ctx, int fencSlot, int refSlot, int plane, const void* lowresMvs, const int32_t* intraCost);
+int x265cu_wp_cost(x265cu_ctx* ctx, int n, const x265cu_weight_item* cands, uint32_t* costs);
+
 /* ---- CostEstimateGroup::finishBatch / processTasks / estimateFrameCost body
  * (slicetype.cpp:1919-1975, 2004-2051) with estimateCUCost (:2068-2225) and the lowres branch of
  * MotionEstimate::motionEstimate (motion.cpp:571-1172).  One call = one batch (n = 1 for

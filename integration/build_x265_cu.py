@@ -5,7 +5,7 @@
                                      (harness/x265_la_driver.cpp): `bench.py` e2e arm, trace parity tests
   oracle/_ref/x265_cu<depth>         the full x265 CLI built the same way: bitstream md5 parity tests
 
-Only encoder/slicetype.cpp, common/lowres.cpp and common/picyuv.cpp differ from the stock build: they are compiled from
+Only encoder/slicetype.cpp, encoder/weightPrediction.cpp, common/lowres.cpp and common/picyuv.cpp differ from the stock build: they are compiled from
 temporary copies with the call-outs of integration/x265_glue.h inserted (make_gpu_sources.py).  Everything else is the
 reference's own objects as built by oracle/build_ref.py.
 """
@@ -17,8 +17,8 @@ ROOT = os.path.dirname(HERE)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import build_ref  # noqa: E402
 
-REPLACED = ("encoder_slicetype.o", "common_lowres.o", "common_picyuv.o")
-OURS = ("slicetype_plain.o", "slicetype_gpu.o", "lowres_gpu.o", "picyuv_gpu.o", "x265_glue.o", "x265_la_driver_gpu.o")
+REPLACED = ("encoder_slicetype.o", "common_lowres.o", "common_picyuv.o", "encoder_weightPrediction.o")
+OURS = ("slicetype_plain.o", "slicetype_gpu.o", "lowres_gpu.o", "picyuv_gpu.o", "weightpred_gpu.o", "weightpred_open.o", "x265_glue.o", "x265_la_driver_gpu.o")
 
 
 def main():
@@ -36,7 +36,7 @@ def main():
         build_ref.run([sys.executable, script, build_ref.REF_ROOT, gen])
         glue_h = os.path.join(HERE, "x265_glue.h")
         jobs = []
-        for name in ("slicetype_gpu", "lowres_gpu", "picyuv_gpu"):
+        for name in ("slicetype_gpu", "lowres_gpu", "picyuv_gpu", "weightpred_gpu"):
             jobs.append((os.path.join(gen, name + ".cpp"), os.path.join(obj, name + ".o"), F, [script, glue_h]))
         F11 = [f for f in F if f != "-std=gnu++98"] + ["-std=gnu++11"]
         jobs.append((os.path.join(HERE, "x265_glue.cpp"), os.path.join(obj, "x265_glue.o"), F11,
@@ -53,7 +53,7 @@ def main():
             (cli_objs if fn.startswith("cli_") else ref_objs).append(os.path.join(obj, fn))
         if not cli_objs:
             raise SystemExit("build_x265_cu: run oracle/build_ref.py --cli first")
-        gpu_objs = [os.path.join(obj, n) for n in ("slicetype_gpu.o", "lowres_gpu.o", "picyuv_gpu.o", "x265_glue.o")]
+        gpu_objs = [os.path.join(obj, n) for n in ("slicetype_gpu.o", "lowres_gpu.o", "picyuv_gpu.o", "weightpred_gpu.o", "x265_glue.o")]
         link = ["-L" + pkg, "-lx265cu_host", "-lx265cu", "-Wl,-rpath," + pkg, "-Wl,-rpath,$ORIGIN/../../src/x265_b200", "-lpthread", "-ldl", "-lm"]
         libs = [os.path.join(pkg, "libx265cu_host.so"), os.path.join(pkg, "libx265cu.so")]
         so = os.path.join(build_ref.OUT, "libx265gpu%d.so" % depth)

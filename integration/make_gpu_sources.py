@@ -5,6 +5,7 @@ usage: make_gpu_sources.py <reference source dir> <out dir>
   encoder/slicetype.cpp -> <out>/slicetype_gpu.cpp
   common/lowres.cpp     -> <out>/lowres_gpu.cpp
   common/picyuv.cpp     -> <out>/picyuv_gpu.cpp
+  encoder/weightPrediction.cpp -> <out>/weightpred_gpu.cpp
 
 Holds no reference source: it finds one-line anchors in the files it is given and inserts call-outs to
 integration/x265_glue.h.  The copies live under oracle/_ref/ (git-ignored).  What changes in x265 (reference line numbers
@@ -26,6 +27,10 @@ of x265_1.9/source):
     :155  Lowres::init                 frameInitLowres + 4x extendPicBorder skipped (the GPU writes the planes)
   picyuv.cpp
     :51   PicYuv::create / destroy     planes in pinned memory (uploads are asynchronous DMA)
+  weightPrediction.cpp
+    :168  weightCost                   + x265glue_wp_cost first (one launch: weight applied on the fly + 8x8 SATDs + intra limit)
+    :312,339,351  weightAnalyse        mcLuma / mcChroma skipped; + x265glue_wp_prepare before the sweep of a plane (motion
+                                       compensation on the device), x265glue_wp_done before mcbuf is freed
 """
 import os
 import re
@@ -164,11 +169,41 @@ def picyuv(src, out):
     p.write(out)
 
 
+def weightpred(src, out):
+    """encoder/weightPrediction.cpp: weightAnalyse keeps its float guesses, its sweep and its decisions; the three pixel
+    loops (mcLuma, mcChroma, weightCost) run on the planes the lookahead left on the device"""
+    p = Patch(src)
+    p.after(p.find(r'^using namespace X265_NS;'), '#include "x265_glue.h"')
+    i = p.find(r'^uint32_t weightCost\(pixel \*\s+fenc,')
+    p.after(p.find(r'^\{', i), '\n'.join([
+        '    {',
+        '        uint32_t gpuCost;',
+        '        if (x265glue_wp_cost(w != NULL, w ? w->inputWeight : 0, w ? (int)w->log2WeightDenom : 0, w ? w->inputOffset : 0, &gpuCost))',
+        '            return gpuCost;',
+        '    }']))
+    i = p.find(r'^void weightAnalyse\(Slice& slice, Frame& frame, x265_param& param\)')
+    k = p.find(r'^\s*mcLuma\(mcbuf, refLowres, mvs\);', i)
+    p.replaces[k] = p.lines[k].replace('mcLuma(', 'if (!x265glue_active()) mcLuma(')
+    n = 0
+    for k in range(i, len(p.lines)):
+        if re.match(r'^\s*mcChroma\(mcbuf, fref, stride, mvs, cache, height, width\);', p.lines[k]):
+            p.replaces[k] = p.lines[k].replace('mcChroma(', 'if (!x265glue_active()) mcChroma(')
+            n += 1
+        if re.match(r'^\s*X265_FREE\(mcbuf\);', p.lines[k]):
+            p.before(k, re.match(r'^(\s*)', p.lines[k]).group(1) + 'x265glue_wp_done();')
+    if n != 2:
+        raise SystemExit("make_gpu_sources: mcChroma anchors: %d" % n)
+    k = p.find(r'^\s*uint32_t origscore = weightCost\(orig, fref, weightTemp, stride, cache, width, height, NULL, !plane\);', i)
+    p.before(k, '            x265glue_wp_prepare(&frame, refFrame, plane, mvs);')
+    p.write(out)
+
+
 def main():
     ref, outdir = sys.argv[1], sys.argv[2]
     slicetype(os.path.join(ref, "encoder/slicetype.cpp"), os.path.join(outdir, "slicetype_gpu.cpp"))
     lowres(os.path.join(ref, "common/lowres.cpp"), os.path.join(outdir, "lowres_gpu.cpp"))
     picyuv(os.path.join(ref, "common/picyuv.cpp"), os.path.join(outdir, "picyuv_gpu.cpp"))
+    weightpred(os.path.join(ref, "encoder/weightPrediction.cpp"), os.path.join(outdir, "weightpred_gpu.cpp"))
 
 
 if __name__ == "__main__":

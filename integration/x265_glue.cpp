@@ -76,6 +76,8 @@ struct GlueState
 {
     x265cu::Lookahead la;
     std::map<xr::Lowres*, x265cu::Lowres*> shadows;
+    pthread_mutex_t mapLock;        /* the frame encoders look shadows up (weightAnalyse) while the lookahead adds / evicts them */
+    pthread_mutex_t wpLock;         /* one weightAnalyse at a time per context (x265cu_wp_prepare .. x265cu_wp_cost) */
     /* X265CU_GLUE_PROFILE=1: wall seconds and calls per call-out, printed by x265glue_close */
     bool profile;
     double secs[6];
@@ -132,8 +134,16 @@ void fillArrays(x265cu::Lowres& a, xr::Lowres* xl, int bframes)
 
 /* the shadow of an x265 Lowres (created on first sight).  Out of device slots: frames older than the last non-B frame
  * never take part in an estimate again (frames[0] = m_lastNonB is the oldest frame any call names) and give theirs up. */
+struct MapGuard
+{
+    pthread_mutex_t* m;
+    MapGuard(pthread_mutex_t* mm) : m(mm) { pthread_mutex_lock(m); }
+    ~MapGuard() { pthread_mutex_unlock(m); }
+};
+
 x265cu::Lowres* shadowOf(GlueState* st, xr::Lookahead* xla, xr::Lowres* xl)
 {
+    MapGuard guard(&st->mapLock);
     std::map<xr::Lowres*, x265cu::Lowres*>::iterator it = st->shadows.find(xl);
     if (it != st->shadows.end())
     {
@@ -324,6 +334,8 @@ extern "C" void x265glue_open(xr::Lookahead* la)
     q.fpsNum = (int)p->fpsNum; q.fpsDenom = (int)p->fpsDenom;
     q.qCompress = p->rc.qCompress;
     GlueState* st = new GlueState;
+    pthread_mutex_init(&st->mapLock, NULL);
+    pthread_mutex_init(&st->wpLock, NULL);
     st->profile = getenv("X265CU_GLUE_PROFILE") && atoi(getenv("X265CU_GLUE_PROFILE"));
     memset(st->secs, 0, sizeof(st->secs)); memset(st->calls, 0, sizeof(st->calls));
     if (!st->la.create(q)) die("x265cu_open", st->la.m_error);
@@ -399,7 +411,10 @@ extern "C" void x265glue_pre_list(xr::Lookahead* la, xr::Frame** frames, int n)
         pics[i] = in;
     }
     /* ONE pipelined call for the list: uploads, lowres + variance kernels, float AQ mapping (callback, host), intra */
-    if (!st->la.preLookaheadBatch(n, &ls[0], &pics[0], true)) die("preLookaheadBatch", st->la.m_error);
+    /* the lowres planes stay on the device: their only host-side reader was weightPrediction.cpp, whose pixel loops run
+     * there too (x265glue_wp_*); the trace harness checksums them, so it gets them */
+    const bool planesBack = traceLevel() > 0 || (getenv("X265CU_GLUE_PLANES_BACK") && atoi(getenv("X265CU_GLUE_PLANES_BACK")));
+    if (!st->la.preLookaheadBatch(n, &ls[0], &pics[0], planesBack)) die("preLookaheadBatch", st->la.m_error);
     for (int i = 0; i < n; i++)
     {
         xr::Lowres& xl = frames[i]->m_lowres;
@@ -537,6 +552,46 @@ extern "C" void x265glue_ct_postswap(xr::Lookahead* la, xr::Lowres* a, xr::Lowre
         if (x265cu_frame_set_propagate(st->la.m_ctx, sh->slot, sh->propagateCost)) die("x265cu_frame_set_propagate", x265cu_last_error(st->la.m_ctx));
         sh->propagateStale = false;
     }
+}
+
+/* ================================================================================================ weightAnalyse */
+namespace {
+__thread GlueState* t_wpState;      /* the context this thread's weightAnalyse is using (holds its wpLock) */
+}
+
+extern "C" void x265glue_wp_done(void)
+{
+    if (t_wpState) { pthread_mutex_unlock(&t_wpState->wpLock); t_wpState = NULL; }
+}
+
+extern "C" void x265glue_wp_prepare(xr::Frame* frame, xr::Frame* refFrame, int plane, const void* mvs)
+{
+    x265glue_wp_done();
+    GlueState* st = NULL;
+    x265cu::Lowres *sf = NULL, *sr = NULL;
+    pthread_mutex_lock(&g_lock);
+    for (std::map<xr::Lookahead*, GlueState*>::iterator it = g_states.begin(); it != g_states.end() && !st; ++it)
+    {
+        MapGuard guard(&it->second->mapLock);
+        std::map<xr::Lowres*, x265cu::Lowres*>::iterator f = it->second->shadows.find(&frame->m_lowres), r = it->second->shadows.find(&refFrame->m_lowres);
+        if (f != it->second->shadows.end() && r != it->second->shadows.end()) { st = it->second; sf = f->second; sr = r->second; }
+    }
+    pthread_mutex_unlock(&g_lock);
+    if (!st) die("weightAnalyse", "a frame whose lowres planes are no longer on the device (raise X265CU_FRAME_SLOTS)");
+    pthread_mutex_lock(&st->wpLock);
+    t_wpState = st;
+    if (x265cu_wp_prepare(st->la.m_ctx, sf->slot, sr->slot, plane, mvs, plane == 0 ? frame->m_lowres.intraCost : NULL))
+        die("x265cu_wp_prepare", x265cu_last_error(st->la.m_ctx));
+}
+
+extern "C" int x265glue_wp_cost(int weighted, int scale, int denom, int offset, unsigned int* cost)
+{
+    if (!t_wpState) die("weightCost", "no x265glue_wp_prepare before it");
+    x265cu_weight_item it = { 0, 0, weighted, scale, denom, offset };
+    uint32_t c = 0;
+    if (x265cu_wp_cost(t_wpState->la.m_ctx, 1, &it, &c)) die("x265cu_wp_cost", x265cu_last_error(t_wpState->la.m_ctx));
+    *cost = c;
+    return 1;
 }
 
 extern "C" void x265glue_sync(xr::Lookahead* la)

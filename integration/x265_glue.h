@@ -58,6 +58,13 @@ void x265glue_ct_finished(X265_NS::Lookahead* la, X265_NS::Lowres* frame, double
 /* ---- Lookahead::slicetypeDecide (slicetype.cpp:1005), before the mini-GOP is handed to the output queue: the padded
  * lowres planes copied back for weightPrediction.cpp have landed */
 void x265glue_sync(X265_NS::Lookahead* la);
+/* ---- weightAnalyse (encoder/weightPrediction.cpp:222-505, called by the frame encoders): before the sweep of a plane -- the
+ * source frame, its reference, the plane and the lowres vectors (or NULL) the motion-compensated copy is built with; every
+ * weightCost of the sweep (:168-220) then is one launch; x265glue_wp_done ends the analysis of the frame (the GPU context
+ * serves one weightAnalyse at a time) */
+void x265glue_wp_prepare(X265_NS::Frame* frame, X265_NS::Frame* refFrame, int plane, const void* mvs);
+int  x265glue_wp_cost(int weighted, int scale, int denom, int offset, unsigned int* cost);
+void x265glue_wp_done(void);
 /* ---- harness: totals over every context closed so far: contexts, h2d bytes, d2h bytes, kernel launches,
  * look-ahead estimate cache (launched ahead, handed out, computed on demand, requests) */
 void x265glue_totals(long long* out8);

@@ -96,6 +96,21 @@ def build_depth(depth, jobs, cli):
         elif not newer(obj, src):
             tasks.append(["g++"] + F + ["-c", src, "-o", obj])
         objs.append(obj)
+    # weightPrediction.cpp keeps mcLuma / mcChroma / weightCost in an anonymous namespace: a second object is compiled from a
+    # temporary copy in which that namespace has a name (and weightAnalyse another one), so that the shim can call the
+    # reference's own functions when the oracle's restatement of them is pinned (tests/test_oracle_vs_ref.py)
+    wp_src = os.path.join(REF_ROOT, "encoder/weightPrediction.cpp")
+    wp_open = os.path.join(gen, "weightpred_open.cpp")
+    wp_obj = os.path.join(d, "obj", "weightpred_open.o")
+    if not newer(wp_open, wp_src, os.path.abspath(__file__)):
+        txt = open(wp_src).read()
+        if txt.count("namespace {") != 1 or "namespace X265_NS {\nvoid weightAnalyse" not in txt:
+            raise SystemExit("build_ref: weightPrediction.cpp anchors not found")
+        txt = txt.replace("namespace {", "namespace wpref {")
+        txt = txt.replace("namespace X265_NS {\nvoid weightAnalyse", "using namespace wpref;\nnamespace X265_NS {\nvoid weightAnalyse_wpref_copy")
+        open(wp_open, "w").write(txt)
+    if not newer(wp_obj, wp_open):
+        tasks.append(["g++"] + F + ["-c", wp_open, "-o", wp_obj])
     with ThreadPoolExecutor(jobs) as ex:
         list(ex.map(run, tasks))
 
@@ -116,9 +131,9 @@ def build_depth(depth, jobs, cli):
     shim_src = os.path.join(HERE, "ref_shim.cpp")
     drv_src = os.path.join(os.path.dirname(HERE), "harness", "x265_la_driver.cpp")   # lookahead-only driver + observation hooks
     shim = os.path.join(OUT, "libx265ref%d.so" % depth)
-    deps = [shim_src, drv_src, lib, os.path.join(HERE, "ref_hooks.h"), os.path.join(HERE, "synth.h")]
+    deps = [shim_src, drv_src, lib, wp_obj, os.path.join(HERE, "ref_hooks.h"), os.path.join(HERE, "synth.h")]
     if os.path.exists(shim_src) and not newer(shim, *deps):
-        run(["g++"] + F + ["-shared", shim_src, drv_src, "-o", shim, "-Wl,--whole-archive", lib, "-Wl,--no-whole-archive",
+        run(["g++"] + F + ["-shared", shim_src, drv_src, wp_obj, "-o", shim, "-Wl,--whole-archive", lib, "-Wl,--no-whole-archive",
                             "-lpthread", "-ldl", "-lm"])
 
     if cli:

@@ -12,6 +12,9 @@
 #include "param.h"
 #include "bitcost.h"
 #include "motion.h"
+#include "lowres.h"
+#include "slice.h"
+#include "mv.h"
 #include "x265.h"
 
 #include <stdio.h>
@@ -25,6 +28,23 @@ struct ExposeBitCost : public BitCost
     const uint16_t* table() const { return m_cost; }
 };
 } // namespace
+
+/* the pixel loops of encoder/weightPrediction.cpp, from the copy with a named namespace (build_ref.py) */
+namespace wpref {
+struct Cache
+{
+    const int * intraCost;
+    int         numPredDir;
+    int         csp;
+    int         hshift;
+    int         vshift;
+    int         lowresWidthInCU;
+    int         lowresHeightInCU;
+};
+void mcLuma(pixel* mcout, Lowres& ref, const MV * mvs);
+void mcChroma(pixel* mcout, pixel* src, intptr_t stride, const MV* mvs, const Cache& cache, int height, int width);
+uint32_t weightCost(pixel* fenc, pixel* ref, pixel* weightTemp, intptr_t stride, const Cache& cache, int width, int height, WeightParam* w, bool bLuma);
+}
 
 /* ================================================================ (1) primitives */
 extern "C" {
@@ -84,6 +104,36 @@ void x265ref_mvcost_table(uint16_t* out)
     memcpy(out, bc.table() - 2 * 32768, (4 * 32768 + 1) * sizeof(uint16_t));
 }
 int x265ref_exp2fix8(double x) { return x265_exp2fix8(x); }
+
+/* weightPrediction.cpp: mcLuma :59-90, mcChroma :92-166 (4:2:0), weightCost :168-220 */
+void x265ref_wp_mc_luma(pixel* const planes[4], intptr_t stride, int width, int lines, const int16_t* mvs, pixel* mcout)
+{
+    Lowres ref;
+    memset(&ref, 0, sizeof(ref));
+    for (int i = 0; i < 4; i++) ref.lowresPlane[i] = planes[i];
+    ref.isLowres = true;
+    ref.lumaStride = stride; ref.width = width; ref.lines = lines;
+    wpref::mcLuma(mcout, ref, (const MV*)mvs);
+}
+void x265ref_wp_mc_chroma(pixel* src, intptr_t stride, const int16_t* mvs, int lowresWidthInCU, int lowresHeightInCU, int height, int width, pixel* mcout)
+{
+    wpref::Cache c;
+    memset(&c, 0, sizeof(c));
+    c.csp = X265_CSP_I420; c.hshift = 1; c.vshift = 1;
+    c.lowresWidthInCU = lowresWidthInCU; c.lowresHeightInCU = lowresHeightInCU;
+    wpref::mcChroma(mcout, src, stride, (const MV*)mvs, c, height, width);
+}
+uint32_t x265ref_wp_cost(pixel* fenc, pixel* ref, pixel* weightTemp, intptr_t stride, int width, int height, const int32_t* intraCost,
+                         int weighted, int scale, int denom, int offset)
+{
+    wpref::Cache c;
+    memset(&c, 0, sizeof(c));
+    c.csp = X265_CSP_I420; c.hshift = 1; c.vshift = 1;
+    c.intraCost = intraCost;
+    WeightParam w;
+    w.bPresentFlag = true; w.inputWeight = scale; w.log2WeightDenom = (uint32_t)denom; w.inputOffset = offset;
+    return wpref::weightCost(fenc, ref, weightTemp, stride, c, width, height, weighted ? &w : NULL, intraCost != NULL);
+}
 
 
 

@@ -52,7 +52,16 @@ static inline int synth_chroma8(int x, int y, int t, int plane, int nframes, uin
     int scene = (t >= nframes / 2 && nframes > 3) ? 1 : 0;
     int tx = x + t + 2048, ty = y + 2048;
     int tex = (int)(synth_mix((uint32_t)(tx >> 2), (uint32_t)(ty >> 2), (uint32_t)(scene * 2 + plane), seed ^ 0x3C3C3C3Cu) & 255u);
-    return 128 + ((tex - 128) >> 2);
+    int v = 128 + ((tex - 128) >> 2);
+    if (scene && (seed & 0x40000000u))
+    {
+        /* seeds with bit 30 set: the chroma planes fade with the luma (the explicit weight analysis then has chroma work:
+         * mcChroma + the chroma sweeps of weightPrediction.cpp); every other seed keeps the static chroma */
+        int g = 70 + 4 * (t - nframes / 2);
+        if (g > 128) g = 128;
+        v = (v * g + 64) >> 7;
+    }
+    return v;
 }
 
 /* depth 8: planes are uint8_t; depth > 8: planes are uint16_t holding value << (depth - 8).

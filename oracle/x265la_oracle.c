@@ -1326,3 +1326,133 @@ int ola_pu_satd(int w, int h, const pixel* a, intptr_t sa, const pixel* b, intpt
             sum += ola_satd4x4(a + y * sa + x, sa, b + y * sb + x, sb);
     return sum;
 }
+
+/* ================================================================================================
+ * explicit weighted-prediction analysis, pixel loops: encoder/weightPrediction.cpp
+ * ============================================================================================== */
+
+/* mcLuma, weightPrediction.cpp:59-90: a motion-compensated copy of the lowres reference, CU by CU, each vector clipped to the
+ * picture + 8 samples.  planes[4] = lowresPlane[0..3] of the reference, mvs = cuCount (x, y) pairs. */
+void ola_wp_mc_luma(pixel* const planes[4], intptr_t stride, int width, int lines, const int16_t* mvs, pixel* mcout)
+{
+    ref_planes r = { { planes[0], planes[1], planes[2], planes[3] }, stride };
+    int cu = 0;
+    for (int y = 0; y < lines; y += 8)
+    {
+        int16_t miny = (int16_t)((-y - 8) * 4), maxy = (int16_t)((lines - y - 1 + 8) * 4);
+        for (int x = 0; x < width; x += 8, cu++)
+        {
+            int16_t minx = (int16_t)((-x - 8) * 4), maxx = (int16_t)((width - x - 1 + 8) * 4);
+            int mx = mvs[2 * cu], my = mvs[2 * cu + 1];
+            mx = mx < minx ? minx : (mx > maxx ? maxx : mx);
+            my = my < miny ? miny : (my > maxy ? maxy : my);
+            pixel blk[64];
+            lowres_mc(&r, (intptr_t)y * stride + x, mx, my, blk);
+            for (int i = 0; i < 8; i++)
+                memcpy(mcout + (intptr_t)(y + i) * stride + x, blk + 8 * i, 8 * sizeof(pixel));
+        }
+    }
+}
+
+/* g_chromaFilter, common/constants.cpp:247-257 */
+static const int16_t wp_chroma_filter[8][4] = {
+    { 0, 64, 0, 0 }, { -2, 58, 10, -2 }, { -4, 54, 16, -2 }, { -6, 46, 28, -4 },
+    { -4, 36, 36, -4 }, { -4, 28, 46, -6 }, { -2, 16, 54, -4 }, { -2, 10, 58, -2 } };
+
+/* mcChroma, weightPrediction.cpp:92-166, for 4:2:0 (8x8 chroma blocks; the four interpolation cases are
+ * interp_horiz_pp_c / interp_vert_pp_c / interp_horiz_ps_c + interp_vert_sp_c with N = 4, common/ipfilter.cpp:80-284).
+ * src points at sample (0,0) of a border-extended chroma plane.  The availability test and the vector index use the SAMPLE
+ * position against the lowres CU counts, as the reference does (:113-121). */
+void ola_wp_mc_chroma(const pixel* src, intptr_t stride, const int16_t* mvs, int lowresWidthInCU, int lowresHeightInCU,
+                      int height, int width, pixel* mcout)
+{
+    const int maxVal = (1 << ORACLE_DEPTH) - 1;
+    const int headRoom = 14 - ORACLE_DEPTH;
+    for (int y = 0; y < height; y += 8)
+    {
+        int cu = y * lowresWidthInCU;
+        int16_t miny = (int16_t)((-y - 8) * 4), maxy = (int16_t)((height - y - 1 + 8) * 4);
+        for (int x = 0; x < width; x += 8, cu++)
+        {
+            intptr_t pixoff = (intptr_t)y * stride + x;
+            if (x < lowresWidthInCU && y < lowresHeightInCU)
+            {
+                int16_t mx = mvs[2 * cu], my = mvs[2 * cu + 1];
+                mx = (int16_t)(mx << 1); my = (int16_t)(my << 1);       /* lowres -> full resolution */
+                mx >>= 1; my >>= 1;                                       /* -> 4:2:0 chroma */
+                int16_t minx = (int16_t)((-x - 8) * 4), maxx = (int16_t)((width - x - 1 + 8) * 4);
+                mx = mx < minx ? minx : (mx > maxx ? maxx : mx);
+                my = my < miny ? miny : (my > maxy ? maxy : my);
+                const pixel* temp = src + pixoff + (intptr_t)(my >> 2) * stride + (mx >> 2);
+                int xFrac = mx & 7, yFrac = my & 7;
+                const int16_t* cx = wp_chroma_filter[xFrac];
+                const int16_t* cy = wp_chroma_filter[yFrac];
+                for (int r = 0; r < 8; r++)
+                    for (int c = 0; c < 8; c++)
+                    {
+                        const pixel* p = temp + (intptr_t)r * stride + c;
+                        int val;
+                        if (!(xFrac | yFrac))
+                            val = p[0];
+                        else if (!yFrac)
+                        {
+                            int sum = p[-1] * cx[0] + p[0] * cx[1] + p[1] * cx[2] + p[2] * cx[3];
+                            int16_t v = (int16_t)((sum + 32) >> 6);
+                            val = v < 0 ? 0 : (v > maxVal ? maxVal : v);
+                        }
+                        else if (!xFrac)
+                        {
+                            int sum = p[-stride] * cy[0] + p[0] * cy[1] + p[stride] * cy[2] + p[2 * stride] * cy[3];
+                            int16_t v = (int16_t)((sum + 32) >> 6);
+                            val = v < 0 ? 0 : (v > maxVal ? maxVal : v);
+                        }
+                        else
+                        {
+                            int shiftH = 6 - headRoom, offH = -(8192 << shiftH);
+                            int shiftV = 6 + headRoom, offV = (1 << (shiftV - 1)) + (8192 << 6);
+                            int sum = 0;
+                            for (int k = 0; k < 4; k++)
+                            {
+                                const pixel* q = p + (intptr_t)(k - 1) * stride;
+                                int h = q[-1] * cx[0] + q[0] * cx[1] + q[1] * cx[2] + q[2] * cx[3];
+                                int16_t imm = (int16_t)((h + offH) >> shiftH);
+                                sum += imm * cy[k];
+                            }
+                            int16_t v = (int16_t)((sum + offV) >> shiftV);
+                            val = v < 0 ? 0 : (v > maxVal ? maxVal : v);
+                        }
+                        mcout[pixoff + (intptr_t)r * stride + c] = (pixel)val;
+                    }
+            }
+            else
+                for (int r = 0; r < 8; r++)
+                    memcpy(mcout + pixoff + (intptr_t)r * stride, src + pixoff + (intptr_t)r * stride, 8 * sizeof(pixel));
+        }
+    }
+}
+
+/* weightCost, weightPrediction.cpp:168-220 (luma, and chroma of 4:2:0 / 4:2:2): the reference plane, weighted when
+ * weighted != 0 (weight_pp_c into weightTemp, which must hold stride * height samples), against the source in 8x8 SATDs;
+ * intraCost != NULL (luma) limits each of them. */
+uint32_t ola_wp_cost(const pixel* fenc, const pixel* ref, pixel* weightTemp, intptr_t stride, int width, int height,
+                     const int32_t* intraCost, int weighted, int scale, int denom, int offset)
+{
+    if (weighted)
+    {
+        int off = offset << (ORACLE_DEPTH - 8);
+        int round = denom ? 1 << (denom - 1) : 0;
+        int correction = 14 - ORACLE_DEPTH;
+        int pwidth = ((width + 15) >> 4) << 4;
+        ola_weight_pp(ref, weightTemp, stride, pwidth, height, scale, round << correction, denom + correction, off);
+        ref = weightTemp;
+    }
+    uint32_t cost = 0;
+    int cu = 0;
+    for (int y = 0; y < height; y += 8)
+        for (int x = 0; x < width; x += 8, cu++)
+        {
+            int cmp = ola_satd8x8(ref + (intptr_t)y * stride + x, stride, fenc + (intptr_t)y * stride + x, stride);
+            cost += intraCost ? (uint32_t)imin(cmp, intraCost[cu]) : (uint32_t)cmp;
+        }
+    return cost;
+}

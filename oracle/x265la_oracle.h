@@ -155,6 +155,12 @@ int ola_pu_satd(int w, int h, const pixel* a, intptr_t sa, const pixel* b, intpt
 
 /* helpers for tests */
 void ola_lowres_mc(pixel* const planes[4], intptr_t stride, intptr_t blockOffset, int qx, int qy, pixel* blk);
+/* explicit weighted-prediction analysis, pixel loops (encoder/weightPrediction.cpp:59-220) */
+void ola_wp_mc_luma(pixel* const planes[4], intptr_t stride, int width, int lines, const int16_t* mvs, pixel* mcout);
+void ola_wp_mc_chroma(const pixel* src, intptr_t stride, const int16_t* mvs, int lowresWidthInCU, int lowresHeightInCU,
+                      int height, int width, pixel* mcout);
+uint32_t ola_wp_cost(const pixel* fenc, const pixel* ref, pixel* weightTemp, intptr_t stride, int width, int height,
+                     const int32_t* intraCost, int weighted, int scale, int denom, int offset);
 uint32_t ola_crc32(const void* p, size_t n);
 void ola_synth_frame(int w, int h, int t, int nframes, uint32_t seed, void* y, int ystride, void* u, void* v, int cstride);
 void ola_copy_picture(const pixel* src, int w, int h, pixel* dst, intptr_t dstStride);

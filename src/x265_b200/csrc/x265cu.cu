@@ -91,6 +91,11 @@ struct x265cu_ctx
     int* dMvs;
     int* dMvCosts;
     unsigned long long* dPropagate;        /* [slot][nCU] Lowres::propagateCost accumulators (x265cu_cutree.cuh) */
+    /* explicit weighted-prediction analysis (x265cu_wp.cuh): compact copies of the source chroma planes per slot, the
+     * motion-compensated reference plane and the vectors / intra costs of the (slice, list, plane) being analysed */
+    uint8_t* dChroma; int chromaPitch, chromaRows; std::vector<char> hasChroma;
+    uint8_t* dWp; size_t dWpCap;
+    WpCostArgs wpArgs; bool wpReady;
     int cutreeCtas;                        /* grid of the cooperative cuTree kernel (one CTA per SM) */
     bool mappedResults;                    /* result arrays go straight into mapped pinned destinations (X265CU_MAPPED_RESULTS=0: always staged) */
     uint16_t* dPropOut; size_t dPropOutCap; /* clamped uint16 copies on their way to the host */
@@ -311,13 +316,16 @@ inline int* slotRowSatds(x265cu_ctx* c, int slot, int d0, int d1)
 inline int* slotMvs(x265cu_ctx* c, int slot, int list, int d) { return c->dMvs + (((size_t)slot * 2 + list) * (c->bf + 1) + (d - 1)) * c->g.nCU; }
 inline int* slotMvCosts(x265cu_ctx* c, int slot, int list, int d) { return c->dMvCosts + (((size_t)slot * 2 + list) * (c->bf + 1) + (d - 1)) * c->g.nCU; }
 
+inline uint8_t* slotChroma(x265cu_ctx* c, int slot, int plane) { return c->dChroma + ((size_t)slot * 2 + plane) * c->chromaPitch * c->chromaRows * c->pb; }
+
 bool badSlot(const x265cu_ctx* c, int s) { return s < 0 || s >= c->cfg.numFrameSlots; }
 
 void freeAll(x265cu_ctx* c)
 {
     cudaFree(c->dPlanes); cudaFree(c->dIntraCost); cudaFree(c->dIntraMode); cudaFree(c->dInvQ);
     cudaFree(c->dLowresCosts); cudaFree(c->dRowSatds); cudaFree(c->dMvs); cudaFree(c->dMvCosts);
-    cudaFree(c->dPropagate);
+    cudaFree(c->dPropagate); cudaFree(c->dChroma);
+    poolGive(g_devPool, c->cfg.device, c->dWp, c->dWpCap);
     cudaFree(c->dLut); cudaFree(c->dSrc); cudaFree(c->dSmall);
     /* the on-demand work buffers go back to the process-wide pool (growDevice / growHost); every stream of the context is
      * idle here (x265cu_close waited for them) */
@@ -388,6 +396,7 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     c->dGeneric = NULL; c->dGenericCap = 0; c->dMemo = NULL; c->dMemoCap = 0;
     c->cutreeCtas = 0;
     c->mappedResults = !(getenv("X265CU_MAPPED_RESULTS") && atoi(getenv("X265CU_MAPPED_RESULTS")) == 0);
+    c->dChroma = NULL; c->dWp = NULL; c->dWpCap = 0; c->wpReady = false;
     c->dPropagate = NULL; c->dPropOut = NULL; c->dPropOutCap = 0; c->hPropOut = NULL; c->hPropOutCap = 0;
     c->timing = false;
     memset(&c->stats, 0, sizeof(c->stats));
@@ -493,6 +502,12 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     OPEN_TRY(cudaMalloc((void**)&c->dMvCosts, S * t1 * n * sizeof(int)));
     OPEN_TRY(cudaMemsetAsync(c->dMvs, 0, S * t1 * n * sizeof(int), c->stream));
     OPEN_TRY(cudaMemsetAsync(c->dMvCosts, 0, S * t1 * n * sizeof(int), c->stream));
+    {
+        const int bxN = (cfg->srcWidth + 15) / 16, byN = (cfg->srcHeight + 15) / 16;
+        c->chromaPitch = 8 * bxN; c->chromaRows = 8 * byN;
+        OPEN_TRY(cudaMalloc((void**)&c->dChroma, S * 2 * (size_t)c->chromaPitch * c->chromaRows * c->pb));
+        c->hasChroma.assign(S, 0);
+    }
     OPEN_TRY(cudaMalloc((void**)&c->dPropagate, S * n * sizeof(unsigned long long)));
     OPEN_TRY(cudaMemsetAsync(c->dPropagate, 0, S * n * sizeof(unsigned long long), c->stream));
     OPEN_TRY(cudaMalloc((void**)&c->dLut, (4 * 32768 + 1) * sizeof(uint16_t)));
@@ -725,6 +740,7 @@ static int frameInitEnqueue(x265cu_ctx* c, int slot, const void* luma, intptr_t 
         CU_TRY(c, cudaStreamWaitEvent(c->stream, c->planesCopied[slot], 0));   /* do not overwrite planes still being copied out */
     /* a new picture in this slot: its order and its MV fields are unknown again */
     c->slotPocKnown[slot] = 0;
+    c->hasChroma[slot] = 0;             /* set again below when this call measures the variance with chroma planes */
     std::fill(c->mvValid.begin() + (size_t)slot * 2 * (c->bf + 1), c->mvValid.begin() + (size_t)(slot + 1) * 2 * (c->bf + 1), 0);
     {
         KernelScope ks(c, X265CU_K_LOWRES);
@@ -782,9 +798,12 @@ static int frameInitEnqueue(x265cu_ctx* c, int slot, const void* luma, intptr_t 
             int blocks = (bxN * byN + 7) / 8;
             if (blocks > 148 * 8) blocks = 148 * 8;      /* warps stride over the 16x16 blocks */
             if (c->pb == 1)
-                frame_var_kernel<uint8_t><<<blocks, 256, 0, c->stream>>>((const uint8_t*)src, pitch, u ? (const uint8_t*)dU : NULL, u ? (const uint8_t*)dV : NULL, cpitch, bxN, byN, dE, dSums);
+                frame_var_kernel<uint8_t><<<blocks, 256, 0, c->stream>>>((const uint8_t*)src, pitch, u ? (const uint8_t*)dU : NULL, u ? (const uint8_t*)dV : NULL, cpitch, bxN, byN, dE, dSums,
+                                                                          u ? (uint8_t*)slotChroma(c, slot, 0) : NULL, u ? (uint8_t*)slotChroma(c, slot, 1) : NULL);
             else
-                frame_var_kernel<uint16_t><<<blocks, 256, 0, c->stream>>>((const uint16_t*)src, pitch, u ? (const uint16_t*)dU : NULL, u ? (const uint16_t*)dV : NULL, cpitch, bxN, byN, dE, dSums);
+                frame_var_kernel<uint16_t><<<blocks, 256, 0, c->stream>>>((const uint16_t*)src, pitch, u ? (const uint16_t*)dU : NULL, u ? (const uint16_t*)dV : NULL, cpitch, bxN, byN, dE, dSums,
+                                                                           u ? (uint16_t*)slotChroma(c, slot, 0) : NULL, u ? (uint16_t*)slotChroma(c, slot, 1) : NULL);
+            c->hasChroma[slot] = u != NULL;
         }
         CU_TRY(c, cudaGetLastError());
         if (!bo)
@@ -853,6 +872,7 @@ int x265cu_frame_upload(x265cu_ctx* c, int slot, const void* y, intptr_t yStride
 }
 
 static int preBatchImpl(x265cu_ctx* c, int n, const x265cu_frame_in* items, x265cu_aq_fn aq, void* user, x265cu_intra_out* outs);
+static void weightArgs(const x265cu_ctx* c, int scale, int denom, int offset, int* round, int* shift, int* off);
 static int intraEnqueue(x265cu_ctx* c, int slot, x265cu_intra_out* out, unsigned long long* sums, unsigned long long* dBatchSums, cudaStream_t st);
 static int intraEnqueueBatch(x265cu_ctx* c, int count, const int* slots, x265cu_intra_out* const* outs, unsigned long long* dBatchSums, cudaStream_t st);
 
@@ -998,6 +1018,8 @@ static int preBatchImpl2(x265cu_ctx* c, int n, const x265cu_frame_in* items, x26
             }
             lb.planes[k2] = slotBuffer(c, f.slot);
             lb.pitch[k2] = f.yStride; vb.ys[k2] = f.yStride; vb.cs[k2] = f.cStride;
+            vb.uKeep[k2] = f.u ? slotChroma(c, f.slot, 0) : NULL; vb.vKeep[k2] = f.u ? slotChroma(c, f.slot, 1) : NULL;
+            c->hasChroma[f.slot] = f.u != NULL;
             vb.energy[k2] = (unsigned int*)(c->dPre + (size_t)i * per);
             vb.sums[k2] = (unsigned long long*)(c->dPre + (size_t)i * per + eBytes);
             for (size_t d = 0; d < c->deferredPlanes.size(); d++)
@@ -1332,6 +1354,114 @@ int x265cu_intra_batch(x265cu_ctx* c, int n, const int* slots, x265cu_intra_out*
         outs[i].sums[1] = (int64_t)sm[1];
     }
     return X265CU_OK;
+}
+
+/* ---- explicit weighted-prediction analysis (x265cu_wp.cuh; encoder/weightPrediction.cpp) ---- */
+int x265cu_wp_prepare(x265cu_ctx* c, int fencSlot, int refSlot, int plane, const void* lowresMvs, const int32_t* intraCost)
+{
+    if (!c || badSlot(c, fencSlot) || badSlot(c, refSlot) || plane < 0 || plane > 2 || (plane == 0 && !intraCost))
+        return c ? fail(c, X265CU_EINVAL, "x265cu_wp_prepare: bad argument") : X265CU_EINVAL;
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CU_TRY(c, cudaSetDevice(c->cfg.device));
+    c->wpReady = false;
+    const GeomDev& g = c->g;
+    if (plane && (!c->hasChroma[fencSlot] || !c->hasChroma[refSlot]))
+        return fail(c, X265CU_EINVAL, "x265cu_wp_prepare: the chroma planes of these frames are not on the device (frames must go through x265cu_frame_init_var* with chroma)");
+    const size_t nCU = (size_t)g.nCU;
+    const size_t lumaMc = (size_t)g.stride * g.lines * c->pb, chromaMc = (size_t)c->chromaPitch * c->chromaRows * c->pb;
+    const size_t offIntra = alignUp(nCU * 4, 256), offMc = offIntra + alignUp(nCU * 4, 256);
+    const size_t offCand = offMc + alignUp(lumaMc > chromaMc ? lumaMc : chromaMc, 256);
+    if (growDevice(c, &c->dWp, &c->dWpCap, offCand + 64 * 1024)) return X265CU_ECUDA;
+    int* dMvs = (int*)c->dWp;
+    int* dIntra = (int*)(c->dWp + offIntra);
+    uint8_t* dMc = c->dWp + offMc;
+    if (lowresMvs)
+    {
+        CU_TRY(c, cudaMemcpyAsync(dMvs, lowresMvs, nCU * 4, cudaMemcpyHostToDevice, c->stream));
+        c->stats.h2dBytes += (int64_t)nCU * 4;
+    }
+    WpCostArgs& a = c->wpArgs;
+    if (plane == 0)
+    {
+        /* the host's intraCost is the truth (rate control may have rescaled it since the lookahead wrote it) */
+        CU_TRY(c, cudaMemcpyAsync(dIntra, intraCost, nCU * 4, cudaMemcpyHostToDevice, c->stream));
+        c->stats.h2dBytes += (int64_t)nCU * 4;
+        a.fenc = slotPlane0(c, fencSlot); a.fencStride = g.stride;
+        a.ref = slotPlane0(c, refSlot); a.refStride = g.stride;
+        a.wBlk = g.width >> 3; a.nBlk = (g.width >> 3) * (g.lines >> 3);
+        a.intraCost = dIntra;
+        if (lowresMvs)
+        {
+            KernelScope ks(c, X265CU_K_WEIGHT);
+            const int blocks = (g.nCU + 63) / 64;
+            if (c->pb == 1) wp_mc_luma_kernel<uint8_t><<<blocks, 256, 0, c->stream>>>((const uint8_t*)slotPlane0(c, refSlot), g, dMvs, (uint8_t*)dMc);
+            else wp_mc_luma_kernel<uint16_t><<<blocks, 256, 0, c->stream>>>((const uint16_t*)slotPlane0(c, refSlot), g, dMvs, (uint16_t*)dMc);
+            CU_TRY(c, cudaGetLastError());
+            a.ref = dMc;
+        }
+    }
+    else
+    {
+        /* the analysis area of the chroma planes: whole 8x8 blocks only (weightPrediction.cpp:329-336) */
+        const int width = ((c->cfg.srcWidth >> 4) << 4) >> 1, height = ((c->cfg.srcHeight >> 4) << 4) >> 1;
+        a.fenc = slotChroma(c, fencSlot, plane - 1); a.fencStride = c->chromaPitch;
+        a.ref = slotChroma(c, refSlot, plane - 1); a.refStride = c->chromaPitch;
+        a.wBlk = width >> 3; a.nBlk = (width >> 3) * (height >> 3);
+        a.intraCost = NULL;
+        if (lowresMvs && width > 0 && height > 0)
+        {
+            KernelScope ks(c, X265CU_K_WEIGHT);
+            dim3 grid((width + 31) / 32, (height + 7) / 8);
+            const int cW = c->cfg.srcWidth >> 1, cH = c->cfg.srcHeight >> 1;
+            /* cache.lowresWidthInCU / HeightInCU = Lowres::width >> 3, lines >> 3 (weightPrediction.cpp:233-234) */
+            if (c->pb == 1)
+                wp_mc_chroma_kernel<uint8_t><<<grid, 256, 0, c->stream>>>((const uint8_t*)a.ref, c->chromaPitch, cW, cH, dMvs, g.width >> 3, g.lines >> 3, width, height,
+                                                                         (uint8_t*)dMc, c->chromaPitch, c->cfg.bitDepth);
+            else
+                wp_mc_chroma_kernel<uint16_t><<<grid, 256, 0, c->stream>>>((const uint16_t*)a.ref, c->chromaPitch, cW, cH, dMvs, g.width >> 3, g.lines >> 3, width, height,
+                                                                          (uint16_t*)dMc, c->chromaPitch, c->cfg.bitDepth);
+            CU_TRY(c, cudaGetLastError());
+            a.ref = dMc;
+        }
+    }
+    c->wpReady = true;
+    return X265CU_OK;
+}
+
+int x265cu_wp_cost(x265cu_ctx* c, int n, const x265cu_weight_item* cands, uint32_t* costs)
+{
+    if (!c || n < 0 || n > 1024 || (n && (!cands || !costs))) return c ? fail(c, X265CU_EINVAL, "x265cu_wp_cost: bad argument") : X265CU_EINVAL;
+    if (!n) return X265CU_OK;
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CU_TRY(c, cudaSetDevice(c->cfg.device));
+    if (!c->wpReady) return fail(c, X265CU_EINVAL, "x265cu_wp_cost: no x265cu_wp_prepare before it");
+    const GeomDev& g = c->g;
+    const size_t nCU = (size_t)g.nCU;
+    const size_t lumaMc = (size_t)g.stride * g.lines * c->pb, chromaMc = (size_t)c->chromaPitch * c->chromaRows * c->pb;
+    const size_t offCand = alignUp(nCU * 4, 256) * 2 + alignUp(lumaMc > chromaMc ? lumaMc : chromaMc, 256);
+    WpCand h[1024];
+    for (int i = 0; i < n; i++)
+    {
+        h[i].weighted = cands[i].weighted; h[i].scale = cands[i].scale;
+        weightArgs(c, cands[i].scale, cands[i].denom, cands[i].offset, &h[i].round, &h[i].shift, &h[i].offset);
+    }
+    WpCand* dCand = (WpCand*)(c->dWp + offCand);
+    unsigned int* dCosts = (unsigned int*)(c->dWp + offCand + alignUp((size_t)n * sizeof(WpCand), 256));
+    CU_TRY(c, cudaMemcpyAsync(dCand, h, (size_t)n * sizeof(WpCand), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemsetAsync(dCosts, 0, (size_t)n * sizeof(unsigned int), c->stream));
+    {
+        KernelScope ks(c, X265CU_K_WEIGHT);
+        int bx = (c->wpArgs.nBlk / 8 + 7) / 8;
+        if (bx > 148 * 2) bx = 148 * 2;
+        if (bx < 1) bx = 1;
+        dim3 grid(bx, n);
+        if (c->pb == 1) wp_cost_kernel<uint8_t><<<grid, 256, 0, c->stream>>>(c->wpArgs, dCand, dCosts, c->correction, c->pixelMax);
+        else wp_cost_kernel<uint16_t><<<grid, 256, 0, c->stream>>>(c->wpArgs, dCand, dCosts, c->correction, c->pixelMax);
+        CU_TRY(c, cudaGetLastError());
+    }
+    CU_TRY(c, cudaMemcpyAsync(costs, dCosts, (size_t)n * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    c->stats.d2hBytes += (int64_t)n * 4;
+    return syncStream(c);
 }
 
 /* ---- cuTree propagation (x265cu_cutree.cuh) ---- */
@@ -2237,9 +2367,9 @@ int x265cu_frame_var(x265cu_ctx* c, const void* y, intptr_t yStride, const void*
         int blocks = (bxN * byN + 7) / 8;
             if (blocks > 148 * 8) blocks = 148 * 8;      /* warps stride over the 16x16 blocks */
         if (c->pb == 1)
-            frame_var_kernel<uint8_t><<<blocks, 256, 0, c->stream>>>((const uint8_t*)dY, ypitch, u ? (const uint8_t*)dU : NULL, u ? (const uint8_t*)dV : NULL, cpitch, bxN, byN, dE, c->dSmall);
+            frame_var_kernel<uint8_t><<<blocks, 256, 0, c->stream>>>((const uint8_t*)dY, ypitch, u ? (const uint8_t*)dU : NULL, u ? (const uint8_t*)dV : NULL, cpitch, bxN, byN, dE, c->dSmall, NULL, NULL);
         else
-            frame_var_kernel<uint16_t><<<blocks, 256, 0, c->stream>>>((const uint16_t*)dY, ypitch, u ? (const uint16_t*)dU : NULL, u ? (const uint16_t*)dV : NULL, cpitch, bxN, byN, dE, c->dSmall);
+            frame_var_kernel<uint16_t><<<blocks, 256, 0, c->stream>>>((const uint16_t*)dY, ypitch, u ? (const uint16_t*)dU : NULL, u ? (const uint16_t*)dV : NULL, cpitch, bxN, byN, dE, c->dSmall, NULL, NULL);
     }
     CU_TRY(c, cudaGetLastError());
     CU_TRY(c, cudaMemcpyAsync(energy, dE, (size_t)bxN * byN * 4, cudaMemcpyDeviceToHost, c->stream));

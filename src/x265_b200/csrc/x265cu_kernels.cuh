@@ -84,7 +84,8 @@ __device__ __forceinline__ int lowres_px(const P* r0, const P* r1, int c0, int c
 #define PRE_BATCH 8
 struct LowresBatch { const void* src[PRE_BATCH]; void* planes[PRE_BATCH]; int64_t pitch[PRE_BATCH]; };
 struct VarBatch { const void* y[PRE_BATCH]; const void* u[PRE_BATCH]; const void* v[PRE_BATCH]; unsigned int* energy[PRE_BATCH]; unsigned long long* sums[PRE_BATCH];
-                  int64_t ys[PRE_BATCH], cs[PRE_BATCH]; };
+                  int64_t ys[PRE_BATCH], cs[PRE_BATCH];
+                  void* uKeep[PRE_BATCH]; void* vKeep[PRE_BATCH]; };      /* compact copies of the chroma planes kept per frame slot (x265cu_wp.cuh), or NULL */
 
 template <typename P>
 __device__ __forceinline__ void lowres_init_body(const P* __restrict__ src, int64_t srcPitch, P* __restrict__ planes, const GeomDev& g)
@@ -186,6 +187,7 @@ struct JobDev
 #include "x265cu_search.cuh"
 #include "x265cu_search_plain.cuh"
 #include "x265cu_search_oct.cuh"
+#include "x265cu_wp.cuh"
 
 /* cost-only estimates (both bDoSearch false): every CU is independent.  grid = (hCU, jobs);
  * a block owns one CU row of one job, so rowSatds needs no atomics. */
@@ -617,7 +619,8 @@ __global__ void __launch_bounds__(256) int_peak_kernel(int mode, int iters, unsi
  * =========================================================================================== */
 template <typename P>
 __device__ __forceinline__ void frame_var_body(const P* __restrict__ y, int64_t ys, const P* __restrict__ u, const P* __restrict__ v, int64_t cs,
-                                               int blocksX, int blocksY, unsigned int* __restrict__ energy, unsigned long long* __restrict__ sums6)
+                                               int blocksX, int blocksY, unsigned int* __restrict__ energy, unsigned long long* __restrict__ sums6,
+                                               P* __restrict__ uKeep = NULL, P* __restrict__ vKeep = NULL)
 {
     __shared__ unsigned long long sAcc[6];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warpsPerCta = blockDim.x >> 5;
@@ -655,6 +658,12 @@ __device__ __forceinline__ void frame_var_body(const P* __restrict__ y, int64_t 
             {
                 unsigned int a = u[co + i], b = v[co + i];
                 s1 += a; q1 += a * a; s2 += b; q2 += b * b;
+                if (uKeep)
+                {
+                    /* every chroma sample passes through here once: leave a compact copy (pitch = 8 * blocksX) behind */
+                    const int64_t ko = (int64_t)(8 * byi + (lane >> 2)) * (8 * blocksX) + 8 * bxi + (lane & 3) * 2 + i;
+                    uKeep[ko] = (P)a; vKeep[ko] = (P)b;
+                }
             }
             s1 = (unsigned int)warp_sum((int)s1); q1 = (unsigned int)warp_sum((int)q1);
             s2 = (unsigned int)warp_sum((int)s2); q2 = (unsigned int)warp_sum((int)q2);
@@ -675,16 +684,17 @@ __device__ __forceinline__ void frame_var_body(const P* __restrict__ y, int64_t 
 
 template <typename P>
 __global__ void __launch_bounds__(256) frame_var_kernel(const P* __restrict__ y, int64_t ys, const P* __restrict__ u, const P* __restrict__ v, int64_t cs,
-                                                         int blocksX, int blocksY, unsigned int* __restrict__ energy, unsigned long long* __restrict__ sums6)
+                                                         int blocksX, int blocksY, unsigned int* __restrict__ energy, unsigned long long* __restrict__ sums6,
+                                                         P* __restrict__ uKeep, P* __restrict__ vKeep)
 {
-    frame_var_body<P>(y, ys, u, v, cs, blocksX, blocksY, energy, sums6);
+    frame_var_body<P>(y, ys, u, v, cs, blocksX, blocksY, energy, sums6, uKeep, vKeep);
 }
 
 template <typename P>
 __global__ void __launch_bounds__(256) frame_var_batch_kernel(VarBatch b, int blocksX, int blocksY)
 {
     const int f = blockIdx.y;
-    frame_var_body<P>((const P*)b.y[f], b.ys[f], (const P*)b.u[f], (const P*)b.v[f], b.cs[f], blocksX, blocksY, b.energy[f], b.sums[f]);
+    frame_var_body<P>((const P*)b.y[f], b.ys[f], (const P*)b.u[f], (const P*)b.v[f], b.cs[f], blocksX, blocksY, b.energy[f], b.sums[f], (P*)b.uKeep[f], (P*)b.vKeep[f]);
 }
 
 #endif /* X265CU_KERNELS_CUH */

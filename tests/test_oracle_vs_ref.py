@@ -193,3 +193,95 @@ def test_pu_sad_satd_all_shapes(depth):
                         got = getattr(O, "ola_pu_" + name)(w, h, ptr(a, oa), 64, ptr(b, ob), 67)
                         want = getattr(R, "x265ref_pu_" + name)(w, h, ptr(a, oa), 64, ptr(b, ob), 67)
                         assert got == want, (depth, w, h, name, it)
+
+
+# ---- explicit weighted-prediction analysis, pixel loops (encoder/weightPrediction.cpp:59-220) ----
+def _wp_libs(depth):
+    O, R = po.oracle(depth), po.ref(depth)
+    V, I, S = C.c_void_p, C.c_int, C.c_ssize_t
+    for f in (O.ola_wp_mc_luma, R.x265ref_wp_mc_luma):
+        f.argtypes = [V, S, I, I, V, V]
+    for f in (O.ola_wp_mc_chroma, R.x265ref_wp_mc_chroma):
+        f.argtypes = [V, S, V, I, I, I, I, V]
+    for f in (O.ola_wp_cost, R.x265ref_wp_cost):
+        f.argtypes = [V, V, V, S, I, I, V, I, I, I, I]
+        f.restype = C.c_uint32
+    return O, R
+
+
+def _wp_planes(depth, seed, w, h, mx, my):
+    """four border-extended lowres-like planes (smooth + noise) and their origin pointers"""
+    dt = po.pixel_dtype(depth)
+    rng = np.random.default_rng(seed)
+    top = (1 << depth) - 1
+    stride = w + 2 * mx
+    planes = []
+    for k in range(4):
+        yy, xx = np.mgrid[0:h, 0:w]
+        base = ((xx * 3 + yy * 5 + 17 * k) % (top + 1)).astype(np.int64) // 2 + rng.integers(0, top // 2 + 1, (h, w))
+        core = np.clip(base, 0, top).astype(dt)
+        planes.append(np.ascontiguousarray(np.pad(core, ((my, my), (mx, mx)), mode="edge")))
+    return planes, stride
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_wp_mc_luma(depth):
+    """mcLuma: oracle == the reference's own function on random vectors (in range, far outside, odd and even)"""
+    O, R = _wp_libs(depth)
+    w, h, mx, my = 88, 56, 48, 40
+    planes, stride = _wp_planes(depth, 5, w, h, mx, my)
+    org = (C.c_void_p * 4)(*[p.ctypes.data + (my * stride + mx) * p.itemsize for p in planes])
+    rng = np.random.default_rng(6)
+    n = (w // 8) * (h // 8)
+    for spread in (6, 40, 400):
+        mvs = rng.integers(-spread, spread + 1, (n, 2)).astype(np.int16)
+        a = np.zeros((h, stride), planes[0].dtype)
+        b = np.zeros_like(a)
+        O.ola_wp_mc_luma(org, stride, w, h, mvs.ctypes.data, a.ctypes.data)
+        R.x265ref_wp_mc_luma(org, stride, w, h, mvs.ctypes.data, b.ctypes.data)
+        assert np.array_equal(a[:, :w], b[:, :w])
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_wp_mc_chroma(depth):
+    """mcChroma (4:2:0): all four interpolation cases, vectors clipped at the picture edges, the literal availability test"""
+    O, R = _wp_libs(depth)
+    w, h, mx, my = 96, 64, 40, 40           # chroma analysis area; lowres CU grid 12 x 8 as for a 192 x 128 picture
+    planes, stride = _wp_planes(depth, 7, w, h, mx, my)
+    src = planes[0]
+    p0 = src.ctypes.data + (my * stride + mx) * src.itemsize
+    rng = np.random.default_rng(8)
+    for wcu, hcu, spread in ((12, 8, 9), (12, 8, 300), (96, 64, 20), (40, 30, 64)):
+        mvs = rng.integers(-spread, spread + 1, (max(wcu * h, 4096), 2)).astype(np.int16)
+        mvs[::5] &= ~7                       # plenty of full-pel and single-axis vectors
+        mvs[1::7, 0] &= ~7
+        mvs[2::7, 1] &= ~7
+        a = np.zeros((h + 2 * my, stride), src.dtype)
+        b = np.zeros_like(a)
+        oa = a.ctypes.data + (my * stride + mx) * a.itemsize
+        ob = b.ctypes.data + (my * stride + mx) * b.itemsize
+        O.ola_wp_mc_chroma(p0, stride, mvs.ctypes.data, wcu, hcu, h, w, oa)
+        R.x265ref_wp_mc_chroma(p0, stride, mvs.ctypes.data, wcu, hcu, h, w, ob)
+        assert np.array_equal(a, b)
+        assert a.any()
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_wp_cost(depth):
+    """weightCost: plain and weighted (the whole range of scales, denominators, offsets), luma (intra-limited) and chroma"""
+    O, R = _wp_libs(depth)
+    w, h, mx, my = 96, 64, 16, 8
+    planes, stride = _wp_planes(depth, 9, w, h, mx, my)
+    f, r = planes[0], planes[1]
+    pf = f.ctypes.data + (my * stride + mx) * f.itemsize
+    pr = r.ctypes.data + (my * stride + mx) * r.itemsize
+    tmp = np.zeros((h + 1, stride), f.dtype)
+    rng = np.random.default_rng(10)
+    intra = rng.integers(0, 1200 << (depth - 8), (w // 8) * (h // 8)).astype(np.int32)
+    cases = [(0, 0, 0, 0)] + [(1, int(s), int(d), int(o)) for s, d, o in zip(rng.integers(0, 128, 40), rng.integers(0, 8, 40), rng.integers(-128, 128, 40))]
+    for luma in (True, False):
+        ic = intra.ctypes.data if luma else None
+        for wt, s, d, o in cases:
+            a = O.ola_wp_cost(pf, pr, tmp.ctypes.data, stride, w, h, ic, wt, s, d, o)
+            b = R.x265ref_wp_cost(pf, pr, tmp.ctypes.data, stride, w, h, ic, wt, s, d, o)
+            assert a == b, (luma, wt, s, d, o)
