@@ -255,6 +255,11 @@ enum { X265CU_SAD_8x8 = 0, X265CU_SATD_8x8 = 1, X265CU_SA8D_8x8 = 2, X265CU_SA8D
 int x265cu_pixelcmp_batch(x265cu_ctx* ctx, int kind, const void* bufA, size_t samplesA, intptr_t strideA,
                           const void* bufB, size_t samplesB, intptr_t strideB,
                           int n, const int64_t* offA, const int64_t* offB, int32_t* out);
+/* pu[partitionFromSizes(width, height)].sad (kind 0) / .satd (kind 1) of the full-resolution motion search (common/pixel.cpp:
+ * 954-1004) for any of the 25 luma PU shapes of enum LumaPU (4x4 .. 64x64, the rectangular and the AMP
+ * shapes): n block pairs of ONE shape.  sad_x3 / sad_x4 are the same measure with one source offset repeated. */
+int x265cu_pixelcmp_pu(x265cu_ctx* ctx, int kind, int width, int height, const void* bufA, size_t samplesA, intptr_t strideA,
+                       const void* bufB, size_t samplesB, intptr_t strideB, int n, const int64_t* offA, const int64_t* offB, int32_t* out);
 /* same metric over every aligned 8x8 block of plane 0 of nPairs pairs of frame slots, device
  * resident, ONE launch; out (host, may be NULL) gets nPairs * cuCount results.  Returns the
  * kernel's device time in milliseconds through *ms when ms != NULL (CUDA events on the ctx stream). */

@@ -934,7 +934,7 @@ static int preBatchImpl2(x265cu_ctx* c, int n, const x265cu_frame_in* items, x26
     for (int i = 0; i < n; i++)
     {
         const x265cu_frame_in& f = items[i];
-        if (!f.energy || !f.sums || ((f.u == NULL) != (f.v == NULL)) || !f.y) return fail(c, X265CU_EINVAL, "x265cu_frame_init_var_batch: bad item");
+        if (!f.energy || !f.sums || ((f.u == NULL) != (f.v == NULL)) || !f.y || badSlot(c, f.slot)) return fail(c, X265CU_EINVAL, "x265cu_frame_init_var_batch: bad item");
         if (f.planesAreDevice || !f.u || (((size_t)f.yStride * c->pb) & 7) || f.yStride < 2 * g.width + 1) pipelined = false;
         const size_t yLin = (lumaRows - 1) * (size_t)f.yStride * c->pb + (size_t)(2 * g.width + 1) * c->pb;
         const size_t cLin = f.u ? (chromaRows - 1) * (size_t)f.cStride * c->pb + (size_t)bxN * 8 * c->pb : 0;
@@ -2196,6 +2196,15 @@ int x265cu_pixelcmp_batch(x265cu_ctx* c, int kind, const void* bufA, size_t samp
     if (!c || kind < 0 || kind > 3 || !bufA || !bufB || n < 0 || (n && (!offA || !offB || !out)))
         return c ? fail(c, X265CU_EINVAL, "x265cu_pixelcmp_batch: bad argument") : X265CU_EINVAL;
     if (!n) return X265CU_OK;
+    {
+        /* every block must lie inside the buffers it is taken from */
+        const int64_t ext = kind == 3 ? 16 : 8;
+        if (strideA < ext || strideB < ext) return fail(c, X265CU_EINVAL, "x265cu_pixelcmp_batch: stride smaller than the block");
+        for (int i = 0; i < n; i++)
+            if (offA[i] < 0 || offB[i] < 0 || (uint64_t)(offA[i] + (ext - 1) * (int64_t)strideA + ext) > samplesA ||
+                (uint64_t)(offB[i] + (ext - 1) * (int64_t)strideB + ext) > samplesB)
+                return fail(c, X265CU_EINVAL, "x265cu_pixelcmp_batch: a block lies outside its buffer");
+    }
     std::lock_guard<std::mutex> lk(c->mtx);
     CU_TRY(c, cudaSetDevice(c->cfg.device));
     size_t bytesA = alignUp(samplesA * c->pb + 16, 256), bytesB = alignUp(samplesB * c->pb + 16, 256);
@@ -2217,6 +2226,53 @@ int x265cu_pixelcmp_batch(x265cu_ctx* c, int kind, const void* bufA, size_t samp
             pixelcmp_batch_kernel<uint8_t><<<blocks, 256, 0, c->stream>>>(kind, (const uint8_t*)dA, strideA, (const uint8_t*)dB, strideB, n, dOffA, dOffB, dOut);
         else
             pixelcmp_batch_kernel<uint16_t><<<blocks, 256, 0, c->stream>>>(kind, (const uint16_t*)dA, strideA, (const uint16_t*)dB, strideB, n, dOffA, dOffB, dOut);
+    }
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaMemcpyAsync(out, dOut, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    return syncStream(c);
+}
+
+int x265cu_pixelcmp_pu(x265cu_ctx* c, int kind, int width, int height, const void* bufA, size_t samplesA, intptr_t strideA,
+                       const void* bufB, size_t samplesB, intptr_t strideB, int n, const int64_t* offA, const int64_t* offB, int32_t* out)
+{
+    if (!c || kind < 0 || kind > 1 || !bufA || !bufB || n < 0 || (n && (!offA || !offB || !out)))
+        return c ? fail(c, X265CU_EINVAL, "x265cu_pixelcmp_pu: bad argument") : X265CU_EINVAL;
+    {
+        /* the 25 luma PU shapes of enum LumaPU (common/primitives.h:49-61) */
+        static const unsigned char shapes[25][2] = { { 4, 4 }, { 8, 8 }, { 16, 16 }, { 32, 32 }, { 64, 64 }, { 8, 4 }, { 4, 8 }, { 16, 8 }, { 8, 16 }, { 32, 16 },
+            { 16, 32 }, { 64, 32 }, { 32, 64 }, { 16, 12 }, { 12, 16 }, { 16, 4 }, { 4, 16 }, { 32, 24 }, { 24, 32 }, { 32, 8 }, { 8, 32 }, { 64, 48 }, { 48, 64 },
+            { 64, 16 }, { 16, 64 } };
+        bool known = false;
+        for (int i = 0; i < 25; i++) known = known || (shapes[i][0] == width && shapes[i][1] == height);
+        if (!known) return fail(c, X265CU_EINVAL, "x265cu_pixelcmp_pu: not a luma PU shape");
+    }
+    if (!n) return X265CU_OK;
+    if (strideA < width || strideB < width) return fail(c, X265CU_EINVAL, "x265cu_pixelcmp_pu: stride smaller than the block");
+    for (int i = 0; i < n; i++)
+        if (offA[i] < 0 || offB[i] < 0 || (uint64_t)(offA[i] + (int64_t)(height - 1) * strideA + width) > samplesA ||
+            (uint64_t)(offB[i] + (int64_t)(height - 1) * strideB + width) > samplesB)
+            return fail(c, X265CU_EINVAL, "x265cu_pixelcmp_pu: a block lies outside its buffer");
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CU_TRY(c, cudaSetDevice(c->cfg.device));
+    size_t bytesA = alignUp(samplesA * c->pb + 16, 256), bytesB = alignUp(samplesB * c->pb + 16, 256);
+    size_t offs = alignUp((size_t)n * 8, 256);
+    size_t need = bytesA + bytesB + 2 * offs + alignUp((size_t)n * 4, 256);
+    if (growDevice(c, &c->dGeneric, &c->dGenericCap, need)) return X265CU_ECUDA;
+    uint8_t* dA = c->dGeneric; uint8_t* dB = dA + bytesA;
+    int64_t* dOffA = (int64_t*)(dB + bytesB); int64_t* dOffB = (int64_t*)((uint8_t*)dOffA + offs);
+    int* dOut = (int*)((uint8_t*)dOffB + offs);
+    CU_TRY(c, cudaMemsetAsync(dA, 0, bytesA + bytesB, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(dA, bufA, samplesA * c->pb, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(dB, bufB, samplesB * c->pb, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(dOffA, offA, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(dOffB, offB, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    {
+        KernelScope ks(c, X265CU_K_PIXEL);
+        const int blocks = (n + 7) / 8;
+        if (c->pb == 1)
+            pixelcmp_pu_kernel<uint8_t><<<blocks, 256, 0, c->stream>>>(kind, width, height, (const uint8_t*)dA, strideA, (const uint8_t*)dB, strideB, n, dOffA, dOffB, dOut);
+        else
+            pixelcmp_pu_kernel<uint16_t><<<blocks, 256, 0, c->stream>>>(kind, width, height, (const uint16_t*)dA, strideA, (const uint16_t*)dB, strideB, n, dOffA, dOffB, dOut);
     }
     CU_TRY(c, cudaGetLastError());
     CU_TRY(c, cudaMemcpyAsync(out, dOut, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));

@@ -421,6 +421,37 @@ __device__ __forceinline__ int sa8d_quad_abs(int d[4][4], int sub)
     return sum;
 }
 
+/* pu[partitionFromSizes(w, h)].sad / .satd for any of the 25 luma PU shapes (common/pixel.cpp:954-1004): n
+ * block pairs of one shape at arbitrary sample offsets, a warp per pair, the lanes stride over the PU's 4x4 tiles.  x265's
+ * satd of every shape is the sum over 4x4 tiles of the halved 4x4 Hadamard abs-sum (satd_4x4 for the widths 4 and 12,
+ * satd_8x4 = two such tiles whose packed sum is halved: each tile's abs-sum is even, so halving per tile is the same). */
+template <typename P>
+__global__ void __launch_bounds__(256) pixelcmp_pu_kernel(int satd, int w, int h, const P* __restrict__ A, int64_t strideA, const P* __restrict__ B, int64_t strideB,
+                                                           int n, const int64_t* __restrict__ offA, const int64_t* __restrict__ offB, int* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (idx >= n) return;
+    const P* a = A + offA[idx];
+    const P* b = B + offB[idx];
+    const int tx = w >> 2, tiles = tx * (h >> 2);
+    int acc = 0;
+    for (int t = lane; t < tiles; t += 32)
+    {
+        const int x = (t % tx) * 4, y = (t / tx) * 4;
+        typename Px<P>::Row4 fa[4], fb[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+            fa[i] = Px<P>::load(a + (int64_t)(y + i) * strideA + x);
+            fb[i] = Px<P>::load(b + (int64_t)(y + i) * strideB + x);
+        }
+        acc += satd ? (satd4x4_abs<P>(fa, fb) >> 1) : sad4x4<P>(fa, fb);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[idx] = acc;
+}
+
 /* n block pairs at arbitrary sample offsets; one quad per pair (kind 3 = sa8d 16x16: four passes) */
 template <typename P>
 __global__ void __launch_bounds__(256) pixelcmp_batch_kernel(int kind, const P* __restrict__ A, int64_t strideA, const P* __restrict__ B, int64_t strideB,

@@ -155,6 +155,51 @@ def test_pixelcmp_batch(mods, depth, kind, fn):
         la.close()
 
 
+PU_SHAPES = [(4, 4), (8, 8), (16, 16), (32, 32), (64, 64), (8, 4), (4, 8), (16, 8), (8, 16), (32, 16), (16, 32), (64, 32), (32, 64), (16, 12),
+             (12, 16), (16, 4), (4, 16), (32, 24), (24, 32), (32, 8), (8, 32), (64, 48), (48, 64), (64, 16), (16, 64)]
+
+
+@pytest.mark.parametrize("depth", [8, 10])
+@pytest.mark.parametrize("kind,fn", [(0, "ola_pu_sad"), (1, "ola_pu_satd")])
+def test_pixelcmp_pu_shapes(mods, depth, kind, fn):
+    """pu[LUMA_WxH].sad / .satd of the 25 luma PU shapes (common/pixel.cpp:954-1004) as a batch operation ==
+    the oracle (pinned against the reference's own primitives table per shape in tests/test_oracle_vs_ref.py); TestBench
+    buffers (random / min / max), FENC_STRIDE-like and odd strides, unaligned offsets"""
+    replay, po, abi = mods
+    lib = po.oracle(depth)
+    f = getattr(lib, fn)
+    f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t]
+    L = abi.lib_cu()
+    L.x265cu_pixelcmp_pu.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_ssize_t, C.c_void_p, C.c_size_t, C.c_ssize_t,
+                                     C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    bufs = _pixel_buffers(po, depth, 4321 + kind)
+    la = abi.Lookahead(64, 64, depth, 1, 4, 0, 0, 0, 0, 0.0)
+    try:
+        for w, h in PU_SHAPES:
+            for a, b in ((bufs[0], bufs[0][::-1].copy()), (bufs[0], bufs[1]), (bufs[2], bufs[0]), (bufs[1], bufs[2])):
+                sa, sb = 64, 131
+                n = 40
+                lim_a, lim_b = a.size - (h - 1) * sa - w, b.size - (h - 1) * sb - w
+                offA = (np.arange(n, dtype=np.int64) * 37) % lim_a
+                offB = (np.arange(n, dtype=np.int64) * 53 + 3) % lim_b
+                out = np.zeros(n, np.int32)
+                r = L.x265cu_pixelcmp_pu(la.ctx, kind, w, h, a.ctypes.data, a.size, sa, b.ctypes.data, b.size, sb, n, offA.ctypes.data, offB.ctypes.data, out.ctypes.data)
+                assert r == 0, L.x265cu_last_error(la.ctx)
+                isz = a.itemsize
+                want = np.array([f(w, h, a.ctypes.data + int(oa) * isz, sa, b.ctypes.data + int(ob) * isz, sb) for oa, ob in zip(offA, offB)], np.int32)
+                assert np.array_equal(out, want), (w, h, out[:6], want[:6])
+        # not a PU shape / a block outside its buffer: refused, not computed
+        out = np.zeros(1, np.int32)
+        off = np.zeros(1, np.int64)
+        a = bufs[0]
+        assert L.x265cu_pixelcmp_pu(la.ctx, kind, 24, 24, a.ctypes.data, a.size, 64, a.ctypes.data, a.size, 64, 1, off.ctypes.data, off.ctypes.data, out.ctypes.data) == -1
+        far = np.array([a.size - 10], np.int64)
+        assert L.x265cu_pixelcmp_pu(la.ctx, kind, 8, 8, a.ctypes.data, a.size, 64, a.ctypes.data, a.size, 64, 1, far.ctypes.data, off.ctypes.data, out.ctypes.data) == -1
+        assert L.x265cu_pixelcmp_batch(la.ctx, 0, a.ctypes.data, a.size, 64, a.ctypes.data, a.size, 64, 1, far.ctypes.data, off.ctypes.data, out.ctypes.data) == -1
+    finally:
+        la.close()
+
+
 def test_bad_arguments_fail_loudly(mods):
     replay, po, abi = mods
     L = abi.lib_cu()
