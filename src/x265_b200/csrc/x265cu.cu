@@ -27,6 +27,7 @@
 #include <string.h>
 #include <algorithm>
 #include <chrono>
+#include <cuda.h>
 #include <map>
 #include <mutex>
 #include <thread>
@@ -142,6 +143,9 @@ struct x265cu_ctx
     int searchMode;        /* 0: plain kernel only, 1: speculative path only (with in-batch seed waves), 2: per search (default) */
     int specMaxDist, specMaxPlans;   /* speculative path: hint at most this many frames away, batch of at most this many searches */
     int plainWarps;        /* CU rows (= warps) per CTA of the plain kernel */
+    int plainTma;          /* plain kernel's windows staged by TMA (cp.async.bulk.tensor.3d), the next CU's window requested a step ahead */
+    bool tmaMapValid;
+    PlainTmaMap tmaMap;    /* the frame mirrors as a tensor [slot x 4 planes][padded rows][stride] */
     int plainOneShot;      /* plain kernel with a window: the no-move positions of a search measured in one burst (la_fast_path) */
     int plainOct;          /* plain wavefront search: 1 = octet kernel (x265cu_search_oct.cuh, default), 0 = quad kernel (x265cu_search_plain.cuh) */
     int octWarps;          /* octet kernel: bands of 4 CU rows (= warps) per CTA */
@@ -415,6 +419,9 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     c->plainWin = -2;
     if (const char* e = getenv("X265CU_PLAIN_WIN")) c->plainWin = atoi(e);
     if (const char* e = getenv("X265CU_PLAIN_ROWS")) c->plainWarps = atoi(e);
+    c->plainTma = 0;
+    if (const char* e = getenv("X265CU_PLAIN_TMA")) c->plainTma = atoi(e) != 0;
+    c->tmaMapValid = false;
     c->plainOneShot = 0;      /* measured: no gain at 1080p, 10 % slower at 4K (profiles/README.md, round 2) */
     if (const char* e = getenv("X265CU_PLAIN_ONESHOT")) c->plainOneShot = atoi(e) != 0;
     c->plainOct = 0; c->octWarps = 2;
@@ -492,6 +499,28 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     const size_t S = (size_t)cfg->numFrameSlots, n = (size_t)g.nCU, t2 = (size_t)(c->bf + 2) * (c->bf + 2), t1 = (size_t)2 * (c->bf + 1);
     size_t planeBytes = S * 4 * (size_t)g.planeSize * c->pb + 256;
     OPEN_TRY(cudaMalloc((void**)&c->dPlanes, planeBytes));
+    {
+        /* the frame mirrors as ONE tensor for TMA: dim 0 = samples of a padded row, dim 1 = padded rows of a plane, dim 2 = planes
+         * (4 per slot); a search window is the box {WIN_W, WIN_H, 4}.  The driver entry point is looked up at run time (no
+         * link-time dependency on libcuda); without it the TMA variant of the plain kernel is simply not offered. */
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = NULL;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn && qres == cudaDriverEntryPointSuccess)
+        {
+            const cuuint64_t dims[3] = { (cuuint64_t)c->g.stride, (cuuint64_t)c->g.paddedLines, (cuuint64_t)4 * cfg->numFrameSlots };
+            const cuuint64_t strides[2] = { (cuuint64_t)c->g.stride * c->pb, (cuuint64_t)c->g.planeSize * c->pb };
+            const cuuint32_t box[3] = { (cuuint32_t)(c->pb == 1 ? PlainTma<uint8_t>::RU * 4 : PlainTma<uint16_t>::RU * 4), WIN_H, 4 };
+            const cuuint32_t estr[3] = { 1, 1, 1 };
+            CUtensorMap m;
+            CUresult r = ((EncodeFn)fn)(&m, c->pb == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, c->dPlanes, dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r == CUDA_SUCCESS) { memcpy(&c->tmaMap, &m, sizeof(m)); c->tmaMapValid = true; }
+        }
+        else
+            cudaGetLastError();
+    }
     OPEN_TRY(cudaMemsetAsync(c->dPlanes, 0, planeBytes, c->stream));   /* CHECKED_MALLOC_ZERO, lowres.cpp:62 */
     OPEN_TRY(cudaMalloc((void**)&c->dIntraCost, S * n * sizeof(int)));
     OPEN_TRY(cudaMalloc((void**)&c->dIntraMode, S * n));
@@ -1959,6 +1988,8 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
         d.d0 = j.d0; d.d1 = j.d1;
         d.doSearch[0] = j.doSearch[0] != 0; d.doSearch[1] = j.doSearch[1] != 0;
         d.bidir = j.d1 > 0;
+        d.tmaZ[0] = wSlotOfJob[i] >= 0 ? -1 : 4 * j.ref0;     /* a weighted reference copy lives outside the mirrors */
+        d.tmaZ[1] = 4 * ref1;
     }
     if (!items.empty()) memcpy(c->hArgs + offItems, &items[0], items.size() * sizeof(SearchItem));
     if (!plans.empty()) memcpy(c->hArgs + offPlans, &plans[0], plans.size() * sizeof(SearchPlan));
@@ -2039,19 +2070,28 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
             /* a launch that fills the GPU is bound by L1 line look-ups: it stages each CU's window in shared memory */
             const bool winVariant = c->plainWin == 1 || (c->plainWin == -1 && ni >= 1024) || (c->plainWin == -2 && c->pb == 1);
             const size_t pbRow4 = c->pb == 1 ? 4 : 8;
-            const size_t smem = (size_t)maxPlainRows * g.wCU * sizeof(unsigned long long) + (winVariant ? (size_t)maxPlainRows * WIN_PITCH * pbRow4 : 0);
+            /* TMA variant: the windows come by cp.async.bulk.tensor.3d, two buffers per warp (the next CU's window is requested a
+             * step ahead); needs the tensor map of the frame mirrors */
+            const bool tma = c->plainTma && c->tmaMapValid && (c->plainWin != 0);
+            const size_t handBytes = ((size_t)maxPlainRows * g.wCU * sizeof(unsigned long long) + 127) & ~(size_t)127;
+            const size_t smem = tma ? handBytes + (size_t)maxPlainRows * 2 * (c->pb == 1 ? (size_t)PlainTma<uint8_t>::PITCH : (size_t)PlainTma<uint16_t>::PITCH) * pbRow4 + (size_t)maxPlainRows * 2 * sizeof(unsigned long long)
+                                    : (size_t)maxPlainRows * g.wCU * sizeof(unsigned long long) + (winVariant ? (size_t)maxPlainRows * WIN_PITCH * pbRow4 : 0);
+#define PLAIN_LAUNCH(P, W_, O_, T_) plain_search_kernel<P, W_, O_, T_><<<ni, maxPlainRows * 32, smem, c->stream>>>(dJobs, dPlans, dItems + classItems[2], g, dLutC, dProg, &dCtl->ticket[0], c->tmaMap)
             if (c->pb == 1)
             {
-                if (winVariant && c->plainOneShot) plain_search_kernel<uint8_t, true, true><<<ni, maxPlainRows * 32, smem, c->stream>>>(dJobs, dPlans, dItems + classItems[2], g, dLutC, dProg, &dCtl->ticket[0]);
-                else if (winVariant) plain_search_kernel<uint8_t, true, false><<<ni, maxPlainRows * 32, smem, c->stream>>>(dJobs, dPlans, dItems + classItems[2], g, dLutC, dProg, &dCtl->ticket[0]);
-                else plain_search_kernel<uint8_t, false, false><<<ni, maxPlainRows * 32, smem, c->stream>>>(dJobs, dPlans, dItems + classItems[2], g, dLutC, dProg, &dCtl->ticket[0]);
+                if (tma) PLAIN_LAUNCH(uint8_t, true, false, true);
+                else if (winVariant && c->plainOneShot) PLAIN_LAUNCH(uint8_t, true, true, false);
+                else if (winVariant) PLAIN_LAUNCH(uint8_t, true, false, false);
+                else PLAIN_LAUNCH(uint8_t, false, false, false);
             }
             else
             {
-                if (winVariant && c->plainOneShot) plain_search_kernel<uint16_t, true, true><<<ni, maxPlainRows * 32, smem, c->stream>>>(dJobs, dPlans, dItems + classItems[2], g, dLutC, dProg, &dCtl->ticket[0]);
-                else if (winVariant) plain_search_kernel<uint16_t, true, false><<<ni, maxPlainRows * 32, smem, c->stream>>>(dJobs, dPlans, dItems + classItems[2], g, dLutC, dProg, &dCtl->ticket[0]);
-                else plain_search_kernel<uint16_t, false, false><<<ni, maxPlainRows * 32, smem, c->stream>>>(dJobs, dPlans, dItems + classItems[2], g, dLutC, dProg, &dCtl->ticket[0]);
+                if (tma) PLAIN_LAUNCH(uint16_t, true, false, true);
+                else if (winVariant && c->plainOneShot) PLAIN_LAUNCH(uint16_t, true, true, false);
+                else if (winVariant) PLAIN_LAUNCH(uint16_t, true, false, false);
+                else PLAIN_LAUNCH(uint16_t, false, false, false);
             }
+#undef PLAIN_LAUNCH
         }
         /* speculative path, per wave -- refine: every CU of every search in parallel (estimates + memo); then the commit
          * wavefront: one CTA per row group, one warp per CU row of the group */

@@ -182,6 +182,7 @@ struct JobDev
     int d0, d1;
     int doSearch[2];
     int bidir;
+    int tmaZ[2];               /* first plane of the list's search reference in the frame-mirror tensor (TMA), -1: not in it */
 };
 
 #include "x265cu_search.cuh"

@@ -198,17 +198,18 @@ __device__ __forceinline__ LaneGeom lane_geom(int lane, int stride)
 #define WIN_UNITS (4 * WIN_PLANE_UNITS)
 #define WIN_PITCH (WIN_UNITS + 8)           /* + slack: an aligned read's second unit may lie one past the end */
 
-/* 4 samples at window position (dx, dy) of plane `plane` */
-template <typename P>
+/* 4 samples at window position (dx, dy) of plane `plane`; RU = units of 4 samples per window row (the TMA variant of the
+ * plain kernel loads wider rows: its boxes must start on 16-byte boundaries) */
+template <typename P, int RU = WIN_ROW_UNITS>
 __device__ __forceinline__ typename Px<P>::Row4 win_read(const typename Px<P>::Row4* win, int plane, int dx, int dy)
 {
-    const typename Px<P>::Row4* u = win + plane * WIN_PLANE_UNITS + dy * WIN_ROW_UNITS + (dx >> 2);
+    const typename Px<P>::Row4* u = win + plane * (WIN_H * RU) + dy * RU + (dx >> 2);
     return Px<P>::combine(u[0], u[1], dx & 3);
 }
 
 /* this lane's 4x4 of the reference block at quarter-pel MV (qx, qy), from the window (lx, ly = the
  * lane's sub-block offset minus the window origin) */
-template <typename P>
+template <typename P, int RU = WIN_ROW_UNITS>
 __device__ __forceinline__ void win_qpel(const typename Px<P>::Row4* win, int lx, int ly, int qx, int qy, typename Px<P>::Row4 out[4])
 {
     const int hpelA = (qy & 2) | ((qx & 2) >> 1);
@@ -217,15 +218,15 @@ __device__ __forceinline__ void win_qpel(const typename Px<P>::Row4* win, int lx
     const int ax = lx + (qx >> 2), ay = ly + (qy >> 2), bx = lx + (qx2 >> 2), by = ly + (qy2 >> 2);
 #pragma unroll
     for (int i = 0; i < 4; i++)
-        out[i] = Px<P>::avg(win_read<P>(win, hpelA, ax, ay + i), win_read<P>(win, hpelB, bx, by + i));
+        out[i] = Px<P>::avg(win_read<P, RU>(win, hpelA, ax, ay + i), win_read<P, RU>(win, hpelB, bx, by + i));
 }
 
-template <typename P>
+template <typename P, int RU = WIN_ROW_UNITS>
 __device__ __forceinline__ void win_fpel(const typename Px<P>::Row4* win, int lx, int ly, int fx, int fy, typename Px<P>::Row4 out[4])
 {
 #pragma unroll
     for (int i = 0; i < 4; i++)
-        out[i] = win_read<P>(win, 0, lx + fx, ly + fy + i);
+        out[i] = win_read<P, RU>(win, 0, lx + fx, ly + fy + i);
 }
 
 /* The whole search of one CU for a given MVP `m` (packed quarter-pel), result before the skip

@@ -45,7 +45,7 @@ __device__ __forceinline__ unsigned long long gtimer_ns() { unsigned long long t
  * So the 13 x 16 x 4-plane window around the first candidate vector is staged once per CU in shared memory with
  * row-coalesced loads (56 line look-ups), and every pass whose 8 candidates lie inside it (warp-uniform test) reads
  * shared memory; a pass that leaves the window reads global memory as before. */
-template <typename P, bool WIN>
+template <typename P, bool WIN, int RU = WIN_ROW_UNITS>
 __device__ __forceinline__ void pfetch_qpel(const P* __restrict__ refLane, int planeSize, int stride, const typename Px<P>::Row4* win,
                                             int lx, int ly, int qx, int qy, typename Px<P>::Row4 out[4])
 {
@@ -53,36 +53,91 @@ __device__ __forceinline__ void pfetch_qpel(const P* __restrict__ refLane, int p
     {
         const int qx2 = qx + (qx & 1), qy2 = qy + (qy & 1);
         const int ax = lx + (qx >> 2), ay = ly + (qy >> 2), bx = lx + (qx2 >> 2), by = ly + (qy2 >> 2);
-        const bool ok = (unsigned)ax <= (unsigned)(WIN_W - 4) && (unsigned)bx <= (unsigned)(WIN_W - 4) &&
+        const bool ok = (unsigned)ax <= (unsigned)(RU * 4 - 4) && (unsigned)bx <= (unsigned)(RU * 4 - 4) &&
                         (unsigned)ay <= (unsigned)(WIN_H - 4) && (unsigned)by <= (unsigned)(WIN_H - 4);
-        if (__all_sync(FULL_MASK, ok)) { win_qpel<P>(win, lx, ly, qx, qy, out); return; }
+        if (__all_sync(FULL_MASK, ok)) { win_qpel<P, RU>(win, lx, ly, qx, qy, out); return; }
     }
     fetch_qpel<P>(refLane, planeSize, stride, qx, qy, out);
 }
 
-template <typename P, bool WIN>
+template <typename P, bool WIN, int RU = WIN_ROW_UNITS>
 __device__ __forceinline__ void pfetch_fpel(const P* __restrict__ refLane, int stride, const typename Px<P>::Row4* win,
                                             int lx, int ly, int fx, int fy, typename Px<P>::Row4 out[4])
 {
     if (WIN)
     {
-        const bool ok = (unsigned)(lx + fx) <= (unsigned)(WIN_W - 4) && (unsigned)(ly + fy) <= (unsigned)(WIN_H - 4);
-        if (__all_sync(FULL_MASK, ok)) { win_fpel<P>(win, lx, ly, fx, fy, out); return; }
+        const bool ok = (unsigned)(lx + fx) <= (unsigned)(RU * 4 - 4) && (unsigned)(ly + fy) <= (unsigned)(WIN_H - 4);
+        if (__all_sync(FULL_MASK, ok)) { win_fpel<P, RU>(win, lx, ly, fx, fy, out); return; }
     }
     fetch_off<P>(refLane, stride, fy * stride + fx, out);
 }
 
-template <typename P, bool WIN, bool ONESHOT>
+/* ---- TMA variant (north_star: "TMA/shared-memory staging of the padded search windows").  The frame mirrors are one 3-D
+ * tensor [slot x 4 planes][padded rows][stride]; a window is ONE box {WIN_W, WIN_H, 4 planes} = one cp.async.bulk.tensor.3d
+ * issued by one lane, landing in the WIN layout, completion on an mbarrier.  Because the copy is asynchronous and costs the
+ * warp no registers, the window of the NEXT CU is requested a whole step ahead (around this CU's first candidate vector, 8
+ * samples to the left: the most likely origin) into the other of two buffers; a step whose origin was foreseen finds its
+ * window in shared memory, any other requests it on demand. ---- */
+/* A TMA box must start on a 16-byte boundary of its row, a window starts on a 4-sample one: the box begins at the boundary
+ * below and is 16 bytes wider (8-bit: 32 samples = 8 units per row; 16-bit: 24 samples = 6 units).  The extra columns are
+ * window too: fewer passes leave it. */
+template <typename P> struct PlainTma;
+template <> struct PlainTma<uint8_t> { enum { RU = 8, ALIGN = 16, PITCH = 448 }; };     /* 4 x 13 x 8 units + slack, 1792 bytes */
+template <> struct PlainTma<uint16_t> { enum { RU = 6, ALIGN = 8, PITCH = 320 }; };     /* 4 x 13 x 6 units + slack, 2560 bytes */
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const void* map, void* bar, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity)
+{
+    uint32_t ok;
+    do
+    {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+    while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+struct alignas(64) PlainTmaMap { unsigned long long opaque[16]; };   /* CUtensorMap (128 bytes, 64-byte aligned) */
+
+template <typename P, bool WIN, bool ONESHOT, bool TMA>
 __global__ void __launch_bounds__(PLAIN_MAX_GROUP_ROWS * 32, PLAIN_MIN_CTAS)
 plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restrict__ plans, const SearchItem* __restrict__ items, GeomDev g,
-                    const uint16_t* __restrict__ lut, unsigned long long* gHand, unsigned int* ticket)
+                    const uint16_t* __restrict__ lut, unsigned long long* gHand, unsigned int* ticket, const __grid_constant__ PlainTmaMap tmap)
 {
-    extern __shared__ unsigned long long sHand[];  /* [blockDim / 32][W] hand-off words (+ one window per warp, WIN) */
+    constexpr int RU = TMA ? (int)PlainTma<P>::RU : WIN_ROW_UNITS;     /* units of 4 samples per window row */
+    extern __shared__ __align__(128) unsigned long long sHand[];  /* [blockDim / 32][W] hand-off words (+ window(s) per warp, WIN) */
     const SearchItem it = items[take_ticket(ticket)];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nRows = it.lastY - it.firstY + 1;
     const int W = g.wCU, H = g.hCU;
     typename Px<P>::Row4* win = (typename Px<P>::Row4*)(sHand + (blockDim.x >> 5) * W) + warp * WIN_PITCH;
+    unsigned long long* tmaBar = NULL;
+    typename Px<P>::Row4* tmaWin = NULL;
+    if (TMA)
+    {
+        /* [warps][2] window buffers on 128-byte boundaries behind the hand-off rows, then [warps][2] barriers */
+        const size_t handBytes = ((size_t)(blockDim.x >> 5) * W * sizeof(unsigned long long) + 127) & ~(size_t)127;
+        typename Px<P>::Row4* base = (typename Px<P>::Row4*)((unsigned char*)sHand + handBytes);
+        tmaWin = base + warp * 2 * PlainTma<P>::PITCH;
+        tmaBar = (unsigned long long*)(base + (blockDim.x >> 5) * 2 * PlainTma<P>::PITCH) + warp * 2;
+        if (lane == 0) { mbar_init(tmaBar, 1); mbar_init(tmaBar + 1, 1); }
+        fence_proxy_async();
+        win = tmaWin;
+    }
     for (int i = threadIdx.x; i < nRows * W; i += blockDim.x) sHand[i] = 0;
     const SearchPlan pl = plans[it.search];
     const JobDev* __restrict__ jp = jobs + pl.job;
@@ -147,6 +202,11 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
     }
     int prevMv = 0;                                /* MV of (cuX + 1, cuY): our own previous result */
     int prevBl = 0, prevMb = 0;                    /* MVs of (cuX, cuY + 1) and (cuX + 1, cuY + 1) as read in the step before */
+    /* TMA: the window requested ahead (buffer, tensor coordinates), barrier phases and copies in flight per buffer */
+    const int tmaZ = TMA ? jp->tmaZ[list] : -1;
+    bool pendValid = false;
+    int pendBuf = 0, pendCol = 0, pendRow = 0;
+    uint32_t phase = 0, inflight = 0;
     unsigned long long nextWord = (!lastRow && W > 1) ? below[W - 2] : 0;   /* hand-off word of this step's below-left, loaded ahead */
     typename Px<P>::Row4 fe[4], feNext[4];
 #pragma unroll
@@ -214,15 +274,72 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
         tWaited = clock64() - tStep0;
 #endif
         int lx = 0, ly = 0;
-        if (WIN)
+        if (WIN && TMA && tmaZ >= 0)
+        {
+            /* the window around the first candidate vector: foreseen one step ago, or requested now */
+            const int wx0 = ((la_mv_x(nb0) >> 2) - PWIN_MX) & ~3, wy0 = (la_mv_y(nb0) >> 2) - PWIN_MY;
+            const int col0 = g.marginX + 8 * cuX + wx0, row = g.marginY + 8 * cuY + wy0;
+            const int col = col0 & ~(PlainTma<P>::ALIGN - 1);         /* the box starts on the 16-byte boundary below the window */
+            const uint32_t winBytes = 4 * WIN_H * RU * 4 * (uint32_t)sizeof(P);
+            int buf;
+            if (pendValid && pendCol == col && pendRow == row)
+                buf = pendBuf;
+            else
+            {
+                buf = pendValid ? pendBuf ^ 1 : 0;
+                __syncwarp();
+                if (inflight & (1u << buf)) { mbar_wait(tmaBar + buf, (phase >> buf) & 1u); phase ^= 1u << buf; }
+                if (lane == 0)
+                {
+                    fence_proxy_async();
+                    mbar_expect_tx(tmaBar + buf, winBytes);
+                    tma_load_3d(tmaWin + buf * PlainTma<P>::PITCH, &tmap, tmaBar + buf, col, row, tmaZ);
+                }
+                inflight |= 1u << buf;
+            }
+            mbar_wait(tmaBar + buf, (phase >> buf) & 1u);
+            phase ^= 1u << buf; inflight &= ~(1u << buf);
+            __syncwarp();
+            win = tmaWin + buf * PlainTma<P>::PITCH;
+            lx = bx - wx0 + (col0 - col); ly = by - wy0;
+            pendValid = false;
+            if (cuX > 0)
+            {
+                /* the next CU (8 samples to the left) most likely has this CU's vector as its first candidate */
+                const int nb = buf ^ 1;
+                if (inflight & (1u << nb)) { mbar_wait(tmaBar + nb, (phase >> nb) & 1u); phase ^= 1u << nb; inflight &= ~(1u << nb); }
+                if (lane == 0)
+                {
+                    fence_proxy_async();
+                    mbar_expect_tx(tmaBar + nb, winBytes);
+                    tma_load_3d(tmaWin + nb * PlainTma<P>::PITCH, &tmap, tmaBar + nb, (col0 - 8) & ~(PlainTma<P>::ALIGN - 1), row, tmaZ);
+                }
+                inflight |= 1u << nb;
+                pendValid = true; pendBuf = nb; pendCol = (col0 - 8) & ~(PlainTma<P>::ALIGN - 1); pendRow = row;
+            }
+        }
+        else if (WIN)
         {
             /* stage the window around the first candidate vector (the most likely MVP) */
             const int wx0 = ((la_mv_x(nb0) >> 2) - PWIN_MX) & ~3, wy0 = (la_mv_y(nb0) >> 2) - PWIN_MY;
             const P* __restrict__ wbase = refPlane + (8 * cuY + wy0) * stride + 8 * cuX + wx0;
             __syncwarp();
+            if (TMA)
+            {
+                /* (a weighted reference copy is not part of the tensor: same rows by loads, in the wide-row layout) */
+                win = tmaWin;
+                for (int i = lane; i < 4 * WIN_H * RU; i += 32)
+                {
+                    const int plane = i / (WIN_H * RU), rem = i - plane * (WIN_H * RU), wr = rem / RU, wc = rem % RU;
+                    win[i] = Px<P>::load_aligned(wbase + plane * planeSize + wr * stride + wc * 4);
+                }
+            }
+            else
+            {
 #pragma unroll
-            for (int k = 0; k < (WIN_UNITS + 31) / 32; k++)
-                if (lane + 32 * k < WIN_UNITS) win[lane + 32 * k] = Px<P>::load_aligned(wbase + wOff[k]);
+                for (int k = 0; k < (WIN_UNITS + 31) / 32; k++)
+                    if (lane + 32 * k < WIN_UNITS) win[lane + 32 * k] = Px<P>::load_aligned(wbase + wOff[k]);
+            }
             __syncwarp();
             lx = bx - wx0; ly = by - wy0;
         }
@@ -244,7 +361,7 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
             PCNT(1, 1);
             const int p = la_cand_mv(s, q < numc ? q : 0);
             typename Px<P>::Row4 r[4];
-            pfetch_qpel<P, WIN>(refLane, planeSize, stride, win, lx, ly, la_mv_x(p), la_mv_y(p), r);
+            pfetch_qpel<P, WIN, RU>(refLane, planeSize, stride, win, lx, ly, la_mv_x(p), la_mv_y(p), r);
             const int cost = quad_sum(satd4x4_abs<P>(fe, r)) >> 1;
             la_upd_cand(s, __shfl_sync(FULL_MASK, cost, 0), __shfl_sync(FULL_MASK, cost, 4),
                         __shfl_sync(FULL_MASK, cost, 8), __shfl_sync(FULL_MASK, cost, 12));
@@ -322,7 +439,7 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
             const int qx = q == 0 ? s.pmx : (q == 1 ? ((s.pmx + 2) >> 2) * 4 : 0);
             const int qy = q == 0 ? s.pmy : (q == 1 ? ((s.pmy + 2) >> 2) * 4 : 0);
             typename Px<P>::Row4 r[4];
-            pfetch_qpel<P, WIN>(refLane, planeSize, stride, win, lx, ly, qx, qy, r);
+            pfetch_qpel<P, WIN, RU>(refLane, planeSize, stride, win, lx, ly, qx, qy, r);
             const int mvc = q == 0 ? 0 : lutx[qx] + luty[qy];
             const int cost = quad_sum(sad4x4<P>(fe, r)) + mvc;
             la_upd_start(s, __shfl_sync(FULL_MASK, cost, 0), __shfl_sync(FULL_MASK, cost, 4), __shfl_sync(FULL_MASK, cost, 8));
@@ -337,7 +454,7 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
             {
                 const int fx = s.bmx + hex6dx, fy = s.bmy + hex6dy;
                 typename Px<P>::Row4 r[4];
-                pfetch_fpel<P, WIN>(refLane, stride, win, lx, ly, fx, fy, r);
+                pfetch_fpel<P, WIN, RU>(refLane, stride, win, lx, ly, fx, fy, r);
                 const int cost = quad_sum(sad4x4<P>(fe, r)) + lutx[fx * 4] + luty[fy * 4];
                 more = la_upd_hex6(s, warp_min_key(q < 6, cost, q));
             }
@@ -347,7 +464,7 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
                 const int hdx = la_hex2x((s.dir + q) & 7), hdy = la_hex2y((s.dir + q) & 7);
                 const int hx = s.bmx + hdx, hy = s.bmy + hdy;
                 typename Px<P>::Row4 r3[4];
-                pfetch_fpel<P, WIN>(refLane, stride, win, lx, ly, hx, hy, r3);
+                pfetch_fpel<P, WIN, RU>(refLane, stride, win, lx, ly, hx, hy, r3);
                 const int c3 = quad_sum(sad4x4<P>(fe, r3)) + lutx[hx * 4] + luty[hy * 4];
                 more = la_upd_hex3(s, warp_min_key(q < 3, c3, q));
             }
@@ -359,7 +476,7 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
             {
                 const int fx = s.bmx + sq8dx, fy = s.bmy + sq8dy;
                 typename Px<P>::Row4 r[4];
-                pfetch_fpel<P, WIN>(refLane, stride, win, lx, ly, fx, fy, r);
+                pfetch_fpel<P, WIN, RU>(refLane, stride, win, lx, ly, fx, fy, r);
                 const int cost = quad_sum(sad4x4<P>(fe, r)) + lutx[fx * 4] + luty[fy * 4];
                 subpel = la_upd_sq8(s, warp_min_key(true, cost, q), lut);
             }
@@ -371,7 +488,7 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
                 {
                     const int qx = s.bmx + hpdx, qy = s.bmy + hpdy;
                     typename Px<P>::Row4 r[4];
-                    pfetch_qpel<P, WIN>(refLane, planeSize, stride, win, lx, ly, qx, qy, r);
+                    pfetch_qpel<P, WIN, RU>(refLane, planeSize, stride, win, lx, ly, qx, qy, r);
                     const int cost = quad_sum(sad4x4<P>(fe, r)) + lutx[qx] + luty[qy];
                     la_upd_hpel(s, warp_min_key(q < 4, cost, q));
                 }
@@ -380,7 +497,7 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
                 {
                     const int qx = s.bmx + qpdx, qy = s.bmy + qpdy;
                     typename Px<P>::Row4 r[4];
-                    pfetch_qpel<P, WIN>(refLane, planeSize, stride, win, lx, ly, qx, qy, r);
+                    pfetch_qpel<P, WIN, RU>(refLane, planeSize, stride, win, lx, ly, qx, qy, r);
                     const int cost = (quad_sum(satd4x4_abs<P>(fe, r)) >> 1) + lutx[qx] + luty[qy];
                     const int c0 = __shfl_sync(FULL_MASK, cost, 0);
                     la_upd_qpel(s, c0, warp_min_key(q >= 1 && q < 5, cost, q));
@@ -404,6 +521,12 @@ plain_search_kernel(const JobDev* __restrict__ jobs, const SearchPlan* __restric
             mcOut[cuXY] = s.outcost;
         }
         PCLK(9);
+        if (TMA && cuX == 0 && inflight)
+        {
+            /* no copy may still be writing into this CTA's shared memory when it retires */
+            for (int b2 = 0; b2 < 2; b2++)
+                if (inflight & (1u << b2)) mbar_wait(tmaBar + b2, (phase >> b2) & 1u);
+        }
 #ifdef X265CU_PLAIN_CLOCKS
         if (lane == 0 && gridDim.x < 700 && lastRow && cuY != H - 1) atomicAdd(&g_plainClk[15], 1ull);
         if (lane == 0 && gridDim.x < 700 && cuY == H - 1) atomicAdd(&g_plainClkB[15], 1ull);

@@ -71,11 +71,14 @@ def test_replay_plain_window_variants(mods, monkeypatch, name, win):
                                       ("pool3_720p", {"X265CU_PLAIN_OCT": "1", "X265CU_OCT_WARPS": "1", "X265CU_OCT_SLACK": "3", "X265CU_OCT_FULL_WARPS": "1"}),
                                       ("odd8", {"X265CU_PLAIN_OCT": "1", "X265CU_PLAIN_WIN": "0"}),
                                       ("c0_720p", {"X265CU_PLAIN_ONESHOT": "1"}), ("c0_720p10", {"X265CU_PLAIN_ONESHOT": "1", "X265CU_PLAIN_WIN": "1"}),
-                                      ("odd8", {"X265CU_PLAIN_ONESHOT": "1"})])
+                                      ("odd8", {"X265CU_PLAIN_ONESHOT": "1"}),
+                                      ("c0_720p", {"X265CU_PLAIN_TMA": "1"}), ("c0_720p10", {"X265CU_PLAIN_TMA": "1", "X265CU_PLAIN_WIN": "1"}),
+                                      ("odd8", {"X265CU_PLAIN_TMA": "1"}), ("pool3_720p", {"X265CU_PLAIN_TMA": "1", "X265CU_PLAIN_ROWS": "8"})])
 def test_replay_experimental_search_kernels(mods, monkeypatch, name, env):
     """kernels kept for the record, off by default (profiles/README.md: measured slower): the octet wavefront kernel (an octet
     per CU, four CU rows per warp in lock step; other band counts, with the keep-a-distance wait, without the window) and the
-    plain kernel's one-shot burst (la_fast_path); both must still be bit-exact"""
+    plain kernel's one-shot burst (la_fast_path) and its TMA-staged, double-buffered windows (cp.async.bulk.tensor.3d +
+    mbarrier; weighted references fall back to the load path inside the same launch); all must still be bit-exact"""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     monkeypatch.setenv("X265CU_SEARCH_MODE", "0")
