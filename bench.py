@@ -250,30 +250,44 @@ class Runner:
         self.la.close()
 
 
-def multi_stream(torch, dist, world, trace, clip, device, nstreams, steps):
-    """nstreams independent encoder streams on ONE GPU, one host thread + one context + one CUDA stream
-    each (x265cu contexts are independent); device-resident mode.  A single stream is bound by the
-    dependent wavefront chain of each estimate and leaves most SMs idle, so streams overlap almost
-    freely.  Timed by wall clock between device-wide synchronizes (auxiliary figure)."""
+def multi_stream(torch, dist, world, rank, workload, device, nstreams, steps):
+    """BASELINE configs[4]: nstreams independent encoder streams per GPU (64 over 8 GPUs), each an x265 Lookahead of its own
+    (own thread pool, own x265cu context, own CUDA stream) bound to libx265cu.so -- the e2e arm, several at a time.  A single
+    stream is bound by the dependent wavefront chain of its estimates and leaves most SMs idle, so streams overlap.  Streams
+    are dealt to the ranks by harness/sharding.py; every stream's decisions (slice type of every picture) are digested and
+    the digests gathered once: each must equal the digest of the reference's decisions (golden trace).  Wall clock between
+    device-wide synchronizes around `steps` passes of every stream, max over ranks."""
     import threading
-    runners = [Runner(trace, clip, None, device, True, torch) for _ in range(nstreams)]
-    errs = []
+    from harness import sharding, replay
+    from oracle import pyoracle as po
+    total = nstreams * world
+    mine = sharding.assign(total, world, rank)
+    trace = po.Trace(replay.trace_path(workload))
+    n = trace.cfg["nframes"]
+    want = [0] * n
+    for e in trace.events:
+        if e[0] == "D":
+            want[e[1]] = e[2]
+    expected = sharding.digest(want)
+    hosts = [X265Host(workload, device) for _ in mine]
+    errs, last = [], {}
 
-    def work(r, n):
+    def work(k, count):
         try:
-            for _ in range(n):
-                r.step()
+            for _ in range(count):
+                _, types, _ = hosts[k].d.run()
+            last[mine[k]] = (n, sharding.digest(types))
         except Exception as ex:   # pragma: no cover
             errs.append(str(ex))
 
-    def run_all(n):
-        th = [threading.Thread(target=work, args=(r, n)) for r in runners]
+    def run_all(count):
+        th = [threading.Thread(target=work, args=(k, count)) for k in range(len(hosts))]
         for t in th:
             t.start()
         for t in th:
             t.join()
 
-    run_all(1)
+    run_all(2)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -285,11 +299,16 @@ def multi_stream(torch, dist, world, trace, clip, device, nstreams, steps):
         t = torch.tensor([dt], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-    for r in runners:
-        r.close()
-    frames = world * nstreams * steps * trace.cfg["nframes"]
-    return {"streams_per_gpu": nstreams, "value": frames / dt, "unit": "frames/s", "steps": steps, "seconds": dt,
-            "timing": "wall clock between device-wide synchronizes, max over ranks", "errors": errs}
+    for h in hosts:
+        h.close()
+    merged = sharding.gather_results(dist if world > 1 else None, last)
+    bad = sorted(sid for sid, (_, dg) in merged.items() if dg != expected)
+    return {"streams_per_gpu": nstreams, "streams": total, "value": total * steps * n / dt, "unit": "frames/s", "steps": steps, "seconds": dt,
+            "what": "x265 1.9 Lookahead per stream bound to libx265cu.so (e2e: host pictures in, every Lowres array back), %d streams on %d GPU(s)" % (total, world),
+            "timing": "wall clock between device-wide synchronizes around all passes of all streams, max over ranks",
+            "parity": ("every stream's slice-type decisions == the reference's (digest %08x, %d streams gathered)" % (expected, len(merged)))
+                      if not bad and len(merged) == total else "FAILED for streams %r (%d of %d gathered)" % (bad, len(merged), total),
+            "errors": errs}
 
 
 def pin_rank(local, nlocal):
@@ -663,7 +682,7 @@ def main():
     # ---- auxiliary: several independent streams per GPU (the production shape, BASELINE configs[4]) ----
     multi = None
     if args.streams > 1 and not args.quick:
-        multi = multi_stream(torch, dist, world, trace, clip, local, args.streams, max(1, min(args.steps, 2)))
+        multi = multi_stream(torch, dist, world, rank, args.workload, local, args.streams, max(args.steps, 20))
     del trace, clip
 
     # ---- the other BASELINE configs, same measurements (N = 1: the target config of north_star is 4K rc-lookahead 40) ----

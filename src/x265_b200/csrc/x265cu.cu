@@ -94,6 +94,7 @@ struct x265cu_ctx
     unsigned long long* dPropagate;        /* [slot][nCU] Lowres::propagateCost accumulators (x265cu_cutree.cuh) */
     /* explicit weighted-prediction analysis (x265cu_wp.cuh): compact copies of the source chroma planes per slot, the
      * motion-compensated reference plane and the vectors / intra costs of the (slice, list, plane) being analysed */
+    std::vector<std::pair<void*, size_t> > fixedAllocs;     /* arrays of x265cu_open, returned to the pool by x265cu_close */
     uint8_t* dChroma; int chromaPitch, chromaRows; std::vector<char> hasChroma;
     uint8_t* dWp; size_t dWpCap;
     WpCostArgs wpArgs; bool wpReady;
@@ -217,6 +218,23 @@ void poolGive(std::vector<PooledBuf>& pool, int device, void* p, size_t cap)
     pool.push_back(b);
 }
 
+/* the per-context arrays of x265cu_open: same sizes for every context of a configuration, so a closed context's arrays serve
+ * the next one (an encoder farm opens and closes contexts all the time; cudaMalloc / cudaFree stall every stream of the device) */
+cudaError_t fixedAlloc(x265cu_ctx* c, void** p, size_t bytes)
+{
+    size_t cap = 0;
+    void* q = poolTake(g_devPool, c->cfg.device, bytes, &cap);
+    if (q && cap != bytes) { poolGive(g_devPool, c->cfg.device, q, cap); q = NULL; }
+    if (!q)
+    {
+        cudaError_t e = cudaMalloc(&q, bytes);
+        if (e != cudaSuccess) return e;
+    }
+    *p = q;
+    c->fixedAllocs.push_back(std::make_pair(q, bytes));
+    return cudaSuccess;
+}
+
 int growDevice(x265cu_ctx* c, uint8_t** p, size_t* cap, size_t need)
 {
     if (*cap >= need) return 0;
@@ -326,11 +344,9 @@ bool badSlot(const x265cu_ctx* c, int s) { return s < 0 || s >= c->cfg.numFrameS
 
 void freeAll(x265cu_ctx* c)
 {
-    cudaFree(c->dPlanes); cudaFree(c->dIntraCost); cudaFree(c->dIntraMode); cudaFree(c->dInvQ);
-    cudaFree(c->dLowresCosts); cudaFree(c->dRowSatds); cudaFree(c->dMvs); cudaFree(c->dMvCosts);
-    cudaFree(c->dPropagate); cudaFree(c->dChroma);
+    for (size_t i = 0; i < c->fixedAllocs.size(); i++) poolGive(g_devPool, c->cfg.device, c->fixedAllocs[i].first, c->fixedAllocs[i].second);
+    c->fixedAllocs.clear();
     poolGive(g_devPool, c->cfg.device, c->dWp, c->dWpCap);
-    cudaFree(c->dLut); cudaFree(c->dSrc); cudaFree(c->dSmall);
     /* the on-demand work buffers go back to the process-wide pool (growDevice / growHost); every stream of the context is
      * idle here (x265cu_close waited for them) */
     const int dev = c->cfg.device;
@@ -498,7 +514,7 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
 
     const size_t S = (size_t)cfg->numFrameSlots, n = (size_t)g.nCU, t2 = (size_t)(c->bf + 2) * (c->bf + 2), t1 = (size_t)2 * (c->bf + 1);
     size_t planeBytes = S * 4 * (size_t)g.planeSize * c->pb + 256;
-    OPEN_TRY(cudaMalloc((void**)&c->dPlanes, planeBytes));
+    OPEN_TRY(fixedAlloc(c, (void**)&c->dPlanes, planeBytes));
     {
         /* the frame mirrors as ONE tensor for TMA: dim 0 = samples of a padded row, dim 1 = padded rows of a plane, dim 2 = planes
          * (4 per slot); a search window is the box {WIN_W, WIN_H, 4}.  The driver entry point is looked up at run time (no
@@ -522,28 +538,28 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
             cudaGetLastError();
     }
     OPEN_TRY(cudaMemsetAsync(c->dPlanes, 0, planeBytes, c->stream));   /* CHECKED_MALLOC_ZERO, lowres.cpp:62 */
-    OPEN_TRY(cudaMalloc((void**)&c->dIntraCost, S * n * sizeof(int)));
-    OPEN_TRY(cudaMalloc((void**)&c->dIntraMode, S * n));
-    OPEN_TRY(cudaMalloc((void**)&c->dInvQ, S * n * sizeof(int)));
-    OPEN_TRY(cudaMalloc((void**)&c->dLowresCosts, S * t2 * n * sizeof(uint16_t)));
-    OPEN_TRY(cudaMalloc((void**)&c->dRowSatds, S * t2 * g.hCU * sizeof(int)));
-    OPEN_TRY(cudaMalloc((void**)&c->dMvs, S * t1 * n * sizeof(int)));
-    OPEN_TRY(cudaMalloc((void**)&c->dMvCosts, S * t1 * n * sizeof(int)));
+    OPEN_TRY(fixedAlloc(c, (void**)&c->dIntraCost, S * n * sizeof(int)));
+    OPEN_TRY(fixedAlloc(c, (void**)&c->dIntraMode, S * n));
+    OPEN_TRY(fixedAlloc(c, (void**)&c->dInvQ, S * n * sizeof(int)));
+    OPEN_TRY(fixedAlloc(c, (void**)&c->dLowresCosts, S * t2 * n * sizeof(uint16_t)));
+    OPEN_TRY(fixedAlloc(c, (void**)&c->dRowSatds, S * t2 * g.hCU * sizeof(int)));
+    OPEN_TRY(fixedAlloc(c, (void**)&c->dMvs, S * t1 * n * sizeof(int)));
+    OPEN_TRY(fixedAlloc(c, (void**)&c->dMvCosts, S * t1 * n * sizeof(int)));
     OPEN_TRY(cudaMemsetAsync(c->dMvs, 0, S * t1 * n * sizeof(int), c->stream));
     OPEN_TRY(cudaMemsetAsync(c->dMvCosts, 0, S * t1 * n * sizeof(int), c->stream));
     {
         const int bxN = (cfg->srcWidth + 15) / 16, byN = (cfg->srcHeight + 15) / 16;
         c->chromaPitch = 8 * bxN; c->chromaRows = 8 * byN;
-        OPEN_TRY(cudaMalloc((void**)&c->dChroma, S * 2 * (size_t)c->chromaPitch * c->chromaRows * c->pb));
+        OPEN_TRY(fixedAlloc(c, (void**)&c->dChroma, S * 2 * (size_t)c->chromaPitch * c->chromaRows * c->pb));
         c->hasChroma.assign(S, 0);
     }
-    OPEN_TRY(cudaMalloc((void**)&c->dPropagate, S * n * sizeof(unsigned long long)));
+    OPEN_TRY(fixedAlloc(c, (void**)&c->dPropagate, S * n * sizeof(unsigned long long)));
     OPEN_TRY(cudaMemsetAsync(c->dPropagate, 0, S * n * sizeof(unsigned long long), c->stream));
-    OPEN_TRY(cudaMalloc((void**)&c->dLut, (4 * 32768 + 1) * sizeof(uint16_t)));
+    OPEN_TRY(fixedAlloc(c, (void**)&c->dLut, (4 * 32768 + 1) * sizeof(uint16_t)));
     OPEN_TRY(cudaMemcpyAsync(c->dLut, cfg->mvcost - 2 * 32768, (4 * 32768 + 1) * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
     c->srcPitch = (int64_t)alignUp((size_t)(2 * g.width + 1), 64);
-    OPEN_TRY(cudaMalloc((void**)&c->dSrc, (size_t)c->srcPitch * (2 * g.lines + 1) * c->pb + 256));
-    OPEN_TRY(cudaMalloc((void**)&c->dSmall, 64 * sizeof(unsigned long long)));
+    OPEN_TRY(fixedAlloc(c, (void**)&c->dSrc, (size_t)c->srcPitch * (2 * g.lines + 1) * c->pb + 256));
+    OPEN_TRY(fixedAlloc(c, (void**)&c->dSmall, 64 * sizeof(unsigned long long)));
     c->hasInvQ.assign(S, 0);
     c->slotPoc.assign(S, 0);
     c->pocBase = 0;
