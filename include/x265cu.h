@@ -260,6 +260,30 @@ int x265cu_pixelcmp_batch(x265cu_ctx* ctx, int kind, const void* bufA, size_t sa
  * shapes): n block pairs of ONE shape.  sad_x3 / sad_x4 are the same measure with one source offset repeated. */
 int x265cu_pixelcmp_pu(x265cu_ctx* ctx, int kind, int width, int height, const void* bufA, size_t samplesA, intptr_t strideA,
                        const void* bufB, size_t samplesB, intptr_t strideB, int n, const int64_t* offA, const int64_t* offB, int32_t* out);
+/* MotionEstimate::motionEstimate on full-resolution planes (encoder/motion.cpp:571-1172 with ref->isLowres == false; SURVEY.md
+ * 8f-4): n independent searches of ONE PU shape in one launch, a warp per search.  searchMethod = X265_DIA_SEARCH (0),
+ * X265_HEX_SEARCH (1), X265_UMH_SEARCH (2), X265_STAR_SEARCH (3), X265_FULL_SEARCH (4) (x265.h); subpelRefine 0..7 selects
+ * workload[] (motion.cpp:45-55).  Luma only, as the lookahead's setSourcePU (motion.cpp:165-181; bChromaSATD needs the
+ * encoder's Yuv/PicYuv objects and stays out of scope).  An item carries what the reference call takes: setSourcePU's offset
+ * (= blockOffset, applied to both planes), mvmin / mvmax in full-pel units, the predictor qmvp and up to 12 candidates mvc in
+ * quarter-pel units, merange.  mvcostCentre = BitCost's table of the slice QP (m_cost, bitcost.cpp:31-59; entries
+ * [-65536, 65536] are read), built by the host as for x265cu_config::mvcostLUT.  Every block the search can touch -- the
+ * window widened by 16 samples on each side -- must lie inside refPlane (x265's planes have the margins for it).
+ * Host arrays in, results out; *ms (may be NULL) = the kernel's device time. */
+enum { X265CU_DIA_SEARCH = 0, X265CU_HEX_SEARCH = 1, X265CU_UMH_SEARCH = 2, X265CU_STAR_SEARCH = 3, X265CU_FULL_SEARCH = 4 };
+typedef struct x265cu_me_item
+{
+    int64_t offset;
+    int16_t mvmin[2], mvmax[2];
+    int16_t qmvp[2];
+    int16_t numCandidates, merange;
+    int16_t mvc[12][2];
+} x265cu_me_item;
+typedef struct x265cu_me_result { int16_t mv[2]; int32_t cost; } x265cu_me_result;
+int x265cu_motion_estimate(x265cu_ctx* ctx, int searchMethod, int subpelRefine, int width, int height,
+                           const void* fencPlane, size_t fencSamples, intptr_t fencStride,
+                           const void* refPlane, size_t refSamples, intptr_t refStride, const uint16_t* mvcostCentre,
+                           int n, const x265cu_me_item* items, x265cu_me_result* out, float* ms);
 /* same metric over every aligned 8x8 block of plane 0 of nPairs pairs of frame slots, device
  * resident, ONE launch; out (host, may be NULL) gets nPairs * cuCount results.  Returns the
  * kernel's device time in milliseconds through *ms when ms != NULL (CUDA events on the ctx stream). */

@@ -135,6 +135,44 @@ uint32_t x265ref_wp_cost(pixel* fenc, pixel* ref, pixel* weightTemp, intptr_t st
     return wpref::weightCost(fenc, ref, weightTemp, stride, c, width, height, weighted ? &w : NULL, intraCost != NULL);
 }
 
+/* MotionEstimate::motionEstimate on full-resolution planes (encoder/motion.cpp:571-1172, ref->isLowres == false), through the
+ * lookahead's luma-only setSourcePU (:165-181).  Items/results have the layout of include/x265cu.h's x265cu_me_item/_result. */
+struct RefMeItem { int64_t offset; int16_t mvmin[2], mvmax[2], qmvp[2]; int16_t numCandidates, merange; int16_t mvc[12][2]; };
+struct RefMeResult { int16_t mv[2]; int32_t cost; };
+namespace { struct MeWithTable : public MotionEstimate { void setTable(uint16_t* centre) { m_cost = centre; } }; }
+/* lutCentre != NULL: the search reads this mvcost table (centre pointer) instead of BitCost's own for `qp` -- the search code
+ * is untouched, only the protected m_cost pointer is set, so that goldens can be made with a table every machine can rebuild */
+void x265ref_motion_estimate_batch(int method, int subme, int qp, int w, int h, pixel* fencPlane, intptr_t fencStride,
+                                   pixel* refPlane, intptr_t refStride, int n, const RefMeItem* items, RefMeResult* out, uint16_t* lutCentre)
+{
+    x265ref_setup();
+    MeWithTable me;
+    me.init(method, subme, X265_CSP_I400);
+    if (lutCentre) me.setTable(lutCentre); else me.setQP(qp);
+    ReferencePlanes ref;
+    memset(&ref, 0, sizeof(ref));
+    ref.fpelPlane[0] = refPlane;
+    ref.lumaStride = refStride;
+    ref.isLowres = false;
+    for (int i = 0; i < n; i++)
+    {
+        const RefMeItem& it = items[i];
+        me.setSourcePU(fencPlane, fencStride, (intptr_t)it.offset, w, h);
+        MV mvc[12], outmv;
+        for (int k = 0; k < it.numCandidates; k++) mvc[k] = MV(it.mvc[k][0], it.mvc[k][1]);
+        out[i].cost = me.motionEstimate(&ref, MV(it.mvmin[0], it.mvmin[1]), MV(it.mvmax[0], it.mvmax[1]), MV(it.qmvp[0], it.qmvp[1]),
+                                        it.numCandidates, mvc, it.merange, outmv);
+        out[i].mv[0] = outmv.x; out[i].mv[1] = outmv.y;
+    }
+}
+/* LUT[-65536 .. 65536] of BitCost::setQP(qp), and the lambda it was made with */
+void x265ref_mvcost_table_qp(int qp, uint16_t* out)
+{
+    ExposeBitCost bc;
+    bc.setQP(qp);
+    memcpy(out, bc.table() - 2 * 32768, (4 * 32768 + 1) * sizeof(uint16_t));
+}
+double x265ref_lambda(int qp) { return x265_lambda_tab[qp]; }
 
 
 } // extern "C"

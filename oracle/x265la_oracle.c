@@ -1456,3 +1456,507 @@ uint32_t ola_wp_cost(const pixel* fenc, const pixel* ref, pixel* weightTemp, int
         }
     return cost;
 }
+
+/* ================================================================================================
+ * full-resolution motion search of one PU: MotionEstimate::motionEstimate with
+ * ref->isLowres == false, encoder/motion.cpp:571-1172, all five integer patterns (DIA :650-668, HEX :670-742,
+ * UMH :744-927, STAR :929-1037 + StarPatternSearch :329-569, FULL :1039-1071), the predictor candidates (:627-641) and
+ * the sub-pel refinement ladder (:1085-1168, workload[] :45-55) on subpelCompare (:1174-1203: luma only, the lookahead's
+ * setSourcePU variant :165-181 has no chroma), whose fractional blocks come from the 8-tap filters
+ * interp_horiz_pp_c / interp_vert_pp_c / interp_hv_pp_c (common/ipfilter.cpp:80-119,166-205,366-372).
+ * Written as a list-driven machine ("measure these points in this order, keep the first strict minimum") instead of the
+ * reference's macro ladders; decisions are the same, point for point.
+ * ============================================================================================== */
+
+/* g_lumaFilter, common/constants.cpp:239-245 */
+static const int16_t pme_luma_filter[4][8] = {
+    { 0, 0, 0, 64, 0, 0, 0, 0 }, { -1, 4, -10, 58, 17, -5, 1, 0 }, { -1, 4, -11, 40, 40, -11, 4, -1 }, { 0, 1, -5, 17, 58, -10, 4, -1 } };
+
+typedef struct pme_state
+{
+    int w, h, sizeScale;                 /* sizeScale[partEnum] = (h * h) >> 4, motion.cpp:121-151 */
+    const pixel* fenc; intptr_t fs;      /* the PU in the source plane */
+    const pixel* fref; intptr_t rs;      /* fpelPlane[0] + blockOffset */
+    const uint16_t* lut;                 /* centre of the mvcost table */
+    int16_t mvpx, mvpy;                  /* setMVP(qmvp): the UNCLIPPED predictor */
+    int16_t minx, miny, maxx, maxy;      /* full-pel search window */
+    int16_t bx, by; int bcost;           /* best full-pel vector so far */
+} pme_state;
+
+static int pme_mvcost(const pme_state* s, int16_t qx, int16_t qy)
+{
+    return (uint16_t)(s->lut[qx - s->mvpx] + s->lut[qy - s->mvpy]);    /* BitCost::mvcost returns uint16_t, bitcost.h:45 */
+}
+static int pme_fpel_cost(const pme_state* s, int mx, int my)
+{
+    return ola_pu_sad(s->w, s->h, s->fenc, s->fs, s->fref + mx + (intptr_t)my * s->rs, s->rs) + pme_mvcost(s, (int16_t)(mx << 2), (int16_t)(my << 2));
+}
+static int pme_in_range(const pme_state* s, int x, int y) { return x >= s->minx && x <= s->maxx && y >= s->miny && y <= s->maxy; }
+/* COST_MV (:225-231): returns 1 when the point became the best */
+static int pme_try(pme_state* s, int mx, int my)
+{
+    int c = pme_fpel_cost(s, mx, my);
+    if (c < s->bcost) { s->bcost = c; s->bx = (int16_t)mx; s->by = (int16_t)my; return 1; }
+    return 0;
+}
+
+/* subpelCompare, :1174-1203, luma part */
+static int pme_subpel(const pme_state* s, int16_t qx, int16_t qy, int useSatd)
+{
+    const pixel* r = s->fref + (qx >> 2) + (intptr_t)(qy >> 2) * s->rs;
+    const int xf = qx & 3, yf = qy & 3, w = s->w, h = s->h;
+    if (!(xf | yf))
+        return useSatd ? ola_pu_satd(w, h, s->fenc, s->fs, r, s->rs) : ola_pu_sad(w, h, s->fenc, s->fs, r, s->rs);
+    pixel buf[64 * 64];
+    if (!yf || !xf)
+    {
+        /* one 8-tap pass, rounded to pixels: shift 6, offset 32 */
+        const int16_t* c = pme_luma_filter[yf ? yf : xf];
+        const intptr_t step = yf ? s->rs : 1;
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++)
+            {
+                const pixel* p = r + x + (intptr_t)y * s->rs - 3 * step;
+                int sum = 0;
+                for (int k = 0; k < 8; k++) sum += p[k * step] * c[k];
+                int16_t v = (int16_t)((sum + 32) >> 6);
+                buf[y * 64 + x] = clip_pixel(v);
+            }
+    }
+    else
+    {
+        /* horizontal pass into 14-bit intermediates over h + 7 rows, then the vertical pass */
+        int16_t mid[(64 + 7) * 64];
+        const int head = 14 - ORACLE_DEPTH, sh1 = 6 - head, off1 = -(8192 << sh1);
+        const int sh2 = 6 + head, off2 = (1 << (sh2 - 1)) + (8192 << 6);
+        const int16_t* cx = pme_luma_filter[xf];
+        const int16_t* cy = pme_luma_filter[yf];
+        for (int y = 0; y < h + 7; y++)
+            for (int x = 0; x < w; x++)
+            {
+                const pixel* p = r + x - 3 + (intptr_t)(y - 3) * s->rs;
+                int sum = 0;
+                for (int k = 0; k < 8; k++) sum += p[k] * cx[k];
+                mid[y * w + x] = (int16_t)((sum + off1) >> sh1);
+            }
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++)
+            {
+                int sum = 0;
+                for (int k = 0; k < 8; k++) sum += mid[(y + k) * w + x] * cy[k];
+                int16_t v = (int16_t)((sum + off2) >> sh2);
+                buf[y * 64 + x] = clip_pixel(v);
+            }
+    }
+    return useSatd ? ola_pu_satd(w, h, s->fenc, s->fs, buf, 64) : ola_pu_sad(w, h, s->fenc, s->fs, buf, 64);
+}
+
+static const int8_t pme_hex2[8][2] = { { -1, -2 }, { -2, 0 }, { -1, 2 }, { 1, 2 }, { 2, 0 }, { 1, -2 }, { -1, -2 }, { -2, 0 } };
+static const int8_t pme_square1[9][2] = { { 0, 0 }, { 0, -1 }, { 0, 1 }, { -1, 0 }, { 1, 0 }, { -1, -1 }, { -1, 1 }, { 1, -1 }, { 1, 1 } };
+static const int8_t pme_hex4[16][2] = { { 0, -4 }, { 0, 4 }, { -2, -3 }, { 2, -3 }, { -4, -2 }, { 4, -2 }, { -4, -1 }, { 4, -1 },
+                                       { -4, 0 }, { 4, 0 }, { -4, 1 }, { 4, 1 }, { -4, 2 }, { 4, 2 }, { -2, 3 }, { 2, 3 } };
+/* offsets[] of the two-point search, :70-80 */
+static const int8_t pme_two_point[16][2] = { { -1, 0 }, { 0, -1 }, { -1, -1 }, { 1, -1 }, { -1, 0 }, { 1, 0 }, { -1, 1 }, { -1, -1 },
+                                            { 1, -1 }, { 1, 1 }, { -1, 0 }, { 0, 1 }, { -1, 1 }, { 1, 1 }, { 1, 0 }, { 0, 1 } };
+
+/* n points around (ox, oy), measured in order; the first strict minimum below bcost wins (COST_MV_X4 :266-283) */
+static void pme_try_around(pme_state* s, int ox, int oy, const int8_t (*d)[2], int n)
+{
+    for (int i = 0; i < n; i++) pme_try(s, ox + d[i][0], oy + d[i][1]);
+}
+
+/* the HEX pattern, :670-742: hexagon walk, then the 8-point square */
+static void pme_hex(pme_state* s, int merange)
+{
+    int dir = -1, best = s->bcost;
+    for (int k = 0; k < 6; k++)
+    {
+        /* order (-2,0) (-1,2) (1,2) (2,0) (1,-2) (-1,-2) = hex2[1..6] */
+        int c = pme_fpel_cost(s, s->bx + pme_hex2[k + 1][0], s->by + pme_hex2[k + 1][1]);
+        if (c < best) { best = c; dir = k; }
+    }
+    if (dir >= 0)
+    {
+        s->bcost = best;
+        s->bx += pme_hex2[dir + 1][0]; s->by += pme_hex2[dir + 1][1];
+        for (int i = (merange >> 1) - 1; i > 0 && pme_in_range(s, s->bx, s->by); i--)
+        {
+            int step = -1;
+            for (int k = 0; k < 3; k++)
+            {
+                int c = pme_fpel_cost(s, s->bx + pme_hex2[dir + k][0], s->by + pme_hex2[dir + k][1]);
+                if (c < best) { best = c; step = k; }
+            }
+            if (step < 0) break;
+            s->bcost = best;
+            dir += step - 1;                       /* dir += (bcost & 7) - 2 with tags 1..3 */
+            dir = (dir + 6) % 6;                   /* mod6m1[dir + 1] */
+            s->bx += pme_hex2[dir + 1][0]; s->by += pme_hex2[dir + 1][1];
+        }
+    }
+    int sq = 0;
+    for (int k = 1; k <= 8; k++)
+    {
+        int c = pme_fpel_cost(s, s->bx + pme_square1[k][0], s->by + pme_square1[k][1]);
+        if (c < s->bcost) { s->bcost = c; sq = k; }
+    }
+    s->bx += pme_square1[sq][0]; s->by += pme_square1[sq][1];
+}
+
+/* CROSS (:303-327) around (ox, oy) */
+static void pme_cross(pme_state* s, int ox, int oy, int start, int xmax, int ymax)
+{
+    int16_t i = (int16_t)start;
+    if (xmax <= imin(s->maxx - ox, ox - s->minx))
+        for (; i < xmax - 2; i += 4)
+        {
+            pme_try(s, ox + i, oy); pme_try(s, ox - i, oy); pme_try(s, ox + i + 2, oy); pme_try(s, ox - i - 2, oy);
+        }
+    for (; i < xmax; i += 2)
+    {
+        if (ox + i <= s->maxx) pme_try(s, ox + i, oy);
+        if (ox - i >= s->minx) pme_try(s, ox - i, oy);
+    }
+    i = (int16_t)start;
+    if (ymax <= imin(s->maxy - oy, oy - s->miny))
+        for (; i < ymax - 2; i += 4)
+        {
+            pme_try(s, ox, oy + i); pme_try(s, ox, oy - i); pme_try(s, ox, oy + i + 2); pme_try(s, ox, oy - i - 2);
+        }
+    for (; i < ymax; i += 2)
+    {
+        if (oy + i <= s->maxy) pme_try(s, ox, oy + i);
+        if (oy - i >= s->miny) pme_try(s, ox, oy - i);
+    }
+}
+
+/* StarPatternSearch, :329-569.  Every ring is a list of points in one fixed order; a point is measured when the whole
+ * ring lies inside the window, otherwise when ITS OWN one or two listed conditions hold (the reference tests only the
+ * components that move: literal). */
+static void pme_star_point(pme_state* s, int x, int y, int ringInside, int okA, int okB, int point, int dist, int* bPoint, int* bDist)
+{
+    if (!(ringInside || (okA && okB))) return;
+    if (pme_try(s, x, y)) { *bPoint = point; *bDist = dist; }
+}
+static void pme_star_pattern(pme_state* s, int* bPoint, int* bDist, int earlyExitIters, int merange)
+{
+    const int ox = s->bx, oy = s->by;
+    int rounds = 0;
+    for (int dist = 1; dist <= 8; dist <<= 1)
+    {
+        const int16_t top = (int16_t)(oy - dist), bottom = (int16_t)(oy + dist), left = (int16_t)(ox - dist), right = (int16_t)(ox + dist);
+        const int16_t top2 = (int16_t)(oy - (dist >> 1)), bottom2 = (int16_t)(oy + (dist >> 1)), left2 = (int16_t)(ox - (dist >> 1)), right2 = (int16_t)(ox + (dist >> 1));
+        const int saved = s->bcost;
+        const int in = top >= s->miny && left >= s->minx && right <= s->maxx && bottom <= s->maxy;
+        pme_star_point(s, ox, top, in, top >= s->miny, 1, 2, dist, bPoint, bDist);
+        if (dist > 1)
+        {
+            pme_star_point(s, left2, top2, in, top2 >= s->miny, left2 >= s->minx, 1, dist >> 1, bPoint, bDist);
+            pme_star_point(s, right2, top2, in, top2 >= s->miny, right2 <= s->maxx, 3, dist >> 1, bPoint, bDist);
+        }
+        pme_star_point(s, left, oy, in, left >= s->minx, 1, 4, dist, bPoint, bDist);
+        pme_star_point(s, right, oy, in, right <= s->maxx, 1, 5, dist, bPoint, bDist);
+        if (dist > 1)
+        {
+            pme_star_point(s, left2, bottom2, in, bottom2 <= s->maxy, left2 >= s->minx, 6, dist >> 1, bPoint, bDist);
+            pme_star_point(s, right2, bottom2, in, bottom2 <= s->maxy, right2 <= s->maxx, 8, dist >> 1, bPoint, bDist);
+        }
+        pme_star_point(s, ox, bottom, in, bottom <= s->maxy, 1, 7, dist, bPoint, bDist);
+        if (s->bcost < saved) rounds = 0;
+        else if (++rounds >= earlyExitIters) return;
+    }
+    for (int16_t dist = 16; dist <= (int16_t)merange; dist <<= 1)
+    {
+        const int16_t top = (int16_t)(oy - dist), bottom = (int16_t)(oy + dist), left = (int16_t)(ox - dist), right = (int16_t)(ox + dist);
+        const int saved = s->bcost;
+        const int in = top >= s->miny && left >= s->minx && right <= s->maxx && bottom <= s->maxy;
+        pme_star_point(s, ox, top, in, top >= s->miny, 1, 0, dist, bPoint, bDist);
+        pme_star_point(s, left, oy, in, left >= s->minx, 1, 0, dist, bPoint, bDist);
+        pme_star_point(s, right, oy, in, right <= s->maxx, 1, 0, dist, bPoint, bDist);
+        pme_star_point(s, ox, bottom, in, bottom <= s->maxy, 1, 0, dist, bPoint, bDist);
+        for (int index = 1; index < 4; index++)
+        {
+            const int16_t yt = (int16_t)(top + (dist >> 2) * index), yb = (int16_t)(bottom - (dist >> 2) * index);
+            const int16_t xl = (int16_t)(ox - (dist >> 2) * index), xr = (int16_t)(ox + (dist >> 2) * index);
+            pme_star_point(s, xl, yt, in, yt >= s->miny, xl >= s->minx, 0, dist, bPoint, bDist);
+            pme_star_point(s, xr, yt, in, yt >= s->miny, xr <= s->maxx, 0, dist, bPoint, bDist);
+            pme_star_point(s, xl, yb, in, yb <= s->maxy, xl >= s->minx, 0, dist, bPoint, bDist);
+            pme_star_point(s, xr, yb, in, yb <= s->maxy, xr <= s->maxx, 0, dist, bPoint, bDist);
+        }
+        if (s->bcost < saved) rounds = 0;
+        else if (++rounds >= earlyExitIters) return;
+    }
+}
+static void pme_two_points(pme_state* s, int point)
+{
+    /* bmv moves when the first point wins: the second is relative to the vector the pair started from */
+    const int x0 = s->bx, y0 = s->by;
+    for (int k = 0; k < 2; k++)
+    {
+        const int x = (int16_t)(x0 + pme_two_point[(point - 1) * 2 + k][0]), y = (int16_t)(y0 + pme_two_point[(point - 1) * 2 + k][1]);
+        if (pme_in_range(s, x, y)) pme_try(s, x, y);
+    }
+}
+/* the raster scan of STAR (:971-1003, step 5, with its `<< 3` in the fourth vector's mvcost) and FULL (:1039-1071, step 1) */
+static void pme_raster(pme_state* s, int step, int fourthShift)
+{
+    for (int16_t ty = s->miny; ty <= s->maxy; ty += step)
+        for (int16_t tx = s->minx; tx <= s->maxx; tx += step)
+        {
+            if (tx + step * 3 <= s->maxx)
+            {
+                for (int k = 0; k < 4; k++)
+                {
+                    if (k) tx += step;
+                    const int sh = k == 3 ? fourthShift : 2;
+                    int c = ola_pu_sad(s->w, s->h, s->fenc, s->fs, s->fref + tx + (intptr_t)ty * s->rs, s->rs) + pme_mvcost(s, (int16_t)(tx << sh), (int16_t)(ty << sh));
+                    if (c < s->bcost) { s->bcost = c; s->bx = tx; s->by = ty; }
+                }
+            }
+            else
+                pme_try(s, tx, ty);
+        }
+}
+
+/* UMH before its final hexagon walk, :744-927; returns 0 when the pattern ended early (no walk), 1 when the HEX walk
+ * follows; *merange may come back widened (:789-833) */
+static int pme_umh(pme_state* s, int16_t pmx, int16_t pmy, int16_t qmvpx, int16_t qmvpy, int numCandidates, const int16_t* mvc, int* merangeIO, int is64)
+{
+    static const int8_t dia1[4][2] = { { 0, -1 }, { 0, 1 }, { -1, 0 }, { 1, 0 } };
+    static const int8_t octA[4][2] = { { 0, -2 }, { -1, -1 }, { 1, -1 }, { -2, 0 } }, octB[4][2] = { { 2, 0 }, { -1, 1 }, { 1, 1 }, { 0, 2 } };
+    static const int8_t ringA[4][2] = { { -1, -2 }, { 1, -2 }, { -2, -1 }, { 2, -1 } }, ringB[4][2] = { { -2, 1 }, { 2, 1 }, { -1, 2 }, { 1, 2 } };
+    static const int8_t corners[4][2] = { { -2, -2 }, { -2, 2 }, { 2, -2 }, { 2, 2 } };
+    static const uint8_t range_mul[4][4] = { { 3, 3, 4, 4 }, { 3, 4, 4, 4 }, { 4, 4, 4, 5 }, { 4, 4, 5, 6 } };
+    int merange = *merangeIO;
+    int crossStart = 1;
+    const int ucost1 = s->bcost;
+    pme_try_around(s, pmx, pmy, dia1, 4);
+    if (pmx | pmy) pme_try_around(s, 0, 0, dia1, 4);
+    const int ucost2 = s->bcost;
+    if ((s->bx | s->by) && !(s->bx == pmx && s->by == pmy)) pme_try_around(s, s->bx, s->by, dia1, 4);
+    if (s->bcost == ucost2) crossStart = 3;
+    int ox = s->bx, oy = s->by;
+#define ME_THRESH(v) (s->bcost < (((v) >> 4) * s->sizeScale))
+    if (s->bcost == ucost2 && ME_THRESH(2000))
+    {
+        pme_try_around(s, ox, oy, octA, 4);
+        pme_try_around(s, ox, oy, octB, 4);
+        if (s->bcost == ucost1 && ME_THRESH(500)) return 0;
+        if (s->bcost == ucost2)
+        {
+            const int16_t range = (int16_t)(merange >> 1) | 1;
+            pme_cross(s, ox, oy, 3, range, range);
+            pme_try_around(s, ox, oy, ringA, 4);
+            pme_try_around(s, ox, oy, ringB, 4);
+            if (s->bcost == ucost2) return 0;
+            crossStart = range + 2;
+        }
+    }
+    if (numCandidates)
+    {
+        int mvd, denom = 1;
+        if (numCandidates == 1)
+            mvd = is64 ? 25 : abs(qmvpx - mvc[0]) + abs(qmvpy - mvc[1]);
+        else
+        {
+            denom = numCandidates - 1;
+            mvd = 0;
+            if (!is64) { mvd = abs(qmvpx - mvc[0]) + abs(qmvpy - mvc[1]); denom++; }
+            for (int i = 0; i < numCandidates - 1; i++)
+                mvd += abs(mvc[2 * i] - mvc[2 * i + 2]) + abs(mvc[2 * i + 1] - mvc[2 * i + 3]);
+        }
+        const int sadCtx = ME_THRESH(1000) ? 0 : ME_THRESH(2000) ? 1 : ME_THRESH(4000) ? 2 : 3;
+        const int mvdCtx = mvd < 10 * denom ? 0 : mvd < 20 * denom ? 1 : mvd < 40 * denom ? 2 : 3;
+        merange = (merange * range_mul[mvdCtx][sadCtx]) >> 2;
+    }
+#undef ME_THRESH
+    /* still centred where the small patterns were (the reference's own FIXME) */
+    pme_cross(s, ox, oy, crossStart, merange, merange >> 1);
+    pme_try_around(s, ox, oy, corners, 4);
+    /* 16-point hexagon grid, scaled 1 .. merange / 4 */
+    ox = s->bx; oy = s->by;
+    uint16_t i = 1;
+    do
+    {
+        if (4 * i > imin(imin(s->maxx - ox, ox - s->minx), imin(s->maxy - oy, oy - s->miny)))
+        {
+            for (int j = 0; j < 16; j++)
+            {
+                const int16_t x = (int16_t)(ox + (int16_t)(pme_hex4[j][0] * (int16_t)i)), y = (int16_t)(oy + (int16_t)(pme_hex4[j][1] * (int16_t)i));
+                if (pme_in_range(s, x, y)) pme_try(s, x, y);
+            }
+        }
+        else
+        {
+            int won = -1;
+            for (int j = 0; j < 16; j++)
+            {
+                const int x = ox + pme_hex4[j][0] * i, y = oy + pme_hex4[j][1] * i;
+                /* ADD_MVCOST reads the table rows directly (no uint16 wrap of the sum; the sum of two entries is < 65536) */
+                int c = ola_pu_sad(s->w, s->h, s->fenc, s->fs, s->fref + x + (intptr_t)y * s->rs, s->rs) + s->lut[x * 4 - s->mvpx] + s->lut[y * 4 - s->mvpy];
+                if (c < s->bcost) { s->bcost = c; won = j; }
+            }
+            if (won >= 0) { s->bx = (int16_t)(ox + i * pme_hex4[won][0]); s->by = (int16_t)(oy + i * pme_hex4[won][1]); }
+        }
+    }
+    while (++i <= merange >> 2);
+    *merangeIO = merange;
+    return pme_in_range(s, s->bx, s->by);
+}
+
+/* searchMethod: 0 DIA, 1 HEX, 2 UMH, 3 STAR, 4 FULL (x265.h X265_*_SEARCH); subpelRefine 0..7.
+ * fencPlane + offset = the PU in the source (stride fencStride); refPlane + offset = the co-located block of the
+ * reference's fpelPlane[0] (stride refStride).  mvmin / mvmax in full-pel units, qmvp and mvc in quarter-pel units.
+ * Returns the cost, writes the quarter-pel vector. */
+int ola_motion_estimate_pu(int searchMethod, int subpelRefine, int w, int h, const pixel* fencPlane, intptr_t fencStride,
+                           const pixel* refPlane, intptr_t refStride, intptr_t offset, const uint16_t* mvcostCentre,
+                           const int16_t mvmin[2], const int16_t mvmax[2], const int16_t qmvp[2],
+                           int numCandidates, const int16_t* mvc, int merange, int16_t outQMv[2])
+{
+    static const struct { int hpelIters, hpelDirs, qpelIters, qpelDirs, hpelSatd; } workload[8] = {
+        { 1, 4, 0, 4, 0 }, { 1, 4, 1, 4, 0 }, { 1, 4, 1, 4, 1 }, { 2, 4, 1, 4, 1 }, { 2, 4, 2, 4, 1 }, { 1, 8, 1, 8, 1 }, { 2, 8, 1, 8, 1 }, { 2, 8, 2, 8, 1 } };
+    pme_state S, *s = &S;
+    s->w = w; s->h = h; s->sizeScale = (h * h) >> 4;
+    s->fenc = fencPlane + offset; s->fs = fencStride;
+    s->fref = refPlane + offset; s->rs = refStride;
+    s->lut = mvcostCentre;
+    s->mvpx = qmvp[0]; s->mvpy = qmvp[1];
+    s->minx = mvmin[0]; s->miny = mvmin[1]; s->maxx = mvmax[0]; s->maxy = mvmax[1];
+    const int16_t qminx = (int16_t)(mvmin[0] << 2), qminy = (int16_t)(mvmin[1] << 2), qmaxx = (int16_t)(mvmax[0] << 2), qmaxy = (int16_t)(mvmax[1] << 2);
+
+    /* the clipped predictor: SAD without mvcost (:597-603) */
+    int16_t pqx = qmvp[0] > qmaxx ? qmaxx : qmvp[0]; if (pqx < qminx) pqx = qminx;
+    int16_t pqy = qmvp[1] > qmaxy ? qmaxy : qmvp[1]; if (pqy < qminy) pqy = qminy;
+    int16_t bestPreX = pqx, bestPreY = pqy;
+    int bprecost = pme_subpel(s, pqx, pqy, 0);
+    const int16_t pmx = (int16_t)((pqx + 2) >> 2), pmy = (int16_t)((pqy + 2) >> 2);   /* pmv.roundToFPel() */
+    s->bx = pmx; s->by = pmy;
+    s->bcost = bprecost;
+    if ((pqx | pqy) & 3)
+        s->bcost = pme_fpel_cost(s, s->bx, s->by);
+    if (pqx | pqy)
+    {
+        int c = pme_fpel_cost(s, 0, 0);
+        if (c < s->bcost) { s->bcost = c; s->bx = s->by = 0; }
+    }
+    /* the other predictor candidates at quarter-pel precision (:627-641) */
+    for (int i = 0; i < numCandidates; i++)
+    {
+        int16_t mx = mvc[2 * i] > qmaxx ? qmaxx : mvc[2 * i]; if (mx < qminx) mx = qminx;
+        int16_t my = mvc[2 * i + 1] > qmaxy ? qmaxy : mvc[2 * i + 1]; if (my < qminy) my = qminy;
+        if ((mx | my) && !(mx == pqx && my == pqy) && !(mx == bestPreX && my == bestPreY))
+        {
+            int c = pme_subpel(s, mx, my, 0) + pme_mvcost(s, mx, my);
+            if (c < bprecost) { bprecost = c; bestPreX = mx; bestPreY = my; }
+        }
+    }
+
+    int walk = 0;
+    switch (searchMethod)
+    {
+    case 0:
+    {
+        /* diamond, radius 1, at most merange steps (:650-668); tags 1, 3, 4, 12 = up, down, left, right */
+        static const int8_t dia[4][2] = { { 0, -1 }, { 0, 1 }, { -1, 0 }, { 1, 0 } };
+        int i = merange;
+        do
+        {
+            int step = -1, best = s->bcost;
+            for (int k = 0; k < 4; k++)
+            {
+                int c = pme_fpel_cost(s, s->bx + dia[k][0], s->by + dia[k][1]);
+                if (c < best) { best = c; step = k; }
+            }
+            if (step < 0) break;
+            s->bcost = best;
+            s->bx += dia[step][0]; s->by += dia[step][1];
+        }
+        while (--i && pme_in_range(s, s->bx, s->by));
+        break;
+    }
+    case 1:
+        walk = 1;
+        break;
+    case 2:
+        walk = pme_umh(s, pmx, pmy, qmvp[0], qmvp[1], numCandidates, mvc, &merange, w == 64 && h == 64);
+        break;
+    case 3:
+    {
+        int bPoint = 0, bDist = 0;
+        pme_star_pattern(s, &bPoint, &bDist, 3, merange);
+        if (bDist == 1)
+        {
+            /* best distance 1: the two outer points next to the winning direction; stop if neither helps */
+            if (!bPoint) break;
+            const int saved = s->bcost;
+            pme_two_points(s, bPoint);
+            if (s->bcost == saved) break;
+        }
+        if (bDist > 5)
+            pme_raster(s, 5, 3);
+        while (bDist > 0)
+        {
+            bDist = 0; bPoint = 0;
+            pme_star_pattern(s, &bPoint, &bDist, 32, merange);
+            if (bDist == 1)
+            {
+                if (bPoint) pme_two_points(s, bPoint);
+                break;
+            }
+        }
+        break;
+    }
+    case 4:
+        pme_raster(s, 1, 2);
+        break;
+    default:
+        return -1;
+    }
+    if (walk) pme_hex(s, merange);
+
+    int16_t qx, qy; int bcost;
+    if (bprecost < s->bcost) { qx = bestPreX; qy = bestPreY; bcost = bprecost; }
+    else { qx = (int16_t)(s->bx << 2); qy = (int16_t)(s->by << 2); bcost = s->bcost; }
+
+    if (!bcost)
+        bcost = pme_mvcost(s, qx, qy);                      /* zero residual: no sub-pel, but the vector's bits count (:1085-1090) */
+    else
+    {
+        const int hs = workload[subpelRefine].hpelSatd;
+        if (hs) bcost = pme_subpel(s, qx, qy, 1) + pme_mvcost(s, qx, qy);
+        for (int pass = 0; pass < 2; pass++)
+        {
+            /* pass 0: half-pel steps with SAD or SATD; pass 1: quarter-pel steps with SATD */
+            const int iters = pass ? workload[subpelRefine].qpelIters : workload[subpelRefine].hpelIters;
+            const int dirs = pass ? workload[subpelRefine].qpelDirs : workload[subpelRefine].hpelDirs;
+            const int mul = pass ? 1 : 2, satd = pass ? 1 : hs;
+            if (pass && !hs) bcost = pme_subpel(s, qx, qy, 1) + pme_mvcost(s, qx, qy);
+            for (int it = 0; it < iters; it++)
+            {
+                int bdir = 0;
+                for (int i = 1; i <= dirs; i++)
+                {
+                    const int16_t cx = (int16_t)(qx + pme_square1[i][0] * mul), cy = (int16_t)(qy + pme_square1[i][1] * mul);
+                    int c = pme_subpel(s, cx, cy, satd) + pme_mvcost(s, cx, cy);
+                    if (c < bcost) { bcost = c; bdir = i; }
+                }
+                if (!bdir) break;
+                qx = (int16_t)(qx + pme_square1[bdir][0] * mul); qy = (int16_t)(qy + pme_square1[bdir][1] * mul);
+            }
+        }
+    }
+    outQMv[0] = qx; outQMv[1] = qy;
+    return bcost;
+}
+
+/* n searches of one PU shape: items as in include/x265cu.h's x265cu_me_item (same layout) */
+void ola_motion_estimate_batch(int searchMethod, int subpelRefine, int w, int h, const pixel* fencPlane, intptr_t fencStride,
+                               const pixel* refPlane, intptr_t refStride, const uint16_t* mvcostCentre, int n, const ola_me_item* items, ola_me_result* out)
+{
+    for (int i = 0; i < n; i++)
+    {
+        const ola_me_item* it = &items[i];
+        out[i].cost = ola_motion_estimate_pu(searchMethod, subpelRefine, w, h, fencPlane, fencStride, refPlane, refStride, (intptr_t)it->offset, mvcostCentre,
+                                             it->mvmin, it->mvmax, it->qmvp, it->numCandidates, &it->mvc[0][0], it->merange, out[i].mv);
+    }
+}

@@ -148,10 +148,29 @@ void ola_estimate_cu_propagate(ola_frame* fenc, ola_frame* ref0, ola_frame* ref1
                                double averageDuration, int fpsNum, int fpsDenom, int weightedBiPred);
 void ola_cutree_finish(ola_frame* f, double averageDuration, int fpsNum, int fpsDenom, int ref0Distance, double cuTreeStrength);
 
-/* full-resolution PU primitives (oracle side only so far): pu[LUMA_WxH].sad / .satd for the 25 luma PU
+/* full-resolution PU primitives: pu[LUMA_WxH].sad / .satd for the 25 luma PU
  * shapes (pixel.cpp:39-118, 192-242, 954-1004) */
 int ola_pu_sad(int w, int h, const pixel* a, intptr_t sa, const pixel* b, intptr_t sb);
 int ola_pu_satd(int w, int h, const pixel* a, intptr_t sa, const pixel* b, intptr_t sb);
+
+/* full-resolution motion search of one PU (motion.cpp:571-1172, isLowres == false): searchMethod 0 DIA / 1 HEX / 2 UMH /
+ * 3 STAR / 4 FULL, subpelRefine 0..7; vectors: mvmin / mvmax full-pel, qmvp / mvc / result quarter-pel.  mvcostCentre is the
+ * centre of a BitCost table of any QP: an input (the host builds it, as for the lookahead) */
+typedef struct ola_me_item
+{
+    int64_t offset;               /* setSourcePU's offset = blockOffset, in samples, into both planes */
+    int16_t mvmin[2], mvmax[2];
+    int16_t qmvp[2];
+    int16_t numCandidates, merange;
+    int16_t mvc[12][2];
+} ola_me_item;
+typedef struct ola_me_result { int16_t mv[2]; int32_t cost; } ola_me_result;
+int ola_motion_estimate_pu(int searchMethod, int subpelRefine, int w, int h, const pixel* fencPlane, intptr_t fencStride,
+                           const pixel* refPlane, intptr_t refStride, intptr_t offset, const uint16_t* mvcostCentre,
+                           const int16_t mvmin[2], const int16_t mvmax[2], const int16_t qmvp[2],
+                           int numCandidates, const int16_t* mvc, int merange, int16_t outQMv[2]);
+void ola_motion_estimate_batch(int searchMethod, int subpelRefine, int w, int h, const pixel* fencPlane, intptr_t fencStride,
+                               const pixel* refPlane, intptr_t refStride, const uint16_t* mvcostCentre, int n, const ola_me_item* items, ola_me_result* out);
 
 /* helpers for tests */
 void ola_lowres_mc(pixel* const planes[4], intptr_t stride, intptr_t blockOffset, int qx, int qy, pixel* blk);

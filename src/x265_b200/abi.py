@@ -70,7 +70,7 @@ class CutreeOp(C.Structure):
 # every symbol include/x265cu.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = (
     "x265cu_abi_version", "x265cu_device_count", "x265cu_open", "x265cu_close", "x265cu_last_error",
-    "x265cu_get_geometry", "x265cu_sync", "x265cu_host_register", "x265cu_host_unregister", "x265cu_trim", "x265cu_wp_prepare", "x265cu_wp_cost", "x265cu_pixelcmp_pu",
+    "x265cu_get_geometry", "x265cu_sync", "x265cu_host_register", "x265cu_host_unregister", "x265cu_trim", "x265cu_wp_prepare", "x265cu_wp_cost", "x265cu_pixelcmp_pu", "x265cu_motion_estimate",
     "x265cu_frame_init", "x265cu_frame_set_invqscale", "x265cu_frame_var", "x265cu_frame_init_var", "x265cu_frame_init_var_batch",
     "x265cu_intra", "x265cu_intra_batch", "x265cu_pre_lookahead_batch", "x265cu_frame_upload",
     "x265cu_weight_cost_batch", "x265cu_estimate_batch", "x265cu_pixelcmp_batch", "x265cu_pixelcmp_frames", "x265cu_pixelcmp_planes", "x265cu_int_peak",

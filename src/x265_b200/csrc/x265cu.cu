@@ -2335,6 +2335,83 @@ int x265cu_pixelcmp_pu(x265cu_ctx* c, int kind, int width, int height, const voi
     return syncStream(c);
 }
 
+/* full-resolution PU motion search (x265cu_me.cuh): n searches of one PU shape, a warp each */
+int x265cu_motion_estimate(x265cu_ctx* c, int searchMethod, int subpelRefine, int width, int height,
+                           const void* fencPlane, size_t fencSamples, intptr_t fencStride,
+                           const void* refPlane, size_t refSamples, intptr_t refStride, const uint16_t* mvcostCentre,
+                           int n, const x265cu_me_item* items, x265cu_me_result* out, float* ms)
+{
+    if (!c || searchMethod < 0 || searchMethod > 4 || subpelRefine < 0 || subpelRefine > 7 || !fencPlane || !refPlane || !mvcostCentre ||
+        n < 0 || (n && (!items || !out)))
+        return c ? fail(c, X265CU_EINVAL, "x265cu_motion_estimate: bad argument") : X265CU_EINVAL;
+    {
+        static const unsigned char shapes[24][2] = { { 8, 8 }, { 16, 16 }, { 32, 32 }, { 64, 64 }, { 8, 4 }, { 4, 8 }, { 16, 8 }, { 8, 16 }, { 32, 16 },
+            { 16, 32 }, { 64, 32 }, { 32, 64 }, { 16, 12 }, { 12, 16 }, { 16, 4 }, { 4, 16 }, { 32, 24 }, { 24, 32 }, { 32, 8 }, { 8, 32 }, { 64, 48 }, { 48, 64 },
+            { 64, 16 }, { 16, 64 } };
+        bool known = false;
+        for (int i = 0; i < 24; i++) known = known || (shapes[i][0] == width && shapes[i][1] == height);
+        if (!known) return fail(c, X265CU_EINVAL, "x265cu_motion_estimate: not an inter PU shape (4x4 is not one: motion.cpp:168)");
+    }
+    if (ms) *ms = 0.f;
+    if (!n) return X265CU_OK;
+    if (fencStride < width || refStride < width) return fail(c, X265CU_EINVAL, "x265cu_motion_estimate: stride smaller than the block");
+    for (int i = 0; i < n; i++)
+    {
+        const x265cu_me_item& it = items[i];
+        if (it.numCandidates < 0 || it.numCandidates > 12 || it.merange < 1 || it.merange > 1024 || it.mvmin[0] > it.mvmax[0] || it.mvmin[1] > it.mvmax[1] ||
+            it.mvmin[0] < -8000 || it.mvmin[1] < -8000 || it.mvmax[0] > 8000 || it.mvmax[1] > 8000)
+            return fail(c, X265CU_EINVAL, "x265cu_motion_estimate: bad item (candidates 0..12, merange 1..1024, mvmin <= mvmax, |mv| <= 8000)");
+        const int64_t lo = it.offset + (int64_t)(it.mvmin[1] - 16) * refStride + it.mvmin[0] - 16;
+        const int64_t hi = it.offset + (int64_t)(it.mvmax[1] + 16 + height - 1) * refStride + it.mvmax[0] + 16 + width;
+        if (it.offset < 0 || lo < 0 || (uint64_t)hi > refSamples || (uint64_t)(it.offset + (int64_t)(height - 1) * fencStride + width) > fencSamples)
+            return fail(c, X265CU_EINVAL, "x265cu_motion_estimate: a search window (+16 samples) leaves the reference plane, or a PU its source plane");
+    }
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CU_TRY(c, cudaSetDevice(c->cfg.device));
+    const size_t bytesA = alignUp(fencSamples * c->pb + 16, 256), bytesB = alignUp(refSamples * c->pb + 16, 256);
+    const size_t lutBytes = alignUp((size_t)131073 * 2, 256), itemBytes = alignUp((size_t)n * sizeof(x265cu_me_item), 256);
+    const size_t need = bytesA + bytesB + lutBytes + itemBytes + alignUp((size_t)n * sizeof(x265cu_me_result), 256);
+    if (growDevice(c, &c->dGeneric, &c->dGenericCap, need)) return X265CU_ECUDA;
+    uint8_t* dA = c->dGeneric; uint8_t* dB = dA + bytesA;
+    uint16_t* dLut = (uint16_t*)(dB + bytesB);
+    MeItemDev* dItems = (MeItemDev*)((uint8_t*)dLut + lutBytes);
+    MeResultDev* dOut = (MeResultDev*)((uint8_t*)dItems + itemBytes);
+    static_assert(sizeof(MeItemDev) == sizeof(x265cu_me_item) && sizeof(MeResultDev) == sizeof(x265cu_me_result), "item layout");
+    CU_TRY(c, cudaMemcpyAsync(dA, fencPlane, fencSamples * c->pb, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(dB, refPlane, refSamples * c->pb, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemsetAsync(dB + refSamples * c->pb, 0, bytesB - refSamples * c->pb, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(dLut, mvcostCentre - 65536, (size_t)131073 * 2, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(dItems, items, (size_t)n * sizeof(x265cu_me_item), cudaMemcpyHostToDevice, c->stream));
+    const int warps = 4;
+    const size_t blockBytes = (size_t)width * height * c->pb;
+    const size_t perWarp = 2 * blockBytes + alignUp((size_t)(height + 7) * width * 2, 16) + 16 * sizeof(MePt) + 16 * sizeof(int);
+    const size_t smem = warps * perWarp;
+    cudaEvent_t e0 = getEvent(c), e1 = getEvent(c);
+    c->stats.launches[X265CU_K_PIXEL]++;
+    const int blocks = (n + warps - 1) / warps;
+    if (c->pb == 1)
+    {
+        CU_TRY(c, cudaFuncSetAttribute(pu_motion_search_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU_TRY(c, cudaEventRecord(e0, c->stream));
+        pu_motion_search_kernel<uint8_t><<<blocks, warps * 32, smem, c->stream>>>(searchMethod, subpelRefine, width, height, c->cfg.bitDepth, (const uint8_t*)dA, fencStride,
+                                                                                 (const uint8_t*)dB, refStride, dLut + 65536, n, dItems, dOut);
+    }
+    else
+    {
+        CU_TRY(c, cudaFuncSetAttribute(pu_motion_search_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU_TRY(c, cudaEventRecord(e0, c->stream));
+        pu_motion_search_kernel<uint16_t><<<blocks, warps * 32, smem, c->stream>>>(searchMethod, subpelRefine, width, height, c->cfg.bitDepth, (const uint16_t*)dA, fencStride,
+                                                                                  (const uint16_t*)dB, refStride, dLut + 65536, n, dItems, dOut);
+    }
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaEventRecord(e1, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(out, dOut, (size_t)n * sizeof(x265cu_me_result), cudaMemcpyDeviceToHost, c->stream));
+    int rc = syncStream(c);
+    if (rc) return rc;
+    if (ms) CU_TRY(c, cudaEventElapsedTime(ms, e0, e1));
+    return X265CU_OK;
+}
+
 int x265cu_pixelcmp_frames(x265cu_ctx* c, int kind, int nPairs, const int* slotsA, const int* slotsB, int32_t* out, float* ms)
 {
     return x265cu_pixelcmp_planes(c, kind, nPairs, slotsA, NULL, slotsB, NULL, out, ms);

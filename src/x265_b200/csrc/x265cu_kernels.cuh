@@ -189,6 +189,7 @@ struct JobDev
 #include "x265cu_search_plain.cuh"
 #include "x265cu_search_oct.cuh"
 #include "x265cu_wp.cuh"
+#include "x265cu_me.cuh"
 
 /* cost-only estimates (both bDoSearch false): every CU is independent.  grid = (hCU, jobs);
  * a block owns one CU row of one job, so rowSatds needs no atomics. */

@@ -285,3 +285,84 @@ def test_wp_cost(depth):
             a = O.ola_wp_cost(pf, pr, tmp.ctypes.data, stride, w, h, ic, wt, s, d, o)
             b = R.x265ref_wp_cost(pf, pr, tmp.ctypes.data, stride, w, h, ic, wt, s, d, o)
             assert a == b, (luma, wt, s, d, o)
+
+
+# ---- full-resolution PU motion search (encoder/motion.cpp:571-1172, every pattern and sub-pel level) ----
+from harness import me_cases as mc
+
+
+def _me_libs(depth):
+    O, R = po.oracle(depth), po.ref(depth)
+    V, I, S = C.c_void_p, C.c_int, C.c_ssize_t
+    O.ola_motion_estimate_batch.argtypes = [I, I, I, I, V, S, V, S, V, I, V, V]
+    O.ola_motion_estimate_batch.restype = None
+    R.x265ref_motion_estimate_batch.argtypes = [I, I, I, I, I, V, S, V, S, I, V, V, V]
+    R.x265ref_motion_estimate_batch.restype = None
+    R.x265ref_mvcost_table_qp.argtypes = [I, V]
+    return O, R
+
+
+def _me_compare(depth, method, subme, w, h, n, seed, qp=30, W=160, H=128, **kw):
+    O, R = _me_libs(depth)
+    fenc, ref, stride, _ = mc.planes(depth, W, H, seed)
+    its = mc.items(W, H, w, h, n, seed + 1, **kw)
+    lut = np.zeros(131073, np.uint16)
+    R.x265ref_mvcost_table_qp(qp, ptr(lut))
+    want = (mc.MeResult * n)(); got = (mc.MeResult * n)()
+    R.x265ref_motion_estimate_batch(method, subme, qp, w, h, ptr(fenc), stride, ptr(ref), stride, n, C.addressof(its), C.addressof(want), None)
+    O.ola_motion_estimate_batch(method, subme, w, h, ptr(fenc), stride, ptr(ref), stride, ptr(lut, 65536), n, C.addressof(its), C.addressof(got))
+    a, b = mc.results_list(want, n), mc.results_list(got, n)
+    bad = [i for i in range(n) if a[i] != b[i]]
+    assert not bad, (depth, method, subme, w, h, bad[:5], [(a[i], b[i]) for i in bad[:3]])
+    return a
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+@pytest.mark.parametrize("method", ["dia", "hex", "umh", "star", "full"])
+def test_motion_estimate_patterns(depth, method):
+    """every integer pattern x every sub-pel level on 16x16 and 8x8 PUs, windows that cut the patterns included"""
+    m = mc.METHODS[method]
+    moved = 0
+    for subme in range(8):
+        for (w, h) in ((16, 16), (8, 8)):
+            n = 12 if method == "full" else 60
+            kw = dict(merange_choices=(4, 9)) if method == "full" else {}
+            res = _me_compare(depth, m, subme, w, h, n, 100 + subme * 7 + w, **kw)
+            moved += sum(1 for r in res if (r[0], r[1]) != (0, 0))
+    assert moved > 50
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_motion_estimate_all_shapes(depth):
+    """the 25 luma PU shapes (4x4 is not a legal inter PU: skipped, motion.cpp:168) with STAR and UMH at the default sub-pel level 2 and at 5"""
+    for (w, h) in mc.PU_SHAPES:
+        if (w, h) == (4, 4):
+            continue
+        for method in ("star", "umh", "hex"):
+            for subme in (2, 5):
+                _me_compare(depth, mc.METHODS[method], subme, w, h, 16, 300 + w * 3 + h, W=192, H=160)
+
+
+@pytest.mark.parametrize("depth", DEPTHS)
+def test_motion_estimate_far_motion(depth):
+    """a reference moved by (37, -22) with predictors at zero: long walks, the 16-point grid of UMH, STAR's raster refinement"""
+    O, R = _me_libs(depth)
+    for method in ("star", "umh", "hex", "dia"):
+        for (w, h) in ((16, 16), (32, 32)):
+            fenc, ref, stride, _ = mc.planes(depth, 256, 192, 77, motion=(31, -22), noise=2)
+            its = mc.items(256, 192, w, h, 40, 78, merange_choices=(32, 57), tight=0.1)
+            for i in range(40):
+                if i % 2 == 0:
+                    its[i].qmvp[0] = its[i].qmvp[1] = 0
+                    its[i].mvmin[0], its[i].mvmin[1], its[i].mvmax[0], its[i].mvmax[1] = -24, -24, 24, 24
+                    its[i].offset = mc.MARGIN * stride + mc.MARGIN + (64 + (i % 5) * 8) * stride + 96 + (i % 7) * 8
+                    its[i].mvmin[0] = -57; its[i].mvmin[1] = -57; its[i].mvmax[0] = 57; its[i].mvmax[1] = 57
+            lut = np.zeros(131073, np.uint16)
+            R.x265ref_mvcost_table_qp(26, ptr(lut))
+            want = (mc.MeResult * 40)(); got = (mc.MeResult * 40)()
+            R.x265ref_motion_estimate_batch(mc.METHODS[method], 3, 26, w, h, ptr(fenc), stride, ptr(ref), stride, 40, C.addressof(its), C.addressof(want), None)
+            O.ola_motion_estimate_batch(mc.METHODS[method], 3, w, h, ptr(fenc), stride, ptr(ref), stride, ptr(lut, 65536), 40, C.addressof(its), C.addressof(got))
+            assert mc.results_list(want, 40) == mc.results_list(got, 40), (method, w, h)
+            if method in ("star", "umh"):
+                far = sum(1 for r in mc.results_list(want, 40) if abs(r[0]) > 80)
+                assert far >= 10, (method, far)
