@@ -326,6 +326,7 @@ extern "C" void x265glue_open(xr::Lookahead* la)
     q.forceCoopSlices = la->m_numCoopSlices; q.forceRowsPerSlice = la->m_numRowsPerSlice;   /* slicetype.cpp:534-558, as computed there */
     q.bEnableWeightedPred = p->bEnableWeightedPred;
     q.bEnableWeightedBiPred = p->bEnableWeightedBiPred;
+    q.bBPyramid = p->bBPyramid;
     q.aqMode = p->rc.aqMode; q.aqStrength = p->rc.aqStrength;
     q.bFrameBias = p->bFrameBias;
     q.device = getenv("X265CU_DEVICE") ? atoi(getenv("X265CU_DEVICE")) : 0;

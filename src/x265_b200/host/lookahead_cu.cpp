@@ -79,12 +79,13 @@ void Lookahead::mvcostTable(int bitDepth, uint16_t* out, int* lambdaInt)
     }
 }
 
-Lookahead::Lookahead() : m_ctx(NULL), m_mvcost(NULL), m_lambda(1), m_resident(false), m_lookAhead(true), m_versionCounter(0), m_newestReady(0), m_episodeNewest(0)
+Lookahead::Lookahead() : m_ctx(NULL), m_mvcost(NULL), m_lambda(1), m_resident(false), m_lookAhead(true), m_versionCounter(0), m_newestReady(0), m_episodeNewest(0), m_trellisAhead(true), m_batchFirst(-1), m_batchLast(-1)
 {
     m_error[0] = 0;
     memset(&m_param, 0, sizeof(m_param));
     memset(m_specStats, 0, sizeof(m_specStats));
     if (const char* e = getenv("X265CU_LOOKAHEAD_CACHE")) m_lookAhead = atoi(e) != 0;
+    if (const char* e = getenv("X265CU_TRELLIS_AHEAD")) m_trellisAhead = atoi(e) != 0;
 }
 Lookahead::~Lookahead() { destroy(); }
 
@@ -628,6 +629,59 @@ void CostEstimateGroup::predictFrom(const std::vector<Lookahead::Request>& ep, s
     }
 }
 
+/* Rule-based part of the look-ahead cache, for requests the history cannot foresee (the first slicetypeDecide of a stream,
+ * a new kind of request).  The non-batch estimates of a b-adapt 2 analysis are those of the trellis: slicetypePath
+ * (slicetype.cpp:1565-1592) tries, for every path length N, the suffixes "P", "BP", "BBP", ... and slicetypePathCost
+ * (:1594-1639) asks for the P estimate of the last segment (N - d -> N) and for its B estimates (b-pyramid: the middle frame
+ * between the two P frames, then the two halves).  The batches of slicetypeAnalyse (:1231-1297) only cover b >= 2 and L1
+ * searches at the distance of an L0 search, below the last frame: what is left are the estimates next to the first frame of
+ * the analysis and every segment that ends at its LAST frame -- 13 (bframes 4) to 27 (bframes 8) one-by-one requests in the first
+ * decision of a stream.  They are listed here in the trellis's own order (the first estimate to find a field's sentinel
+ * searches it, and the vectors of a field depend on the kind of estimate that did, :2146-2160) and ride in the launch of the
+ * request that was not foreseen.  Nothing here can change a result: an entry is handed out only to exactly the request it
+ * computed (takeAhead); a wrong guess is dropped at the next batch. */
+void CostEstimateGroup::predictTrellis(const Lookahead::Request& rq, Lowres* skipFenc, int skipD0, int skipD1, const std::vector<EstReq>& already,
+                                       std::vector<EstReq>& out)
+{
+    Lookahead& la = m_lookahead;
+    const int maxD = la.m_param.bframes + 1;
+    int first = rq.p0, last = rq.p1;
+    if (la.m_batchFirst >= 0 && la.m_batchFirst <= rq.p0 && rq.p0 - la.m_batchFirst <= la.m_param.lookaheadDepth + maxD) first = la.m_batchFirst;
+    if (la.m_batchLast >= 0 && la.m_batchLast + 1 > last && la.m_batchLast + 1 - rq.p1 <= la.m_param.lookaheadDepth + maxD) last = la.m_batchLast + 1;
+    std::vector<Lookahead::Request> ep;
+    for (int N = first + 1; N <= last; N++)
+    {
+        if (la.m_byPoc.find(N) == la.m_byPoc.end()) break;          /* a stream's frames arrive in order */
+        for (int d = 1; d <= maxD && N - d >= first; d++)
+        {
+            const int c = N - d;
+            if (la.m_byPoc.find(c) == la.m_byPoc.end()) break;
+            bool all = true;
+            for (int b = c + 1; b < N; b++) all = all && la.m_byPoc.find(b) != la.m_byPoc.end();
+            if (!all) break;
+            Lookahead::Request q = { c, N, N };
+            ep.push_back(q);
+            if (la.m_param.bBPyramid && d > 2)
+            {
+                const int middle = c + d / 2;
+                Lookahead::Request m = { c, middle, N };
+                ep.push_back(m);
+                for (int b = c + 1; b < middle; b++) { Lookahead::Request r = { c, b, middle }; ep.push_back(r); }
+                for (int b = middle + 1; b < N; b++) { Lookahead::Request r = { middle, b, N }; ep.push_back(r); }
+            }
+            else
+                for (int b = c + 1; b < N; b++) { Lookahead::Request r = { c, b, N }; ep.push_back(r); }
+        }
+    }
+    bool valid = true;
+    std::vector<EstReq> more;
+    predictFrom(ep, 0, 0, skipFenc, skipD0, skipD1, already, more, valid);
+    if (!valid) return;
+    const size_t room = already.size() < 192 ? 192 - already.size() : 0;   /* bounds the side buffers of one call */
+    if (more.size() > room) more.resize(room);
+    out.swap(more);
+}
+
 bool CostEstimateGroup::finishBatch()
 {
     Lookahead& la = m_lookahead;
@@ -637,6 +691,9 @@ bool CostEstimateGroup::finishBatch()
         const Estimate& e = m_estimates[i];
         EstReq r = { m_frames[e.b], m_frames[e.p0], m_frames[e.p1], e.b - e.p0, e.p1 - e.b, false, false };
         reqs[i] = r;
+        const int lo = m_frames[e.p0]->frameNum, hi = m_frames[e.p1]->frameNum;
+        if (i == 0 || lo < la.m_batchFirst) la.m_batchFirst = lo;
+        if (i == 0 || hi > la.m_batchLast) la.m_batchLast = hi;
     }
     if (m_jobTotal && !la.m_episode.empty())
     {
@@ -763,6 +820,12 @@ int64_t CostEstimateGroup::singleCost(int p0, int p1, int b, bool intraPenalty)
                     }
                 }
                 reqs.insert(reqs.end(), best.begin(), best.end());
+                if (la.m_trellisAhead)
+                {
+                    std::vector<EstReq> more;
+                    predictTrellis(rq, fenc, d0, d1, reqs, more);
+                    reqs.insert(reqs.end(), more.begin(), more.end());
+                }
             }
             if (getenv("X265CU_LOOKAHEAD_DEBUG"))
                 fprintf(stderr, "singleCost (%d,%d,%d): on demand, %d ahead, episode %d prev %d\n", rq.p0, rq.b, rq.p1, (int)reqs.size() - 1, (int)la.m_episode.size(), (int)la.m_history.size());
@@ -1200,6 +1263,7 @@ void* x265cuh_open(const x265cuh_params* p, char* err, int errLen)
     q.sourceWidth = p->sourceWidth; q.sourceHeight = p->sourceHeight; q.bitDepth = p->bitDepth; q.maxCUSize = p->maxCUSize;
     q.bframes = p->bframes; q.lookaheadDepth = p->lookaheadDepth; q.lookaheadSlices = p->lookaheadSlices; q.poolWorkers = p->poolWorkers;
     q.fpsNum = p->fpsNum; q.fpsDenom = p->fpsDenom; q.qCompress = p->qCompress; q.bEnableWeightedBiPred = p->bEnableWeightedBiPred;
+    q.bBPyramid = 1;         /* x265's default; the flat view is only driven with traces of default-pyramid runs (a hint, see Param) */
     q.bEnableWeightedPred = p->bEnableWeightedPred; q.aqMode = p->aqMode; q.aqStrength = p->aqStrength;
     q.bFrameBias = p->bFrameBias; q.device = p->device; q.frameSlots = p->frameSlots;
     q.stream = p->stream; q.searchWarps = p->searchWarps;

@@ -59,6 +59,7 @@ struct Param
     /* cooperative-slice geometry as the host computed it (Lookahead::Lookahead, slicetype.cpp:534-558); 0 = derive it here
      * from lookaheadSlices / poolWorkers / sourceHeight */
     int forceCoopSlices, forceRowsPerSlice;
+    int bBPyramid;           /* x265_param::bBPyramid: only a hint for which estimates to compute ahead, never changes a result */
 };
 
 struct WeightParam { int present, scale, denom, offset; };
@@ -150,6 +151,8 @@ public:
     std::vector<std::vector<Request> > m_history;   /* ... and the runs before it (most recent last) */
     std::vector<int> m_historyNewest;          /* how many frames had gone through preLookahead() when each of those runs began */
     int m_newestReady, m_episodeNewest;        /* ... now / when the current run began (a stream's frames arrive in order) */
+    bool m_trellisAhead;                       /* X265CU_TRELLIS_AHEAD=0 turns the rule-based part of the cache off (experiments) */
+    int m_batchFirst, m_batchLast;             /* frameNum range of the most recent batch (-1: none yet) */
     uint64_t m_versionCounter;
     int64_t m_specStats[4];                    /* launched ahead, handed out, requests computed alone, requests total */
 
@@ -227,6 +230,7 @@ protected:
     bool runEstimates(const EstReq* e, int n);
     void predictFrom(const std::vector<Lookahead::Request>& ep, size_t first, int shift, Lowres* skipFenc, int skipD0, int skipD1,
                      const std::vector<EstReq>& already, std::vector<EstReq>& out, bool& valid);
+    void predictTrellis(const Lookahead::Request& rq, Lowres* skipFenc, int skipD0, int skipD1, const std::vector<EstReq>& already, std::vector<EstReq>& out);
     bool takeAhead(Lowres* fenc, Lowres* ref0, Lowres* ref1, int d0, int d1);
 };
 
