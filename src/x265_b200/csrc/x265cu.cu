@@ -789,8 +789,8 @@ static int frameInitEnqueue(x265cu_ctx* c, int slot, const void* luma, intptr_t 
     std::fill(c->mvValid.begin() + (size_t)slot * 2 * (c->bf + 1), c->mvValid.begin() + (size_t)(slot + 1) * 2 * (c->bf + 1), 0);
     {
         KernelScope ks(c, X265CU_K_LOWRES);
-        const int padW = g.width + 2 * g.marginX;
-        dim3 grid((padW / 4 + 255) / 256, g.paddedLines);
+        const int padW = g.width + 2 * g.marginX, unit = 16 / c->pb;
+        dim3 grid((unsigned)(((int64_t)((padW + unit - 1) / unit) * g.paddedLines + 255) / 256));
         if (c->pb == 1)
             lowres_init_kernel<uint8_t><<<grid, 256, 0, c->stream>>>((const uint8_t*)src, pitch, (uint8_t*)slotBuffer(c, slot), g);
         else
@@ -1076,8 +1076,8 @@ static int preBatchImpl2(x265cu_ctx* c, int n, const x265cu_frame_in* items, x26
         }
         {
             KernelScope ks(c, X265CU_K_LOWRES);
-            const int padW = g.width + 2 * g.marginX;
-            dim3 grid((padW / 4 + 255) / 256, g.paddedLines, count);
+            const int padW = g.width + 2 * g.marginX, unit = 16 / c->pb;
+            dim3 grid((unsigned)(((int64_t)((padW + unit - 1) / unit) * g.paddedLines + 255) / 256), 1, count);
             if (c->pb == 1) lowres_init_batch_kernel<uint8_t><<<grid, 256, 0, c->stream>>>(lb, g);
             else lowres_init_batch_kernel<uint16_t><<<grid, 256, 0, c->stream>>>(lb, g);
         }

@@ -5,7 +5,9 @@
  * common/intrapred.cpp:31-51) live in shared memory.  As in the search kernel a quad measures one
  * candidate (here: one prediction mode) and each lane its 4x4 sub-block:
  *   pass 1: DC, planar, angular 5,10,...,30   (8 modes = 8 quads)
- *   pass 2: best-2 / best+2                   pass 3: best-1 / best+1
+ *   pass 2: the six modes the two refinement rounds (best-2 / best+2, then -1 / +1 around the winner of that,
+ *           slicetype.cpp:292-310) can ask for: best-3 .. best+3 without best; the two rounds are then decided on the
+ *           measured costs in the reference's order (strict <, minus before plus)
  * Angular prediction (intra_pred_ang_c<8>, intrapred.cpp:102-204) is done in its "vertical" form
  * for every mode: horizontal modes swap the roles of the top and left neighbours and produce the
  * transposed block; since a 4x4 Hadamard abs-sum is invariant under transposition, the lane just
@@ -94,16 +96,17 @@ __device__ __forceinline__ void intra_body(const P* __restrict__ plane0, const G
 
     int icost = LA_COST_MAX, ilow = 0, acost = LA_COST_MAX, alow = 4;
 #pragma unroll 1
-    for (int pass = 0; pass < 3; pass++)
+    for (int pass = 0; pass < 2; pass++)
     {
         int mode, valid = 1;
         if (pass == 0)
             mode = q == 0 ? 1 : (q == 1 ? 0 : 5 * (q - 1));          /* DC, planar, 5,10,...,30 */
         else
         {
-            const int dist = pass == 1 ? 2 : 1;
-            mode = q == 0 ? alow - dist : alow + dist;
-            valid = q < 2;
+            /* quads 0..5: alow -2, +2, -3, -1, +1, +3 (alow is one of 5,...,30: all within 2..33) */
+            const int off = q == 0 ? -2 : q == 1 ? 2 : q == 2 ? -3 : q == 3 ? -1 : q == 4 ? 1 : 3;
+            mode = alow + off;
+            valid = q < 6;
             if (!valid) mode = 10;
         }
         int d[4][4];
@@ -201,10 +204,14 @@ __device__ __forceinline__ void intra_body(const P* __restrict__ plane0, const G
         }
         else
         {
-            const int dist = pass == 1 ? 2 : 1;
-            const int minusmode = alow - dist, plusmode = alow + dist;
-            if (c[0] < acost) { acost = c[0]; alow = minusmode; }
-            if (c[1] < acost) { acost = c[1]; alow = plusmode; }
+            const int a = alow;
+            if (c[0] < acost) { acost = c[0]; alow = a - 2; }
+            if (c[1] < acost) { acost = c[1]; alow = a + 2; }
+            const int a2 = alow;
+            const int cm = a2 < a ? c[2] : (a2 == a ? c[3] : c[4]);     /* cost of a2 - 1 */
+            const int cp = a2 < a ? c[3] : (a2 == a ? c[4] : c[5]);     /* cost of a2 + 1 */
+            if (cm < acost) { acost = cm; alow = a2 - 1; }
+            if (cp < acost) { acost = cp; alow = a2 + 1; }
         }
     }
     if (acost < icost) { icost = acost; ilow = alow; }

@@ -67,7 +67,7 @@ struct GeomDev
 };
 
 /* ===========================================================================================
- * lowres_init: one thread = 4 consecutive samples of one padded output row, all four planes.
+ * lowres_init: one thread = 16 bytes of one padded output row of each of the four planes.
  * Rows/columns in the margins recompute the clamped source position, so the border replication
  * of extendPicBorder is fused into the same pass: no second kernel, no inter-block dependency.
  * FILTER(a,b,c,d) = avg(avg(a,b), avg(c,d)) with round-up at both levels == chained __vavgu4.
@@ -87,13 +87,40 @@ struct VarBatch { const void* y[PRE_BATCH]; const void* u[PRE_BATCH]; const void
                   int64_t ys[PRE_BATCH], cs[PRE_BATCH];
                   void* uKeep[PRE_BATCH]; void* vKeep[PRE_BATCH]; };      /* compact copies of the chroma planes kept per frame slot (x265cu_wp.cuh), or NULL */
 
+/* One thread = LOWRES_UNIT(P) = 16 / sizeof(P) consecutive samples of one padded output row of all four planes: one 16-byte
+ * store per plane.  Threads are numbered over the units of the whole padded plane (unitsPerRow x paddedLines), so every
+ * thread of the grid has work.  Interior units whose source rows are 16-byte aligned read 2 x 16 bytes + 1 sample per
+ * source row and compute with packed rounded averages; units that lie entirely in the left / right margin replicate one
+ * value; the rest (mixed units, unaligned sources) go sample by sample. */
+#define LOWRES_UNIT(P) (16 / (int)sizeof(P))
+
+/* 8 packed source samples lo|hi of a vertical average + the 9th -> 4 outputs at even positions and 4 at odd + 1/2 */
+__device__ __forceinline__ void lowres_pack8(uint32_t lo, uint32_t hi, uint32_t next, uint32_t& full, uint32_t& half)
+{
+    const uint32_t e = __byte_perm(lo, hi, 0x6420), o = __byte_perm(lo, hi, 0x7531);
+    const uint32_t f = (e >> 8) | (next << 24);
+    full = __vavgu4(e, o);
+    half = __vavgu4(o, f);
+}
+/* the same for 16-bit samples: 4 packed samples lo|hi + the 5th -> 2 + 2 outputs */
+__device__ __forceinline__ void lowres_pack16(uint32_t lo, uint32_t hi, uint32_t next, uint32_t& full, uint32_t& half)
+{
+    const uint32_t e = __byte_perm(lo, hi, 0x5410), o = __byte_perm(lo, hi, 0x7632);
+    const uint32_t f = (e >> 16) | (next << 16);
+    full = __vavgu2(e, o);
+    half = __vavgu2(o, f);
+}
+
 template <typename P>
 __device__ __forceinline__ void lowres_init_body(const P* __restrict__ src, int64_t srcPitch, P* __restrict__ planes, const GeomDev& g)
 {
-    const int oy = blockIdx.y;                                  /* padded row */
-    const int ox0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4; /* padded column of the first of 4 samples */
+    const int V = LOWRES_UNIT(P);
     const int padW = g.width + 2 * g.marginX;
-    if (ox0 >= padW) return;
+    const int unitsPerRow = (padW + V - 1) / V;
+    const int unit = blockIdx.x * blockDim.x + threadIdx.x;
+    if (unit >= unitsPerRow * g.paddedLines) return;
+    const int oy = unit / unitsPerRow;                          /* padded row */
+    const int ox0 = (unit - oy * unitsPerRow) * V;              /* padded column of the first sample */
     int yy = oy - g.marginY;
     yy = yy < 0 ? 0 : (yy > g.lines - 1 ? g.lines - 1 : yy);
     const P* r0 = src + (int64_t)(2 * yy) * srcPitch;
@@ -104,44 +131,79 @@ __device__ __forceinline__ void lowres_init_body(const P* __restrict__ src, int6
     P* dv = dh + g.planeSize;
     P* dc = dv + g.planeSize;
     const int x0 = ox0 - g.marginX;
-    int o0[4], oh[4], ov[4], oc[4];
-    if (sizeof(P) == 1 && x0 >= 0 && x0 + 3 < g.width && ox0 + 3 < padW)
+    const bool whole = ox0 + V <= padW && (((uintptr_t)planes | (uintptr_t)(g.stride * (int)sizeof(P)) | (uintptr_t)(g.planeSize * (int64_t)sizeof(P))) & 15) == 0;
+    if (whole && x0 >= 0 && x0 + V <= g.width && (((uintptr_t)src | (uintptr_t)(srcPitch * (int64_t)sizeof(P))) & 15) == 0 && ((2 * x0 * (int)sizeof(P)) & 15) == 0)
     {
-        /* interior fast path, 8-bit: 8 source bytes + 1 per row, packed rounded averages */
-        const uint8_t* s0 = (const uint8_t*)r0 + 2 * x0;
-        const uint8_t* s1 = (const uint8_t*)r1 + 2 * x0;
-        const uint8_t* s2 = (const uint8_t*)r2 + 2 * x0;
-        uint2 a = __ldg((const uint2*)s0), b = __ldg((const uint2*)s1), c = __ldg((const uint2*)s2);
-        uint32_t a8 = __ldg(s0 + 8), b8 = __ldg(s1 + 8), c8 = __ldg(s2 + 8);
-        uint32_t v01lo = __vavgu4(a.x, b.x), v01hi = __vavgu4(a.y, b.y), v01x = (a8 + b8 + 1) >> 1;
-        uint32_t v12lo = __vavgu4(b.x, c.x), v12hi = __vavgu4(b.y, c.y), v12x = (b8 + c8 + 1) >> 1;
-        /* even columns 0,2,4,6 / odd 1,3,5,7 / even shifted 2,4,6,8 */
-        uint32_t e01 = __byte_perm(v01lo, v01hi, 0x6420), o01 = __byte_perm(v01lo, v01hi, 0x7531);
-        uint32_t e12 = __byte_perm(v12lo, v12hi, 0x6420), o12 = __byte_perm(v12lo, v12hi, 0x7531);
-        uint32_t f01 = (e01 >> 8) | (v01x << 24), f12 = (e12 >> 8) | (v12x << 24);
-        *(uint32_t*)d0 = __vavgu4(e01, o01);
-        *(uint32_t*)dh = __vavgu4(o01, f01);
-        *(uint32_t*)dv = __vavgu4(e12, o12);
-        *(uint32_t*)dc = __vavgu4(o12, f12);
+        /* interior fast path: 2 V + 1 source samples per row */
+        const uint4* s0 = (const uint4*)(r0 + 2 * x0);
+        const uint4* s1 = (const uint4*)(r1 + 2 * x0);
+        const uint4* s2 = (const uint4*)(r2 + 2 * x0);
+        const uint4 a0 = __ldg(s0), a1 = __ldg(s0 + 1), b0 = __ldg(s1), b1 = __ldg(s1 + 1), c0 = __ldg(s2), c1 = __ldg(s2 + 1);
+        const uint32_t ax = __ldg(r0 + 2 * x0 + 2 * V), bx = __ldg(r1 + 2 * x0 + 2 * V), cx = __ldg(r2 + 2 * x0 + 2 * V);
+        uint32_t v01[9], v12[9];
+        if (sizeof(P) == 1)
+        {
+            v01[0] = __vavgu4(a0.x, b0.x); v01[1] = __vavgu4(a0.y, b0.y); v01[2] = __vavgu4(a0.z, b0.z); v01[3] = __vavgu4(a0.w, b0.w);
+            v01[4] = __vavgu4(a1.x, b1.x); v01[5] = __vavgu4(a1.y, b1.y); v01[6] = __vavgu4(a1.z, b1.z); v01[7] = __vavgu4(a1.w, b1.w);
+            v12[0] = __vavgu4(b0.x, c0.x); v12[1] = __vavgu4(b0.y, c0.y); v12[2] = __vavgu4(b0.z, c0.z); v12[3] = __vavgu4(b0.w, c0.w);
+            v12[4] = __vavgu4(b1.x, c1.x); v12[5] = __vavgu4(b1.y, c1.y); v12[6] = __vavgu4(b1.z, c1.z); v12[7] = __vavgu4(b1.w, c1.w);
+        }
+        else
+        {
+            v01[0] = __vavgu2(a0.x, b0.x); v01[1] = __vavgu2(a0.y, b0.y); v01[2] = __vavgu2(a0.z, b0.z); v01[3] = __vavgu2(a0.w, b0.w);
+            v01[4] = __vavgu2(a1.x, b1.x); v01[5] = __vavgu2(a1.y, b1.y); v01[6] = __vavgu2(a1.z, b1.z); v01[7] = __vavgu2(a1.w, b1.w);
+            v12[0] = __vavgu2(b0.x, c0.x); v12[1] = __vavgu2(b0.y, c0.y); v12[2] = __vavgu2(b0.z, c0.z); v12[3] = __vavgu2(b0.w, c0.w);
+            v12[4] = __vavgu2(b1.x, c1.x); v12[5] = __vavgu2(b1.y, c1.y); v12[6] = __vavgu2(b1.z, c1.z); v12[7] = __vavgu2(b1.w, c1.w);
+        }
+        v01[8] = (ax + bx + 1) >> 1;
+        v12[8] = (bx + cx + 1) >> 1;
+        uint32_t o0[4], oh[4], ov[4], oc[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+        {
+            const uint32_t mask = sizeof(P) == 1 ? 0xffu : 0xffffu;
+            if (sizeof(P) == 1)
+            {
+                lowres_pack8(v01[2 * j], v01[2 * j + 1], v01[2 * j + 2] & mask, o0[j], oh[j]);
+                lowres_pack8(v12[2 * j], v12[2 * j + 1], v12[2 * j + 2] & mask, ov[j], oc[j]);
+            }
+            else
+            {
+                lowres_pack16(v01[2 * j], v01[2 * j + 1], v01[2 * j + 2] & mask, o0[j], oh[j]);
+                lowres_pack16(v12[2 * j], v12[2 * j + 1], v12[2 * j + 2] & mask, ov[j], oc[j]);
+            }
+        }
+        *(uint4*)d0 = make_uint4(o0[0], o0[1], o0[2], o0[3]);
+        *(uint4*)dh = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+        *(uint4*)dv = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+        *(uint4*)dc = make_uint4(oc[0], oc[1], oc[2], oc[3]);
         return;
     }
-#pragma unroll
-    for (int i = 0; i < 4; i++)
+    if (whole && (x0 + V <= 0 || x0 >= g.width))
+    {
+        /* entirely in the left / right margin: the edge sample of each plane, replicated */
+        const int xx = x0 < 0 ? 0 : g.width - 1;
+        const int c0 = 2 * xx, c1 = c0 + 1, c2 = c0 + 2;
+        uint32_t e0 = (uint32_t)lowres_px(r0, r1, c0, c1), eh = (uint32_t)lowres_px(r0, r1, c1, c2);
+        uint32_t ev = (uint32_t)lowres_px(r1, r2, c0, c1), ec = (uint32_t)lowres_px(r1, r2, c1, c2);
+        const uint32_t rep = sizeof(P) == 1 ? 0x01010101u : 0x00010001u;
+        e0 *= rep; eh *= rep; ev *= rep; ec *= rep;
+        *(uint4*)d0 = make_uint4(e0, e0, e0, e0);
+        *(uint4*)dh = make_uint4(eh, eh, eh, eh);
+        *(uint4*)dv = make_uint4(ev, ev, ev, ev);
+        *(uint4*)dc = make_uint4(ec, ec, ec, ec);
+        return;
+    }
+    for (int i = 0; i < V && ox0 + i < padW; i++)
     {
         int xx = x0 + i;
         xx = xx < 0 ? 0 : (xx > g.width - 1 ? g.width - 1 : xx);
-        int c0 = 2 * xx, c1 = c0 + 1, c2 = c0 + 2;
-        o0[i] = lowres_px(r0, r1, c0, c1);
-        oh[i] = lowres_px(r0, r1, c1, c2);
-        ov[i] = lowres_px(r1, r2, c0, c1);
-        oc[i] = lowres_px(r1, r2, c1, c2);
+        const int c0 = 2 * xx, c1 = c0 + 1, c2 = c0 + 2;
+        d0[i] = (P)lowres_px(r0, r1, c0, c1);
+        dh[i] = (P)lowres_px(r0, r1, c1, c2);
+        dv[i] = (P)lowres_px(r1, r2, c0, c1);
+        dc[i] = (P)lowres_px(r1, r2, c1, c2);
     }
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-        if (ox0 + i < padW)
-        {
-            d0[i] = (P)o0[i]; dh[i] = (P)oh[i]; dv[i] = (P)ov[i]; dc[i] = (P)oc[i];
-        }
 }
 
 template <typename P>
@@ -645,11 +707,40 @@ __global__ void __launch_bounds__(256) int_peak_kernel(int mode, int iters, unsi
 
 /* ===========================================================================================
  * frame_var: pixel_var<16> (luma) + pixel_var<8> (Cb, Cr) per 16x16 block, acEnergyCu
- * (slicetype.cpp:48-93).  One warp per 16x16 block, blocks strided over a grid sized to the GPU;
- * the six frame sums (wp_sum[0..2], wp_ssd[0..2]) are kept per warp, reduced per CTA in shared
- * memory and added to sums6 with six atomics per CTA.  8-bit rows that are 8-byte aligned are read
- * as one 64-bit word per lane and summed with the packed-byte instructions.
+ * (slicetype.cpp:48-93).  Wide form (16-byte aligned luma rows, 8-byte aligned chroma rows): a QUAD
+ * per 16x16 block, a warp per 8 consecutive blocks; a lane reads 4 luma rows of its block with one
+ * 16-byte load each (two at 16 bit) and 2 rows of Cb and of Cr with one 8-byte load each, sums with
+ * the packed-byte instructions (__vsadu4 against 0, dp4a of a word with itself), and a block's six
+ * sums meet in two shuffle steps; the loads of a warp cover 128 (256) contiguous bytes per row.
+ * Otherwise: one warp per block, 64-bit or scalar loads.  Groups / blocks are strided over a grid
+ * sized to the GPU; the six frame sums (wp_sum[0..2], wp_ssd[0..2]) are kept per lane, reduced per
+ * CTA in shared memory and added to sums6 with six atomics per CTA.
  * =========================================================================================== */
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+    return v;
+}
+template <typename P> struct VarAcc;
+template <> struct VarAcc<uint8_t>
+{
+    static __device__ __forceinline__ void add(uint32_t w, unsigned int& sum, unsigned int& sqr) { sum += __vsadu4(w, 0); sqr = __dp4a(w, w, sqr); }
+};
+template <> struct VarAcc<uint16_t>
+{
+    static __device__ __forceinline__ void add(uint32_t w, unsigned int& sum, unsigned int& sqr)
+    {
+        const unsigned int lo = w & 0xffffu, hi = w >> 16;
+        sum += lo + hi; sqr += lo * lo + hi * hi;
+    }
+};
+__device__ __forceinline__ unsigned int quad_sum_u(unsigned int v)
+{
+    v += __shfl_xor_sync(FULL_MASK, v, 1);
+    v += __shfl_xor_sync(FULL_MASK, v, 2);
+    return v;
+}
 template <typename P>
 __device__ __forceinline__ void frame_var_body(const P* __restrict__ y, int64_t ys, const P* __restrict__ u, const P* __restrict__ v, int64_t cs,
                                                int blocksX, int blocksY, unsigned int* __restrict__ energy, unsigned long long* __restrict__ sums6,
@@ -661,7 +752,70 @@ __device__ __forceinline__ void frame_var_body(const P* __restrict__ y, int64_t 
     __syncthreads();
     unsigned long long acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0, acc4 = 0, acc5 = 0;
     const bool packed = sizeof(P) == 1 && (((uintptr_t)y | (uintptr_t)(ys * (int64_t)sizeof(P))) & 7) == 0;
-    for (int blk = blockIdx.x * warpsPerCta + warp; blk < blocksX * blocksY; blk += gridDim.x * warpsPerCta)
+    const bool wide = (((uintptr_t)y | (uintptr_t)(ys * (int64_t)sizeof(P))) & 15) == 0 &&
+                      (!(u && v) || ((((uintptr_t)u | (uintptr_t)v | (uintptr_t)(cs * (int64_t)sizeof(P))) & (8 * sizeof(P) - 1)) == 0 &&
+                                     (!uKeep || (((uintptr_t)uKeep | (uintptr_t)vKeep) & (8 * sizeof(P) - 1)) == 0)));
+    const int nBlk = blocksX * blocksY;
+    if (wide)
+    {
+        const int q = lane >> 2, sub = lane & 3;
+        for (int grp = blockIdx.x * warpsPerCta + warp; grp * 8 < nBlk; grp += gridDim.x * warpsPerCta)
+        {
+            const int blk = grp * 8 + q;
+            const bool valid = blk < nBlk;
+            const int bxi = valid ? blk % blocksX : 0, byi = valid ? blk / blocksX : 0;
+            unsigned int sum = 0, sqr = 0, s1 = 0, q1 = 0, s2 = 0, q2 = 0;
+            if (valid)
+            {
+                const P* p = y + (int64_t)(16 * byi + 4 * sub) * ys + 16 * bxi;
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+#pragma unroll
+                    for (int h = 0; h < (int)sizeof(P); h++)
+                    {
+                        const uint4 w = __ldg((const uint4*)(p + (int64_t)r * ys) + h);
+                        VarAcc<P>::add(w.x, sum, sqr); VarAcc<P>::add(w.y, sum, sqr); VarAcc<P>::add(w.z, sum, sqr); VarAcc<P>::add(w.w, sum, sqr);
+                    }
+                if (u && v)
+                {
+#pragma unroll
+                    for (int r = 0; r < 2; r++)
+                    {
+                        const int64_t co = (int64_t)(8 * byi + 2 * sub + r) * cs + 8 * bxi;
+                        const int64_t ko = (int64_t)(8 * byi + 2 * sub + r) * (8 * blocksX) + 8 * bxi;
+                        if (sizeof(P) == 1)
+                        {
+                            const uint2 a = __ldg((const uint2*)(u + co)), b = __ldg((const uint2*)(v + co));
+                            VarAcc<P>::add(a.x, s1, q1); VarAcc<P>::add(a.y, s1, q1);
+                            VarAcc<P>::add(b.x, s2, q2); VarAcc<P>::add(b.y, s2, q2);
+                            if (uKeep) { *(uint2*)(uKeep + ko) = a; *(uint2*)(vKeep + ko) = b; }
+                        }
+                        else
+                        {
+                            const uint4 a = __ldg((const uint4*)(u + co)), b = __ldg((const uint4*)(v + co));
+                            VarAcc<P>::add(a.x, s1, q1); VarAcc<P>::add(a.y, s1, q1); VarAcc<P>::add(a.z, s1, q1); VarAcc<P>::add(a.w, s1, q1);
+                            VarAcc<P>::add(b.x, s2, q2); VarAcc<P>::add(b.y, s2, q2); VarAcc<P>::add(b.z, s2, q2); VarAcc<P>::add(b.w, s2, q2);
+                            if (uKeep) { *(uint4*)(uKeep + ko) = a; *(uint4*)(vKeep + ko) = b; }
+                        }
+                    }
+                }
+            }
+            acc0 += sum; acc3 += sqr; acc1 += s1; acc4 += q1; acc2 += s2; acc5 += q2;
+            sum = quad_sum_u(sum); sqr = quad_sum_u(sqr);
+            unsigned int var = sqr - (unsigned int)(((unsigned long long)sum * sum) >> 8);
+            if (u && v)
+            {
+                s1 = quad_sum_u(s1); q1 = quad_sum_u(q1); s2 = quad_sum_u(s2); q2 = quad_sum_u(q2);
+                var += q1 - (unsigned int)(((unsigned long long)s1 * s1) >> 6);
+                var += q2 - (unsigned int)(((unsigned long long)s2 * s2) >> 6);
+            }
+            if (valid && sub == 0) energy[blk] = var;
+        }
+        acc0 = (unsigned long long)warp_sum_u64(acc0); acc3 = warp_sum_u64(acc3);
+        if (u && v) { acc1 = warp_sum_u64(acc1); acc4 = warp_sum_u64(acc4); acc2 = warp_sum_u64(acc2); acc5 = warp_sum_u64(acc5); }
+    }
+    else
+    for (int blk = blockIdx.x * warpsPerCta + warp; blk < nBlk; blk += gridDim.x * warpsPerCta)
     {
         const int bxi = blk % blocksX, byi = blk / blocksX;
         /* luma: 256 samples, 8 per lane */
