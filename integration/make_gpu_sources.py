@@ -19,7 +19,7 @@ of x265_1.9/source):
     :1005 slicetypeDecide              + x265glue_sync(this) before the mini-GOP goes to the output queue
     :1668-1701, :1672, :1734  cuTree   + x265glue_ct_zero after each propagateCost memset; pre/post-swap around std::swap
     :1760 estimateCUPropagate          CU loops replaced by x265glue_propagate (queued)
-    :1845 cuTreeFinish                 + x265glue_ct_fetch first (runs the queued pass, one launch), x265glue_ct_finished last
+    :1845 cuTreeFinish                 + x265glue_ct_finish first (runs the queued pass, one launch; log2 mapping in the host layer, then returns), x265glue_ct_finished last
     :1921 CostEstimateGroup::finishBatch   body replaced by x265glue_finish_batch (one x265cu_estimate_batch per batch)
     :1980 estimateFrameCost            + x265glue_ensure first (singleCost: look-ahead estimate cache, weightsAnalyse on the GPU)
   lowres.cpp
@@ -123,7 +123,7 @@ def slicetype(src, out):
     k = p.find(r'^\s*for \(uint16_t blocky = 0; blocky < m_8x8Height; blocky\+\+\)', j)
     p.before(k, '    if (x265glue_propagate(this, frames, averageDuration, p0, p1, b, referenced)) { } else')
     i = p.find(r'^void Lookahead::cuTreeFinish\(')
-    p.after(p.find(r'^\{', i), '    x265glue_ct_fetch(this, frame);')
+    p.after(p.find(r'^\{', i), '    if (x265glue_ct_finish(this, frame, averageDuration, ref0Distance)) return;')
     p.before(p.find(r'^\}', i), '    x265glue_ct_finished(this, frame, averageDuration, ref0Distance);')
 
     # a batch of estimates in one call

@@ -530,6 +530,26 @@ extern "C" void x265glue_ct_fetch(xr::Lookahead* la, xr::Lowres* frame)
     if (!st->la.propagateCost(*shadowOf(st, la, frame))) die("propagateCost", st->la.m_error);
 }
 
+/* Lookahead::cuTreeFinish (slicetype.cpp:1844-1862) through the host layer: the queued pass runs (one launch), the frame's
+ * propagateCost comes back, and the log2 mapping to qpCuTreeOffset is x265cu::Lookahead::cuTreeFinish -- the reference's
+ * expressions, compiled like the reference, with X265_LOG2 of the (integer) arguments memoised: the same libm call's
+ * result, reused (the loop is 0.2 ms per 1080p frame with two log2 calls per CU, 31 times per 60 frames).  Returns 1:
+ * the caller returns; 0 (X265CU_GLUE_OWN_FINISH=0): only the fetch was done and x265's own loop runs. */
+extern "C" int x265glue_ct_finish(xr::Lookahead* la, xr::Lowres* frame, double averageDuration, int ref0Distance)
+{
+    static const bool own = !(getenv("X265CU_GLUE_OWN_FINISH") && atoi(getenv("X265CU_GLUE_OWN_FINISH")) == 0);
+    if (!own) { x265glue_ct_fetch(la, frame); return 0; }
+    GlueState* st = stateOf(la);
+    {
+        Timed timed(st, T_CTFETCH);
+        x265cu::Lowres* sh = shadowOf(st, la, frame);
+        if (ref0Distance) sh->weightedCostDelta[ref0Distance - 1] = frame->weightedCostDelta[ref0Distance - 1];
+        if (!st->la.cuTreeFinish(sh, averageDuration, ref0Distance)) die("cuTreeFinish", st->la.m_error);
+    }
+    x265glue_ct_finished(la, frame, averageDuration, ref0Distance);
+    return 1;
+}
+
 extern "C" void x265glue_ct_finished(xr::Lookahead*, xr::Lowres* frame, double averageDuration, int ref0Distance)
 {
     if (traceLevel() && x265ref_hook_ctfinish) x265ref_hook_ctfinish(frame, averageDuration, ref0Distance);

@@ -55,6 +55,7 @@ int  x265glue_propagate(X265_NS::Lookahead* la, X265_NS::Lowres** frames, double
 void x265glue_ct_fetch(X265_NS::Lookahead* la, X265_NS::Lowres* frame);
 /* ... and its last statement (observation only: trace harness) */
 void x265glue_ct_finished(X265_NS::Lookahead* la, X265_NS::Lowres* frame, double averageDuration, int ref0Distance);
+int  x265glue_ct_finish(X265_NS::Lookahead* la, X265_NS::Lowres* frame, double averageDuration, int ref0Distance);
 /* ---- Lookahead::slicetypeDecide (slicetype.cpp:1005), before the mini-GOP is handed to the output queue: the padded
  * lowres planes copied back for weightPrediction.cpp have landed */
 void x265glue_sync(X265_NS::Lookahead* la);

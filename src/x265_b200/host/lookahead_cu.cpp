@@ -1224,20 +1224,32 @@ bool Lookahead::cuTreeFinish(Lowres* frame, double averageDuration, int ref0Dist
     if (ref0Distance && frame->weightedCostDelta[ref0Distance - 1] > 0)
         weightdelta = (1.0 - frame->weightedCostDelta[ref0Distance - 1]);
     /* X265_LOG2 of small positive integers, memoised: the arguments are integers (costs), the same few thousand
-     * values come back frame after frame, and a cached result of the same libm call is the same double */
-    if (m_log2Lut.empty()) m_log2Lut.assign((size_t)1 << 20, -1.0);
-    double* lut = &m_log2Lut[0];
-    const int lutSize = (int)m_log2Lut.size();
+     * values come back frame after frame, and a cached result of the same libm call is the same double.  One table per
+     * process (zero pages until touched; 0.0 = not computed yet -- log2(1) is simply recomputed); entries are written
+     * whole and are the same from every thread. */
+    static uint64_t* const table = (uint64_t*)calloc((size_t)1 << 20, sizeof(uint64_t));
+    const int lutSize = table ? 1 << 20 : 0;
+    struct Memo
+    {
+        static inline double log2i(uint64_t* t, int size, int v)
+        {
+            if (v <= 1 || v >= size) return log2((double)v);
+            uint64_t bits = __atomic_load_n(&t[v], __ATOMIC_RELAXED);
+            double r;
+            if (bits) { memcpy(&r, &bits, sizeof(r)); return r; }
+            r = log2((double)v);
+            memcpy(&bits, &r, sizeof(r));
+            __atomic_store_n(&t[v], bits, __ATOMIC_RELAXED);
+            return r;
+        }
+    };
     for (int cuIndex = 0; cuIndex < m_cuCount; cuIndex++)
     {
         int intracost = (frame->intraCost[cuIndex] * frame->invQscaleFactor[cuIndex] + 128) >> 8;
         if (intracost)
         {
             int propagateCost = (frame->propagateCost[cuIndex] * fpsFactor + 128) >> 8;
-            const int a = intracost + propagateCost, b = intracost;
-            double la, lb;
-            if (a > 0 && a < lutSize) { la = lut[a]; if (la < 0) la = lut[a] = log2((double)a); } else la = log2((double)a);
-            if (b > 0 && b < lutSize) { lb = lut[b]; if (lb < 0) lb = lut[b] = log2((double)b); } else lb = log2((double)b);
+            const double la = Memo::log2i(table, lutSize, intracost + propagateCost), lb = Memo::log2i(table, lutSize, intracost);
             volatile double diff = la - lb;          /* evaluated left to right, as the reference's object code does */
             double log2_ratio = diff + weightdelta;
             frame->qpCuTreeOffset[cuIndex] = frame->qpAqOffset[cuIndex] - m_cuTreeStrength * log2_ratio;

@@ -197,7 +197,6 @@ public:
     std::vector<x265cu_cutree_op> m_ctOps;
     std::vector<Lowres*> m_ctTouched;
     double m_cuTreeStrength;
-    std::vector<double> m_log2Lut;          /* memoised log2 of integer costs (cuTreeFinish) */
     int64_t m_ctStats[3];                   /* propagate steps, launches (queue runs), mirrors re-uploaded */
     void cuTreeZero(Lowres& f);
     bool estimateCUPropagate(Lowres** frames, double averageDuration, int p0, int p1, int b, int referenced);
