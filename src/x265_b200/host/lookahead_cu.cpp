@@ -1,6 +1,9 @@
 /* lookahead_cu.cpp -- see lookahead_cu.h.  Host layer above the C ABI; float decisions only. */
 #include "lookahead_cu.h"
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 
 #include <math.h>
@@ -11,16 +14,92 @@
 
 namespace x265cu {
 
-/* host threads for the per-frame float AQ mapping of a pre-lookahead list (X265CU_HOST_THREADS overrides) */
-static unsigned hostThreads()
+/* A small persistent pool for the float AQ mapping (one per process, created on first use): the reference spreads the frames
+ * of a pre-lookahead list over its workers (slicetype.cpp:837-855); here the GPU delivers the energies of a few frames at a
+ * time, so the frames of such a run AND the block rows inside a frame (independent in aq-mode 1) are spread over the cores
+ * this process may use.  run(n, f) calls f(0..n-1), the caller takes part; a second caller at the same time (another stream
+ * of the process) simply runs its items itself. */
+class HostPool
 {
-    if (const char* e = getenv("X265CU_HOST_THREADS")) return (unsigned)atoi(e);
-    /* the cores this process may run on (a pinned rank sees its share, not the whole box) */
-    cpu_set_t set;
-    unsigned n = std::thread::hardware_concurrency();
-    if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) n = (unsigned)CPU_COUNT(&set);
-    return n >= 8 ? n / 4 : (n >= 2 ? 2 : 1);
-}
+public:
+    static HostPool& get() { static HostPool p; return p; }
+    int threads() const { return (int)m_threads.size() + 1; }
+    void run(int n, const std::function<void(int)>& f)
+    {
+        if (n <= 1 || m_threads.empty() || !m_busy.try_lock()) { for (int i = 0; i < n; i++) f(i); return; }
+        {
+            std::lock_guard<std::mutex> lk(m_mtx);
+            m_fn = &f; m_total = n; m_next = 0; m_pending = n; m_gen++;
+        }
+        m_work.notify_all();
+        take();
+        {
+            std::unique_lock<std::mutex> lk(m_mtx);
+            m_done.wait(lk, [this]() { return m_pending == 0; });
+            m_fn = NULL;
+        }
+        m_busy.unlock();
+    }
+
+private:
+    HostPool() : m_fn(NULL), m_total(0), m_next(0), m_pending(0), m_gen(0), m_stop(false)
+    {
+        unsigned n = 1;
+        if (const char* e = getenv("X265CU_HOST_THREADS")) n = (unsigned)atoi(e);
+        else
+        {
+            cpu_set_t set;
+            n = std::thread::hardware_concurrency();
+            if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) n = (unsigned)CPU_COUNT(&set);
+            if (n > 16) n = 16;
+        }
+        for (unsigned t = 1; t < n; t++) m_threads.push_back(std::thread([this]() { loop(); }));
+    }
+    ~HostPool()
+    {
+        { std::lock_guard<std::mutex> lk(m_mtx); m_stop = true; }
+        m_work.notify_all();
+        for (size_t t = 0; t < m_threads.size(); t++) m_threads[t].join();
+    }
+    void take()
+    {
+        for (;;)
+        {
+            int i;
+            const std::function<void(int)>* f;
+            {
+                std::lock_guard<std::mutex> lk(m_mtx);
+                if (!m_fn || m_next >= m_total) return;
+                i = m_next++; f = m_fn;
+            }
+            (*f)(i);
+            bool last;
+            { std::lock_guard<std::mutex> lk(m_mtx); last = --m_pending == 0; }
+            if (last) m_done.notify_all();
+        }
+    }
+    void loop()
+    {
+        uint64_t seen = 0;
+        for (;;)
+        {
+            {
+                std::unique_lock<std::mutex> lk(m_mtx);
+                m_work.wait(lk, [this, seen]() { return m_stop || (m_gen != seen && m_fn && m_next < m_total); });
+                if (m_stop) return;
+                seen = m_gen;
+            }
+            take();
+        }
+    }
+    std::vector<std::thread> m_threads;
+    std::mutex m_mtx, m_busy;
+    std::condition_variable m_work, m_done;
+    const std::function<void(int)>* m_fn;
+    int m_total, m_next, m_pending;
+    uint64_t m_gen;
+    bool m_stop;
+};
 
 namespace {
 inline int imin(int a, int b) { return a < b ? a : b; }
@@ -31,14 +110,13 @@ inline size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
 /* x265_exp2fix8, common/common.cpp:94-101; LUT entries are round(256 * (2^(i/64) - 1)) */
 int exp2fix8(double x)
 {
-    static uint8_t lut[64];
-    static bool init = false;
-    if (!init)
+    struct Lut
     {
-        for (int i = 0; i < 64; i++)
-            lut[i] = (uint8_t)floor(256.0 * (pow(2.0, i / 64.0) - 1.0) + 0.5);
-        init = true;
-    }
+        uint8_t v[64];
+        Lut() { for (int i = 0; i < 64; i++) v[i] = (uint8_t)floor(256.0 * (pow(2.0, i / 64.0) - 1.0) + 0.5); }
+    };
+    static const Lut table;         /* (thread-safe initialisation: the mapping runs on several threads) */
+    const uint8_t* lut = table.v;
     int i = (int)(x * (-64.f / 6.f) + 512.5f);
     if (i < 0) return 0;
     if (i > 1023) return 0xffff;
@@ -295,6 +373,48 @@ bool Lookahead::lowresInit(Lowres& l, const void* luma, intptr_t stride, int poc
     return true;
 }
 
+/* aq-mode 1 (slicetype.cpp:193-207): qp_adj = strength * (log2(max(energy, 1)) - const), blocks independent of each other;
+ * block rows [byFirst, byLast).  One compiled instance serves the whole-frame call and the row slices of the pool. */
+__attribute__((noinline)) void Lookahead::aqMapRows(Lowres& l, const uint32_t* energy, const float* quantOffsets, int byFirst, int byLast)
+{
+    const Param& param = m_param;
+    const int blocksX = (param.sourceWidth + 15) / 16;
+    const double strength = param.aqStrength * 1.0397f;
+    double qp_adj;
+    int blockXY = byFirst * blocksX;
+    for (int by = byFirst; by < byLast; by++)
+        for (int bx = 0; bx < blocksX; bx++)
+        {
+            uint32_t e = energy[blockXY];
+            qp_adj = strength * (log2((double)(e > 1 ? e : 1)) - (14.427f + 2 * (param.bitDepth - 8)));
+            if (quantOffsets != NULL)
+                qp_adj += quantOffsets[blockXY];
+            l.qpAqOffset[blockXY] = qp_adj;
+            l.qpCuTreeOffset[blockXY] = qp_adj;
+            l.invQscaleFactor[blockXY] = exp2fix8(qp_adj);
+            blockXY++;
+        }
+}
+
+/* what calcAdaptiveQuantFrame does around the mapping: wp_sum / wp_ssd from the six frame sums (slicetype.cpp:138-160, 209-227) */
+void Lookahead::aqFrameSums(Lowres& l, const uint64_t* sums)
+{
+    const Param& param = m_param;
+    for (int i = 0; i < 3; i++) { l.wp_sum[i] = sums[i]; l.wp_ssd[i] = sums[3 + i]; }
+    if (param.bEnableWeightedPred || param.bEnableWeightedBiPred)
+    {
+        int maxCol = ((param.sourceWidth + 8) >> 4) << 4;
+        int maxRow = ((param.sourceHeight + 8) >> 4) << 4;
+        int width[3] = { maxCol, maxCol >> 1, maxCol >> 1 };
+        int height[3] = { maxRow, maxRow >> 1, maxRow >> 1 };
+        for (int i = 0; i < 3; i++)
+        {
+            uint64_t sum = l.wp_sum[i], ssd = l.wp_ssd[i];
+            l.wp_ssd[i] = ssd - (sum * sum + (width[i] * height[i]) / 2) / (width[i] * height[i]);
+        }
+    }
+}
+
 /* LookaheadTLD::calcAdaptiveQuantFrame, encoder/slicetype.cpp:95-228.
  * The per-block AC energy and the wp sums come from the GPU; the mapping below is the host float. */
 bool Lookahead::calcAdaptiveQuantFrame(Lowres& l, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride,
@@ -376,6 +496,9 @@ bool Lookahead::calcAdaptiveQuantFrame(Lowres& l, const void* y, intptr_t yStrid
             strength = param.aqStrength * 1.0397f;
 
         blockXY = 0;
+        if (param.aqMode == 1)
+            aqMapRows(l, &energy[0], quantOffsets, 0, blocksY);
+        else
         for (int by = 0; by < blocksY; by++)
             for (int bx = 0; bx < blocksX; bx++)
             {
@@ -538,20 +661,27 @@ bool Lookahead::preLookaheadBatch(int n, Lowres** ls, const PictureIn* pics, boo
         {
             AqCtx* a = (AqCtx*)user;
             /* the mapping is per frame and independent: the reference runs the frames of the list on different workers,
-             * so do we for a run of several frames (same code, same flags, same results) */
-            unsigned nThreads = hostThreads();
-            if (nThreads > 4) nThreads = 4;
-            if ((int)nThreads > count / 2) nThreads = (unsigned)(count / 2);
-            if (nThreads <= 1)
-                for (int i = first; i < first + count; i++) one(a, i);
-            else
+             * so do we for a run of several frames (same code, same flags, same results); in aq-mode 1 the block rows of a
+             * frame are independent too and are spread as well */
+            Lookahead* la = a->la;
+            const Param& p = la->m_param;
+            HostPool& pool = HostPool::get();
+            if (p.aqMode == 1 && p.aqStrength != 0)
             {
-                std::vector<std::thread> workers;
-                for (unsigned t = 1; t < nThreads; t++)
-                    workers.push_back(std::thread([a, first, count, t, nThreads]() { for (int i = first + (int)t; i < first + count; i += (int)nThreads) one(a, i); }));
-                for (int i = first; i < first + count; i += (int)nThreads) one(a, i);
-                for (size_t t = 0; t < workers.size(); t++) workers[t].join();
+                const int blocksY = (p.sourceHeight + 15) / 16;
+                int slices = (pool.threads() + count - 1) / count;
+                if (slices > blocksY) slices = blocksY;
+                if (slices < 1) slices = 1;
+                pool.run(count * slices, [a, la, first, slices, blocksY](int k)
+                {
+                    const int i = first + k / slices, sl = k % slices;
+                    const int r0 = (int)((int64_t)blocksY * sl / slices), r1 = (int)((int64_t)blocksY * (sl + 1) / slices);
+                    if (sl == 0) la->aqFrameSums(*a->ls[i], a->items[i].sums);
+                    la->aqMapRows(*a->ls[i], a->items[i].energy, a->pics[i].quantOffsets, r0, r1);
+                });
             }
+            else
+                pool.run(count, [a, first](int k) { one(a, first + k); });
             for (int i = 0; i < count; i++) invQ[i] = a->ls[first + i]->invQscaleFactor;
         }
     };
@@ -1215,18 +1345,13 @@ const uint16_t* Lookahead::propagateCost(Lowres& f)
 }
 
 /* Lookahead::cuTreeFinish, slicetype.cpp:1844-1862: float mapping on the host (compiled like the reference) */
-bool Lookahead::cuTreeFinish(Lowres* frame, double averageDuration, int ref0Distance)
+/* the loop of Lookahead::cuTreeFinish (slicetype.cpp:1853-1862).  X265_LOG2 of small positive integers is memoised: the
+ * arguments are integers (costs), the same few thousand values come back frame after frame, and a cached result of the same
+ * libm call is the same double.  One table per process (zero pages until touched; 0.0 = not computed yet -- log2(1) is simply
+ * recomputed); entries are written whole and are the same from every thread. */
+void cuTreeFinishMap(const int32_t* intraCost, const int* invQscaleFactor, const uint16_t* propagateCost, const double* qpAqOffset,
+                     double* qpCuTreeOffset, int cuCount, int fpsFactor, double weightdelta, double cuTreeStrength)
 {
-    if (!cuTreeRun(&frame, 1)) return false;
-    if (m_resident) return true;         /* intraCost / qpAqOffset are not on the host in resident mode (propagateCost is) */
-    int fpsFactor = (int)(clipDuration(averageDuration) / clipDuration((double)m_param.fpsDenom / m_param.fpsNum) * 256);
-    double weightdelta = 0.0;
-    if (ref0Distance && frame->weightedCostDelta[ref0Distance - 1] > 0)
-        weightdelta = (1.0 - frame->weightedCostDelta[ref0Distance - 1]);
-    /* X265_LOG2 of small positive integers, memoised: the arguments are integers (costs), the same few thousand
-     * values come back frame after frame, and a cached result of the same libm call is the same double.  One table per
-     * process (zero pages until touched; 0.0 = not computed yet -- log2(1) is simply recomputed); entries are written
-     * whole and are the same from every thread. */
     static uint64_t* const table = (uint64_t*)calloc((size_t)1 << 20, sizeof(uint64_t));
     const int lutSize = table ? 1 << 20 : 0;
     struct Memo
@@ -1243,18 +1368,30 @@ bool Lookahead::cuTreeFinish(Lowres* frame, double averageDuration, int ref0Dist
             return r;
         }
     };
-    for (int cuIndex = 0; cuIndex < m_cuCount; cuIndex++)
+    for (int cuIndex = 0; cuIndex < cuCount; cuIndex++)
     {
-        int intracost = (frame->intraCost[cuIndex] * frame->invQscaleFactor[cuIndex] + 128) >> 8;
+        int intracost = (intraCost[cuIndex] * invQscaleFactor[cuIndex] + 128) >> 8;
         if (intracost)
         {
-            int propagateCost = (frame->propagateCost[cuIndex] * fpsFactor + 128) >> 8;
-            const double la = Memo::log2i(table, lutSize, intracost + propagateCost), lb = Memo::log2i(table, lutSize, intracost);
+            int propCost = (propagateCost[cuIndex] * fpsFactor + 128) >> 8;
+            const double la = Memo::log2i(table, lutSize, intracost + propCost), lb = Memo::log2i(table, lutSize, intracost);
             volatile double diff = la - lb;          /* evaluated left to right, as the reference's object code does */
             double log2_ratio = diff + weightdelta;
-            frame->qpCuTreeOffset[cuIndex] = frame->qpAqOffset[cuIndex] - m_cuTreeStrength * log2_ratio;
+            qpCuTreeOffset[cuIndex] = qpAqOffset[cuIndex] - cuTreeStrength * log2_ratio;
         }
     }
+}
+
+bool Lookahead::cuTreeFinish(Lowres* frame, double averageDuration, int ref0Distance)
+{
+    if (!cuTreeRun(&frame, 1)) return false;
+    if (m_resident) return true;         /* intraCost / qpAqOffset are not on the host in resident mode (propagateCost is) */
+    int fpsFactor = (int)(clipDuration(averageDuration) / clipDuration((double)m_param.fpsDenom / m_param.fpsNum) * 256);
+    double weightdelta = 0.0;
+    if (ref0Distance && frame->weightedCostDelta[ref0Distance - 1] > 0)
+        weightdelta = (1.0 - frame->weightedCostDelta[ref0Distance - 1]);
+    cuTreeFinishMap(frame->intraCost, frame->invQscaleFactor, frame->propagateCost, frame->qpAqOffset, frame->qpCuTreeOffset, m_cuCount,
+                    fpsFactor, weightdelta, m_cuTreeStrength);
     return true;
 }
 
@@ -1267,6 +1404,13 @@ bool Lookahead::cuTreeFinish(Lowres* frame, double averageDuration, int ref0Dist
 using namespace x265cu;
 
 extern "C" {
+
+/* the float mapping of cuTreeFinish on caller-supplied arrays: needs no GPU (CPU test of the pinned-compiler arithmetic) */
+void x265cuh_cutree_finish_map(const int32_t* intraCost, const int* invQscaleFactor, const uint16_t* propagateCost, const double* qpAqOffset,
+                               double* qpCuTreeOffset, int cuCount, int fpsFactor, double weightdelta, double cuTreeStrength)
+{
+    cuTreeFinishMap(intraCost, invQscaleFactor, propagateCost, qpAqOffset, qpCuTreeOffset, cuCount, fpsFactor, weightdelta, cuTreeStrength);
+}
 
 void* x265cuh_open(const x265cuh_params* p, char* err, int errLen)
 {

@@ -170,6 +170,8 @@ public:
     void forgetFrame(Lowres* l);            /* drop everything the look-ahead estimate cache derived from this frame */
     /* Lowres::init (lowres.cpp:128-165); luma = PicYuv::m_picOrg[0] padded as copyFromPicture does */
     bool lowresInit(Lowres& l, const void* luma, intptr_t stride, int poc, bool copyPlanesBack);
+    void aqMapRows(Lowres& l, const uint32_t* energy, const float* quantOffsets, int byFirst, int byLast);
+    void aqFrameSums(Lowres& l, const uint64_t* sums);
     /* LookaheadTLD::calcAdaptiveQuantFrame; planes padded like PicYuv */
     bool calcAdaptiveQuantFrame(Lowres& l, const void* y, intptr_t yStride, const void* u, const void* v, intptr_t cStride,
                                 const uint32_t* preEnergy = NULL, const uint64_t* preSums = NULL, bool publish = true,
@@ -250,6 +252,8 @@ typedef struct x265cuh_params
     int bEnableWeightedBiPred;
 } x265cuh_params;
 void* x265cuh_open(const x265cuh_params* p, char* err, int errLen);
+void  x265cuh_cutree_finish_map(const int32_t* intraCost, const int* invQscaleFactor, const uint16_t* propagateCost, const double* qpAqOffset,
+                                double* qpCuTreeOffset, int cuCount, int fpsFactor, double weightdelta, double cuTreeStrength);
 void  x265cuh_close(void* la);
 int   x265cuh_sync(void* la);                                 /* x265cu_sync: pending plane copy-backs have landed */
 void  x265cuh_set_resident(void* la, int on);                /* device-resident inputs/outputs (see Lookahead::m_resident) */
