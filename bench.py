@@ -577,8 +577,13 @@ def measure(args, workload, torch, dist, world, local, rank, headline):
     for k in ("search", "lowres", "var", "intra"):
         if kms.get(k, 0) > 0:
             ach = alg[k] / (kms[k] * 1e-3) / 1e9
+            cap = prof.get(k, {}).get(workload) or {}
+            per_launch_units = (units if k == "search" else nframes) / max(klaunch[k], 1)
             hbm_block[k] = {"achieved": ach, "frac": ach / hbm, "ms_per_step": kms[k], "launches_per_step": klaunch[k],
-                            "algorithmic_bytes_per_step": alg[k], "traffic": (prof.get(k, {}).get(workload) or {}).get("dram_bytes_per_unit")}
+                            "algorithmic_bytes_per_step": alg[k],
+                            # DRAM bytes of an average launch of this run, scaled from the committed ncu capture (per launch, like `achieved`)
+                            "traffic": cap["dram_bytes"] / cap["units"] * per_launch_units if cap.get("dram_bytes") else None,
+                            "captured_launch": {kk: cap[kk] for kk in ("kernel", "units", "dram_bytes", "us", "source") if kk in cap} or None}
     if roofline is None:
         d = hbm_block.get(dom, {"achieved": 0.0, "frac": 0.0})
         roofline = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": d["achieved"], "peak": hbm, "unit": "GB/s", "frac": d["frac"],
@@ -588,6 +593,11 @@ def measure(args, workload, torch, dist, world, local, rank, headline):
         satd["roofline_gpix_per_s"] = roof_pix
         satd["frac"] = satd["gpix_per_s"] / roof_pix
         satd["gb_per_s"] = satd["bytes_per_launch"] / (satd["ms"] * 1e-3) / 1e9
+        cap = prof.get("pixel", {}).get(workload) or {}
+        if cap.get("dram_bytes"):
+            # DRAM bytes of this launch, scaled from the committed ncu capture of the same kernel (bytes per plane pair)
+            satd["traffic"] = cap["dram_bytes"] / cap["units"] * satd.get("pairs", cap["units"])
+            satd["traffic_source"] = cap.get("source")
 
     # ---- CPU baseline (reported, not the target): the reference's own lookahead on the host cores ----
     cpu_baseline = None

@@ -2163,6 +2163,13 @@ int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_j
     if (!items.empty() && ((const SearchCtl*)(c->hArgs + offProg))->error)
         return fail(c, X265CU_ECUDA, "x265cu_estimate_batch: a wavefront hand-off wait timed out (search results incomplete)");
     const std::chrono::steady_clock::time_point tH3 = std::chrono::steady_clock::now();
+    {
+        static const bool dbgBatch = getenv("X265CU_BATCH_DEBUG") != NULL;
+        if (dbgBatch)
+            fprintf(stderr, "  estimate_batch: %d jobs, %zu searches (%zu row-group items), %zu cost-only, %zu weighted; planning %.3f ms, enqueue %.3f ms, wait %.3f ms\n",
+                    n, plans.size(), items.size(), costIdx.size(), weightedJobs.size(), std::chrono::duration<double, std::milli>(tH1 - tH0).count(),
+                    std::chrono::duration<double, std::milli>(tH2 - tH1).count(), std::chrono::duration<double, std::milli>(tH3 - tH2).count());
+    }
 #ifdef X265CU_SEARCH_STATS
     if (!plans.empty() && getenv("X265CU_TRACE_BATCH"))
     {
