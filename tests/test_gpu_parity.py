@@ -92,6 +92,13 @@ def test_replay_without_lookahead_cache(mods, monkeypatch):
     _replay(mods, "pool3_720p")
 
 
+def test_replay_without_rule_based_prediction(mods, monkeypatch):
+    """the cache with its history only (no trellis-segment prediction for requests the history cannot foresee)"""
+    monkeypatch.setenv("X265CU_TRELLIS_AHEAD", "0")
+    _replay(mods, "c0_720p")
+    _replay(mods, "pool3_720p")
+
+
 @pytest.mark.parametrize("var,val", [("X265CU_PRE_PIPELINE", "0"), ("X265CU_MAPPED_RESULTS", "0"), ("X265CU_DEFER_PLANES", "0")])
 def test_replay_transfer_variants(mods, monkeypatch, var, val):
     """the other setting of each host<->device transfer strategy: pre-lookahead list as three calls instead of the pipelined

@@ -56,3 +56,33 @@ def test_x265_host_trace_equals_reference(name, levels, built, tmp_path):
         assert types2 == types
     finally:
         d.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env", [{"X265CU_TRELLIS_AHEAD": "0"}, {"X265CU_GLUE_OWN_FINISH": "0"}, {"X265CU_LOOKAHEAD_CACHE": "0"}, {"X265CU_HOST_THREADS": "1"}])
+def test_x265_host_switches_do_not_change_the_trace(env, built, tmp_path):
+    """the other setting of each host-side switch of the x265-hosted path: the look-ahead cache without its rule-based part /
+    off altogether, cuTreeFinish's mapping by x265's own loop, the AQ mapping on one thread -- same trace.  (A subprocess per
+    setting: the switches are read once per process.)"""
+    import subprocess
+    import sys
+    if not _have(8):
+        pytest.skip("oracle/_ref/libx265gpu8.so not built (reference tree absent at build time)")
+    code = (
+        "import os, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "from harness import x265host as xh\n"
+        "from harness.workloads import WORKLOADS\n"
+        "for name in ('c0_720p', 'pool3_720p'):\n"
+        "    depth, w, h, n, seed, pool, opts, _ = WORKLOADS[name]\n"
+        "    d = xh.LaDriver(depth, w, h, n, seed, opts, pool, True)\n"
+        "    tr = os.path.join(%r, name + '.trace')\n"
+        "    d.run(trace=tr, level=1)\n"
+        "    mm = xh.compare_traces(tr, os.path.join(%r, 'tests', 'golden', name + '.trace'), 1)\n"
+        "    d.close()\n"
+        "    assert not mm, (name, mm[:6])\n"
+        "print('ok')\n" % (ROOT, str(tmp_path), ROOT))
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, "-c", code], env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, (env, r.stdout[-400:], r.stderr[-800:])
