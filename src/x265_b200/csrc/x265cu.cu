@@ -1105,11 +1105,15 @@ static int preBatchImpl2(x265cu_ctx* c, int n, const x265cu_frame_in* items, x26
         {
             KernelScope ks(c, X265CU_K_VAR);
             int blocks = (bxN * byN + 7) / 8;
-            const int cap = 148 * 8 / count > 148 ? 148 * 8 / count : 148;      /* warps stride over the 16x16 blocks */
+            static const int varPair = getenv("X265CU_VAR_PAIR") ? atoi(getenv("X265CU_VAR_PAIR")) : 1;           /* 0: a quad per block (tests) */
+            static const int varCtas = getenv("X265CU_VAR_CTAS") ? atoi(getenv("X265CU_VAR_CTAS")) : 148 * 8;
+            const int cap = varCtas / count > 148 ? varCtas / count : 148;      /* warps stride over the 16x16 blocks */
             if (blocks > cap) blocks = cap;
             dim3 grid(blocks, count);
-            if (c->pb == 1) frame_var_batch_kernel<uint8_t><<<grid, 256, 0, c->stream>>>(vb, bxN, byN);
-            else frame_var_batch_kernel<uint16_t><<<grid, 256, 0, c->stream>>>(vb, bxN, byN);
+            if (c->pb == 1 && varPair) frame_var_batch_kernel<uint8_t, true><<<grid, 256, 0, c->stream>>>(vb, bxN, byN);
+            else if (c->pb == 1) frame_var_batch_kernel<uint8_t, false><<<grid, 256, 0, c->stream>>>(vb, bxN, byN);
+            else if (varPair) frame_var_batch_kernel<uint16_t, true><<<grid, 256, 0, c->stream>>>(vb, bxN, byN);
+            else frame_var_batch_kernel<uint16_t, false><<<grid, 256, 0, c->stream>>>(vb, bxN, byN);
         }
         CU_TRY(c, cudaGetLastError());
         for (int k2 = 0; k2 < count; k2++)

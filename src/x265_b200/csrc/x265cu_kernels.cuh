@@ -707,11 +707,15 @@ __global__ void __launch_bounds__(256) int_peak_kernel(int mode, int iters, unsi
 
 /* ===========================================================================================
  * frame_var: pixel_var<16> (luma) + pixel_var<8> (Cb, Cr) per 16x16 block, acEnergyCu
- * (slicetype.cpp:48-93).  Wide form (16-byte aligned luma rows, 8-byte aligned chroma rows): a QUAD
- * per 16x16 block, a warp per 8 consecutive blocks; a lane reads 4 luma rows of its block with one
- * 16-byte load each (two at 16 bit) and 2 rows of Cb and of Cr with one 8-byte load each, sums with
- * the packed-byte instructions (__vsadu4 against 0, dp4a of a word with itself), and a block's six
- * sums meet in two shuffle steps; the loads of a warp cover 128 (256) contiguous bytes per row.
+ * (slicetype.cpp:48-93).  Wide forms (16-byte aligned luma rows, 8-byte aligned chroma rows).  PAIR
+ * (the batch kernel's default): a pair of lanes per 16x16 block, a warp per 16 consecutive blocks; a
+ * lane reads 8 luma rows of its block with one 16-byte load each (two at 16 bit) and 4 rows of Cb and
+ * of Cr with one 8-byte load each, all issued before the first is consumed; every load instruction
+ * of the warp covers whole 128-byte lines of the rows it touches (256 bytes of luma, 128 of chroma);
+ * sums with the packed-byte instructions (__vsadu4 against 0, dp4a of a word with itself), a block's
+ * six sums meet in one shuffle step.  Measured at 4K (48 frames, 7 launches): 0.199 ms against 0.287
+ * ms for the QUAD form (a quad per block, a warp per 8 blocks, 4 + 2 rows per lane: 64-byte pieces
+ * of the chroma rows per instruction), which the single-frame kernel keeps.
  * Otherwise: one warp per block, 64-bit or scalar loads.  Groups / blocks are strided over a grid
  * sized to the GPU; the six frame sums (wp_sum[0..2], wp_ssd[0..2]) are kept per lane, reduced per
  * CTA in shared memory and added to sums6 with six atomics per CTA.
@@ -741,7 +745,7 @@ __device__ __forceinline__ unsigned int quad_sum_u(unsigned int v)
     v += __shfl_xor_sync(FULL_MASK, v, 2);
     return v;
 }
-template <typename P>
+template <typename P, bool PAIR = false>
 __device__ __forceinline__ void frame_var_body(const P* __restrict__ y, int64_t ys, const P* __restrict__ u, const P* __restrict__ v, int64_t cs,
                                                int blocksX, int blocksY, unsigned int* __restrict__ energy, unsigned long long* __restrict__ sums6,
                                                P* __restrict__ uKeep = NULL, P* __restrict__ vKeep = NULL)
@@ -756,7 +760,77 @@ __device__ __forceinline__ void frame_var_body(const P* __restrict__ y, int64_t 
                       (!(u && v) || ((((uintptr_t)u | (uintptr_t)v | (uintptr_t)(cs * (int64_t)sizeof(P))) & (8 * sizeof(P) - 1)) == 0 &&
                                      (!uKeep || (((uintptr_t)uKeep | (uintptr_t)vKeep) & (8 * sizeof(P) - 1)) == 0)));
     const int nBlk = blocksX * blocksY;
-    if (wide)
+    if (PAIR && wide)
+    {
+        /* a PAIR of lanes per 16x16 block, a warp per 16 consecutive blocks: a lane reads 8 luma rows (16-byte loads) and 4 rows
+         * of Cb and of Cr; every load instruction of the warp covers whole 128-byte lines of each row it touches */
+        const int q = lane >> 1, sub = lane & 1;
+        for (int grp = blockIdx.x * warpsPerCta + warp; grp * 16 < nBlk; grp += gridDim.x * warpsPerCta)
+        {
+            const int blk = grp * 16 + q;
+            const bool valid = blk < nBlk;
+            const int bxi = valid ? blk % blocksX : 0, byi = valid ? blk / blocksX : 0;
+            unsigned int sum = 0, sqr = 0, s1 = 0, q1 = 0, s2 = 0, q2 = 0;
+            if (valid)
+            {
+                const P* p = y + (int64_t)(16 * byi + 8 * sub) * ys + 16 * bxi;
+                uint4 w[8 * (int)sizeof(P)];
+#pragma unroll
+                for (int r = 0; r < 8; r++)
+#pragma unroll
+                    for (int h = 0; h < (int)sizeof(P); h++)
+                        w[r * (int)sizeof(P) + h] = __ldg((const uint4*)(p + (int64_t)r * ys) + h);
+                if (u && v)
+                {
+                    const int64_t co = (int64_t)(8 * byi + 4 * sub) * cs + 8 * bxi;
+                    const int64_t ko = (int64_t)(8 * byi + 4 * sub) * (8 * blocksX) + 8 * bxi;
+                    if (sizeof(P) == 1)
+                    {
+                        uint2 a[4], b[4];
+#pragma unroll
+                        for (int r = 0; r < 4; r++) { a[r] = __ldg((const uint2*)(u + co + r * cs)); b[r] = __ldg((const uint2*)(v + co + r * cs)); }
+#pragma unroll
+                        for (int r = 0; r < 4; r++)
+                        {
+                            VarAcc<P>::add(a[r].x, s1, q1); VarAcc<P>::add(a[r].y, s1, q1);
+                            VarAcc<P>::add(b[r].x, s2, q2); VarAcc<P>::add(b[r].y, s2, q2);
+                            if (uKeep) { *(uint2*)(uKeep + ko + r * (8 * blocksX)) = a[r]; *(uint2*)(vKeep + ko + r * (8 * blocksX)) = b[r]; }
+                        }
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int r = 0; r < 4; r++)
+                        {
+                            const uint4 a = __ldg((const uint4*)(u + co + r * cs)), b = __ldg((const uint4*)(v + co + r * cs));
+                            VarAcc<P>::add(a.x, s1, q1); VarAcc<P>::add(a.y, s1, q1); VarAcc<P>::add(a.z, s1, q1); VarAcc<P>::add(a.w, s1, q1);
+                            VarAcc<P>::add(b.x, s2, q2); VarAcc<P>::add(b.y, s2, q2); VarAcc<P>::add(b.z, s2, q2); VarAcc<P>::add(b.w, s2, q2);
+                            if (uKeep) { *(uint4*)(uKeep + ko + r * (8 * blocksX)) = a; *(uint4*)(vKeep + ko + r * (8 * blocksX)) = b; }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 8 * (int)sizeof(P); k++)
+                {
+                    VarAcc<P>::add(w[k].x, sum, sqr); VarAcc<P>::add(w[k].y, sum, sqr); VarAcc<P>::add(w[k].z, sum, sqr); VarAcc<P>::add(w[k].w, sum, sqr);
+                }
+            }
+            acc0 += sum; acc3 += sqr; acc1 += s1; acc4 += q1; acc2 += s2; acc5 += q2;
+            sum += __shfl_xor_sync(FULL_MASK, sum, 1); sqr += __shfl_xor_sync(FULL_MASK, sqr, 1);
+            unsigned int var = sqr - (unsigned int)(((unsigned long long)sum * sum) >> 8);
+            if (u && v)
+            {
+                s1 += __shfl_xor_sync(FULL_MASK, s1, 1); q1 += __shfl_xor_sync(FULL_MASK, q1, 1);
+                s2 += __shfl_xor_sync(FULL_MASK, s2, 1); q2 += __shfl_xor_sync(FULL_MASK, q2, 1);
+                var += q1 - (unsigned int)(((unsigned long long)s1 * s1) >> 6);
+                var += q2 - (unsigned int)(((unsigned long long)s2 * s2) >> 6);
+            }
+            if (valid && sub == 0) energy[blk] = var;
+        }
+        acc0 = (unsigned long long)warp_sum_u64(acc0); acc3 = warp_sum_u64(acc3);
+        if (u && v) { acc1 = warp_sum_u64(acc1); acc4 = warp_sum_u64(acc4); acc2 = warp_sum_u64(acc2); acc5 = warp_sum_u64(acc5); }
+    }
+    else if (!PAIR && wide)
     {
         const int q = lane >> 2, sub = lane & 3;
         for (int grp = blockIdx.x * warpsPerCta + warp; grp * 8 < nBlk; grp += gridDim.x * warpsPerCta)
@@ -877,11 +951,11 @@ __global__ void __launch_bounds__(256) frame_var_kernel(const P* __restrict__ y,
     frame_var_body<P>(y, ys, u, v, cs, blocksX, blocksY, energy, sums6, uKeep, vKeep);
 }
 
-template <typename P>
+template <typename P, bool PAIR>
 __global__ void __launch_bounds__(256) frame_var_batch_kernel(VarBatch b, int blocksX, int blocksY)
 {
     const int f = blockIdx.y;
-    frame_var_body<P>((const P*)b.y[f], b.ys[f], (const P*)b.u[f], (const P*)b.v[f], b.cs[f], blocksX, blocksY, b.energy[f], b.sums[f], (P*)b.uKeep[f], (P*)b.vKeep[f]);
+    frame_var_body<P, PAIR>((const P*)b.y[f], b.ys[f], (const P*)b.u[f], (const P*)b.v[f], b.cs[f], blocksX, blocksY, b.energy[f], b.sums[f], (P*)b.uKeep[f], (P*)b.vKeep[f]);
 }
 
 #endif /* X265CU_KERNELS_CUH */
