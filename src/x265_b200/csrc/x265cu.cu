@@ -1105,8 +1105,8 @@ static int preBatchImpl2(x265cu_ctx* c, int n, const x265cu_frame_in* items, x26
         {
             KernelScope ks(c, X265CU_K_VAR);
             int blocks = (bxN * byN + 7) / 8;
-            static const int varPair = getenv("X265CU_VAR_PAIR") ? atoi(getenv("X265CU_VAR_PAIR")) : 1;           /* 0: a quad per block (tests) */
-            static const int varCtas = getenv("X265CU_VAR_CTAS") ? atoi(getenv("X265CU_VAR_CTAS")) : 148 * 8;
+            const int varPair = getenv("X265CU_VAR_PAIR") ? atoi(getenv("X265CU_VAR_PAIR")) : 1;           /* 0: a quad per block (tests) */
+            const int varCtas = getenv("X265CU_VAR_CTAS") && atoi(getenv("X265CU_VAR_CTAS")) >= 148 ? atoi(getenv("X265CU_VAR_CTAS")) : 148 * 8;
             const int cap = varCtas / count > 148 ? varCtas / count : 148;      /* warps stride over the 16x16 blocks */
             if (blocks > cap) blocks = cap;
             dim3 grid(blocks, count);

@@ -109,6 +109,13 @@ def test_replay_transfer_variants(mods, monkeypatch, var, val):
     _replay(mods, "tiny10")
 
 
+def test_replay_frame_var_quad_form(mods, monkeypatch):
+    """the variance kernel's other wide form (a quad per 16x16 block instead of a pair of lanes), 8 and 10 bit"""
+    monkeypatch.setenv("X265CU_VAR_PAIR", "0")
+    _replay(mods, "c0_720p")
+    _replay(mods, "tiny10")
+
+
 def test_replay_config1_1080p(mods):
     """BASELINE.json configs[1]: 1080p, b-adapt 2, rc-lookahead 40, cuTree on (the bench workload)"""
     _replay(mods, "c1_1080p")
