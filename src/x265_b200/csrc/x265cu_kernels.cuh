@@ -293,15 +293,30 @@ __global__ void __launch_bounds__(128) cost_kernel(const JobDev* __restrict__ jo
         const int nWarps = blockDim.x >> 5;
         /* a warp takes 8 adjacent CUs (one per quad) and measures both bidir candidates of each: the average of the two
          * motion-compensated blocks, then the average of the two co-located blocks (aligned rows: one load per row) */
+        /* the vectors of the NEXT round are requested before this round's pixels (the stores below keep the compiler from
+         * hoisting them): the vector -> pixel address dependency is off the critical path of every round but the first */
+        int mv0n = 0, mv1n = 0;
+        if (warp * 8 + q < W) { mv0n = job.mvs[0][warp * 8 + q + cuY * W]; mv1n = job.mvs[1][warp * 8 + q + cuY * W]; }
         for (int base = warp * 8; base < W; base += nWarps * 8)
         {
             const int cuX = base + q;
             const int valid = cuX < W;
             const int cuXY = (valid ? cuX : 0) + cuY * W;
+            const int mv0 = mv0n, mv1 = mv1n;
+            {
+                const int nx = cuX + nWarps * 8;
+                if (nx < W) { mv0n = job.mvs[0][nx + cuY * W]; mv1n = job.mvs[1][nx + cuY * W]; }
+            }
+            /* what la_cu_finish reads, requested together with the pixels */
+            int mc0 = 0, mc1 = 0, icost = 0, invq = 256;
+            if (valid && sub == 0)
+            {
+                mc0 = job.mvCosts[0][cuXY]; mc1 = job.mvCosts[1][cuXY]; icost = job.intraCost[cuXY];
+                if (hasQ) invq = job.invQ[cuXY];
+            }
             int partMc = 0, partCo = 0;
             if (valid)
             {
-                const int mv0 = job.mvs[0][cuXY], mv1 = job.mvs[1][cuXY];
                 const int px = 8 * cuX + bx, py = 8 * cuY + by;
                 typename Px<P>::Row4 fe[4], a[4], b[4];
 #pragma unroll
@@ -321,8 +336,7 @@ __global__ void __launch_bounds__(128) cost_kernel(const JobDev* __restrict__ jo
             const int cost = quad_sum(partMc) >> 1, other = quad_sum(partCo) >> 1;
             if (valid && sub == 0)
             {
-                LaCuResult res = la_cu_finish(cuX, cuY, W, H, 1, job.mvCosts[0][cuXY], job.mvCosts[1][cuXY], cost, other,
-                                              job.intraCost[cuXY], hasQ, hasQ ? job.invQ[cuXY] : 256);
+                LaCuResult res = la_cu_finish(cuX, cuY, W, H, 1, mc0, mc1, cost, other, icost, hasQ, invq);
                 if (res.scored) { accCost += res.bcost; accAq += res.bcostAq; }
                 rowSum += res.bcostAq;
                 job.lowresCosts[cuXY] = res.lowresCost;
