@@ -23,6 +23,8 @@
 #include <cuda_runtime.h>
 #include <sched.h>
 #include <stdio.h>
+#include <time.h>
+#include <unistd.h>
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
@@ -261,12 +263,54 @@ int growHost(x265cu_ctx* c, uint8_t** p, size_t* cap, size_t need)
     return 0;
 }
 
+/* ---- streams and events are pooled across the contexts of a process too (per device).  A host that opens a context per
+ * encode (or, like the lookahead-only driver, per run) would otherwise create and destroy a handful of streams and a few
+ * hundred events each time; stream creation / destruction goes through the driver's system-wide resource manager, and with
+ * one process per GPU doing that at the same moment on an 8-GPU box the calls of OTHER processes stall behind it (measured:
+ * cudaStreamSynchronize of an idle stream blocked for 0.6-1.4 s).  A stream is given back idle (x265cu_close waits first). ---- */
+struct ResPool { std::vector<cudaStream_t> streams; std::vector<cudaEvent_t> events, timingEvents; };
+std::map<int, ResPool> g_resPool;
+std::mutex g_resMtx;
+
+cudaError_t takeStream(int dev, cudaStream_t* s)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_resMtx);
+        ResPool& rp = g_resPool[dev];
+        if (!rp.streams.empty()) { *s = rp.streams.back(); rp.streams.pop_back(); return cudaSuccess; }
+    }
+    return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
+}
+void giveStream(int dev, cudaStream_t s)
+{
+    if (!s) return;
+    std::lock_guard<std::mutex> lk(g_resMtx);
+    g_resPool[dev].streams.push_back(s);
+}
+cudaError_t takeEvent(int dev, cudaEvent_t* e, bool timing = false)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_resMtx);
+        ResPool& rp = g_resPool[dev];
+        std::vector<cudaEvent_t>& v = timing ? rp.timingEvents : rp.events;
+        if (!v.empty()) { *e = v.back(); v.pop_back(); return cudaSuccess; }
+    }
+    return timing ? cudaEventCreate(e) : cudaEventCreateWithFlags(e, cudaEventDisableTiming);
+}
+void giveEvent(int dev, cudaEvent_t e, bool timing = false)
+{
+    if (!e) return;
+    std::lock_guard<std::mutex> lk(g_resMtx);
+    ResPool& rp = g_resPool[dev];
+    (timing ? rp.timingEvents : rp.events).push_back(e);
+}
+
 /* ---- timing helpers ---- */
 cudaEvent_t getEvent(x265cu_ctx* c)
 {
     if (!c->freeEvents.empty()) { cudaEvent_t e = c->freeEvents.back(); c->freeEvents.pop_back(); return e; }
-    cudaEvent_t e;
-    cudaEventCreate(&e);
+    cudaEvent_t e = NULL;
+    takeEvent(c->cfg.device, &e, true);
     return e;
 }
 
@@ -297,8 +341,27 @@ void resolveEvents(x265cu_ctx* c)
     c->pending.clear();
 }
 
+/* X265CU_SLOW_LOG_MS=N (diagnostics): every library call / wait that takes longer than N ms is reported on stderr with a wall-clock
+ * stamp, so that stalls of several processes sharing a box can be lined up */
+struct SlowLog
+{
+    const char* name; std::chrono::steady_clock::time_point t0; double limit;
+    static double threshold() { static const double v = getenv("X265CU_SLOW_LOG_MS") ? atof(getenv("X265CU_SLOW_LOG_MS")) : 0.0; return v; }
+    explicit SlowLog(const char* n) : name(n), limit(threshold()) { if (limit > 0) t0 = std::chrono::steady_clock::now(); }
+    ~SlowLog()
+    {
+        if (limit <= 0) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (ms < limit) return;
+        struct timespec ts;
+        clock_gettime(CLOCK_REALTIME, &ts);
+        fprintf(stderr, "x265cu slow call [pid %d, wall %ld.%03ld]: %s took %.1f ms\n", (int)getpid(), (long)(ts.tv_sec % 100000), ts.tv_nsec / 1000000, name, ms);
+    }
+};
+
 int syncStream(x265cu_ctx* c)
 {
+    SlowLog slow("cudaStreamSynchronize(stream)");
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     resolveEvents(c);
     return 0;
@@ -356,22 +419,22 @@ void freeAll(x265cu_ctx* c)
     poolGive(g_devPool, dev, c->dSrcLin, c->dSrcLinCap); poolGive(g_devPool, dev, c->dUp, c->dUpCap); poolGive(g_devPool, dev, c->dPre, c->dPreCap);
     poolGive(g_hostPool, dev, c->hStage, c->hStageCap); poolGive(g_hostPool, dev, c->hArgs, c->hArgsCap); poolGive(g_hostPool, dev, c->hPre, c->hPreCap);
     for (size_t i = 0; i < c->wPool.size(); i++) poolGive(g_devPool, dev, c->wPool[i], (size_t)4 * c->g.planeSize * c->pb + 256);
-    if (c->upStream) cudaStreamDestroy(c->upStream);
-    if (c->intraStream) cudaStreamDestroy(c->intraStream);
+    giveStream(dev, c->upStream);
+    giveStream(dev, c->intraStream);
     for (size_t i = 0; i < c->slotUp.size(); i++)
     {
         poolGive(g_devPool, dev, c->slotUp[i].d, c->slotUp[i].cap);
-        if (c->slotUp[i].done) cudaEventDestroy(c->slotUp[i].done);
-        if (c->slotUp[i].read) cudaEventDestroy(c->slotUp[i].read);
+        giveEvent(dev, c->slotUp[i].done);
+        giveEvent(dev, c->slotUp[i].read);
     }
-    for (size_t i = 0; i < c->preEvents.size(); i++) cudaEventDestroy(c->preEvents[i]);
-    for (size_t i = 0; i < c->upEvents.size(); i++) cudaEventDestroy(c->upEvents[i]);
-    for (size_t i = 0; i < c->freeEvents.size(); i++) cudaEventDestroy(c->freeEvents[i]);
-    if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
-    if (c->copyStream) cudaStreamDestroy(c->copyStream);
-    if (c->evKernel) cudaEventDestroy(c->evKernel);
-    for (size_t i = 0; i < c->planesCopied.size(); i++) if (c->planesCopied[i]) cudaEventDestroy(c->planesCopied[i]);
-    for (size_t i = 0; i < c->planesReady.size(); i++) if (c->planesReady[i]) cudaEventDestroy(c->planesReady[i]);
+    for (size_t i = 0; i < c->preEvents.size(); i++) giveEvent(dev, c->preEvents[i]);
+    for (size_t i = 0; i < c->upEvents.size(); i++) giveEvent(dev, c->upEvents[i]);
+    for (size_t i = 0; i < c->freeEvents.size(); i++) giveEvent(dev, c->freeEvents[i], true);
+    if (c->ownStream) giveStream(dev, c->stream);
+    giveStream(dev, c->copyStream);
+    giveEvent(dev, c->evKernel);
+    for (size_t i = 0; i < c->planesCopied.size(); i++) giveEvent(dev, c->planesCopied[i]);
+    for (size_t i = 0; i < c->planesReady.size(); i++) giveEvent(dev, c->planesReady[i]);
 }
 
 } // namespace
@@ -392,6 +455,7 @@ const char* x265cu_last_error(const x265cu_ctx* ctx) { return ctx ? ctx->err : g
 
 int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
 {
+    SlowLog slow("x265cu_open");
     if (!cfg || !out) { snprintf(g_openError, sizeof(g_openError), "x265cu_open: NULL argument"); return X265CU_EINVAL; }
     *out = NULL;
     if (cfg->srcWidth < 16 || cfg->srcHeight < 16 || cfg->bframes < 0 || cfg->bframes > X265CU_BFRAME_MAX ||
@@ -495,9 +559,9 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
 
     OPEN_TRY(cudaSetDevice(cfg->device));
     if (cfg->stream) c->stream = (cudaStream_t)cfg->stream;
-    else { OPEN_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->ownStream = true; }
-    OPEN_TRY(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
-    OPEN_TRY(cudaEventCreateWithFlags(&c->evKernel, cudaEventDisableTiming));
+    else { OPEN_TRY(takeStream(c->cfg.device, &c->stream)); c->ownStream = true; }
+    OPEN_TRY(takeStream(c->cfg.device, &c->copyStream));
+    OPEN_TRY(takeEvent(c->cfg.device, &c->evKernel));
     c->planesCopied.assign(cfg->numFrameSlots, (cudaEvent_t)NULL);
     c->planesPending.assign(cfg->numFrameSlots, 0);
     c->planesReady.assign(cfg->numFrameSlots, (cudaEvent_t)NULL);
@@ -508,9 +572,9 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
         c->slotUp.assign(cfg->numFrameSlots, z);
     }
     for (int i = 0; i < cfg->numFrameSlots; i++)
-        OPEN_TRY(cudaEventCreateWithFlags(&c->planesReady[i], cudaEventDisableTiming));
+        OPEN_TRY(takeEvent(c->cfg.device, &c->planesReady[i]));
     for (int i = 0; i < cfg->numFrameSlots; i++)
-        OPEN_TRY(cudaEventCreateWithFlags(&c->planesCopied[i], cudaEventDisableTiming));
+        OPEN_TRY(takeEvent(c->cfg.device, &c->planesCopied[i]));
 
     const size_t S = (size_t)cfg->numFrameSlots, n = (size_t)g.nCU, t2 = (size_t)(c->bf + 2) * (c->bf + 2), t1 = (size_t)2 * (c->bf + 1);
     size_t planeBytes = S * 4 * (size_t)g.planeSize * c->pb + 256;
@@ -573,6 +637,7 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
 
 void x265cu_close(x265cu_ctx* c)
 {
+    SlowLog slow("x265cu_close");
     if (!c) return;
     cudaSetDevice(c->cfg.device);
     cudaStreamSynchronize(c->stream);
@@ -650,16 +715,22 @@ int x265cu_get_geometry(const x265cu_ctx* c, x265cu_geometry* o)
 int x265cu_sync(x265cu_ctx* c)
 {
     if (!c) return X265CU_EINVAL;
-    std::lock_guard<std::mutex> lk(c->mtx);
+    SlowLog slowAll("x265cu_sync");
+    std::unique_lock<std::mutex> lk(c->mtx, std::defer_lock);
+    { SlowLog slow("x265cu_sync: lock"); lk.lock(); }
     if (flushDeferredPlanes(c)) return X265CU_ECUDA;
     int r = syncStream(c);
-    CU_TRY(c, cudaStreamSynchronize(c->copyStream));     /* pending plane copy-backs have landed */
+    {
+        SlowLog slow("x265cu_sync: cudaStreamSynchronize(copyStream)");
+        CU_TRY(c, cudaStreamSynchronize(c->copyStream));     /* pending plane copy-backs have landed */
+    }
     for (size_t i = 0; i < c->planesPending.size(); i++) c->planesPending[i] = 0;
     return r;
 }
 
 int x265cu_host_register(void* ptr, size_t bytes)
 {
+    SlowLog slow("x265cu_host_register");
     if (!ptr || !bytes) return X265CU_EINVAL;
     /* pinned AND mapped: copies to it are asynchronous, and result arrays can be written into it by a kernel */
     cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
@@ -678,6 +749,7 @@ int x265cu_host_register(void* ptr, size_t bytes)
 
 int x265cu_host_unregister(void* ptr)
 {
+    SlowLog slow("x265cu_host_unregister");
     if (!ptr) return X265CU_EINVAL;
     {
         std::lock_guard<std::mutex> lk(g_regMtx);
@@ -695,6 +767,15 @@ void x265cu_trim(void)
     for (size_t i = 0; i < g_hostPool.size(); i++) cudaFreeHost(g_hostPool[i].p);
     g_devPool.clear();
     g_hostPool.clear();
+    std::lock_guard<std::mutex> lr(g_resMtx);
+    for (std::map<int, ResPool>::iterator it = g_resPool.begin(); it != g_resPool.end(); ++it)
+    {
+        cudaSetDevice(it->first);
+        for (size_t i = 0; i < it->second.streams.size(); i++) cudaStreamDestroy(it->second.streams[i]);
+        for (size_t i = 0; i < it->second.events.size(); i++) cudaEventDestroy(it->second.events[i]);
+        for (size_t i = 0; i < it->second.timingEvents.size(); i++) cudaEventDestroy(it->second.timingEvents[i]);
+    }
+    g_resPool.clear();
 }
 
 int x265cu_stats_enable(x265cu_ctx* c, int timing)
@@ -892,8 +973,8 @@ int x265cu_frame_upload(x265cu_ctx* c, int slot, const void* y, intptr_t yStride
     const size_t cLin = (chromaRows - 1) * (size_t)cStride * c->pb + (size_t)bxN * 8 * c->pb;
     const size_t need = alignUp(yLin, 256) + 2 * alignUp(cLin, 256) + 256;
     x265cu_ctx::SlotUpload& su = c->slotUp[slot];
-    if (!c->upStream) CU_TRY(c, cudaStreamCreateWithFlags(&c->upStream, cudaStreamNonBlocking));
-    if (!su.done) { CU_TRY(c, cudaEventCreateWithFlags(&su.done, cudaEventDisableTiming)); CU_TRY(c, cudaEventCreateWithFlags(&su.read, cudaEventDisableTiming)); }
+    if (!c->upStream) CU_TRY(c, takeStream(c->cfg.device, &c->upStream));
+    if (!su.done) { CU_TRY(c, takeEvent(c->cfg.device, &su.done)); CU_TRY(c, takeEvent(c->cfg.device, &su.read)); }
     if (su.cap < need)
     {
         if (su.d) { CU_TRY(c, cudaStreamSynchronize(c->stream)); CU_TRY(c, cudaStreamSynchronize(c->upStream)); poolGive(g_devPool, c->cfg.device, su.d, su.cap); su.d = NULL; su.cap = 0; }
@@ -932,6 +1013,7 @@ int x265cu_frame_init_var_batch(x265cu_ctx* c, int n, const x265cu_frame_in* ite
 
 int x265cu_pre_lookahead_batch(x265cu_ctx* c, int n, const x265cu_frame_in* items, x265cu_aq_fn aq, void* user, x265cu_intra_out* outs)
 {
+    SlowLog slow("x265cu_pre_lookahead_batch");
     if (!c || n < 0 || (n && (!items || !aq || !outs))) return c ? fail(c, X265CU_EINVAL, "x265cu_pre_lookahead_batch: bad argument") : X265CU_EINVAL;
     if (!n) return X265CU_OK;
     std::lock_guard<std::mutex> lk(c->mtx);
@@ -960,11 +1042,11 @@ static int preBatchImpl2(x265cu_ctx* c, int n, const x265cu_frame_in* items, x26
     CU_TRY(c, cudaMemsetAsync(c->dPre, 0, intraSumsOff + (size_t)n * 16, c->stream));
     if (aq)
     {
-        if (!c->intraStream) CU_TRY(c, cudaStreamCreateWithFlags(&c->intraStream, cudaStreamNonBlocking));
+        if (!c->intraStream) CU_TRY(c, takeStream(c->cfg.device, &c->intraStream));
         while ((int)c->preEvents.size() < n)
         {
             cudaEvent_t e;
-            CU_TRY(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            CU_TRY(c, takeEvent(c->cfg.device, &e));
             c->preEvents.push_back(e);
         }
     }
@@ -988,11 +1070,11 @@ static int preBatchImpl2(x265cu_ctx* c, int n, const x265cu_frame_in* items, x26
     if (pipelined)
     {
         if (growDevice(c, &c->dUp, &c->dUpCap, off[n] + 256)) return X265CU_ECUDA;
-        if (!c->upStream) CU_TRY(c, cudaStreamCreateWithFlags(&c->upStream, cudaStreamNonBlocking));
+        if (!c->upStream) CU_TRY(c, takeStream(c->cfg.device, &c->upStream));
         while ((int)c->upEvents.size() < n)
         {
             cudaEvent_t e;
-            CU_TRY(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            CU_TRY(c, takeEvent(c->cfg.device, &e));
             c->upEvents.push_back(e);
         }
         for (int i = 0; i < n; i++)
@@ -1032,7 +1114,7 @@ static int preBatchImpl2(x265cu_ctx* c, int n, const x265cu_frame_in* items, x26
         while (c->preEvents.size() < chunkFirst.size())
         {
             cudaEvent_t e;
-            CU_TRY(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            CU_TRY(c, takeEvent(c->cfg.device, &e));
             c->preEvents.push_back(e);
         }
     for (size_t ch = 0; ch + 1 < chunkFirst.size() && chunked; ch++)
@@ -1550,6 +1632,7 @@ int x265cu_frame_set_array(x265cu_ctx* c, int slot, int which, int d0, int d1, c
 
 int x265cu_cutree_run(x265cu_ctx* c, int n, const x265cu_cutree_op* ops, int nOut, const int* outSlots, uint16_t* const* outPropagateCost)
 {
+    SlowLog slow("x265cu_cutree_run");
     if (!c || n < 0 || nOut < 0 || (n && !ops) || (nOut && (!outSlots || !outPropagateCost)))
         return c ? fail(c, X265CU_EINVAL, "x265cu_cutree_run: bad argument") : X265CU_EINVAL;
     std::lock_guard<std::mutex> lk(c->mtx);
@@ -1702,6 +1785,7 @@ int x265cu_weight_cost_batch(x265cu_ctx* c, int n, const x265cu_weight_item* ite
 /* -------------------------------------------------------------------------------------------- */
 int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_job_result* results)
 {
+    SlowLog slow("x265cu_estimate_batch");
     if (!c || n < 0 || (n && (!jobs || !results))) return c ? fail(c, X265CU_EINVAL, "x265cu_estimate_batch: bad argument") : X265CU_EINVAL;
     if (!n) return X265CU_OK;
     std::lock_guard<std::mutex> lk(c->mtx);
