@@ -28,6 +28,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cuda.h>
 #include <map>
@@ -101,6 +102,7 @@ struct x265cu_ctx
     uint8_t* dWp; size_t dWpCap;
     WpCostArgs wpArgs; bool wpReady;
     int cutreeCtas;                        /* grid of the cooperative cuTree kernel (one CTA per SM) */
+    const char* lastEnqueued;              /* diagnostics (X265CU_SLOW_LOG_MS): the entry that last put work on the stream */
     bool mappedResults;                    /* result arrays go straight into mapped pinned destinations (X265CU_MAPPED_RESULTS=0: always staged) */
     uint16_t* dPropOut; size_t dPropOutCap; /* clamped uint16 copies on their way to the host */
     uint16_t* hPropOut; size_t hPropOutCap;
@@ -305,6 +307,16 @@ void giveEvent(int dev, cudaEvent_t e, bool timing = false)
     (timing ? rp.timingEvents : rp.events).push_back(e);
 }
 
+/* entries without a context (pinned-memory registration) run on the device of the most recent x265cu_open of the process, else on
+ * $X265CU_DEVICE, never on the runtime's default device 0 by accident (a process per GPU must not create a context on GPU 0) */
+std::atomic<int> g_defaultDevice(-1);
+void bindDefaultDevice()
+{
+    int dev = g_defaultDevice.load();
+    if (dev < 0 && getenv("X265CU_DEVICE")) dev = atoi(getenv("X265CU_DEVICE"));
+    if (dev >= 0) { if (cudaSetDevice(dev) != cudaSuccess) cudaGetLastError(); }
+}
+
 /* ---- timing helpers ---- */
 cudaEvent_t getEvent(x265cu_ctx* c)
 {
@@ -476,7 +488,7 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     c->err[0] = 0;
     c->dPlanes = NULL; c->dIntraCost = NULL; c->dIntraMode = NULL; c->dInvQ = NULL; c->dLowresCosts = NULL; c->dRowSatds = NULL;
     c->dMvs = NULL; c->dMvCosts = NULL; c->dLut = NULL; c->dSrc = NULL; c->dSmall = NULL;
-    c->dStage = NULL; c->dStageCap = 0; c->hStage = NULL; c->hStageCap = 0; c->dArgs = NULL; c->dArgsCap = 0; c->hArgs = NULL; c->hArgsCap = 0; c->hPre = NULL; c->hPreCap = 0; c->dPre = NULL; c->dPreCap = 0; c->dSrcLin = NULL; c->dSrcLinCap = 0; c->dUp = NULL; c->dUpCap = 0; c->upStream = NULL; c->intraStream = NULL;
+    c->dStage = NULL; c->dStageCap = 0; c->hStage = NULL; c->hStageCap = 0; c->dArgs = NULL; c->dArgsCap = 0; c->hArgs = NULL; c->hArgsCap = 0; c->hPre = NULL; c->hPreCap = 0; c->dPre = NULL; c->dPreCap = 0; c->dSrcLin = NULL; c->dSrcLinCap = 0; c->dUp = NULL; c->dUpCap = 0; c->upStream = NULL; c->intraStream = NULL; c->lastEnqueued = NULL;
     c->dGeneric = NULL; c->dGenericCap = 0; c->dMemo = NULL; c->dMemoCap = 0;
     c->cutreeCtas = 0;
     c->mappedResults = !(getenv("X265CU_MAPPED_RESULTS") && atoi(getenv("X265CU_MAPPED_RESULTS")) == 0);
@@ -558,6 +570,7 @@ int x265cu_open(const x265cu_config* cfg, x265cu_ctx** out)
     } while (0)
 
     OPEN_TRY(cudaSetDevice(cfg->device));
+    g_defaultDevice.store(cfg->device);
     if (cfg->stream) c->stream = (cudaStream_t)cfg->stream;
     else { OPEN_TRY(takeStream(c->cfg.device, &c->stream)); c->ownStream = true; }
     OPEN_TRY(takeStream(c->cfg.device, &c->copyStream));
@@ -718,8 +731,19 @@ int x265cu_sync(x265cu_ctx* c)
     SlowLog slowAll("x265cu_sync");
     std::unique_lock<std::mutex> lk(c->mtx, std::defer_lock);
     { SlowLog slow("x265cu_sync: lock"); lk.lock(); }
+    /* (every entry binds the calling thread to the context's device first: a thread that has made no other call yet -- a pool
+     * worker running a slicetypeDecide that found everything cached -- would otherwise run on the runtime's default device 0 and
+     * create a context there: 0.6-1.4 s per process on an 8-GPU box, measured) */
+    CU_TRY(c, cudaSetDevice(c->cfg.device));
     if (flushDeferredPlanes(c)) return X265CU_ECUDA;
+    const bool diag = SlowLog::threshold() > 0;
+    const cudaError_t q0 = diag ? cudaStreamQuery(c->stream) : cudaSuccess;
+    const std::chrono::steady_clock::time_point tq = std::chrono::steady_clock::now();
     int r = syncStream(c);
+    if (diag && std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tq).count() >= SlowLog::threshold())
+        fprintf(stderr, "x265cu slow call [pid %d]: x265cu_sync found the stream %s before the wait; last entry that enqueued: %s\n", (int)getpid(),
+                q0 == cudaSuccess ? "IDLE" : (q0 == cudaErrorNotReady ? "BUSY" : cudaGetErrorString(q0)), c->lastEnqueued ? c->lastEnqueued : "-");
+    if (q0 != cudaSuccess) cudaGetLastError();
     {
         SlowLog slow("x265cu_sync: cudaStreamSynchronize(copyStream)");
         CU_TRY(c, cudaStreamSynchronize(c->copyStream));     /* pending plane copy-backs have landed */
@@ -732,6 +756,7 @@ int x265cu_host_register(void* ptr, size_t bytes)
 {
     SlowLog slow("x265cu_host_register");
     if (!ptr || !bytes) return X265CU_EINVAL;
+    bindDefaultDevice();
     /* pinned AND mapped: copies to it are asynchronous, and result arrays can be written into it by a kernel */
     cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
     if (e != cudaSuccess) { cudaGetLastError(); return X265CU_ECUDA; }
@@ -750,6 +775,7 @@ int x265cu_host_register(void* ptr, size_t bytes)
 int x265cu_host_unregister(void* ptr)
 {
     SlowLog slow("x265cu_host_unregister");
+    bindDefaultDevice();
     if (!ptr) return X265CU_EINVAL;
     {
         std::lock_guard<std::mutex> lk(g_regMtx);
@@ -782,6 +808,7 @@ int x265cu_stats_enable(x265cu_ctx* c, int timing)
 {
     if (!c) return X265CU_EINVAL;
     std::lock_guard<std::mutex> lk(c->mtx);
+    CU_TRY(c, cudaSetDevice(c->cfg.device));
     syncStream(c);
     c->timing = timing != 0;
     return X265CU_OK;
@@ -791,6 +818,7 @@ int x265cu_stats_get(x265cu_ctx* c, x265cu_stats* o, int reset)
 {
     if (!c || !o) return X265CU_EINVAL;
     std::lock_guard<std::mutex> lk(c->mtx);
+    CU_TRY(c, cudaSetDevice(c->cfg.device));
     int r = syncStream(c);
     *o = c->stats;
     if (reset) memset(&c->stats, 0, sizeof(c->stats));
@@ -1013,6 +1041,7 @@ int x265cu_frame_init_var_batch(x265cu_ctx* c, int n, const x265cu_frame_in* ite
 
 int x265cu_pre_lookahead_batch(x265cu_ctx* c, int n, const x265cu_frame_in* items, x265cu_aq_fn aq, void* user, x265cu_intra_out* outs)
 {
+    if (c) c->lastEnqueued = "pre_lookahead_batch";
     SlowLog slow("x265cu_pre_lookahead_batch");
     if (!c || n < 0 || (n && (!items || !aq || !outs))) return c ? fail(c, X265CU_EINVAL, "x265cu_pre_lookahead_batch: bad argument") : X265CU_EINVAL;
     if (!n) return X265CU_OK;
@@ -1325,6 +1354,7 @@ static int preBatchImpl2(x265cu_ctx* c, int n, const x265cu_frame_in* items, x26
 
 int x265cu_frame_set_invqscale(x265cu_ctx* c, int slot, const int32_t* invQ)
 {
+    if (c) c->lastEnqueued = "frame_set_invqscale";
     if (!c || badSlot(c, slot)) return c ? fail(c, X265CU_EINVAL, "x265cu_frame_set_invqscale: bad slot") : X265CU_EINVAL;
     std::lock_guard<std::mutex> lk(c->mtx);
     CU_TRY(c, cudaSetDevice(c->cfg.device));
@@ -1632,6 +1662,7 @@ int x265cu_frame_set_array(x265cu_ctx* c, int slot, int which, int d0, int d1, c
 
 int x265cu_cutree_run(x265cu_ctx* c, int n, const x265cu_cutree_op* ops, int nOut, const int* outSlots, uint16_t* const* outPropagateCost)
 {
+    if (c) c->lastEnqueued = "cutree_run";
     SlowLog slow("x265cu_cutree_run");
     if (!c || n < 0 || nOut < 0 || (n && !ops) || (nOut && (!outSlots || !outPropagateCost)))
         return c ? fail(c, X265CU_EINVAL, "x265cu_cutree_run: bad argument") : X265CU_EINVAL;
@@ -1785,6 +1816,7 @@ int x265cu_weight_cost_batch(x265cu_ctx* c, int n, const x265cu_weight_item* ite
 /* -------------------------------------------------------------------------------------------- */
 int x265cu_estimate_batch(x265cu_ctx* c, int n, const x265cu_job* jobs, x265cu_job_result* results)
 {
+    if (c) c->lastEnqueued = "estimate_batch";
     SlowLog slow("x265cu_estimate_batch");
     if (!c || n < 0 || (n && (!jobs || !results))) return c ? fail(c, X265CU_EINVAL, "x265cu_estimate_batch: bad argument") : X265CU_EINVAL;
     if (!n) return X265CU_OK;
