@@ -71,3 +71,28 @@ def test_product_never_touches_the_oracle():
                 assert "oracle/" not in txt.replace("tests/core_emul.cpp", "") or f == "la_core.h", f
                 assert "pyoracle" not in txt, f
                 assert "ola_" not in txt, f
+
+
+def test_every_entry_binds_its_thread_to_the_context_device():
+    """Static check of csrc/x265cu.cu: every ABI entry that touches the device calls cudaSetDevice(ctx device) itself or
+    delegates to an implementation that does.  (The library links its own CUDA runtime: a host thread that has made no call
+    yet -- an x265 pool worker whose first call is x265cu_sync -- would otherwise run on the default device 0 and create a
+    context there; on an 8-GPU box with one process per GPU that cost 0.6-1.4 s per process, found in round 2.)"""
+    src = open(os.path.join(ROOT, "src", "x265_b200", "csrc", "x265cu.cu")).read()
+    no_device_work = {"x265cu_abi_version", "x265cu_device_count", "x265cu_last_error", "x265cu_get_geometry"}
+    delegates = {"x265cu_frame_init": "frameInitImpl", "x265cu_frame_init_var": "frameInitImpl", "x265cu_pixelcmp_frames": "x265cu_pixelcmp_planes",
+                 "x265cu_host_register": "bindDefaultDevice", "x265cu_host_unregister": "bindDefaultDevice"}
+    seen = 0
+    for m in re.finditer(r"^(?:int|void|const char\*)\s+(x265cu_[a-z0-9_]+)\s*\(", src, re.M):
+        name = m.group(1)
+        body = src[m.start():src.find("\n}\n", m.start())]
+        if name in no_device_work:
+            continue
+        seen += 1
+        ok = "cudaSetDevice" in body or (name in delegates and delegates[name] in body)
+        assert ok, "%s makes device calls without binding the thread to the context's device" % name
+    assert seen >= 25
+    for impl in ("frameInitImpl", "bindDefaultDevice"):
+        i = src.find("int " + impl + "(") if impl == "frameInitImpl" else src.find("void " + impl + "(")
+        i = src.find("static int " + impl + "(", src.find("static int " + impl + "(") + 1) if impl == "frameInitImpl" else i
+        assert i >= 0 and "cudaSetDevice" in src[i:src.find("\n}\n", i)], impl
