@@ -157,13 +157,13 @@ void Lookahead::mvcostTable(int bitDepth, uint16_t* out, int* lambdaInt)
     }
 }
 
-Lookahead::Lookahead() : m_ctx(NULL), m_mvcost(NULL), m_lambda(1), m_resident(false), m_lookAhead(true), m_versionCounter(0), m_newestReady(0), m_episodeNewest(0), m_trellisAhead(true), m_batchFirst(-1), m_batchLast(-1)
+Lookahead::Lookahead() : m_ctx(NULL), m_mvcost(NULL), m_lambda(1), m_resident(false), m_lookAhead(true), m_versionCounter(0), m_newestReady(0), m_episodeNewest(0), m_trellisAhead(true), m_trellisAtBatch(false), m_trellisBref(false), m_batchFirst(-1), m_batchLast(-1)
 {
     m_error[0] = 0;
     memset(&m_param, 0, sizeof(m_param));
     memset(m_specStats, 0, sizeof(m_specStats));
     if (const char* e = getenv("X265CU_LOOKAHEAD_CACHE")) m_lookAhead = atoi(e) != 0;
-    if (const char* e = getenv("X265CU_TRELLIS_AHEAD")) m_trellisAhead = atoi(e) != 0;
+    if (const char* e = getenv("X265CU_TRELLIS_AHEAD")) { m_trellisAhead = (atoi(e) & 1) != 0; m_trellisAtBatch = (atoi(e) & 2) != 0; m_trellisBref = (atoi(e) & 4) != 0; }
 }
 Lookahead::~Lookahead() { destroy(); }
 
@@ -801,13 +801,25 @@ void CostEstimateGroup::predictTrellis(const Lookahead::Request& rq, Lowres* ski
             }
             else
                 for (int b = c + 1; b < N; b++) { Lookahead::Request r = { c, b, N }; ep.push_back(r); }
+            /* slicetypeDecide's own frame costs for the mini-GOP it settles on (slicetype.cpp:992-1035) use the B-ref it
+             * inserts at list[bframes / 2]; for an even number of B frames that is not the trellis's middle frame */
+            const int nb = d - 1, bref = c + nb / 2 + 1;
+            if (la.m_trellisBref && la.m_param.bBPyramid && nb > 1 && bref != c + d / 2)
+            {
+                Lookahead::Request m = { c, bref, N };
+                ep.push_back(m);
+                for (int b = c + 1; b < bref; b++) { Lookahead::Request r = { c, b, bref }; ep.push_back(r); }
+                for (int b = bref + 1; b < N; b++) { Lookahead::Request r = { bref, b, N }; ep.push_back(r); }
+            }
         }
     }
     bool valid = true;
     std::vector<EstReq> more;
     predictFrom(ep, 0, 0, skipFenc, skipD0, skipD1, already, more, valid);
     if (!valid) return;
-    const size_t room = already.size() < 192 ? 192 - already.size() : 0;   /* bounds the side buffers of one call */
+    size_t aheadAlready = 0;
+    for (size_t k = 0; k < already.size(); k++) aheadAlready += already[k].ahead ? 1 : 0;
+    const size_t room = aheadAlready < 192 ? 192 - aheadAlready : 0;   /* bounds the side buffers of one call */
     if (more.size() > room) more.resize(room);
     out.swap(more);
 }
@@ -847,6 +859,17 @@ bool CostEstimateGroup::finishBatch()
                 fprintf(stderr, "finishBatch: %d jobs, shift %d (newest %d, then %d), pattern of %d, valid %d, %d ahead\n", m_jobTotal, shift,
                         la.m_newestReady, la.m_historyNewest.back(), (int)la.m_history.back().size(), (int)valid, (int)ahead.size());
         }
+    }
+    if (la.m_lookAhead && la.m_trellisAtBatch && m_jobTotal && la.m_batchLast >= 0)
+    {
+        /* ... and what the history does not cover of the trellis that follows this batch (its segments up to the frame
+         * after the batch's last one: the analysis's last frame) rides along too */
+        const Lookahead::Request rq = { la.m_batchLast, la.m_batchLast + 1, la.m_batchLast + 1 };
+        std::vector<EstReq> more;
+        predictTrellis(rq, NULL, 0, 0, reqs, more);
+        reqs.insert(reqs.end(), more.begin(), more.end());
+        if (getenv("X265CU_LOOKAHEAD_DEBUG") && !more.empty())
+            fprintf(stderr, "finishBatch: %d more ahead by the trellis rule\n", (int)more.size());
     }
     bool ok = reqs.empty() ? true : runEstimates(&reqs[0], (int)reqs.size());
     m_jobTotal = 0;

@@ -151,6 +151,7 @@ public:
     std::vector<std::vector<Request> > m_history;   /* ... and the runs before it (most recent last) */
     std::vector<int> m_historyNewest;          /* how many frames had gone through preLookahead() when each of those runs began */
     int m_newestReady, m_episodeNewest;        /* ... now / when the current run began (a stream's frames arrive in order) */
+    bool m_trellisAtBatch, m_trellisBref;      /* X265CU_TRELLIS_AHEAD bits 1, 2 (experiments, off: measured slower): the rule also at batch time / with slicetypeDecide's B-ref variant */
     bool m_trellisAhead;                       /* X265CU_TRELLIS_AHEAD=0 turns the rule-based part of the cache off (experiments) */
     int m_batchFirst, m_batchLast;             /* frameNum range of the most recent batch (-1: none yet) */
     uint64_t m_versionCounter;
