@@ -865,8 +865,12 @@ bool CostEstimateGroup::finishBatch()
         /* ... and what the history does not cover of the trellis that follows this batch (its segments up to the frame
          * after the batch's last one: the analysis's last frame) rides along too */
         const Lookahead::Request rq = { la.m_batchLast, la.m_batchLast + 1, la.m_batchLast + 1 };
-        std::vector<EstReq> more;
-        predictTrellis(rq, NULL, 0, 0, reqs, more);
+        std::vector<EstReq> all, more;
+        predictTrellis(rq, NULL, 0, 0, reqs, all);
+        /* only what the frame-cost batch that follows cannot contain: estimates that touch the frame after the batch's
+         * last one (the batches stop below it, slicetype.cpp:1235,1263,1276); everything else it is about to compute */
+        for (size_t k = 0; k < all.size(); k++)
+            if (all[k].fenc->frameNum == rq.p1 || all[k].ref1->frameNum == rq.p1) more.push_back(all[k]);
         reqs.insert(reqs.end(), more.begin(), more.end());
         if (getenv("X265CU_LOOKAHEAD_DEBUG") && !more.empty())
             fprintf(stderr, "finishBatch: %d more ahead by the trellis rule\n", (int)more.size());
